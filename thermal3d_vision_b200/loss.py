@@ -1,0 +1,244 @@
+"""Thermal-aware training loss -- host side of the fused sm_100a kernels.
+
+Mirrors /root/reference/utils/loss.py: same function names, positional order,
+keyword names, defaults and return types, so
+``train_thermal_dustr.py`` can import this module as ``utils.loss``.  All
+arithmetic happens in libt3d_sm100.so (``t3d_loss_fwd_bwd``): one fused pass
+produces the loss partial sums AND d/dpred, d/dconf; autograd only hands the
+precomputed gradients back (scaled on the device by ``grad_output``).
+
+Extension over the reference: the batched entry points
+``fused_thermal_loss`` / ``fused_thermal_loss_fwd_bwd`` take ``[B,H,W,3]``
+tensors and reproduce the training loop's "mean over valid samples"
+(train_thermal_dustr.py:182-360) without any host synchronisation.
+"""
+from __future__ import annotations
+
+from typing import NamedTuple, Optional
+
+import torch
+
+from . import _lib
+
+OUT_STRIDE = 8  # T3D_LOSS_OUT_STRIDE
+
+
+class FusedLossResult(NamedTuple):
+    loss: torch.Tensor          # 0-d: mean over valid samples (or the sample's loss when B == 1)
+    per_sample: torch.Tensor    # [B, 8] total, basic, edge, smooth, detail, valid, -, -
+    batch: torch.Tensor         # [8]   mean total, mean components, n_valid, B, -
+
+
+def _prep(t: Optional[torch.Tensor], device) -> Optional[torch.Tensor]:
+    if t is None:
+        return None
+    if t.dtype != torch.float32:
+        t = t.float()
+    if t.device != device:
+        t = t.to(device)
+    return t.contiguous()
+
+
+def _launch(bwd, p1, p2, g1, g2, c1, c2, t1, t2, need_dconf, alpha, ew, sw, dw, multi, grad_scale,
+            rescale_invalid, out=None):
+    """Raw call into the C ABI on already-prepared [B,H,W,3] CUDA tensors."""
+    lib = _lib.lib()
+    B, H, W, _ = p1.shape
+    dev = p1.device
+    tch = 0 if t1 is None or t2 is None else int(t1.shape[1])
+    ws_bytes = lib.t3d_loss_workspace_bytes(B, H, W, int(multi))
+    if out is None:
+        out = {}
+    ws = out.get("workspace")
+    if ws is None or ws.numel() < ws_bytes:
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    per_sample = out.get("per_sample")
+    if per_sample is None:
+        per_sample = torch.empty(B, OUT_STRIDE, dtype=torch.float32, device=dev)
+    batch = out.get("batch")
+    if batch is None:
+        batch = torch.empty(OUT_STRIDE, dtype=torch.float32, device=dev)
+    f64 = out.get("per_sample_f64")
+    stream = _lib.current_stream_ptr()
+    dp1 = dp2 = dc1 = dc2 = None
+    if bwd:
+        dp1 = out.get("dpred1"); dp2 = out.get("dpred2")
+        if dp1 is None:
+            dp1 = torch.empty_like(p1)
+        if dp2 is None:
+            dp2 = torch.empty_like(p2)
+        if need_dconf[0]:
+            dc1 = out.get("dconf1")
+            if dc1 is None:
+                dc1 = torch.empty(B, H, W, dtype=torch.float32, device=dev)
+        if need_dconf[1]:
+            dc2 = out.get("dconf2")
+            if dc2 is None:
+                dc2 = torch.empty(B, H, W, dtype=torch.float32, device=dev)
+        rc = lib.t3d_loss_fwd_bwd(
+            _lib.ptr(p1), _lib.ptr(p2), _lib.ptr(g1), _lib.ptr(g2), _lib.ptr(c1), _lib.ptr(c2),
+            _lib.ptr(t1), _lib.ptr(t2), tch, _lib.ptr(dp1), _lib.ptr(dp2), _lib.ptr(dc1), _lib.ptr(dc2),
+            B, H, W, int(multi), alpha, ew, sw, dw, grad_scale,
+            _lib.ptr(per_sample), _lib.ptr(batch), _lib.ptr(f64), _lib.ptr(ws), ws.numel(), stream)
+        _lib.check(rc, "t3d_loss_fwd_bwd")
+        if rescale_invalid:
+            rc = lib.t3d_loss_rescale_invalid(_lib.ptr(dp1), _lib.ptr(dp2), _lib.ptr(dc1), _lib.ptr(dc2),
+                                              _lib.ptr(per_sample), _lib.ptr(batch), B, H, W, stream)
+            _lib.check(rc, "t3d_loss_rescale_invalid")
+    else:
+        rc = lib.t3d_loss_fwd(
+            _lib.ptr(p1), _lib.ptr(p2), _lib.ptr(g1), _lib.ptr(g2), _lib.ptr(c1), _lib.ptr(c2),
+            _lib.ptr(t1), _lib.ptr(t2), tch, B, H, W, int(multi), alpha, ew, sw, dw,
+            _lib.ptr(per_sample), _lib.ptr(batch), _lib.ptr(f64), _lib.ptr(ws), ws.numel(), stream)
+        _lib.check(rc, "t3d_loss_fwd")
+    return per_sample, batch, dp1, dp2, dc1, dc2
+
+
+class _FusedLoss(torch.autograd.Function):
+    """forward = fused fwd+bwd kernel; backward = device-side scale by grad_output."""
+
+    @staticmethod
+    def forward(ctx, p1, p2, c1, c2, g1, g2, t1, t2, cfg):
+        alpha, ew, sw, dw, multi, batch_mean = cfg
+        need = ctx.needs_input_grad
+        bwd = bool(need[0] or need[1] or need[2] or need[3])
+        need_dconf = (bool(need[2]) and c1 is not None, bool(need[3]) and c2 is not None)
+        B = p1.shape[0]
+        per_sample, batch, dp1, dp2, dc1, dc2 = _launch(
+            bwd, p1, p2, g1, g2, c1, c2, t1, t2, need_dconf, alpha, ew, sw, dw, multi,
+            (1.0 / B) if batch_mean else 1.0, rescale_invalid=batch_mean)
+        ctx.shape = tuple(p1.shape)
+        ctx.grads = (dp1, dp2, dc1, dc2) if bwd else None
+        ctx.mark_non_differentiable(per_sample, batch)
+        # B == 1 per-sample call: the loss itself (no validity filter, as utils/loss.py:295)
+        loss = batch[0] if batch_mean else per_sample[0, 0]
+        return loss.clone(), per_sample, batch
+
+    @staticmethod
+    def backward(ctx, g_loss, _g_ps, _g_b):
+        if ctx.grads is None:
+            return (None,) * 9
+        dp1, dp2, dc1, dc2 = ctx.grads
+        ctx.grads = None    # the gradients are scaled in place: single use
+        B, H, W, _ = ctx.shape
+        go = g_loss.detach().to(dtype=torch.float32, device=dp1.device).reshape(1).contiguous()
+        rc = _lib.lib().t3d_scale_grads(_lib.ptr(dp1), _lib.ptr(dp2), _lib.ptr(dc1), _lib.ptr(dc2),
+                                       _lib.ptr(go), B, H, W, _lib.current_stream_ptr())
+        _lib.check(rc, "t3d_scale_grads")
+        need = ctx.needs_input_grad
+        return (dp1 if need[0] else None, dp2 if need[1] else None,
+                dc1 if need[2] else None, dc2 if need[3] else None, None, None, None, None, None)
+
+
+def _device_of(*ts):
+    for t in ts:
+        if t is not None and t.is_cuda:
+            return t.device
+    if not torch.cuda.is_available():
+        raise _lib.T3DError("no CUDA device: thermal3d_vision_b200 has no CPU path")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def fused_thermal_loss(pred_pts1, pred_pts2, gt_pts1, gt_pts2, confidences1=None, confidences2=None,
+                       thermal_img1=None, thermal_img2=None, *, alpha=0.2, edge_weight=0.5,
+                       smoothness_weight=0.3, detail_weight=0.3, multi_scale=True,
+                       batch_mean=True) -> FusedLossResult:
+    """Batched fused loss: tensors are [B,H,W,3] / [B,H,W] / [B,C,H,W].
+
+    ``loss`` = mean over VALID samples (finite and > 0) of the per-sample
+    enhanced_thermal_aware_loss; gradients w.r.t. pred and confidences flow
+    through autograd.  No host synchronisation.
+    """
+    dev = _device_of(pred_pts1, pred_pts2, gt_pts1, gt_pts2)
+    p1, p2, g1, g2 = (_prep(t, dev) for t in (pred_pts1, pred_pts2, gt_pts1, gt_pts2))
+    c1, c2, t1, t2 = (_prep(t, dev) for t in (confidences1, confidences2, thermal_img1, thermal_img2))
+    if p1.dim() != 4 or p1.shape[-1] != 3:
+        raise ValueError(f"pointmaps must be [B,H,W,3], got {tuple(p1.shape)}")
+    for name, t in (("pred_pts2", p2), ("gt_pts1", g1), ("gt_pts2", g2)):
+        if t.shape != p1.shape:
+            raise ValueError(f"{name} shape {tuple(t.shape)} != pred_pts1 shape {tuple(p1.shape)}")
+    B, H, W, _ = p1.shape
+    for name, t in (("confidences1", c1), ("confidences2", c2)):
+        if t is not None and tuple(t.shape) != (B, H, W):
+            raise ValueError(f"{name} must be [B,H,W]={B, H, W}, got {tuple(t.shape)}")
+    if (t1 is None) != (t2 is None):
+        t1 = t2 = None                                     # utils/loss.py:116: both or nothing
+    if t1 is not None:
+        if t1.dim() != 4 or t1.shape[1] not in (1, 3) or t1.shape != t2.shape or \
+                tuple(t1.shape[2:]) != (H, W) or t1.shape[0] != B:
+            raise ValueError(f"thermal images must be [B,1|3,H,W], got {tuple(t1.shape)} / {tuple(t2.shape)}")
+        if multi_scale and (H < 4 or W < 4):
+            raise ValueError("multi_scale needs H, W >= 4 (the reference breaks on squeezed dims; SURVEY.md D.7)")
+    cfg = (float(alpha), float(edge_weight), float(smoothness_weight), float(detail_weight),
+           bool(multi_scale), bool(batch_mean))
+    loss, per_sample, batch = _FusedLoss.apply(p1, p2, c1, c2, g1, g2, t1, t2, cfg)
+    return FusedLossResult(loss, per_sample, batch)
+
+
+def fused_thermal_loss_fwd_bwd(pred_pts1, pred_pts2, gt_pts1, gt_pts2, confidences1=None, confidences2=None,
+                               thermal_img1=None, thermal_img2=None, *, alpha=0.2, edge_weight=0.5,
+                               smoothness_weight=0.3, detail_weight=0.3, multi_scale=True,
+                               conf_grad=True, out=None):
+    """Functional (no autograd) fused step on prepared contiguous fp32 CUDA tensors.
+
+    Returns dict(per_sample, batch, dpred1, dpred2, dconf1, dconf2); gradients are those of the
+    mean over valid samples.  ``out`` may hold preallocated buffers of the same names (+ 'workspace').
+    """
+    _lib.require_cuda(pred_pts1, pred_pts2, gt_pts1, gt_pts2, confidences1, confidences2, thermal_img1, thermal_img2)
+    B = pred_pts1.shape[0]
+    need_dconf = (conf_grad and confidences1 is not None, conf_grad and confidences2 is not None)
+    ps, bt, dp1, dp2, dc1, dc2 = _launch(
+        True, pred_pts1, pred_pts2, gt_pts1, gt_pts2, confidences1, confidences2, thermal_img1, thermal_img2,
+        need_dconf, float(alpha), float(edge_weight), float(smoothness_weight), float(detail_weight),
+        bool(multi_scale), 1.0 / B, rescale_invalid=True, out=out)
+    return {"per_sample": ps, "batch": bt, "dpred1": dp1, "dpred2": dp2, "dconf1": dc1, "dconf2": dc2}
+
+
+# ----------------------------------------------------------------------------- reference signatures
+def _unbatched(pred_pts1, pred_pts2, gt_pts1, gt_pts2, c1, c2, t1, t2, alpha, ew, sw, dw, multi):
+    src_device = pred_pts1.device
+    if pred_pts1.dim() != 3 or pred_pts1.shape[-1] != 3:
+        raise ValueError(f"expected [H,W,3] pointmaps, got {tuple(pred_pts1.shape)}")
+    if t1 is not None and t2 is not None:
+        if not (isinstance(t1, torch.Tensor) and t1.dim() == 3):
+            # the reference leaves thermal_gray1 unbound here (utils/loss.py:118-140, NameError)
+            raise ValueError("thermal images must be 3-D [C,H,W] tensors")
+        if t1.shape[0] not in (1, 3):
+            t1, t2 = t1[:1], t2[:1]                         # utils/loss.py:123: channel 0
+        t1, t2 = t1.unsqueeze(0), t2.unsqueeze(0)
+    else:
+        t1 = t2 = None
+    ub = lambda t: None if t is None else t.unsqueeze(0)
+    res = fused_thermal_loss(ub(pred_pts1), ub(pred_pts2), ub(gt_pts1), ub(gt_pts2), ub(c1), ub(c2), t1, t2,
+                             alpha=alpha, edge_weight=ew, smoothness_weight=sw, detail_weight=dw,
+                             multi_scale=multi, batch_mean=False)
+    loss = res.loss if res.loss.device == src_device else res.loss.to(src_device)
+    return loss, res.per_sample
+
+
+def confidence_weighted_regression_loss(pred_pts1, pred_pts2, gt_pts1, gt_pts2,
+                                        confidences1=None, confidences2=None, alpha=0.2):
+    """Drop-in for utils/loss.py:75-98."""
+    loss, _ = _unbatched(pred_pts1, pred_pts2, gt_pts1, gt_pts2, confidences1, confidences2,
+                         None, None, alpha, 0.0, 0.0, 0.0, False)
+    return loss
+
+
+def enhanced_thermal_aware_loss(pred_pts1, pred_pts2, gt_pts1, gt_pts2,
+                                confidences1=None, confidences2=None,
+                                thermal_img1=None, thermal_img2=None,
+                                alpha=0.2, edge_weight=0.5, smoothness_weight=0.3,
+                                detail_weight=0.3, multi_scale=True):
+    """Drop-in for utils/loss.py:100-305: returns (total_loss, dict of python floats)."""
+    loss, per_sample = _unbatched(pred_pts1, pred_pts2, gt_pts1, gt_pts2, confidences1, confidences2,
+                                  thermal_img1, thermal_img2, alpha, edge_weight, smoothness_weight,
+                                  detail_weight, multi_scale)
+    vals = per_sample[0, :5].tolist()                       # one 20-byte D2H (the reference does 4 .item())
+    thermal_on = thermal_img1 is not None and thermal_img2 is not None
+    comps = {
+        "basic_loss": vals[1],
+        "edge_loss": vals[2] if thermal_on else 0,
+        "smoothness_loss": vals[3] if thermal_on else 0,
+        "detail_loss": vals[4] if thermal_on else 0,
+    }
+    return loss, comps
