@@ -124,6 +124,91 @@ int t3d_loss_rescale_invalid(float* dpred1, float* dpred2, float* dconf1, float*
 int t3d_scale_grads(float* dpred1, float* dpred2, float* dconf1, float* dconf2,
                     const float* grad_output, int B, int H, int W, void* stream);
 
+/* ----------------------------------------------------------- preprocessing */
+/* cv2.resize(src, (dst_w, dst_h)) INTER_LINEAR, OpenCV C++ path (IPP off), bit-exact
+ * (SURVEY.md Appendix B).  mode 0: uint16 -> uint16, round-half-even + saturate
+ * (train path, data/dataset_loader.py:242); mode 1: uint16 -> (/65535.0f) ->
+ * float32 (inference path, thermal_dustr_inference.py:42-52 and
+ * utils/evaluate_depth_metrics.py:179-189); mode 2: float32 -> float32.
+ * src [B,src_h,src_w], dst [B,dst_h,dst_w]. */
+int t3d_resize_bilinear(const void* src, void* dst, int mode, int B, int src_h, int src_w,
+                        int dst_h, int dst_w, void* stream);
+
+/* cv2.resize(..., interpolation=INTER_NEAREST) of float32 maps
+ * (utils/evaluate_depth_metrics.py:320-323). */
+int t3d_resize_nearest_f32(const float* src, float* dst, int B, int src_h, int src_w,
+                           int dst_h, int dst_w, void* stream);
+
+size_t t3d_preprocess_workspace_bytes(int B, int dst_h, int dst_w);
+
+/* Train path, batched: raw uint16 frames [B,src_h,src_w] -> cv2.resize (uint16)
+ * -> float raw counts -> enhance_thermal_contrast (data/dataset_loader.py:237-249
+ * + :110,118 + utils/preprocessing.py:6-30): exact 65 536-bin histogram
+ * (shared-memory privatised), p2/p98 as np.percentile returns them (float64),
+ * clip((x - p2) / (p98 - p2), 0, 1) in float64, one rounding to float32,
+ * replicated into out_channels (1 or 3) identical planes.
+ * out [B,out_channels,dst_h,dst_w] float32; hist [B,65536] uint32 (== np.bincount
+ * of the resized frame); percentiles [B,2] float64. */
+int t3d_preprocess_train_u16(const uint16_t* raw, int B, int src_h, int src_w, int dst_h, int dst_w,
+                             float* out, int out_channels, unsigned int* hist, double* percentiles,
+                             void* workspace, size_t workspace_bytes, void* stream);
+
+/* enhance_thermal_contrast on float data (utils/preprocessing.py:6-30): x is
+ * [B,channels,n].  channels == 3: if np.allclose(c0,c1) and np.allclose(c0,c2)
+ * the plane is c0, else the fp32 gray 0.299 c0 + 0.587 c1 + 0.114 c2 (:13-19;
+ * close_flags[B] int32 receives the decision); any other channel count: the
+ * whole array is one plane of channels*n values.  Percentiles by exact radix
+ * select on the float keys; out [B,out_channels,plane] float32;
+ * percentiles [B,2] float64. */
+int t3d_contrast_normalize_f32(const float* x, int B, int channels, int n, float* out, int out_channels,
+                               double* percentiles, int* close_flags, void* stream);
+
+/* close_flags[b] = np.allclose(c0, c1) and np.allclose(c0, c2) for x [B,3,n]
+ * (rtol 1e-5, atol 1e-8, float32; utils/preprocessing.py:15,40). */
+int t3d_channels_close(const float* x, int B, int n, int* close_flags, void* stream);
+
+/* enhance_thermal_fixed_range arithmetic (utils/preprocessing.py:47-62), float32
+ * throughout: (optional x*65535) -> clip [21800, 25000] -> (x - 21800) / 3200 over
+ * n elements.  close_flag (nullable, device int): when *close_flag != 0 every
+ * output plane of `plane` elements is computed from the first plane (the
+ * reference collapses np.allclose channels to channel 0 and re-replicates, :39-41,67-71). */
+int t3d_fixed_range_normalize(const float* x, float* y, size_t n, size_t plane, const int* close_flag,
+                              int normalized, void* stream);
+
+/* ------------------------------------------------- pointmap -> depth, metrics */
+size_t t3d_depth_metrics_workspace_bytes(int B, int H, int W);
+
+/* compute_depth_metrics (utils/metrics.py:4-69; the 3-metric variant of
+ * utils/evaluate_depth_metrics.py:20-80 is a subset), batched over B images.
+ * pred element (b,i) is read at pred[(b*H*W + i)*pred_stride + pred_offset]:
+ * stride 3 / offset 2 evaluates the Z channel of an AoS pointmap in place
+ * (pointmap -> depth, utils/metrics.py:121); stride 1 / offset 0 is a depth map.
+ * gt [B,gt_h,gt_w] is nearest-resampled to (H,W) when the sizes differ
+ * (utils/evaluate_depth_metrics.py:320-323).  mask (nullable) [B,H,W] uint8;
+ * NULL -> gt > 0 & finite (:27).
+ * out [B][8] float32: abs_rel, sq_rel, rmse, rmse_log, acc_1, acc_2, acc_3,
+ * n_valid (n_valid == 0 -> NaN,NaN,NaN,NaN,0,0,0 as :34-43); out_f64 (nullable)
+ * the same in double (acc_k are float64 in numpy); out_medians (nullable)
+ * [B][2] = median(gt), median(pred). */
+int t3d_depth_metrics(const float* pred, int pred_stride, int pred_offset,
+                      const float* gt, int gt_h, int gt_w, const unsigned char* mask,
+                      int B, int H, int W, int median_scaling,
+                      float* out, double* out_f64, float* out_medians,
+                      void* workspace, size_t workspace_bytes, void* stream);
+
+/* depth = pointmap[..., 2] materialised (thermal_dustr_inference.py:133-134). */
+int t3d_pointmap_to_depth(const float* pointmap, float* depth, size_t n_pixels, void* stream);
+
+/* estimate_camera_intrinsics, estimation branch (scripts/pseudo_gt.py:151-184):
+ * fx = median((u - W/2) / (X/Z)), fy = median((v - H/2) / (Y/Z)) over Z > 0.
+ * depth (nullable) [B,H,W] supplies Z, else the pointmap's Z.  out_K [B][9] float64. */
+int t3d_estimate_focal(const float* pointmap, const float* depth, int B, int H, int W,
+                       double* out_K, void* stream);
+
+/* EXTENSION (the reference never applies K): u = fx X/Z + cx, v = fy Y/Z + cy; uv [n][2]. */
+int t3d_project_points(const float* pointmap, float fx, float fy, float cx, float cy,
+                       float* uv, size_t n_pixels, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -67,10 +67,14 @@ def _huber_torch(d):
     return torch.where(d < HUBER_DELTA, 0.5 * d.pow(2), HUBER_DELTA * (d - 0.5 * HUBER_DELTA))
 
 
-def enhanced_thermal_aware_loss_torch(p1, p2, g1, g2, c1=None, c2=None, t1=None, t2=None,
+def enhanced_thermal_aware_loss_torch(pred_pts1, pred_pts2, gt_pts1, gt_pts2,
+                                      confidences1=None, confidences2=None,
+                                      thermal_img1=None, thermal_img2=None,
                                       alpha=0.2, edge_weight=0.5, smoothness_weight=0.3,
                                       detail_weight=0.3, multi_scale=True):
     """utils/loss.py:100-305.  Returns (total, dict of python floats)."""
+    p1, p2, g1, g2, c1, c2, t1, t2 = (pred_pts1, pred_pts2, gt_pts1, gt_pts2, confidences1,
+                                      confidences2, thermal_img1, thermal_img2)
     basic = confidence_weighted_regression_loss_torch(p1, p2, g1, g2, c1, c2, alpha)
     edge = smooth = detail = 0
     if t1 is not None and t2 is not None:

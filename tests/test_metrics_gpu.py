@@ -1,0 +1,131 @@
+"""GPU parity: pointmap->depth + depth metrics through the C ABI vs oracle / golden vectors.
+Bar: rtol 1e-5 on the float metrics; the delta-accuracies are exact counts / n."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import ref_depth, ref_metrics
+
+pytestmark = pytest.mark.gpu
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+K7 = ref_metrics.KEYS7
+
+
+@pytest.fixture(scope="module")
+def kat():
+    return np.load(os.path.join(G, "metrics_kat.npz"))
+
+
+def _vec(m):
+    return np.array([m[k] for k in K7], np.float64)
+
+
+def _close(got, ref):
+    np.testing.assert_allclose(got[:4], ref[:4], rtol=1e-5)
+    np.testing.assert_array_equal(got[4:7], ref[4:7])
+
+
+@pytest.mark.parametrize("split", ["day", "night"])
+def test_reference_golden_real_depth_maps(cuda_device, kat, split):
+    from thermal3d_vision_b200 import metrics as tm
+    gt, pred = kat[f"{split}_gt"], kat[f"{split}_pred"]
+    for ms in (True, False):
+        m = tm.compute_depth_metrics(torch.from_numpy(pred).to(cuda_device), gt, median_scaling=ms)
+        assert [type(m[k]).__name__ for k in K7] == ["float32"] * 4 + ["float64"] * 3
+        _close(_vec(m), kat[f"{split}_crop_ms{int(ms)}"])
+        e = tm.compute_depth_metrics_eval(pred, gt, median_scaling=ms)
+        ref = kat[f"{split}_crop_eval_ms{int(ms)}"]
+        assert e["rmse"] == pytest.approx(ref[0], rel=1e-5) and e["acc_1.25"] == ref[1] and e["acc_1.25^2"] == ref[2]
+    m = tm.compute_depth_metrics(pred, gt, mask=kat[f"{split}_mask"])
+    _close(_vec(m), kat[f"{split}_crop_masked"])
+    # GT at another resolution: fused nearest resample (utils/evaluate_depth_metrics.py:320-323)
+    r = tm.compute_depth_metrics_batch(torch.from_numpy(pred)[None], torch.from_numpy(kat[f"{split}_gt_big"])[None])
+    _close(r["metrics_f64"][0, :7].cpu().numpy(), kat[f"{split}_crop_resampled"])
+
+
+def test_empty_mask_and_key_quirk(cuda_device, kat):
+    from thermal3d_vision_b200 import metrics as tm
+    m = tm.compute_depth_metrics(kat["day_pred"], np.zeros_like(kat["day_gt"]))
+    assert set(m) == {"abs_rel", "sq_rel", "rmse", "rmse_log", "a1", "a2", "a3"}
+    assert np.isnan(m["abs_rel"]) and m["a1"] == 0.0
+    e = tm.compute_depth_metrics_eval(kat["day_pred"], np.zeros_like(kat["day_gt"]))
+    assert np.isnan(e["rmse"]) and e["acc_1.25"] == 0.0
+
+
+@pytest.mark.parametrize("H,W", [(224, 224), (384, 512), (37, 53), (1, 9)])
+def test_pointmap_z_in_place_batched(cuda_device, H, W):
+    """pointmap -> depth fused into the metric pass (utils/metrics.py:121), odd sizes, B > 1."""
+    from thermal3d_vision_b200 import metrics as tm
+    rng = np.random.default_rng(H * W)
+    B = 3
+    gt = (1.5 + 3 * np.abs(rng.normal(size=(B, H, W)))).astype(np.float32)
+    pm = rng.normal(size=(B, H, W, 3)).astype(np.float32)
+    pm[..., 2] = gt * (1 + 0.3 * rng.normal(size=gt.shape)).astype(np.float32)
+    pm[..., 2] = np.abs(pm[..., 2]) + 0.05
+    gt[1, : max(1, H // 4)] = 0
+    gt[2].flat[0] = np.nan
+    d = torch.from_numpy(pm).to(cuda_device)
+    r = tm.compute_depth_metrics_batch(d, torch.from_numpy(gt))
+    got = r["metrics_f64"].cpu().numpy()
+    for b in range(B):
+        ref = ref_metrics.compute_depth_metrics(ref_depth.pointmap_to_depth(pm[b]), gt[b])
+        _close(got[b, :7], _vec(ref))
+        exact = ref_metrics.compute_depth_metrics(pm[b, ..., 2], gt[b], dtype=np.float64)
+        np.testing.assert_allclose(got[b, :4], _vec(exact)[:4], rtol=2e-5)
+    # a strided pointmap[..., 2] view goes through the same in-place path
+    m = tm.compute_depth_metrics(d[0][..., 2], gt[0])
+    _close(_vec(m), _vec(ref_metrics.compute_depth_metrics(pm[0, ..., 2], gt[0])))
+    # medians are exact order statistics
+    med = r["medians"].cpu().numpy()
+    for b in range(B):
+        mk = (gt[b] > 0) & np.isfinite(gt[b])
+        assert med[b, 0] == np.median(gt[b][mk]) and med[b, 1] == np.median(pm[b, ..., 2][mk])
+
+
+def test_nan_and_degenerate_predictions(cuda_device):
+    from thermal3d_vision_b200 import metrics as tm
+    rng = np.random.default_rng(3)
+    gt = (1 + rng.random((16, 20))).astype(np.float32)
+    pred = gt.copy(); pred[3, 4] = np.nan
+    ref = ref_metrics.compute_depth_metrics(pred, gt)
+    got = tm.compute_depth_metrics(pred, gt)
+    for k in K7:
+        assert (np.isnan(ref[k]) and np.isnan(got[k])) or ref[k] == pytest.approx(got[k], rel=1e-5), k
+    pred = np.zeros_like(gt)                     # median 0 -> scale inf
+    ref = ref_metrics.compute_depth_metrics(pred, gt)
+    got = tm.compute_depth_metrics(pred, gt)
+    for k in K7:
+        assert (np.isnan(ref[k]) and np.isnan(got[k])) or ref[k] == got[k] or ref[k] == pytest.approx(got[k], rel=1e-5), k
+
+
+def test_depth_and_intrinsics_helpers(cuda_device, kat):
+    from thermal3d_vision_b200 import depth as td
+    pm = kat["focal_pointmap"]
+    z = td.pointmap_to_depth(pm)
+    assert isinstance(z, np.ndarray) and (z == pm[..., 2]).all()
+    zt = td.pointmap_to_depth(torch.from_numpy(pm).to(cuda_device))
+    assert zt.is_cuda and (zt.cpu().numpy() == pm[..., 2]).all()
+    K = td.estimate_camera_intrinsics(pm, pm[..., 2])
+    np.testing.assert_array_equal(K, kat["focal_K"])
+    uv = td.project_points(pm, kat["calib_json_K"]).cpu().numpy()
+    u, v = ref_depth.project_points(pm, kat["calib_json_K"])
+    np.testing.assert_array_equal(uv[..., 0], u); np.testing.assert_array_equal(uv[..., 1], v)
+    with pytest.raises(ValueError):
+        td.load_thermal_calibration("calib.txt")
+
+
+def test_accumulator_matches_reference_semantics(cuda_device, kat):
+    from thermal3d_vision_b200 import metrics as tm
+    preds = np.stack([kat["day_pred"], kat["night_pred"], kat["day_pred"]])
+    gts = np.stack([kat["day_gt"], kat["night_gt"], np.zeros_like(kat["day_gt"])])   # last image: empty mask
+    r = tm.compute_depth_metrics_batch(preds, gts)
+    acc = tm.MetricAccumulator(cuda_device)
+    acc.update(r["metrics_f64"])
+    got = acc.result()
+    per = [ref_metrics.compute_depth_metrics(preds[i], gts[i]) for i in range(2)]
+    per.append({k: np.nan for k in K7})      # what a KeyError-free reference would accumulate (Appendix D.11/12)
+    ref = ref_metrics.accumulate_dataset(per)
+    for k in K7[:4]:
+        assert got[k] == pytest.approx(ref[k], rel=1e-5)

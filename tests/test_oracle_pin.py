@@ -1,0 +1,66 @@
+"""CPU, build container only: the oracle restatements equal the LIVE, unmodified reference on fresh
+random inputs.  Skipped where /root/reference is not mounted (the GPU box): there the golden
+fixtures (test_oracle_golden.py) carry the pin."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import ref_loss, ref_metrics, ref_preprocess, ref_sobel, reference_bridge
+
+pytestmark = pytest.mark.skipif(not reference_bridge.available(), reason="reference tree not mounted")
+
+
+@pytest.fixture(scope="module")
+def ref():
+    return reference_bridge.load()
+
+
+@pytest.mark.parametrize("H,W,multi", [(33, 47, True), (64, 64, False), (224, 224, True)])
+def test_loss_equals_live_reference(ref, H, W, multi):
+    kw = dict(alpha=0.2, edge_weight=0.5, smoothness_weight=0.3, detail_weight=0.4, multi_scale=multi)
+    ins = ref_loss.make_kat_inputs(H, W, seed=H + W)
+
+    def run(fn):
+        a = [x.clone() for x in ins]
+        a[4] = a[4] * 3 - 1
+        for k in (0, 1, 4, 5):
+            a[k].requires_grad_()
+        loss, comp = fn(*a, **kw)
+        loss.backward()
+        return loss.item(), comp, [a[k].grad for k in (0, 1, 4, 5)]
+
+    r, o = run(ref.loss.enhanced_thermal_aware_loss), run(ref_loss.enhanced_thermal_aware_loss_torch)
+    # same fp32 op sequence per term; only the order in which the per-view terms are added differs
+    assert r[0] == pytest.approx(o[0], rel=2e-6)
+    for k in r[1]:
+        assert r[1][k] == pytest.approx(o[1][k], rel=2e-6)
+    for x, y in zip(r[2], o[2]):
+        assert (x - y).abs().max().item() <= 2e-9
+
+
+def test_preprocess_equals_live_reference(ref):
+    raw = ref_preprocess.make_raw_frames(2, seed=11)
+    for frame in raw:
+        for (w, h) in ((224, 224), (512, 384), (301, 199)):
+            assert (ref.cv2.resize(frame, (w, h)) == ref_preprocess.resize_bilinear(frame, (h, w))).all()
+            x = frame.astype(np.float32) / 65535.0
+            assert (ref.cv2.resize(x, (w, h)) == ref_preprocess.resize_bilinear(x, (h, w))).all()
+            t = torch.from_numpy(np.repeat(ref.cv2.resize(frame, (w, h)).astype(np.float32)[None], 3, 0))
+            assert (ref.preprocessing.enhance_thermal_contrast(t).numpy() == ref_preprocess.train_path(frame, (h, w))[0]).all()
+
+
+def test_metrics_equal_live_reference(ref):
+    rng = np.random.default_rng(0)
+    gt = (1.5 + 3 * np.abs(rng.normal(size=(96, 128)))).astype(np.float32)
+    pred = (gt * (1 + 0.2 * rng.normal(size=gt.shape))).astype(np.float32)
+    gt[:5] = 0
+    for ms in (True, False):
+        a = ref.metrics.compute_depth_metrics(pred.copy(), gt.copy(), median_scaling=ms)
+        b = ref_metrics.compute_depth_metrics(pred, gt, median_scaling=ms)
+        assert all(a[k] == b[k] for k in a)
+
+
+def test_sobel_equals_live_reference(ref):
+    m = ref.model.ThermalDUSt3R(torch.nn.Identity())
+    x = torch.rand(1, 1, 31, 45)
+    assert torch.equal(m.preprocess_thermal(x), ref_sobel.preprocess_thermal_torch(x, m.edge_weight, m.temp_scale))

@@ -1,0 +1,149 @@
+"""GPU parity: thermal preprocessing through the C ABI vs the oracle / golden vectors.
+Bar: BIT-EXACT outputs, percentiles and histograms (BASELINE.json north_star)."""
+import hashlib
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import ref_preprocess
+
+pytestmark = pytest.mark.gpu
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+sha = lambda a: hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()[:16]
+
+
+@pytest.fixture(scope="module")
+def kat():
+    return np.load(os.path.join(G, "preprocess_kat.npz"))
+
+
+def _frames():
+    raw = np.random.default_rng(0).normal(22800, 400, (512, 640)).clip(0, 65535).astype(np.uint16)
+    mix = ref_preprocess.make_raw_frames(3, seed=7)
+    return [("day0", raw), ("mix0", mix[0]), ("mix1", mix[1]), ("mix2", mix[2])]
+
+
+@pytest.mark.parametrize("w,h", [(224, 224), (512, 384), (333, 217)])
+def test_train_path_bit_exact_vs_reference_golden(cuda_device, kat, w, h):
+    """data/dataset_loader.py:237-249 + enhance_thermal_contrast, batched over 4 frames."""
+    from thermal3d_vision_b200 import preprocessing as pp
+    frames = _frames()
+    raw = torch.from_numpy(np.stack([f for _, f in frames])).to(cuda_device)
+    tb = pp.preprocess_thermal_batch(raw, (w, h), path="train")
+    r16 = pp.resize_bilinear(raw, (h, w), mode="u16")
+    out = tb.thermal.cpu().numpy()
+    hist = tb.histogram.cpu().numpy().view(np.uint32)
+    pct = tb.percentiles.cpu().numpy()
+    for i, (name, frame) in enumerate(frames):
+        tag = f"{name}_{w}x{h}"
+        assert [sha(r16[i].cpu().numpy()), sha(out[i])] == list(kat[tag + "_train"]), tag
+        assert tuple(pct[i]) == tuple(kat[tag + "_train_p"]), tag
+        assert sha(hist[i]) == str(kat[tag + "_hist_sha"]), tag
+        assert float(out[i].astype(np.float64).sum()) == float(kat[tag + "_train_sum"])
+        # and against the oracle arrays directly
+        o, p2, p98, r = ref_preprocess.train_path(frame, (h, w))
+        assert (out[i] == o).all() and (hist[i] == ref_preprocess.histogram_u16(r)).all()
+        assert (out[i][0] == out[i][1]).all() and (out[i][0] == out[i][2]).all()
+
+
+@pytest.mark.parametrize("w,h", [(224, 224), (512, 384), (333, 217)])
+def test_inference_path_bit_exact(cuda_device, kat, w, h):
+    """thermal_dustr_inference.py:25-60: /65535 -> float resize -> enhance (radix-select percentiles)."""
+    from thermal3d_vision_b200 import preprocessing as pp
+    frames = _frames()
+    raw = torch.from_numpy(np.stack([f for _, f in frames])).to(cuda_device)
+    tb = pp.preprocess_thermal_batch(raw, (w, h), path="inference")
+    rf = pp.resize_bilinear(raw, (h, w), mode="u16_to_unit_f32")
+    out = tb.thermal.cpu().numpy()
+    pct = tb.percentiles.cpu().numpy()
+    for i, (name, _) in enumerate(frames):
+        tag = f"{name}_{w}x{h}"
+        assert [sha(rf[i].cpu().numpy()), sha(out[i])] == list(kat[tag + "_infer"]), tag
+        assert tuple(pct[i]) == tuple(kat[tag + "_infer_p"]), tag
+
+
+def test_drop_in_functions(cuda_device, kat):
+    from thermal3d_vision_b200 import preprocessing as pp
+    # enhance_thermal_contrast: CUDA in -> CUDA out, CPU in -> CPU out, None -> None
+    t = torch.from_numpy(np.repeat(kat["small_resized_u16"].astype(np.float32)[None], 3, 0))
+    y = pp.enhance_thermal_contrast(t)
+    assert not y.is_cuda and y.shape == (3, 28, 36) and y.dtype == torch.float32
+    assert (y.numpy() == kat["small_train_out"]).all()
+    yc = pp.enhance_thermal_contrast(t.to(cuda_device))
+    assert yc.is_cuda and (yc.cpu().numpy() == kat["small_train_out"]).all()
+    ti = torch.from_numpy(np.repeat(kat["small_resized_f32"][None], 3, 0))
+    assert (pp.enhance_thermal_contrast(ti).numpy() == kat["small_infer_out"]).all()
+    assert pp.enhance_thermal_contrast(None) is None and pp.enhance_thermal_fixed_range(None) is None
+    # gray path (channels not allclose)
+    g = torch.from_numpy(kat["gray_in"])
+    assert (pp.enhance_thermal_contrast(g).numpy() == kat["gray_out"]).all()
+    assert (pp.enhance_thermal_fixed_range(g).numpy() == kat["gray_fixed_out"]).all()
+    # 1-channel and 2-D inputs follow the reference's shape rules
+    one = ti[:1]
+    o1, _, _ = ref_preprocess.enhance_thermal_contrast(one.numpy())
+    y1 = pp.enhance_thermal_contrast(one)
+    assert y1.shape == (1, 28, 36) and (y1.numpy() == o1).all()
+    two = ti[0]
+    o2, _, _ = ref_preprocess.enhance_thermal_contrast(two.numpy())
+    y2 = pp.enhance_thermal_contrast(two)
+    assert y2.shape == (3, 28, 36) and (y2.numpy() == o2).all()
+    # fixed range, both modes and shapes
+    for x, norm in ((ti, True), (t, False), (one, True), (two, True)):
+        ref = ref_preprocess.enhance_thermal_fixed_range(x.numpy(), normalized=norm)
+        got = pp.enhance_thermal_fixed_range(x, normalized=norm)
+        assert got.shape == ref.shape and (got.numpy() == ref).all()
+    # nearest + plain resize helpers
+    assert (pp.resize_nearest(torch.from_numpy(kat["nearest_in"]), (21, 33)).numpy() == kat["nearest_out"]).all()
+    assert (pp.resize_bilinear(torch.from_numpy(kat["small_raw"]), (28, 36)).numpy() == kat["small_resized_u16"]).all()
+
+
+def test_edge_cases(cuda_device):
+    from thermal3d_vision_b200 import preprocessing as pp
+    # constant image: p98 == p2 -> 0/0 = NaN everywhere (utils/preprocessing.py:23)
+    c = torch.full((3, 8, 12), 7.0)
+    y = pp.enhance_thermal_contrast(c)
+    assert torch.isnan(y).all()
+    # NaN in the input -> NaN percentiles -> all NaN
+    n = torch.rand(3, 8, 12); n[:, 2, 3] = float("nan")
+    assert torch.isnan(pp.enhance_thermal_contrast(n)).all()
+    # two-valued image -> +-inf / clip behaviour equals numpy
+    rng = np.random.default_rng(4)
+    for shape in ((3, 5, 7), (3, 1, 9), (3, 31, 2)):
+        x = np.repeat(rng.random(shape[1:]).astype(np.float32)[None], 3, 0)
+        ref, _, _ = ref_preprocess.enhance_thermal_contrast(x)
+        got = pp.enhance_thermal_contrast(torch.from_numpy(x)).numpy()
+        assert (got == ref).all()
+    # saturated / extreme 16-bit frames
+    raw = np.zeros((3, 64, 80), np.uint16)
+    raw[0] = 65535; raw[1, ::2] = 65535; raw[2] = rng.integers(0, 65536, (64, 80))
+    tb = pp.preprocess_thermal_batch(torch.from_numpy(raw), (40, 32), path="train")
+    for i in range(3):
+        o, p2, p98, r = ref_preprocess.train_path(raw[i], (32, 40))
+        got = tb.thermal[i].cpu().numpy()
+        assert np.array_equal(got, o, equal_nan=True)
+        assert (tb.histogram[i].cpu().numpy().view(np.uint32) == ref_preprocess.histogram_u16(r)).all()
+    # no resize (src size == dst size)
+    tb = pp.preprocess_thermal_batch(torch.from_numpy(raw[2:]), (80, 64), path="train")
+    o, _, _, _ = ref_preprocess.train_path(raw[2], (64, 80))
+    assert (tb.thermal[0].cpu().numpy() == o).all()
+
+
+def test_full_size_properties(cuda_device):
+    """BASELINE config 5 shape: 640x512 u16 -> 512x384, a batch of 32 frames; size-independent properties."""
+    from thermal3d_vision_b200 import preprocessing as pp
+    raw = ref_preprocess.make_raw_frames(32, seed=21)
+    d = torch.from_numpy(raw).to(cuda_device)
+    a = pp.preprocess_thermal_batch(d, (512, 384), path="train")
+    b = pp.preprocess_thermal_batch(d, (512, 384), path="train")
+    assert torch.equal(a.thermal, b.thermal) and torch.equal(a.histogram, b.histogram)      # deterministic
+    assert (a.histogram.sum(1) == 384 * 512).all()                                           # checksum of checksums
+    assert a.thermal.min() >= 0 and a.thermal.max() <= 1
+    # idempotence of the normalisation on its own output range: re-normalising keeps order
+    frac = ((a.thermal[:, 0] > 0) & (a.thermal[:, 0] < 1)).float().mean(dim=(1, 2))
+    assert ((frac > 0.94) & (frac <= 0.9601)).all()          # 2nd..98th percentile window
+    for i in (0, 17, 31):
+        o, p2, p98, _ = ref_preprocess.train_path(raw[i], (384, 512))
+        assert (a.thermal[i].cpu().numpy() == o).all()
+        assert tuple(a.percentiles[i].tolist()) == (p2, p98)

@@ -587,21 +587,36 @@ __global__ void __launch_bounds__(128) loss_finalize_kernel(const FinalizeArgs a
         is_last = (done == (unsigned)a.B - 1);
     }
     __syncthreads();
-    if (is_last && tid == 0) {
-        // batch stage, fixed sample order (deterministic): mean over valid samples
+    if (is_last) {
+        // batch stage: mean over valid samples; fixed-shape tree over a fixed sample->thread map (deterministic)
+        __shared__ double bs[128][6];
         __threadfence();
-        double s[5] = {0, 0, 0, 0, 0};
-        int nv = 0;
-        for (int i = 0; i < a.B; ++i) {
-            const volatile float* o = a.out_sample + (size_t)i * T3D_LOSS_OUT_STRIDE;
-            if (o[5] != 0.f) {
-                ++nv;
-                for (int k = 0; k < 5; ++k) s[k] += (double)o[k];
+        double s[6] = {0, 0, 0, 0, 0, 0};
+        for (int i = tid; i < a.B; i += 128) {
+            const float* o = a.out_sample + (size_t)i * T3D_LOSS_OUT_STRIDE;
+            const float4 v0 = __ldcg(reinterpret_cast<const float4*>(o));
+            const float4 v1 = __ldcg(reinterpret_cast<const float4*>(o) + 1);
+            if (v1.y != 0.f) {
+                s[0] += (double)v0.x; s[1] += (double)v0.y; s[2] += (double)v0.z; s[3] += (double)v0.w;
+                s[4] += (double)v1.x; s[5] += 1.0;
             }
         }
-        for (int k = 0; k < 5; ++k) a.out_batch[k] = nv ? (float)(s[k] / nv) : 0.f;
-        a.out_batch[5] = (float)nv; a.out_batch[6] = (float)a.B; a.out_batch[7] = 0.f;
-        *a.counter = 0u;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) bs[tid][k] = s[k];
+        __syncthreads();
+        for (int stride = 64; stride > 0; stride >>= 1) {
+            if (tid < stride) {
+#pragma unroll
+                for (int k = 0; k < 6; ++k) bs[tid][k] += bs[tid + stride][k];
+            }
+            __syncthreads();
+        }
+        if (tid == 0) {
+            const double nv = bs[0][5];
+            for (int k = 0; k < 5; ++k) a.out_batch[k] = (nv > 0) ? (float)(bs[0][k] / nv) : 0.f;
+            a.out_batch[5] = (float)nv; a.out_batch[6] = (float)a.B; a.out_batch[7] = 0.f;
+            *a.counter = 0u;
+        }
     }
 }
 

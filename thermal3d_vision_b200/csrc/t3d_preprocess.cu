@@ -1,0 +1,475 @@
+// t3d_preprocess.cu -- 16-bit radiometric thermal -> normalised, contrast
+// equalised, resized float thermal (sm_100a).
+//
+// Replaces /root/reference/utils/preprocessing.py:6-30 (enhance_thermal_contrast),
+// :32-73 (enhance_thermal_fixed_range) and the cv2.resize calls around them
+// (data/dataset_loader.py:237-249 train path, thermal_dustr_inference.py:25-60
+// inference path, utils/evaluate_depth_metrics.py:320-323 nearest GT resample).
+// Exact recipes: SURVEY.md Appendix B.  Outputs are bit-exact with
+// numpy/OpenCV (IPP off): no FMA contraction in the interpolation, fp64 in
+// the normalisation, integer histograms.
+#include "t3d_common.cuh"
+#include "t3d_select.cuh"
+
+namespace {
+
+// ------------------------------------------------------------------ bilinear taps
+struct Tap { int s0, s1; float c0, c1; };
+
+// cv2 INTER_LINEAR tap for destination index d (resize.cpp, non-IPP path):
+// f = (float)((d + 0.5) * scale - 0.5) rounded to fp32 BEFORE floor.
+__device__ __forceinline__ Tap linear_tap(int d, int src_dim, double scale) {
+    const double fd = __dsub_rn(__dmul_rn(__dadd_rn((double)d, 0.5), scale), 0.5);
+    float f = __double2float_rn(fd);
+    int s = __float2int_rd(f);
+    f = __fsub_rn(f, (float)s);
+    if (s < 0) { s = 0; f = 0.f; }
+    if (s >= src_dim - 1) { s = src_dim - 1; f = 0.f; }
+    Tap t;
+    t.s0 = s; t.s1 = min(s + 1, src_dim - 1);
+    t.c0 = __fsub_rn(1.0f, f); t.c1 = f;
+    return t;
+}
+
+template <typename SrcT, bool DIV65535>
+__device__ __forceinline__ float src_value(const SrcT* __restrict__ p) {
+    const float v = (float)__ldg(p);
+    return DIV65535 ? __fdiv_rn(v, 65535.0f) : v;
+}
+
+template <typename SrcT, bool DIV65535>
+__device__ __forceinline__ float bilinear_at(const SrcT* __restrict__ src, int sw, const Tap& ty, const Tap& tx) {
+    const SrcT* r0 = src + (size_t)ty.s0 * sw;
+    const SrcT* r1 = src + (size_t)ty.s1 * sw;
+    // horizontal pass then vertical pass, every product rounded separately (no FMA)
+    const float h0 = __fadd_rn(__fmul_rn(src_value<SrcT, DIV65535>(r0 + tx.s0), tx.c0),
+                               __fmul_rn(src_value<SrcT, DIV65535>(r0 + tx.s1), tx.c1));
+    const float h1 = __fadd_rn(__fmul_rn(src_value<SrcT, DIV65535>(r1 + tx.s0), tx.c0),
+                               __fmul_rn(src_value<SrcT, DIV65535>(r1 + tx.s1), tx.c1));
+    return __fadd_rn(__fmul_rn(h0, ty.c0), __fmul_rn(h1, ty.c1));
+}
+
+__device__ __forceinline__ uint16_t sat_u16(float v) {
+    const int r = __float2int_rn(v);        // round half to even
+    return (uint16_t)min(max(r, 0), 65535);
+}
+
+// ------------------------------------------------------------------ K1: resize kernels
+// MODE 0: u16 -> u16 (train path, data/dataset_loader.py:242)
+// MODE 1: u16 -> f32 with /65535 first (inference path, thermal_dustr_inference.py:42-52)
+// MODE 2: f32 -> f32
+template <int MODE>
+__global__ void __launch_bounds__(256) resize_bilinear_kernel(const void* __restrict__ src_, void* __restrict__ dst_,
+                                                              int B, int sh, int sw, int dh, int dw) {
+    const double scx = (double)sw / (double)dw, scy = (double)sh / (double)dh;
+    const size_t total = (size_t)B * dh * dw;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (size_t)gridDim.x * blockDim.x) {
+        const int x = (int)(idx % dw);
+        const size_t t = idx / dw;
+        const int y = (int)(t % dh);
+        const int b = (int)(t / dh);
+        const Tap tx = linear_tap(x, sw, scx), ty = linear_tap(y, sh, scy);
+        if (MODE == 0) {
+            const uint16_t* s = reinterpret_cast<const uint16_t*>(src_) + (size_t)b * sh * sw;
+            reinterpret_cast<uint16_t*>(dst_)[idx] = sat_u16(bilinear_at<uint16_t, false>(s, sw, ty, tx));
+        } else if (MODE == 1) {
+            const uint16_t* s = reinterpret_cast<const uint16_t*>(src_) + (size_t)b * sh * sw;
+            reinterpret_cast<float*>(dst_)[idx] = bilinear_at<uint16_t, true>(s, sw, ty, tx);
+        } else {
+            const float* s = reinterpret_cast<const float*>(src_) + (size_t)b * sh * sw;
+            reinterpret_cast<float*>(dst_)[idx] = bilinear_at<float, false>(s, sw, ty, tx);
+        }
+    }
+}
+
+// cv2 INTER_NEAREST: sx = min(floor(dx * src_w / dst_w), src_w - 1) (utils/evaluate_depth_metrics.py:321-323)
+__global__ void __launch_bounds__(256) resize_nearest_kernel(const float* __restrict__ src, float* __restrict__ dst,
+                                                             int B, int sh, int sw, int dh, int dw) {
+    const double fx = (double)sw / (double)dw, fy = (double)sh / (double)dh;
+    const size_t total = (size_t)B * dh * dw;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (size_t)gridDim.x * blockDim.x) {
+        const int x = (int)(idx % dw);
+        const size_t t = idx / dw;
+        const int y = (int)(t % dh);
+        const int b = (int)(t / dh);
+        const int sx = min((int)floor(__dmul_rn((double)x, fx)), sw - 1);
+        const int sy = min((int)floor(__dmul_rn((double)y, fy)), sh - 1);
+        dst[idx] = __ldg(src + ((size_t)b * sh + sy) * sw + sx);
+    }
+}
+
+// ------------------------------------------------------------------ K2a: fused resize + privatised histogram (train path)
+// One CTA owns up to 49 152 output pixels of one frame and a shared-memory
+// histogram of all 65 536 values packed as 2 x u16 per word (128 KB): counts
+// cannot overflow because a CTA sees < 65 536 pixels.  Non-zero bins are merged
+// into the frame's global u32 histogram with atomics (integer adds: exact and
+// order independent -> bit-exact, deterministic).
+constexpr int kHistThreads = 1024;
+constexpr int kHistMaxPx = 49152;
+constexpr int kHistWords = 32768;
+
+template <bool RESIZE>
+__global__ void __launch_bounds__(kHistThreads, 1)
+resize_hist_u16_kernel(const uint16_t* __restrict__ src, uint16_t* __restrict__ resized,
+                       unsigned int* __restrict__ hist, int sh, int sw, int dh, int dw, int chunks) {
+    extern __shared__ unsigned int sh_hist[];   // kHistWords
+    const int b = blockIdx.x / chunks, chunk = blockIdx.x - b * chunks;
+    const int npx = dh * dw;
+    const int per = (npx + chunks - 1) / chunks;
+    const int p0 = chunk * per, p1 = min(p0 + per, npx);
+    for (int i = threadIdx.x; i < kHistWords; i += kHistThreads) sh_hist[i] = 0u;
+    __syncthreads();
+    const uint16_t* s = src + (size_t)b * sh * sw;
+    const double scx = (double)sw / (double)dw, scy = (double)sh / (double)dh;
+    for (int p = p0 + threadIdx.x; p < p1; p += kHistThreads) {
+        uint16_t v;
+        if (RESIZE) {
+            const int y = p / dw, x = p - y * dw;
+            const Tap tx = linear_tap(x, sw, scx), ty = linear_tap(y, sh, scy);
+            v = sat_u16(bilinear_at<uint16_t, false>(s, sw, ty, tx));
+            resized[(size_t)b * npx + p] = v;
+        } else {
+            v = __ldg(s + p);
+        }
+        atomicAdd(&sh_hist[v >> 1], (v & 1) ? 0x10000u : 1u);
+    }
+    __syncthreads();
+    unsigned int* gh = hist + (size_t)b * 65536;
+    for (int i = threadIdx.x; i < kHistWords; i += kHistThreads) {
+        const unsigned int w = sh_hist[i];
+        if (w & 0xffffu) atomicAdd(&gh[2 * i], w & 0xffffu);
+        if (w >> 16) atomicAdd(&gh[2 * i + 1], w >> 16);
+    }
+}
+
+// np.percentile(method='linear') finish (numpy _quantile/_lerp): a, b fp32 order
+// statistics, d = b - a in fp32, result fp64 two-sided lerp.
+__device__ __forceinline__ double lerp_percentile(float a, float b, double g) {
+    const float d = __fsub_rn(b, a);
+    return (g < 0.5) ? __dadd_rn((double)a, __dmul_rn((double)d, g))
+                     : __dsub_rn((double)b, __dmul_rn((double)d, __dsub_rn(1.0, g)));
+}
+
+__device__ __forceinline__ void percentile_ranks(int n, double q, unsigned int* k, double* g) {
+    const double vi = __dmul_rn((double)(n - 1), __ddiv_rn(q, 100.0));
+    const double fl = floor(vi);
+    *k = (unsigned int)fl;
+    *g = __dsub_rn(vi, fl);
+}
+
+// K2b: p2 / p98 from the exact histogram: one CTA per frame, 1024 threads x 64 bins.
+__global__ void __launch_bounds__(1024) percentile_from_hist_kernel(const unsigned int* __restrict__ hist, int n,
+                                                                    double* __restrict__ out_p) {
+    __shared__ unsigned int warp_tot[32];
+    __shared__ float found[4];
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
+    const unsigned int* h = hist + (size_t)b * 65536 + tid * 64;
+    unsigned int loc[64];
+    unsigned int sum = 0;
+#pragma unroll
+    for (int i = 0; i < 64; i += 4) {
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(h + i));
+        loc[i] = v.x; loc[i + 1] = v.y; loc[i + 2] = v.z; loc[i + 3] = v.w;
+        sum += v.x + v.y + v.z + v.w;
+    }
+    unsigned int incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    if (lane == 31) warp_tot[wrp] = incl;
+    __syncthreads();
+    if (wrp == 0) {
+        unsigned int w = warp_tot[lane], wi = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned int t = __shfl_up_sync(0xffffffffu, wi, o);
+            if (lane >= o) wi += t;
+        }
+        warp_tot[lane] = wi - w;
+    }
+    __syncthreads();
+    const unsigned int excl = warp_tot[wrp] + incl - sum;
+    unsigned int k[2]; double g[2];
+    percentile_ranks(n, 2.0, &k[0], &g[0]);
+    percentile_ranks(n, 98.0, &k[1], &g[1]);
+    const unsigned int ranks[4] = {k[0], min(k[0] + 1, (unsigned)n - 1), k[1], min(k[1] + 1, (unsigned)n - 1)};
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        if (ranks[r] >= excl && ranks[r] < excl + sum) {
+            unsigned int c = excl;
+            for (int i = 0; i < 64; ++i) {
+                c += loc[i];
+                if (ranks[r] < c) { found[r] = (float)(tid * 64 + i); break; }
+            }
+        }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        out_p[2 * b] = lerp_percentile(found[0], found[1], g[0]);
+        out_p[2 * b + 1] = lerp_percentile(found[2], found[3], g[1]);
+    }
+}
+
+// ------------------------------------------------------------------ channel collapse (utils/preprocessing.py:13-19)
+// flag[b] = 1 iff np.allclose(c0, c1) and np.allclose(c0, c2)   (rtol 1e-5, atol 1e-8, fp32)
+__device__ __forceinline__ bool is_close(float a, float b) {
+    const bool fin = isfinite(b);
+    const bool le = fabsf(__fsub_rn(a, b)) <= __fadd_rn(1e-8f, __fmul_rn(1e-5f, fabsf(b)));
+    return (le && fin) || (a == b);
+}
+
+__global__ void __launch_bounds__(256) channels_close_kernel(const float* __restrict__ x, int n, int* __restrict__ flag) {
+    // grid: (chunks, B); flag pre-set to 1; any violation clears it (idempotent store -> deterministic)
+    const int b = blockIdx.y;
+    const float* c0 = x + (size_t)b * 3 * n;
+    bool ok = true;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const float a = __ldg(c0 + i);
+        ok = ok && is_close(a, __ldg(c0 + n + i)) && is_close(a, __ldg(c0 + 2 * (size_t)n + i));
+    }
+    if (!__all_sync(0xffffffffu, ok) && (threadIdx.x & 31) == 0) flag[b] = 0;
+}
+
+__global__ void set_int_kernel(int* p, int n, int v) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+
+// the plane enhance_thermal_contrast works on: channel 0, or fp32 gray (no FMA), or the raw array
+__device__ __forceinline__ float plane_value(const float* __restrict__ img, int n, int channels, int collapse_to_c0, int i) {
+    if (channels != 3 || collapse_to_c0) return __ldg(img + i);
+    return gray3(__ldg(img + i), __ldg(img + n + i), __ldg(img + 2 * (size_t)n + i));
+}
+
+// ------------------------------------------------------------------ K2c: percentiles of arbitrary float data (radix select)
+// one CTA per image; out_p[b] = {p2, p98} as np.percentile(plane, (2, 98)) would return (fp64).
+__global__ void __launch_bounds__(t3d_select::kThreads, 1)
+percentile_select_kernel(const float* __restrict__ x, int n, int channels, const int* __restrict__ close_flag,
+                         double* __restrict__ out_p) {
+    __shared__ t3d_select::Smem sm;
+    __shared__ int s_nan;
+    const int b = blockIdx.x;
+    const float* img = x + (size_t)b * channels * n;
+    const int collapse = (channels == 3) ? close_flag[b] : 0;
+    const int count = (channels == 3) ? n : n * channels;     // non-3-channel input: the whole array
+    auto value = [&](int i) { return plane_value(img, n, channels, collapse, i); };
+    if (threadIdx.x == 0) s_nan = 0;
+    __syncthreads();
+    bool has_nan = false;
+    for (int i = threadIdx.x; i < count; i += blockDim.x) has_nan |= isnan(value(i));
+    if (has_nan) s_nan = 1;
+    __syncthreads();
+    if (s_nan) {                                                // np.percentile propagates NaN
+        if (threadIdx.x == 0) { out_p[2 * b] = __longlong_as_double(0x7ff8000000000000LL); out_p[2 * b + 1] = out_p[2 * b]; }
+        return;
+    }
+    auto get = [&](int i, float* v) { *v = value(i); return true; };
+    unsigned int k[2]; double g[2];
+    percentile_ranks(count, 2.0, &k[0], &g[0]);
+    percentile_ranks(count, 98.0, &k[1], &g[1]);
+    float os[4];
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        os[2 * r] = t3d_select::select_rank(sm, count, k[r], get);
+        const unsigned int k1 = min(k[r] + 1, (unsigned)count - 1);
+        os[2 * r + 1] = (g[r] == 0.0 || k1 == k[r]) ? os[2 * r] : t3d_select::select_rank(sm, count, k1, get);
+    }
+    if (threadIdx.x == 0) {
+        out_p[2 * b] = lerp_percentile(os[0], os[1], g[0]);
+        out_p[2 * b + 1] = lerp_percentile(os[2], os[3], g[1]);
+    }
+}
+
+// ------------------------------------------------------------------ K2d: clip-normalise in fp64, broadcast
+// out = float( clip((double(x) - p2) / (p98 - p2), 0, 1) ), NaN propagates like np.clip
+__device__ __forceinline__ float normalize_px(double x, double p2, double den) {
+    const double q = __ddiv_rn(__dsub_rn(x, p2), den);
+    if (isnan(q)) return __int_as_float(0x7fc00000);
+    return __double2float_rn(fmin(fmax(q, 0.0), 1.0));
+}
+
+// source is the resized u16 plane (train path); writes `rep` identical planes [B, rep, n]
+__global__ void __launch_bounds__(256) normalize_u16_kernel(const uint16_t* __restrict__ src, const double* __restrict__ p,
+                                                            float* __restrict__ dst, int n, int rep, int vec) {
+    const int b = blockIdx.y;
+    const double p2 = p[2 * b], den = __dsub_rn(p[2 * b + 1], p2);
+    const uint16_t* s = src + (size_t)b * n;
+    float* d = dst + (size_t)b * rep * n;
+    const int n4 = vec ? (n >> 2) : 0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += gridDim.x * blockDim.x) {
+        const ushort4 v = __ldg(reinterpret_cast<const ushort4*>(s) + i);
+        const float4 o = make_float4(normalize_px((double)v.x, p2, den), normalize_px((double)v.y, p2, den),
+                                     normalize_px((double)v.z, p2, den), normalize_px((double)v.w, p2, den));
+        for (int r = 0; r < rep; ++r) stg_stream_f4(d + (size_t)r * n + 4 * (size_t)i, o);
+    }
+    if (blockIdx.x == 0) {
+        for (int i = (n4 << 2) + threadIdx.x; i < n; i += blockDim.x) {
+            const float o = normalize_px((double)__ldg(s + i), p2, den);
+            for (int r = 0; r < rep; ++r) d[(size_t)r * n + i] = o;
+        }
+    }
+}
+
+// float source [B, channels, n] (drop-in enhance_thermal_contrast); rep output planes
+__global__ void __launch_bounds__(256) normalize_f32_kernel(const float* __restrict__ x, int n, int channels,
+                                                            const int* __restrict__ close_flag,
+                                                            const double* __restrict__ p, float* __restrict__ dst,
+                                                            int rep, int count) {
+    const int b = blockIdx.y;
+    const double p2 = p[2 * b], den = __dsub_rn(p[2 * b + 1], p2);
+    const float* img = x + (size_t)b * channels * n;
+    const int collapse = (channels == 3) ? close_flag[b] : 0;
+    float* d = dst + (size_t)b * rep * count;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
+        const float o = normalize_px((double)plane_value(img, n, channels, collapse, i), p2, den);
+        for (int r = 0; r < rep; ++r) d[(size_t)r * count + i] = o;
+    }
+}
+
+// ------------------------------------------------------------------ fixed range (utils/preprocessing.py:47-62), fp32 throughout
+__global__ void __launch_bounds__(256) fixed_range_kernel(const float* __restrict__ x, float* __restrict__ y, size_t n,
+                                                          size_t plane, const int* __restrict__ close_flag,
+                                                          int normalized) {
+    // close_flag (3-channel input whose channels are np.allclose): every output plane is f(channel 0)
+    const bool collapse = close_flag && close_flag[0];
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        float v = __ldg(x + (collapse ? i % plane : i));
+        if (normalized) v = __fmul_rn(v, 65535.0f);
+        // np.clip propagates NaN; fminf/fmaxf would not
+        const float c = isnan(v) ? v : fminf(fmaxf(v, 21800.0f), 25000.0f);
+        y[i] = __fdiv_rn(__fsub_rn(c, 21800.0f), 3200.0f);
+    }
+}
+
+int grid_for(size_t n, int threads, int per_sm = 8) {
+    const size_t need = (n + threads - 1) / threads;
+    const size_t cap = (size_t)t3d_sm_count() * per_sm;
+    return (int)(need < cap ? (need ? need : 1) : cap);
+}
+
+}  // namespace
+
+// ====================================================================== C ABI
+extern "C" {
+
+int t3d_resize_bilinear(const void* src, void* dst, int mode, int B, int src_h, int src_w,
+                        int dst_h, int dst_w, void* stream) {
+    T3D_REQUIRE(src && dst, "NULL pointer");
+    T3D_REQUIRE(B >= 1 && src_h >= 1 && src_w >= 1 && dst_h >= 1 && dst_w >= 1, "bad dims");
+    T3D_REQUIRE(mode >= 0 && mode <= 2, "mode must be 0 (u16->u16), 1 (u16->/65535->f32) or 2 (f32->f32)");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const int grid = grid_for((size_t)B * dst_h * dst_w, 256);
+    if (mode == 0) resize_bilinear_kernel<0><<<grid, 256, 0, st>>>(src, dst, B, src_h, src_w, dst_h, dst_w);
+    else if (mode == 1) resize_bilinear_kernel<1><<<grid, 256, 0, st>>>(src, dst, B, src_h, src_w, dst_h, dst_w);
+    else resize_bilinear_kernel<2><<<grid, 256, 0, st>>>(src, dst, B, src_h, src_w, dst_h, dst_w);
+    T3D_LAUNCH_CHECK("resize_bilinear_kernel");
+    return T3D_OK;
+}
+
+int t3d_resize_nearest_f32(const float* src, float* dst, int B, int src_h, int src_w, int dst_h, int dst_w,
+                           void* stream) {
+    T3D_REQUIRE(src && dst, "NULL pointer");
+    T3D_REQUIRE(B >= 1 && src_h >= 1 && src_w >= 1 && dst_h >= 1 && dst_w >= 1, "bad dims");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    resize_nearest_kernel<<<grid_for((size_t)B * dst_h * dst_w, 256), 256, 0, st>>>(src, dst, B, src_h, src_w, dst_h, dst_w);
+    T3D_LAUNCH_CHECK("resize_nearest_kernel");
+    return T3D_OK;
+}
+
+size_t t3d_preprocess_workspace_bytes(int B, int dst_h, int dst_w) {
+    if (B < 1 || dst_h < 1 || dst_w < 1) return 0;
+    return t3d_align_up((size_t)B * dst_h * dst_w * sizeof(uint16_t), 256);
+}
+
+int t3d_preprocess_train_u16(const uint16_t* raw, int B, int src_h, int src_w, int dst_h, int dst_w,
+                             float* out, int out_channels, unsigned int* hist, double* percentiles,
+                             void* workspace, size_t workspace_bytes, void* stream) {
+    T3D_REQUIRE(raw && out && hist && percentiles && workspace, "NULL pointer");
+    T3D_REQUIRE(B >= 1 && src_h >= 1 && src_w >= 1 && dst_h >= 1 && dst_w >= 1, "bad dims");
+    T3D_REQUIRE(out_channels == 1 || out_channels == 3, "out_channels must be 1 or 3");
+    T3D_REQUIRE((size_t)dst_h * dst_w < (1u << 30), "frame too large");
+    if (workspace_bytes < t3d_preprocess_workspace_bytes(B, dst_h, dst_w)) {
+        t3d_set_error("workspace too small");
+        return T3D_ERR_WORKSPACE;
+    }
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    uint16_t* resized = reinterpret_cast<uint16_t*>(workspace);
+    const int npx = dst_h * dst_w;
+    const bool same = (src_h == dst_h && src_w == dst_w);
+    T3D_CUDA(cudaMemsetAsync(hist, 0, (size_t)B * 65536 * sizeof(unsigned int), st));
+    const int chunks = (npx + kHistMaxPx - 1) / kHistMaxPx;
+    static bool attr_set = false;
+    if (!attr_set) {
+        T3D_CUDA(cudaFuncSetAttribute(resize_hist_u16_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      kHistWords * 4));
+        T3D_CUDA(cudaFuncSetAttribute(resize_hist_u16_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      kHistWords * 4));
+        attr_set = true;
+    }
+    if (same)
+        resize_hist_u16_kernel<false><<<B * chunks, kHistThreads, kHistWords * 4, st>>>(
+            raw, resized, hist, src_h, src_w, dst_h, dst_w, chunks);
+    else
+        resize_hist_u16_kernel<true><<<B * chunks, kHistThreads, kHistWords * 4, st>>>(
+            raw, resized, hist, src_h, src_w, dst_h, dst_w, chunks);
+    T3D_LAUNCH_CHECK("resize_hist_u16_kernel");
+    percentile_from_hist_kernel<<<B, 1024, 0, st>>>(hist, npx, percentiles);
+    T3D_LAUNCH_CHECK("percentile_from_hist_kernel");
+    dim3 grid((unsigned)min((npx / 4 + 255) / 256 + 1, 64), (unsigned)B);
+    const uint16_t* nsrc = same ? raw : resized;
+    const int vec = (npx % 4 == 0) && t3d_aligned16(out) && ((reinterpret_cast<uintptr_t>(nsrc) & 7u) == 0);
+    normalize_u16_kernel<<<grid, 256, 0, st>>>(nsrc, percentiles, out, npx, out_channels, vec);
+    T3D_LAUNCH_CHECK("normalize_u16_kernel");
+    return T3D_OK;
+}
+
+int t3d_contrast_normalize_f32(const float* x, int B, int channels, int n, float* out, int out_channels,
+                               double* percentiles, int* close_flags, void* stream) {
+    T3D_REQUIRE(x && out && percentiles && close_flags, "NULL pointer");
+    T3D_REQUIRE(B >= 1 && channels >= 1 && n >= 1, "bad dims");
+    T3D_REQUIRE((double)channels * n < 2.0e9, "image too large");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const int count = (channels == 3) ? n : n * channels;
+    if (channels == 3) {
+        set_int_kernel<<<(B + 255) / 256, 256, 0, st>>>(close_flags, B, 1);
+        T3D_LAUNCH_CHECK("set_int_kernel");
+        dim3 g((unsigned)min((n + 255) / 256, 32), (unsigned)B);
+        channels_close_kernel<<<g, 256, 0, st>>>(x, n, close_flags);
+        T3D_LAUNCH_CHECK("channels_close_kernel");
+    }
+    percentile_select_kernel<<<B, t3d_select::kThreads, 0, st>>>(x, n, channels, close_flags, percentiles);
+    T3D_LAUNCH_CHECK("percentile_select_kernel");
+    dim3 g2((unsigned)min((count + 255) / 256, 64), (unsigned)B);
+    normalize_f32_kernel<<<g2, 256, 0, st>>>(x, n, channels, close_flags, percentiles, out, out_channels, count);
+    T3D_LAUNCH_CHECK("normalize_f32_kernel");
+    return T3D_OK;
+}
+
+int t3d_channels_close(const float* x, int B, int n, int* close_flags, void* stream) {
+    T3D_REQUIRE(x && close_flags, "NULL pointer");
+    T3D_REQUIRE(B >= 1 && n >= 1, "bad dims");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    set_int_kernel<<<(B + 255) / 256, 256, 0, st>>>(close_flags, B, 1);
+    T3D_LAUNCH_CHECK("set_int_kernel");
+    dim3 g((unsigned)min((n + 255) / 256, 32), (unsigned)B);
+    channels_close_kernel<<<g, 256, 0, st>>>(x, n, close_flags);
+    T3D_LAUNCH_CHECK("channels_close_kernel");
+    return T3D_OK;
+}
+
+int t3d_fixed_range_normalize(const float* x, float* y, size_t n, size_t plane, const int* close_flag,
+                              int normalized, void* stream) {
+    T3D_REQUIRE(x && y, "NULL pointer");
+    if (n == 0) return T3D_OK;
+    T3D_REQUIRE(plane >= 1, "bad plane size");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    fixed_range_kernel<<<grid_for(n, 256), 256, 0, st>>>(x, y, n, plane, close_flag, normalized);
+    T3D_LAUNCH_CHECK("fixed_range_kernel");
+    return T3D_OK;
+}
+
+}  // extern "C"
