@@ -1,0 +1,339 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the Thermal3D-Vision per-pixel hot path on B200.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]                 # our sm_100a path
+  python bench.py --impl reference [--gpus N] [--steps K] [--warmup W]  # CPU oracle port of the reference
+
+A "step" is one pass of the hot path over one batch of synthetic input:
+thermal preprocessing of 2B raw 16-bit frames -> fused thermal-aware loss
+fwd+bwd over B pointmap pairs -> pointmap->depth + depth metrics of B frames
+(thermal3d_vision_b200.pipeline.HotPathStep).  Workload = BASELINE.json
+configs[2] ("DUSt3R-512 shape: batch=64 512x384 pointmap pairs"), the
+configuration the metric's 70 %-of-HBM target is quoted on; per-rank batch is
+fixed as N grows (weak scaling, sharded by image, one packed NCCL all-reduce
+of 16 doubles per step).  One JSON line on stdout (rank 0).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "frames/sec of fused loss fwd+bwd+preproc"
+UNIT = "pairs/s"
+EDGE_W, SMOOTH_W, DETAIL_W, ALPHA = 0.5, 0.3, 0.4, 0.2
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=64, help="pairs per rank")
+    ap.add_argument("--height", type=int, default=384)
+    ap.add_argument("--width", type=int, default=512)
+    ap.add_argument("--multi-scale", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-sample-pairs", type=int, default=2)
+    return ap.parse_args()
+
+
+def workload_name(a):
+    return f"dust3r512_batch{a.batch}_{a.width}x{a.height}_pairs_loss_fwd_bwd+preproc_640x512_u16+depth_metrics"
+
+
+def config_dict(a, world):
+    return {"workload": workload_name(a), "per_rank_batch": a.batch, "global_batch": a.batch * world,
+            "pointmap_hw": [a.height, a.width], "raw_frame_hw": [512, 640], "multi_scale": bool(a.multi_scale),
+            "edge_weight": EDGE_W, "smoothness_weight": SMOOTH_W, "detail_weight": DETAIL_W, "alpha": ALPHA,
+            "parallelism": f"dp{world} (sharded by image, one packed 128-byte all-reduce per step)",
+            "l2_policy": "inputs_exceed_l2 (1.2 GB of inputs per step vs 126 MB L2; no flush needed)"}
+
+
+# --------------------------------------------------------------------------- synthetic inputs
+def make_inputs_torch(B, H, W, seed, device):
+    import torch
+    g = torch.Generator(device=device).manual_seed(seed)
+    r = lambda *s: torch.randn(*s, device=device, generator=g)
+    gt1, gt2 = r(B, H, W, 3), r(B, H, W, 3)
+    gt1[..., 2] = 1.5 + 3 * gt1[..., 2].abs()
+    gt2[..., 2] = 1.5 + 3 * gt2[..., 2].abs()
+    pred1 = gt1 + 0.1 * r(B, H, W, 3)
+    pred2 = gt2 + 0.1 * r(B, H, W, 3)
+    conf1 = 1 + 4 * torch.rand(B, H, W, device=device, generator=g)
+    conf2 = 1 + 4 * torch.rand(B, H, W, device=device, generator=g)
+    raws = []
+    for _ in range(2):          # day: N(22800, 400); night: N(22300, 250) + hot blobs -- inside the Freiburg window
+        night = torch.rand(B, 1, 1, device=device, generator=g) < 0.4
+        f = torch.where(night, 22300 + 250 * r(B, 512, 640), 22800 + 400 * r(B, 512, 640))
+        blobs = (torch.rand(B, 512 // 32, 640 // 32, device=device, generator=g) < 0.01).float()
+        blobs = blobs.repeat_interleave(32, 1).repeat_interleave(32, 2) * 1500.0
+        f = f + torch.where(night, blobs, torch.zeros_like(blobs))
+        raws.append(f.clamp(0, 65535).to(torch.int32).to(torch.uint16))
+    gt_depth = gt1[..., 2].contiguous()
+    return {"raw1": raws[0], "raw2": raws[1], "pred1": pred1, "pred2": pred2, "gt1": gt1, "gt2": gt2,
+            "conf1": conf1, "conf2": conf2, "gt_depth": gt_depth}
+
+
+# --------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            p = [x.strip() for x in ln.split(",")]
+            if len(p) < 6:
+                continue
+            try:
+                sm.append(float(p[0])); mx.append(float(p[1]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------- CPU arm (oracle port of the reference)
+def cpu_step_fn(a):
+    """Returns (fn(n_pairs) -> None, description).  The unmodified reference cannot travel to the GPU box,
+    so this is the oracle port (oracle/): same per-sample loop as train_thermal_dustr.py:182-360 (loss per
+    sample -> mean over valid -> one backward), cv2.resize + percentile normalisation per frame as
+    data/dataset_loader.py:237-249 / utils/preprocessing.py:6-30, compute_depth_metrics per frame."""
+    import numpy as np
+    import torch
+    from oracle import ref_loss, ref_metrics, ref_preprocess
+    try:
+        import cv2
+        resize = lambda f, hw: cv2.resize(f, (hw[1], hw[0]))      # what the reference actually calls
+    except Exception:
+        resize = ref_preprocess.resize_bilinear
+    torch.set_num_threads(os.cpu_count() or 1)
+    H, W = a.height, a.width
+    n = a.cpu_sample_pairs
+    P1, P2, G1, G2, C1, C2, _, _ = ref_loss.make_batch_inputs(n, H, W, seed=0, smooth=False)
+    raw = ref_preprocess.make_raw_frames(2 * n, seed=0)
+    kw = dict(alpha=ALPHA, edge_weight=EDGE_W, smoothness_weight=SMOOTH_W, detail_weight=DETAIL_W,
+              multi_scale=bool(a.multi_scale))
+
+    def step():
+        th = []
+        for f in raw:
+            r = resize(f, (H, W)).astype(np.float32)
+            t = torch.from_numpy(np.repeat(r[None], 3, 0))
+            th.append(torch.from_numpy(ref_preprocess.enhance_thermal_contrast(t.numpy())[0]))
+        p1, p2 = P1.clone().requires_grad_(), P2.clone().requires_grad_()
+        c1, c2 = C1.clone().requires_grad_(), C2.clone().requires_grad_()
+        tot, nv = 0.0, 0
+        for i in range(n):
+            loss, _ = ref_loss.enhanced_thermal_aware_loss_torch(p1[i], p2[i], G1[i], G2[i], c1[i], c2[i],
+                                                                 th[2 * i], th[2 * i + 1], **kw)
+            if torch.isfinite(loss) and loss > 0:
+                tot = tot + loss
+                nv += 1
+        (tot / max(nv, 1)).backward()
+        for i in range(n):
+            ref_metrics.compute_depth_metrics(p1[i, ..., 2].detach().numpy(), G1[i, ..., 2].numpy())
+
+    return step, n, f"{n} of {a.batch} pairs ({W}x{H}) per step: per-sample loss loop + backward, 2 frames/pair preprocessed, metrics per pair"
+
+
+def time_cpu(a, min_seconds=10.0, max_iters=50, warmup=1):
+    step, n, desc = cpu_step_fn(a)
+    for _ in range(warmup):
+        step()
+    t0, it = time.perf_counter(), 0
+    while True:
+        step(); it += 1
+        el = time.perf_counter() - t0
+        if el >= min_seconds or it >= max_iters:
+            break
+    return {"value": n * it / el, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
+            "sample": desc + f"; {it} iterations in {el:.1f} s"}
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if rank != 0:
+        return
+    step, n, desc = cpu_step_fn(a)
+    steps = min(a.steps, 12)          # bounded so the run ends within minutes on host cores
+    for _ in range(min(a.warmup, 2)):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    el = time.perf_counter() - t0
+    v = n * steps / el
+    out = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": a.gpus, "steps": steps,
+           "warmup": min(a.warmup, 2), "ms_per_step": 1e3 * el / steps, "higher_is_better": True, "scaling": "weak",
+           "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config_dict(a, world),
+           "cpu_baseline": {"value": v, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port", "sample": desc},
+           "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "gpu_launches": 0, "note": "oracle port of the reference's CPU path on the host cores; the python reference "
+                                      "itself is not on the GPU box (no /root/reference there)"}
+    print(json.dumps(out), flush=True)
+
+
+# --------------------------------------------------------------------------- our arm
+def run_b200(a):
+    import torch
+    import torch.distributed as dist
+    from thermal3d_vision_b200 import _lib
+    from thermal3d_vision_b200.pipeline import HotPathStep
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl b200 needs a CUDA device (there is no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    if world != a.gpus and rank == 0:
+        print(f"[bench] note: --gpus {a.gpus} but WORLD_SIZE={world}; using {world}", file=sys.stderr)
+    _lib.lib()
+
+    B, H, W = a.batch, a.height, a.width
+    step = HotPathStep(B, H, W, device=dev, multi_scale=bool(a.multi_scale), alpha=ALPHA, edge_weight=EDGE_W,
+                       smoothness_weight=SMOOTH_W, detail_weight=DETAIL_W, distributed=world > 1)
+    d = make_inputs_torch(B, H, W, seed=rank, device=dev)
+    args = (d["raw1"], d["raw2"], d["pred1"], d["pred2"], d["gt1"], d["gt2"], d["conf1"], d["conf2"], d["gt_depth"])
+    host = {k: v.cpu().pin_memory() for k, v in d.items()}
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return t.item()
+        return ms
+
+    # ---------------- device-resident timing ("value")
+    for _ in range(max(a.warmup, 3)):
+        step.run_device(*args)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.15)
+    _lib.profile_begin("loss_tile_kernel", a.steps + 4)
+    n0 = _lib.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(a.steps):
+        step.run_device(*args)
+    e1.record()
+    barrier()
+    launches = _lib.launch_count() - n0
+    kern_ms, kern_n = _lib.profile_end()
+    ms_dev = max_over_ranks(e0.elapsed_time(e1))
+    clocks = sampler.stop() if rank == 0 else None
+    summary = HotPathStep.summarize(step.result.cpu())
+
+    # ---------------- end to end through the public API with HOST buffers ("e2e")
+    for _ in range(2):
+        step.run_host(host)
+    barrier()
+    e0.record()
+    for _ in range(a.steps):
+        step.run_host(host)
+    e1.record()
+    barrier()
+    ms_e2e = max_over_ranks(e0.elapsed_time(e1))
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        peak_src = "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+        ab = step.algorithmic_bytes()
+        kern_bytes = ab["loss"]
+        kern_avg_ms = kern_ms / max(kern_n, 1)
+        achieved = kern_bytes / (kern_avg_ms * 1e-3) / 1e9 if kern_n else None
+        step_bytes = sum(ab.values())
+        out = {
+            "metric": METRIC, "value": world * B * a.steps / (ms_dev * 1e-3), "unit": UNIT, "n_gpus": world,
+            "steps": a.steps, "warmup": max(a.warmup, 3), "ms_per_step": ms_dev / a.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": config_dict(a, world),
+            "roofline": {"bound": "hbm", "kernel": "loss_tile_kernel (fused loss fwd+bwd)",
+                         "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": (achieved / peak) if achieved else None, "traffic": None,
+                         "algorithmic_bytes_per_launch": kern_bytes, "avg_launch_ms": kern_avg_ms,
+                         "launches_timed": kern_n, "peak_source": peak_src,
+                         "step_algorithmic_bytes": step_bytes,
+                         "step_frac_of_peak": step_bytes / (ms_dev / a.steps * 1e-3) / 1e9 / peak},
+            "e2e": {"value": world * B * a.steps / (ms_e2e * 1e-3), "unit": UNIT,
+                    "h2d_bytes_per_step": HotPathStep.h2d_bytes(host), "d2h_bytes_per_step": 16 * 8,
+                    "ms_per_step": ms_e2e / a.steps},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "check": {k: summary[k] for k in ("loss", "abs_rel", "acc_1", "n_valid")},
+        }
+        if world == 1 and not a.no_cpu_baseline:
+            out["cpu_baseline"] = time_cpu(a)
+        else:
+            out["cpu_baseline"] = None
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_b200(a)
+
+
+if __name__ == "__main__":
+    main()

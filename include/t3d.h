@@ -50,6 +50,13 @@ int t3d_device_info(int* sm_count, int* cc_major, int* cc_minor);
 /* Number of kernels this library has launched from the calling process
  * (monotonic; bench.py reports the delta over the timed region). */
 uint64_t t3d_launch_count(void);
+/* Per-kernel device timing for roofline reports: between begin and end, every
+ * launch of a kernel whose name contains `kernel_name_substr` is bracketed by
+ * CUDA events on its launching stream (at most max_launches of them).
+ * t3d_profile_end synchronises on the last event and returns the summed kernel
+ * time and the number of launches timed. */
+int t3d_profile_begin(const char* kernel_name_substr, int max_launches);
+int t3d_profile_end(double* total_ms, int* launches);
 
 /* -------------------------------------------------------------------- loss */
 /* Replaces utils/loss.py:75-98 (confidence_weighted_regression_loss) and
@@ -208,6 +215,15 @@ int t3d_estimate_focal(const float* pointmap, const float* depth, int B, int H, 
 /* EXTENSION (the reference never applies K): u = fx X/Z + cx, v = fy Y/Z + cy; uv [n][2]. */
 int t3d_project_points(const float* pointmap, float fx, float fy, float cx, float cy,
                        float* uv, size_t n_pixels, void* stream);
+
+/* ------------------------------------------------------ step result packing */
+/* out16 (float64[16]) = [0] sum over VALID samples of the per-sample loss, [1..4] sums
+ * of basic/edge/smoothness/detail, [5] n_valid, [6] B (train_thermal_dustr.py:320,359);
+ * [7..13] sums of the FINITE per-image metrics abs_rel..acc_3, [14] n_images
+ * (utils/metrics.py:128-136); [15] 0.  Either input may be NULL.  This is the one
+ * vector a data-parallel job all-reduces per step. */
+int t3d_pack_step_result(const float* loss_per_sample, const double* metrics_f64, int B, int n_images,
+                         double* out16, void* stream);
 
 #ifdef __cplusplus
 }

@@ -64,7 +64,8 @@ def test_pointmap_z_in_place_batched(cuda_device, H, W):
     pm = rng.normal(size=(B, H, W, 3)).astype(np.float32)
     pm[..., 2] = gt * (1 + 0.3 * rng.normal(size=gt.shape)).astype(np.float32)
     pm[..., 2] = np.abs(pm[..., 2]) + 0.05
-    gt[1, : max(1, H // 4)] = 0
+    gt[1, : H // 4] = 0
+    gt[1, 0, : W // 3] = 0
     gt[2].flat[0] = np.nan
     d = torch.from_numpy(pm).to(cuda_device)
     r = tm.compute_depth_metrics_batch(d, torch.from_numpy(gt))

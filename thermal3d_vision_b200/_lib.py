@@ -27,6 +27,8 @@ _SIGNATURES = {
     "t3d_last_error": (C.c_char_p, []),
     "t3d_device_info": (C.c_int, [C.POINTER(C.c_int)] * 3),
     "t3d_launch_count": (C.c_uint64, []),
+    "t3d_profile_begin": (C.c_int, [C.c_char_p, C.c_int]),
+    "t3d_profile_end": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_int)]),
     "t3d_loss_workspace_bytes": (C.c_size_t, [C.c_int] * 4),
     "t3d_thermal_grad_stats": (C.c_int, [c_ptr, c_ptr, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                          c_ptr, c_ptr, C.c_size_t, c_ptr]),
@@ -50,6 +52,7 @@ _SIGNATURES = {
                           + [C.c_int] * 4 + [c_ptr] * 3 + [c_ptr, C.c_size_t, c_ptr]),
     "t3d_pointmap_to_depth": (C.c_int, [c_ptr, c_ptr, C.c_size_t, c_ptr]),
     "t3d_estimate_focal": (C.c_int, [c_ptr, c_ptr, C.c_int, C.c_int, C.c_int, c_ptr, c_ptr]),
+    "t3d_pack_step_result": (C.c_int, [c_ptr, c_ptr, C.c_int, C.c_int, c_ptr, c_ptr]),
     "t3d_project_points": (C.c_int, [c_ptr] + [C.c_float] * 4 + [c_ptr, C.c_size_t, c_ptr]),
 }
 
@@ -103,6 +106,17 @@ def check(rc: int, what: str = "") -> None:
 
 def launch_count() -> int:
     return int(lib().t3d_launch_count())
+
+
+def profile_begin(kernel_substr: str, max_launches: int = 4096) -> None:
+    check(lib().t3d_profile_begin(kernel_substr.encode(), int(max_launches)), "t3d_profile_begin")
+
+
+def profile_end():
+    """-> (total kernel ms, launches timed) for the kernel named in profile_begin."""
+    ms, n = C.c_double(0.0), C.c_int(0)
+    check(lib().t3d_profile_end(C.byref(ms), C.byref(n)), "t3d_profile_end")
+    return ms.value, n.value
 
 
 def ptr(t):

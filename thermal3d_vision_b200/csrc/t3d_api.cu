@@ -4,6 +4,8 @@
 
 #include <atomic>
 #include <mutex>
+#include <vector>
+#include <string.h>
 
 namespace {
 thread_local char g_err[512] = "";
@@ -25,6 +27,32 @@ void t3d_set_error(const char* fmt, ...) {
     va_start(ap, fmt);
     vsnprintf(g_err, sizeof(g_err), fmt, ap);
     va_end(ap);
+}
+
+// ---------------------------------------------------------------- per-kernel event timing
+namespace {
+struct Prof {
+    std::mutex mu;
+    bool active = false;
+    char pattern[96] = "";
+    std::vector<cudaEvent_t> ev;   // start/stop pairs
+    int used = 0, cap = 0;
+} g_prof;
+}  // namespace
+
+bool t3d_prof_before(const char* name, cudaStream_t st) {
+    if (!g_prof.active) return false;
+    std::lock_guard<std::mutex> lk(g_prof.mu);
+    if (!g_prof.active || g_prof.used >= g_prof.cap || !strstr(name, g_prof.pattern)) return false;
+    cudaEventRecord(g_prof.ev[2 * g_prof.used], st);
+    return true;
+}
+
+void t3d_prof_after(cudaStream_t st) {
+    std::lock_guard<std::mutex> lk(g_prof.mu);
+    if (!g_prof.active || g_prof.used >= g_prof.cap) return;
+    cudaEventRecord(g_prof.ev[2 * g_prof.used + 1], st);
+    ++g_prof.used;
 }
 
 void t3d_count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
@@ -53,5 +81,34 @@ int t3d_device_info(int* sm_count, int* cc_major, int* cc_minor) {
 }
 
 uint64_t t3d_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+int t3d_profile_begin(const char* kernel_name_substr, int max_launches) {
+    T3D_REQUIRE(kernel_name_substr && max_launches > 0 && max_launches <= (1 << 20), "bad arguments");
+    std::lock_guard<std::mutex> lk(g_prof.mu);
+    for (cudaEvent_t e : g_prof.ev) cudaEventDestroy(e);
+    g_prof.ev.assign((size_t)2 * max_launches, nullptr);
+    for (auto& e : g_prof.ev) T3D_CUDA(cudaEventCreate(&e));
+    strncpy(g_prof.pattern, kernel_name_substr, sizeof(g_prof.pattern) - 1);
+    g_prof.pattern[sizeof(g_prof.pattern) - 1] = 0;
+    g_prof.used = 0; g_prof.cap = max_launches; g_prof.active = true;
+    return T3D_OK;
+}
+
+int t3d_profile_end(double* total_ms, int* launches) {
+    std::lock_guard<std::mutex> lk(g_prof.mu);
+    g_prof.active = false;
+    double tot = 0.0;
+    for (int i = 0; i < g_prof.used; ++i) {
+        T3D_CUDA(cudaEventSynchronize(g_prof.ev[2 * i + 1]));
+        float ms = 0.f;
+        T3D_CUDA(cudaEventElapsedTime(&ms, g_prof.ev[2 * i], g_prof.ev[2 * i + 1]));
+        tot += ms;
+    }
+    if (total_ms) *total_ms = tot;
+    if (launches) *launches = g_prof.used;
+    for (cudaEvent_t e : g_prof.ev) cudaEventDestroy(e);
+    g_prof.ev.clear(); g_prof.used = 0; g_prof.cap = 0;
+    return T3D_OK;
+}
 
 }  // extern "C"

@@ -46,6 +46,19 @@ void t3d_count_launch(int n = 1);
 
 int t3d_sm_count();   // cached per process (current device at first call)
 
+// Optional per-kernel CUDA-event timing (t3d_profile_begin / t3d_profile_end in include/t3d.h).
+bool t3d_prof_before(const char* name, cudaStream_t st);
+void t3d_prof_after(cudaStream_t st);
+
+// T3D_LAUNCH("kernel_name", stream, kernel<<<grid, block, smem, stream>>>(args...));
+#define T3D_LAUNCH(name, st, ...)                        \
+    do {                                                 \
+        const bool prof__ = t3d_prof_before(name, st);   \
+        __VA_ARGS__;                                     \
+        if (prof__) t3d_prof_after(st);                  \
+        T3D_LAUNCH_CHECK(name);                          \
+    } while (0)
+
 static inline bool t3d_aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 static inline size_t t3d_align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 

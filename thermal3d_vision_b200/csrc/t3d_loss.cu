@@ -682,8 +682,7 @@ int check_dims(int B, int H, int W) {
 template <bool MULTI, bool VEC>
 int launch_stats(const StatsArgs& sa, cudaStream_t st) {
     const int grid = sa.B * 2 * sa.tiles_x * sa.tiles_y;
-    thermal_stats_kernel<MULTI, VEC><<<grid, kSThreads, 0, st>>>(sa);
-    T3D_LAUNCH_CHECK("thermal_stats_kernel");
+    T3D_LAUNCH("thermal_stats_kernel", st, thermal_stats_kernel<MULTI, VEC><<<grid, kSThreads, 0, st>>>(sa));
     return T3D_OK;
 }
 
@@ -707,8 +706,7 @@ int launch_loss(const LossArgs& la, cudaStream_t st) {
         attr_set = true;
     }
     const int grid = la.B * 2 * la.tiles_x * la.tiles_y;
-    loss_tile_kernel<MULTI, VEC, BWD><<<grid, kThreads, smem, st>>>(la);
-    T3D_LAUNCH_CHECK("loss_tile_kernel");
+    T3D_LAUNCH("loss_tile_kernel", st, loss_tile_kernel<MULTI, VEC, BWD><<<grid, kThreads, smem, st>>>(la));
     return T3D_OK;
 }
 
@@ -778,8 +776,7 @@ int loss_impl(bool bwd, const float* pred1, const float* pred2, const float* gt1
     fa.partials = loss_partials; fa.out_sample = out_sample; fa.out_batch = out_batch; fa.out_f64 = out_f64;
     fa.counter = counter; fa.B = B; fa.H = H; fa.W = W; fa.tiles = L.tiles_x * L.tiles_y;
     fa.multi = ms ? 1 : 0; fa.thermal_on = thermal_on ? 1 : 0; fa.ew = ew; fa.sw = sw; fa.dw = dw;
-    loss_finalize_kernel<<<B, 128, 0, st>>>(fa);
-    T3D_LAUNCH_CHECK("loss_finalize_kernel");
+    T3D_LAUNCH("loss_finalize_kernel", st, loss_finalize_kernel<<<B, 128, 0, st>>>(fa));
     return T3D_OK;
 }
 
@@ -804,8 +801,7 @@ int t3d_thermal_grad_stats(const float* thermal1, const float* thermal2, int the
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     float* partials = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + L.stats_partials);
     if (int rc = run_stats(thermal1, thermal2, thermal_channels, B, H, W, multi_scale, partials, L, st)) return rc;
-    thermal_stats_finalize_kernel<<<B * 2, 32, 0, st>>>(partials, L.stiles_x * L.stiles_y, H, W, multi_scale, out_stats);
-    T3D_LAUNCH_CHECK("thermal_stats_finalize_kernel");
+    T3D_LAUNCH("thermal_stats_finalize_kernel", st, thermal_stats_finalize_kernel<<<B * 2, 32, 0, st>>>(partials, L.stiles_x * L.stiles_y, H, W, multi_scale, out_stats));
     return T3D_OK;
 }
 
@@ -846,9 +842,8 @@ static int scale_common(int mode, float* dpred1, float* dpred2, float* dconf1, f
     sa.B = B; sa.plane = (size_t)H * W;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     const int grid = t3d_sm_count() * 8;
-    if (mode == 0) scale_grads_kernel<0><<<grid, 256, 0, st>>>(sa);
-    else scale_grads_kernel<1><<<grid, 256, 0, st>>>(sa);
-    T3D_LAUNCH_CHECK("scale_grads_kernel");
+    if (mode == 0) T3D_LAUNCH("scale_grads_kernel", st, scale_grads_kernel<0><<<grid, 256, 0, st>>>(sa));
+    else T3D_LAUNCH("scale_grads_kernel", st, scale_grads_kernel<1><<<grid, 256, 0, st>>>(sa));
     return T3D_OK;
 }
 

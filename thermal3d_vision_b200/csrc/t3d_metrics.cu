@@ -302,16 +302,12 @@ int t3d_depth_metrics(const float* pred, int pred_stride, int pred_offset,
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     T3D_CUDA(cudaMemsetAsync(w.counters, 0, (size_t)B * 4 * sizeof(int), st));
     dim3 g((unsigned)chunks, (unsigned)B);
-    depth_extract_kernel<<<g, kChunkThreads, 0, st>>>(pred, pred_stride, pred_offset, gt, gt_h, gt_w, mask, H, W,
-                                                      w.vz, w.vg, w.valid, w.counters);
-    T3D_LAUNCH_CHECK("depth_extract_kernel");
-    median_scale_kernel<<<B, t3d_select::kThreads, 0, st>>>(w.vz, w.vg, w.valid, w.counters, n, median_scaling,
-                                                            w.scale, out_medians);
-    T3D_LAUNCH_CHECK("median_scale_kernel");
-    metrics_sum_kernel<<<g, kChunkThreads, 0, st>>>(w.vz, w.vg, w.valid, w.scale, n, chunks, w.partials);
-    T3D_LAUNCH_CHECK("metrics_sum_kernel");
-    metrics_finalize_kernel<<<B, 32, 0, st>>>(w.partials, w.counters, chunks, out, out_f64);
-    T3D_LAUNCH_CHECK("metrics_finalize_kernel");
+    T3D_LAUNCH("depth_extract_kernel", st, depth_extract_kernel<<<g, kChunkThreads, 0, st>>>(pred, pred_stride, pred_offset, gt, gt_h, gt_w, mask, H, W,
+                                                      w.vz, w.vg, w.valid, w.counters));
+    T3D_LAUNCH("median_scale_kernel", st, median_scale_kernel<<<B, t3d_select::kThreads, 0, st>>>(w.vz, w.vg, w.valid, w.counters, n, median_scaling,
+                                                            w.scale, out_medians));
+    T3D_LAUNCH("metrics_sum_kernel", st, metrics_sum_kernel<<<g, kChunkThreads, 0, st>>>(w.vz, w.vg, w.valid, w.scale, n, chunks, w.partials));
+    T3D_LAUNCH("metrics_finalize_kernel", st, metrics_finalize_kernel<<<B, 32, 0, st>>>(w.partials, w.counters, chunks, out, out_f64));
     return T3D_OK;
 }
 
@@ -321,8 +317,7 @@ int t3d_pointmap_to_depth(const float* pointmap, float* depth, size_t n_pixels, 
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     const size_t blocks = (n_pixels + 255) / 256;
     const int grid = (int)(blocks < (size_t)t3d_sm_count() * 8 ? blocks : (size_t)t3d_sm_count() * 8);
-    pointmap_to_depth_kernel<<<grid, 256, 0, st>>>(pointmap, depth, n_pixels);
-    T3D_LAUNCH_CHECK("pointmap_to_depth_kernel");
+    T3D_LAUNCH("pointmap_to_depth_kernel", st, pointmap_to_depth_kernel<<<grid, 256, 0, st>>>(pointmap, depth, n_pixels));
     return T3D_OK;
 }
 
@@ -330,8 +325,7 @@ int t3d_estimate_focal(const float* pointmap, const float* depth, int B, int H, 
     T3D_REQUIRE(pointmap && out_K, "NULL pointer");
     T3D_REQUIRE(B >= 1 && H >= 1 && W >= 1, "bad dims");
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    focal_estimate_kernel<<<B, t3d_select::kThreads, 0, st>>>(pointmap, depth, H, W, out_K);
-    T3D_LAUNCH_CHECK("focal_estimate_kernel");
+    T3D_LAUNCH("focal_estimate_kernel", st, focal_estimate_kernel<<<B, t3d_select::kThreads, 0, st>>>(pointmap, depth, H, W, out_K));
     return T3D_OK;
 }
 
@@ -342,8 +336,7 @@ int t3d_project_points(const float* pointmap, float fx, float fy, float cx, floa
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     const size_t blocks = (n_pixels + 255) / 256;
     const int grid = (int)(blocks < (size_t)t3d_sm_count() * 8 ? blocks : (size_t)t3d_sm_count() * 8);
-    project_points_kernel<<<grid, 256, 0, st>>>(pointmap, fx, fy, cx, cy, uv, n_pixels);
-    T3D_LAUNCH_CHECK("project_points_kernel");
+    T3D_LAUNCH("project_points_kernel", st, project_points_kernel<<<grid, 256, 0, st>>>(pointmap, fx, fy, cx, cy, uv, n_pixels));
     return T3D_OK;
 }
 

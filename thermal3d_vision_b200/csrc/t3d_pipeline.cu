@@ -1,0 +1,66 @@
+// t3d_pipeline.cu -- packs the per-step scalars of the hot path into the one
+// small vector that is all-reduced across ranks:
+// training [sum valid loss, sum basic, edge, smooth, detail, n_valid, B] as
+// train_thermal_dustr.py:320,359 accumulates them, evaluation [7 metric sums,
+// n_images] as utils/metrics.py:128-136 does (non-finite metrics skipped but
+// the image still counted).
+#include "t3d_common.cuh"
+
+namespace {
+
+__global__ void __launch_bounds__(128) pack_step_result_kernel(const float* __restrict__ loss_per_sample,
+                                                               const double* __restrict__ metrics_f64, int B,
+                                                               int n_images, double* __restrict__ out) {
+    __shared__ double red[128][14];
+    const int tid = threadIdx.x;
+    double v[14];
+#pragma unroll
+    for (int k = 0; k < 14; ++k) v[k] = 0.0;
+    if (loss_per_sample) {
+        for (int b = tid; b < B; b += 128) {
+            const float* o = loss_per_sample + (size_t)b * T3D_LOSS_OUT_STRIDE;
+            if (o[5] != 0.f) {
+#pragma unroll
+                for (int k = 0; k < 5; ++k) v[k] += (double)o[k];
+                v[5] += 1.0;
+            }
+        }
+    }
+    if (metrics_f64) {
+        for (int b = tid; b < n_images; b += 128) {
+            const double* m = metrics_f64 + (size_t)b * 8;
+#pragma unroll
+            for (int k = 0; k < 7; ++k) if (isfinite(m[k])) v[7 + k] += m[k];
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 14; ++k) red[tid][k] = v[k];
+    __syncthreads();
+    for (int s = 64; s > 0; s >>= 1) {           // fixed-shape tree: deterministic
+        if (tid < s) {
+#pragma unroll
+            for (int k = 0; k < 14; ++k) red[tid][k] += red[tid + s][k];
+        }
+        __syncthreads();
+    }
+    if (tid < 16) {
+        double r;
+        if (tid == 6) r = loss_per_sample ? (double)B : 0.0;
+        else if (tid == 14) r = metrics_f64 ? (double)n_images : 0.0;
+        else if (tid == 15) r = 0.0;
+        else r = red[0][tid];
+        out[tid] = r;
+    }
+}
+
+}  // namespace
+
+extern "C" int t3d_pack_step_result(const float* loss_per_sample, const double* metrics_f64, int B, int n_images,
+                                    double* out16, void* stream) {
+    T3D_REQUIRE(out16, "NULL pointer");
+    T3D_REQUIRE(B >= 0 && n_images >= 0, "bad dims");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    T3D_LAUNCH("pack_step_result_kernel", st,
+               pack_step_result_kernel<<<1, 128, 0, st>>>(loss_per_sample, metrics_f64, B, n_images, out16));
+    return T3D_OK;
+}

@@ -363,10 +363,9 @@ int t3d_resize_bilinear(const void* src, void* dst, int mode, int B, int src_h, 
     T3D_REQUIRE(mode >= 0 && mode <= 2, "mode must be 0 (u16->u16), 1 (u16->/65535->f32) or 2 (f32->f32)");
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     const int grid = grid_for((size_t)B * dst_h * dst_w, 256);
-    if (mode == 0) resize_bilinear_kernel<0><<<grid, 256, 0, st>>>(src, dst, B, src_h, src_w, dst_h, dst_w);
-    else if (mode == 1) resize_bilinear_kernel<1><<<grid, 256, 0, st>>>(src, dst, B, src_h, src_w, dst_h, dst_w);
-    else resize_bilinear_kernel<2><<<grid, 256, 0, st>>>(src, dst, B, src_h, src_w, dst_h, dst_w);
-    T3D_LAUNCH_CHECK("resize_bilinear_kernel");
+    if (mode == 0) T3D_LAUNCH("resize_bilinear_kernel", st, resize_bilinear_kernel<0><<<grid, 256, 0, st>>>(src, dst, B, src_h, src_w, dst_h, dst_w));
+    else if (mode == 1) T3D_LAUNCH("resize_bilinear_kernel", st, resize_bilinear_kernel<1><<<grid, 256, 0, st>>>(src, dst, B, src_h, src_w, dst_h, dst_w));
+    else T3D_LAUNCH("resize_bilinear_kernel", st, resize_bilinear_kernel<2><<<grid, 256, 0, st>>>(src, dst, B, src_h, src_w, dst_h, dst_w));
     return T3D_OK;
 }
 
@@ -375,8 +374,7 @@ int t3d_resize_nearest_f32(const float* src, float* dst, int B, int src_h, int s
     T3D_REQUIRE(src && dst, "NULL pointer");
     T3D_REQUIRE(B >= 1 && src_h >= 1 && src_w >= 1 && dst_h >= 1 && dst_w >= 1, "bad dims");
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    resize_nearest_kernel<<<grid_for((size_t)B * dst_h * dst_w, 256), 256, 0, st>>>(src, dst, B, src_h, src_w, dst_h, dst_w);
-    T3D_LAUNCH_CHECK("resize_nearest_kernel");
+    T3D_LAUNCH("resize_nearest_kernel", st, resize_nearest_kernel<<<grid_for((size_t)B * dst_h * dst_w, 256), 256, 0, st>>>(src, dst, B, src_h, src_w, dst_h, dst_w));
     return T3D_OK;
 }
 
@@ -411,19 +409,16 @@ int t3d_preprocess_train_u16(const uint16_t* raw, int B, int src_h, int src_w, i
         attr_set = true;
     }
     if (same)
-        resize_hist_u16_kernel<false><<<B * chunks, kHistThreads, kHistWords * 4, st>>>(
-            raw, resized, hist, src_h, src_w, dst_h, dst_w, chunks);
+        T3D_LAUNCH("resize_hist_u16_kernel", st, resize_hist_u16_kernel<false><<<B * chunks, kHistThreads, kHistWords * 4, st>>>(
+            raw, resized, hist, src_h, src_w, dst_h, dst_w, chunks));
     else
-        resize_hist_u16_kernel<true><<<B * chunks, kHistThreads, kHistWords * 4, st>>>(
-            raw, resized, hist, src_h, src_w, dst_h, dst_w, chunks);
-    T3D_LAUNCH_CHECK("resize_hist_u16_kernel");
-    percentile_from_hist_kernel<<<B, 1024, 0, st>>>(hist, npx, percentiles);
-    T3D_LAUNCH_CHECK("percentile_from_hist_kernel");
+        T3D_LAUNCH("resize_hist_u16_kernel", st, resize_hist_u16_kernel<true><<<B * chunks, kHistThreads, kHistWords * 4, st>>>(
+            raw, resized, hist, src_h, src_w, dst_h, dst_w, chunks));
+    T3D_LAUNCH("percentile_from_hist_kernel", st, percentile_from_hist_kernel<<<B, 1024, 0, st>>>(hist, npx, percentiles));
     dim3 grid((unsigned)min((npx / 4 + 255) / 256 + 1, 64), (unsigned)B);
     const uint16_t* nsrc = same ? raw : resized;
     const int vec = (npx % 4 == 0) && t3d_aligned16(out) && ((reinterpret_cast<uintptr_t>(nsrc) & 7u) == 0);
-    normalize_u16_kernel<<<grid, 256, 0, st>>>(nsrc, percentiles, out, npx, out_channels, vec);
-    T3D_LAUNCH_CHECK("normalize_u16_kernel");
+    T3D_LAUNCH("normalize_u16_kernel", st, normalize_u16_kernel<<<grid, 256, 0, st>>>(nsrc, percentiles, out, npx, out_channels, vec));
     return T3D_OK;
 }
 
@@ -435,17 +430,13 @@ int t3d_contrast_normalize_f32(const float* x, int B, int channels, int n, float
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     const int count = (channels == 3) ? n : n * channels;
     if (channels == 3) {
-        set_int_kernel<<<(B + 255) / 256, 256, 0, st>>>(close_flags, B, 1);
-        T3D_LAUNCH_CHECK("set_int_kernel");
+        T3D_LAUNCH("set_int_kernel", st, set_int_kernel<<<(B + 255) / 256, 256, 0, st>>>(close_flags, B, 1));
         dim3 g((unsigned)min((n + 255) / 256, 32), (unsigned)B);
-        channels_close_kernel<<<g, 256, 0, st>>>(x, n, close_flags);
-        T3D_LAUNCH_CHECK("channels_close_kernel");
+        T3D_LAUNCH("channels_close_kernel", st, channels_close_kernel<<<g, 256, 0, st>>>(x, n, close_flags));
     }
-    percentile_select_kernel<<<B, t3d_select::kThreads, 0, st>>>(x, n, channels, close_flags, percentiles);
-    T3D_LAUNCH_CHECK("percentile_select_kernel");
+    T3D_LAUNCH("percentile_select_kernel", st, percentile_select_kernel<<<B, t3d_select::kThreads, 0, st>>>(x, n, channels, close_flags, percentiles));
     dim3 g2((unsigned)min((count + 255) / 256, 64), (unsigned)B);
-    normalize_f32_kernel<<<g2, 256, 0, st>>>(x, n, channels, close_flags, percentiles, out, out_channels, count);
-    T3D_LAUNCH_CHECK("normalize_f32_kernel");
+    T3D_LAUNCH("normalize_f32_kernel", st, normalize_f32_kernel<<<g2, 256, 0, st>>>(x, n, channels, close_flags, percentiles, out, out_channels, count));
     return T3D_OK;
 }
 
@@ -453,11 +444,9 @@ int t3d_channels_close(const float* x, int B, int n, int* close_flags, void* str
     T3D_REQUIRE(x && close_flags, "NULL pointer");
     T3D_REQUIRE(B >= 1 && n >= 1, "bad dims");
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    set_int_kernel<<<(B + 255) / 256, 256, 0, st>>>(close_flags, B, 1);
-    T3D_LAUNCH_CHECK("set_int_kernel");
+    T3D_LAUNCH("set_int_kernel", st, set_int_kernel<<<(B + 255) / 256, 256, 0, st>>>(close_flags, B, 1));
     dim3 g((unsigned)min((n + 255) / 256, 32), (unsigned)B);
-    channels_close_kernel<<<g, 256, 0, st>>>(x, n, close_flags);
-    T3D_LAUNCH_CHECK("channels_close_kernel");
+    T3D_LAUNCH("channels_close_kernel", st, channels_close_kernel<<<g, 256, 0, st>>>(x, n, close_flags));
     return T3D_OK;
 }
 
@@ -467,8 +456,7 @@ int t3d_fixed_range_normalize(const float* x, float* y, size_t n, size_t plane, 
     if (n == 0) return T3D_OK;
     T3D_REQUIRE(plane >= 1, "bad plane size");
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    fixed_range_kernel<<<grid_for(n, 256), 256, 0, st>>>(x, y, n, plane, close_flag, normalized);
-    T3D_LAUNCH_CHECK("fixed_range_kernel");
+    T3D_LAUNCH("fixed_range_kernel", st, fixed_range_kernel<<<grid_for(n, 256), 256, 0, st>>>(x, y, n, plane, close_flag, normalized));
     return T3D_OK;
 }
 

@@ -1,0 +1,114 @@
+"""The hot path as one step: thermal preprocessing -> fused thermal-aware loss
+(forward + backward) -> pointmap->depth + depth metrics, batched over B pairs.
+
+This is the public API `bench.py` times.  One "pair" = one training sample =
+two 16-bit thermal frames, two predicted and two pseudo-GT pointmaps with
+confidences (train_thermal_dustr.py:136-360) + the depth metrics of view 1
+(utils/metrics.py:72-138).  All arithmetic runs in libt3d_sm100.so; this class
+only owns buffers, streams and the (optional) data-parallel all-reduce.
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional
+
+import torch
+
+from . import _lib
+from . import loss as _loss
+from . import metrics as _metrics
+from . import preprocessing as _pre
+
+RESULT_SIZE = 16   # packed result vector (float64): see HotPathStep.run_device
+
+
+class HotPathStep:
+    def __init__(self, B: int, H: int, W: int, raw_hw=(512, 640), device=None, multi_scale: bool = False,
+                 alpha=0.2, edge_weight=0.5, smoothness_weight=0.3, detail_weight=0.4, distributed: bool = False):
+        self.B, self.H, self.W, self.raw_hw = B, H, W, tuple(raw_hw)
+        self.device = torch.device(device if device is not None else "cuda")
+        self.kw = dict(alpha=alpha, edge_weight=edge_weight, smoothness_weight=smoothness_weight,
+                       detail_weight=detail_weight, multi_scale=multi_scale)
+        self.distributed = distributed
+        dev = self.device
+        lib = _lib.lib()
+        f32 = dict(dtype=torch.float32, device=dev)
+        # outputs / workspaces are allocated once (the library never allocates)
+        self.loss_out = {
+            "workspace": torch.empty(lib.t3d_loss_workspace_bytes(B, H, W, 1), dtype=torch.uint8, device=dev),
+            "per_sample": torch.empty(B, 8, **f32), "batch": torch.empty(8, **f32),
+            "dpred1": torch.empty(B, H, W, 3, **f32), "dpred2": torch.empty(B, H, W, 3, **f32),
+            "dconf1": torch.empty(B, H, W, **f32), "dconf2": torch.empty(B, H, W, **f32),
+        }
+        self.pre_out = [{
+            "thermal": torch.empty(B, 3, H, W, **f32),
+            "percentiles": torch.empty(B, 2, dtype=torch.float64, device=dev),
+            "histogram": torch.empty(B, 65536, dtype=torch.int32, device=dev),
+            "workspace": torch.empty(lib.t3d_preprocess_workspace_bytes(B, H, W), dtype=torch.uint8, device=dev),
+        } for _ in range(2)]
+        self.met_out = {
+            "workspace": torch.empty(lib.t3d_depth_metrics_workspace_bytes(B, H, W), dtype=torch.uint8, device=dev),
+            "metrics": torch.empty(B, 8, **f32), "metrics_f64": torch.empty(B, 8, dtype=torch.float64, device=dev),
+            "medians": torch.empty(B, 2, **f32),
+        }
+        self.result = torch.zeros(RESULT_SIZE, dtype=torch.float64, device=dev)
+        self.result_host = torch.zeros(RESULT_SIZE, dtype=torch.float64).pin_memory()
+        self.staging: Optional[Dict[str, torch.Tensor]] = None
+
+    # ------------------------------------------------------------------ bytes
+    def algorithmic_bytes(self) -> Dict[str, int]:
+        B, n = self.B, self.H * self.W
+        raw = self.raw_hw[0] * self.raw_hw[1]
+        return {
+            "loss": 112 * B * n,                               # read 80 B/px-pair, write 32
+            "preprocess": 2 * B * (2 * raw + 12 * n),          # u16 frame in, 3 fp32 planes out
+            "metrics": B * (12 * n + 4 * n + 64),              # pointmap (AoS sectors) + GT in, 64 B out
+        }
+
+    # ------------------------------------------------------------------ device-resident step
+    def run_device(self, raw1, raw2, pred1, pred2, gt1, gt2, conf1, conf2, gt_depth):
+        """All inputs already in HBM.  Returns the packed device result vector (float64):
+        [0] sum of valid per-sample losses  [1..4] sums of components  [5] n_valid  [6] B
+        [7..13] sums of finite per-image metrics (abs_rel..acc_3)  [14] n_images  [15] unused.
+        With distributed=True the vector is all-reduced (SUM) over ranks: ONE small NCCL call."""
+        size = (self.W, self.H)
+        t1 = _pre.preprocess_thermal_batch(raw1, size, path="train", out=self.pre_out[0]).thermal
+        t2 = _pre.preprocess_thermal_batch(raw2, size, path="train", out=self.pre_out[1]).thermal
+        lo = _loss.fused_thermal_loss_fwd_bwd(pred1, pred2, gt1, gt2, conf1, conf2, t1, t2, out=self.loss_out, **self.kw)
+        me = _metrics.compute_depth_metrics_batch(pred1, gt_depth, out=self.met_out)   # Z of pred1 read in place
+        r = self.result
+        rc = _lib.lib().t3d_pack_step_result(_lib.ptr(lo["per_sample"]), _lib.ptr(me["metrics_f64"]), self.B, self.B,
+                                             _lib.ptr(r), _lib.current_stream_ptr())
+        _lib.check(rc, "t3d_pack_step_result")
+        if self.distributed:
+            import torch.distributed as dist
+            dist.all_reduce(r, op=dist.ReduceOp.SUM)
+        return r
+
+    # ------------------------------------------------------------------ host-buffer step (e2e)
+    def run_host(self, host: Dict[str, torch.Tensor]):
+        """Inputs are PINNED HOST tensors (raw1, raw2 uint16; pred1, pred2, gt1, gt2, conf1, conf2, gt_depth float32).
+        Copies them to the device, runs the step, copies the packed result back to pinned host memory.
+        Asynchronous on the current stream; `result_host` is valid after a stream synchronise."""
+        if self.staging is None:
+            self.staging = {k: torch.empty(v.shape, dtype=v.dtype, device=self.device) for k, v in host.items()}
+        for k, v in host.items():
+            self.staging[k].copy_(v, non_blocking=True)
+        s = self.staging
+        r = self.run_device(s["raw1"], s["raw2"], s["pred1"], s["pred2"], s["gt1"], s["gt2"], s["conf1"], s["conf2"],
+                            s["gt_depth"])
+        self.result_host.copy_(r, non_blocking=True)
+        return self.result_host
+
+    @staticmethod
+    def h2d_bytes(host: Dict[str, torch.Tensor]) -> int:
+        return int(sum(v.numel() * v.element_size() for v in host.values()))
+
+    @staticmethod
+    def summarize(result_host: torch.Tensor) -> Dict[str, float]:
+        r = result_host.tolist()
+        nv, n_img = max(r[5], 1.0), max(r[14], 1.0)
+        out = {"loss": r[0] / nv, "basic_loss": r[1] / nv, "edge_loss": r[2] / nv, "smoothness_loss": r[3] / nv,
+               "detail_loss": r[4] / nv, "n_valid": r[5], "n_pairs": r[6]}
+        for i, k in enumerate(_metrics.KEYS7):
+            out[k] = r[7 + i] / n_img
+        return out
