@@ -174,7 +174,7 @@ def cpu_step_fn(a):
     return step, n, f"{n} of {a.batch} pairs ({W}x{H}) per step: per-sample loss loop + backward, 2 frames/pair preprocessed, metrics per pair"
 
 
-def time_cpu(a, min_seconds=10.0, max_iters=50, warmup=1):
+def time_cpu(a, min_seconds=12.0, max_iters=2000, warmup=1):
     step, n, desc = cpu_step_fn(a)
     for _ in range(warmup):
         step()

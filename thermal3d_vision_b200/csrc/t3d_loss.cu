@@ -11,7 +11,9 @@
 //                          partial sums AND d/dpred, d/dconf written once
 //   loss_finalize_kernel   deterministic fixed-order fp64 second stage
 //   rescale / scale        device-conditional gradient rescaling (no host sync)
-#include "t3d_common.cuh"
+#include "t3d_loss_internal.cuh"
+
+#include <stdlib.h>
 
 namespace {
 
@@ -208,8 +210,10 @@ __device__ __forceinline__ float diff_term(bool valid, float za, float zb, float
 
 __device__ __forceinline__ float edge_weight_of(float tx, float ty, float inv_mx, float inv_my, float m) {
     // utils/loss.py:240-256: exp(-8 clamp(tx/mean,0,m)) * exp(-8 clamp(ty/mean,0,m))
-    const float cx = fminf(fmaxf(tx * inv_mx, 0.f), m);
-    const float cy = fminf(fmaxf(ty * inv_my, 0.f), m);
+    // tx, ty >= 0 so only the upper clamp acts; the select form lets NaN through like torch.clamp
+    const float ax = tx * inv_mx, ay = ty * inv_my;
+    const float cx = (ax > m) ? m : ax;
+    const float cy = (ay > m) ? m : ay;
     return expf(-kThermalFactor * cx) * expf(-kThermalFactor * cy);
 }
 
@@ -304,7 +308,7 @@ __global__ void __launch_bounds__(kThreads, MULTI ? 2 : 3) loss_tile_kernel(cons
                 const float dx = p[3 * e] - g[3 * e], dy = p[3 * e + 1] - g[3 * e + 1], dz = p[3 * e + 2] - g[3 * e + 2];
                 const float l = ((fabsf(dx) + fabsf(dy)) + fabsf(dz)) / 3.0f;             // utils/loss.py:82
                 const float craw = c[e];
-                const float cc = fminf(fmaxf(craw, kConfMin), kConfMax);                  // :91
+                const float cc = (craw < kConfMin) ? kConfMin : ((craw > kConfMax) ? kConfMax : craw);   // :91, NaN passes
                 const bool ok = e < nvalid;
                 if (ok) sum_basic += cc * l - a.alpha * logf(cc);                          // :95
                 zq[e] = p[3 * e + 2];
@@ -668,7 +672,8 @@ WsLayout ws_layout(int B, int H, int W) {
     size_t off = 0;
     L.counter = off;        off += 256;
     L.stats_partials = off; off += t3d_align_up((size_t)B * 2 * L.stiles_x * L.stiles_y * 4 * sizeof(float), 256);
-    L.loss_partials = off;  off += t3d_align_up((size_t)B * 2 * L.tiles_x * L.tiles_y * kNTerms * sizeof(float), 256);
+    // sized for the tile kernel (16-row tiles) and the marching kernel (>= 8-row bands)
+    L.loss_partials = off;  off += t3d_align_up((size_t)B * 2 * L.tiles_x * ((H + 7) / 8) * kNTerms * sizeof(float), 256);
     L.total = off;
     return L;
 }
@@ -734,7 +739,7 @@ int loss_impl(bool bwd, const float* pred1, const float* pred2, const float* gt1
     float* loss_partials = reinterpret_cast<float*>(ws + L.loss_partials);
     unsigned int* counter = reinterpret_cast<unsigned int*>(ws + L.counter);
 
-    T3D_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned int), st));
+    T3D_CUDA(cudaMemsetAsync(counter, 0, 2 * sizeof(unsigned int), st));   // [0] finalize ticket, [1] work queue
     if (thermal_on) {
         if (int rc = run_stats(thermal1, thermal2, tch, B, H, W, multi, stats_partials, L, st)) return rc;
     }
@@ -762,8 +767,27 @@ int loss_impl(bool bwd, const float* pred1, const float* pred2, const float* gt1
                t3d_aligned16(thermal1) && t3d_aligned16(thermal2) && t3d_aligned16(dpred1) &&
                t3d_aligned16(dpred2) && t3d_aligned16(dconf1) && t3d_aligned16(dconf2);
     const bool ms = multi && thermal_on;
+    int n_partials = L.tiles_x * L.tiles_y;
     int rc;
-    if (bwd) {
+    static const int march_rows = [] {
+        const char* e = getenv("T3D_MARCH_ROWS");           // tuning knob; 0 disables the fast path
+        const int v = e ? atoi(e) : 16;
+        return (v == 0) ? 0 : (v < 8 ? 8 : v);
+    }();
+    if (vec && thermal_on && !ms && march_rows > 0) {
+        // fast path: TMA-fed warp-marching kernel (t3d_loss_march.cu)
+        MarchArgs ma;
+        for (int v = 0; v < 2; ++v) {
+            ma.pred[v] = la.pred[v]; ma.gt[v] = la.gt[v]; ma.conf[v] = la.conf[v]; ma.thermal[v] = la.thermal[v];
+            ma.dpred[v] = la.dpred[v]; ma.dconf[v] = la.dconf[v];
+        }
+        ma.stats_partials = stats_partials; ma.partials = loss_partials; ma.queue = counter + 1;
+        ma.B = B; ma.H = H; ma.W = W; ma.tch = tch; ma.stiles = la.stiles;
+        ma.rows_per_band = march_rows; ma.nbands = (H + march_rows - 1) / march_rows; ma.nstrips = (W + 127) / 128;
+        ma.alpha = alpha; ma.kb = la.kb; ma.kc = la.kc; ma.kE = la.kE[0]; ma.kS = la.kS[0]; ma.kD = la.kD[0];
+        n_partials = ma.nbands * ma.nstrips;
+        rc = t3d_launch_loss_march(ma, bwd, st);
+    } else if (bwd) {
         if (ms) rc = vec ? launch_loss<true, true, true>(la, st) : launch_loss<true, false, true>(la, st);
         else    rc = vec ? launch_loss<false, true, true>(la, st) : launch_loss<false, false, true>(la, st);
     } else {
@@ -774,7 +798,7 @@ int loss_impl(bool bwd, const float* pred1, const float* pred2, const float* gt1
 
     FinalizeArgs fa;
     fa.partials = loss_partials; fa.out_sample = out_sample; fa.out_batch = out_batch; fa.out_f64 = out_f64;
-    fa.counter = counter; fa.B = B; fa.H = H; fa.W = W; fa.tiles = L.tiles_x * L.tiles_y;
+    fa.counter = counter; fa.B = B; fa.H = H; fa.W = W; fa.tiles = n_partials;
     fa.multi = ms ? 1 : 0; fa.thermal_on = thermal_on ? 1 : 0; fa.ew = ew; fa.sw = sw; fa.dw = dw;
     T3D_LAUNCH("loss_finalize_kernel", st, loss_finalize_kernel<<<B, 128, 0, st>>>(fa));
     return T3D_OK;

@@ -1,0 +1,18 @@
+// t3d_loss_internal.cuh -- interface between t3d_loss.cu (entry points, tile kernel,
+// second-stage reduction) and t3d_loss_march.cu (TMA-fed warp-marching fast path).
+#pragma once
+#include "t3d_common.cuh"
+
+struct MarchArgs {
+    const float* pred[2]; const float* gt[2]; const float* conf[2]; const float* thermal[2];
+    float* dpred[2]; float* dconf[2];
+    const float* stats_partials;   // [B*2][stiles][4]
+    float* partials;               // [B*2][nbands*nstrips][8]: basic, E, S, D, 0...
+    unsigned int* queue;           // work-item counter, zero on entry
+    int B, H, W, tch, stiles;
+    int rows_per_band, nbands, nstrips;
+    float alpha, kb, kc, kE, kS, kD;
+};
+
+// requires: W % 4 == 0, all pointers 16-byte aligned, tch in {1, 3}, single scale
+int t3d_launch_loss_march(const MarchArgs& a, bool bwd, cudaStream_t st);

@@ -1,0 +1,386 @@
+// t3d_loss_march.cu -- fast path of the fused thermal-aware loss (single scale,
+// 16-byte aligned, W % 4 == 0): warp-marching stencil fed by the TMA engine.
+//
+// Same math as loss_tile_kernel in t3d_loss.cu (utils/loss.py:75-98,100-305 and
+// its closed-form backward); different machine mapping:
+//
+//  * a work item is (image-view, 128-pixel strip, band of R rows); warps pull items
+//    from a global queue (persistent grid, one CTA per SM, no inter-warp sync);
+//  * the warp's lane 0 streams the strip's rows global -> shared with
+//    cp.async.bulk (1-D TMA: pred / gt AoS segments, confidence, thermal planes)
+//    into a warp-private NS-stage ring; completion is an mbarrier transaction
+//    count, so loads in flight cost no registers and the LSU sees no 48-byte
+//    strided AoS pattern;
+//  * each lane owns 4 consecutive pixels and marches down the rows: vertical
+//    neighbours live in registers (the row below is read once and becomes the
+//    current row), horizontal neighbours come from warp shuffles, the one pixel
+//    left/right of the strip from the 4-pixel halo the bulk copy brought along;
+//  * every forward-difference term q is evaluated exactly once per pixel
+//    (q_y of the row above is carried, q_x of the left neighbour is shuffled),
+//    gradients are gathered (no atomics) and written once with 128-bit stores.
+#include "t3d_loss_internal.cuh"
+
+namespace {
+
+constexpr float kEps = 1e-5f;
+constexpr float kHuber = 0.1f;
+constexpr float kConfMin = 1e-5f, kConfMax = 10.0f;
+
+constexpr int kStripPx = 128;            // 32 lanes x 4 pixels
+constexpr int kSegPx = kStripPx + 8;     // + 4-pixel halo each side (keeps 16-byte alignment of AoS rows)
+
+template <int TCH> struct Stage {
+    static constexpr int kPred = 0;
+    static constexpr int kGt = kSegPx * 3;
+    static constexpr int kConf = 2 * kSegPx * 3;
+    static constexpr int kTh = kConf + kStripPx;
+    static constexpr int kFloats = kTh + TCH * kSegPx;     // 1352 floats (TCH = 3)
+};
+
+// ------------------------------------------------------------------ PTX helpers (sm_100a)
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" :: "r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// 1-D bulk async copy global -> shared (TMA engine, SASS UBLKCP); completes `bytes` on the mbarrier
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+// ------------------------------------------------------------------ math
+struct Sums { float E, S, D; };
+
+// one forward-difference term; `valid == false` (zero-padded last column/row) contributes nothing
+__device__ __forceinline__ float q_term(bool valid, float za, float zb, float ga, float gb, float w, float omw,
+                                        float kE_omw, float kS2w, float kD, Sums& acc) {
+    zb = valid ? zb : za;
+    gb = valid ? gb : ga;
+    const float s = zb - za;
+    const float a = fabsf(s);
+    const float b = fabsf(gb - ga);
+    const float e = a - b;
+    const float d = fabsf(e);
+    const bool quad = d < kHuber;                                         // strict (utils/loss.py:275)
+    acc.E = fmaf(a, omw, acc.E);
+    acc.S = fmaf(a * a, w, acc.S);
+    acc.D += quad ? 0.5f * d * d : fmaf(kHuber, d, -0.5f * kHuber * kHuber);
+    const float dh = quad ? e : copysignf(kHuber, e);                     // rho'(d) sgn(e)
+    const float t = fmaf(kD, dh, fmaf(kS2w, a, kE_omw));
+    return (s > 0.f) ? t : ((s < 0.f) ? -t : 0.f);
+}
+
+__device__ __forceinline__ float edge_w(float tx, float ty, float inv_mx, float inv_my, float m) {
+    // exp(-8 clamp(tx/mean,0,m)) * exp(-8 clamp(ty/mean,0,m))  (utils/loss.py:240-256)
+    // tx, ty >= 0: the lower clamp is a no-op; the select form lets NaN through like torch.clamp
+    const float ax = tx * inv_mx, ay = ty * inv_my;
+    const float cx = (ax > m) ? m : ax;
+    const float cy = (ay > m) ? m : ay;
+    return __expf(-8.0f * (cx + cy));
+}
+
+template <int TCH>
+__device__ __forceinline__ void gray_quad(const float* __restrict__ th, int idx, float g[4]) {
+    const float4 c0 = *reinterpret_cast<const float4*>(th + idx);
+    if (TCH == 3) {
+        const float4 c1 = *reinterpret_cast<const float4*>(th + kSegPx + idx);
+        const float4 c2 = *reinterpret_cast<const float4*>(th + 2 * kSegPx + idx);
+        g[0] = gray3(c0.x, c1.x, c2.x); g[1] = gray3(c0.y, c1.y, c2.y);
+        g[2] = gray3(c0.z, c1.z, c2.z); g[3] = gray3(c0.w, c1.w, c2.w);
+    } else {
+        g[0] = c0.x; g[1] = c0.y; g[2] = c0.z; g[3] = c0.w;
+    }
+}
+template <int TCH>
+__device__ __forceinline__ float gray_px(const float* __restrict__ th, int idx) {
+    return (TCH == 3) ? gray3(th[idx], th[kSegPx + idx], th[2 * kSegPx + idx]) : th[idx];
+}
+
+__device__ __forceinline__ void load_aos_quad(const float* __restrict__ base, int idx, float v[12]) {
+    const float4* p = reinterpret_cast<const float4*>(base + idx * 3);
+    const float4 a = p[0], b = p[1], c = p[2];
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    v[8] = c.x; v[9] = c.y; v[10] = c.z; v[11] = c.w;
+}
+
+// ------------------------------------------------------------------ kernel
+template <int TCH, bool BWD, int NS, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, 1) loss_march_kernel(const MarchArgs a) {
+    using St = Stage<TCH>;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+    float* ring = reinterpret_cast<float*>(smem_raw) + (size_t)wrp * NS * St::kFloats;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + (size_t)WARPS * NS * St::kFloats * sizeof(float)) + wrp * NS;
+
+    if (lane == 0) {
+#pragma unroll
+        for (int s = 0; s < NS; ++s) mbar_init(&bars[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncwarp();
+
+    const int H = a.H, W = a.W;
+    const size_t plane = (size_t)H * W;
+    const int ntasks = a.B * 2 * a.nbands * a.nstrips;
+    uint32_t pos = 0;                                  // rows streamed so far by this warp (ring position)
+
+    for (;;) {
+        int task = 0;
+        if (lane == 0) task = (int)atomicAdd(a.queue, 1u);
+        task = __shfl_sync(0xffffffffu, task, 0);
+        if (task >= ntasks) break;
+        const int s = task % a.nstrips;
+        const int t2 = task / a.nstrips;
+        const int k = t2 % a.nbands;
+        const int img = t2 / a.nbands;
+        const int b = img >> 1, view = img & 1;
+        const int ra = k * a.rows_per_band, rb = min(ra + a.rows_per_band, H);
+        const int i_lo = max(ra - 1, 0), i_hi = min(rb, H - 1);
+        const int n_rows = i_hi - i_lo + 1;
+        const int col0 = s * kStripPx;
+        const int c0 = max(col0 - 4, 0), c1 = min(col0 + kStripPx + 4, W);
+        const int npx = c1 - c0, off = col0 - c0;
+        const int own_n = min(kStripPx, W - col0);
+        const int j = col0 + 4 * lane;
+        const bool active = 4 * lane < own_n;
+        const bool last_lane = active && (4 * lane + 4 >= own_n);
+        const int idx = 4 * lane + off;                // smem pixel index of this lane's quad
+
+        const float* __restrict__ pred = a.pred[view] + (size_t)b * plane * 3;
+        const float* __restrict__ gt = a.gt[view] + (size_t)b * plane * 3;
+        const float* __restrict__ conf = a.conf[view] ? a.conf[view] + (size_t)b * plane : nullptr;
+        const float* __restrict__ th = a.thermal[view] + (size_t)b * TCH * plane;
+        float* __restrict__ dpred = BWD ? a.dpred[view] + (size_t)b * plane * 3 : nullptr;
+        float* __restrict__ dconf = (BWD && a.dconf[view]) ? a.dconf[view] + (size_t)b * plane : nullptr;
+
+        // 1 / (mean + eps) of |Dx gray|, |Dy gray| of this image: fixed-order sum of the stats partials
+        float inv_mx, inv_my;
+        {
+            float sx = 0.f, sy = 0.f;
+            const float* sp = a.stats_partials + (size_t)img * a.stiles * 4;
+            for (int t = lane; t < a.stiles; t += 32) { sx += sp[t * 4]; sy += sp[t * 4 + 1]; }
+            sx = warp_sum(sx); sy = warp_sum(sy);
+            const float invN = 1.0f / (float)plane;
+            inv_mx = 1.0f / (sx * invN + kEps);
+            inv_my = 1.0f / (sy * invN + kEps);
+        }
+        const float m = (view == 0) ? 0.4f : 0.5f;       // utils/loss.py:253-256
+        const uint32_t row_bytes = (uint32_t)npx * (24u + 4u * TCH) + (conf ? (uint32_t)own_n * 4u : 0u);
+
+        auto issue_row = [&](int ri) {                    // lane 0 only
+            const uint32_t p = pos + (uint32_t)ri;
+            float* st = ring + (size_t)(p % NS) * St::kFloats;
+            uint64_t* bar = &bars[p % NS];
+            const size_t rowpix = (size_t)(i_lo + ri) * W;
+            mbar_arrive_expect_tx(bar, row_bytes);
+            bulk_g2s(st + St::kPred, pred + (rowpix + c0) * 3, (uint32_t)npx * 12u, bar);
+            bulk_g2s(st + St::kGt, gt + (rowpix + c0) * 3, (uint32_t)npx * 12u, bar);
+            if (conf) bulk_g2s(st + St::kConf, conf + rowpix + col0, (uint32_t)own_n * 4u, bar);
+#pragma unroll
+            for (int c = 0; c < TCH; ++c)
+                bulk_g2s(st + St::kTh + c * kSegPx, th + (size_t)c * plane + rowpix + c0, (uint32_t)npx * 4u, bar);
+        };
+        auto stage_of = [&](int ri) { return ring + (size_t)((pos + (uint32_t)ri) % NS) * St::kFloats; };
+        auto wait_row = [&](int ri) {
+            const uint32_t p = pos + (uint32_t)ri;
+            mbar_wait(&bars[p % NS], (p / NS) & 1u);
+        };
+
+        if (lane == 0) {
+            const int pre = min(NS, n_rows);
+            for (int ri = 0; ri < pre; ++ri) issue_row(ri);
+        }
+
+        // current row state (registers)
+        float cP[12], cG[12], cg[4];
+        wait_row(0);
+        {
+            const float* st = stage_of(0);
+            if (active) {
+                load_aos_quad(st + St::kPred, idx, cP);
+                load_aos_quad(st + St::kGt, idx, cG);
+                gray_quad<TCH>(st + St::kTh, idx, cg);
+            } else {
+#pragma unroll
+                for (int e = 0; e < 12; ++e) { cP[e] = 0.f; cG[e] = 0.f; }
+                cg[0] = cg[1] = cg[2] = cg[3] = 0.f;
+            }
+        }
+        float qy_prev[4] = {0.f, 0.f, 0.f, 0.f};
+        float sum_b = 0.f;
+        Sums tot = {0.f, 0.f, 0.f};
+
+        const int n_cur = rb - i_lo;                      // rows that are "current" at some iteration
+        for (int ri = 0; ri < n_cur; ++ri) {
+            const int r = i_lo + ri;
+            const bool own = r >= ra;
+            const bool has_below = r + 1 < H;
+            const float* st = stage_of(ri);
+            float nP[12], nG[12], ng[4];
+            const float* stn = nullptr;
+            if (has_below) {
+                wait_row(ri + 1);
+                stn = stage_of(ri + 1);
+                if (active) {
+                    load_aos_quad(stn + St::kPred, idx, nP);
+                    load_aos_quad(stn + St::kGt, idx, nG);
+                    gray_quad<TCH>(stn + St::kTh, idx, ng);
+                }
+            }
+            if (!has_below || !active) {
+#pragma unroll
+                for (int e = 0; e < 12; ++e) { nP[e] = 0.f; nG[e] = 0.f; }
+                ng[0] = ng[1] = ng[2] = ng[3] = 0.f;
+            }
+
+            // ---- basic term (own rows only): utils/loss.py:81-98
+            float gq[12];
+#pragma unroll
+            for (int e = 0; e < 12; ++e) gq[e] = 0.f;
+            if (own && active) {
+                float c[4] = {1.f, 1.f, 1.f, 1.f};
+                if (conf) {
+                    const float4 cc = *reinterpret_cast<const float4*>(st + St::kConf + 4 * lane);
+                    c[0] = cc.x; c[1] = cc.y; c[2] = cc.z; c[3] = cc.w;
+                }
+                float dc[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const float dx = cP[3 * e] - cG[3 * e], dy = cP[3 * e + 1] - cG[3 * e + 1],
+                                dz = cP[3 * e + 2] - cG[3 * e + 2];
+                    const float l = ((fabsf(dx) + fabsf(dy)) + fabsf(dz)) * (1.0f / 3.0f);
+                    const float craw = c[e];
+                    const float cc = (craw < kConfMin) ? kConfMin : ((craw > kConfMax) ? kConfMax : craw);  // NaN passes
+                    sum_b += fmaf(cc, l, -a.alpha * __logf(cc));
+                    if (BWD) {
+                        const float k3 = cc * a.kb;
+                        gq[3 * e] = (dx > 0.f) ? k3 : ((dx < 0.f) ? -k3 : 0.f);
+                        gq[3 * e + 1] = (dy > 0.f) ? k3 : ((dy < 0.f) ? -k3 : 0.f);
+                        gq[3 * e + 2] = (dz > 0.f) ? k3 : ((dz < 0.f) ? -k3 : 0.f);
+                        const bool inside = (craw >= kConfMin) && (craw <= kConfMax);
+                        dc[e] = inside ? (l - __fdividef(a.alpha, cc)) * a.kc : 0.f;
+                    }
+                }
+                if (BWD && dconf) stg_stream_f4(dconf + (size_t)r * W + j, make_float4(dc[0], dc[1], dc[2], dc[3]));
+            }
+
+            // ---- horizontal neighbours of the current row
+            const float cz[4] = {cP[2], cP[5], cP[8], cP[11]};
+            const float cgz[4] = {cG[2], cG[5], cG[8], cG[11]};
+            float zr = __shfl_down_sync(0xffffffffu, cz[0], 1);
+            float gzr = __shfl_down_sync(0xffffffffu, cgz[0], 1);
+            float gr = __shfl_down_sync(0xffffffffu, cg[0], 1);
+            if (last_lane && (j + 4 < W)) {               // right neighbour lives in the strip's halo
+                zr = st[St::kPred + (idx + 4) * 3 + 2];
+                gzr = st[St::kGt + (idx + 4) * 3 + 2];
+                gr = gray_px<TCH>(st + St::kTh, idx + 4);
+            }
+            const float zx[5] = {cz[0], cz[1], cz[2], cz[3], zr};
+            const float gzx[5] = {cgz[0], cgz[1], cgz[2], cgz[3], gzr};
+            const float gx[5] = {cg[0], cg[1], cg[2], cg[3], gr};
+            const float nz[4] = {nP[2], nP[5], nP[8], nP[11]};
+            const float ngz[4] = {nG[2], nG[5], nG[8], nG[11]};
+
+            // ---- edge weights, q terms
+            Sums acc = {0.f, 0.f, 0.f};
+            float qx[4], qy[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const bool vx = (j + e) < W - 1;
+                const float tx = vx ? fabsf(gx[e + 1] - gx[e]) : 0.f;
+                const float ty = has_below ? fabsf(ng[e] - cg[e]) : 0.f;
+                const float w = edge_w(tx, ty, inv_mx, inv_my, m);
+                const float omw = 1.0f - w;
+                const float kE_omw = a.kE * omw, kS2w = 2.0f * a.kS * w;
+                qx[e] = q_term(vx, zx[e], zx[e + 1], gzx[e], gzx[e + 1], w, omw, kE_omw, kS2w, a.kD, acc);
+                qy[e] = q_term(has_below, zx[e], nz[e], gzx[e], ngz[e], w, omw, kE_omw, kS2w, a.kD, acc);
+            }
+            // q_x of the pixel left of this quad
+            float qxl = __shfl_up_sync(0xffffffffu, qx[3], 1);
+            if (lane == 0) {
+                qxl = 0.f;
+                if (col0 > 0) {                           // pixel col0-1 is in the halo (idx - 1)
+                    const float zl = st[St::kPred + (idx - 1) * 3 + 2];
+                    const float gzl = st[St::kGt + (idx - 1) * 3 + 2];
+                    const float gl = gray_px<TCH>(st + St::kTh, idx - 1);
+                    const float tyl = has_below ? fabsf(gray_px<TCH>(stn + St::kTh, idx - 1) - gl) : 0.f;
+                    const float wl = edge_w(fabsf(cg[0] - gl), tyl, inv_mx, inv_my, m);
+                    const float omw = 1.0f - wl;
+                    Sums dummy = {0.f, 0.f, 0.f};
+                    qxl = q_term(true, zl, cz[0], gzl, cgz[0], wl, omw, a.kE * omw, 2.0f * a.kS * wl, a.kD, dummy);
+                }
+            }
+            if (own && active) {
+                tot.E += acc.E; tot.S += acc.S; tot.D += acc.D;
+                if (BWD) {
+                    gq[2] += -qx[0] + qxl - qy[0] + qy_prev[0];
+                    gq[5] += -qx[1] + qx[0] - qy[1] + qy_prev[1];
+                    gq[8] += -qx[2] + qx[1] - qy[2] + qy_prev[2];
+                    gq[11] += -qx[3] + qx[2] - qy[3] + qy_prev[3];
+                    float* o = dpred + ((size_t)r * W + j) * 3;
+                    stg_stream_f4(o, make_float4(gq[0], gq[1], gq[2], gq[3]));
+                    stg_stream_f4(o + 4, make_float4(gq[4], gq[5], gq[6], gq[7]));
+                    stg_stream_f4(o + 8, make_float4(gq[8], gq[9], gq[10], gq[11]));
+                }
+            }
+#pragma unroll
+            for (int e = 0; e < 4; ++e) { qy_prev[e] = qy[e]; cg[e] = ng[e]; }
+#pragma unroll
+            for (int e = 0; e < 12; ++e) { cP[e] = nP[e]; cG[e] = nG[e]; }
+
+            __syncwarp();                                 // every lane is done reading stage(ri)
+            if (lane == 0 && ri + NS < n_rows) issue_row(ri + NS);
+        }
+        pos += (uint32_t)n_rows;
+
+        // ---- per-task partial sums (fixed butterfly: deterministic)
+        sum_b = warp_sum(sum_b);
+        tot.E = warp_sum(tot.E); tot.S = warp_sum(tot.S); tot.D = warp_sum(tot.D);
+        if (lane == 0) {
+            float4* o = reinterpret_cast<float4*>(a.partials + (size_t)task * 8);
+            o[0] = make_float4(sum_b, tot.E, tot.S, tot.D);
+            o[1] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    }
+}
+
+template <int TCH, bool BWD>
+int launch(const MarchArgs& a, cudaStream_t st) {
+    constexpr int NS = 4;
+    constexpr int WARPS = (TCH == 3) ? 10 : 12;
+    constexpr size_t smem = (size_t)WARPS * NS * Stage<TCH>::kFloats * sizeof(float) + (size_t)WARPS * NS * 8;
+    static_assert(smem <= 227 * 1024, "ring does not fit in shared memory");
+    static bool attr_set = false;
+    if (!attr_set) {
+        T3D_CUDA(cudaFuncSetAttribute(loss_march_kernel<TCH, BWD, NS, WARPS>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+    }
+    const int grid = t3d_sm_count();
+    T3D_LAUNCH("loss_march_kernel", st,
+               loss_march_kernel<TCH, BWD, NS, WARPS><<<grid, WARPS * 32, smem, st>>>(a));
+    return T3D_OK;
+}
+
+}  // namespace
+
+int t3d_launch_loss_march(const MarchArgs& a, bool bwd, cudaStream_t st) {
+    if (a.tch == 3) return bwd ? launch<3, true>(a, st) : launch<3, false>(a, st);
+    return bwd ? launch<1, true>(a, st) : launch<1, false>(a, st);
+}

@@ -19,11 +19,25 @@ namespace {
 constexpr int kChunkThreads = 256;
 constexpr int kNPart = 8;   // abs_rel, sq_rel, sq, log2, a1, a2, a3, (pad)
 
+// Batched exact medians: multi-CTA 3-pass radix select (11 + 11 + 10 bits of the monotone key).
+// Two streams per image (0 = gt, 1 = pred) and two targets per stream (A = rank (n-1)/2, B = rank n/2;
+// np.median averages them).  Histogram kernels run on (chunks x B) CTAs with shared-memory histograms
+// and warp-aggregated atomics; tiny pick kernels scan the merged histograms between passes.
+constexpr int kSelBins = 2048;
+
+struct SelState {           // per (image, stream)
+    unsigned int prefix[2]; // selected high bits of target A / B
+    unsigned int rank[2];   // remaining rank inside the prefix
+};
+
 struct MetricsWs {
-    float* vz; float* vg; unsigned char* valid;
-    int* counters;     // [B][4]: n_valid, pred_nan, gt_nan, pad
-    float* scale;      // [B]
-    double* partials;  // [B][chunks][kNPart]
+    float* vz; float* vg;
+    int* counters;          // [B][4]: n_valid, pred_nan, gt_nan, pad
+    unsigned int* hist;     // [B][2 streams][2 targets][kSelBins]
+    SelState* state;        // [B][2]
+    float* scale;           // [B]
+    double* partials;       // [B][chunks][kNPart]
+    size_t zero_bytes;      // counters + hist are contiguous: one memset
     size_t total;
 };
 
@@ -32,10 +46,12 @@ MetricsWs metrics_ws(void* base, int B, int n, int chunks) {
     size_t off = 0;
     char* p = reinterpret_cast<char*>(base);
     auto take = [&](size_t bytes) { char* r = p ? p + off : nullptr; off += t3d_align_up(bytes, 256); return r; };
+    w.counters = reinterpret_cast<int*>(take((size_t)B * 4 * sizeof(int)));
+    w.hist = reinterpret_cast<unsigned int*>(take((size_t)B * 4 * kSelBins * sizeof(unsigned int)));
+    w.zero_bytes = off;
     w.vz = reinterpret_cast<float*>(take((size_t)B * n * 4));
     w.vg = reinterpret_cast<float*>(take((size_t)B * n * 4));
-    w.valid = reinterpret_cast<unsigned char*>(take((size_t)B * n));
-    w.counters = reinterpret_cast<int*>(take((size_t)B * 4 * sizeof(int)));
+    w.state = reinterpret_cast<SelState*>(take((size_t)B * 2 * sizeof(SelState)));
     w.scale = reinterpret_cast<float*>(take((size_t)B * sizeof(float)));
     w.partials = reinterpret_cast<double*>(take((size_t)B * chunks * kNPart * sizeof(double)));
     w.total = off;
@@ -44,36 +60,61 @@ MetricsWs metrics_ws(void* base, int B, int n, int chunks) {
 
 int chunks_for(int n) { return max(1, min(96, (n + 4095) / 4096)); }
 
-// ------------------------------------------------------------------ M1: extract (K5)
+// one shared-memory histogram increment, aggregated over the lanes of the warp that hit the same bin
+// (depth values crowd into a few exponent bins: without aggregation same-address atomics serialise)
+__device__ __forceinline__ void hist_add(unsigned int* h, bool on, unsigned int bin) {
+    const unsigned int key = on ? bin : 0xffffffffu;
+    const unsigned int peers = __match_any_sync(0xffffffffu, key);
+    if (on && (threadIdx.x & 31) == (unsigned)(__ffs(peers) - 1)) atomicAdd(&h[bin], (unsigned)__popc(peers));
+}
+
+__device__ __forceinline__ void merge_hist(const unsigned int* sh, unsigned int* gh, int count) {
+    for (int i = threadIdx.x; i < count; i += blockDim.x) {
+        const unsigned int v = sh[i];
+        if (v) atomicAdd(&gh[i], v);
+    }
+}
+
+// ------------------------------------------------------------------ M1: extract (K5) + first select pass
 // pred element (b, i) lives at pred[(b*n + i) * pred_stride + pred_offset]: stride 3 / offset 2 reads
 // the Z channel of an AoS pointmap in place (depth is never materialised by the caller).
+// Invalid pixels are stored as vg = NaN (a *selected* NaN GT makes every metric NaN anyway: gt_nan counter).
 __global__ void __launch_bounds__(kChunkThreads)
 depth_extract_kernel(const float* __restrict__ pred, int pred_stride, int pred_offset,
                      const float* __restrict__ gt, int gt_h, int gt_w, const unsigned char* __restrict__ mask,
                      int H, int W, float* __restrict__ vz, float* __restrict__ vg,
-                     unsigned char* __restrict__ valid, int* __restrict__ counters) {
+                     int* __restrict__ counters, unsigned int* __restrict__ hist) {
+    __shared__ unsigned int sh[2][kSelBins];
     const int b = blockIdx.y, n = H * W;
+    for (int i = threadIdx.x; i < 2 * kSelBins; i += kChunkThreads) (&sh[0][0])[i] = 0u;
+    __syncthreads();
     const bool resample = (gt_h != H) || (gt_w != W);
     const double fx = (double)gt_w / (double)W, fy = (double)gt_h / (double)H;
     const float* g = gt + (size_t)b * gt_h * gt_w;
     const float* p = pred + (size_t)b * n * pred_stride + pred_offset;
     int nv = 0, pnan = 0, gnan = 0;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        float gv;
-        if (resample) {   // cv2 INTER_NEAREST (utils/evaluate_depth_metrics.py:321-323)
-            const int y = i / W, x = i - y * W;
-            const int sx = min((int)floor(__dmul_rn((double)x, fx)), gt_w - 1);
-            const int sy = min((int)floor(__dmul_rn((double)y, fy)), gt_h - 1);
-            gv = __ldg(g + (size_t)sy * gt_w + sx);
-        } else {
-            gv = __ldg(g + i);
+    const int span = gridDim.x * kChunkThreads;
+    for (int i0 = blockIdx.x * kChunkThreads; i0 < n; i0 += span) {      // warp-uniform trip count
+        const int i = i0 + threadIdx.x;
+        bool ok = false;
+        float gv = 0.f, pv = 0.f;
+        if (i < n) {
+            if (resample) {   // cv2 INTER_NEAREST (utils/evaluate_depth_metrics.py:321-323)
+                const int y = i / W, x = i - y * W;
+                const int sx = min((int)floor(__dmul_rn((double)x, fx)), gt_w - 1);
+                const int sy = min((int)floor(__dmul_rn((double)y, fy)), gt_h - 1);
+                gv = __ldg(g + (size_t)sy * gt_w + sx);
+            } else {
+                gv = __ldg(g + i);
+            }
+            pv = __ldg(p + (size_t)i * pred_stride);
+            ok = mask ? (mask[(size_t)b * n + i] != 0) : (gv > 0.f && isfinite(gv));   // utils/metrics.py:27
+            vz[(size_t)b * n + i] = pv;
+            vg[(size_t)b * n + i] = ok ? gv : __int_as_float(0x7fc00000);
+            if (ok) { ++nv; pnan += isnan(pv); gnan += isnan(gv); }
         }
-        const float pv = __ldg(p + (size_t)i * pred_stride);
-        const bool ok = mask ? (mask[(size_t)b * n + i] != 0) : (gv > 0.f && isfinite(gv));   // utils/metrics.py:27
-        vz[(size_t)b * n + i] = pv;
-        vg[(size_t)b * n + i] = gv;
-        valid[(size_t)b * n + i] = ok ? 1 : 0;
-        if (ok) { ++nv; pnan += isnan(pv); gnan += isnan(gv); }
+        hist_add(sh[0], ok && !isnan(gv), t3d_select::float_key(gv) >> 21);
+        hist_add(sh[1], ok && !isnan(pv), t3d_select::float_key(pv) >> 21);
     }
     nv = __reduce_add_sync(0xffffffffu, nv);
     pnan = __reduce_add_sync(0xffffffffu, pnan);
@@ -83,67 +124,158 @@ depth_extract_kernel(const float* __restrict__ pred, int pred_stride, int pred_o
         if (pnan) atomicAdd(&counters[4 * b + 1], pnan);
         if (gnan) atomicAdd(&counters[4 * b + 2], gnan);
     }
+    __syncthreads();
+    unsigned int* gh = hist + (size_t)b * 4 * kSelBins;
+    merge_hist(sh[0], gh, kSelBins);                      // stream 0, target A
+    merge_hist(sh[1], gh + 2 * kSelBins, kSelBins);       // stream 1, target A
 }
 
-// ------------------------------------------------------------------ M2: medians -> scale
-// np.median of a float32 vector: mean of the two middle order statistics in fp32 (even n); NaN if any NaN.
-__device__ float median_of(t3d_select::Smem& sm, const float* __restrict__ v, const unsigned char* __restrict__ valid,
-                           int n, int n_valid, int n_nan) {
-    if (n_nan > 0) return __int_as_float(0x7fc00000);
-    auto get = [&](int i, float* out) { *out = v[i]; return valid[i] != 0; };
-    const unsigned int r0 = (unsigned)(n_valid - 1) / 2, r1 = (unsigned)n_valid / 2;
-    const float a = t3d_select::select_rank(sm, n, r0, get);
-    if (r1 == r0) return a;
-    const float b = t3d_select::select_rank(sm, n, r1, get);
-    return __fmul_rn(__fadd_rn(a, b), 0.5f);
+// ------------------------------------------------------------------ select: pick kernel (one CTA per image)
+// PASS 0/1/2 = after the histogram of bits [31:21] / [20:10] / [9:0].
+__device__ __forceinline__ void scan_pick(const unsigned int* __restrict__ gh, unsigned int* sbuf, unsigned int* wtot,
+                                          unsigned int rank, int nb, unsigned int* out_bin, unsigned int* out_rank) {
+    // 256 threads x 8 bins; deterministic prefix scan
+    const int tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
+    unsigned int loc[8], sum = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { loc[k] = (8 * tid + k < nb) ? gh[8 * tid + k] : 0u; sum += loc[k]; }
+    unsigned int incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const unsigned int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+    if (lane == 31) wtot[wrp] = incl;
+    __syncthreads();
+    if (tid == 0) { unsigned int a = 0; for (int w = 0; w < 8; ++w) { const unsigned int t = wtot[w]; wtot[w] = a; a += t; } }
+    __syncthreads();
+    unsigned int c = wtot[wrp] + incl - sum;
+    if (rank >= c && rank < c + sum) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            if (rank < c + loc[k]) { sbuf[0] = 8 * tid + k; sbuf[1] = rank - c; break; }
+            c += loc[k];
+        }
+    }
+    __syncthreads();
+    *out_bin = sbuf[0]; *out_rank = sbuf[1];
+    __syncthreads();
 }
 
-__global__ void __launch_bounds__(t3d_select::kThreads, 1)
-median_scale_kernel(const float* __restrict__ vz, const float* __restrict__ vg, const unsigned char* __restrict__ valid,
-                    const int* __restrict__ counters, int n, int median_scaling, float* __restrict__ scale,
-                    float* __restrict__ out_medians) {
-    __shared__ t3d_select::Smem sm;
+template <int PASS>
+__global__ void __launch_bounds__(256) select_pick_kernel(unsigned int* __restrict__ hist, SelState* __restrict__ state,
+                                                          const int* __restrict__ counters, int median_scaling,
+                                                          float* __restrict__ scale, float* __restrict__ out_medians) {
+    __shared__ unsigned int sbuf[2], wtot[8];
+    __shared__ float med[2];
     const int b = blockIdx.x;
     const int nv = counters[4 * b];
-    float s = 1.0f, mg = 0.f, mp = 0.f;
+    constexpr int SH = (PASS == 0) ? 21 : (PASS == 1 ? 10 : 0);
+    constexpr int NB = (PASS == 2) ? 1024 : 2048;
+    unsigned int* gh = hist + (size_t)b * 4 * kSelBins;
     if (nv > 0 && median_scaling) {
-        mg = median_of(sm, vg + (size_t)b * n, valid + (size_t)b * n, n, nv, counters[4 * b + 2]);
-        mp = median_of(sm, vz + (size_t)b * n, valid + (size_t)b * n, n, nv, counters[4 * b + 1]);
-        s = __fdiv_rn(mg, mp);                                   // utils/metrics.py:47
+        for (int s = 0; s < 2; ++s) {
+            SelState st = (PASS == 0) ? SelState{{0u, 0u}, {(unsigned)(nv - 1) / 2, (unsigned)nv / 2}} : state[2 * b + s];
+            if (counters[4 * b + (s == 0 ? 2 : 1)] > 0) continue;        // NaN in the stream -> median NaN
+            const bool shared_hist = (PASS == 0) || (st.prefix[0] == st.prefix[1]);
+            unsigned int bin, rk;
+            scan_pick(gh + (2 * s) * kSelBins, sbuf, wtot, st.rank[0], NB, &bin, &rk);
+            st.prefix[0] |= bin << SH; st.rank[0] = rk;
+            scan_pick(gh + (2 * s + (shared_hist ? 0 : 1)) * kSelBins, sbuf, wtot, st.rank[1], NB, &bin, &rk);
+            st.prefix[1] |= bin << SH; st.rank[1] = rk;
+            if (threadIdx.x == 0) {
+                state[2 * b + s] = st;
+                if (PASS == 2) {                                          // np.median: fp32 mean of the two middles
+                    const float a = t3d_select::key_float(st.prefix[0]), c = t3d_select::key_float(st.prefix[1]);
+                    med[s] = (st.prefix[0] == st.prefix[1]) ? a : __fmul_rn(__fadd_rn(a, c), 0.5f);
+                }
+            }
+        }
     }
-    if (threadIdx.x == 0) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < 4 * kSelBins; i += 256) gh[i] = 0u;     // ready for the next pass / next call
+    if (PASS == 2 && threadIdx.x == 0) {
+        float s = 1.0f, mg = 0.f, mp = 0.f;
+        if (nv > 0 && median_scaling) {
+            const float qnan = __int_as_float(0x7fc00000);
+            mg = counters[4 * b + 2] > 0 ? qnan : med[0];
+            mp = counters[4 * b + 1] > 0 ? qnan : med[1];
+            s = __fdiv_rn(mg, mp);                                        // utils/metrics.py:47
+        }
         scale[b] = s;
         if (out_medians) { out_medians[2 * b] = mg; out_medians[2 * b + 1] = mp; }
     }
+}
+
+// ------------------------------------------------------------------ select: histogram kernel for passes 1 and 2
+template <int PASS>
+__global__ void __launch_bounds__(kChunkThreads)
+select_hist_kernel(const float* __restrict__ vz, const float* __restrict__ vg, const SelState* __restrict__ state,
+                   const int* __restrict__ counters, int n, int median_scaling, unsigned int* __restrict__ hist) {
+    __shared__ unsigned int sh[4][kSelBins];
+    const int b = blockIdx.y;
+    if (!median_scaling || counters[4 * b] == 0) return;
+    constexpr int SH = (PASS == 1) ? 10 : 0;
+    constexpr unsigned int DM = (PASS == 1) ? 2047u : 1023u;
+    constexpr unsigned int FIXED = (PASS == 1) ? 0xffe00000u : 0xfffffc00u;
+    for (int i = threadIdx.x; i < 4 * kSelBins; i += kChunkThreads) (&sh[0][0])[i] = 0u;
+    const SelState sg = state[2 * b], sp = state[2 * b + 1];
+    const bool two_g = sg.prefix[0] != sg.prefix[1], two_p = sp.prefix[0] != sp.prefix[1];
+    __syncthreads();
+    const float* g = vg + (size_t)b * n;
+    const float* z = vz + (size_t)b * n;
+    const int span = gridDim.x * kChunkThreads;
+    for (int i0 = blockIdx.x * kChunkThreads; i0 < n; i0 += span) {
+        const int i = i0 + threadIdx.x;
+        float gv = __int_as_float(0x7fc00000), pv = 0.f;
+        if (i < n) { gv = __ldg(g + i); pv = __ldg(z + i); }
+        const bool ok = !isnan(gv);
+        const unsigned int kg = t3d_select::float_key(gv), kp = t3d_select::float_key(pv);
+        hist_add(sh[0], ok && (kg & FIXED) == sg.prefix[0], (kg >> SH) & DM);
+        if (two_g) hist_add(sh[1], ok && (kg & FIXED) == sg.prefix[1], (kg >> SH) & DM);
+        const bool okp = ok && !isnan(pv);
+        hist_add(sh[2], okp && (kp & FIXED) == sp.prefix[0], (kp >> SH) & DM);
+        if (two_p) hist_add(sh[3], okp && (kp & FIXED) == sp.prefix[1], (kp >> SH) & DM);
+    }
+    __syncthreads();
+    merge_hist(&sh[0][0], hist + (size_t)b * 4 * kSelBins, 4 * kSelBins);
 }
 
 // ------------------------------------------------------------------ M3: per-pixel terms
 __device__ __forceinline__ float np_maximum(float a, float b) { return (isnan(a) || isnan(b)) ? __int_as_float(0x7fc00000) : fmaxf(a, b); }
 
 __global__ void __launch_bounds__(kChunkThreads)
-metrics_sum_kernel(const float* __restrict__ vz, const float* __restrict__ vg, const unsigned char* __restrict__ valid,
+metrics_sum_kernel(const float* __restrict__ vz, const float* __restrict__ vg,
                    const float* __restrict__ scale, int n, int chunks, double* __restrict__ partials) {
     __shared__ double red[kChunkThreads / 32][kNPart];
     const int b = blockIdx.y, chunk = blockIdx.x;
     const float s = scale[b];
     const int per = (n + chunks - 1) / chunks;
     const int i0 = chunk * per, i1 = min(i0 + per, n);
+    float accf[4] = {0.f, 0.f, 0.f, 0.f};        // short fp32 runs (<= 16 terms) folded into fp64
     double acc[4] = {0, 0, 0, 0};
     int cnt[3] = {0, 0, 0};
+    int run = 0;
     for (int i = i0 + threadIdx.x; i < i1; i += kChunkThreads) {
-        if (!valid[(size_t)b * n + i]) continue;
-        const float gt = vg[(size_t)b * n + i];
-        const float pr = __fmul_rn(vz[(size_t)b * n + i], s);                    // pred *= scale   (:48)
-        const float th = np_maximum(__fdiv_rn(gt, pr), __fdiv_rn(pr, gt));       // :51
+        const float gt = __ldg(vg + (size_t)b * n + i);
+        if (isnan(gt)) continue;                                                 // invalid pixel marker
+        const float pr = __fmul_rn(__ldg(vz + (size_t)b * n + i), s);            // pred *= scale   (:48)
+        const float q = __fdiv_rn(gt, pr);
+        const float th = np_maximum(q, __fdiv_rn(pr, gt));                       // :51 (exact IEEE: counts are exact)
         cnt[0] += th < 1.25f; cnt[1] += th < 1.5625f; cnt[2] += th < 1.953125f;  // :52-54
         const float d = __fsub_rn(gt, pr);
         const float d2 = __fmul_rn(d, d);
-        acc[0] += (double)__fdiv_rn(fabsf(d), gt);                               // :56
-        acc[1] += (double)__fdiv_rn(d2, gt);                                     // :57
-        acc[2] += (double)d2;                                                    // :58
+        const float rg = __frcp_rn(gt);
+        accf[0] += fabsf(d) * rg;                                                // :56  |gt - pred| / gt
+        accf[1] += d2 * rg;                                                      // :57
+        accf[2] += d2;                                                           // :58
         const float dl = __fsub_rn(logf(gt), logf(pr));
-        acc[3] += (double)__fmul_rn(dl, dl);                                     // :59
+        accf[3] += dl * dl;                                                      // :59
+        if (++run == 16) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { acc[k] += (double)accf[k]; accf[k] = 0.f; }
+            run = 0;
+        }
     }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) acc[k] += (double)accf[k];
     double v[kNPart] = {acc[0], acc[1], acc[2], acc[3], (double)cnt[0], (double)cnt[1], (double)cnt[2], 0.0};
 #pragma unroll
     for (int k = 0; k < kNPart - 1; ++k) v[k] = warp_sum(v[k]);
@@ -172,6 +304,7 @@ __global__ void metrics_finalize_kernel(const double* __restrict__ partials, con
     for (int c = 0; c < chunks; ++c) s += partials[((size_t)b * chunks + c) * kNPart + k];
     const int nv = counters[4 * b];
     const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+    if (counters[4 * b + 2] > 0 && k < 4) s = qnan;                              // a selected NaN GT poisons every mean
     double r;
     if (k == 7) r = (double)nv;
     else if (nv == 0) r = (k < 4) ? qnan : 0.0;                                  // utils/metrics.py:34-43
@@ -300,13 +433,16 @@ int t3d_depth_metrics(const float* pred, int pred_stride, int pred_offset,
     MetricsWs w = metrics_ws(workspace, B, n, chunks);
     if (workspace_bytes < w.total) { t3d_set_error("workspace too small"); return T3D_ERR_WORKSPACE; }
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    T3D_CUDA(cudaMemsetAsync(w.counters, 0, (size_t)B * 4 * sizeof(int), st));
+    T3D_CUDA(cudaMemsetAsync(w.counters, 0, w.zero_bytes, st));     // counters + select histograms
     dim3 g((unsigned)chunks, (unsigned)B);
-    T3D_LAUNCH("depth_extract_kernel", st, depth_extract_kernel<<<g, kChunkThreads, 0, st>>>(pred, pred_stride, pred_offset, gt, gt_h, gt_w, mask, H, W,
-                                                      w.vz, w.vg, w.valid, w.counters));
-    T3D_LAUNCH("median_scale_kernel", st, median_scale_kernel<<<B, t3d_select::kThreads, 0, st>>>(w.vz, w.vg, w.valid, w.counters, n, median_scaling,
-                                                            w.scale, out_medians));
-    T3D_LAUNCH("metrics_sum_kernel", st, metrics_sum_kernel<<<g, kChunkThreads, 0, st>>>(w.vz, w.vg, w.valid, w.scale, n, chunks, w.partials));
+    T3D_LAUNCH("depth_extract_kernel", st, depth_extract_kernel<<<g, kChunkThreads, 0, st>>>(
+        pred, pred_stride, pred_offset, gt, gt_h, gt_w, mask, H, W, w.vz, w.vg, w.counters, w.hist));
+    T3D_LAUNCH("select_pick_kernel", st, select_pick_kernel<0><<<B, 256, 0, st>>>(w.hist, w.state, w.counters, median_scaling, w.scale, out_medians));
+    T3D_LAUNCH("select_hist_kernel", st, select_hist_kernel<1><<<g, kChunkThreads, 0, st>>>(w.vz, w.vg, w.state, w.counters, n, median_scaling, w.hist));
+    T3D_LAUNCH("select_pick_kernel", st, select_pick_kernel<1><<<B, 256, 0, st>>>(w.hist, w.state, w.counters, median_scaling, w.scale, out_medians));
+    T3D_LAUNCH("select_hist_kernel", st, select_hist_kernel<2><<<g, kChunkThreads, 0, st>>>(w.vz, w.vg, w.state, w.counters, n, median_scaling, w.hist));
+    T3D_LAUNCH("select_pick_kernel", st, select_pick_kernel<2><<<B, 256, 0, st>>>(w.hist, w.state, w.counters, median_scaling, w.scale, out_medians));
+    T3D_LAUNCH("metrics_sum_kernel", st, metrics_sum_kernel<<<g, kChunkThreads, 0, st>>>(w.vz, w.vg, w.scale, n, chunks, w.partials));
     T3D_LAUNCH("metrics_finalize_kernel", st, metrics_finalize_kernel<<<B, 32, 0, st>>>(w.partials, w.counters, chunks, out, out_f64));
     return T3D_OK;
 }
