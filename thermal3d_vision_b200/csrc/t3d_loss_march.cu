@@ -66,31 +66,38 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
 // ------------------------------------------------------------------ math
 struct Sums { float E, S, D; };
 
-// one forward-difference term; `valid == false` (zero-padded last column/row) contributes nothing
-__device__ __forceinline__ float q_term(bool valid, float za, float zb, float ga, float gb, float w, float omw,
+// NaN-propagating min / max (SASS FMNMX.NAN): torch.clamp lets NaN through, fminf/fmaxf would not
+__device__ __forceinline__ float min_nan(float a, float b) { float d; asm("min.NaN.f32 %0, %1, %2;" : "=f"(d) : "f"(a), "f"(b)); return d; }
+__device__ __forceinline__ float max_nan(float a, float b) { float d; asm("max.NaN.f32 %0, %1, %2;" : "=f"(d) : "f"(a), "f"(b)); return d; }
+
+// sgn(x) * |t-signed value|: (x > 0) ? t : (x < 0 ? -t : 0) with one compare (sgn(0) = 0 like ATen)
+__device__ __forceinline__ float times_sgn(float t, float x) {
+    const float r = __uint_as_float(__float_as_uint(t) ^ (__float_as_uint(x) & 0x80000000u));
+    return (x != 0.f) ? r : 0.f;
+}
+
+// one forward-difference term.  The zero-padded last column / row is expressed
+// by the caller handing in zb == za, gb == ga (all contributions vanish, sgn(0) = 0).
+__device__ __forceinline__ float q_term(float za, float zb, float ga, float gb, float w, float omw,
                                         float kE_omw, float kS2w, float kD, Sums& acc) {
-    zb = valid ? zb : za;
-    gb = valid ? gb : ga;
     const float s = zb - za;
     const float a = fabsf(s);
     const float b = fabsf(gb - ga);
     const float e = a - b;
     const float d = fabsf(e);
-    const bool quad = d < kHuber;                                         // strict (utils/loss.py:275)
+    const float c = fminf(d, kHuber);                                     // huber(d) = c^2/2 + delta (d - c)
     acc.E = fmaf(a, omw, acc.E);
     acc.S = fmaf(a * a, w, acc.S);
-    acc.D += quad ? 0.5f * d * d : fmaf(kHuber, d, -0.5f * kHuber * kHuber);
-    const float dh = quad ? e : copysignf(kHuber, e);                     // rho'(d) sgn(e)
+    acc.D += fmaf(0.5f * c, c, kHuber * (d - c));
+    const float dh = fminf(fmaxf(e, -kHuber), kHuber);                    // rho'(d) sgn(e)
     const float t = fmaf(kD, dh, fmaf(kS2w, a, kE_omw));
-    return (s > 0.f) ? t : ((s < 0.f) ? -t : 0.f);
+    return times_sgn(t, s);
 }
 
 __device__ __forceinline__ float edge_w(float tx, float ty, float inv_mx, float inv_my, float m) {
-    // exp(-8 clamp(tx/mean,0,m)) * exp(-8 clamp(ty/mean,0,m))  (utils/loss.py:240-256)
-    // tx, ty >= 0: the lower clamp is a no-op; the select form lets NaN through like torch.clamp
-    const float ax = tx * inv_mx, ay = ty * inv_my;
-    const float cx = (ax > m) ? m : ax;
-    const float cy = (ay > m) ? m : ay;
+    // exp(-8 clamp(tx/mean,0,m)) * exp(-8 clamp(ty/mean,0,m))  (utils/loss.py:240-256); tx, ty >= 0
+    const float cx = min_nan(tx * inv_mx, m);
+    const float cy = min_nan(ty * inv_my, m);
     return __expf(-8.0f * (cx + cy));
 }
 
@@ -111,11 +118,18 @@ __device__ __forceinline__ float gray_px(const float* __restrict__ th, int idx) 
     return (TCH == 3) ? gray3(th[idx], th[kSegPx + idx], th[2 * kSegPx + idx]) : th[idx];
 }
 
-__device__ __forceinline__ void load_aos_quad(const float* __restrict__ base, int idx, float v[12]) {
-    const float4* p = reinterpret_cast<const float4*>(base + idx * 3);
-    const float4 a = p[0], b = p[1], c = p[2];
-    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
-    v[8] = c.x; v[9] = c.y; v[10] = c.z; v[11] = c.w;
+struct RowRegs { float P[12], G[12], g[4]; };    // pred xyz, gt xyz (AoS order), gray of one lane's 4 pixels
+
+template <int TCH>
+__device__ __forceinline__ void load_row(const float* __restrict__ st, int idx, RowRegs& r) {
+    const float4* p = reinterpret_cast<const float4*>(st + Stage<TCH>::kPred + idx * 3);
+    const float4* q = reinterpret_cast<const float4*>(st + Stage<TCH>::kGt + idx * 3);
+    const float4 a = p[0], b = p[1], c = p[2], d = q[0], e = q[1], f = q[2];
+    r.P[0] = a.x; r.P[1] = a.y; r.P[2] = a.z; r.P[3] = a.w; r.P[4] = b.x; r.P[5] = b.y; r.P[6] = b.z; r.P[7] = b.w;
+    r.P[8] = c.x; r.P[9] = c.y; r.P[10] = c.z; r.P[11] = c.w;
+    r.G[0] = d.x; r.G[1] = d.y; r.G[2] = d.z; r.G[3] = d.w; r.G[4] = e.x; r.G[5] = e.y; r.G[6] = e.z; r.G[7] = e.w;
+    r.G[8] = f.x; r.G[9] = f.y; r.G[10] = f.z; r.G[11] = f.w;
+    gray_quad<TCH>(st + Stage<TCH>::kTh, idx, r.g);
 }
 
 // ------------------------------------------------------------------ kernel
@@ -138,6 +152,8 @@ __global__ void __launch_bounds__(WARPS * 32, 1) loss_march_kernel(const MarchAr
     const int H = a.H, W = a.W;
     const size_t plane = (size_t)H * W;
     const int ntasks = a.B * 2 * a.nbands * a.nstrips;
+    const float kE = a.kE, kS2 = 2.0f * a.kS, kD = a.kD, kb = a.kb, kc = a.kc, alpha = a.alpha;
+    const float alpha_ln2 = alpha * 0.69314718055994531f;
     uint32_t pos = 0;                                  // rows streamed so far by this warp (ring position)
 
     for (;;) {
@@ -160,14 +176,16 @@ __global__ void __launch_bounds__(WARPS * 32, 1) loss_march_kernel(const MarchAr
         const int j = col0 + 4 * lane;
         const bool active = 4 * lane < own_n;
         const bool last_lane = active && (4 * lane + 4 >= own_n);
+        const bool right_in_image = (j + 4 < W);
         const int idx = 4 * lane + off;                // smem pixel index of this lane's quad
 
         const float* __restrict__ pred = a.pred[view] + (size_t)b * plane * 3;
         const float* __restrict__ gt = a.gt[view] + (size_t)b * plane * 3;
         const float* __restrict__ conf = a.conf[view] ? a.conf[view] + (size_t)b * plane : nullptr;
         const float* __restrict__ th = a.thermal[view] + (size_t)b * TCH * plane;
-        float* __restrict__ dpred = BWD ? a.dpred[view] + (size_t)b * plane * 3 : nullptr;
-        float* __restrict__ dconf = (BWD && a.dconf[view]) ? a.dconf[view] + (size_t)b * plane : nullptr;
+        // running output pointers of this lane's quad (row i_lo; advanced by one row per iteration)
+        float* dp_ptr = BWD ? a.dpred[view] + ((size_t)b * plane + (size_t)i_lo * W + j) * 3 : nullptr;
+        float* dc_ptr = (BWD && a.dconf[view]) ? a.dconf[view] + (size_t)b * plane + (size_t)i_lo * W + j : nullptr;
 
         // 1 / (mean + eps) of |Dx gray|, |Dy gray| of this image: fixed-order sum of the stats partials
         float inv_mx, inv_my;
@@ -180,6 +198,8 @@ __global__ void __launch_bounds__(WARPS * 32, 1) loss_march_kernel(const MarchAr
             inv_mx = 1.0f / (sx * invN + kEps);
             inv_my = 1.0f / (sy * invN + kEps);
         }
+        // NaN / Inf thermal pixels make the reference loss NaN (clamp(NaN) = NaN): poison the task's sums
+        const bool thermal_bad = !(inv_mx > 0.f && inv_mx <= 1.0e5f && inv_my > 0.f && inv_my <= 1.0e5f);
         const float m = (view == 0) ? 0.4f : 0.5f;       // utils/loss.py:253-256
         const uint32_t row_bytes = (uint32_t)npx * (24u + 4u * TCH) + (conf ? (uint32_t)own_n * 4u : 0u);
 
@@ -207,109 +227,51 @@ __global__ void __launch_bounds__(WARPS * 32, 1) loss_march_kernel(const MarchAr
             for (int ri = 0; ri < pre; ++ri) issue_row(ri);
         }
 
-        // current row state (registers)
-        float cP[12], cG[12], cg[4];
-        wait_row(0);
-        {
-            const float* st = stage_of(0);
-            if (active) {
-                load_aos_quad(st + St::kPred, idx, cP);
-                load_aos_quad(st + St::kGt, idx, cG);
-                gray_quad<TCH>(st + St::kTh, idx, cg);
-            } else {
-#pragma unroll
-                for (int e = 0; e < 12; ++e) { cP[e] = 0.f; cG[e] = 0.f; }
-                cg[0] = cg[1] = cg[2] = cg[3] = 0.f;
-            }
-        }
         float qy_prev[4] = {0.f, 0.f, 0.f, 0.f};
         float sum_b = 0.f;
         Sums tot = {0.f, 0.f, 0.f};
 
-        const int n_cur = rb - i_lo;                      // rows that are "current" at some iteration
-        for (int ri = 0; ri < n_cur; ++ri) {
+        // one row: `cur` holds row r, `nxt` receives row r+1 (read once from the ring, current next time)
+        auto step = [&](RowRegs& cur, RowRegs& nxt, int ri) {
             const int r = i_lo + ri;
             const bool own = r >= ra;
             const bool has_below = r + 1 < H;
             const float* st = stage_of(ri);
-            float nP[12], nG[12], ng[4];
-            const float* stn = nullptr;
+            const float* stn = st;
             if (has_below) {
                 wait_row(ri + 1);
                 stn = stage_of(ri + 1);
-                if (active) {
-                    load_aos_quad(stn + St::kPred, idx, nP);
-                    load_aos_quad(stn + St::kGt, idx, nG);
-                    gray_quad<TCH>(stn + St::kTh, idx, ng);
-                }
-            }
-            if (!has_below || !active) {
+                load_row<TCH>(stn, idx, nxt);
+            } else {                                      // zero-padded last image row: dy == 0
 #pragma unroll
-                for (int e = 0; e < 12; ++e) { nP[e] = 0.f; nG[e] = 0.f; }
-                ng[0] = ng[1] = ng[2] = ng[3] = 0.f;
+                for (int e = 0; e < 4; ++e) { nxt.P[3 * e + 2] = cur.P[3 * e + 2]; nxt.G[3 * e + 2] = cur.G[3 * e + 2]; nxt.g[e] = cur.g[e]; }
             }
 
-            // ---- basic term (own rows only): utils/loss.py:81-98
-            float gq[12];
-#pragma unroll
-            for (int e = 0; e < 12; ++e) gq[e] = 0.f;
-            if (own && active) {
-                float c[4] = {1.f, 1.f, 1.f, 1.f};
-                if (conf) {
-                    const float4 cc = *reinterpret_cast<const float4*>(st + St::kConf + 4 * lane);
-                    c[0] = cc.x; c[1] = cc.y; c[2] = cc.z; c[3] = cc.w;
-                }
-                float dc[4];
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const float dx = cP[3 * e] - cG[3 * e], dy = cP[3 * e + 1] - cG[3 * e + 1],
-                                dz = cP[3 * e + 2] - cG[3 * e + 2];
-                    const float l = ((fabsf(dx) + fabsf(dy)) + fabsf(dz)) * (1.0f / 3.0f);
-                    const float craw = c[e];
-                    const float cc = (craw < kConfMin) ? kConfMin : ((craw > kConfMax) ? kConfMax : craw);  // NaN passes
-                    sum_b += fmaf(cc, l, -a.alpha * __logf(cc));
-                    if (BWD) {
-                        const float k3 = cc * a.kb;
-                        gq[3 * e] = (dx > 0.f) ? k3 : ((dx < 0.f) ? -k3 : 0.f);
-                        gq[3 * e + 1] = (dy > 0.f) ? k3 : ((dy < 0.f) ? -k3 : 0.f);
-                        gq[3 * e + 2] = (dz > 0.f) ? k3 : ((dz < 0.f) ? -k3 : 0.f);
-                        const bool inside = (craw >= kConfMin) && (craw <= kConfMax);
-                        dc[e] = inside ? (l - __fdividef(a.alpha, cc)) * a.kc : 0.f;
-                    }
-                }
-                if (BWD && dconf) stg_stream_f4(dconf + (size_t)r * W + j, make_float4(dc[0], dc[1], dc[2], dc[3]));
+            // ---- horizontal neighbours of the current row (zero-padded last column: dx == 0)
+            float zr = __shfl_down_sync(0xffffffffu, cur.P[2], 1);
+            float gzr = __shfl_down_sync(0xffffffffu, cur.G[2], 1);
+            float gr = __shfl_down_sync(0xffffffffu, cur.g[0], 1);
+            if (last_lane) {
+                if (right_in_image) {                     // the strip's right halo pixel
+                    zr = st[St::kPred + (idx + 4) * 3 + 2];
+                    gzr = st[St::kGt + (idx + 4) * 3 + 2];
+                    gr = gray_px<TCH>(st + St::kTh, idx + 4);
+                } else { zr = cur.P[11]; gzr = cur.G[11]; gr = cur.g[3]; }
             }
+            const float zx[5] = {cur.P[2], cur.P[5], cur.P[8], cur.P[11], zr};
+            const float gzx[5] = {cur.G[2], cur.G[5], cur.G[8], cur.G[11], gzr};
+            const float gx[5] = {cur.g[0], cur.g[1], cur.g[2], cur.g[3], gr};
 
-            // ---- horizontal neighbours of the current row
-            const float cz[4] = {cP[2], cP[5], cP[8], cP[11]};
-            const float cgz[4] = {cG[2], cG[5], cG[8], cG[11]};
-            float zr = __shfl_down_sync(0xffffffffu, cz[0], 1);
-            float gzr = __shfl_down_sync(0xffffffffu, cgz[0], 1);
-            float gr = __shfl_down_sync(0xffffffffu, cg[0], 1);
-            if (last_lane && (j + 4 < W)) {               // right neighbour lives in the strip's halo
-                zr = st[St::kPred + (idx + 4) * 3 + 2];
-                gzr = st[St::kGt + (idx + 4) * 3 + 2];
-                gr = gray_px<TCH>(st + St::kTh, idx + 4);
-            }
-            const float zx[5] = {cz[0], cz[1], cz[2], cz[3], zr};
-            const float gzx[5] = {cgz[0], cgz[1], cgz[2], cgz[3], gzr};
-            const float gx[5] = {cg[0], cg[1], cg[2], cg[3], gr};
-            const float nz[4] = {nP[2], nP[5], nP[8], nP[11]};
-            const float ngz[4] = {nG[2], nG[5], nG[8], nG[11]};
-
-            // ---- edge weights, q terms
+            // ---- edge weights, q terms (each exactly once)
             Sums acc = {0.f, 0.f, 0.f};
             float qx[4], qy[4];
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-                const bool vx = (j + e) < W - 1;
-                const float tx = vx ? fabsf(gx[e + 1] - gx[e]) : 0.f;
-                const float ty = has_below ? fabsf(ng[e] - cg[e]) : 0.f;
-                const float w = edge_w(tx, ty, inv_mx, inv_my, m);
+                const float w = edge_w(fabsf(gx[e + 1] - gx[e]), fabsf(nxt.g[e] - gx[e]), inv_mx, inv_my, m);
                 const float omw = 1.0f - w;
-                const float kE_omw = a.kE * omw, kS2w = 2.0f * a.kS * w;
-                qx[e] = q_term(vx, zx[e], zx[e + 1], gzx[e], gzx[e + 1], w, omw, kE_omw, kS2w, a.kD, acc);
-                qy[e] = q_term(has_below, zx[e], nz[e], gzx[e], ngz[e], w, omw, kE_omw, kS2w, a.kD, acc);
+                const float kE_omw = kE * omw, kS2w = kS2 * w;
+                qx[e] = q_term(zx[e], zx[e + 1], gzx[e], gzx[e + 1], w, omw, kE_omw, kS2w, kD, acc);
+                qy[e] = q_term(zx[e], nxt.P[3 * e + 2], gzx[e], nxt.G[3 * e + 2], w, omw, kE_omw, kS2w, kD, acc);
             }
             // q_x of the pixel left of this quad
             float qxl = __shfl_up_sync(0xffffffffu, qx[3], 1);
@@ -319,40 +281,73 @@ __global__ void __launch_bounds__(WARPS * 32, 1) loss_march_kernel(const MarchAr
                     const float zl = st[St::kPred + (idx - 1) * 3 + 2];
                     const float gzl = st[St::kGt + (idx - 1) * 3 + 2];
                     const float gl = gray_px<TCH>(st + St::kTh, idx - 1);
-                    const float tyl = has_below ? fabsf(gray_px<TCH>(stn + St::kTh, idx - 1) - gl) : 0.f;
-                    const float wl = edge_w(fabsf(cg[0] - gl), tyl, inv_mx, inv_my, m);
+                    const float gln = has_below ? gray_px<TCH>(stn + St::kTh, idx - 1) : gl;
+                    const float wl = edge_w(fabsf(gx[0] - gl), fabsf(gln - gl), inv_mx, inv_my, m);
                     const float omw = 1.0f - wl;
                     Sums dummy = {0.f, 0.f, 0.f};
-                    qxl = q_term(true, zl, cz[0], gzl, cgz[0], wl, omw, a.kE * omw, 2.0f * a.kS * wl, a.kD, dummy);
+                    qxl = q_term(zl, zx[0], gzl, gzx[0], wl, omw, kE * omw, kS2 * wl, kD, dummy);
                 }
             }
-            if (own && active) {
+
+            if (own) {
                 tot.E += acc.E; tot.S += acc.S; tot.D += acc.D;
-                if (BWD) {
-                    gq[2] += -qx[0] + qxl - qy[0] + qy_prev[0];
-                    gq[5] += -qx[1] + qx[0] - qy[1] + qy_prev[1];
-                    gq[8] += -qx[2] + qx[1] - qy[2] + qy_prev[2];
-                    gq[11] += -qx[3] + qx[2] - qy[3] + qy_prev[3];
-                    float* o = dpred + ((size_t)r * W + j) * 3;
-                    stg_stream_f4(o, make_float4(gq[0], gq[1], gq[2], gq[3]));
-                    stg_stream_f4(o + 4, make_float4(gq[4], gq[5], gq[6], gq[7]));
-                    stg_stream_f4(o + 8, make_float4(gq[8], gq[9], gq[10], gq[11]));
+                // ---- basic term: utils/loss.py:81-98
+                float c[4] = {1.f, 1.f, 1.f, 1.f};
+                if (conf) {
+                    const float4 cc = *reinterpret_cast<const float4*>(st + St::kConf + 4 * lane);
+                    c[0] = cc.x; c[1] = cc.y; c[2] = cc.z; c[3] = cc.w;
+                }
+                const float dzs[4] = {-qx[0] + qxl - qy[0] + qy_prev[0], -qx[1] + qx[0] - qy[1] + qy_prev[1],
+                                      -qx[2] + qx[1] - qy[2] + qy_prev[2], -qx[3] + qx[2] - qy[3] + qy_prev[3]};
+                float gq[12], dc[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const float dx = cur.P[3 * e] - cur.G[3 * e], dy = cur.P[3 * e + 1] - cur.G[3 * e + 1],
+                                dz = cur.P[3 * e + 2] - cur.G[3 * e + 2];
+                    const float l = ((fabsf(dx) + fabsf(dy)) + fabsf(dz)) * (1.0f / 3.0f);
+                    const float craw = c[e];
+                    const float cc = min_nan(max_nan(craw, kConfMin), kConfMax);
+                    sum_b += fmaf(cc, l, -alpha_ln2 * __log2f(cc));
+                    if (BWD) {
+                        const float k3 = cc * kb;
+                        gq[3 * e] = times_sgn(k3, dx);
+                        gq[3 * e + 1] = times_sgn(k3, dy);
+                        gq[3 * e + 2] = times_sgn(k3, dz) + dzs[e];
+                        const bool inside = (craw >= kConfMin) && (craw <= kConfMax);
+                        dc[e] = inside ? (l - __fdividef(alpha, cc)) * kc : 0.f;
+                    }
+                }
+                if (BWD && active) {
+                    if (dc_ptr) stg_stream_f4(dc_ptr, make_float4(dc[0], dc[1], dc[2], dc[3]));
+                    stg_stream_f4(dp_ptr, make_float4(gq[0], gq[1], gq[2], gq[3]));
+                    stg_stream_f4(dp_ptr + 4, make_float4(gq[4], gq[5], gq[6], gq[7]));
+                    stg_stream_f4(dp_ptr + 8, make_float4(gq[8], gq[9], gq[10], gq[11]));
                 }
             }
+            if (BWD) { dp_ptr += (size_t)W * 3; if (dc_ptr) dc_ptr += W; }
 #pragma unroll
-            for (int e = 0; e < 4; ++e) { qy_prev[e] = qy[e]; cg[e] = ng[e]; }
-#pragma unroll
-            for (int e = 0; e < 12; ++e) { cP[e] = nP[e]; cG[e] = nG[e]; }
+            for (int e = 0; e < 4; ++e) qy_prev[e] = qy[e];
 
             __syncwarp();                                 // every lane is done reading stage(ri)
             if (lane == 0 && ri + NS < n_rows) issue_row(ri + NS);
+        };
+
+        RowRegs A, Bq;
+        wait_row(0);
+        load_row<TCH>(stage_of(0), idx, A);
+        const int n_cur = rb - i_lo;                      // rows that are "current" at some iteration
+        for (int ri = 0; ri < n_cur; ri += 2) {           // ping-pong the two register sets: no row copies
+            step(A, Bq, ri);
+            if (ri + 1 < n_cur) step(Bq, A, ri + 1);
         }
         pos += (uint32_t)n_rows;
 
-        // ---- per-task partial sums (fixed butterfly: deterministic)
+        // ---- per-task partial sums (fixed butterfly: deterministic); inactive lanes hold garbage
+        if (!active) { sum_b = 0.f; tot.E = 0.f; tot.S = 0.f; tot.D = 0.f; }
         sum_b = warp_sum(sum_b);
         tot.E = warp_sum(tot.E); tot.S = warp_sum(tot.S); tot.D = warp_sum(tot.D);
         if (lane == 0) {
+            if (thermal_bad) tot.E = __int_as_float(0x7fc00000);
             float4* o = reinterpret_cast<float4*>(a.partials + (size_t)task * 8);
             o[0] = make_float4(sum_b, tot.E, tot.S, tot.D);
             o[1] = make_float4(0.f, 0.f, 0.f, 0.f);
