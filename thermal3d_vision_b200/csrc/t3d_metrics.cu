@@ -19,25 +19,25 @@ namespace {
 constexpr int kChunkThreads = 256;
 constexpr int kNPart = 8;   // abs_rel, sq_rel, sq, log2, a1, a2, a3, (pad)
 
-// Batched exact medians: multi-CTA 3-pass radix select (11 + 11 + 10 bits of the monotone key).
-// Two streams per image (0 = gt, 1 = pred) and two targets per stream (A = rank (n-1)/2, B = rank n/2;
-// np.median averages them).  Histogram kernels run on (chunks x B) CTAs with shared-memory histograms
-// and warp-aggregated atomics; tiny pick kernels scan the merged histograms between passes.
-constexpr int kSelBins = 2048;
-
-struct SelState {           // per (image, stream)
-    unsigned int prefix[2]; // selected high bits of target A / B
-    unsigned int rank[2];   // remaining rank inside the prefix
-};
+// Batched exact medians in two passes over the data (np.median, utils/metrics.py:47):
+//   S  sample 4096 valid pixels per image, sort them in shared memory, and bracket the median of each
+//      stream (0 = gt, 1 = pred) by two sample order statistics 5 sigma apart;
+//   X  the extraction pass (the only full read of the AoS pointmap) counts the elements below the bracket
+//      and collects the few percent that fall inside it;
+//   M  one CTA per image selects the exact middle order statistics among the candidates (radix select in
+//      shared memory).  If a bracket misses (probability ~1e-6, or degenerate data) that image falls back
+//      to a full 3-pass radix select over the planar copies -- slower, same exact result.
+constexpr int kSample = 4096;
+constexpr int kCandCap = 32768;     // candidates per (image, stream)
+constexpr int kCtaCand = 768;       // candidates per CTA per stream staged in shared memory
 
 struct MetricsWs {
     float* vz; float* vg;
-    int* counters;          // [B][4]: n_valid, pred_nan, gt_nan, pad
-    unsigned int* hist;     // [B][2 streams][2 targets][kSelBins]
-    SelState* state;        // [B][2]
+    int* counters;          // [B][8]: n_valid, pred_nan, gt_nan, fallback, lt_g, lt_p, ncand_g, ncand_p
+    unsigned int* bracket;  // [B][2 streams][2]: lo key, hi key (inclusive); lo > hi = no bracket
+    unsigned int* cand;     // [B][2][kCandCap] keys
     float* scale;           // [B]
     double* partials;       // [B][chunks][kNPart]
-    size_t zero_bytes;      // counters + hist are contiguous: one memset
     size_t total;
 };
 
@@ -46,12 +46,11 @@ MetricsWs metrics_ws(void* base, int B, int n, int chunks) {
     size_t off = 0;
     char* p = reinterpret_cast<char*>(base);
     auto take = [&](size_t bytes) { char* r = p ? p + off : nullptr; off += t3d_align_up(bytes, 256); return r; };
-    w.counters = reinterpret_cast<int*>(take((size_t)B * 4 * sizeof(int)));
-    w.hist = reinterpret_cast<unsigned int*>(take((size_t)B * 4 * kSelBins * sizeof(unsigned int)));
-    w.zero_bytes = off;
+    w.counters = reinterpret_cast<int*>(take((size_t)B * 8 * sizeof(int)));
+    w.bracket = reinterpret_cast<unsigned int*>(take((size_t)B * 4 * sizeof(unsigned int)));
     w.vz = reinterpret_cast<float*>(take((size_t)B * n * 4));
     w.vg = reinterpret_cast<float*>(take((size_t)B * n * 4));
-    w.state = reinterpret_cast<SelState*>(take((size_t)B * 2 * sizeof(SelState)));
+    w.cand = reinterpret_cast<unsigned int*>(take((size_t)B * 2 * kCandCap * sizeof(unsigned int)));
     w.scale = reinterpret_cast<float*>(take((size_t)B * sizeof(float)));
     w.partials = reinterpret_cast<double*>(take((size_t)B * chunks * kNPart * sizeof(double)));
     w.total = off;
@@ -60,186 +59,238 @@ MetricsWs metrics_ws(void* base, int B, int n, int chunks) {
 
 int chunks_for(int n) { return max(1, min(96, (n + 4095) / 4096)); }
 
-// one shared-memory histogram increment, aggregated over the lanes of the warp that hit the same bin
-// (depth values crowd into a few exponent bins: without aggregation same-address atomics serialise)
-__device__ __forceinline__ void hist_add(unsigned int* h, bool on, unsigned int bin) {
-    const unsigned int key = on ? bin : 0xffffffffu;
-    const unsigned int peers = __match_any_sync(0xffffffffu, key);
-    if (on && (threadIdx.x & 31) == (unsigned)(__ffs(peers) - 1)) atomicAdd(&h[bin], (unsigned)__popc(peers));
+struct PixelSrc {            // how to read (gt, pred, valid) of pixel i of image b
+    const float* pred; const float* gt; const unsigned char* mask;
+    int pred_stride, gt_h, gt_w, H, W, resample;
+    double fx, fy;
+};
+
+__device__ __forceinline__ void read_pixel(const PixelSrc& s, const float* __restrict__ g, const float* __restrict__ p,
+                                           const unsigned char* __restrict__ m, int i, float& gv, float& pv, bool& ok) {
+    if (s.resample) {   // cv2 INTER_NEAREST (utils/evaluate_depth_metrics.py:321-323)
+        const int y = i / s.W, x = i - y * s.W;
+        const int sx = min((int)floor(__dmul_rn((double)x, s.fx)), s.gt_w - 1);
+        const int sy = min((int)floor(__dmul_rn((double)y, s.fy)), s.gt_h - 1);
+        gv = __ldg(g + (size_t)sy * s.gt_w + sx);
+    } else {
+        gv = __ldg(g + i);
+    }
+    pv = __ldg(p + (size_t)i * s.pred_stride);
+    ok = m ? (m[i] != 0) : (gv > 0.f && isfinite(gv));     // utils/metrics.py:27
 }
 
-__device__ __forceinline__ void merge_hist(const unsigned int* sh, unsigned int* gh, int count) {
-    for (int i = threadIdx.x; i < count; i += blockDim.x) {
-        const unsigned int v = sh[i];
-        if (v) atomicAdd(&gh[i], v);
+// ------------------------------------------------------------------ S: sample + bracket
+__global__ void __launch_bounds__(1024, 1) metrics_sample_kernel(const PixelSrc s, int pred_offset,
+                                                                 unsigned int* __restrict__ bracket) {
+    __shared__ unsigned int key[2][kSample];
+    __shared__ int cnt[2];
+    const int b = blockIdx.x, tid = threadIdx.x, n = s.H * s.W;
+    const float* g = s.gt + (size_t)b * s.gt_h * s.gt_w;
+    const float* p = s.pred + (size_t)b * n * s.pred_stride + pred_offset;
+    const unsigned char* m = s.mask ? s.mask + (size_t)b * n : nullptr;
+    if (tid < 2) cnt[tid] = 0;
+    __syncthreads();
+    int c0 = 0, c1 = 0;
+#pragma unroll
+    for (int q = 0; q < kSample / 1024; ++q) {
+        const int k = q * 1024 + tid;
+        // n >= kSample: evenly strided distinct pixels; smaller images: every pixel exactly once
+        const int i = (n >= kSample) ? (int)(((long long)k * n) / kSample) : k;
+        unsigned int kg = 0xffffffffu, kp = 0xffffffffu;          // sentinel sorts last
+        if (i < n) {
+            float gv, pv; bool ok;
+            read_pixel(s, g, p, m, i, gv, pv, ok);
+            if (ok && !isnan(gv)) { kg = t3d_select::float_key(gv); ++c0; }
+            if (ok && !isnan(pv)) { kp = t3d_select::float_key(pv); ++c1; }
+        }
+        key[0][k] = kg; key[1][k] = kp;
+    }
+    c0 = __reduce_add_sync(0xffffffffu, c0); c1 = __reduce_add_sync(0xffffffffu, c1);
+    if ((tid & 31) == 0) { atomicAdd(&cnt[0], c0); atomicAdd(&cnt[1], c1); }
+    __syncthreads();
+    // bitonic sort of both arrays (ascending), 2048 compare-exchanges per stage per array
+    for (int size = 2; size <= kSample; size <<= 1) {
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+#pragma unroll
+            for (int q = 0; q < kSample / 2048; ++q) {
+                const int t = q * 1024 + tid;
+                const int lo = 2 * t - (t & (stride - 1));       // index with bit `stride` clear
+                const int hi = lo + stride;
+                const bool up = (lo & size) == 0;
+#pragma unroll
+                for (int a = 0; a < 2; ++a) {
+                    const unsigned int x = key[a][lo], y = key[a][hi];
+                    if ((x > y) == up) { key[a][lo] = y; key[a][hi] = x; }
+                }
+            }
+            __syncthreads();
+        }
+    }
+    if (tid < 2) {
+        const int mm = cnt[tid];
+        unsigned int lo = 1u, hi = 0u;                             // no bracket -> fallback
+        if (mm >= 64) {
+            const int d = (int)ceilf(2.5f * sqrtf((float)mm)) + 2; // +-5 sigma of the sample-median rank
+            const int mid = mm / 2;
+            const int rl = mid - d, rh = mid + d;
+            lo = (rl <= 0) ? 0u : key[tid][rl];
+            hi = (rh >= mm - 1) ? 0xfffffffeu : key[tid][rh];
+        }
+        bracket[4 * b + 2 * tid] = lo; bracket[4 * b + 2 * tid + 1] = hi;
     }
 }
 
-// ------------------------------------------------------------------ M1: extract (K5) + first select pass
+// ------------------------------------------------------------------ X: extract (K5) + count + collect
 // pred element (b, i) lives at pred[(b*n + i) * pred_stride + pred_offset]: stride 3 / offset 2 reads
 // the Z channel of an AoS pointmap in place (depth is never materialised by the caller).
 // Invalid pixels are stored as vg = NaN (a *selected* NaN GT makes every metric NaN anyway: gt_nan counter).
 __global__ void __launch_bounds__(kChunkThreads)
-depth_extract_kernel(const float* __restrict__ pred, int pred_stride, int pred_offset,
-                     const float* __restrict__ gt, int gt_h, int gt_w, const unsigned char* __restrict__ mask,
-                     int H, int W, float* __restrict__ vz, float* __restrict__ vg,
-                     int* __restrict__ counters, unsigned int* __restrict__ hist) {
-    __shared__ unsigned int sh[2][kSelBins];
-    const int b = blockIdx.y, n = H * W;
-    for (int i = threadIdx.x; i < 2 * kSelBins; i += kChunkThreads) (&sh[0][0])[i] = 0u;
+depth_extract_kernel(const PixelSrc s, int pred_offset, float* __restrict__ vz, float* __restrict__ vg,
+                     int* __restrict__ counters, const unsigned int* __restrict__ bracket,
+                     unsigned int* __restrict__ cand) {
+    __shared__ unsigned int scand[2][kCtaCand];
+    __shared__ int scount[2], sbase[2];
+    const int b = blockIdx.y, n = s.H * s.W, tid = threadIdx.x, lane = tid & 31;
+    const float* g = s.gt + (size_t)b * s.gt_h * s.gt_w;
+    const float* p = s.pred + (size_t)b * n * s.pred_stride + pred_offset;
+    const unsigned char* m = s.mask ? s.mask + (size_t)b * n : nullptr;
+    const unsigned int lo_g = bracket[4 * b], hi_g = bracket[4 * b + 1], lo_p = bracket[4 * b + 2], hi_p = bracket[4 * b + 3];
+    if (tid < 2) scount[tid] = 0;
     __syncthreads();
-    const bool resample = (gt_h != H) || (gt_w != W);
-    const double fx = (double)gt_w / (double)W, fy = (double)gt_h / (double)H;
-    const float* g = gt + (size_t)b * gt_h * gt_w;
-    const float* p = pred + (size_t)b * n * pred_stride + pred_offset;
-    int nv = 0, pnan = 0, gnan = 0;
-    const int span = gridDim.x * kChunkThreads;
-    for (int i0 = blockIdx.x * kChunkThreads; i0 < n; i0 += span) {      // warp-uniform trip count
-        const int i = i0 + threadIdx.x;
-        bool ok = false;
-        float gv = 0.f, pv = 0.f;
-        if (i < n) {
-            if (resample) {   // cv2 INTER_NEAREST (utils/evaluate_depth_metrics.py:321-323)
-                const int y = i / W, x = i - y * W;
-                const int sx = min((int)floor(__dmul_rn((double)x, fx)), gt_w - 1);
-                const int sy = min((int)floor(__dmul_rn((double)y, fy)), gt_h - 1);
-                gv = __ldg(g + (size_t)sy * gt_w + sx);
-            } else {
-                gv = __ldg(g + i);
-            }
-            pv = __ldg(p + (size_t)i * pred_stride);
-            ok = mask ? (mask[(size_t)b * n + i] != 0) : (gv > 0.f && isfinite(gv));   // utils/metrics.py:27
-            vz[(size_t)b * n + i] = pv;
-            vg[(size_t)b * n + i] = ok ? gv : __int_as_float(0x7fc00000);
-            if (ok) { ++nv; pnan += isnan(pv); gnan += isnan(gv); }
+    int nv = 0, pnan = 0, gnan = 0, lt_g = 0, lt_p = 0;
+    const int per = (n + gridDim.x - 1) / gridDim.x;
+    const int i_begin = blockIdx.x * per, i_end = min(i_begin + per, n);
+    constexpr int U = 4;
+    for (int i0 = i_begin; i0 < i_end; i0 += U * kChunkThreads) {          // warp-uniform trip count
+        float gv[U], pv[U]; bool ok[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {                                      // all loads first (MLP)
+            const int i = i0 + u * kChunkThreads + tid;
+            gv[u] = 0.f; pv[u] = 0.f; ok[u] = false;
+            if (i < i_end) read_pixel(s, g, p, m, i, gv[u], pv[u], ok[u]);
         }
-        hist_add(sh[0], ok && !isnan(gv), t3d_select::float_key(gv) >> 21);
-        hist_add(sh[1], ok && !isnan(pv), t3d_select::float_key(pv) >> 21);
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int i = i0 + u * kChunkThreads + tid;
+            if (i < i_end) {
+                vz[(size_t)b * n + i] = pv[u];
+                vg[(size_t)b * n + i] = ok[u] ? gv[u] : __int_as_float(0x7fc00000);
+            }
+            const bool okg = ok[u] && !isnan(gv[u]), okp = ok[u] && !isnan(pv[u]);
+            nv += ok[u]; pnan += ok[u] && isnan(pv[u]); gnan += ok[u] && isnan(gv[u]);
+            const unsigned int kg = t3d_select::float_key(gv[u]), kp = t3d_select::float_key(pv[u]);
+            lt_g += okg && kg < lo_g; lt_p += okp && kp < lo_p;
+            const bool in_g = okg && kg >= lo_g && kg <= hi_g, in_p = okp && kp >= lo_p && kp <= hi_p;
+            // warp-aggregated append to the CTA's candidate lists
+            const unsigned int mg = __ballot_sync(0xffffffffu, in_g), mp = __ballot_sync(0xffffffffu, in_p);
+            if (mg) {
+                int base = 0;
+                if (lane == 0) base = atomicAdd(&scount[0], __popc(mg));
+                base = __shfl_sync(0xffffffffu, base, 0);
+                const int slot = base + __popc(mg & ((1u << lane) - 1));
+                if (in_g && slot < kCtaCand) scand[0][slot] = kg;
+            }
+            if (mp) {
+                int base = 0;
+                if (lane == 0) base = atomicAdd(&scount[1], __popc(mp));
+                base = __shfl_sync(0xffffffffu, base, 0);
+                const int slot = base + __popc(mp & ((1u << lane) - 1));
+                if (in_p && slot < kCtaCand) scand[1][slot] = kp;
+            }
+        }
     }
-    nv = __reduce_add_sync(0xffffffffu, nv);
-    pnan = __reduce_add_sync(0xffffffffu, pnan);
+    nv = __reduce_add_sync(0xffffffffu, nv); pnan = __reduce_add_sync(0xffffffffu, pnan);
     gnan = __reduce_add_sync(0xffffffffu, gnan);
-    if ((threadIdx.x & 31) == 0) {
-        if (nv) atomicAdd(&counters[4 * b], nv);
-        if (pnan) atomicAdd(&counters[4 * b + 1], pnan);
-        if (gnan) atomicAdd(&counters[4 * b + 2], gnan);
+    lt_g = __reduce_add_sync(0xffffffffu, lt_g); lt_p = __reduce_add_sync(0xffffffffu, lt_p);
+    int* c = counters + 8 * b;
+    if (lane == 0) {
+        if (nv) atomicAdd(&c[0], nv);
+        if (pnan) atomicAdd(&c[1], pnan);
+        if (gnan) atomicAdd(&c[2], gnan);
+        if (lt_g) atomicAdd(&c[4], lt_g);
+        if (lt_p) atomicAdd(&c[5], lt_p);
     }
     __syncthreads();
-    unsigned int* gh = hist + (size_t)b * 4 * kSelBins;
-    merge_hist(sh[0], gh, kSelBins);                      // stream 0, target A
-    merge_hist(sh[1], gh + 2 * kSelBins, kSelBins);       // stream 1, target A
-}
-
-// ------------------------------------------------------------------ select: pick kernel (one CTA per image)
-// PASS 0/1/2 = after the histogram of bits [31:21] / [20:10] / [9:0].
-__device__ __forceinline__ void scan_pick(const unsigned int* __restrict__ gh, unsigned int* sbuf, unsigned int* wtot,
-                                          unsigned int rank, int nb, unsigned int* out_bin, unsigned int* out_rank) {
-    // 256 threads x 8 bins; deterministic prefix scan
-    const int tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
-    unsigned int loc[8], sum = 0;
-#pragma unroll
-    for (int k = 0; k < 8; ++k) { loc[k] = (8 * tid + k < nb) ? gh[8 * tid + k] : 0u; sum += loc[k]; }
-    unsigned int incl = sum;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { const unsigned int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
-    if (lane == 31) wtot[wrp] = incl;
-    __syncthreads();
-    if (tid == 0) { unsigned int a = 0; for (int w = 0; w < 8; ++w) { const unsigned int t = wtot[w]; wtot[w] = a; a += t; } }
-    __syncthreads();
-    unsigned int c = wtot[wrp] + incl - sum;
-    if (rank >= c && rank < c + sum) {
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            if (rank < c + loc[k]) { sbuf[0] = 8 * tid + k; sbuf[1] = rank - c; break; }
-            c += loc[k];
+    if (tid < 2) {
+        const int k = scount[tid];
+        if (k > kCtaCand) { atomicExch(&c[3], 1); sbase[tid] = -1; }         // local overflow -> fallback
+        else {
+            const int base = k ? atomicAdd(&c[6 + tid], k) : 0;
+            if (base + k > kCandCap) { atomicExch(&c[3], 1); sbase[tid] = -1; }
+            else sbase[tid] = base;
         }
     }
     __syncthreads();
-    *out_bin = sbuf[0]; *out_rank = sbuf[1];
-    __syncthreads();
+#pragma unroll
+    for (int a = 0; a < 2; ++a) {
+        const int base = sbase[a], k = min(scount[a], kCtaCand);
+        if (base >= 0)
+            for (int q = tid; q < k; q += kChunkThreads) cand[((size_t)b * 2 + a) * kCandCap + base + q] = scand[a][q];
+    }
 }
 
-template <int PASS>
-__global__ void __launch_bounds__(256) select_pick_kernel(unsigned int* __restrict__ hist, SelState* __restrict__ state,
-                                                          const int* __restrict__ counters, int median_scaling,
-                                                          float* __restrict__ scale, float* __restrict__ out_medians) {
-    __shared__ unsigned int sbuf[2], wtot[8];
-    __shared__ float med[2];
-    const int b = blockIdx.x;
-    const int nv = counters[4 * b];
-    constexpr int SH = (PASS == 0) ? 21 : (PASS == 1 ? 10 : 0);
-    constexpr int NB = (PASS == 2) ? 1024 : 2048;
-    unsigned int* gh = hist + (size_t)b * 4 * kSelBins;
+// ------------------------------------------------------------------ M: exact medians -> scale
+constexpr int kMedThreads = t3d_select::kThreads;
+
+__global__ void __launch_bounds__(kMedThreads, 1)
+median_scale_kernel(const float* __restrict__ vz, const float* __restrict__ vg, const int* __restrict__ counters,
+                    const unsigned int* __restrict__ cand, int n, int median_scaling, float* __restrict__ scale,
+                    float* __restrict__ out_medians) {
+    extern __shared__ unsigned int skeys[];                       // kCandCap keys
+    __shared__ t3d_select::Smem sm;
+    const int b = blockIdx.x, tid = threadIdx.x;
+    const int* c = counters + 8 * b;
+    const int nv = c[0];
+    float med[2] = {0.f, 0.f};
     if (nv > 0 && median_scaling) {
-        for (int s = 0; s < 2; ++s) {
-            SelState st = (PASS == 0) ? SelState{{0u, 0u}, {(unsigned)(nv - 1) / 2, (unsigned)nv / 2}} : state[2 * b + s];
-            if (counters[4 * b + (s == 0 ? 2 : 1)] > 0) continue;        // NaN in the stream -> median NaN
-            const bool shared_hist = (PASS == 0) || (st.prefix[0] == st.prefix[1]);
-            unsigned int bin, rk;
-            scan_pick(gh + (2 * s) * kSelBins, sbuf, wtot, st.rank[0], NB, &bin, &rk);
-            st.prefix[0] |= bin << SH; st.rank[0] = rk;
-            scan_pick(gh + (2 * s + (shared_hist ? 0 : 1)) * kSelBins, sbuf, wtot, st.rank[1], NB, &bin, &rk);
-            st.prefix[1] |= bin << SH; st.rank[1] = rk;
-            if (threadIdx.x == 0) {
-                state[2 * b + s] = st;
-                if (PASS == 2) {                                          // np.median: fp32 mean of the two middles
-                    const float a = t3d_select::key_float(st.prefix[0]), c = t3d_select::key_float(st.prefix[1]);
-                    med[s] = (st.prefix[0] == st.prefix[1]) ? a : __fmul_rn(__fadd_rn(a, c), 0.5f);
-                }
+        const unsigned int r0 = (unsigned)(nv - 1) / 2, r1 = (unsigned)nv / 2;
+        for (int a = 0; a < 2; ++a) {                             // a = 0: gt, 1: pred
+            if (c[a == 0 ? 2 : 1] > 0) { med[a] = __int_as_float(0x7fc00000); continue; }   // NaN in the stream
+            const int lt = c[4 + a], nc = c[6 + a];
+            const bool bracket_ok = (c[3] == 0) && ((int)r0 >= lt) && ((int)r1 < lt + nc) && nc <= kCandCap;
+            float x0, x1;
+            if (bracket_ok) {
+                const unsigned int* src = cand + ((size_t)b * 2 + a) * kCandCap;
+                for (int q = tid; q < nc; q += kMedThreads) skeys[q] = src[q];
+                __syncthreads();
+                auto get = [&](int i, float* v) { *v = t3d_select::key_float(skeys[i]); return true; };
+                x0 = t3d_select::select_rank(sm, nc, r0 - lt, get);
+                x1 = (r1 == r0) ? x0 : t3d_select::select_rank(sm, nc, r1 - lt, get);
+            } else {                                              // fallback: full radix select, same result
+                const float* v = (a == 0 ? vg : vz) + (size_t)b * n;
+                const float* gm = vg + (size_t)b * n;
+                auto get = [&](int i, float* o) { *o = v[i]; return !isnan(gm[i]); };
+                x0 = t3d_select::select_rank(sm, n, r0, get);
+                x1 = (r1 == r0) ? x0 : t3d_select::select_rank(sm, n, r1, get);
             }
+            med[a] = (r1 == r0) ? x0 : __fmul_rn(__fadd_rn(x0, x1), 0.5f);   // np.median: fp32 mean of the middles
+            __syncthreads();
         }
     }
-    __syncthreads();
-    for (int i = threadIdx.x; i < 4 * kSelBins; i += 256) gh[i] = 0u;     // ready for the next pass / next call
-    if (PASS == 2 && threadIdx.x == 0) {
-        float s = 1.0f, mg = 0.f, mp = 0.f;
-        if (nv > 0 && median_scaling) {
-            const float qnan = __int_as_float(0x7fc00000);
-            mg = counters[4 * b + 2] > 0 ? qnan : med[0];
-            mp = counters[4 * b + 1] > 0 ? qnan : med[1];
-            s = __fdiv_rn(mg, mp);                                        // utils/metrics.py:47
-        }
-        scale[b] = s;
-        if (out_medians) { out_medians[2 * b] = mg; out_medians[2 * b + 1] = mp; }
+    if (tid == 0) {
+        scale[b] = (nv > 0 && median_scaling) ? __fdiv_rn(med[0], med[1]) : 1.0f;   // utils/metrics.py:47
+        if (out_medians) { out_medians[2 * b] = med[0]; out_medians[2 * b + 1] = med[1]; }
     }
-}
-
-// ------------------------------------------------------------------ select: histogram kernel for passes 1 and 2
-template <int PASS>
-__global__ void __launch_bounds__(kChunkThreads)
-select_hist_kernel(const float* __restrict__ vz, const float* __restrict__ vg, const SelState* __restrict__ state,
-                   const int* __restrict__ counters, int n, int median_scaling, unsigned int* __restrict__ hist) {
-    __shared__ unsigned int sh[4][kSelBins];
-    const int b = blockIdx.y;
-    if (!median_scaling || counters[4 * b] == 0) return;
-    constexpr int SH = (PASS == 1) ? 10 : 0;
-    constexpr unsigned int DM = (PASS == 1) ? 2047u : 1023u;
-    constexpr unsigned int FIXED = (PASS == 1) ? 0xffe00000u : 0xfffffc00u;
-    for (int i = threadIdx.x; i < 4 * kSelBins; i += kChunkThreads) (&sh[0][0])[i] = 0u;
-    const SelState sg = state[2 * b], sp = state[2 * b + 1];
-    const bool two_g = sg.prefix[0] != sg.prefix[1], two_p = sp.prefix[0] != sp.prefix[1];
-    __syncthreads();
-    const float* g = vg + (size_t)b * n;
-    const float* z = vz + (size_t)b * n;
-    const int span = gridDim.x * kChunkThreads;
-    for (int i0 = blockIdx.x * kChunkThreads; i0 < n; i0 += span) {
-        const int i = i0 + threadIdx.x;
-        float gv = __int_as_float(0x7fc00000), pv = 0.f;
-        if (i < n) { gv = __ldg(g + i); pv = __ldg(z + i); }
-        const bool ok = !isnan(gv);
-        const unsigned int kg = t3d_select::float_key(gv), kp = t3d_select::float_key(pv);
-        hist_add(sh[0], ok && (kg & FIXED) == sg.prefix[0], (kg >> SH) & DM);
-        if (two_g) hist_add(sh[1], ok && (kg & FIXED) == sg.prefix[1], (kg >> SH) & DM);
-        const bool okp = ok && !isnan(pv);
-        hist_add(sh[2], okp && (kp & FIXED) == sp.prefix[0], (kp >> SH) & DM);
-        if (two_p) hist_add(sh[3], okp && (kp & FIXED) == sp.prefix[1], (kp >> SH) & DM);
-    }
-    __syncthreads();
-    merge_hist(&sh[0][0], hist + (size_t)b * 4 * kSelBins, 4 * kSelBins);
 }
 
 // ------------------------------------------------------------------ M3: per-pixel terms
 __device__ __forceinline__ float np_maximum(float a, float b) { return (isnan(a) || isnan(b)) ? __int_as_float(0x7fc00000) : fmaxf(a, b); }
+
+__device__ __forceinline__ void metric_terms(float gt, float z, float s, float accf[4], int cnt[3]) {
+    if (isnan(gt)) return;                                                   // invalid pixel marker
+    const float pr = __fmul_rn(z, s);                                        // pred *= scale   (:48)
+    const float q = __fdiv_rn(gt, pr);
+    const float th = np_maximum(q, __fdiv_rn(pr, gt));                       // :51 (exact IEEE: counts are exact)
+    cnt[0] += th < 1.25f; cnt[1] += th < 1.5625f; cnt[2] += th < 1.953125f;  // :52-54
+    const float d = __fsub_rn(gt, pr);
+    const float d2 = __fmul_rn(d, d);
+    const float rg = __frcp_rn(gt);
+    accf[0] += fabsf(d) * rg;                                                // :56  |gt - pred| / gt
+    accf[1] += d2 * rg;                                                      // :57
+    accf[2] += d2;                                                           // :58
+    const float dl = __fsub_rn(logf(gt), logf(pr));
+    accf[3] += dl * dl;                                                      // :59
+}
 
 __global__ void __launch_bounds__(kChunkThreads)
 metrics_sum_kernel(const float* __restrict__ vz, const float* __restrict__ vg,
@@ -247,35 +298,38 @@ metrics_sum_kernel(const float* __restrict__ vz, const float* __restrict__ vg,
     __shared__ double red[kChunkThreads / 32][kNPart];
     const int b = blockIdx.y, chunk = blockIdx.x;
     const float s = scale[b];
-    const int per = (n + chunks - 1) / chunks;
-    const int i0 = chunk * per, i1 = min(i0 + per, n);
-    float accf[4] = {0.f, 0.f, 0.f, 0.f};        // short fp32 runs (<= 16 terms) folded into fp64
+    const float* g = vg + (size_t)b * n;
+    const float* z = vz + (size_t)b * n;
     double acc[4] = {0, 0, 0, 0};
     int cnt[3] = {0, 0, 0};
-    int run = 0;
-    for (int i = i0 + threadIdx.x; i < i1; i += kChunkThreads) {
-        const float gt = __ldg(vg + (size_t)b * n + i);
-        if (isnan(gt)) continue;                                                 // invalid pixel marker
-        const float pr = __fmul_rn(__ldg(vz + (size_t)b * n + i), s);            // pred *= scale   (:48)
-        const float q = __fdiv_rn(gt, pr);
-        const float th = np_maximum(q, __fdiv_rn(pr, gt));                       // :51 (exact IEEE: counts are exact)
-        cnt[0] += th < 1.25f; cnt[1] += th < 1.5625f; cnt[2] += th < 1.953125f;  // :52-54
-        const float d = __fsub_rn(gt, pr);
-        const float d2 = __fmul_rn(d, d);
-        const float rg = __frcp_rn(gt);
-        accf[0] += fabsf(d) * rg;                                                // :56  |gt - pred| / gt
-        accf[1] += d2 * rg;                                                      // :57
-        accf[2] += d2;                                                           // :58
-        const float dl = __fsub_rn(logf(gt), logf(pr));
-        accf[3] += dl * dl;                                                      // :59
-        if (++run == 16) {
+    if ((n & 3) == 0) {                       // 128-bit path; fp32 runs of 8 terms folded into fp64
+        const int n4 = n >> 2, per = (n4 + chunks - 1) / chunks;
+        const int q0 = chunk * per, q1 = min(q0 + per, n4);
+        for (int q = q0 + threadIdx.x; q < q1; q += 2 * kChunkThreads) {
+            const int q2 = q + kChunkThreads;
+            const float4 ga = __ldg(reinterpret_cast<const float4*>(g) + q);
+            const float4 za = __ldg(reinterpret_cast<const float4*>(z) + q);
+            float4 gb = make_float4(__int_as_float(0x7fc00000), __int_as_float(0x7fc00000),
+                                    __int_as_float(0x7fc00000), __int_as_float(0x7fc00000)), zb = gb;
+            if (q2 < q1) { gb = __ldg(reinterpret_cast<const float4*>(g) + q2); zb = __ldg(reinterpret_cast<const float4*>(z) + q2); }
+            float accf[4] = {0.f, 0.f, 0.f, 0.f};
+            metric_terms(ga.x, za.x, s, accf, cnt); metric_terms(ga.y, za.y, s, accf, cnt);
+            metric_terms(ga.z, za.z, s, accf, cnt); metric_terms(ga.w, za.w, s, accf, cnt);
+            metric_terms(gb.x, zb.x, s, accf, cnt); metric_terms(gb.y, zb.y, s, accf, cnt);
+            metric_terms(gb.z, zb.z, s, accf, cnt); metric_terms(gb.w, zb.w, s, accf, cnt);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) { acc[k] += (double)accf[k]; accf[k] = 0.f; }
-            run = 0;
+            for (int k = 0; k < 4; ++k) acc[k] += (double)accf[k];
+        }
+    } else {
+        const int per = (n + chunks - 1) / chunks;
+        const int i0 = chunk * per, i1 = min(i0 + per, n);
+        for (int i = i0 + threadIdx.x; i < i1; i += kChunkThreads) {
+            float accf[4] = {0.f, 0.f, 0.f, 0.f};
+            metric_terms(__ldg(g + i), __ldg(z + i), s, accf, cnt);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) acc[k] += (double)accf[k];
         }
     }
-#pragma unroll
-    for (int k = 0; k < 4; ++k) acc[k] += (double)accf[k];
     double v[kNPart] = {acc[0], acc[1], acc[2], acc[3], (double)cnt[0], (double)cnt[1], (double)cnt[2], 0.0};
 #pragma unroll
     for (int k = 0; k < kNPart - 1; ++k) v[k] = warp_sum(v[k]);
@@ -302,9 +356,9 @@ __global__ void metrics_finalize_kernel(const double* __restrict__ partials, con
     if (k >= kNPart) return;
     double s = 0;
     for (int c = 0; c < chunks; ++c) s += partials[((size_t)b * chunks + c) * kNPart + k];
-    const int nv = counters[4 * b];
+    const int nv = counters[8 * b];
     const double qnan = __longlong_as_double(0x7ff8000000000000LL);
-    if (counters[4 * b + 2] > 0 && k < 4) s = qnan;                              // a selected NaN GT poisons every mean
+    if (counters[8 * b + 2] > 0 && k < 4) s = qnan;                              // a selected NaN GT poisons every mean
     double r;
     if (k == 7) r = (double)nv;
     else if (nv == 0) r = (k < 4) ? qnan : 0.0;                                  // utils/metrics.py:34-43
@@ -433,15 +487,26 @@ int t3d_depth_metrics(const float* pred, int pred_stride, int pred_offset,
     MetricsWs w = metrics_ws(workspace, B, n, chunks);
     if (workspace_bytes < w.total) { t3d_set_error("workspace too small"); return T3D_ERR_WORKSPACE; }
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    T3D_CUDA(cudaMemsetAsync(w.counters, 0, w.zero_bytes, st));     // counters + select histograms
+    T3D_CUDA(cudaMemsetAsync(w.counters, 0, (size_t)B * 8 * sizeof(int), st));
+    PixelSrc src;
+    src.pred = pred; src.gt = gt; src.mask = mask; src.pred_stride = pred_stride;
+    src.gt_h = gt_h; src.gt_w = gt_w; src.H = H; src.W = W; src.resample = (gt_h != H) || (gt_w != W);
+    src.fx = (double)gt_w / (double)W; src.fy = (double)gt_h / (double)H;
     dim3 g((unsigned)chunks, (unsigned)B);
+    static bool attr_set = false;
+    if (!attr_set) {
+        T3D_CUDA(cudaFuncSetAttribute(median_scale_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      kCandCap * (int)sizeof(unsigned int)));
+        attr_set = true;
+    }
+    if (median_scaling)
+        T3D_LAUNCH("metrics_sample_kernel", st, metrics_sample_kernel<<<B, 1024, 0, st>>>(src, pred_offset, w.bracket));
+    else
+        T3D_CUDA(cudaMemsetAsync(w.bracket, 0xff, (size_t)B * 4 * sizeof(unsigned int), st));   // empty brackets
     T3D_LAUNCH("depth_extract_kernel", st, depth_extract_kernel<<<g, kChunkThreads, 0, st>>>(
-        pred, pred_stride, pred_offset, gt, gt_h, gt_w, mask, H, W, w.vz, w.vg, w.counters, w.hist));
-    T3D_LAUNCH("select_pick_kernel", st, select_pick_kernel<0><<<B, 256, 0, st>>>(w.hist, w.state, w.counters, median_scaling, w.scale, out_medians));
-    T3D_LAUNCH("select_hist_kernel", st, select_hist_kernel<1><<<g, kChunkThreads, 0, st>>>(w.vz, w.vg, w.state, w.counters, n, median_scaling, w.hist));
-    T3D_LAUNCH("select_pick_kernel", st, select_pick_kernel<1><<<B, 256, 0, st>>>(w.hist, w.state, w.counters, median_scaling, w.scale, out_medians));
-    T3D_LAUNCH("select_hist_kernel", st, select_hist_kernel<2><<<g, kChunkThreads, 0, st>>>(w.vz, w.vg, w.state, w.counters, n, median_scaling, w.hist));
-    T3D_LAUNCH("select_pick_kernel", st, select_pick_kernel<2><<<B, 256, 0, st>>>(w.hist, w.state, w.counters, median_scaling, w.scale, out_medians));
+        src, pred_offset, w.vz, w.vg, w.counters, w.bracket, w.cand));
+    T3D_LAUNCH("median_scale_kernel", st, median_scale_kernel<<<B, kMedThreads, kCandCap * sizeof(unsigned int), st>>>(
+        w.vz, w.vg, w.counters, w.cand, n, median_scaling, w.scale, out_medians));
     T3D_LAUNCH("metrics_sum_kernel", st, metrics_sum_kernel<<<g, kChunkThreads, 0, st>>>(w.vz, w.vg, w.scale, n, chunks, w.partials));
     T3D_LAUNCH("metrics_finalize_kernel", st, metrics_finalize_kernel<<<B, 32, 0, st>>>(w.partials, w.counters, chunks, out, out_f64));
     return T3D_OK;

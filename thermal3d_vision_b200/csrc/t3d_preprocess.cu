@@ -109,35 +109,73 @@ __global__ void __launch_bounds__(256) resize_nearest_kernel(const float* __rest
 constexpr int kHistThreads = 1024;
 constexpr int kHistMaxPx = 49152;
 constexpr int kHistWords = 32768;
+constexpr int kHistMaxW = 4096;      // widest destination row whose x taps fit the shared-memory table
 
+// grid: B * chunks; a CTA owns `rows_per` destination rows of one frame.  Warps take rows, lanes take
+// columns (4 independent pixels in flight per lane); the y tap is computed once per row, the x taps once
+// per CTA (shared-memory table).
 template <bool RESIZE>
 __global__ void __launch_bounds__(kHistThreads, 1)
 resize_hist_u16_kernel(const uint16_t* __restrict__ src, uint16_t* __restrict__ resized,
-                       unsigned int* __restrict__ hist, int sh, int sw, int dh, int dw, int chunks) {
-    extern __shared__ unsigned int sh_hist[];   // kHistWords
+                       unsigned int* __restrict__ hist, int sh, int sw, int dh, int dw, int chunks, int rows_per) {
+    extern __shared__ unsigned int sh_hist[];   // kHistWords, then the x-tap table (RESIZE only)
+    uint2* xt = reinterpret_cast<uint2*>(sh_hist + kHistWords);     // {s0 | s1 << 16, bits of f}
     const int b = blockIdx.x / chunks, chunk = blockIdx.x - b * chunks;
-    const int npx = dh * dw;
-    const int per = (npx + chunks - 1) / chunks;
-    const int p0 = chunk * per, p1 = min(p0 + per, npx);
-    for (int i = threadIdx.x; i < kHistWords; i += kHistThreads) sh_hist[i] = 0u;
-    __syncthreads();
+    const int y0 = chunk * rows_per, y1 = min(y0 + rows_per, dh);
+    const int tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
+    for (int i = tid; i < kHistWords; i += kHistThreads) sh_hist[i] = 0u;
     const uint16_t* s = src + (size_t)b * sh * sw;
     const double scx = (double)sw / (double)dw, scy = (double)sh / (double)dh;
-    for (int p = p0 + threadIdx.x; p < p1; p += kHistThreads) {
-        uint16_t v;
-        if (RESIZE) {
-            const int y = p / dw, x = p - y * dw;
-            const Tap tx = linear_tap(x, sw, scx), ty = linear_tap(y, sh, scy);
-            v = sat_u16(bilinear_at<uint16_t, false>(s, sw, ty, tx));
-            resized[(size_t)b * npx + p] = v;
-        } else {
-            v = __ldg(s + p);
+    if (RESIZE) {
+        for (int x = tid; x < dw; x += kHistThreads) {
+            const Tap t = linear_tap(x, sw, scx);
+            xt[x] = make_uint2((unsigned)t.s0 | ((unsigned)t.s1 << 16), __float_as_uint(t.c1));
         }
-        atomicAdd(&sh_hist[v >> 1], (v & 1) ? 0x10000u : 1u);
+    }
+    __syncthreads();
+    for (int y = y0 + wrp; y < y1; y += kHistThreads / 32) {
+        uint16_t* out_row = resized + ((size_t)b * dh + y) * dw;
+        if (RESIZE) {
+            const Tap ty = linear_tap(y, sh, scy);
+            const uint16_t* r0 = s + (size_t)ty.s0 * sw;
+            const uint16_t* r1 = s + (size_t)ty.s1 * sw;
+            for (int x0 = lane; x0 < dw; x0 += 128) {
+                float a00[4], a01[4], a10[4], a11[4], f[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {                     // all 16 loads first
+                    const int x = x0 + 32 * u;
+                    if (x < dw) {
+                        const uint2 t = xt[x];
+                        const int s0 = t.x & 0xffff, s1 = t.x >> 16;
+                        f[u] = __uint_as_float(t.y);
+                        a00[u] = (float)__ldg(r0 + s0); a01[u] = (float)__ldg(r0 + s1);
+                        a10[u] = (float)__ldg(r1 + s0); a11[u] = (float)__ldg(r1 + s1);
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int x = x0 + 32 * u;
+                    if (x < dw) {
+                        const float c0 = __fsub_rn(1.0f, f[u]), c1 = f[u];
+                        const float h0 = __fadd_rn(__fmul_rn(a00[u], c0), __fmul_rn(a01[u], c1));
+                        const float h1 = __fadd_rn(__fmul_rn(a10[u], c0), __fmul_rn(a11[u], c1));
+                        const uint16_t v = sat_u16(__fadd_rn(__fmul_rn(h0, ty.c0), __fmul_rn(h1, ty.c1)));
+                        out_row[x] = v;
+                        atomicAdd(&sh_hist[v >> 1], (v & 1) ? 0x10000u : 1u);
+                    }
+                }
+            }
+        } else {
+            const uint16_t* r0 = s + (size_t)y * sw;
+            for (int x = lane; x < dw; x += 32) {
+                const uint16_t v = __ldg(r0 + x);
+                atomicAdd(&sh_hist[v >> 1], (v & 1) ? 0x10000u : 1u);
+            }
+        }
     }
     __syncthreads();
     unsigned int* gh = hist + (size_t)b * 65536;
-    for (int i = threadIdx.x; i < kHistWords; i += kHistThreads) {
+    for (int i = tid; i < kHistWords; i += kHistThreads) {
         const unsigned int w = sh_hist[i];
         if (w & 0xffffu) atomicAdd(&gh[2 * i], w & 0xffffu);
         if (w >> 16) atomicAdd(&gh[2 * i + 1], w >> 16);
@@ -399,21 +437,24 @@ int t3d_preprocess_train_u16(const uint16_t* raw, int B, int src_h, int src_w, i
     const int npx = dst_h * dst_w;
     const bool same = (src_h == dst_h && src_w == dst_w);
     T3D_CUDA(cudaMemsetAsync(hist, 0, (size_t)B * 65536 * sizeof(unsigned int), st));
-    const int chunks = (npx + kHistMaxPx - 1) / kHistMaxPx;
+    T3D_REQUIRE(dst_w <= kHistMaxW && src_w <= 65535, "frame too wide (dst_w <= 4096, src_w <= 65535)");
+    const int rows_cap = kHistMaxPx / dst_w;                    // < 65 536 pixels per CTA: u16 bins cannot overflow
+    const int chunks = (dst_h + rows_cap - 1) / rows_cap;
+    const int rows_per = (dst_h + chunks - 1) / chunks;
+    const size_t hsmem = (size_t)kHistWords * 4 + (same ? 0 : (size_t)dst_w * sizeof(uint2));
     static bool attr_set = false;
     if (!attr_set) {
-        T3D_CUDA(cudaFuncSetAttribute(resize_hist_u16_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      kHistWords * 4));
-        T3D_CUDA(cudaFuncSetAttribute(resize_hist_u16_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      kHistWords * 4));
+        const int max_smem = kHistWords * 4 + kHistMaxW * (int)sizeof(uint2);
+        T3D_CUDA(cudaFuncSetAttribute(resize_hist_u16_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+        T3D_CUDA(cudaFuncSetAttribute(resize_hist_u16_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
         attr_set = true;
     }
     if (same)
-        T3D_LAUNCH("resize_hist_u16_kernel", st, resize_hist_u16_kernel<false><<<B * chunks, kHistThreads, kHistWords * 4, st>>>(
-            raw, resized, hist, src_h, src_w, dst_h, dst_w, chunks));
+        T3D_LAUNCH("resize_hist_u16_kernel", st, resize_hist_u16_kernel<false><<<B * chunks, kHistThreads, hsmem, st>>>(
+            raw, resized, hist, src_h, src_w, dst_h, dst_w, chunks, rows_per));
     else
-        T3D_LAUNCH("resize_hist_u16_kernel", st, resize_hist_u16_kernel<true><<<B * chunks, kHistThreads, kHistWords * 4, st>>>(
-            raw, resized, hist, src_h, src_w, dst_h, dst_w, chunks));
+        T3D_LAUNCH("resize_hist_u16_kernel", st, resize_hist_u16_kernel<true><<<B * chunks, kHistThreads, hsmem, st>>>(
+            raw, resized, hist, src_h, src_w, dst_h, dst_w, chunks, rows_per));
     T3D_LAUNCH("percentile_from_hist_kernel", st, percentile_from_hist_kernel<<<B, 1024, 0, st>>>(hist, npx, percentiles));
     dim3 grid((unsigned)min((npx / 4 + 255) / 256 + 1, 64), (unsigned)B);
     const uint16_t* nsrc = same ? raw : resized;
