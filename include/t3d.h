@@ -94,6 +94,9 @@ int t3d_thermal_grad_stats(const float* thermal1, const float* thermal2, int the
  * reduction.  conf1/conf2 may be NULL (-> ones, utils/loss.py:85-88);
  * thermal1/thermal2 may both be NULL (-> basic loss only, utils/loss.py:116);
  * dconf1/dconf2 may be NULL (confidence without grad).
+ * thermal_stats1/2 (nullable) [B][stats_tiles][4]: partial sums of |Dx gray|, |Dy gray|
+ * of each thermal image as t3d_preprocess_train_u16 emits them; when given (and
+ * multi_scale == 0) the statistics pass over the thermal images is skipped.
  * Gradients are those of  grad_scale * loss_b  for every sample b (pass 1/B for
  * a batch mean); t3d_loss_rescale_invalid turns them into the gradients of the
  * mean over VALID samples without a host sync. */
@@ -101,6 +104,7 @@ int t3d_loss_fwd_bwd(const float* pred1, const float* pred2,
                      const float* gt1, const float* gt2,
                      const float* conf1, const float* conf2,
                      const float* thermal1, const float* thermal2, int thermal_channels,
+                     const float* thermal_stats1, const float* thermal_stats2, int stats_tiles,
                      float* dpred1, float* dpred2, float* dconf1, float* dconf2,
                      int B, int H, int W, int multi_scale,
                      float alpha, float edge_weight, float smoothness_weight, float detail_weight,
@@ -113,6 +117,7 @@ int t3d_loss_fwd(const float* pred1, const float* pred2,
                  const float* gt1, const float* gt2,
                  const float* conf1, const float* conf2,
                  const float* thermal1, const float* thermal2, int thermal_channels,
+                 const float* thermal_stats1, const float* thermal_stats2, int stats_tiles,
                  int B, int H, int W, int multi_scale,
                  float alpha, float edge_weight, float smoothness_weight, float detail_weight,
                  float* out_sample, float* out_batch, double* out_sample_f64,
@@ -130,6 +135,21 @@ int t3d_loss_rescale_invalid(float* dpred1, float* dpred2, float* dconf1, float*
  * the device when *grad_output == 1.0f.  Used by autograd backward. */
 int t3d_scale_grads(float* dpred1, float* dpred2, float* dconf1, float* dconf2,
                     const float* grad_output, int B, int H, int W, void* stream);
+
+/* v1 loss, utils/loss.py:4-72 (thermal_aware_loss; imported but never called by the
+ * reference's training loop -- kept for API completeness): basic + unpadded
+ * |dz| * exp(-10 |d gray|) means; the reference evaluates that expression twice, as
+ * "edge" and as "smoothness".  out_sample slot 2 == slot 3, slot 4 = 0.  dpred1/dpred2
+ * NULL -> forward only. */
+size_t t3d_loss_v1_workspace_bytes(int B, int H, int W);
+int t3d_loss_v1_fwd_bwd(const float* pred1, const float* pred2, const float* gt1, const float* gt2,
+                        const float* conf1, const float* conf2,
+                        const float* thermal1, const float* thermal2, int thermal_channels,
+                        float* dpred1, float* dpred2, float* dconf1, float* dconf2,
+                        int B, int H, int W,
+                        float alpha, float edge_weight, float smoothness_weight, float grad_scale,
+                        float* out_sample, float* out_batch, double* out_sample_f64,
+                        void* workspace, size_t workspace_bytes, void* stream);
 
 /* ----------------------------------------------------------- preprocessing */
 /* cv2.resize(src, (dst_w, dst_h)) INTER_LINEAR, OpenCV C++ path (IPP off), bit-exact
@@ -155,10 +175,15 @@ size_t t3d_preprocess_workspace_bytes(int B, int dst_h, int dst_w);
  * clip((x - p2) / (p98 - p2), 0, 1) in float64, one rounding to float32,
  * replicated into out_channels (1 or 3) identical planes.
  * out [B,out_channels,dst_h,dst_w] float32; hist [B,65536] uint32 (== np.bincount
- * of the resized frame); percentiles [B,2] float64. */
+ * of the resized frame); percentiles [B,2] float64.
+ * grad_stats (nullable) [B][t3d_preprocess_stats_tiles()][4] float32: partial sums of
+ * |Dx gray|, |Dy gray| of the OUTPUT image (utils/loss.py:184-201), produced while the
+ * output is written; hand them to t3d_loss_fwd_bwd to skip its statistics pass. */
 int t3d_preprocess_train_u16(const uint16_t* raw, int B, int src_h, int src_w, int dst_h, int dst_w,
                              float* out, int out_channels, unsigned int* hist, double* percentiles,
-                             void* workspace, size_t workspace_bytes, void* stream);
+                             float* grad_stats, void* workspace, size_t workspace_bytes, void* stream);
+/* Number of statistic partials per frame written to grad_stats (0: not available for this shape). */
+int t3d_preprocess_stats_tiles(int dst_h, int dst_w);
 
 /* enhance_thermal_contrast on float data (utils/preprocessing.py:6-30): x is
  * [B,channels,n].  channels == 3: if np.allclose(c0,c1) and np.allclose(c0,c2)
@@ -215,6 +240,19 @@ int t3d_estimate_focal(const float* pointmap, const float* depth, int B, int H, 
 /* EXTENSION (the reference never applies K): u = fx X/Z + cx, v = fy Y/Z + cy; uv [n][2]. */
 int t3d_project_points(const float* pointmap, float fx, float fy, float cx, float cy,
                        float* uv, size_t n_pixels, void* stream);
+
+/* ------------------------------------------------------ Sobel thermal enhancer */
+/* ThermalDUSt3R.preprocess_thermal (thermal_dustr_model.py:110-142).  x [B,C,H,W] with
+ * C in {1,3}; a 1-channel input is replicated to 3 (:116-117), so out is always
+ * [B,3,H,W].  params = device float[2] {edge_weight, temp_scale} (:104-107);
+ * local_norm = use_local_normalization (:108). */
+size_t t3d_sobel_workspace_bytes(int B, int C, int H, int W);
+int t3d_sobel_enhance_fwd(const float* x, const float* params, int B, int C, int H, int W, int local_norm,
+                          float* out, void* workspace, size_t workspace_bytes, void* stream);
+/* d(sum dout*out)/d edge_weight and /d temp_scale -> dparams float[2] (what autograd gives the
+ * two nn.Parameters).  dout [B,3,H,W]. */
+int t3d_sobel_enhance_bwd_params(const float* x, const float* params, const float* dout, int B, int C, int H, int W,
+                                 int local_norm, float* dparams, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------ step result packing */
 /* out16 (float64[16]) = [0] sum over VALID samples of the per-sample loss, [1..4] sums

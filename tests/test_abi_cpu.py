@@ -35,7 +35,7 @@ def test_bad_arguments_are_rejected_without_a_gpu(lib_built):
     lib = lib_built.lib()
     assert lib.t3d_loss_workspace_bytes(0, 4, 4, 0) == 0
     assert lib.t3d_loss_workspace_bytes(2, 384, 512, 1) > 0
-    rc = lib.t3d_loss_fwd_bwd(*([None] * 8), 3, *([None] * 4), 1, 8, 8, 0, 0.2, 0.5, 0.3, 0.4, 1.0,
+    rc = lib.t3d_loss_fwd_bwd(*([None] * 8), 3, None, None, 0, *([None] * 4), 1, 8, 8, 0, 0.2, 0.5, 0.3, 0.4, 1.0,
                               None, None, None, None, 0, None)
     assert rc == -1
     assert b"NULL" in lib.t3d_last_error()

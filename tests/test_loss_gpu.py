@@ -199,3 +199,53 @@ def test_errors(cuda_device):
                                         thermal_img2=torch.zeros(8, 8, device=cuda_device))
     with pytest.raises(ValueError):
         t3d.fused_thermal_loss(p[None], p[None], p[None], torch.zeros(1, 8, 9, 3, device=cuda_device))
+
+
+@pytest.mark.parametrize("H,W", [(40, 64), (37, 51)])
+def test_v1_thermal_aware_loss(cuda_device, H, W):
+    """utils/loss.py:4-72 (dead code in the reference's training loop; API completeness)."""
+    from thermal3d_vision_b200 import loss as t3d
+    ins = ref_loss.make_kat_inputs(H, W, seed=H)
+    a = [x.clone() for x in ins]
+    for k in (0, 1, 4, 5):
+        a[k].requires_grad_()
+    ref, rc = ref_loss.thermal_aware_loss_torch(*a, alpha=0.2, edge_weight=0.5, smoothness_weight=0.3)
+    ref.backward()
+    d = [x.to(cuda_device) for x in ins]
+    for k in (0, 1, 4, 5):
+        d[k].requires_grad_()
+    got, gc = t3d.thermal_aware_loss(*d, alpha=0.2, edge_weight=0.5, smoothness_weight=0.3)
+    got.backward()
+    assert set(gc) == {"basic_loss", "edge_loss", "smoothness_loss"}
+    assert got.item() == pytest.approx(ref.item(), rel=1e-5)
+    for k in gc:
+        assert gc[k] == pytest.approx(rc[k], rel=1e-5)
+    for k in (0, 1, 4, 5):
+        torch.testing.assert_close(d[k].grad.cpu(), a[k].grad, rtol=1e-4, atol=1e-6)
+
+
+def test_v1_golden_value(cuda_device):
+    import os
+    from thermal3d_vision_b200 import loss as t3d
+    kat = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "loss_kat.npz"))
+    d = [x.to(cuda_device) for x in ref_loss.make_kat_inputs(224, 224, seed=0)]
+    got, gc = t3d.thermal_aware_loss(*d, alpha=0.2, edge_weight=0.5, smoothness_weight=0.3)
+    np.testing.assert_allclose([got.item(), gc["basic_loss"], gc["edge_loss"], gc["smoothness_loss"]], kat["v1"], rtol=1e-5)
+
+
+def test_golden_table_full_size(cuda_device):
+    """KAT-L rows of SURVEY.md Appendix C incl. 384x512 (values produced by the reference itself)."""
+    import os
+    from thermal3d_vision_b200 import loss as t3d
+    kat = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "loss_kat.npz"))
+    for row in kat["table"]:
+        H, W, multi = int(row[0]), int(row[1]), bool(row[2])
+        d = [x.to(cuda_device) for x in ref_loss.make_kat_inputs(H, W, seed=0)]
+        for k in (0, 1, 4, 5):
+            d[k].requires_grad_()
+        loss, comp = t3d.enhanced_thermal_aware_loss(*d, multi_scale=multi, **KW)
+        loss.backward()
+        got = [loss.item(), comp["basic_loss"], comp["edge_loss"], comp["smoothness_loss"], comp["detail_loss"],
+               d[0].grad.abs().double().sum().item(), d[1].grad.abs().double().sum().item(),
+               d[4].grad.abs().double().sum().item(), d[5].grad.abs().double().sum().item()]
+        np.testing.assert_allclose(got, row[3:], rtol=1e-5)

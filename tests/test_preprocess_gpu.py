@@ -147,3 +147,36 @@ def test_full_size_properties(cuda_device):
         o, p2, p98, _ = ref_preprocess.train_path(raw[i], (384, 512))
         assert (a.thermal[i].cpu().numpy() == o).all()
         assert tuple(a.percentiles[i].tolist()) == (p2, p98)
+
+
+def test_grad_stats_feed_the_loss(cuda_device):
+    """The normalisation kernel's thermal-gradient sums equal what the loss's own statistics pass
+    computes, and a loss call that consumes them matches the oracle (rtol 1e-5 / grads 1e-4)."""
+    from oracle import ref_loss
+    from thermal3d_vision_b200 import loss as t3d
+    from thermal3d_vision_b200 import preprocessing as pp
+    B, H, W = 3, 96, 160
+    raw = torch.from_numpy(ref_preprocess.make_raw_frames(2 * B, seed=5)).to(cuda_device)
+    tb1 = pp.preprocess_thermal_batch(raw[:B], (W, H), path="train")
+    tb2 = pp.preprocess_thermal_batch(raw[B:], (W, H), path="train")
+    assert tb1.grad_stats is not None and tb1.grad_stats.shape[0] == B
+    P1, P2, G1, G2, C1, C2, _, _ = ref_loss.make_batch_inputs(B, H, W, seed=9)
+    d = [x.to(cuda_device) for x in (P1, P2, G1, G2, C1, C2)]
+    kw = dict(alpha=0.2, edge_weight=0.5, smoothness_weight=0.3, detail_weight=0.4, multi_scale=False)
+    a = t3d.fused_thermal_loss_fwd_bwd(*d, tb1.thermal, tb2.thermal, **kw)
+    b = t3d.fused_thermal_loss_fwd_bwd(*d, tb1.thermal, tb2.thermal, thermal_stats=(tb1.grad_stats, tb2.grad_stats), **kw)
+    torch.testing.assert_close(a["per_sample"], b["per_sample"], rtol=2e-6, atol=0)
+    torch.testing.assert_close(a["dpred1"], b["dpred1"], rtol=1e-5, atol=1e-10)
+    # sums of the stats against numpy on the produced thermal image
+    th = tb1.thermal.cpu().numpy()
+    g = (np.float32(0.299) * th[:, 0] + np.float32(0.587) * th[:, 1]) + np.float32(0.114) * th[:, 2]
+    sx = np.abs(np.diff(g.astype(np.float64), axis=2)).sum(axis=(1, 2))
+    sy = np.abs(np.diff(g.astype(np.float64), axis=1)).sum(axis=(1, 2))
+    got = tb1.grad_stats.double().sum(1).cpu().numpy()
+    np.testing.assert_allclose(got[:, 0], sx, rtol=1e-5)
+    np.testing.assert_allclose(got[:, 1], sy, rtol=1e-5)
+    # and the whole thing against the oracle
+    mean, rows, _ = ref_loss.batched_loss_torch(P1, P2, G1, G2, C1, C2, tb1.thermal.cpu(), tb2.thermal.cpu(),
+                                                alpha=0.2, edge_weight=0.5, smoothness_weight=0.3, detail_weight=0.4,
+                                                multi_scale=False)
+    np.testing.assert_allclose(b["per_sample"][:, :5].cpu().numpy(), rows, rtol=1e-5)

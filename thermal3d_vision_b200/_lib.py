@@ -32,17 +32,21 @@ _SIGNATURES = {
     "t3d_loss_workspace_bytes": (C.c_size_t, [C.c_int] * 4),
     "t3d_thermal_grad_stats": (C.c_int, [c_ptr, c_ptr, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                          c_ptr, c_ptr, C.c_size_t, c_ptr]),
-    "t3d_loss_fwd_bwd": (C.c_int, [c_ptr] * 8 + [C.c_int] + [c_ptr] * 4 + [C.c_int] * 4
+    "t3d_loss_fwd_bwd": (C.c_int, [c_ptr] * 8 + [C.c_int] + [c_ptr, c_ptr, C.c_int] + [c_ptr] * 4 + [C.c_int] * 4
                          + [C.c_float] * 5 + [c_ptr] * 3 + [c_ptr, C.c_size_t, c_ptr]),
-    "t3d_loss_fwd": (C.c_int, [c_ptr] * 8 + [C.c_int] + [C.c_int] * 4 + [C.c_float] * 4
+    "t3d_loss_fwd": (C.c_int, [c_ptr] * 8 + [C.c_int] + [c_ptr, c_ptr, C.c_int] + [C.c_int] * 4 + [C.c_float] * 4
                      + [c_ptr] * 3 + [c_ptr, C.c_size_t, c_ptr]),
+    "t3d_loss_v1_workspace_bytes": (C.c_size_t, [C.c_int] * 3),
+    "t3d_loss_v1_fwd_bwd": (C.c_int, [c_ptr] * 8 + [C.c_int] + [c_ptr] * 4 + [C.c_int] * 3 + [C.c_float] * 4
+                            + [c_ptr] * 3 + [c_ptr, C.c_size_t, c_ptr]),
     "t3d_loss_rescale_invalid": (C.c_int, [c_ptr] * 6 + [C.c_int] * 3 + [c_ptr]),
     "t3d_scale_grads": (C.c_int, [c_ptr] * 5 + [C.c_int] * 3 + [c_ptr]),
     "t3d_resize_bilinear": (C.c_int, [c_ptr, c_ptr] + [C.c_int] * 6 + [c_ptr]),
     "t3d_resize_nearest_f32": (C.c_int, [c_ptr, c_ptr] + [C.c_int] * 5 + [c_ptr]),
     "t3d_preprocess_workspace_bytes": (C.c_size_t, [C.c_int] * 3),
-    "t3d_preprocess_train_u16": (C.c_int, [c_ptr] + [C.c_int] * 5 + [c_ptr, C.c_int, c_ptr, c_ptr,
+    "t3d_preprocess_train_u16": (C.c_int, [c_ptr] + [C.c_int] * 5 + [c_ptr, C.c_int, c_ptr, c_ptr, c_ptr,
                                                                     c_ptr, C.c_size_t, c_ptr]),
+    "t3d_preprocess_stats_tiles": (C.c_int, [C.c_int, C.c_int]),
     "t3d_contrast_normalize_f32": (C.c_int, [c_ptr, C.c_int, C.c_int, C.c_int, c_ptr, C.c_int,
                                              c_ptr, c_ptr, c_ptr]),
     "t3d_channels_close": (C.c_int, [c_ptr, C.c_int, C.c_int, c_ptr, c_ptr]),
@@ -52,6 +56,9 @@ _SIGNATURES = {
                           + [C.c_int] * 4 + [c_ptr] * 3 + [c_ptr, C.c_size_t, c_ptr]),
     "t3d_pointmap_to_depth": (C.c_int, [c_ptr, c_ptr, C.c_size_t, c_ptr]),
     "t3d_estimate_focal": (C.c_int, [c_ptr, c_ptr, C.c_int, C.c_int, C.c_int, c_ptr, c_ptr]),
+    "t3d_sobel_workspace_bytes": (C.c_size_t, [C.c_int] * 4),
+    "t3d_sobel_enhance_fwd": (C.c_int, [c_ptr, c_ptr] + [C.c_int] * 5 + [c_ptr, c_ptr, C.c_size_t, c_ptr]),
+    "t3d_sobel_enhance_bwd_params": (C.c_int, [c_ptr, c_ptr, c_ptr] + [C.c_int] * 5 + [c_ptr, c_ptr, C.c_size_t, c_ptr]),
     "t3d_pack_step_result": (C.c_int, [c_ptr, c_ptr, C.c_int, C.c_int, c_ptr, c_ptr]),
     "t3d_project_points": (C.c_int, [c_ptr] + [C.c_float] * 4 + [c_ptr, C.c_size_t, c_ptr]),
 }

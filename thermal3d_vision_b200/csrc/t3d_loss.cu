@@ -139,18 +139,19 @@ __global__ void __launch_bounds__(kSThreads, 4) thermal_stats_kernel(const Stats
         float v = 0.f;
 #pragma unroll
         for (int w = 0; w < kSThreads / 32; ++w) v += red[w][tid];
-        a.partials[((size_t)img * tiles + tile) * 4 + tid] = v;
+        a.partials[(((size_t)view * a.B + b) * tiles + tile) * 4 + tid] = v;   // [view][b][tile][4]
     }
 }
 
 // out_stats[B][2][2][2] = means (public API of t3d_thermal_grad_stats)
-__global__ void thermal_stats_finalize_kernel(const float* __restrict__ partials, int stiles,
+__global__ void thermal_stats_finalize_kernel(const float* __restrict__ partials, int stiles, int B,
                                               int H, int W, int multi, float* __restrict__ out) {
-    const int img = blockIdx.x;
+    const int img = blockIdx.x;      // 2 b + view
     const int k = threadIdx.x;  // 0..3
     if (k >= 4) return;
     double s = 0.0;
-    for (int t = 0; t < stiles; ++t) s += (double)partials[((size_t)img * stiles + t) * 4 + k];
+    const size_t base = ((size_t)(img & 1) * B + (img >> 1)) * stiles;
+    for (int t = 0; t < stiles; ++t) s += (double)partials[(base + t) * 4 + k];
     const double n1 = (double)H * W, n2 = (double)(H >> 1) * (W >> 1);
     double m = (k < 2) ? s / n1 : ((multi && n2 > 0) ? s / n2 : 0.0);
     out[(size_t)img * 4 + k] = (float)m;
@@ -166,7 +167,7 @@ constexpr int kNTerms = 8;            // basic, E1, S1, D1, E2, S2, D2, (pad)
 struct LossArgs {
     const float* pred[2]; const float* gt[2]; const float* conf[2]; const float* thermal[2];
     float* dpred[2]; float* dconf[2];
-    const float* stats_partials;  // [B*2][stiles][4]
+    const float* stats[2];        // per view: [B][stiles][4]
     float* partials;              // [B*2][tiles][kNTerms]
     int B, H, W, tch, tiles_x, tiles_y, stiles;
     float alpha;
@@ -255,7 +256,7 @@ __global__ void __launch_bounds__(kThreads, MULTI ? 2 : 3) loss_tile_kernel(cons
     // 1/(mean + eps) of the thermal gradients of this image (fixed-order sum of the stats partials)
     if (thermal_on && tid < 4) {
         double s = 0.0;
-        const float* sp = a.stats_partials + (size_t)img * a.stiles * 4 + tid;
+        const float* sp = a.stats[view] + (size_t)b * a.stiles * 4 + tid;
         for (int t = 0; t < a.stiles; ++t) s += (double)sp[(size_t)t * 4];
         const double n = (tid < 2) ? (double)H * W : (double)(H >> 1) * (W >> 1);
         const float mean = (n > 0) ? (float)(s / n) : 0.f;
@@ -659,6 +660,77 @@ __global__ void __launch_bounds__(256) scale_grads_kernel(const ScaleArgs a) {
     }
 }
 
+// ------------------------------------------------------------------ v1 loss (utils/loss.py:4-72)
+// basic + (edge_weight + smoothness_weight) * sum_views [ mean_{H x (W-1)} |Dx z| exp(-10 |Dx gray|)
+//                                                       + mean_{(H-1) x W} |Dy z| exp(-10 |Dy gray|) ]
+// (the reference computes the same expression twice, as "edge" and as "smoothness").  Dead code in the
+// reference's training loop; kept for API completeness -> simple one-thread-per-pixel kernel.
+struct V1Args {
+    const float* pred[2]; const float* gt[2]; const float* conf[2]; const float* thermal[2];
+    float* dpred[2]; float* dconf[2];
+    float* partials;      // [B*2][blocks][kNTerms]
+    int B, H, W, tch, blocks;
+    float alpha, kb, kc, kx, ky;      // kx = gscale (ew+sw) / (H (W-1)), ky = gscale (ew+sw) / ((H-1) W)
+    float sx, sy;                     // N / (H (W-1)), N / ((H-1) W): the second stage divides by N
+};
+
+template <bool BWD>
+__global__ void __launch_bounds__(256) loss_v1_kernel(const V1Args a) {
+    __shared__ float red[8][2];
+    const int img = blockIdx.y, b = img >> 1, view = img & 1;
+    const int H = a.H, W = a.W;
+    const size_t plane = (size_t)H * W;
+    const int idx = blockIdx.x * 256 + threadIdx.x;
+    const float* pred = a.pred[view] + (size_t)b * plane * 3;
+    const float* gt = a.gt[view] + (size_t)b * plane * 3;
+    const float* conf = a.conf[view] ? a.conf[view] + (size_t)b * plane : nullptr;
+    const float* th = a.tch ? a.thermal[view] + (size_t)b * a.tch * plane : nullptr;
+    float sum_b = 0.f, sum_e = 0.f;
+    if (idx < (int)plane) {
+        const int i = idx / W, j = idx - i * W;
+        const float px = pred[(size_t)idx * 3], py = pred[(size_t)idx * 3 + 1], pz = pred[(size_t)idx * 3 + 2];
+        const float dx = px - gt[(size_t)idx * 3], dy = py - gt[(size_t)idx * 3 + 1], dz = pz - gt[(size_t)idx * 3 + 2];
+        const float l = ((fabsf(dx) + fabsf(dy)) + fabsf(dz)) / 3.0f;
+        const float craw = conf ? conf[idx] : 1.0f;
+        const float cc = (craw < kConfMin) ? kConfMin : ((craw > kConfMax) ? kConfMax : craw);
+        sum_b = cc * l - a.alpha * logf(cc);
+        float gz = sgnf(dz) * cc * a.kb;
+        if (th) {
+            auto G = [&](int q) { return load_gray_px(th, a.tch, plane, (size_t)q); };
+            auto Z = [&](int q) { return pred[(size_t)q * 3 + 2]; };
+            const float g0 = G(idx);
+            if (j < W - 1) {
+                const float s = Z(idx + 1) - pz, e = expf(-fabsf(G(idx + 1) - g0) * 10.f);
+                sum_e += fabsf(s) * e * a.sx;
+                gz -= sgnf(s) * e * a.kx;
+            }
+            if (i < H - 1) {
+                const float s = Z(idx + W) - pz, e = expf(-fabsf(G(idx + W) - g0) * 10.f);
+                sum_e += fabsf(s) * e * a.sy;
+                gz -= sgnf(s) * e * a.ky;
+            }
+            if (j > 0) gz += sgnf(pz - Z(idx - 1)) * expf(-fabsf(g0 - G(idx - 1)) * 10.f) * a.kx;
+            if (i > 0) gz += sgnf(pz - Z(idx - W)) * expf(-fabsf(g0 - G(idx - W)) * 10.f) * a.ky;
+        }
+        if (BWD) {
+            float* o = a.dpred[view] + ((size_t)b * plane + idx) * 3;
+            o[0] = sgnf(dx) * cc * a.kb; o[1] = sgnf(dy) * cc * a.kb; o[2] = gz;
+            if (a.dconf[view]) {
+                const bool inside = (craw >= kConfMin) && (craw <= kConfMax);
+                a.dconf[view][(size_t)b * plane + idx] = inside ? (l - a.alpha / cc) * a.kc : 0.f;
+            }
+        }
+    }
+    sum_b = warp_sum(sum_b); sum_e = warp_sum(sum_e);
+    if ((threadIdx.x & 31) == 0) { red[threadIdx.x >> 5][0] = sum_b; red[threadIdx.x >> 5][1] = sum_e; }
+    __syncthreads();
+    if (threadIdx.x < kNTerms) {
+        float v = 0.f;
+        if (threadIdx.x < 3) for (int w = 0; w < 8; ++w) v += red[w][threadIdx.x == 0 ? 0 : 1];   // [0] basic, [1] = [2] = edge
+        a.partials[((size_t)img * a.blocks + blockIdx.x) * kNTerms + threadIdx.x] = v;
+    }
+}
+
 // ------------------------------------------------------------------ host helpers
 struct WsLayout {
     size_t stats_partials, loss_partials, counter, total;
@@ -717,7 +789,7 @@ int launch_loss(const LossArgs& la, cudaStream_t st) {
 
 int loss_impl(bool bwd, const float* pred1, const float* pred2, const float* gt1, const float* gt2,
               const float* conf1, const float* conf2, const float* thermal1, const float* thermal2,
-              int tch, float* dpred1, float* dpred2, float* dconf1, float* dconf2,
+              int tch, const float* ustats1, const float* ustats2, int ustats_tiles, float* dpred1, float* dpred2, float* dconf1, float* dconf2,
               int B, int H, int W, int multi, float alpha, float ew, float sw, float dw, float gscale,
               float* out_sample, float* out_batch, double* out_f64,
               void* workspace, size_t ws_bytes, void* stream) {
@@ -740,7 +812,12 @@ int loss_impl(bool bwd, const float* pred1, const float* pred2, const float* gt1
     unsigned int* counter = reinterpret_cast<unsigned int*>(ws + L.counter);
 
     T3D_CUDA(cudaMemsetAsync(counter, 0, 2 * sizeof(unsigned int), st));   // [0] finalize ticket, [1] work queue
-    if (thermal_on) {
+    // thermal-gradient statistics: supplied by the caller (fused into the preprocessing) or computed here
+    const bool user_stats = thermal_on && !multi && ustats1 && ustats2 && ustats_tiles > 0;
+    const float* stats_v[2] = {stats_partials, stats_partials + (size_t)B * L.stiles_x * L.stiles_y * 4};
+    int stiles = L.stiles_x * L.stiles_y;
+    if (user_stats) { stats_v[0] = ustats1; stats_v[1] = ustats2; stiles = ustats_tiles; }
+    else if (thermal_on) {
         if (int rc = run_stats(thermal1, thermal2, tch, B, H, W, multi, stats_partials, L, st)) return rc;
     }
 
@@ -749,9 +826,9 @@ int loss_impl(bool bwd, const float* pred1, const float* pred2, const float* gt1
     la.conf[0] = conf1; la.conf[1] = conf2;
     la.thermal[0] = thermal_on ? thermal1 : nullptr; la.thermal[1] = thermal_on ? thermal2 : nullptr;
     la.dpred[0] = dpred1; la.dpred[1] = dpred2; la.dconf[0] = dconf1; la.dconf[1] = dconf2;
-    la.stats_partials = stats_partials; la.partials = loss_partials;
+    la.stats[0] = stats_v[0]; la.stats[1] = stats_v[1]; la.partials = loss_partials;
     la.B = B; la.H = H; la.W = W; la.tch = thermal_on ? tch : 0;
-    la.tiles_x = L.tiles_x; la.tiles_y = L.tiles_y; la.stiles = L.stiles_x * L.stiles_y;
+    la.tiles_x = L.tiles_x; la.tiles_y = L.tiles_y; la.stiles = stiles;
     la.alpha = alpha;
     const double N = (double)H * W, n2 = (double)(H / 2) * (W / 2);
     la.kb = (float)((double)gscale / (3.0 * N));
@@ -781,7 +858,7 @@ int loss_impl(bool bwd, const float* pred1, const float* pred2, const float* gt1
             ma.pred[v] = la.pred[v]; ma.gt[v] = la.gt[v]; ma.conf[v] = la.conf[v]; ma.thermal[v] = la.thermal[v];
             ma.dpred[v] = la.dpred[v]; ma.dconf[v] = la.dconf[v];
         }
-        ma.stats_partials = stats_partials; ma.partials = loss_partials; ma.queue = counter + 1;
+        ma.stats[0] = stats_v[0]; ma.stats[1] = stats_v[1]; ma.partials = loss_partials; ma.queue = counter + 1;
         ma.B = B; ma.H = H; ma.W = W; ma.tch = tch; ma.stiles = la.stiles;
         ma.rows_per_band = march_rows; ma.nbands = (H + march_rows - 1) / march_rows; ma.nstrips = (W + 127) / 128;
         ma.alpha = alpha; ma.kb = la.kb; ma.kc = la.kc; ma.kE = la.kE[0]; ma.kS = la.kS[0]; ma.kD = la.kD[0];
@@ -825,20 +902,21 @@ int t3d_thermal_grad_stats(const float* thermal1, const float* thermal2, int the
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     float* partials = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + L.stats_partials);
     if (int rc = run_stats(thermal1, thermal2, thermal_channels, B, H, W, multi_scale, partials, L, st)) return rc;
-    T3D_LAUNCH("thermal_stats_finalize_kernel", st, thermal_stats_finalize_kernel<<<B * 2, 32, 0, st>>>(partials, L.stiles_x * L.stiles_y, H, W, multi_scale, out_stats));
+    T3D_LAUNCH("thermal_stats_finalize_kernel", st, thermal_stats_finalize_kernel<<<B * 2, 32, 0, st>>>(partials, L.stiles_x * L.stiles_y, B, H, W, multi_scale, out_stats));
     return T3D_OK;
 }
 
 int t3d_loss_fwd_bwd(const float* pred1, const float* pred2, const float* gt1, const float* gt2,
                      const float* conf1, const float* conf2,
                      const float* thermal1, const float* thermal2, int thermal_channels,
+                     const float* thermal_stats1, const float* thermal_stats2, int stats_tiles,
                      float* dpred1, float* dpred2, float* dconf1, float* dconf2,
                      int B, int H, int W, int multi_scale,
                      float alpha, float edge_weight, float smoothness_weight, float detail_weight,
                      float grad_scale, float* out_sample, float* out_batch, double* out_sample_f64,
                      void* workspace, size_t workspace_bytes, void* stream) {
     return loss_impl(true, pred1, pred2, gt1, gt2, conf1, conf2, thermal1, thermal2, thermal_channels,
-                     dpred1, dpred2, dconf1, dconf2, B, H, W, multi_scale, alpha, edge_weight,
+                     thermal_stats1, thermal_stats2, stats_tiles, dpred1, dpred2, dconf1, dconf2, B, H, W, multi_scale, alpha, edge_weight,
                      smoothness_weight, detail_weight, grad_scale, out_sample, out_batch, out_sample_f64,
                      workspace, workspace_bytes, stream);
 }
@@ -846,12 +924,13 @@ int t3d_loss_fwd_bwd(const float* pred1, const float* pred2, const float* gt1, c
 int t3d_loss_fwd(const float* pred1, const float* pred2, const float* gt1, const float* gt2,
                  const float* conf1, const float* conf2,
                  const float* thermal1, const float* thermal2, int thermal_channels,
+                 const float* thermal_stats1, const float* thermal_stats2, int stats_tiles,
                  int B, int H, int W, int multi_scale,
                  float alpha, float edge_weight, float smoothness_weight, float detail_weight,
                  float* out_sample, float* out_batch, double* out_sample_f64,
                  void* workspace, size_t workspace_bytes, void* stream) {
     return loss_impl(false, pred1, pred2, gt1, gt2, conf1, conf2, thermal1, thermal2, thermal_channels,
-                     nullptr, nullptr, nullptr, nullptr, B, H, W, multi_scale, alpha, edge_weight,
+                     thermal_stats1, thermal_stats2, stats_tiles, nullptr, nullptr, nullptr, nullptr, B, H, W, multi_scale, alpha, edge_weight,
                      smoothness_weight, detail_weight, 1.0f, out_sample, out_batch, out_sample_f64,
                      workspace, workspace_bytes, stream);
 }
@@ -882,6 +961,54 @@ int t3d_scale_grads(float* dpred1, float* dpred2, float* dconf1, float* dconf2,
                     const float* grad_output, int B, int H, int W, void* stream) {
     T3D_REQUIRE(grad_output, "NULL pointer");
     return scale_common(1, dpred1, dpred2, dconf1, dconf2, nullptr, nullptr, grad_output, B, H, W, stream);
+}
+
+int t3d_loss_v1_fwd_bwd(const float* pred1, const float* pred2, const float* gt1, const float* gt2,
+                        const float* conf1, const float* conf2,
+                        const float* thermal1, const float* thermal2, int thermal_channels,
+                        float* dpred1, float* dpred2, float* dconf1, float* dconf2,
+                        int B, int H, int W,
+                        float alpha, float edge_weight, float smoothness_weight, float grad_scale,
+                        float* out_sample, float* out_batch, double* out_sample_f64,
+                        void* workspace, size_t workspace_bytes, void* stream) {
+    if (int rc = check_dims(B, H, W)) return rc;
+    T3D_REQUIRE(pred1 && pred2 && gt1 && gt2 && out_sample && out_batch && workspace, "NULL pointer");
+    const bool thermal_on = thermal1 != nullptr && thermal2 != nullptr;
+    if (thermal_on) T3D_REQUIRE(thermal_channels == 1 || thermal_channels == 3, "thermal_channels must be 1 or 3");
+    const bool bwd = dpred1 != nullptr && dpred2 != nullptr;
+    const size_t plane = (size_t)H * W;
+    const int blocks = (int)((plane + 255) / 256);
+    const size_t need = 256 + t3d_align_up((size_t)B * 2 * blocks * kNTerms * sizeof(float), 256);
+    if (workspace_bytes < need) { t3d_set_error("workspace too small: %zu < %zu", workspace_bytes, need); return T3D_ERR_WORKSPACE; }
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    unsigned int* counter = reinterpret_cast<unsigned int*>(workspace);
+    float* partials = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + 256);
+    T3D_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned int), st));
+    V1Args a;
+    a.pred[0] = pred1; a.pred[1] = pred2; a.gt[0] = gt1; a.gt[1] = gt2; a.conf[0] = conf1; a.conf[1] = conf2;
+    a.thermal[0] = thermal1; a.thermal[1] = thermal2; a.dpred[0] = dpred1; a.dpred[1] = dpred2;
+    a.dconf[0] = dconf1; a.dconf[1] = dconf2; a.partials = partials;
+    a.B = B; a.H = H; a.W = W; a.tch = thermal_on ? thermal_channels : 0; a.blocks = blocks;
+    const double N = (double)plane, nx = (double)H * (W - 1), ny = (double)(H - 1) * W;
+    const double wsum = (double)edge_weight + (double)smoothness_weight;
+    a.alpha = alpha; a.kb = (float)(grad_scale / (3.0 * N)); a.kc = (float)(grad_scale / N);
+    a.kx = (float)(grad_scale * wsum / nx); a.ky = (float)(grad_scale * wsum / ny);   // W == 1 or H == 1: inf -> NaN like mean(empty)
+    a.sx = (float)(N / nx); a.sy = (float)(N / ny);
+    dim3 grid((unsigned)blocks, (unsigned)(B * 2));
+    if (bwd) T3D_LAUNCH("loss_v1_kernel", st, loss_v1_kernel<true><<<grid, 256, 0, st>>>(a));
+    else T3D_LAUNCH("loss_v1_kernel", st, loss_v1_kernel<false><<<grid, 256, 0, st>>>(a));
+    FinalizeArgs fa;
+    fa.partials = partials; fa.out_sample = out_sample; fa.out_batch = out_batch; fa.out_f64 = out_sample_f64;
+    fa.counter = counter; fa.B = B; fa.H = H; fa.W = W; fa.tiles = blocks;
+    fa.multi = 0; fa.thermal_on = thermal_on ? 1 : 0; fa.ew = edge_weight; fa.sw = smoothness_weight; fa.dw = 0.f;
+    T3D_LAUNCH("loss_finalize_kernel", st, loss_finalize_kernel<<<B, 128, 0, st>>>(fa));
+    return T3D_OK;
+}
+
+size_t t3d_loss_v1_workspace_bytes(int B, int H, int W) {
+    if (B < 1 || H < 1 || W < 1) return 0;
+    const size_t blocks = ((size_t)H * W + 255) / 256;
+    return 256 + t3d_align_up((size_t)B * 2 * blocks * kNTerms * sizeof(float), 256);
 }
 
 }  // extern "C"

@@ -6,7 +6,7 @@
 struct MarchArgs {
     const float* pred[2]; const float* gt[2]; const float* conf[2]; const float* thermal[2];
     float* dpred[2]; float* dconf[2];
-    const float* stats_partials;   // [B*2][stiles][4]
+    const float* stats[2];         // per view: [B][stiles][4]
     float* partials;               // [B*2][nbands*nstrips][8]: basic, E, S, D, 0...
     unsigned int* queue;           // work-item counter, zero on entry
     int B, H, W, tch, stiles;

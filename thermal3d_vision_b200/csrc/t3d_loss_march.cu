@@ -191,7 +191,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) loss_march_kernel(const MarchAr
         float inv_mx, inv_my;
         {
             float sx = 0.f, sy = 0.f;
-            const float* sp = a.stats_partials + (size_t)img * a.stiles * 4;
+            const float* sp = a.stats[view] + (size_t)b * a.stiles * 4;
             for (int t = lane; t < a.stiles; t += 32) { sx += sp[t * 4]; sy += sp[t * 4 + 1]; }
             sx = warp_sum(sx); sy = warp_sum(sy);
             const float invN = 1.0f / (float)plane;

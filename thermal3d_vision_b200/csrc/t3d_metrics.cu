@@ -14,6 +14,8 @@
 #include "t3d_common.cuh"
 #include "t3d_select.cuh"
 
+#include <stdlib.h>
+
 namespace {
 
 constexpr int kChunkThreads = 256;
@@ -29,7 +31,7 @@ constexpr int kNPart = 8;   // abs_rel, sq_rel, sq, log2, a1, a2, a3, (pad)
 //      to a full 3-pass radix select over the planar copies -- slower, same exact result.
 constexpr int kSample = 4096;
 constexpr int kCandCap = 32768;     // candidates per (image, stream)
-constexpr int kCtaCand = 768;       // candidates per CTA per stream staged in shared memory
+constexpr int kCtaCand = 2048;      // candidates per CTA per stream staged in shared memory
 
 struct MetricsWs {
     float* vz; float* vg;
@@ -57,7 +59,10 @@ MetricsWs metrics_ws(void* base, int B, int n, int chunks) {
     return w;
 }
 
-int chunks_for(int n) { return max(1, min(96, (n + 4095) / 4096)); }
+int chunks_for(int n) {
+    static const int px = [] { const char* e = getenv("T3D_METRIC_CHUNK_PX"); const int v = e ? atoi(e) : 8192; return v < 1024 ? 1024 : v; }();
+    return max(1, min(96, (n + px - 1) / px));
+}
 
 struct PixelSrc {            // how to read (gt, pred, valid) of pixel i of image b
     const float* pred; const float* gt; const unsigned char* mask;
@@ -83,6 +88,7 @@ __device__ __forceinline__ void read_pixel(const PixelSrc& s, const float* __res
 __global__ void __launch_bounds__(1024, 1) metrics_sample_kernel(const PixelSrc s, int pred_offset,
                                                                  unsigned int* __restrict__ bracket) {
     __shared__ unsigned int key[2][kSample];
+    __shared__ t3d_select::Smem sm;
     __shared__ int cnt[2];
     const int b = blockIdx.x, tid = threadIdx.x, n = s.H * s.W;
     const float* g = s.gt + (size_t)b * s.gt_h * s.gt_w;
@@ -96,7 +102,7 @@ __global__ void __launch_bounds__(1024, 1) metrics_sample_kernel(const PixelSrc 
         const int k = q * 1024 + tid;
         // n >= kSample: evenly strided distinct pixels; smaller images: every pixel exactly once
         const int i = (n >= kSample) ? (int)(((long long)k * n) / kSample) : k;
-        unsigned int kg = 0xffffffffu, kp = 0xffffffffu;          // sentinel sorts last
+        unsigned int kg = 0xffffffffu, kp = 0xffffffffu;          // sentinel: not part of the sample
         if (i < n) {
             float gv, pv; bool ok;
             read_pixel(s, g, p, m, i, gv, pv, ok);
@@ -108,35 +114,18 @@ __global__ void __launch_bounds__(1024, 1) metrics_sample_kernel(const PixelSrc 
     c0 = __reduce_add_sync(0xffffffffu, c0); c1 = __reduce_add_sync(0xffffffffu, c1);
     if ((tid & 31) == 0) { atomicAdd(&cnt[0], c0); atomicAdd(&cnt[1], c1); }
     __syncthreads();
-    // bitonic sort of both arrays (ascending), 2048 compare-exchanges per stage per array
-    for (int size = 2; size <= kSample; size <<= 1) {
-        for (int stride = size >> 1; stride > 0; stride >>= 1) {
-#pragma unroll
-            for (int q = 0; q < kSample / 2048; ++q) {
-                const int t = q * 1024 + tid;
-                const int lo = 2 * t - (t & (stride - 1));       // index with bit `stride` clear
-                const int hi = lo + stride;
-                const bool up = (lo & size) == 0;
-#pragma unroll
-                for (int a = 0; a < 2; ++a) {
-                    const unsigned int x = key[a][lo], y = key[a][hi];
-                    if ((x > y) == up) { key[a][lo] = y; key[a][hi] = x; }
-                }
-            }
-            __syncthreads();
-        }
-    }
-    if (tid < 2) {
-        const int mm = cnt[tid];
+    // two order statistics of each sample, +-5 sigma around the sample median rank (radix select in smem)
+    for (int a = 0; a < 2; ++a) {
+        const int mm = cnt[a];
         unsigned int lo = 1u, hi = 0u;                             // no bracket -> fallback
-        if (mm >= 64) {
-            const int d = (int)ceilf(2.5f * sqrtf((float)mm)) + 2; // +-5 sigma of the sample-median rank
-            const int mid = mm / 2;
-            const int rl = mid - d, rh = mid + d;
-            lo = (rl <= 0) ? 0u : key[tid][rl];
-            hi = (rh >= mm - 1) ? 0xfffffffeu : key[tid][rh];
+        if (mm >= 64) {                                            // block-uniform
+            const int d = (int)ceilf(2.5f * sqrtf((float)mm)) + 2;
+            const int mid = mm / 2, rl = mid - d, rh = mid + d;
+            auto get = [&](int i, float* v) { const unsigned int k = key[a][i]; *v = t3d_select::key_float(k); return k != 0xffffffffu; };
+            lo = (rl <= 0) ? 0u : t3d_select::float_key(t3d_select::select_rank(sm, kSample, (unsigned)rl, get));
+            hi = (rh >= mm - 1) ? 0xfffffffeu : t3d_select::float_key(t3d_select::select_rank(sm, kSample, (unsigned)rh, get));
         }
-        bracket[4 * b + 2 * tid] = lo; bracket[4 * b + 2 * tid + 1] = hi;
+        if (tid == 0) { bracket[4 * b + 2 * a] = lo; bracket[4 * b + 2 * a + 1] = hi; }
     }
 }
 
@@ -149,13 +138,14 @@ depth_extract_kernel(const PixelSrc s, int pred_offset, float* __restrict__ vz, 
                      int* __restrict__ counters, const unsigned int* __restrict__ bracket,
                      unsigned int* __restrict__ cand) {
     __shared__ unsigned int scand[2][kCtaCand];
-    __shared__ int scount[2], sbase[2];
+    __shared__ int scount[2], sbase[2], sred[5];
     const int b = blockIdx.y, n = s.H * s.W, tid = threadIdx.x, lane = tid & 31;
     const float* g = s.gt + (size_t)b * s.gt_h * s.gt_w;
     const float* p = s.pred + (size_t)b * n * s.pred_stride + pred_offset;
     const unsigned char* m = s.mask ? s.mask + (size_t)b * n : nullptr;
     const unsigned int lo_g = bracket[4 * b], hi_g = bracket[4 * b + 1], lo_p = bracket[4 * b + 2], hi_p = bracket[4 * b + 3];
     if (tid < 2) scount[tid] = 0;
+    if (tid < 5) sred[tid] = 0;
     __syncthreads();
     int nv = 0, pnan = 0, gnan = 0, lt_g = 0, lt_p = 0;
     const int per = (n + gridDim.x - 1) / gridDim.x;
@@ -203,13 +193,15 @@ depth_extract_kernel(const PixelSrc s, int pred_offset, float* __restrict__ vz, 
     gnan = __reduce_add_sync(0xffffffffu, gnan);
     lt_g = __reduce_add_sync(0xffffffffu, lt_g); lt_p = __reduce_add_sync(0xffffffffu, lt_p);
     int* c = counters + 8 * b;
-    if (lane == 0) {
-        if (nv) atomicAdd(&c[0], nv);
-        if (pnan) atomicAdd(&c[1], pnan);
-        if (gnan) atomicAdd(&c[2], gnan);
-        if (lt_g) atomicAdd(&c[4], lt_g);
-        if (lt_p) atomicAdd(&c[5], lt_p);
+    if (lane == 0) {                                   // CTA-level first: one global atomic per counter per CTA
+        if (nv) atomicAdd(&sred[0], nv);
+        if (pnan) atomicAdd(&sred[1], pnan);
+        if (gnan) atomicAdd(&sred[2], gnan);
+        if (lt_g) atomicAdd(&sred[3], lt_g);
+        if (lt_p) atomicAdd(&sred[4], lt_p);
     }
+    __syncthreads();
+    if (tid < 5 && sred[tid]) atomicAdd(&c[tid < 3 ? tid : tid + 1], sred[tid]);
     __syncthreads();
     if (tid < 2) {
         const int k = scount[tid];
@@ -255,7 +247,23 @@ median_scale_kernel(const float* __restrict__ vz, const float* __restrict__ vg, 
                 __syncthreads();
                 auto get = [&](int i, float* v) { *v = t3d_select::key_float(skeys[i]); return true; };
                 x0 = t3d_select::select_rank(sm, nc, r0 - lt, get);
-                x1 = (r1 == r0) ? x0 : t3d_select::select_rank(sm, nc, r1 - lt, get);
+                x1 = x0;
+                if (r1 != r0) {      // x_(r0+1): x0 again if it has duplicates past rank r0, else the next larger key
+                    const unsigned int k0 = t3d_select::float_key(x0);
+                    unsigned int le = 0, nxt = 0xffffffffu;
+                    for (int q = tid; q < nc; q += kMedThreads) {
+                        const unsigned int k = skeys[q];
+                        le += k <= k0;
+                        if (k > k0) nxt = min(nxt, k);
+                    }
+                    le = __reduce_add_sync(0xffffffffu, le); nxt = __reduce_min_sync(0xffffffffu, nxt);
+                    if ((tid & 31) == 0) { sm.hist[tid >> 5] = le; sm.hist[64 + (tid >> 5)] = nxt; }
+                    __syncthreads();
+                    le = 0; nxt = 0xffffffffu;
+                    for (int w = 0; w < kMedThreads / 32; ++w) { le += sm.hist[w]; nxt = min(nxt, sm.hist[64 + w]); }
+                    __syncthreads();
+                    x1 = (le > r1 - lt) ? x0 : t3d_select::key_float(nxt);
+                }
             } else {                                              // fallback: full radix select, same result
                 const float* v = (a == 0 ? vg : vz) + (size_t)b * n;
                 const float* gm = vg + (size_t)b * n;
@@ -284,11 +292,11 @@ __device__ __forceinline__ void metric_terms(float gt, float z, float s, float a
     cnt[0] += th < 1.25f; cnt[1] += th < 1.5625f; cnt[2] += th < 1.953125f;  // :52-54
     const float d = __fsub_rn(gt, pr);
     const float d2 = __fmul_rn(d, d);
-    const float rg = __frcp_rn(gt);
+    const float rg = __fdividef(1.0f, gt);
     accf[0] += fabsf(d) * rg;                                                // :56  |gt - pred| / gt
     accf[1] += d2 * rg;                                                      // :57
     accf[2] += d2;                                                           // :58
-    const float dl = __fsub_rn(logf(gt), logf(pr));
+    const float dl = __logf(gt) - __logf(pr);
     accf[3] += dl * dl;                                                      // :59
 }
 

@@ -352,6 +352,74 @@ __global__ void __launch_bounds__(256) normalize_u16_kernel(const uint16_t* __re
     }
 }
 
+// Vector path of the train-path normalisation (W % 4 == 0), fused with the thermal-gradient statistics
+// the loss needs (utils/loss.py:184-201,240-249): per frame a shared-memory LUT over the integer values
+// between floor(p2) and ceil(p98) replaces the per-pixel fp64 divide (same function, same bits), and the
+// sums of |Dx gray|, |Dy gray| of the OUTPUT image are reduced per CTA into stats[b][band][0..1]
+// (gray = 0.299 v + 0.587 v + 0.114 v in fp32 when the output is replicated to 3 planes).
+constexpr int kNormBands = 8;        // CTAs per frame == statistic partials per frame (T3D_STATS_TILES)
+constexpr int kLutMax = 12288;
+constexpr int kNormThreads = 512;
+
+template <int REP>
+__global__ void __launch_bounds__(kNormThreads) normalize_stats_u16_kernel(const uint16_t* __restrict__ src,
+                                                                           const double* __restrict__ p,
+                                                                           float* __restrict__ dst, int H, int W,
+                                                                           float* __restrict__ stats) {
+    extern __shared__ float lut[];
+    __shared__ float red[kNormThreads / 32][2];
+    const int b = blockIdx.y, band = blockIdx.x, tid = threadIdx.x;
+    const int n = H * W;
+    const double p2 = p[2 * b], p98 = p[2 * b + 1], den = __dsub_rn(p98, p2);
+    const int lo = (int)floor(p2), hi = (int)ceil(p98);
+    const int range = hi - lo + 1;
+    const bool use_lut = range <= kLutMax;
+    if (use_lut)
+        for (int k = tid; k < range; k += kNormThreads) lut[k] = normalize_px((double)(lo + k), p2, den);
+    __syncthreads();
+    auto norm = [&](int v) -> float {
+        if (!use_lut) return normalize_px((double)v, p2, den);
+        return (v < lo) ? 0.0f : ((v > hi) ? 1.0f : lut[v - lo]);     // below p2 -> clip 0, above p98 -> clip 1
+    };
+    auto gray = [&](float o) -> float { return (REP == 3) ? gray3(o, o, o) : o; };
+    const uint16_t* s = src + (size_t)b * n;
+    float* d = dst + (size_t)b * REP * n;
+    const int rows_per = (H + kNormBands - 1) / kNormBands;
+    const int y0 = band * rows_per, y1 = min(y0 + rows_per, H);
+    const int qw = W >> 2;
+    float tx = 0.f, ty = 0.f;
+    for (int q = tid; q < (y1 - y0) * qw; q += kNormThreads) {
+        const int i = y0 + q / qw, j = 4 * (q % qw);
+        const size_t idx = (size_t)i * W + j;
+        const ushort4 v = __ldg(reinterpret_cast<const ushort4*>(s + idx));
+        const float4 o = make_float4(norm(v.x), norm(v.y), norm(v.z), norm(v.w));
+#pragma unroll
+        for (int r = 0; r < REP; ++r) stg_stream_f4(d + (size_t)r * n + idx, o);
+        if (stats) {
+            const float g0 = gray(o.x), g1 = gray(o.y), g2 = gray(o.z), g3 = gray(o.w);
+            tx += fabsf(g1 - g0) + fabsf(g2 - g1) + fabsf(g3 - g2);
+            if (j + 4 < W) tx += fabsf(gray(norm(__ldg(s + idx + 4))) - g3);
+            if (i + 1 < H) {
+                const ushort4 w = __ldg(reinterpret_cast<const ushort4*>(s + idx + W));
+                ty += fabsf(gray(norm(w.x)) - g0) + fabsf(gray(norm(w.y)) - g1) +
+                      fabsf(gray(norm(w.z)) - g2) + fabsf(gray(norm(w.w)) - g3);
+            }
+        }
+    }
+    if (stats) {
+        tx = warp_sum(tx); ty = warp_sum(ty);
+        if ((tid & 31) == 0) { red[tid >> 5][0] = tx; red[tid >> 5][1] = ty; }
+        __syncthreads();
+        if (tid < 2) {
+            float v = 0.f;
+#pragma unroll
+            for (int w = 0; w < kNormThreads / 32; ++w) v += red[w][tid];
+            stats[((size_t)b * kNormBands + band) * 4 + tid] = v;
+            stats[((size_t)b * kNormBands + band) * 4 + 2 + tid] = 0.f;      // scale-2 sums are not produced here
+        }
+    }
+}
+
 // float source [B, channels, n] (drop-in enhance_thermal_contrast); rep output planes
 __global__ void __launch_bounds__(256) normalize_f32_kernel(const float* __restrict__ x, int n, int channels,
                                                             const int* __restrict__ close_flag,
@@ -423,7 +491,7 @@ size_t t3d_preprocess_workspace_bytes(int B, int dst_h, int dst_w) {
 
 int t3d_preprocess_train_u16(const uint16_t* raw, int B, int src_h, int src_w, int dst_h, int dst_w,
                              float* out, int out_channels, unsigned int* hist, double* percentiles,
-                             void* workspace, size_t workspace_bytes, void* stream) {
+                             float* grad_stats, void* workspace, size_t workspace_bytes, void* stream) {
     T3D_REQUIRE(raw && out && hist && percentiles && workspace, "NULL pointer");
     T3D_REQUIRE(B >= 1 && src_h >= 1 && src_w >= 1 && dst_h >= 1 && dst_w >= 1, "bad dims");
     T3D_REQUIRE(out_channels == 1 || out_channels == 3, "out_channels must be 1 or 3");
@@ -456,11 +524,32 @@ int t3d_preprocess_train_u16(const uint16_t* raw, int B, int src_h, int src_w, i
         T3D_LAUNCH("resize_hist_u16_kernel", st, resize_hist_u16_kernel<true><<<B * chunks, kHistThreads, hsmem, st>>>(
             raw, resized, hist, src_h, src_w, dst_h, dst_w, chunks, rows_per));
     T3D_LAUNCH("percentile_from_hist_kernel", st, percentile_from_hist_kernel<<<B, 1024, 0, st>>>(hist, npx, percentiles));
-    dim3 grid((unsigned)min((npx / 4 + 255) / 256 + 1, 64), (unsigned)B);
     const uint16_t* nsrc = same ? raw : resized;
-    const int vec = (npx % 4 == 0) && t3d_aligned16(out) && ((reinterpret_cast<uintptr_t>(nsrc) & 7u) == 0);
-    T3D_LAUNCH("normalize_u16_kernel", st, normalize_u16_kernel<<<grid, 256, 0, st>>>(nsrc, percentiles, out, npx, out_channels, vec));
+    const int vec = (dst_w % 4 == 0) && t3d_aligned16(out) && ((reinterpret_cast<uintptr_t>(nsrc) & 7u) == 0);
+    if (vec) {
+        static bool nattr = false;
+        if (!nattr) {
+            T3D_CUDA(cudaFuncSetAttribute(normalize_stats_u16_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kLutMax * 4));
+            T3D_CUDA(cudaFuncSetAttribute(normalize_stats_u16_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kLutMax * 4));
+            nattr = true;
+        }
+        dim3 grid(kNormBands, (unsigned)B);
+        if (out_channels == 3)
+            T3D_LAUNCH("normalize_stats_u16_kernel", st, normalize_stats_u16_kernel<3><<<grid, kNormThreads, kLutMax * 4, st>>>(
+                nsrc, percentiles, out, dst_h, dst_w, grad_stats));
+        else
+            T3D_LAUNCH("normalize_stats_u16_kernel", st, normalize_stats_u16_kernel<1><<<grid, kNormThreads, kLutMax * 4, st>>>(
+                nsrc, percentiles, out, dst_h, dst_w, grad_stats));
+    } else {
+        T3D_REQUIRE(grad_stats == nullptr, "grad_stats needs dst_w %% 4 == 0 (t3d_preprocess_stats_tiles() == 0 here)");
+        dim3 grid((unsigned)min((npx / 4 + 255) / 256 + 1, 64), (unsigned)B);
+        T3D_LAUNCH("normalize_u16_kernel", st, normalize_u16_kernel<<<grid, 256, 0, st>>>(nsrc, percentiles, out, npx, out_channels, 0));
+    }
     return T3D_OK;
+}
+
+int t3d_preprocess_stats_tiles(int dst_h, int dst_w) {
+    return (dst_h >= 1 && dst_w >= 4 && dst_w % 4 == 0) ? kNormBands : 0;
 }
 
 int t3d_contrast_normalize_f32(const float* x, int B, int channels, int n, float* out, int out_channels,

@@ -40,7 +40,7 @@ def _prep(t: Optional[torch.Tensor], device) -> Optional[torch.Tensor]:
 
 
 def _launch(bwd, p1, p2, g1, g2, c1, c2, t1, t2, need_dconf, alpha, ew, sw, dw, multi, grad_scale,
-            rescale_invalid, out=None):
+            rescale_invalid, out=None, thermal_stats=None):
     """Raw call into the C ABI on already-prepared [B,H,W,3] CUDA tensors."""
     lib = _lib.lib()
     B, H, W, _ = p1.shape
@@ -60,6 +60,17 @@ def _launch(bwd, p1, p2, g1, g2, c1, c2, t1, t2, need_dconf, alpha, ew, sw, dw, 
         batch = torch.empty(OUT_STRIDE, dtype=torch.float32, device=dev)
     f64 = out.get("per_sample_f64")
     stream = _lib.current_stream_ptr()
+    st1 = st2 = None
+    st_tiles = 0
+    if thermal_stats is not None and tch and not multi:
+        st1, st2 = thermal_stats
+        if st1 is not None and st2 is not None:
+            if st1.shape != st2.shape or st1.dim() != 3 or st1.shape[0] != B or st1.shape[2] != 4 \
+                    or st1.dtype != torch.float32 or not st1.is_contiguous() or not st2.is_contiguous():
+                raise ValueError("thermal_stats must be two contiguous float32 [B, tiles, 4] tensors")
+            st_tiles = int(st1.shape[1])
+        else:
+            st1 = st2 = None
     dp1 = dp2 = dc1 = dc2 = None
     if bwd:
         dp1 = out.get("dpred1"); dp2 = out.get("dpred2")
@@ -77,7 +88,8 @@ def _launch(bwd, p1, p2, g1, g2, c1, c2, t1, t2, need_dconf, alpha, ew, sw, dw, 
                 dc2 = torch.empty(B, H, W, dtype=torch.float32, device=dev)
         rc = lib.t3d_loss_fwd_bwd(
             _lib.ptr(p1), _lib.ptr(p2), _lib.ptr(g1), _lib.ptr(g2), _lib.ptr(c1), _lib.ptr(c2),
-            _lib.ptr(t1), _lib.ptr(t2), tch, _lib.ptr(dp1), _lib.ptr(dp2), _lib.ptr(dc1), _lib.ptr(dc2),
+            _lib.ptr(t1), _lib.ptr(t2), tch, _lib.ptr(st1), _lib.ptr(st2), st_tiles,
+            _lib.ptr(dp1), _lib.ptr(dp2), _lib.ptr(dc1), _lib.ptr(dc2),
             B, H, W, int(multi), alpha, ew, sw, dw, grad_scale,
             _lib.ptr(per_sample), _lib.ptr(batch), _lib.ptr(f64), _lib.ptr(ws), ws.numel(), stream)
         _lib.check(rc, "t3d_loss_fwd_bwd")
@@ -88,7 +100,8 @@ def _launch(bwd, p1, p2, g1, g2, c1, c2, t1, t2, need_dconf, alpha, ew, sw, dw, 
     else:
         rc = lib.t3d_loss_fwd(
             _lib.ptr(p1), _lib.ptr(p2), _lib.ptr(g1), _lib.ptr(g2), _lib.ptr(c1), _lib.ptr(c2),
-            _lib.ptr(t1), _lib.ptr(t2), tch, B, H, W, int(multi), alpha, ew, sw, dw,
+            _lib.ptr(t1), _lib.ptr(t2), tch, _lib.ptr(st1), _lib.ptr(st2), st_tiles,
+            B, H, W, int(multi), alpha, ew, sw, dw,
             _lib.ptr(per_sample), _lib.ptr(batch), _lib.ptr(f64), _lib.ptr(ws), ws.numel(), stream)
         _lib.check(rc, "t3d_loss_fwd")
     return per_sample, batch, dp1, dp2, dc1, dc2
@@ -178,11 +191,13 @@ def fused_thermal_loss(pred_pts1, pred_pts2, gt_pts1, gt_pts2, confidences1=None
 def fused_thermal_loss_fwd_bwd(pred_pts1, pred_pts2, gt_pts1, gt_pts2, confidences1=None, confidences2=None,
                                thermal_img1=None, thermal_img2=None, *, alpha=0.2, edge_weight=0.5,
                                smoothness_weight=0.3, detail_weight=0.3, multi_scale=True,
-                               conf_grad=True, out=None):
+                               conf_grad=True, out=None, thermal_stats=None):
     """Functional (no autograd) fused step on prepared contiguous fp32 CUDA tensors.
 
     Returns dict(per_sample, batch, dpred1, dpred2, dconf1, dconf2); gradients are those of the
     mean over valid samples.  ``out`` may hold preallocated buffers of the same names (+ 'workspace').
+    ``thermal_stats`` = (ThermalBatch.grad_stats of view 1, of view 2): the thermal-gradient sums the
+    preprocessing kernel already produced; the loss then skips its own pass over the thermal images.
     """
     _lib.require_cuda(pred_pts1, pred_pts2, gt_pts1, gt_pts2, confidences1, confidences2, thermal_img1, thermal_img2)
     B = pred_pts1.shape[0]
@@ -190,7 +205,7 @@ def fused_thermal_loss_fwd_bwd(pred_pts1, pred_pts2, gt_pts1, gt_pts2, confidenc
     ps, bt, dp1, dp2, dc1, dc2 = _launch(
         True, pred_pts1, pred_pts2, gt_pts1, gt_pts2, confidences1, confidences2, thermal_img1, thermal_img2,
         need_dconf, float(alpha), float(edge_weight), float(smoothness_weight), float(detail_weight),
-        bool(multi_scale), 1.0 / B, rescale_invalid=True, out=out)
+        bool(multi_scale), 1.0 / B, rescale_invalid=True, out=out, thermal_stats=thermal_stats)
     return {"per_sample": ps, "batch": bt, "dpred1": dp1, "dpred2": dp2, "dconf1": dc1, "dconf2": dc2}
 
 
@@ -242,3 +257,75 @@ def enhanced_thermal_aware_loss(pred_pts1, pred_pts2, gt_pts1, gt_pts2,
         "detail_loss": vals[4] if thermal_on else 0,
     }
     return loss, comps
+
+
+class _LossV1(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, p1, p2, c1, c2, g1, g2, t1, t2, cfg):
+        alpha, ew, sw = cfg
+        lib = _lib.lib()
+        B, H, W, _ = p1.shape
+        dev = p1.device
+        need = ctx.needs_input_grad
+        bwd = bool(need[0] or need[1] or need[2] or need[3])
+        tch = 0 if t1 is None else int(t1.shape[1])
+        ws = torch.empty(lib.t3d_loss_v1_workspace_bytes(B, H, W), dtype=torch.uint8, device=dev)
+        per_sample = torch.empty(B, OUT_STRIDE, dtype=torch.float32, device=dev)
+        batch = torch.empty(OUT_STRIDE, dtype=torch.float32, device=dev)
+        dp1 = torch.empty_like(p1) if bwd else None
+        dp2 = torch.empty_like(p2) if bwd else None
+        dc1 = torch.empty(B, H, W, dtype=torch.float32, device=dev) if (bwd and need[2] and c1 is not None) else None
+        dc2 = torch.empty(B, H, W, dtype=torch.float32, device=dev) if (bwd and need[3] and c2 is not None) else None
+        rc = lib.t3d_loss_v1_fwd_bwd(_lib.ptr(p1), _lib.ptr(p2), _lib.ptr(g1), _lib.ptr(g2), _lib.ptr(c1), _lib.ptr(c2),
+                                     _lib.ptr(t1), _lib.ptr(t2), tch, _lib.ptr(dp1), _lib.ptr(dp2), _lib.ptr(dc1),
+                                     _lib.ptr(dc2), B, H, W, alpha, ew, sw, 1.0, _lib.ptr(per_sample), _lib.ptr(batch),
+                                     None, _lib.ptr(ws), ws.numel(), _lib.current_stream_ptr())
+        _lib.check(rc, "t3d_loss_v1_fwd_bwd")
+        ctx.shape = tuple(p1.shape)
+        ctx.grads = (dp1, dp2, dc1, dc2) if bwd else None
+        ctx.mark_non_differentiable(per_sample)
+        return per_sample[0, 0].clone(), per_sample
+
+    @staticmethod
+    def backward(ctx, g_loss, _g_ps):
+        if ctx.grads is None:
+            return (None,) * 9
+        dp1, dp2, dc1, dc2 = ctx.grads
+        ctx.grads = None
+        B, H, W, _ = ctx.shape
+        go = g_loss.detach().to(dtype=torch.float32, device=dp1.device).reshape(1).contiguous()
+        rc = _lib.lib().t3d_scale_grads(_lib.ptr(dp1), _lib.ptr(dp2), _lib.ptr(dc1), _lib.ptr(dc2),
+                                       _lib.ptr(go), B, H, W, _lib.current_stream_ptr())
+        _lib.check(rc, "t3d_scale_grads")
+        need = ctx.needs_input_grad
+        return (dp1 if need[0] else None, dp2 if need[1] else None,
+                dc1 if need[2] else None, dc2 if need[3] else None, None, None, None, None, None)
+
+
+def thermal_aware_loss(pred_pts1, pred_pts2, gt_pts1, gt_pts2,
+                       confidences1=None, confidences2=None,
+                       thermal_img1=None, thermal_img2=None,
+                       alpha=0.2, edge_weight=0.5, smoothness_weight=0.3):
+    """Drop-in for utils/loss.py:4-72 (v1 loss; the reference imports it but never calls it)."""
+    src_device = pred_pts1.device
+    dev = _device_of(pred_pts1, pred_pts2, gt_pts1, gt_pts2)
+    if pred_pts1.dim() != 3 or pred_pts1.shape[-1] != 3:
+        raise ValueError(f"expected [H,W,3] pointmaps, got {tuple(pred_pts1.shape)}")
+    t1 = t2 = None
+    thermal_on = thermal_img1 is not None and thermal_img2 is not None
+    if thermal_on and isinstance(thermal_img1, torch.Tensor) and thermal_img1.dim() == 3:   # :19
+        t1, t2 = thermal_img1, thermal_img2
+        if t1.shape[0] != 3:
+            t1, t2 = t1[:1], t2[:1]
+        t1, t2 = _prep(t1.unsqueeze(0), dev), _prep(t2.unsqueeze(0), dev)
+    elif thermal_on:
+        # reference: edge stays 0 but the smoothness branch hits unbound gradients -> NameError (:54-58)
+        raise ValueError("thermal images must be 3-D [C,H,W] tensors")
+    ub = lambda t: None if t is None else _prep(t.unsqueeze(0), dev)
+    loss, ps = _LossV1.apply(ub(pred_pts1), ub(pred_pts2), ub(confidences1), ub(confidences2),
+                             ub(gt_pts1), ub(gt_pts2), t1, t2,
+                             (float(alpha), float(edge_weight), float(smoothness_weight)))
+    vals = ps[0, :4].tolist()
+    comps = {"basic_loss": vals[1], "edge_loss": vals[2] if t1 is not None else 0,
+             "smoothness_loss": vals[3] if t1 is not None else 0}
+    return (loss if loss.device == src_device else loss.to(src_device)), comps

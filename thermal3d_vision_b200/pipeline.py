@@ -71,9 +71,12 @@ class HotPathStep:
         [7..13] sums of finite per-image metrics (abs_rel..acc_3)  [14] n_images  [15] unused.
         With distributed=True the vector is all-reduced (SUM) over ranks: ONE small NCCL call."""
         size = (self.W, self.H)
-        t1 = _pre.preprocess_thermal_batch(raw1, size, path="train", out=self.pre_out[0]).thermal
-        t2 = _pre.preprocess_thermal_batch(raw2, size, path="train", out=self.pre_out[1]).thermal
-        lo = _loss.fused_thermal_loss_fwd_bwd(pred1, pred2, gt1, gt2, conf1, conf2, t1, t2, out=self.loss_out, **self.kw)
+        tb1 = _pre.preprocess_thermal_batch(raw1, size, path="train", out=self.pre_out[0])
+        tb2 = _pre.preprocess_thermal_batch(raw2, size, path="train", out=self.pre_out[1])
+        # the normalisation kernel already summed the thermal gradients: the loss skips its statistics pass
+        lo = _loss.fused_thermal_loss_fwd_bwd(pred1, pred2, gt1, gt2, conf1, conf2, tb1.thermal, tb2.thermal,
+                                              out=self.loss_out, thermal_stats=(tb1.grad_stats, tb2.grad_stats),
+                                              **self.kw)
         me = _metrics.compute_depth_metrics_batch(pred1, gt_depth, out=self.met_out)   # Z of pred1 read in place
         r = self.result
         rc = _lib.lib().t3d_pack_step_result(_lib.ptr(lo["per_sample"]), _lib.ptr(me["metrics_f64"]), self.B, self.B,

@@ -71,6 +71,7 @@ class ThermalBatch(NamedTuple):
     thermal: torch.Tensor                      # [B, C, h, w] float32 in [0, 1]
     percentiles: torch.Tensor                  # [B, 2] float64 (p2, p98)
     histogram: Optional[torch.Tensor] = None   # [B, 65536] int32 view of the uint32 counts (train path)
+    grad_stats: Optional[torch.Tensor] = None  # [B, tiles, 4] partial sums of |Dx gray|, |Dy gray| (train path)
 
 
 def preprocess_thermal_batch(raw_u16: torch.Tensor, img_size=(224, 224), path: str = "train",
@@ -105,10 +106,17 @@ def preprocess_thermal_batch(raw_u16: torch.Tensor, img_size=(224, 224), path: s
         ws = out.get("workspace")
         if ws is None or ws.numel() < ws_bytes:
             ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        tiles = lib.t3d_preprocess_stats_tiles(dh, dw)
+        stats = None
+        if tiles > 0:
+            stats = out.get("grad_stats")
+            if stats is None:
+                stats = torch.empty(B, tiles, 4, dtype=torch.float32, device=dev)
         rc = lib.t3d_preprocess_train_u16(_lib.ptr(x), B, sh, sw, dh, dw, _lib.ptr(thermal), out_channels,
-                                          _lib.ptr(hist), _lib.ptr(pct), _lib.ptr(ws), ws.numel(), stream)
+                                          _lib.ptr(hist), _lib.ptr(pct), _lib.ptr(stats), _lib.ptr(ws), ws.numel(),
+                                          stream)
         _lib.check(rc, "t3d_preprocess_train_u16")
-        return ThermalBatch(thermal, pct, hist)
+        return ThermalBatch(thermal, pct, hist, stats)
     if path == "inference":
         resized = torch.empty(B, dh, dw, dtype=torch.float32, device=dev)
         rc = lib.t3d_resize_bilinear(_lib.ptr(x), _lib.ptr(resized), 1, B, sh, sw, dh, dw, stream)
