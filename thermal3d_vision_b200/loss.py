@@ -191,13 +191,15 @@ def fused_thermal_loss(pred_pts1, pred_pts2, gt_pts1, gt_pts2, confidences1=None
 def fused_thermal_loss_fwd_bwd(pred_pts1, pred_pts2, gt_pts1, gt_pts2, confidences1=None, confidences2=None,
                                thermal_img1=None, thermal_img2=None, *, alpha=0.2, edge_weight=0.5,
                                smoothness_weight=0.3, detail_weight=0.3, multi_scale=True,
-                               conf_grad=True, out=None, thermal_stats=None):
+                               conf_grad=True, out=None, thermal_stats=None, grad_scale=None):
     """Functional (no autograd) fused step on prepared contiguous fp32 CUDA tensors.
 
     Returns dict(per_sample, batch, dpred1, dpred2, dconf1, dconf2); gradients are those of the
     mean over valid samples.  ``out`` may hold preallocated buffers of the same names (+ 'workspace').
     ``thermal_stats`` = (ThermalBatch.grad_stats of view 1, of view 2): the thermal-gradient sums the
     preprocessing kernel already produced; the loss then skips its own pass over the thermal images.
+    ``grad_scale`` (default 1/B) is the a-priori upstream gradient, e.g. 1/(B * world_size) for the mean
+    over a data-parallel global batch.
     """
     _lib.require_cuda(pred_pts1, pred_pts2, gt_pts1, gt_pts2, confidences1, confidences2, thermal_img1, thermal_img2)
     B = pred_pts1.shape[0]
@@ -205,7 +207,8 @@ def fused_thermal_loss_fwd_bwd(pred_pts1, pred_pts2, gt_pts1, gt_pts2, confidenc
     ps, bt, dp1, dp2, dc1, dc2 = _launch(
         True, pred_pts1, pred_pts2, gt_pts1, gt_pts2, confidences1, confidences2, thermal_img1, thermal_img2,
         need_dconf, float(alpha), float(edge_weight), float(smoothness_weight), float(detail_weight),
-        bool(multi_scale), 1.0 / B, rescale_invalid=True, out=out, thermal_stats=thermal_stats)
+        bool(multi_scale), (1.0 / B) if grad_scale is None else float(grad_scale), rescale_invalid=True, out=out,
+        thermal_stats=thermal_stats)
     return {"per_sample": ps, "batch": bt, "dpred1": dp1, "dpred2": dp2, "dconf1": dc1, "dconf2": dc2}
 
 

@@ -14,6 +14,7 @@ from typing import Dict, Optional
 import torch
 
 from . import _lib
+from . import distributed as _dist
 from . import loss as _loss
 from . import metrics as _metrics
 from . import preprocessing as _pre
@@ -76,6 +77,7 @@ class HotPathStep:
         # the normalisation kernel already summed the thermal gradients: the loss skips its statistics pass
         lo = _loss.fused_thermal_loss_fwd_bwd(pred1, pred2, gt1, gt2, conf1, conf2, tb1.thermal, tb2.thermal,
                                               out=self.loss_out, thermal_stats=(tb1.grad_stats, tb2.grad_stats),
+                                              grad_scale=_dist.global_grad_scale(self.B) if self.distributed else None,
                                               **self.kw)
         me = _metrics.compute_depth_metrics_batch(pred1, gt_depth, out=self.met_out)   # Z of pred1 read in place
         r = self.result
@@ -83,8 +85,7 @@ class HotPathStep:
                                              _lib.ptr(r), _lib.current_stream_ptr())
         _lib.check(rc, "t3d_pack_step_result")
         if self.distributed:
-            import torch.distributed as dist
-            dist.all_reduce(r, op=dist.ReduceOp.SUM)
+            _dist.all_reduce_result(r)
         return r
 
     # ------------------------------------------------------------------ host-buffer step (e2e)
@@ -108,10 +109,4 @@ class HotPathStep:
 
     @staticmethod
     def summarize(result_host: torch.Tensor) -> Dict[str, float]:
-        r = result_host.tolist()
-        nv, n_img = max(r[5], 1.0), max(r[14], 1.0)
-        out = {"loss": r[0] / nv, "basic_loss": r[1] / nv, "edge_loss": r[2] / nv, "smoothness_loss": r[3] / nv,
-               "detail_loss": r[4] / nv, "n_valid": r[5], "n_pairs": r[6]}
-        for i, k in enumerate(_metrics.KEYS7):
-            out[k] = r[7 + i] / n_img
-        return out
+        return _dist.summarize(result_host.tolist())
