@@ -133,17 +133,21 @@ __global__ void __launch_bounds__(1024, 1) metrics_sample_kernel(const PixelSrc 
 // pred element (b, i) lives at pred[(b*n + i) * pred_stride + pred_offset]: stride 3 / offset 2 reads
 // the Z channel of an AoS pointmap in place (depth is never materialised by the caller).
 // Invalid pixels are stored as vg = NaN (a *selected* NaN GT makes every metric NaN anyway: gt_nan counter).
-__global__ void __launch_bounds__(kChunkThreads)
+template <bool GENERAL>      // GENERAL: user mask and/or GT nearest-resample; else mask = gt > 0 & finite, same size
+__global__ void __launch_bounds__(kChunkThreads, 6)
 depth_extract_kernel(const PixelSrc s, int pred_offset, float* __restrict__ vz, float* __restrict__ vg,
                      int* __restrict__ counters, const unsigned int* __restrict__ bracket,
                      unsigned int* __restrict__ cand) {
     __shared__ unsigned int scand[2][kCtaCand];
     __shared__ int scount[2], sbase[2], sred[5];
     const int b = blockIdx.y, n = s.H * s.W, tid = threadIdx.x, lane = tid & 31;
-    const float* g = s.gt + (size_t)b * s.gt_h * s.gt_w;
-    const float* p = s.pred + (size_t)b * n * s.pred_stride + pred_offset;
-    const unsigned char* m = s.mask ? s.mask + (size_t)b * n : nullptr;
+    const float* __restrict__ g = s.gt + (size_t)b * s.gt_h * s.gt_w;
+    const float* __restrict__ p = s.pred + (size_t)b * n * s.pred_stride + pred_offset;
+    const unsigned char* __restrict__ m = s.mask ? s.mask + (size_t)b * n : nullptr;
+    float* __restrict__ oz = vz + (size_t)b * n;
+    float* __restrict__ og = vg + (size_t)b * n;
     const unsigned int lo_g = bracket[4 * b], hi_g = bracket[4 * b + 1], lo_p = bracket[4 * b + 2], hi_p = bracket[4 * b + 3];
+    const int pstride = s.pred_stride;
     if (tid < 2) scount[tid] = 0;
     if (tid < 5) sred[tid] = 0;
     __syncthreads();
@@ -151,42 +155,44 @@ depth_extract_kernel(const PixelSrc s, int pred_offset, float* __restrict__ vz, 
     const int per = (n + gridDim.x - 1) / gridDim.x;
     const int i_begin = blockIdx.x * per, i_end = min(i_begin + per, n);
     constexpr int U = 4;
-    for (int i0 = i_begin; i0 < i_end; i0 += U * kChunkThreads) {          // warp-uniform trip count
+    for (int i0 = i_begin + tid; i0 < i_end; i0 += U * kChunkThreads) {
         float gv[U], pv[U]; bool ok[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {                                      // all loads first (MLP)
-            const int i = i0 + u * kChunkThreads + tid;
+            const int i = i0 + u * kChunkThreads;
             gv[u] = 0.f; pv[u] = 0.f; ok[u] = false;
-            if (i < i_end) read_pixel(s, g, p, m, i, gv[u], pv[u], ok[u]);
+            if (i < i_end) {
+                if (GENERAL) read_pixel(s, g, p, m, i, gv[u], pv[u], ok[u]);
+                else { gv[u] = __ldg(g + i); pv[u] = __ldg(p + i * pstride); }
+            }
         }
+        unsigned int kgs[U], kps[U];    // keys of this iteration; fg / fp: which are candidates
+        unsigned int fg = 0, fp = 0;
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-            const int i = i0 + u * kChunkThreads + tid;
+            const int i = i0 + u * kChunkThreads;
+            if (!GENERAL) ok[u] = (i < i_end) && gv[u] > 0.f && gv[u] <= 3.402823466e38f;   // gt > 0 & finite (:27)
             if (i < i_end) {
-                vz[(size_t)b * n + i] = pv[u];
-                vg[(size_t)b * n + i] = ok[u] ? gv[u] : __int_as_float(0x7fc00000);
+                oz[i] = pv[u];
+                og[i] = ok[u] ? gv[u] : __int_as_float(0x7fc00000);
             }
-            const bool okg = ok[u] && !isnan(gv[u]), okp = ok[u] && !isnan(pv[u]);
-            nv += ok[u]; pnan += ok[u] && isnan(pv[u]); gnan += ok[u] && isnan(gv[u]);
-            const unsigned int kg = t3d_select::float_key(gv[u]), kp = t3d_select::float_key(pv[u]);
-            lt_g += okg && kg < lo_g; lt_p += okp && kp < lo_p;
-            const bool in_g = okg && kg >= lo_g && kg <= hi_g, in_p = okp && kp >= lo_p && kp <= hi_p;
-            // warp-aggregated append to the CTA's candidate lists
-            const unsigned int mg = __ballot_sync(0xffffffffu, in_g), mp = __ballot_sync(0xffffffffu, in_p);
-            if (mg) {
-                int base = 0;
-                if (lane == 0) base = atomicAdd(&scount[0], __popc(mg));
-                base = __shfl_sync(0xffffffffu, base, 0);
-                const int slot = base + __popc(mg & ((1u << lane) - 1));
-                if (in_g && slot < kCtaCand) scand[0][slot] = kg;
-            }
-            if (mp) {
-                int base = 0;
-                if (lane == 0) base = atomicAdd(&scount[1], __popc(mp));
-                base = __shfl_sync(0xffffffffu, base, 0);
-                const int slot = base + __popc(mp & ((1u << lane) - 1));
-                if (in_p && slot < kCtaCand) scand[1][slot] = kp;
-            }
+            const bool gn = GENERAL && isnan(gv[u]), pn = isnan(pv[u]);
+            const bool okg = ok[u] && !gn, okp = ok[u] && !pn;
+            nv += ok[u]; pnan += ok[u] && pn; gnan += ok[u] && gn;
+            kgs[u] = t3d_select::float_key(gv[u]); kps[u] = t3d_select::float_key(pv[u]);
+            lt_g += okg && kgs[u] < lo_g; lt_p += okp && kps[u] < lo_p;
+            fg |= (unsigned)(okg && kgs[u] >= lo_g && kgs[u] <= hi_g) << u;
+            fp |= (unsigned)(okp && kps[u] >= lo_p && kps[u] <= hi_p) << u;
+        }
+        if (fg) {                       // one shared-memory atomic per thread with candidates (~1 in 4)
+            int slot = atomicAdd(&scount[0], __popc(fg));
+#pragma unroll
+            for (int u = 0; u < U; ++u) if (fg & (1u << u)) { if (slot < kCtaCand) scand[0][slot] = kgs[u]; ++slot; }
+        }
+        if (fp) {
+            int slot = atomicAdd(&scount[1], __popc(fp));
+#pragma unroll
+            for (int u = 0; u < U; ++u) if (fp & (1u << u)) { if (slot < kCtaCand) scand[1][slot] = kps[u]; ++slot; }
         }
     }
     nv = __reduce_add_sync(0xffffffffu, nv); pnan = __reduce_add_sync(0xffffffffu, pnan);
@@ -202,7 +208,6 @@ depth_extract_kernel(const PixelSrc s, int pred_offset, float* __restrict__ vz, 
     }
     __syncthreads();
     if (tid < 5 && sred[tid]) atomicAdd(&c[tid < 3 ? tid : tid + 1], sred[tid]);
-    __syncthreads();
     if (tid < 2) {
         const int k = scount[tid];
         if (k > kCtaCand) { atomicExch(&c[3], 1); sbase[tid] = -1; }         // local overflow -> fallback
@@ -511,8 +516,12 @@ int t3d_depth_metrics(const float* pred, int pred_stride, int pred_offset,
         T3D_LAUNCH("metrics_sample_kernel", st, metrics_sample_kernel<<<B, 1024, 0, st>>>(src, pred_offset, w.bracket));
     else
         T3D_CUDA(cudaMemsetAsync(w.bracket, 0xff, (size_t)B * 4 * sizeof(unsigned int), st));   // empty brackets
-    T3D_LAUNCH("depth_extract_kernel", st, depth_extract_kernel<<<g, kChunkThreads, 0, st>>>(
-        src, pred_offset, w.vz, w.vg, w.counters, w.bracket, w.cand));
+    if (mask || src.resample)
+        T3D_LAUNCH("depth_extract_kernel", st, depth_extract_kernel<true><<<g, kChunkThreads, 0, st>>>(
+            src, pred_offset, w.vz, w.vg, w.counters, w.bracket, w.cand));
+    else
+        T3D_LAUNCH("depth_extract_kernel", st, depth_extract_kernel<false><<<g, kChunkThreads, 0, st>>>(
+            src, pred_offset, w.vz, w.vg, w.counters, w.bracket, w.cand));
     T3D_LAUNCH("median_scale_kernel", st, median_scale_kernel<<<B, kMedThreads, kCandCap * sizeof(unsigned int), st>>>(
         w.vz, w.vg, w.counters, w.cand, n, median_scaling, w.scale, out_medians));
     T3D_LAUNCH("metrics_sum_kernel", st, metrics_sum_kernel<<<g, kChunkThreads, 0, st>>>(w.vz, w.vg, w.scale, n, chunks, w.partials));

@@ -51,6 +51,13 @@ class HotPathStep:
             "metrics": torch.empty(B, 8, **f32), "metrics_f64": torch.empty(B, 8, dtype=torch.float64, device=dev),
             "medians": torch.empty(B, 2, **f32),
         }
+        # side streams: the two preprocessing calls and the metric pipeline are independent of each other
+        # (many short, latency-bound kernels) and overlap; the loss needs both thermal batches and then
+        # runs alone on the caller's stream
+        self.side = [torch.cuda.Stream(device=dev) for _ in range(2)]
+        self.fork = torch.cuda.Event()
+        self.joins = [torch.cuda.Event() for _ in range(2)]
+        self.overlap = True
         self.result = torch.zeros(RESULT_SIZE, dtype=torch.float64, device=dev)
         self.result_host = torch.zeros(RESULT_SIZE, dtype=torch.float64).pin_memory()
         self.staging: Optional[Dict[str, torch.Tensor]] = None
@@ -72,14 +79,29 @@ class HotPathStep:
         [7..13] sums of finite per-image metrics (abs_rel..acc_3)  [14] n_images  [15] unused.
         With distributed=True the vector is all-reduced (SUM) over ranks: ONE small NCCL call."""
         size = (self.W, self.H)
-        tb1 = _pre.preprocess_thermal_batch(raw1, size, path="train", out=self.pre_out[0])
-        tb2 = _pre.preprocess_thermal_batch(raw2, size, path="train", out=self.pre_out[1])
+        main = torch.cuda.current_stream(self.device)
+        if self.overlap:
+            self.fork.record(main)
+            with torch.cuda.stream(self.side[0]):           # view-2 preprocessing
+                self.side[0].wait_event(self.fork)
+                tb2 = _pre.preprocess_thermal_batch(raw2, size, path="train", out=self.pre_out[1])
+                self.joins[0].record(self.side[0])
+            with torch.cuda.stream(self.side[1]):           # depth metrics (Z of pred1 read in place)
+                self.side[1].wait_event(self.fork)
+                me = _metrics.compute_depth_metrics_batch(pred1, gt_depth, out=self.met_out)
+                self.joins[1].record(self.side[1])
+            tb1 = _pre.preprocess_thermal_batch(raw1, size, path="train", out=self.pre_out[0])
+            main.wait_event(self.joins[0])
+            main.wait_event(self.joins[1])
+        else:
+            tb1 = _pre.preprocess_thermal_batch(raw1, size, path="train", out=self.pre_out[0])
+            tb2 = _pre.preprocess_thermal_batch(raw2, size, path="train", out=self.pre_out[1])
+            me = _metrics.compute_depth_metrics_batch(pred1, gt_depth, out=self.met_out)
         # the normalisation kernel already summed the thermal gradients: the loss skips its statistics pass
         lo = _loss.fused_thermal_loss_fwd_bwd(pred1, pred2, gt1, gt2, conf1, conf2, tb1.thermal, tb2.thermal,
                                               out=self.loss_out, thermal_stats=(tb1.grad_stats, tb2.grad_stats),
                                               grad_scale=_dist.global_grad_scale(self.B) if self.distributed else None,
                                               **self.kw)
-        me = _metrics.compute_depth_metrics_batch(pred1, gt_depth, out=self.met_out)   # Z of pred1 read in place
         r = self.result
         rc = _lib.lib().t3d_pack_step_result(_lib.ptr(lo["per_sample"]), _lib.ptr(me["metrics_f64"]), self.B, self.B,
                                              _lib.ptr(r), _lib.current_stream_ptr())
