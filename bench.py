@@ -34,7 +34,7 @@ EDGE_W, SMOOTH_W, DETAIL_W, ALPHA = 0.5, 0.3, 0.4, 0.2
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=64, help="pairs per rank")
@@ -94,7 +94,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._pump, daemon=True)
             self.t.start()
@@ -260,7 +260,8 @@ def run_b200(a):
     if rank == 0:
         sampler.start()
         time.sleep(0.15)
-    _lib.profile_begin("loss_tile_kernel", a.steps + 4)
+    dominant = "loss_tile_kernel" if a.multi_scale else "loss_march_kernel"
+    _lib.profile_begin(dominant, a.steps + 4)
     n0 = _lib.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
@@ -304,7 +305,7 @@ def run_b200(a):
             "steps": a.steps, "warmup": max(a.warmup, 3), "ms_per_step": ms_dev / a.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": config_dict(a, world),
-            "roofline": {"bound": "hbm", "kernel": "loss_tile_kernel (fused loss fwd+bwd)",
+            "roofline": {"bound": "hbm", "kernel": dominant + " (fused loss fwd+bwd, both views)",
                          "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": (achieved / peak) if achieved else None, "traffic": None,
                          "algorithmic_bytes_per_launch": kern_bytes, "avg_launch_ms": kern_avg_ms,

@@ -106,80 +106,106 @@ __global__ void __launch_bounds__(256) resize_nearest_kernel(const float* __rest
 // cannot overflow because a CTA sees < 65 536 pixels.  Non-zero bins are merged
 // into the frame's global u32 histogram with atomics (integer adds: exact and
 // order independent -> bit-exact, deterministic).
-constexpr int kHistThreads = 1024;
-constexpr int kHistMaxPx = 49152;
-constexpr int kHistWords = 32768;
-constexpr int kHistMaxW = 4096;      // widest destination row whose x taps fit the shared-memory table
+constexpr int kHistThreads = 256;
+constexpr int kHistRows = 16;        // destination rows per CTA
+constexpr int kWinBins = 16384;      // privatised window of the 65 536-bin histogram (2 x u16 counters per word)
+constexpr int kWinWords = kWinBins / 2;
+constexpr int kHistMaxW = 4092;      // widest destination row: x-tap table in shared memory and < 65 536 px per CTA
 
-// grid: B * chunks; a CTA owns `rows_per` destination rows of one frame.  Warps take rows, lanes take
-// columns (4 independent pixels in flight per lane); the y tap is computed once per row, the x taps once
-// per CTA (shared-memory table).
+// One CTA = kHistRows destination rows of one frame.  Thermal frames occupy a narrow band of the 16-bit range,
+// so the CTA privatises only a 16 384-bin WINDOW of the histogram in shared memory (32 KB -> 6 CTAs per SM),
+// centred on the values of a sample row; the rare values outside the window go straight to the frame's
+// global histogram.  Integer adds only: exact and order independent -> bit-exact, deterministic.
+// Warps take rows, lanes take columns with 4 independent pixels in flight; y tap once per row, x taps from a
+// shared-memory table.  The frame's [vmin, vmax] is published for the percentile kernel.
 template <bool RESIZE>
-__global__ void __launch_bounds__(kHistThreads, 1)
+__global__ void __launch_bounds__(kHistThreads, 6)
 resize_hist_u16_kernel(const uint16_t* __restrict__ src, uint16_t* __restrict__ resized,
-                       unsigned int* __restrict__ hist, int sh, int sw, int dh, int dw, int chunks, int rows_per) {
-    extern __shared__ unsigned int sh_hist[];   // kHistWords, then the x-tap table (RESIZE only)
-    uint2* xt = reinterpret_cast<uint2*>(sh_hist + kHistWords);     // {s0 | s1 << 16, bits of f}
-    const int b = blockIdx.x / chunks, chunk = blockIdx.x - b * chunks;
-    const int y0 = chunk * rows_per, y1 = min(y0 + rows_per, dh);
+                       unsigned int* __restrict__ hist, unsigned int* __restrict__ meta /* [B] min, [B] max */,
+                       int B, int sh, int sw, int dh, int dw, int chunks) {
+    extern __shared__ unsigned int win[];       // kWinWords, then the x-tap table (RESIZE only)
+    uint2* xt = reinterpret_cast<uint2*>(win + kWinWords);          // {s0 | s1 << 16, bits of f}
+    __shared__ unsigned int s_lo, s_hi;
     const int tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
-    for (int i = tid; i < kHistWords; i += kHistThreads) sh_hist[i] = 0u;
+    const int b = blockIdx.x / chunks, chunk = blockIdx.x - b * chunks;
+    const int y0 = chunk * kHistRows, y1 = min(y0 + kHistRows, dh);
     const uint16_t* s = src + (size_t)b * sh * sw;
+    unsigned int* gh = hist + (size_t)b * 65536;
     const double scx = (double)sw / (double)dw, scy = (double)sh / (double)dh;
+    for (int i = tid; i < kWinWords; i += kHistThreads) win[i] = 0u;
     if (RESIZE) {
         for (int x = tid; x < dw; x += kHistThreads) {
             const Tap t = linear_tap(x, sw, scx);
             xt[x] = make_uint2((unsigned)t.s0 | ((unsigned)t.s1 << 16), __float_as_uint(t.c1));
         }
     }
+    if (tid == 0) { s_lo = 0xffffu; s_hi = 0u; }
     __syncthreads();
-    for (int y = y0 + wrp; y < y1; y += kHistThreads / 32) {
-        uint16_t* out_row = resized + ((size_t)b * dh + y) * dw;
+    auto pixel = [&](const uint16_t* r0, const uint16_t* r1, const Tap& ty, int x) -> unsigned int {
+        const uint2 t = xt[x];
+        const int s0 = t.x & 0xffff, s1 = t.x >> 16;
+        const float f = __uint_as_float(t.y), c0 = __fsub_rn(1.0f, f);
+        const float h0 = __fadd_rn(__fmul_rn((float)__ldg(r0 + s0), c0), __fmul_rn((float)__ldg(r0 + s1), f));
+        const float h1 = __fadd_rn(__fmul_rn((float)__ldg(r1 + s0), c0), __fmul_rn((float)__ldg(r1 + s1), f));
+        return sat_u16(__fadd_rn(__fmul_rn(h0, ty.c0), __fmul_rn(h1, ty.c1)));
+    };
+    // window centre from a strided sample of the CTA's middle row
+    {
+        const int ym = (y0 + y1) >> 1, x = (int)(((long long)tid * dw) / kHistThreads);
+        unsigned int v;
         if (RESIZE) {
+            const Tap ty = linear_tap(ym, sh, scy);
+            v = pixel(s + (size_t)ty.s0 * sw, s + (size_t)ty.s1 * sw, ty, x);
+        } else {
+            v = __ldg(s + (size_t)ym * sw + x);
+        }
+        const unsigned int lo = __reduce_min_sync(0xffffffffu, v), hi = __reduce_max_sync(0xffffffffu, v);
+        if (lane == 0) { atomicMin(&s_lo, lo); atomicMax(&s_hi, hi); }
+    }
+    __syncthreads();
+    const int centre = (int)((s_lo + s_hi) >> 1);
+    const unsigned int wbase = (unsigned)min(max(centre - kWinBins / 2, 0), 65536 - kWinBins) & ~1u;
+    __syncthreads();
+    if (tid == 0) { s_lo = 0xffffu; s_hi = 0u; }
+    __syncthreads();
+    unsigned int vlo = 0xffffu, vhi = 0u;
+    auto count = [&](unsigned int v) {
+        vlo = min(vlo, v); vhi = max(vhi, v);
+        const unsigned int d = v - wbase;
+        if (d < (unsigned)kWinBins) atomicAdd(&win[d >> 1], (d & 1) ? 0x10000u : 1u);
+        else atomicAdd(&gh[v], 1u);
+    };
+    for (int y = y0 + wrp; y < y1; y += kHistThreads / 32) {
+        if (RESIZE) {
+            uint16_t* out_row = resized + ((size_t)b * dh + y) * dw;
             const Tap ty = linear_tap(y, sh, scy);
             const uint16_t* r0 = s + (size_t)ty.s0 * sw;
             const uint16_t* r1 = s + (size_t)ty.s1 * sw;
-            for (int x0 = lane; x0 < dw; x0 += 128) {
-                float a00[4], a01[4], a10[4], a11[4], f[4];
+            constexpr int U = 4;
+            for (int x0 = lane; x0 < dw; x0 += 32 * U) {
+                unsigned int v[U];
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {                     // all 16 loads first
-                    const int x = x0 + 32 * u;
-                    if (x < dw) {
-                        const uint2 t = xt[x];
-                        const int s0 = t.x & 0xffff, s1 = t.x >> 16;
-                        f[u] = __uint_as_float(t.y);
-                        a00[u] = (float)__ldg(r0 + s0); a01[u] = (float)__ldg(r0 + s1);
-                        a10[u] = (float)__ldg(r1 + s0); a11[u] = (float)__ldg(r1 + s1);
-                    }
-                }
+                for (int u = 0; u < U; ++u) { const int x = x0 + 32 * u; v[u] = (x < dw) ? pixel(r0, r1, ty, x) : 0u; }
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
+                for (int u = 0; u < U; ++u) {
                     const int x = x0 + 32 * u;
-                    if (x < dw) {
-                        const float c0 = __fsub_rn(1.0f, f[u]), c1 = f[u];
-                        const float h0 = __fadd_rn(__fmul_rn(a00[u], c0), __fmul_rn(a01[u], c1));
-                        const float h1 = __fadd_rn(__fmul_rn(a10[u], c0), __fmul_rn(a11[u], c1));
-                        const uint16_t v = sat_u16(__fadd_rn(__fmul_rn(h0, ty.c0), __fmul_rn(h1, ty.c1)));
-                        out_row[x] = v;
-                        atomicAdd(&sh_hist[v >> 1], (v & 1) ? 0x10000u : 1u);
-                    }
+                    if (x < dw) { out_row[x] = (uint16_t)v[u]; count(v[u]); }
                 }
             }
         } else {
             const uint16_t* r0 = s + (size_t)y * sw;
-            for (int x = lane; x < dw; x += 32) {
-                const uint16_t v = __ldg(r0 + x);
-                atomicAdd(&sh_hist[v >> 1], (v & 1) ? 0x10000u : 1u);
-            }
+            for (int x = lane; x < dw; x += 32) count(__ldg(r0 + x));
         }
     }
+    vlo = __reduce_min_sync(0xffffffffu, vlo); vhi = __reduce_max_sync(0xffffffffu, vhi);
+    if (lane == 0 && vlo <= vhi) { atomicMin(&s_lo, vlo); atomicMax(&s_hi, vhi); }
     __syncthreads();
-    unsigned int* gh = hist + (size_t)b * 65536;
-    for (int i = tid; i < kHistWords; i += kHistThreads) {
-        const unsigned int w = sh_hist[i];
-        if (w & 0xffffu) atomicAdd(&gh[2 * i], w & 0xffffu);
-        if (w >> 16) atomicAdd(&gh[2 * i + 1], w >> 16);
+    for (int i = tid; i < kWinWords; i += kHistThreads) {          // sparse merge of the window
+        const unsigned int w = win[i];
+        if (w & 0xffffu) atomicAdd(&gh[wbase + 2 * i], w & 0xffffu);
+        if (w >> 16) atomicAdd(&gh[wbase + 2 * i + 1], w >> 16);
     }
+    if (tid == 0 && s_lo <= s_hi) { atomicMin(&meta[b], s_lo); atomicMax(&meta[B + b], s_hi); }
 }
 
 // np.percentile(method='linear') finish (numpy _quantile/_lerp): a, b fp32 order
@@ -197,21 +223,20 @@ __device__ __forceinline__ void percentile_ranks(int n, double q, unsigned int* 
     *g = __dsub_rn(vi, fl);
 }
 
-// K2b: p2 / p98 from the exact histogram: one CTA per frame, 1024 threads x 64 bins.
-__global__ void __launch_bounds__(1024) percentile_from_hist_kernel(const unsigned int* __restrict__ hist, int n,
+// K2b: p2 / p98 from the exact histogram: one CTA per frame scans only the frame's [vmin, vmax] bins.
+__global__ void __launch_bounds__(1024) percentile_from_hist_kernel(const unsigned int* __restrict__ hist,
+                                                                    const unsigned int* __restrict__ meta, int B, int n,
                                                                     double* __restrict__ out_p) {
     __shared__ unsigned int warp_tot[32];
     __shared__ float found[4];
     const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
-    const unsigned int* h = hist + (size_t)b * 65536 + tid * 64;
-    unsigned int loc[64];
+    const unsigned int vmin = min(meta[b], 65535u), vmax = min(meta[B + b], 65535u);
+    const int range = (vmax >= vmin) ? (int)(vmax - vmin + 1) : 0;
+    const int span = (range + 1023) / 1024;                      // consecutive bins per thread (<= 64)
+    const unsigned int* h = hist + (size_t)b * 65536;
+    const int first = (int)vmin + tid * span;
     unsigned int sum = 0;
-#pragma unroll
-    for (int i = 0; i < 64; i += 4) {
-        const uint4 v = __ldg(reinterpret_cast<const uint4*>(h + i));
-        loc[i] = v.x; loc[i + 1] = v.y; loc[i + 2] = v.z; loc[i + 3] = v.w;
-        sum += v.x + v.y + v.z + v.w;
-    }
+    for (int k = 0; k < span; ++k) { const int v = first + k; if (v <= (int)vmax) sum += __ldg(h + v); }
     unsigned int incl = sum;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -239,9 +264,9 @@ __global__ void __launch_bounds__(1024) percentile_from_hist_kernel(const unsign
     for (int r = 0; r < 4; ++r) {
         if (ranks[r] >= excl && ranks[r] < excl + sum) {
             unsigned int c = excl;
-            for (int i = 0; i < 64; ++i) {
-                c += loc[i];
-                if (ranks[r] < c) { found[r] = (float)(tid * 64 + i); break; }
+            for (int q = 0; q < span; ++q) {
+                c += __ldg(h + first + q);
+                if (ranks[r] < c) { found[r] = (float)(first + q); break; }
             }
         }
     }
@@ -357,52 +382,85 @@ __global__ void __launch_bounds__(256) normalize_u16_kernel(const uint16_t* __re
 // between floor(p2) and ceil(p98) replaces the per-pixel fp64 divide (same function, same bits), and the
 // sums of |Dx gray|, |Dy gray| of the OUTPUT image are reduced per CTA into stats[b][band][0..1]
 // (gray = 0.299 v + 0.587 v + 0.114 v in fp32 when the output is replicated to 3 planes).
-constexpr int kNormBands = 8;        // CTAs per frame == statistic partials per frame (T3D_STATS_TILES)
-constexpr int kLutMax = 12288;
-constexpr int kNormThreads = 512;
+constexpr int kNormBands = 24;       // CTAs per frame == statistic partials per frame (T3D_STATS_TILES)
+constexpr int kLutMax = 6144;        // float2 entries (48 KB)
+constexpr int kNormThreads = 256;
 
+// Thread layout: up to 128 column-quads x row-lanes; a row-lane marches down its rows keeping the row below
+// in registers (it is the current row of the next iteration), so every u16 row is loaded once per column.
 template <int REP>
 __global__ void __launch_bounds__(kNormThreads) normalize_stats_u16_kernel(const uint16_t* __restrict__ src,
                                                                            const double* __restrict__ p,
                                                                            float* __restrict__ dst, int H, int W,
                                                                            float* __restrict__ stats) {
-    extern __shared__ float lut[];
+    extern __shared__ float2 lut[];                 // {normalised value, its gray} for v in [lo-1, hi+1]
     __shared__ float red[kNormThreads / 32][2];
     const int b = blockIdx.y, band = blockIdx.x, tid = threadIdx.x;
     const int n = H * W;
     const double p2 = p[2 * b], p98 = p[2 * b + 1], den = __dsub_rn(p98, p2);
-    const int lo = (int)floor(p2), hi = (int)ceil(p98);
-    const int range = hi - lo + 1;
+    auto gray = [&](float o) -> float { return (REP == 3) ? gray3(o, o, o) : o; };
+    // below floor(p2) the result clips to 0, above ceil(p98) to 1: one LUT entry each side covers the rest
+    const int lom1 = (int)floor(p2) - 1, hip1 = (int)ceil(p98) + 1;
+    const int range = hip1 - lom1 + 1;
     const bool use_lut = range <= kLutMax;
     if (use_lut)
-        for (int k = tid; k < range; k += kNormThreads) lut[k] = normalize_px((double)(lo + k), p2, den);
+        for (int k = tid; k < range; k += kNormThreads) {
+            const float o = normalize_px((double)(lom1 + k), p2, den);
+            lut[k] = make_float2(o, gray(o));
+        }
     __syncthreads();
-    auto norm = [&](int v) -> float {
-        if (!use_lut) return normalize_px((double)v, p2, den);
-        return (v < lo) ? 0.0f : ((v > hi) ? 1.0f : lut[v - lo]);     // below p2 -> clip 0, above p98 -> clip 1
+    auto look = [&](int v) -> float2 {
+        if (use_lut) return lut[min(max(v, lom1), hip1) - lom1];
+        const float o = normalize_px((double)v, p2, den);
+        return make_float2(o, gray(o));
     };
-    auto gray = [&](float o) -> float { return (REP == 3) ? gray3(o, o, o) : o; };
-    const uint16_t* s = src + (size_t)b * n;
-    float* d = dst + (size_t)b * REP * n;
+    const uint16_t* __restrict__ s = src + (size_t)b * n;
+    float* __restrict__ d = dst + (size_t)b * REP * n;
     const int rows_per = (H + kNormBands - 1) / kNormBands;
     const int y0 = band * rows_per, y1 = min(y0 + rows_per, H);
     const int qw = W >> 2;
+    const int CQ = min(qw, 128), RL = kNormThreads / CQ;
+    const int cq0 = tid % CQ, rl = tid / CQ;
+    const int sub = (y1 - y0 + RL - 1) / RL;
+    const int ya = y0 + rl * sub, yb = min(ya + sub, y1);
     float tx = 0.f, ty = 0.f;
-    for (int q = tid; q < (y1 - y0) * qw; q += kNormThreads) {
-        const int i = y0 + q / qw, j = 4 * (q % qw);
-        const size_t idx = (size_t)i * W + j;
-        const ushort4 v = __ldg(reinterpret_cast<const ushort4*>(s + idx));
-        const float4 o = make_float4(norm(v.x), norm(v.y), norm(v.z), norm(v.w));
+    if (rl < RL && ya < yb) {
+        for (int cq = cq0; cq < qw; cq += CQ) {
+            const int j = 4 * cq;
+            const bool has_right = (j + 4 < W);
+            const uint16_t* col = s + j;
+            // row ya; the raw values of the row after next are always in flight (software prefetch)
+            ushort4 v = __ldg(reinterpret_cast<const ushort4*>(col + (size_t)ya * W));
+            float2 c0 = look(v.x), c1 = look(v.y), c2 = look(v.z), c3 = look(v.w);
+            float gr = has_right ? look(__ldg(col + (size_t)ya * W + 4)).y : c3.y;
+            const int last = (stats ? min(yb, H - 1) : yb - 1);          // last row that must be fetched as "below"
+            ushort4 pw = make_ushort4(0, 0, 0, 0); unsigned short pr = 0;
+            if (ya + 1 <= last) {
+                pw = __ldg(reinterpret_cast<const ushort4*>(col + (size_t)(ya + 1) * W));
+                if (has_right) pr = __ldg(col + (size_t)(ya + 1) * W + 4);
+            }
+            for (int i = ya; i < yb; ++i) {
+                const size_t idx = (size_t)i * W + j;
+                const ushort4 w = pw; const unsigned short wr = pr;
+                const bool have_next = (i + 1 <= last);
+                if (i + 2 <= last) {                                      // prefetch row i+2
+                    pw = __ldg(reinterpret_cast<const ushort4*>(col + (size_t)(i + 2) * W));
+                    if (has_right) pr = __ldg(col + (size_t)(i + 2) * W + 4);
+                }
+                float2 n0 = c0, n1 = c1, n2 = c2, n3 = c3;
+                float ngr = gr;
+                if (have_next) {
+                    n0 = look(w.x); n1 = look(w.y); n2 = look(w.z); n3 = look(w.w);
+                    ngr = has_right ? look(wr).y : n3.y;
+                }
+                const float4 o = make_float4(c0.x, c1.x, c2.x, c3.x);
 #pragma unroll
-        for (int r = 0; r < REP; ++r) stg_stream_f4(d + (size_t)r * n + idx, o);
-        if (stats) {
-            const float g0 = gray(o.x), g1 = gray(o.y), g2 = gray(o.z), g3 = gray(o.w);
-            tx += fabsf(g1 - g0) + fabsf(g2 - g1) + fabsf(g3 - g2);
-            if (j + 4 < W) tx += fabsf(gray(norm(__ldg(s + idx + 4))) - g3);
-            if (i + 1 < H) {
-                const ushort4 w = __ldg(reinterpret_cast<const ushort4*>(s + idx + W));
-                ty += fabsf(gray(norm(w.x)) - g0) + fabsf(gray(norm(w.y)) - g1) +
-                      fabsf(gray(norm(w.z)) - g2) + fabsf(gray(norm(w.w)) - g3);
+                for (int r = 0; r < REP; ++r) stg_stream_f4(d + (size_t)r * n + idx, o);
+                if (stats) {
+                    tx += fabsf(c1.y - c0.y) + fabsf(c2.y - c1.y) + fabsf(c3.y - c2.y) + fabsf(gr - c3.y);
+                    ty += fabsf(n0.y - c0.y) + fabsf(n1.y - c1.y) + fabsf(n2.y - c2.y) + fabsf(n3.y - c3.y);
+                }
+                c0 = n0; c1 = n1; c2 = n2; c3 = n3; gr = ngr;
             }
         }
     }
@@ -486,7 +544,8 @@ int t3d_resize_nearest_f32(const float* src, float* dst, int B, int src_h, int s
 
 size_t t3d_preprocess_workspace_bytes(int B, int dst_h, int dst_w) {
     if (B < 1 || dst_h < 1 || dst_w < 1) return 0;
-    return t3d_align_up((size_t)B * dst_h * dst_w * sizeof(uint16_t), 256);
+    return t3d_align_up((size_t)B * dst_h * dst_w * sizeof(uint16_t), 256) +      // resized frames
+           t3d_align_up((size_t)(2 * B + 1) * sizeof(unsigned int), 256);          // per-frame vmin / vmax, work queue
 }
 
 int t3d_preprocess_train_u16(const uint16_t* raw, int B, int src_h, int src_w, int dst_h, int dst_w,
@@ -503,42 +562,44 @@ int t3d_preprocess_train_u16(const uint16_t* raw, int B, int src_h, int src_w, i
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     uint16_t* resized = reinterpret_cast<uint16_t*>(workspace);
     const int npx = dst_h * dst_w;
+    unsigned int* meta = reinterpret_cast<unsigned int*>(reinterpret_cast<char*>(workspace) +
+                                                         t3d_align_up((size_t)B * npx * sizeof(uint16_t), 256));
     const bool same = (src_h == dst_h && src_w == dst_w);
     T3D_CUDA(cudaMemsetAsync(hist, 0, (size_t)B * 65536 * sizeof(unsigned int), st));
-    T3D_REQUIRE(dst_w <= kHistMaxW && src_w <= 65535, "frame too wide (dst_w <= 4096, src_w <= 65535)");
-    const int rows_cap = kHistMaxPx / dst_w;                    // < 65 536 pixels per CTA: u16 bins cannot overflow
-    const int chunks = (dst_h + rows_cap - 1) / rows_cap;
-    const int rows_per = (dst_h + chunks - 1) / chunks;
-    const size_t hsmem = (size_t)kHistWords * 4 + (same ? 0 : (size_t)dst_w * sizeof(uint2));
+    T3D_CUDA(cudaMemsetAsync(meta, 0xff, (size_t)B * sizeof(unsigned int), st));            // vmin = 0xffffffff
+    T3D_CUDA(cudaMemsetAsync(meta + B, 0, (size_t)(B + 1) * sizeof(unsigned int), st));     // vmax = 0, queue = 0
+    T3D_REQUIRE(dst_w <= kHistMaxW && src_w <= 65535, "frame too wide (dst_w <= 4092, src_w <= 65535)");
+    const int chunks = (dst_h + kHistRows - 1) / kHistRows;       // kHistRows * dst_w < 65 536: u16 bins cannot overflow
+    const size_t hsmem = (size_t)kWinWords * 4 + (same ? 0 : (size_t)dst_w * sizeof(uint2));
     static bool attr_set = false;
     if (!attr_set) {
-        const int max_smem = kHistWords * 4 + kHistMaxW * (int)sizeof(uint2);
+        const int max_smem = kWinWords * 4 + kHistMaxW * (int)sizeof(uint2);
         T3D_CUDA(cudaFuncSetAttribute(resize_hist_u16_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
         T3D_CUDA(cudaFuncSetAttribute(resize_hist_u16_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
         attr_set = true;
     }
     if (same)
         T3D_LAUNCH("resize_hist_u16_kernel", st, resize_hist_u16_kernel<false><<<B * chunks, kHistThreads, hsmem, st>>>(
-            raw, resized, hist, src_h, src_w, dst_h, dst_w, chunks, rows_per));
+            raw, resized, hist, meta, B, src_h, src_w, dst_h, dst_w, chunks));
     else
         T3D_LAUNCH("resize_hist_u16_kernel", st, resize_hist_u16_kernel<true><<<B * chunks, kHistThreads, hsmem, st>>>(
-            raw, resized, hist, src_h, src_w, dst_h, dst_w, chunks, rows_per));
-    T3D_LAUNCH("percentile_from_hist_kernel", st, percentile_from_hist_kernel<<<B, 1024, 0, st>>>(hist, npx, percentiles));
+            raw, resized, hist, meta, B, src_h, src_w, dst_h, dst_w, chunks));
+    T3D_LAUNCH("percentile_from_hist_kernel", st, percentile_from_hist_kernel<<<B, 1024, 0, st>>>(hist, meta, B, npx, percentiles));
     const uint16_t* nsrc = same ? raw : resized;
     const int vec = (dst_w % 4 == 0) && t3d_aligned16(out) && ((reinterpret_cast<uintptr_t>(nsrc) & 7u) == 0);
     if (vec) {
         static bool nattr = false;
         if (!nattr) {
-            T3D_CUDA(cudaFuncSetAttribute(normalize_stats_u16_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kLutMax * 4));
-            T3D_CUDA(cudaFuncSetAttribute(normalize_stats_u16_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kLutMax * 4));
+            T3D_CUDA(cudaFuncSetAttribute(normalize_stats_u16_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kLutMax * 8));
+            T3D_CUDA(cudaFuncSetAttribute(normalize_stats_u16_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kLutMax * 8));
             nattr = true;
         }
         dim3 grid(kNormBands, (unsigned)B);
         if (out_channels == 3)
-            T3D_LAUNCH("normalize_stats_u16_kernel", st, normalize_stats_u16_kernel<3><<<grid, kNormThreads, kLutMax * 4, st>>>(
+            T3D_LAUNCH("normalize_stats_u16_kernel", st, normalize_stats_u16_kernel<3><<<grid, kNormThreads, kLutMax * 8, st>>>(
                 nsrc, percentiles, out, dst_h, dst_w, grad_stats));
         else
-            T3D_LAUNCH("normalize_stats_u16_kernel", st, normalize_stats_u16_kernel<1><<<grid, kNormThreads, kLutMax * 4, st>>>(
+            T3D_LAUNCH("normalize_stats_u16_kernel", st, normalize_stats_u16_kernel<1><<<grid, kNormThreads, kLutMax * 8, st>>>(
                 nsrc, percentiles, out, dst_h, dst_w, grad_stats));
     } else {
         T3D_REQUIRE(grad_stats == nullptr, "grad_stats needs dst_w %% 4 == 0 (t3d_preprocess_stats_tiles() == 0 here)");
