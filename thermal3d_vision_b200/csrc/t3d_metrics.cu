@@ -53,7 +53,7 @@ MetricsWs metrics_ws(void* base, int B, int n, int chunks) {
     w.vz = reinterpret_cast<float*>(take((size_t)B * n * 4));
     w.vg = reinterpret_cast<float*>(take((size_t)B * n * 4));
     w.cand = reinterpret_cast<unsigned int*>(take((size_t)B * 2 * kCandCap * sizeof(unsigned int)));
-    w.scale = reinterpret_cast<float*>(take((size_t)B * sizeof(float)));
+    w.scale = reinterpret_cast<float*>(take((size_t)B * 2 * sizeof(float)));
     w.partials = reinterpret_cast<double*>(take((size_t)B * chunks * kNPart * sizeof(double)));
     w.total = off;
     return w;
@@ -85,48 +85,47 @@ __device__ __forceinline__ void read_pixel(const PixelSrc& s, const float* __res
 }
 
 // ------------------------------------------------------------------ S: sample + bracket
+// grid (2, B): blockIdx.x = stream (0 = gt, 1 = pred)
 __global__ void __launch_bounds__(1024, 1) metrics_sample_kernel(const PixelSrc s, int pred_offset,
                                                                  unsigned int* __restrict__ bracket) {
-    __shared__ unsigned int key[2][kSample];
+    __shared__ unsigned int key[kSample];
     __shared__ t3d_select::Smem sm;
-    __shared__ int cnt[2];
-    const int b = blockIdx.x, tid = threadIdx.x, n = s.H * s.W;
+    __shared__ int cnt;
+    const int a = blockIdx.x, b = blockIdx.y, tid = threadIdx.x, n = s.H * s.W;
     const float* g = s.gt + (size_t)b * s.gt_h * s.gt_w;
     const float* p = s.pred + (size_t)b * n * s.pred_stride + pred_offset;
     const unsigned char* m = s.mask ? s.mask + (size_t)b * n : nullptr;
-    if (tid < 2) cnt[tid] = 0;
+    if (tid == 0) cnt = 0;
     __syncthreads();
-    int c0 = 0, c1 = 0;
+    int c = 0;
 #pragma unroll
     for (int q = 0; q < kSample / 1024; ++q) {
         const int k = q * 1024 + tid;
         // n >= kSample: evenly strided distinct pixels; smaller images: every pixel exactly once
         const int i = (n >= kSample) ? (int)(((long long)k * n) / kSample) : k;
-        unsigned int kg = 0xffffffffu, kp = 0xffffffffu;          // sentinel: not part of the sample
+        unsigned int kk = 0xffffffffu;                             // sentinel: not part of the sample
         if (i < n) {
             float gv, pv; bool ok;
             read_pixel(s, g, p, m, i, gv, pv, ok);
-            if (ok && !isnan(gv)) { kg = t3d_select::float_key(gv); ++c0; }
-            if (ok && !isnan(pv)) { kp = t3d_select::float_key(pv); ++c1; }
+            const float v = (a == 0) ? gv : pv;
+            if (ok && !isnan(v)) { kk = t3d_select::float_key(v); ++c; }
         }
-        key[0][k] = kg; key[1][k] = kp;
+        key[k] = kk;
     }
-    c0 = __reduce_add_sync(0xffffffffu, c0); c1 = __reduce_add_sync(0xffffffffu, c1);
-    if ((tid & 31) == 0) { atomicAdd(&cnt[0], c0); atomicAdd(&cnt[1], c1); }
+    c = __reduce_add_sync(0xffffffffu, c);
+    if ((tid & 31) == 0) atomicAdd(&cnt, c);
     __syncthreads();
-    // two order statistics of each sample, +-5 sigma around the sample median rank (radix select in smem)
-    for (int a = 0; a < 2; ++a) {
-        const int mm = cnt[a];
-        unsigned int lo = 1u, hi = 0u;                             // no bracket -> fallback
-        if (mm >= 64) {                                            // block-uniform
-            const int d = (int)ceilf(2.5f * sqrtf((float)mm)) + 2;
-            const int mid = mm / 2, rl = mid - d, rh = mid + d;
-            auto get = [&](int i, float* v) { const unsigned int k = key[a][i]; *v = t3d_select::key_float(k); return k != 0xffffffffu; };
-            lo = (rl <= 0) ? 0u : t3d_select::float_key(t3d_select::select_rank(sm, kSample, (unsigned)rl, get));
-            hi = (rh >= mm - 1) ? 0xfffffffeu : t3d_select::float_key(t3d_select::select_rank(sm, kSample, (unsigned)rh, get));
-        }
-        if (tid == 0) { bracket[4 * b + 2 * a] = lo; bracket[4 * b + 2 * a + 1] = hi; }
+    // two order statistics of the sample, +-5 sigma around the sample median rank (radix select in smem)
+    const int mm = cnt;
+    unsigned int lo = 1u, hi = 0u;                                 // no bracket -> fallback
+    if (mm >= 64) {                                                // block-uniform
+        const int d = (int)ceilf(2.5f * sqrtf((float)mm)) + 2;
+        const int mid = mm / 2, rl = mid - d, rh = mid + d;
+        auto get = [&](int i, float* v) { const unsigned int k = key[i]; *v = t3d_select::key_float(k); return k != 0xffffffffu; };
+        lo = (rl <= 0) ? 0u : t3d_select::float_key(t3d_select::select_rank(sm, kSample, (unsigned)rl, get));
+        hi = (rh >= mm - 1) ? 0xfffffffeu : t3d_select::float_key(t3d_select::select_rank(sm, kSample, (unsigned)rh, get));
     }
+    if (tid == 0) { bracket[4 * b + 2 * a] = lo; bracket[4 * b + 2 * a + 1] = hi; }
 }
 
 // ------------------------------------------------------------------ X: extract (K5) + count + collect
@@ -229,20 +228,20 @@ depth_extract_kernel(const PixelSrc s, int pred_offset, float* __restrict__ vz, 
 // ------------------------------------------------------------------ M: exact medians -> scale
 constexpr int kMedThreads = t3d_select::kThreads;
 
+// grid (2, B): blockIdx.x = stream (0 = gt, 1 = pred); writes medians[b][stream]
 __global__ void __launch_bounds__(kMedThreads, 1)
 median_scale_kernel(const float* __restrict__ vz, const float* __restrict__ vg, const int* __restrict__ counters,
-                    const unsigned int* __restrict__ cand, int n, int median_scaling, float* __restrict__ scale,
-                    float* __restrict__ out_medians) {
+                    const unsigned int* __restrict__ cand, int n, int median_scaling, float* __restrict__ medians) {
     extern __shared__ unsigned int skeys[];                       // kCandCap keys
     __shared__ t3d_select::Smem sm;
-    const int b = blockIdx.x, tid = threadIdx.x;
+    const int a = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
     const int* c = counters + 8 * b;
     const int nv = c[0];
-    float med[2] = {0.f, 0.f};
+    float med = 0.f;
     if (nv > 0 && median_scaling) {
         const unsigned int r0 = (unsigned)(nv - 1) / 2, r1 = (unsigned)nv / 2;
-        for (int a = 0; a < 2; ++a) {                             // a = 0: gt, 1: pred
-            if (c[a == 0 ? 2 : 1] > 0) { med[a] = __int_as_float(0x7fc00000); continue; }   // NaN in the stream
+        if (c[a == 0 ? 2 : 1] > 0) med = __int_as_float(0x7fc00000);      // NaN in the stream -> median NaN
+        else {
             const int lt = c[4 + a], nc = c[6 + a];
             const bool bracket_ok = (c[3] == 0) && ((int)r0 >= lt) && ((int)r1 < lt + nc) && nc <= kCandCap;
             float x0, x1;
@@ -276,14 +275,10 @@ median_scale_kernel(const float* __restrict__ vz, const float* __restrict__ vg, 
                 x0 = t3d_select::select_rank(sm, n, r0, get);
                 x1 = (r1 == r0) ? x0 : t3d_select::select_rank(sm, n, r1, get);
             }
-            med[a] = (r1 == r0) ? x0 : __fmul_rn(__fadd_rn(x0, x1), 0.5f);   // np.median: fp32 mean of the middles
-            __syncthreads();
+            med = (r1 == r0) ? x0 : __fmul_rn(__fadd_rn(x0, x1), 0.5f);   // np.median: fp32 mean of the middles
         }
     }
-    if (tid == 0) {
-        scale[b] = (nv > 0 && median_scaling) ? __fdiv_rn(med[0], med[1]) : 1.0f;   // utils/metrics.py:47
-        if (out_medians) { out_medians[2 * b] = med[0]; out_medians[2 * b + 1] = med[1]; }
-    }
+    if (tid == 0) medians[2 * b + a] = med;
 }
 
 // ------------------------------------------------------------------ M3: per-pixel terms
@@ -307,10 +302,12 @@ __device__ __forceinline__ void metric_terms(float gt, float z, float s, float a
 
 __global__ void __launch_bounds__(kChunkThreads)
 metrics_sum_kernel(const float* __restrict__ vz, const float* __restrict__ vg,
-                   const float* __restrict__ scale, int n, int chunks, double* __restrict__ partials) {
+                   const float* __restrict__ medians, const int* __restrict__ counters, int median_scaling,
+                   int n, int chunks, double* __restrict__ partials) {
     __shared__ double red[kChunkThreads / 32][kNPart];
     const int b = blockIdx.y, chunk = blockIdx.x;
-    const float s = scale[b];
+    // scale = median(gt) / median(pred)  (utils/metrics.py:47)
+    const float s = (median_scaling && counters[8 * b] > 0) ? __fdiv_rn(medians[2 * b], medians[2 * b + 1]) : 1.0f;
     const float* g = vg + (size_t)b * n;
     const float* z = vz + (size_t)b * n;
     double acc[4] = {0, 0, 0, 0};
@@ -513,7 +510,7 @@ int t3d_depth_metrics(const float* pred, int pred_stride, int pred_offset,
         attr_set = true;
     }
     if (median_scaling)
-        T3D_LAUNCH("metrics_sample_kernel", st, metrics_sample_kernel<<<B, 1024, 0, st>>>(src, pred_offset, w.bracket));
+        T3D_LAUNCH("metrics_sample_kernel", st, metrics_sample_kernel<<<dim3(2, B), 1024, 0, st>>>(src, pred_offset, w.bracket));
     else
         T3D_CUDA(cudaMemsetAsync(w.bracket, 0xff, (size_t)B * 4 * sizeof(unsigned int), st));   // empty brackets
     if (mask || src.resample)
@@ -522,9 +519,11 @@ int t3d_depth_metrics(const float* pred, int pred_stride, int pred_offset,
     else
         T3D_LAUNCH("depth_extract_kernel", st, depth_extract_kernel<false><<<g, kChunkThreads, 0, st>>>(
             src, pred_offset, w.vz, w.vg, w.counters, w.bracket, w.cand));
-    T3D_LAUNCH("median_scale_kernel", st, median_scale_kernel<<<B, kMedThreads, kCandCap * sizeof(unsigned int), st>>>(
-        w.vz, w.vg, w.counters, w.cand, n, median_scaling, w.scale, out_medians));
-    T3D_LAUNCH("metrics_sum_kernel", st, metrics_sum_kernel<<<g, kChunkThreads, 0, st>>>(w.vz, w.vg, w.scale, n, chunks, w.partials));
+    float* medians = out_medians ? out_medians : w.scale;       // [B][2]: median(gt), median(pred)
+    T3D_LAUNCH("median_scale_kernel", st, median_scale_kernel<<<dim3(2, B), kMedThreads, kCandCap * sizeof(unsigned int), st>>>(
+        w.vz, w.vg, w.counters, w.cand, n, median_scaling, medians));
+    T3D_LAUNCH("metrics_sum_kernel", st, metrics_sum_kernel<<<g, kChunkThreads, 0, st>>>(
+        w.vz, w.vg, medians, w.counters, median_scaling, n, chunks, w.partials));
     T3D_LAUNCH("metrics_finalize_kernel", st, metrics_finalize_kernel<<<B, 32, 0, st>>>(w.partials, w.counters, chunks, out, out_f64));
     return T3D_OK;
 }

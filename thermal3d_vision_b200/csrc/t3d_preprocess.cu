@@ -107,21 +107,35 @@ __global__ void __launch_bounds__(256) resize_nearest_kernel(const float* __rest
 // into the frame's global u32 histogram with atomics (integer adds: exact and
 // order independent -> bit-exact, deterministic).
 constexpr int kHistThreads = 256;
-constexpr int kHistRows = 16;        // destination rows per CTA
+constexpr int kHistRows = 32;        // destination rows per CTA
 constexpr int kWinBins = 16384;      // privatised window of the 65 536-bin histogram (2 x u16 counters per word)
 constexpr int kWinWords = kWinBins / 2;
-constexpr int kHistMaxW = 4092;      // widest destination row: x-tap table in shared memory and < 65 536 px per CTA
+constexpr int kHistMaxW = 2044;      // widest destination row: x-tap table in shared memory and < 65 536 px per CTA
+
+// all bilinear taps of one resize geometry, computed once per call (fp64 tap arithmetic is not cheap)
+__global__ void build_taps_kernel(int sh, int sw, int dh, int dw, uint2* __restrict__ xt, uint4* __restrict__ yt) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < dw) {
+        const Tap t = linear_tap(i, sw, (double)sw / (double)dw);
+        xt[i] = make_uint2((unsigned)t.s0 | ((unsigned)t.s1 << 16), __float_as_uint(t.c1));
+    }
+    if (i < dh) {
+        const Tap t = linear_tap(i, sh, (double)sh / (double)dh);
+        yt[i] = make_uint4((unsigned)t.s0, (unsigned)t.s1, __float_as_uint(t.c0), __float_as_uint(t.c1));
+    }
+}
 
 // One CTA = kHistRows destination rows of one frame.  Thermal frames occupy a narrow band of the 16-bit range,
 // so the CTA privatises only a 16 384-bin WINDOW of the histogram in shared memory (32 KB -> 6 CTAs per SM),
 // centred on the values of a sample row; the rare values outside the window go straight to the frame's
 // global histogram.  Integer adds only: exact and order independent -> bit-exact, deterministic.
-// Warps take rows, lanes take columns with 4 independent pixels in flight; y tap once per row, x taps from a
-// shared-memory table.  The frame's [vmin, vmax] is published for the percentile kernel.
+// Warps take rows, lanes take columns with 4 independent pixels in flight.  The frame's [vmin, vmax] is
+// published for the percentile kernel.
 template <bool RESIZE>
 __global__ void __launch_bounds__(kHistThreads, 6)
 resize_hist_u16_kernel(const uint16_t* __restrict__ src, uint16_t* __restrict__ resized,
                        unsigned int* __restrict__ hist, unsigned int* __restrict__ meta /* [B] min, [B] max */,
+                       const uint2* __restrict__ gxt, const uint4* __restrict__ gyt,
                        int B, int sh, int sw, int dh, int dw, int chunks) {
     extern __shared__ unsigned int win[];       // kWinWords, then the x-tap table (RESIZE only)
     uint2* xt = reinterpret_cast<uint2*>(win + kWinWords);          // {s0 | s1 << 16, bits of f}
@@ -131,16 +145,15 @@ resize_hist_u16_kernel(const uint16_t* __restrict__ src, uint16_t* __restrict__ 
     const int y0 = chunk * kHistRows, y1 = min(y0 + kHistRows, dh);
     const uint16_t* s = src + (size_t)b * sh * sw;
     unsigned int* gh = hist + (size_t)b * 65536;
-    const double scx = (double)sw / (double)dw, scy = (double)sh / (double)dh;
     for (int i = tid; i < kWinWords; i += kHistThreads) win[i] = 0u;
-    if (RESIZE) {
-        for (int x = tid; x < dw; x += kHistThreads) {
-            const Tap t = linear_tap(x, sw, scx);
-            xt[x] = make_uint2((unsigned)t.s0 | ((unsigned)t.s1 << 16), __float_as_uint(t.c1));
-        }
-    }
+    if (RESIZE) for (int x = tid; x < dw; x += kHistThreads) xt[x] = __ldg(gxt + x);
     if (tid == 0) { s_lo = 0xffffu; s_hi = 0u; }
     __syncthreads();
+    auto ytap = [&](int y) -> Tap {
+        const uint4 t = __ldg(gyt + y);
+        Tap r; r.s0 = (int)t.x; r.s1 = (int)t.y; r.c0 = __uint_as_float(t.z); r.c1 = __uint_as_float(t.w);
+        return r;
+    };
     auto pixel = [&](const uint16_t* r0, const uint16_t* r1, const Tap& ty, int x) -> unsigned int {
         const uint2 t = xt[x];
         const int s0 = t.x & 0xffff, s1 = t.x >> 16;
@@ -154,7 +167,7 @@ resize_hist_u16_kernel(const uint16_t* __restrict__ src, uint16_t* __restrict__ 
         const int ym = (y0 + y1) >> 1, x = (int)(((long long)tid * dw) / kHistThreads);
         unsigned int v;
         if (RESIZE) {
-            const Tap ty = linear_tap(ym, sh, scy);
+            const Tap ty = ytap(ym);
             v = pixel(s + (size_t)ty.s0 * sw, s + (size_t)ty.s1 * sw, ty, x);
         } else {
             v = __ldg(s + (size_t)ym * sw + x);
@@ -178,7 +191,7 @@ resize_hist_u16_kernel(const uint16_t* __restrict__ src, uint16_t* __restrict__ 
     for (int y = y0 + wrp; y < y1; y += kHistThreads / 32) {
         if (RESIZE) {
             uint16_t* out_row = resized + ((size_t)b * dh + y) * dw;
-            const Tap ty = linear_tap(y, sh, scy);
+            const Tap ty = ytap(y);
             const uint16_t* r0 = s + (size_t)ty.s0 * sw;
             const uint16_t* r1 = s + (size_t)ty.s1 * sw;
             constexpr int U = 4;
@@ -200,12 +213,18 @@ resize_hist_u16_kernel(const uint16_t* __restrict__ src, uint16_t* __restrict__ 
     vlo = __reduce_min_sync(0xffffffffu, vlo); vhi = __reduce_max_sync(0xffffffffu, vhi);
     if (lane == 0 && vlo <= vhi) { atomicMin(&s_lo, vlo); atomicMax(&s_hi, vhi); }
     __syncthreads();
-    for (int i = tid; i < kWinWords; i += kHistThreads) {          // sparse merge of the window
-        const unsigned int w = win[i];
-        if (w & 0xffffu) atomicAdd(&gh[wbase + 2 * i], w & 0xffffu);
-        if (w >> 16) atomicAdd(&gh[wbase + 2 * i + 1], w >> 16);
+    const unsigned int lo = s_lo, hi = s_hi;
+    if (lo <= hi) {
+        // sparse merge of the touched part of the window
+        const int w0 = (int)max((int)(lo - wbase), 0) >> 1, w1 = min((int)((hi - wbase) >> 1), kWinWords - 1);
+        if (hi >= wbase && lo < wbase + kWinBins)
+            for (int i = w0 + tid; i <= w1; i += kHistThreads) {
+                const unsigned int w = win[i];
+                if (w & 0xffffu) atomicAdd(&gh[wbase + 2 * i], w & 0xffffu);
+                if (w >> 16) atomicAdd(&gh[wbase + 2 * i + 1], w >> 16);
+            }
+        if (tid == 0) { atomicMin(&meta[b], lo); atomicMax(&meta[B + b], hi); }
     }
-    if (tid == 0 && s_lo <= s_hi) { atomicMin(&meta[b], s_lo); atomicMax(&meta[B + b], s_hi); }
 }
 
 // np.percentile(method='linear') finish (numpy _quantile/_lerp): a, b fp32 order
@@ -383,7 +402,7 @@ __global__ void __launch_bounds__(256) normalize_u16_kernel(const uint16_t* __re
 // sums of |Dx gray|, |Dy gray| of the OUTPUT image are reduced per CTA into stats[b][band][0..1]
 // (gray = 0.299 v + 0.587 v + 0.114 v in fp32 when the output is replicated to 3 planes).
 constexpr int kNormBands = 24;       // CTAs per frame == statistic partials per frame (T3D_STATS_TILES)
-constexpr int kLutMax = 6144;        // float2 entries (48 KB)
+constexpr int kLutMax = 4096;        // float2 entries (32 KB): covers p98 - p2 < 4093 counts, else the direct fp64 path
 constexpr int kNormThreads = 256;
 
 // Thread layout: up to 128 column-quads x row-lanes; a row-lane marches down its rows keeping the row below
@@ -545,7 +564,9 @@ int t3d_resize_nearest_f32(const float* src, float* dst, int B, int src_h, int s
 size_t t3d_preprocess_workspace_bytes(int B, int dst_h, int dst_w) {
     if (B < 1 || dst_h < 1 || dst_w < 1) return 0;
     return t3d_align_up((size_t)B * dst_h * dst_w * sizeof(uint16_t), 256) +      // resized frames
-           t3d_align_up((size_t)(2 * B + 1) * sizeof(unsigned int), 256);          // per-frame vmin / vmax, work queue
+           t3d_align_up((size_t)(2 * B + 1) * sizeof(unsigned int), 256) +         // per-frame vmin / vmax
+           t3d_align_up((size_t)dst_w * sizeof(uint2), 256) +                      // x taps
+           t3d_align_up((size_t)dst_h * sizeof(uint4), 256);                       // y taps
 }
 
 int t3d_preprocess_train_u16(const uint16_t* raw, int B, int src_h, int src_w, int dst_h, int dst_w,
@@ -568,7 +589,9 @@ int t3d_preprocess_train_u16(const uint16_t* raw, int B, int src_h, int src_w, i
     T3D_CUDA(cudaMemsetAsync(hist, 0, (size_t)B * 65536 * sizeof(unsigned int), st));
     T3D_CUDA(cudaMemsetAsync(meta, 0xff, (size_t)B * sizeof(unsigned int), st));            // vmin = 0xffffffff
     T3D_CUDA(cudaMemsetAsync(meta + B, 0, (size_t)(B + 1) * sizeof(unsigned int), st));     // vmax = 0, queue = 0
-    T3D_REQUIRE(dst_w <= kHistMaxW && src_w <= 65535, "frame too wide (dst_w <= 4092, src_w <= 65535)");
+    T3D_REQUIRE(dst_w <= kHistMaxW && src_w <= 65535, "frame too wide (dst_w <= 2044, src_w <= 65535)");
+    uint2* gxt = reinterpret_cast<uint2*>(reinterpret_cast<char*>(meta) + t3d_align_up((size_t)(2 * B + 1) * sizeof(unsigned int), 256));
+    uint4* gyt = reinterpret_cast<uint4*>(reinterpret_cast<char*>(gxt) + t3d_align_up((size_t)dst_w * sizeof(uint2), 256));
     const int chunks = (dst_h + kHistRows - 1) / kHistRows;       // kHistRows * dst_w < 65 536: u16 bins cannot overflow
     const size_t hsmem = (size_t)kWinWords * 4 + (same ? 0 : (size_t)dst_w * sizeof(uint2));
     static bool attr_set = false;
@@ -578,12 +601,15 @@ int t3d_preprocess_train_u16(const uint16_t* raw, int B, int src_h, int src_w, i
         T3D_CUDA(cudaFuncSetAttribute(resize_hist_u16_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
         attr_set = true;
     }
-    if (same)
+    if (same) {
         T3D_LAUNCH("resize_hist_u16_kernel", st, resize_hist_u16_kernel<false><<<B * chunks, kHistThreads, hsmem, st>>>(
-            raw, resized, hist, meta, B, src_h, src_w, dst_h, dst_w, chunks));
-    else
+            raw, resized, hist, meta, gxt, gyt, B, src_h, src_w, dst_h, dst_w, chunks));
+    } else {
+        const int tn = max(dst_w, dst_h);
+        T3D_LAUNCH("build_taps_kernel", st, build_taps_kernel<<<(tn + 255) / 256, 256, 0, st>>>(src_h, src_w, dst_h, dst_w, gxt, gyt));
         T3D_LAUNCH("resize_hist_u16_kernel", st, resize_hist_u16_kernel<true><<<B * chunks, kHistThreads, hsmem, st>>>(
-            raw, resized, hist, meta, B, src_h, src_w, dst_h, dst_w, chunks));
+            raw, resized, hist, meta, gxt, gyt, B, src_h, src_w, dst_h, dst_w, chunks));
+    }
     T3D_LAUNCH("percentile_from_hist_kernel", st, percentile_from_hist_kernel<<<B, 1024, 0, st>>>(hist, meta, B, npx, percentiles));
     const uint16_t* nsrc = same ? raw : resized;
     const int vec = (dst_w % 4 == 0) && t3d_aligned16(out) && ((reinterpret_cast<uintptr_t>(nsrc) & 7u) == 0);
