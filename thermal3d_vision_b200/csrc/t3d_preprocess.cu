@@ -145,6 +145,8 @@ resize_hist_u16_kernel(const uint16_t* __restrict__ src, uint16_t* __restrict__ 
     const int y0 = chunk * kHistRows, y1 = min(y0 + kHistRows, dh);
     const uint16_t* s = src + (size_t)b * sh * sw;
     unsigned int* gh = hist + (size_t)b * 65536;
+    const int srow = (sw + 7) & ~7;
+    const bool vec_rows = ((sw & 7) == 0) && ((reinterpret_cast<uintptr_t>(src) & 15u) == 0);
     for (int i = tid; i < kWinWords; i += kHistThreads) win[i] = 0u;
     if (RESIZE) for (int x = tid; x < dw; x += kHistThreads) xt[x] = __ldg(gxt + x);
     if (tid == 0) { s_lo = 0xffffu; s_hi = 0u; }
@@ -188,23 +190,45 @@ resize_hist_u16_kernel(const uint16_t* __restrict__ src, uint16_t* __restrict__ 
         if (d < (unsigned)kWinBins) atomicAdd(&win[d >> 1], (d & 1) ? 0x10000u : 1u);
         else atomicAdd(&gh[v], 1u);
     };
+    // per-warp staging of the two source rows of an output row (coalesced 128-bit loads, then 2-byte LDS taps)
+    uint16_t* stage = reinterpret_cast<uint16_t*>(xt + ((dw + 1) & ~1)) + (size_t)wrp * 2 * srow;   // 16-byte aligned; srow = sw rounded up to 8
     for (int y = y0 + wrp; y < y1; y += kHistThreads / 32) {
         if (RESIZE) {
             uint16_t* out_row = resized + ((size_t)b * dh + y) * dw;
             const Tap ty = ytap(y);
             const uint16_t* r0 = s + (size_t)ty.s0 * sw;
             const uint16_t* r1 = s + (size_t)ty.s1 * sw;
+            __syncwarp();
+            if (vec_rows) {
+                for (int k = lane; k < (sw >> 3); k += 32) {
+                    reinterpret_cast<uint4*>(stage)[k] = __ldg(reinterpret_cast<const uint4*>(r0) + k);
+                    reinterpret_cast<uint4*>(stage + srow)[k] = __ldg(reinterpret_cast<const uint4*>(r1) + k);
+                }
+            } else {
+                for (int k = lane; k < sw; k += 32) { stage[k] = __ldg(r0 + k); stage[srow + k] = __ldg(r1 + k); }
+            }
+            __syncwarp();
+            const uint16_t* a0 = stage;
+            const uint16_t* a1 = stage + srow;
+            const float cy0 = ty.c0, cy1 = ty.c1;
+            auto px = [&](int x) -> unsigned int {
+                const uint2 t = xt[x];
+                const int s0 = t.x & 0xffff, s1 = t.x >> 16;
+                const float f = __uint_as_float(t.y), c0 = __fsub_rn(1.0f, f);
+                const float h0 = __fadd_rn(__fmul_rn((float)a0[s0], c0), __fmul_rn((float)a0[s1], f));
+                const float h1 = __fadd_rn(__fmul_rn((float)a1[s0], c0), __fmul_rn((float)a1[s1], f));
+                return sat_u16(__fadd_rn(__fmul_rn(h0, cy0), __fmul_rn(h1, cy1)));
+            };
             constexpr int U = 4;
-            for (int x0 = lane; x0 < dw; x0 += 32 * U) {
+            int x0 = lane;
+            for (; x0 + 32 * (U - 1) < dw; x0 += 32 * U) {            // unguarded fast path
                 unsigned int v[U];
 #pragma unroll
-                for (int u = 0; u < U; ++u) { const int x = x0 + 32 * u; v[u] = (x < dw) ? pixel(r0, r1, ty, x) : 0u; }
+                for (int u = 0; u < U; ++u) v[u] = px(x0 + 32 * u);
 #pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    const int x = x0 + 32 * u;
-                    if (x < dw) { out_row[x] = (uint16_t)v[u]; count(v[u]); }
-                }
+                for (int u = 0; u < U; ++u) { out_row[x0 + 32 * u] = (uint16_t)v[u]; count(v[u]); }
             }
+            for (; x0 < dw; x0 += 32) { const unsigned int v = px(x0); out_row[x0] = (uint16_t)v; count(v); }
         } else {
             const uint16_t* r0 = s + (size_t)y * sw;
             for (int x = lane; x < dw; x += 32) count(__ldg(r0 + x));
@@ -408,7 +432,7 @@ constexpr int kNormThreads = 256;
 // Thread layout: up to 128 column-quads x row-lanes; a row-lane marches down its rows keeping the row below
 // in registers (it is the current row of the next iteration), so every u16 row is loaded once per column.
 template <int REP>
-__global__ void __launch_bounds__(kNormThreads) normalize_stats_u16_kernel(const uint16_t* __restrict__ src,
+__global__ void __launch_bounds__(kNormThreads, 4) normalize_stats_u16_kernel(const uint16_t* __restrict__ src,
                                                                            const double* __restrict__ p,
                                                                            float* __restrict__ dst, int H, int W,
                                                                            float* __restrict__ stats) {
@@ -593,10 +617,12 @@ int t3d_preprocess_train_u16(const uint16_t* raw, int B, int src_h, int src_w, i
     uint2* gxt = reinterpret_cast<uint2*>(reinterpret_cast<char*>(meta) + t3d_align_up((size_t)(2 * B + 1) * sizeof(unsigned int), 256));
     uint4* gyt = reinterpret_cast<uint4*>(reinterpret_cast<char*>(gxt) + t3d_align_up((size_t)dst_w * sizeof(uint2), 256));
     const int chunks = (dst_h + kHistRows - 1) / kHistRows;       // kHistRows * dst_w < 65 536: u16 bins cannot overflow
-    const size_t hsmem = (size_t)kWinWords * 4 + (same ? 0 : (size_t)dst_w * sizeof(uint2));
+    const size_t stage_bytes = same ? 0 : (size_t)(kHistThreads / 32) * 2 * ((src_w + 7) & ~7) * sizeof(uint16_t);
+    const size_t hsmem = (size_t)kWinWords * 4 + (same ? 0 : (size_t)((dst_w + 1) & ~1) * sizeof(uint2)) + stage_bytes;
+    T3D_REQUIRE(hsmem <= 200 * 1024, "source rows too wide for the shared-memory staging (src_w <= ~9000)");
     static bool attr_set = false;
     if (!attr_set) {
-        const int max_smem = kWinWords * 4 + kHistMaxW * (int)sizeof(uint2);
+        const int max_smem = 200 * 1024;
         T3D_CUDA(cudaFuncSetAttribute(resize_hist_u16_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
         T3D_CUDA(cudaFuncSetAttribute(resize_hist_u16_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
         attr_set = true;
