@@ -300,6 +300,12 @@ def run_b200(a):
         kern_avg_ms = kern_ms / max(kern_n, 1)
         achieved = kern_bytes / (kern_avg_ms * 1e-3) / 1e9 if kern_n else None
         step_bytes = sum(ab.values())
+        # DRAM bytes of one loss_march_kernel launch from the committed ncu capture (profiles/); only valid
+        # for the exact configuration it was taken on
+        traffic, traffic_src = None, None
+        if (B, H, W, bool(a.multi_scale)) == (64, 384, 512, False):
+            traffic = 1064839936 + 373636096
+            traffic_src = "profiles/r01_loss_march_v2_metrics.csv (dram__bytes_read.sum + dram__bytes_write.sum, 1 launch)"
         out = {
             "metric": METRIC, "value": world * B * a.steps / (ms_dev * 1e-3), "unit": UNIT, "n_gpus": world,
             "steps": a.steps, "warmup": max(a.warmup, 3), "ms_per_step": ms_dev / a.steps,
@@ -307,7 +313,8 @@ def run_b200(a):
             "config": config_dict(a, world),
             "roofline": {"bound": "hbm", "kernel": dominant + " (fused loss fwd+bwd, both views)",
                          "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": (achieved / peak) if achieved else None, "traffic": None,
+                         "frac": (achieved / peak) if achieved else None, "traffic": traffic,
+                         "traffic_source": traffic_src,
                          "algorithmic_bytes_per_launch": kern_bytes, "avg_launch_ms": kern_avg_ms,
                          "launches_timed": kern_n, "peak_source": peak_src,
                          "step_algorithmic_bytes": step_bytes,

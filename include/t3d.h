@@ -166,6 +166,13 @@ int t3d_resize_bilinear(const void* src, void* dst, int mode, int B, int src_h, 
 int t3d_resize_nearest_f32(const float* src, float* dst, int B, int src_h, int src_w,
                            int dst_h, int dst_w, void* stream);
 
+/* F.interpolate(mode='bilinear', align_corners=False) of channels-LAST float32 data
+ * [B,src_h,src_w,C] -> [B,dst_h,dst_w,C] (C = 3: AoS pointmaps, C = 1: confidences), the
+ * resampling train_thermal_dustr.py:234-271,465-481 applies to the pseudo-GT when its
+ * size differs from the prediction's. */
+int t3d_interp_bilinear_f32(const float* src, float* dst, int B, int channels_last, int src_h, int src_w,
+                            int dst_h, int dst_w, void* stream);
+
 size_t t3d_preprocess_workspace_bytes(int B, int dst_h, int dst_w);
 
 /* Train path, batched: raw uint16 frames [B,src_h,src_w] -> cv2.resize (uint16)

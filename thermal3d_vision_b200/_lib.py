@@ -43,6 +43,7 @@ _SIGNATURES = {
     "t3d_scale_grads": (C.c_int, [c_ptr] * 5 + [C.c_int] * 3 + [c_ptr]),
     "t3d_resize_bilinear": (C.c_int, [c_ptr, c_ptr] + [C.c_int] * 6 + [c_ptr]),
     "t3d_resize_nearest_f32": (C.c_int, [c_ptr, c_ptr] + [C.c_int] * 5 + [c_ptr]),
+    "t3d_interp_bilinear_f32": (C.c_int, [c_ptr, c_ptr] + [C.c_int] * 6 + [c_ptr]),
     "t3d_preprocess_workspace_bytes": (C.c_size_t, [C.c_int] * 3),
     "t3d_preprocess_train_u16": (C.c_int, [c_ptr] + [C.c_int] * 5 + [c_ptr, C.c_int, c_ptr, c_ptr, c_ptr,
                                                                     c_ptr, C.c_size_t, c_ptr]),

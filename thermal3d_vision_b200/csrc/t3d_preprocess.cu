@@ -552,6 +552,34 @@ __global__ void __launch_bounds__(256) fixed_range_kernel(const float* __restric
     }
 }
 
+// ------------------------------------------------------------------ torch bilinear resample (align_corners=False)
+// F.interpolate(x, size, mode='bilinear', align_corners=False) as train_thermal_dustr.py:234-271,465-481 applies
+// it to the pseudo-GT pointmaps ([H,W,3] AoS -> permuted to NCHW there; here read and written in place as AoS)
+// and confidences.  ATen: scale = in / out (fp32); src = max(scale * (dst + 0.5) - 0.5, 0); i0 = (int)src;
+// i1 = i0 + (i0 < in - 1); l1 = src - i0; l0 = 1 - l1; out = l0y (l0x v00 + l1x v01) + l1y (l0x v10 + l1x v11).
+__global__ void __launch_bounds__(256) interp_bilinear_kernel(const float* __restrict__ src, float* __restrict__ dst,
+                                                              int B, int C, int sh, int sw, int dh, int dw) {
+    const float ry = (float)sh / (float)dh, rx = (float)sw / (float)dw;
+    const size_t total = (size_t)B * dh * dw;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (size_t)gridDim.x * blockDim.x) {
+        const int x = (int)(idx % dw);
+        const size_t t = idx / dw;
+        const int y = (int)(t % dh);
+        const int b = (int)(t / dh);
+        const float fy = fmaxf(ry * ((float)y + 0.5f) - 0.5f, 0.f), fx = fmaxf(rx * ((float)x + 0.5f) - 0.5f, 0.f);
+        const int y0 = (int)fy, x0 = (int)fx;
+        const int y1 = y0 + ((y0 < sh - 1) ? 1 : 0), x1 = x0 + ((x0 < sw - 1) ? 1 : 0);
+        const float ly1 = fy - (float)y0, ly0 = 1.f - ly1, lx1 = fx - (float)x0, lx0 = 1.f - lx1;
+        const float* p = src + (size_t)b * sh * sw * C;
+        for (int c = 0; c < C; ++c) {
+            const float v00 = __ldg(p + ((size_t)y0 * sw + x0) * C + c), v01 = __ldg(p + ((size_t)y0 * sw + x1) * C + c);
+            const float v10 = __ldg(p + ((size_t)y1 * sw + x0) * C + c), v11 = __ldg(p + ((size_t)y1 * sw + x1) * C + c);
+            dst[idx * C + c] = ly0 * (lx0 * v00 + lx1 * v01) + ly1 * (lx0 * v10 + lx1 * v11);
+        }
+    }
+}
+
 int grid_for(size_t n, int threads, int per_sm = 8) {
     const size_t need = (n + threads - 1) / threads;
     const size_t cap = (size_t)t3d_sm_count() * per_sm;
@@ -700,6 +728,16 @@ int t3d_fixed_range_normalize(const float* x, float* y, size_t n, size_t plane, 
     T3D_REQUIRE(plane >= 1, "bad plane size");
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     T3D_LAUNCH("fixed_range_kernel", st, fixed_range_kernel<<<grid_for(n, 256), 256, 0, st>>>(x, y, n, plane, close_flag, normalized));
+    return T3D_OK;
+}
+
+int t3d_interp_bilinear_f32(const float* src, float* dst, int B, int channels_last, int src_h, int src_w,
+                            int dst_h, int dst_w, void* stream) {
+    T3D_REQUIRE(src && dst, "NULL pointer");
+    T3D_REQUIRE(B >= 1 && channels_last >= 1 && src_h >= 1 && src_w >= 1 && dst_h >= 1 && dst_w >= 1, "bad dims");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    T3D_LAUNCH("interp_bilinear_kernel", st, interp_bilinear_kernel<<<grid_for((size_t)B * dst_h * dst_w, 256), 256, 0, st>>>(
+        src, dst, B, channels_last, src_h, src_w, dst_h, dst_w));
     return T3D_OK;
 }
 

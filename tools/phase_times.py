@@ -1,0 +1,39 @@
+"""Developer tool: time the phases of HotPathStep.run_device with CUDA events."""
+import sys, os, json
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import bench
+from thermal3d_vision_b200.pipeline import HotPathStep
+from thermal3d_vision_b200 import preprocessing as pp, metrics as tm, loss as tl, _lib
+dev = torch.device("cuda:0")
+B, H, W = 64, 384, 512
+d = bench.make_inputs_torch(B, H, W, 0, dev)
+step = HotPathStep(B, H, W, device=dev)
+args = (d["raw1"], d["raw2"], d["pred1"], d["pred2"], d["gt1"], d["gt2"], d["conf1"], d["conf2"], d["gt_depth"])
+def timeit(fn, n=50):
+    for _ in range(5): fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(n): fn()
+    e1.record(); torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / n * 1e3
+res = {}
+for ov in (True, False):
+    step.overlap = ov
+    res[f"step_overlap={ov}"] = timeit(lambda: step.run_device(*args))
+size = (W, H)
+res["pre1"] = timeit(lambda: pp.preprocess_thermal_batch(d["raw1"], size, out=step.pre_out[0]))
+raw2 = torch.cat([d["raw1"], d["raw2"]])
+out2 = {}
+t = pp.preprocess_thermal_batch(raw2, size, out=out2)
+out2.update({"thermal": t.thermal, "percentiles": t.percentiles, "histogram": t.histogram, "grad_stats": t.grad_stats})
+res["pre_both_128"] = timeit(lambda: pp.preprocess_thermal_batch(raw2, size, out=out2))
+res["metrics"] = timeit(lambda: tm.compute_depth_metrics_batch(d["pred1"], d["gt_depth"], out=step.met_out))
+tb1 = pp.preprocess_thermal_batch(d["raw1"], size, out=step.pre_out[0]); tb2 = pp.preprocess_thermal_batch(d["raw2"], size, out=step.pre_out[1])
+kw = dict(alpha=0.2, edge_weight=0.5, smoothness_weight=0.3, detail_weight=0.4, multi_scale=False)
+res["loss_with_stats"] = timeit(lambda: tl.fused_thermal_loss_fwd_bwd(d["pred1"], d["pred2"], d["gt1"], d["gt2"], d["conf1"], d["conf2"], tb1.thermal, tb2.thermal, out=step.loss_out, thermal_stats=(tb1.grad_stats, tb2.grad_stats), **kw))
+res["loss_no_stats"] = timeit(lambda: tl.fused_thermal_loss_fwd_bwd(d["pred1"], d["pred2"], d["gt1"], d["gt2"], d["conf1"], d["conf2"], tb1.thermal, tb2.thermal, out=step.loss_out, **kw))
+kwm = dict(kw); kwm["multi_scale"] = True
+res["loss_multiscale"] = timeit(lambda: tl.fused_thermal_loss_fwd_bwd(d["pred1"], d["pred2"], d["gt1"], d["gt2"], d["conf1"], d["conf2"], tb1.thermal, tb2.thermal, out=step.loss_out, **kwm))
+print(json.dumps(res, indent=1))
