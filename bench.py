@@ -79,6 +79,8 @@ def make_inputs_torch(B, H, W, seed, device):
         f = f + torch.where(night, blobs, torch.zeros_like(blobs))
         raws.append(f.clamp(0, 65535).to(torch.int32).to(torch.uint16))
     gt_depth = gt1[..., 2].contiguous()
+    both = torch.cat(raws)            # the two views as halves of one tensor: preprocessed by one call
+    raws = [both[:B], both[B:]]
     return {"raw1": raws[0], "raw2": raws[1], "pred1": pred1, "pred2": pred2, "gt1": gt1, "gt2": gt2,
             "conf1": conf1, "conf2": conf2, "gt_depth": gt_depth}
 

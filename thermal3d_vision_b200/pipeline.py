@@ -40,12 +40,18 @@ class HotPathStep:
             "dpred1": torch.empty(B, H, W, 3, **f32), "dpred2": torch.empty(B, H, W, 3, **f32),
             "dconf1": torch.empty(B, H, W, **f32), "dconf2": torch.empty(B, H, W, **f32),
         }
-        self.pre_out = [{
-            "thermal": torch.empty(B, 3, H, W, **f32),
-            "percentiles": torch.empty(B, 2, dtype=torch.float64, device=dev),
-            "histogram": torch.empty(B, 65536, dtype=torch.int32, device=dev),
-            "workspace": torch.empty(lib.t3d_preprocess_workspace_bytes(B, H, W), dtype=torch.uint8, device=dev),
-        } for _ in range(2)]
+        # both views are preprocessed by ONE call when the caller hands them over as the two halves of a single
+        # [2B,...] tensor (what run_host's staging does): outputs are halves of one buffer as well
+        self.pre_both = {
+            "thermal": torch.empty(2 * B, 3, H, W, **f32),
+            "percentiles": torch.empty(2 * B, 2, dtype=torch.float64, device=dev),
+            "histogram": torch.empty(2 * B, 65536, dtype=torch.int32, device=dev),
+            "grad_stats": torch.empty(2 * B, max(lib.t3d_preprocess_stats_tiles(H, W), 1), 4, **f32),
+            "workspace": torch.empty(lib.t3d_preprocess_workspace_bytes(2 * B, H, W), dtype=torch.uint8, device=dev),
+        }
+        self.pre_out = [{k: (v[:B] if i == 0 else v[B:]) if k != "workspace" else
+                         torch.empty(lib.t3d_preprocess_workspace_bytes(B, H, W), dtype=torch.uint8, device=dev)
+                         for k, v in self.pre_both.items()} for i in range(2)]
         self.met_out = {
             "workspace": torch.empty(lib.t3d_depth_metrics_workspace_bytes(B, H, W), dtype=torch.uint8, device=dev),
             "metrics": torch.empty(B, 8, **f32), "metrics_f64": torch.empty(B, 8, dtype=torch.float64, device=dev),
@@ -79,27 +85,37 @@ class HotPathStep:
         [7..13] sums of finite per-image metrics (abs_rel..acc_3)  [14] n_images  [15] unused.
         With distributed=True the vector is all-reduced (SUM) over ranks: ONE small NCCL call."""
         size = (self.W, self.H)
+        B = self.B
         main = torch.cuda.current_stream(self.device)
+        stacked = (raw1.is_contiguous() and raw2.is_contiguous() and raw1.shape == raw2.shape and
+                   raw1.untyped_storage().data_ptr() == raw2.untyped_storage().data_ptr() and
+                   raw2.storage_offset() == raw1.storage_offset() + raw1.numel())      # halves of one tensor
+        if stacked:
+            raw_both = torch.as_strided(raw1, (2 * B,) + tuple(raw1.shape[1:]), raw1.stride(), raw1.storage_offset())
+
+        def preprocess_all():
+            if stacked:
+                tb = _pre.preprocess_thermal_batch(raw_both, size, path="train", out=self.pre_both)
+                gs = tb.grad_stats
+                return (tb.thermal[:B], tb.thermal[B:]), (None, None) if gs is None else (gs[:B], gs[B:])
+            a = _pre.preprocess_thermal_batch(raw1, size, path="train", out=self.pre_out[0])
+            b = _pre.preprocess_thermal_batch(raw2, size, path="train", out=self.pre_out[1])
+            return (a.thermal, b.thermal), (a.grad_stats, b.grad_stats)
+
         if self.overlap:
             self.fork.record(main)
-            with torch.cuda.stream(self.side[0]):           # view-2 preprocessing
-                self.side[0].wait_event(self.fork)
-                tb2 = _pre.preprocess_thermal_batch(raw2, size, path="train", out=self.pre_out[1])
-                self.joins[0].record(self.side[0])
             with torch.cuda.stream(self.side[1]):           # depth metrics (Z of pred1 read in place)
                 self.side[1].wait_event(self.fork)
                 me = _metrics.compute_depth_metrics_batch(pred1, gt_depth, out=self.met_out)
                 self.joins[1].record(self.side[1])
-            tb1 = _pre.preprocess_thermal_batch(raw1, size, path="train", out=self.pre_out[0])
-            main.wait_event(self.joins[0])
+            (t1, t2), stats = preprocess_all()
             main.wait_event(self.joins[1])
         else:
-            tb1 = _pre.preprocess_thermal_batch(raw1, size, path="train", out=self.pre_out[0])
-            tb2 = _pre.preprocess_thermal_batch(raw2, size, path="train", out=self.pre_out[1])
+            (t1, t2), stats = preprocess_all()
             me = _metrics.compute_depth_metrics_batch(pred1, gt_depth, out=self.met_out)
         # the normalisation kernel already summed the thermal gradients: the loss skips its statistics pass
-        lo = _loss.fused_thermal_loss_fwd_bwd(pred1, pred2, gt1, gt2, conf1, conf2, tb1.thermal, tb2.thermal,
-                                              out=self.loss_out, thermal_stats=(tb1.grad_stats, tb2.grad_stats),
+        lo = _loss.fused_thermal_loss_fwd_bwd(pred1, pred2, gt1, gt2, conf1, conf2, t1, t2,
+                                              out=self.loss_out, thermal_stats=stats,
                                               grad_scale=_dist.global_grad_scale(self.B) if self.distributed else None,
                                               **self.kw)
         r = self.result
@@ -116,7 +132,10 @@ class HotPathStep:
         Copies them to the device, runs the step, copies the packed result back to pinned host memory.
         Asynchronous on the current stream; `result_host` is valid after a stream synchronise."""
         if self.staging is None:
-            self.staging = {k: torch.empty(v.shape, dtype=v.dtype, device=self.device) for k, v in host.items()}
+            self.staging = {k: torch.empty(v.shape, dtype=v.dtype, device=self.device) for k, v in host.items()
+                            if k not in ("raw1", "raw2")}
+            both = torch.empty((2 * self.B,) + tuple(host["raw1"].shape[1:]), dtype=host["raw1"].dtype, device=self.device)
+            self.staging["raw1"], self.staging["raw2"] = both[:self.B], both[self.B:]
         for k, v in host.items():
             self.staging[k].copy_(v, non_blocking=True)
         s = self.staging
