@@ -69,8 +69,9 @@ def test_per_sample_api_matches_oracle(cuda_device, H, W, multi):
     _check_grad("dconf2", d[5].grad, ref[5], f64["dc2"])
 
 
+@pytest.mark.parametrize("multi", [True, False])      # True: tile kernel, False: TMA marching kernel
 @pytest.mark.parametrize("variant", ["no_conf", "no_thermal", "one_channel", "conf_no_grad", "basic_only_fn"])
-def test_optional_arguments(cuda_device, variant):
+def test_optional_arguments(cuda_device, variant, multi):
     from thermal3d_vision_b200 import loss as t3d
     H, W = 40, 64
     p1, p2, g1, g2, c1, c2, t1, t2 = ref_loss.make_kat_inputs(H, W, seed=7)
@@ -80,7 +81,7 @@ def test_optional_arguments(cuda_device, variant):
         t1 = t2 = None
     if variant == "one_channel":
         t1, t2 = t1[:1].contiguous(), t2[:1].contiguous()
-    ref = _oracle_sample(p1, p2, g1, g2, c1, c2, t1, t2, True, **KW)
+    ref = _oracle_sample(p1, p2, g1, g2, c1, c2, t1, t2, multi, **KW)
     d = [None if x is None else x.to(cuda_device) for x in (p1, p2, g1, g2, c1, c2, t1, t2)]
     d[0].requires_grad_(); d[1].requires_grad_()
     if c1 is not None and variant != "conf_no_grad":
@@ -88,7 +89,7 @@ def test_optional_arguments(cuda_device, variant):
     if variant == "basic_only_fn":
         loss = t3d.confidence_weighted_regression_loss(d[0], d[1], d[2], d[3], d[4], d[5], alpha=0.2)
     else:
-        loss, comp = t3d.enhanced_thermal_aware_loss(*d, multi_scale=True, **KW)
+        loss, comp = t3d.enhanced_thermal_aware_loss(*d, multi_scale=multi, **KW)
         if variant == "no_thermal":
             assert comp["edge_loss"] == 0 and comp["smoothness_loss"] == 0 and comp["detail_loss"] == 0
     loss.backward()
@@ -249,3 +250,36 @@ def test_golden_table_full_size(cuda_device):
                d[0].grad.abs().double().sum().item(), d[1].grad.abs().double().sum().item(),
                d[4].grad.abs().double().sum().item(), d[5].grad.abs().double().sum().item()]
         np.testing.assert_allclose(got, row[3:], rtol=1e-5)
+
+
+@pytest.mark.parametrize("H,W", [(33, 132), (1, 128), (2, 8), (130, 516)])
+def test_marching_kernel_edge_shapes(cuda_device, H, W):
+    """Shapes that stress the TMA marching path: odd heights, single row, partial strips, bands of 1 row."""
+    from thermal3d_vision_b200 import loss as t3d
+    B = 2
+    P1, P2, G1, G2, C1, C2, T1, T2 = ref_loss.make_batch_inputs(B, H, W, seed=H + W, stress_conf=True, smooth=H >= 8 and W >= 8)
+    Pa, Pb, Ca, Cb = (x.clone().requires_grad_() for x in (P1, P2, C1, C2))
+    mean, rows, valid = ref_loss.batched_loss_torch(Pa, Pb, G1, G2, Ca, Cb, T1, T2, multi_scale=False, **KW)
+    mean.backward()
+    d = [x.to(cuda_device) for x in (P1, P2, G1, G2, C1, C2, T1, T2)]
+    for k in (0, 1, 4, 5):
+        d[k].requires_grad_()
+    res = t3d.fused_thermal_loss(*d, multi_scale=False, **KW)
+    res.loss.backward()
+    np.testing.assert_allclose(res.per_sample[:, :5].cpu().numpy(), rows, rtol=1e-5)
+    for got, ref in ((d[0].grad, Pa.grad), (d[1].grad, Pb.grad), (d[4].grad, Ca.grad), (d[5].grad, Cb.grad)):
+        torch.testing.assert_close(got.cpu(), ref, rtol=1e-4, atol=1e-6)
+
+
+def test_nan_thermal_poisons_only_that_sample(cuda_device):
+    """clamp(NaN) = NaN in the reference: a NaN thermal pixel makes the sample's loss NaN -> sample skipped."""
+    from thermal3d_vision_b200 import loss as t3d
+    B, H, W = 3, 32, 128
+    P1, P2, G1, G2, C1, C2, T1, T2 = ref_loss.make_batch_inputs(B, H, W, seed=4)
+    T2[1, :, 5, 7] = float("nan")
+    for multi in (False, True):
+        mean, rows, valid = ref_loss.batched_loss_torch(P1, P2, G1, G2, C1, C2, T1, T2, multi_scale=multi, **KW)
+        assert valid.tolist() == [True, False, True]
+        res = t3d.fused_thermal_loss(*(x.to(cuda_device) for x in (P1, P2, G1, G2, C1, C2, T1, T2)), multi_scale=multi, **KW)
+        assert res.per_sample[:, 5].tolist() == [1.0, 0.0, 1.0]
+        assert res.loss.item() == pytest.approx(mean.item(), rel=1e-5)

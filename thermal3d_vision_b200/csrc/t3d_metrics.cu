@@ -284,11 +284,22 @@ median_scale_kernel(const float* __restrict__ vz, const float* __restrict__ vg, 
 // ------------------------------------------------------------------ M3: per-pixel terms
 __device__ __forceinline__ float np_maximum(float a, float b) { return (isnan(a) || isnan(b)) ? __int_as_float(0x7fc00000) : fmaxf(a, b); }
 
+// Per-pixel terms of utils/metrics.py:48-59.  GENERAL == false (mask = gt > 0 & finite, so gt is a positive
+// finite number): exactly one of gt/pred, pred/gt is >= 1, hence max(gt/pred, pred/gt) = max(gt,p) / min(gt,p)
+// -- ONE IEEE division keeps the delta-counts exact -- and (log gt - log p)^2 = log(thresh)^2.  Non-positive or
+// NaN predictions take the literal two-division form (same results as numpy: NaN / inf propagate).
+template <bool GENERAL>
 __device__ __forceinline__ void metric_terms(float gt, float z, float s, float accf[4], int cnt[3]) {
     if (isnan(gt)) return;                                                   // invalid pixel marker
     const float pr = __fmul_rn(z, s);                                        // pred *= scale   (:48)
-    const float q = __fdiv_rn(gt, pr);
-    const float th = np_maximum(q, __fdiv_rn(pr, gt));                       // :51 (exact IEEE: counts are exact)
+    float th, dl;
+    if (!GENERAL && pr > 0.f) {
+        th = __fdiv_rn(fmaxf(gt, pr), fminf(gt, pr));                        // :51
+        dl = 0.69314718f * __log2f(th);                                      // |log gt - log pred|
+    } else {
+        th = np_maximum(__fdiv_rn(gt, pr), __fdiv_rn(pr, gt));
+        dl = __logf(gt) - __logf(pr);
+    }
     cnt[0] += th < 1.25f; cnt[1] += th < 1.5625f; cnt[2] += th < 1.953125f;  // :52-54
     const float d = __fsub_rn(gt, pr);
     const float d2 = __fmul_rn(d, d);
@@ -296,10 +307,10 @@ __device__ __forceinline__ void metric_terms(float gt, float z, float s, float a
     accf[0] += fabsf(d) * rg;                                                // :56  |gt - pred| / gt
     accf[1] += d2 * rg;                                                      // :57
     accf[2] += d2;                                                           // :58
-    const float dl = __logf(gt) - __logf(pr);
     accf[3] += dl * dl;                                                      // :59
 }
 
+template <bool GENERAL>
 __global__ void __launch_bounds__(kChunkThreads)
 metrics_sum_kernel(const float* __restrict__ vz, const float* __restrict__ vg,
                    const float* __restrict__ medians, const int* __restrict__ counters, int median_scaling,
@@ -323,10 +334,10 @@ metrics_sum_kernel(const float* __restrict__ vz, const float* __restrict__ vg,
                                     __int_as_float(0x7fc00000), __int_as_float(0x7fc00000)), zb = gb;
             if (q2 < q1) { gb = __ldg(reinterpret_cast<const float4*>(g) + q2); zb = __ldg(reinterpret_cast<const float4*>(z) + q2); }
             float accf[4] = {0.f, 0.f, 0.f, 0.f};
-            metric_terms(ga.x, za.x, s, accf, cnt); metric_terms(ga.y, za.y, s, accf, cnt);
-            metric_terms(ga.z, za.z, s, accf, cnt); metric_terms(ga.w, za.w, s, accf, cnt);
-            metric_terms(gb.x, zb.x, s, accf, cnt); metric_terms(gb.y, zb.y, s, accf, cnt);
-            metric_terms(gb.z, zb.z, s, accf, cnt); metric_terms(gb.w, zb.w, s, accf, cnt);
+            metric_terms<GENERAL>(ga.x, za.x, s, accf, cnt); metric_terms<GENERAL>(ga.y, za.y, s, accf, cnt);
+            metric_terms<GENERAL>(ga.z, za.z, s, accf, cnt); metric_terms<GENERAL>(ga.w, za.w, s, accf, cnt);
+            metric_terms<GENERAL>(gb.x, zb.x, s, accf, cnt); metric_terms<GENERAL>(gb.y, zb.y, s, accf, cnt);
+            metric_terms<GENERAL>(gb.z, zb.z, s, accf, cnt); metric_terms<GENERAL>(gb.w, zb.w, s, accf, cnt);
 #pragma unroll
             for (int k = 0; k < 4; ++k) acc[k] += (double)accf[k];
         }
@@ -335,7 +346,7 @@ metrics_sum_kernel(const float* __restrict__ vz, const float* __restrict__ vg,
         const int i0 = chunk * per, i1 = min(i0 + per, n);
         for (int i = i0 + threadIdx.x; i < i1; i += kChunkThreads) {
             float accf[4] = {0.f, 0.f, 0.f, 0.f};
-            metric_terms(__ldg(g + i), __ldg(z + i), s, accf, cnt);
+            metric_terms<GENERAL>(__ldg(g + i), __ldg(z + i), s, accf, cnt);
 #pragma unroll
             for (int k = 0; k < 4; ++k) acc[k] += (double)accf[k];
         }
@@ -522,8 +533,12 @@ int t3d_depth_metrics(const float* pred, int pred_stride, int pred_offset,
     float* medians = out_medians ? out_medians : w.scale;       // [B][2]: median(gt), median(pred)
     T3D_LAUNCH("median_scale_kernel", st, median_scale_kernel<<<dim3(2, B), kMedThreads, kCandCap * sizeof(unsigned int), st>>>(
         w.vz, w.vg, w.counters, w.cand, n, median_scaling, medians));
-    T3D_LAUNCH("metrics_sum_kernel", st, metrics_sum_kernel<<<g, kChunkThreads, 0, st>>>(
-        w.vz, w.vg, medians, w.counters, median_scaling, n, chunks, w.partials));
+    if (mask)       // a caller-supplied mask may select non-positive / non-finite GT: literal formulas
+        T3D_LAUNCH("metrics_sum_kernel", st, metrics_sum_kernel<true><<<g, kChunkThreads, 0, st>>>(
+            w.vz, w.vg, medians, w.counters, median_scaling, n, chunks, w.partials));
+    else
+        T3D_LAUNCH("metrics_sum_kernel", st, metrics_sum_kernel<false><<<g, kChunkThreads, 0, st>>>(
+            w.vz, w.vg, medians, w.counters, median_scaling, n, chunks, w.partials));
     T3D_LAUNCH("metrics_finalize_kernel", st, metrics_finalize_kernel<<<B, 32, 0, st>>>(w.partials, w.counters, chunks, out, out_f64));
     return T3D_OK;
 }
