@@ -34,7 +34,7 @@ EDGE_W, SMOOTH_W, DETAIL_W, ALPHA = 0.5, 0.3, 0.4, 0.2
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--steps", type=int, default=500)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=64, help="pairs per rank")
@@ -87,13 +87,55 @@ def make_inputs_torch(B, H, W, seed, device):
 
 # --------------------------------------------------------------------------- clocks
 class ClockSampler:
+    """SM clock + throttle reasons sampled DURING the timed region.  In-process NVML (a sample every ~2 ms from a
+    thread; the timed region of a default run is only ~0.1 s, too short for an nvidia-smi subprocess to start);
+    falls back to `nvidia-smi -lms` when pynvml is missing."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
         self.index, self.proc, self.lines = index, None, []
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self.nvml, self.handle, self.stop_flag, self.t = None, None, threading.Event(), None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = index
+            if vis:
+                ids = [v.strip() for v in vis.split(",") if v.strip()]
+                if index < len(ids) and ids[index].isdigit():
+                    phys = int(ids[index])
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
+
+    def _nvml_loop(self):
+        nv = self.nvml
+        bits = {"hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+                "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+                "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4)}
+        get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+            getattr(nv, "nvmlDeviceGetCurrentClocksThrottleReasons")
+        while not self.stop_flag.is_set():
+            try:
+                self.samples.append(float(nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM)))
+                r = int(get_reasons(self.handle))
+                for name, bit in bits.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.002)
 
     def start(self):
+        if self.nvml is not None:
+            self.t = threading.Thread(target=self._nvml_loop, daemon=True)
+            self.t.start()
+            return
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
                                           "--format=csv,noheader,nounits", "-lms", "20"],
@@ -103,11 +145,21 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
+    def mark(self):
+        """Drop what was sampled so far (called right before the timed region starts)."""
+        self.samples.clear(); self.reasons.clear(); self.lines.clear()
+
     def _pump(self):
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
     def stop(self):
+        if self.nvml is not None:
+            self.stop_flag.set()
+            self.t.join(timeout=1)
+            sm = sorted(self.samples)
+            return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.max_mhz,
+                    "reasons": sorted(self.reasons), "samples": len(sm), "source": "nvml, ~2 ms period, timed region only"}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -129,7 +181,7 @@ class ClockSampler:
                     reasons.add(name)
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi -lms 20"}
 
 
 # --------------------------------------------------------------------------- CPU arm (oracle port of the reference)
@@ -267,6 +319,8 @@ def run_b200(a):
     n0 = _lib.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    if rank == 0:
+        sampler.mark()
     e0.record()
     for _ in range(a.steps):
         step.run_device(*args)

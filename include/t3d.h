@@ -83,7 +83,13 @@ size_t t3d_loss_workspace_bytes(int B, int H, int W, int multi_scale);
  * of the zero-padded forward differences.  out_stats [B][2 views][2 scales][2]
  * float32 = the means (scale-2 slots are 0 when multi_scale == 0).
  * thermal_channels is 1 or 3 (gray = 0.299 c0 + 0.587 c1 + 0.114 c2 in fp32,
- * utils/loss.py:119-124). */
+ * utils/loss.py:119-124).  In the loss entry points 3 may be OR-ed with
+ * T3D_THERMAL_REPLICATED: the caller guarantees that the three planes of every
+ * image are bit-identical (what enhance_thermal_contrast always returns,
+ * utils/preprocessing.py:22-28; t3d_preprocess_train_u16 with out_channels 3
+ * produces exactly that), so the kernel reads plane 0 only and evaluates
+ * gray3(v, v, v) -- the same bits, a third of the thermal traffic. */
+#define T3D_THERMAL_REPLICATED 0x100
 int t3d_thermal_grad_stats(const float* thermal1, const float* thermal2, int thermal_channels,
                            int B, int H, int W, int multi_scale,
                            float* out_stats, void* workspace, size_t workspace_bytes,

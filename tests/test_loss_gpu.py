@@ -283,3 +283,21 @@ def test_nan_thermal_poisons_only_that_sample(cuda_device):
         res = t3d.fused_thermal_loss(*(x.to(cuda_device) for x in (P1, P2, G1, G2, C1, C2, T1, T2)), multi_scale=multi, **KW)
         assert res.per_sample[:, 5].tolist() == [1.0, 0.0, 1.0]
         assert res.loss.item() == pytest.approx(mean.item(), rel=1e-5)
+
+
+@pytest.mark.parametrize("H,W", [(48, 256), (33, 132)])
+def test_replicated_thermal_planes_read_once(cuda_device, H, W):
+    """T3D_THERMAL_REPLICATED: reading plane 0 only and evaluating gray3(v, v, v) is bit-identical to reading the
+    three replicated planes enhance_thermal_contrast returns (utils/preprocessing.py:22-28)."""
+    from thermal3d_vision_b200 import loss as t3d
+    B = 3
+    P1, P2, G1, G2, C1, C2, T1, T2 = ref_loss.make_batch_inputs(B, H, W, seed=11)
+    T1 = T1[:, :1].repeat(1, 3, 1, 1).contiguous()
+    T2 = T2[:, :1].repeat(1, 3, 1, 1).contiguous()
+    d = [x.to(cuda_device) for x in (P1, P2, G1, G2, C1, C2, T1, T2)]
+    a = t3d.fused_thermal_loss_fwd_bwd(*d, multi_scale=False, **KW)
+    b = t3d.fused_thermal_loss_fwd_bwd(*d, multi_scale=False, thermal_replicated=True, **KW)
+    for k in ("per_sample", "batch", "dpred1", "dpred2", "dconf1", "dconf2"):
+        assert torch.equal(a[k], b[k]), k
+    mean, rows, _ = ref_loss.batched_loss_torch(P1, P2, G1, G2, C1, C2, T1, T2, multi_scale=False, **KW)
+    np.testing.assert_allclose(b["per_sample"][:, :5].cpu().numpy(), rows, rtol=1e-5)

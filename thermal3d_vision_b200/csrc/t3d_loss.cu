@@ -797,7 +797,9 @@ int loss_impl(bool bwd, const float* pred1, const float* pred2, const float* gt1
     T3D_REQUIRE(pred1 && pred2 && gt1 && gt2, "pred/gt pointers must not be NULL");
     T3D_REQUIRE(out_sample && out_batch && workspace, "output / workspace pointers must not be NULL");
     const bool thermal_on = thermal1 != nullptr && thermal2 != nullptr;   // utils/loss.py:116
-    if (thermal_on) T3D_REQUIRE(tch == 1 || tch == 3, "thermal_channels must be 1 or 3, got %d", tch);
+    const int replicated = (tch == (3 | T3D_THERMAL_REPLICATED));
+    if (replicated) tch = 3;
+    if (thermal_on) T3D_REQUIRE(tch == 1 || tch == 3, "thermal_channels must be 1, 3 or 3 | T3D_THERMAL_REPLICATED, got %d", tch);
     if (bwd) T3D_REQUIRE(dpred1 && dpred2, "dpred pointers must not be NULL");
     const WsLayout L = ws_layout(B, H, W);
     if (ws_bytes < L.total) {
@@ -859,7 +861,7 @@ int loss_impl(bool bwd, const float* pred1, const float* pred2, const float* gt1
             ma.dpred[v] = la.dpred[v]; ma.dconf[v] = la.dconf[v];
         }
         ma.stats[0] = stats_v[0]; ma.stats[1] = stats_v[1]; ma.partials = loss_partials; ma.queue = counter + 1;
-        ma.B = B; ma.H = H; ma.W = W; ma.tch = tch; ma.stiles = la.stiles;
+        ma.B = B; ma.H = H; ma.W = W; ma.tch = tch; ma.stiles = la.stiles; ma.replicated = replicated;
         ma.rows_per_band = march_rows; ma.nbands = (H + march_rows - 1) / march_rows; ma.nstrips = (W + 127) / 128;
         ma.alpha = alpha; ma.kb = la.kb; ma.kc = la.kc; ma.kE = la.kE[0]; ma.kS = la.kS[0]; ma.kD = la.kD[0];
         n_partials = ma.nbands * ma.nstrips;

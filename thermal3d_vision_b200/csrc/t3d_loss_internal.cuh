@@ -10,6 +10,7 @@ struct MarchArgs {
     float* partials;               // [B*2][nbands*nstrips][8]: basic, E, S, D, 0...
     unsigned int* queue;           // work-item counter, zero on entry
     int B, H, W, tch, stiles;
+    int replicated;                // tch == 3 and the planes of every image are bit-identical: read plane 0 only
     int rows_per_band, nbands, nstrips;
     float alpha, kb, kc, kE, kS, kD;
 };

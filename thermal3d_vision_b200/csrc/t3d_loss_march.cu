@@ -101,10 +101,16 @@ __device__ __forceinline__ float edge_w(float tx, float ty, float inv_mx, float 
     return __expf(-8.0f * (cx + cy));
 }
 
-template <int TCH>
+// REP: the image's 3 planes are bit-identical replicas (what enhance_thermal_contrast always returns,
+// utils/preprocessing.py:22-28): only plane 0 is staged and gray = gray3(v, v, v) -- the same bits as
+// reading the three planes, a third of the thermal traffic.
+template <int TCH, bool REP>
 __device__ __forceinline__ void gray_quad(const float* __restrict__ th, int idx, float g[4]) {
     const float4 c0 = *reinterpret_cast<const float4*>(th + idx);
-    if (TCH == 3) {
+    if (REP) {
+        g[0] = gray3(c0.x, c0.x, c0.x); g[1] = gray3(c0.y, c0.y, c0.y);
+        g[2] = gray3(c0.z, c0.z, c0.z); g[3] = gray3(c0.w, c0.w, c0.w);
+    } else if (TCH == 3) {
         const float4 c1 = *reinterpret_cast<const float4*>(th + kSegPx + idx);
         const float4 c2 = *reinterpret_cast<const float4*>(th + 2 * kSegPx + idx);
         g[0] = gray3(c0.x, c1.x, c2.x); g[1] = gray3(c0.y, c1.y, c2.y);
@@ -113,14 +119,15 @@ __device__ __forceinline__ void gray_quad(const float* __restrict__ th, int idx,
         g[0] = c0.x; g[1] = c0.y; g[2] = c0.z; g[3] = c0.w;
     }
 }
-template <int TCH>
+template <int TCH, bool REP>
 __device__ __forceinline__ float gray_px(const float* __restrict__ th, int idx) {
+    if (REP) { const float v = th[idx]; return gray3(v, v, v); }
     return (TCH == 3) ? gray3(th[idx], th[kSegPx + idx], th[2 * kSegPx + idx]) : th[idx];
 }
 
 struct RowRegs { float P[12], G[12], g[4]; };    // pred xyz, gt xyz (AoS order), gray of one lane's 4 pixels
 
-template <int TCH>
+template <int TCH, bool REP>
 __device__ __forceinline__ void load_row(const float* __restrict__ st, int idx, RowRegs& r) {
     const float4* p = reinterpret_cast<const float4*>(st + Stage<TCH>::kPred + idx * 3);
     const float4* q = reinterpret_cast<const float4*>(st + Stage<TCH>::kGt + idx * 3);
@@ -129,12 +136,13 @@ __device__ __forceinline__ void load_row(const float* __restrict__ st, int idx, 
     r.P[8] = c.x; r.P[9] = c.y; r.P[10] = c.z; r.P[11] = c.w;
     r.G[0] = d.x; r.G[1] = d.y; r.G[2] = d.z; r.G[3] = d.w; r.G[4] = e.x; r.G[5] = e.y; r.G[6] = e.z; r.G[7] = e.w;
     r.G[8] = f.x; r.G[9] = f.y; r.G[10] = f.z; r.G[11] = f.w;
-    gray_quad<TCH>(st + Stage<TCH>::kTh, idx, r.g);
+    gray_quad<TCH, REP>(st + Stage<TCH>::kTh, idx, r.g);
 }
 
 // ------------------------------------------------------------------ kernel
-template <int TCH, bool BWD, int NS, int WARPS>
+template <int TCH, bool REP, bool BWD, int NS, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32, 1) loss_march_kernel(const MarchArgs a) {
+    static_assert(!REP || TCH == 1, "replicated planes: one plane is staged");
     using St = Stage<TCH>;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
@@ -182,7 +190,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) loss_march_kernel(const MarchAr
         const float* __restrict__ pred = a.pred[view] + (size_t)b * plane * 3;
         const float* __restrict__ gt = a.gt[view] + (size_t)b * plane * 3;
         const float* __restrict__ conf = a.conf[view] ? a.conf[view] + (size_t)b * plane : nullptr;
-        const float* __restrict__ th = a.thermal[view] + (size_t)b * TCH * plane;
+        const float* __restrict__ th = a.thermal[view] + (size_t)b * (REP ? 3 : TCH) * plane;
         // running output pointers of this lane's quad (row i_lo; advanced by one row per iteration)
         float* dp_ptr = BWD ? a.dpred[view] + ((size_t)b * plane + (size_t)i_lo * W + j) * 3 : nullptr;
         float* dc_ptr = (BWD && a.dconf[view]) ? a.dconf[view] + (size_t)b * plane + (size_t)i_lo * W + j : nullptr;
@@ -241,7 +249,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) loss_march_kernel(const MarchAr
             if (has_below) {
                 wait_row(ri + 1);
                 stn = stage_of(ri + 1);
-                load_row<TCH>(stn, idx, nxt);
+                load_row<TCH, REP>(stn, idx, nxt);
             } else {                                      // zero-padded last image row: dy == 0
 #pragma unroll
                 for (int e = 0; e < 4; ++e) { nxt.P[3 * e + 2] = cur.P[3 * e + 2]; nxt.G[3 * e + 2] = cur.G[3 * e + 2]; nxt.g[e] = cur.g[e]; }
@@ -255,7 +263,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) loss_march_kernel(const MarchAr
                 if (right_in_image) {                     // the strip's right halo pixel
                     zr = st[St::kPred + (idx + 4) * 3 + 2];
                     gzr = st[St::kGt + (idx + 4) * 3 + 2];
-                    gr = gray_px<TCH>(st + St::kTh, idx + 4);
+                    gr = gray_px<TCH, REP>(st + St::kTh, idx + 4);
                 } else { zr = cur.P[11]; gzr = cur.G[11]; gr = cur.g[3]; }
             }
             const float zx[5] = {cur.P[2], cur.P[5], cur.P[8], cur.P[11], zr};
@@ -280,8 +288,8 @@ __global__ void __launch_bounds__(WARPS * 32, 1) loss_march_kernel(const MarchAr
                 if (col0 > 0) {                           // pixel col0-1 is in the halo (idx - 1)
                     const float zl = st[St::kPred + (idx - 1) * 3 + 2];
                     const float gzl = st[St::kGt + (idx - 1) * 3 + 2];
-                    const float gl = gray_px<TCH>(st + St::kTh, idx - 1);
-                    const float gln = has_below ? gray_px<TCH>(stn + St::kTh, idx - 1) : gl;
+                    const float gl = gray_px<TCH, REP>(st + St::kTh, idx - 1);
+                    const float gln = has_below ? gray_px<TCH, REP>(stn + St::kTh, idx - 1) : gl;
                     const float wl = edge_w(fabsf(gx[0] - gl), fabsf(gln - gl), inv_mx, inv_my, m);
                     const float omw = 1.0f - wl;
                     Sums dummy = {0.f, 0.f, 0.f};
@@ -334,7 +342,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) loss_march_kernel(const MarchAr
 
         RowRegs A, Bq;
         wait_row(0);
-        load_row<TCH>(stage_of(0), idx, A);
+        load_row<TCH, REP>(stage_of(0), idx, A);
         const int n_cur = rb - i_lo;                      // rows that are "current" at some iteration
         for (int ri = 0; ri < n_cur; ri += 2) {           // ping-pong the two register sets: no row copies
             step(A, Bq, ri);
@@ -355,7 +363,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) loss_march_kernel(const MarchAr
     }
 }
 
-template <int TCH, bool BWD>
+template <int TCH, bool REP, bool BWD>
 int launch(const MarchArgs& a, cudaStream_t st) {
     constexpr int NS = 4;
     constexpr int WARPS = (TCH == 3) ? 10 : 12;
@@ -363,19 +371,20 @@ int launch(const MarchArgs& a, cudaStream_t st) {
     static_assert(smem <= 227 * 1024, "ring does not fit in shared memory");
     static bool attr_set = false;
     if (!attr_set) {
-        T3D_CUDA(cudaFuncSetAttribute(loss_march_kernel<TCH, BWD, NS, WARPS>,
+        T3D_CUDA(cudaFuncSetAttribute(loss_march_kernel<TCH, REP, BWD, NS, WARPS>,
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set = true;
     }
     const int grid = t3d_sm_count();
     T3D_LAUNCH("loss_march_kernel", st,
-               loss_march_kernel<TCH, BWD, NS, WARPS><<<grid, WARPS * 32, smem, st>>>(a));
+               loss_march_kernel<TCH, REP, BWD, NS, WARPS><<<grid, WARPS * 32, smem, st>>>(a));
     return T3D_OK;
 }
 
 }  // namespace
 
 int t3d_launch_loss_march(const MarchArgs& a, bool bwd, cudaStream_t st) {
-    if (a.tch == 3) return bwd ? launch<3, true>(a, st) : launch<3, false>(a, st);
-    return bwd ? launch<1, true>(a, st) : launch<1, false>(a, st);
+    if (a.tch == 3 && a.replicated) return bwd ? launch<1, true, true>(a, st) : launch<1, true, false>(a, st);
+    if (a.tch == 3) return bwd ? launch<3, false, true>(a, st) : launch<3, false, false>(a, st);
+    return bwd ? launch<1, false, true>(a, st) : launch<1, false, false>(a, st);
 }

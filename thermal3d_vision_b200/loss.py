@@ -21,6 +21,7 @@ import torch
 from . import _lib
 
 OUT_STRIDE = 8  # T3D_LOSS_OUT_STRIDE
+THERMAL_REPLICATED = 0x100  # T3D_THERMAL_REPLICATED
 
 
 class FusedLossResult(NamedTuple):
@@ -40,12 +41,14 @@ def _prep(t: Optional[torch.Tensor], device) -> Optional[torch.Tensor]:
 
 
 def _launch(bwd, p1, p2, g1, g2, c1, c2, t1, t2, need_dconf, alpha, ew, sw, dw, multi, grad_scale,
-            rescale_invalid, out=None, thermal_stats=None):
+            rescale_invalid, out=None, thermal_stats=None, thermal_replicated=False):
     """Raw call into the C ABI on already-prepared [B,H,W,3] CUDA tensors."""
     lib = _lib.lib()
     B, H, W, _ = p1.shape
     dev = p1.device
     tch = 0 if t1 is None or t2 is None else int(t1.shape[1])
+    if thermal_replicated and tch == 3:
+        tch |= THERMAL_REPLICATED          # include/t3d.h: the kernel reads plane 0 only
     ws_bytes = lib.t3d_loss_workspace_bytes(B, H, W, int(multi))
     if out is None:
         out = {}
@@ -191,7 +194,8 @@ def fused_thermal_loss(pred_pts1, pred_pts2, gt_pts1, gt_pts2, confidences1=None
 def fused_thermal_loss_fwd_bwd(pred_pts1, pred_pts2, gt_pts1, gt_pts2, confidences1=None, confidences2=None,
                                thermal_img1=None, thermal_img2=None, *, alpha=0.2, edge_weight=0.5,
                                smoothness_weight=0.3, detail_weight=0.3, multi_scale=True,
-                               conf_grad=True, out=None, thermal_stats=None, grad_scale=None):
+                               conf_grad=True, out=None, thermal_stats=None, grad_scale=None,
+                               thermal_replicated=False):
     """Functional (no autograd) fused step on prepared contiguous fp32 CUDA tensors.
 
     Returns dict(per_sample, batch, dpred1, dpred2, dconf1, dconf2); gradients are those of the
@@ -199,7 +203,9 @@ def fused_thermal_loss_fwd_bwd(pred_pts1, pred_pts2, gt_pts1, gt_pts2, confidenc
     ``thermal_stats`` = (ThermalBatch.grad_stats of view 1, of view 2): the thermal-gradient sums the
     preprocessing kernel already produced; the loss then skips its own pass over the thermal images.
     ``grad_scale`` (default 1/B) is the a-priori upstream gradient, e.g. 1/(B * world_size) for the mean
-    over a data-parallel global batch.
+    over a data-parallel global batch.  ``thermal_replicated``: promise that the 3 planes of every thermal
+    image are bit-identical (ThermalBatch.replicated; what enhance_thermal_contrast always returns): the
+    kernel then reads one plane instead of three, same results.
     """
     _lib.require_cuda(pred_pts1, pred_pts2, gt_pts1, gt_pts2, confidences1, confidences2, thermal_img1, thermal_img2)
     B = pred_pts1.shape[0]
@@ -208,7 +214,7 @@ def fused_thermal_loss_fwd_bwd(pred_pts1, pred_pts2, gt_pts1, gt_pts2, confidenc
         True, pred_pts1, pred_pts2, gt_pts1, gt_pts2, confidences1, confidences2, thermal_img1, thermal_img2,
         need_dconf, float(alpha), float(edge_weight), float(smoothness_weight), float(detail_weight),
         bool(multi_scale), (1.0 / B) if grad_scale is None else float(grad_scale), rescale_invalid=True, out=out,
-        thermal_stats=thermal_stats)
+        thermal_stats=thermal_stats, thermal_replicated=thermal_replicated)
     return {"per_sample": ps, "batch": bt, "dpred1": dp1, "dpred2": dp2, "dconf1": dc1, "dconf2": dc2}
 
 

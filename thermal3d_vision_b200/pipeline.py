@@ -73,7 +73,8 @@ class HotPathStep:
         B, n = self.B, self.H * self.W
         raw = self.raw_hw[0] * self.raw_hw[1]
         return {
-            "loss": 112 * B * n,                               # read 80 B/px-pair, write 32
+            # read 2x12 pred, 2x12 gt, 2x4 conf, 2x4 thermal (the 3 planes are replicas: one is read), write 32
+            "loss": 96 * B * n,
             "preprocess": 2 * B * (2 * raw + 12 * n),          # u16 frame in, 3 fp32 planes out
             "metrics": B * (12 * n + 4 * n + 64),              # pointmap (AoS sectors) + GT in, 64 B out
         }
@@ -116,6 +117,7 @@ class HotPathStep:
         # the normalisation kernel already summed the thermal gradients: the loss skips its statistics pass
         lo = _loss.fused_thermal_loss_fwd_bwd(pred1, pred2, gt1, gt2, conf1, conf2, t1, t2,
                                               out=self.loss_out, thermal_stats=stats,
+                                              thermal_replicated=True,   # preprocess_thermal_batch wrote 3 identical planes
                                               grad_scale=_dist.global_grad_scale(self.B) if self.distributed else None,
                                               **self.kw)
         r = self.result

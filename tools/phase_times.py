@@ -33,7 +33,16 @@ res["metrics"] = timeit(lambda: tm.compute_depth_metrics_batch(d["pred1"], d["gt
 tb1 = pp.preprocess_thermal_batch(d["raw1"], size, out=step.pre_out[0]); tb2 = pp.preprocess_thermal_batch(d["raw2"], size, out=step.pre_out[1])
 kw = dict(alpha=0.2, edge_weight=0.5, smoothness_weight=0.3, detail_weight=0.4, multi_scale=False)
 res["loss_with_stats"] = timeit(lambda: tl.fused_thermal_loss_fwd_bwd(d["pred1"], d["pred2"], d["gt1"], d["gt2"], d["conf1"], d["conf2"], tb1.thermal, tb2.thermal, out=step.loss_out, thermal_stats=(tb1.grad_stats, tb2.grad_stats), **kw))
+res["loss_with_stats_replicated"] = timeit(lambda: tl.fused_thermal_loss_fwd_bwd(d["pred1"], d["pred2"], d["gt1"], d["gt2"], d["conf1"], d["conf2"], tb1.thermal, tb2.thermal, out=step.loss_out, thermal_stats=(tb1.grad_stats, tb2.grad_stats), thermal_replicated=True, **kw))
 res["loss_no_stats"] = timeit(lambda: tl.fused_thermal_loss_fwd_bwd(d["pred1"], d["pred2"], d["gt1"], d["gt2"], d["conf1"], d["conf2"], tb1.thermal, tb2.thermal, out=step.loss_out, **kw))
 kwm = dict(kw); kwm["multi_scale"] = True
 res["loss_multiscale"] = timeit(lambda: tl.fused_thermal_loss_fwd_bwd(d["pred1"], d["pred2"], d["gt1"], d["gt2"], d["conf1"], d["conf2"], tb1.thermal, tb2.thermal, out=step.loss_out, **kwm))
+# host-side enqueue cost of one step (no sync inside; the launch queue is deep enough for 20 steps)
+import time
+step.overlap = True
+torch.cuda.synchronize()
+t0 = time.perf_counter()
+for _ in range(20): step.run_device(*args)
+res["host_enqueue_us_per_step"] = (time.perf_counter() - t0) / 20 * 1e6
+torch.cuda.synchronize()
 print(json.dumps(res, indent=1))
