@@ -180,3 +180,48 @@ def test_grad_stats_feed_the_loss(cuda_device):
                                                 alpha=0.2, edge_weight=0.5, smoothness_weight=0.3, detail_weight=0.4,
                                                 multi_scale=False)
     np.testing.assert_allclose(b["per_sample"][:, :5].cpu().numpy(), rows, rtol=1e-5)
+
+
+@pytest.mark.parametrize("w,h", [(224, 224), (512, 384), (333, 217), (640, 512)])
+def test_bracket_percentiles_match_histogram_path(cuda_device, w, h):
+    """histogram=False (sampled value windows, t3d_preprocess_bracket.cu) must give the same bits as the
+    exact-histogram path and the oracle: outputs, percentiles, thermal-gradient sums."""
+    from thermal3d_vision_b200 import preprocessing as pp
+    frames = _frames()
+    raw = torch.from_numpy(np.stack([f for _, f in frames])).to(cuda_device)
+    a = pp.preprocess_thermal_batch(raw, (w, h), path="train", histogram=True)
+    b = pp.preprocess_thermal_batch(raw, (w, h), path="train", histogram=False)
+    assert b.histogram is None
+    assert torch.equal(a.percentiles, b.percentiles)
+    assert torch.equal(a.thermal, b.thermal)
+    if a.grad_stats is not None:
+        assert torch.equal(a.grad_stats, b.grad_stats)
+    for i, (name, frame) in enumerate(frames):
+        o, p2, p98, _ = ref_preprocess.train_path(frame, (h, w))
+        assert tuple(b.percentiles[i].tolist()) == (p2, p98), name
+        assert (b.thermal[i].cpu().numpy() == o).all(), name
+
+
+def test_bracket_percentiles_adversarial_frames(cuda_device):
+    """Frames built to defeat the sampled windows (window wider than its cap, heavy duplicates, two-valued,
+    constant, column-periodic): the per-frame exact fallback must kick in and give the oracle's bits."""
+    from thermal3d_vision_b200 import preprocessing as pp
+    rng = np.random.default_rng(12)
+    H, W = 96, 160
+    frames = [
+        rng.integers(0, 65536, (H, W)).astype(np.uint16),                           # uniform over the whole range
+        np.full((H, W), 31000, np.uint16),                                          # constant
+        np.where(rng.random((H, W)) < 0.5, 100, 60000).astype(np.uint16),           # two-valued
+        (np.arange(W)[None, :] % 16 * 4000 + np.zeros((H, 1))).astype(np.uint16),   # column-periodic
+        np.where(rng.random((H, W)) < 0.03, 65535, rng.integers(20000, 20040, (H, W))).astype(np.uint16),
+        np.sort(rng.integers(0, 65536, H * W)).reshape(H, W).astype(np.uint16),     # sorted ramp
+    ]
+    raw = torch.from_numpy(np.stack(frames)).to(cuda_device)
+    for size in ((W, H), (80, 64), (224, 224)):          # no resize / downscale / upscale
+        a = pp.preprocess_thermal_batch(raw, size, path="train", histogram=True)
+        b = pp.preprocess_thermal_batch(raw, size, path="train", histogram=False)
+        assert torch.equal(a.percentiles, b.percentiles), size
+        assert torch.equal(a.thermal.view(torch.int32), b.thermal.view(torch.int32)), size    # NaN-safe bit compare
+        for i, f in enumerate(frames):
+            o, p2, p98, _ = ref_preprocess.train_path(f, (size[1], size[0]))
+            assert np.array_equal(b.thermal[i].cpu().numpy(), o, equal_nan=True), (size, i)

@@ -8,28 +8,10 @@
 // Exact recipes: SURVEY.md Appendix B.  Outputs are bit-exact with
 // numpy/OpenCV (IPP off): no FMA contraction in the interpolation, fp64 in
 // the normalisation, integer histograms.
-#include "t3d_common.cuh"
+#include "t3d_preprocess_internal.cuh"
 #include "t3d_select.cuh"
 
 namespace {
-
-// ------------------------------------------------------------------ bilinear taps
-struct Tap { int s0, s1; float c0, c1; };
-
-// cv2 INTER_LINEAR tap for destination index d (resize.cpp, non-IPP path):
-// f = (float)((d + 0.5) * scale - 0.5) rounded to fp32 BEFORE floor.
-__device__ __forceinline__ Tap linear_tap(int d, int src_dim, double scale) {
-    const double fd = __dsub_rn(__dmul_rn(__dadd_rn((double)d, 0.5), scale), 0.5);
-    float f = __double2float_rn(fd);
-    int s = __float2int_rd(f);
-    f = __fsub_rn(f, (float)s);
-    if (s < 0) { s = 0; f = 0.f; }
-    if (s >= src_dim - 1) { s = src_dim - 1; f = 0.f; }
-    Tap t;
-    t.s0 = s; t.s1 = min(s + 1, src_dim - 1);
-    t.c0 = __fsub_rn(1.0f, f); t.c1 = f;
-    return t;
-}
 
 template <typename SrcT, bool DIV65535>
 __device__ __forceinline__ float src_value(const SrcT* __restrict__ p) {
@@ -47,11 +29,6 @@ __device__ __forceinline__ float bilinear_at(const SrcT* __restrict__ src, int s
     const float h1 = __fadd_rn(__fmul_rn(src_value<SrcT, DIV65535>(r1 + tx.s0), tx.c0),
                                __fmul_rn(src_value<SrcT, DIV65535>(r1 + tx.s1), tx.c1));
     return __fadd_rn(__fmul_rn(h0, ty.c0), __fmul_rn(h1, ty.c1));
-}
-
-__device__ __forceinline__ uint16_t sat_u16(float v) {
-    const int r = __float2int_rn(v);        // round half to even
-    return (uint16_t)min(max(r, 0), 65535);
 }
 
 // ------------------------------------------------------------------ K1: resize kernels
@@ -251,27 +228,14 @@ resize_hist_u16_kernel(const uint16_t* __restrict__ src, uint16_t* __restrict__ 
     }
 }
 
-// np.percentile(method='linear') finish (numpy _quantile/_lerp): a, b fp32 order
-// statistics, d = b - a in fp32, result fp64 two-sided lerp.
-__device__ __forceinline__ double lerp_percentile(float a, float b, double g) {
-    const float d = __fsub_rn(b, a);
-    return (g < 0.5) ? __dadd_rn((double)a, __dmul_rn((double)d, g))
-                     : __dsub_rn((double)b, __dmul_rn((double)d, __dsub_rn(1.0, g)));
-}
-
-__device__ __forceinline__ void percentile_ranks(int n, double q, unsigned int* k, double* g) {
-    const double vi = __dmul_rn((double)(n - 1), __ddiv_rn(q, 100.0));
-    const double fl = floor(vi);
-    *k = (unsigned int)fl;
-    *g = __dsub_rn(vi, fl);
-}
-
 // K2b: p2 / p98 from the exact histogram: one CTA per frame scans only the frame's [vmin, vmax] bins.
 __global__ void __launch_bounds__(1024) percentile_from_hist_kernel(const unsigned int* __restrict__ hist,
                                                                     const unsigned int* __restrict__ meta, int B, int n,
-                                                                    double* __restrict__ out_p) {
+                                                                    double* __restrict__ out_p, int rep3,
+                                                                    float2* __restrict__ glut, int2* __restrict__ lutmeta) {
     __shared__ unsigned int warp_tot[32];
     __shared__ float found[4];
+    __shared__ double s_p[2];
     const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
     const unsigned int vmin = min(meta[b], 65535u), vmax = min(meta[B + b], 65535u);
     const int range = (vmax >= vmin) ? (int)(vmax - vmin + 1) : 0;
@@ -315,9 +279,12 @@ __global__ void __launch_bounds__(1024) percentile_from_hist_kernel(const unsign
     }
     __syncthreads();
     if (tid == 0) {
-        out_p[2 * b] = lerp_percentile(found[0], found[1], g[0]);
-        out_p[2 * b + 1] = lerp_percentile(found[2], found[3], g[1]);
+        s_p[0] = lerp_percentile(found[0], found[1], g[0]);
+        s_p[1] = lerp_percentile(found[2], found[3], g[1]);
+        out_p[2 * b] = s_p[0]; out_p[2 * b + 1] = s_p[1];
     }
+    __syncthreads();
+    build_norm_lut(b, s_p[0], s_p[1], rep3, glut, lutmeta);
 }
 
 // ------------------------------------------------------------------ channel collapse (utils/preprocessing.py:13-19)
@@ -391,13 +358,6 @@ percentile_select_kernel(const float* __restrict__ x, int n, int channels, const
 }
 
 // ------------------------------------------------------------------ K2d: clip-normalise in fp64, broadcast
-// out = float( clip((double(x) - p2) / (p98 - p2), 0, 1) ), NaN propagates like np.clip
-__device__ __forceinline__ float normalize_px(double x, double p2, double den) {
-    const double q = __ddiv_rn(__dsub_rn(x, p2), den);
-    if (isnan(q)) return __int_as_float(0x7fc00000);
-    return __double2float_rn(fmin(fmax(q, 0.0), 1.0));
-}
-
 // source is the resized u16 plane (train path); writes `rep` identical planes [B, rep, n]
 __global__ void __launch_bounds__(256) normalize_u16_kernel(const uint16_t* __restrict__ src, const double* __restrict__ p,
                                                             float* __restrict__ dst, int n, int rep, int vec) {
@@ -421,100 +381,166 @@ __global__ void __launch_bounds__(256) normalize_u16_kernel(const uint16_t* __re
 }
 
 // Vector path of the train-path normalisation (W % 4 == 0), fused with the thermal-gradient statistics
-// the loss needs (utils/loss.py:184-201,240-249): per frame a shared-memory LUT over the integer values
-// between floor(p2) and ceil(p98) replaces the per-pixel fp64 divide (same function, same bits), and the
-// sums of |Dx gray|, |Dy gray| of the OUTPUT image are reduced per CTA into stats[b][band][0..1]
-// (gray = 0.299 v + 0.587 v + 0.114 v in fp32 when the output is replicated to 3 planes).
+// the loss needs (utils/loss.py:184-201,240-249): the frame's LUT over the integer values between floor(p2)
+// and ceil(p98) (tabulated once per frame by the percentile kernel with the fp64 formula: same function, same
+// bits, no per-pixel fp64 divide) is copied to shared memory, and the sums of |Dx gray|, |Dy gray| of the
+// OUTPUT image are reduced per CTA into stats[b][band][0..1] (gray = 0.299 v + 0.587 v + 0.114 v in fp32
+// when the output is replicated to 3 planes).
 constexpr int kNormBands = 24;       // CTAs per frame == statistic partials per frame (T3D_STATS_TILES)
-constexpr int kLutMax = 4096;        // float2 entries (32 KB): covers p98 - p2 < 4093 counts, else the direct fp64 path
 constexpr int kNormThreads = 256;
+constexpr int kNormWarps = kNormThreads / 32;
 
-// Thread layout: up to 128 column-quads x row-lanes; a row-lane marches down its rows keeping the row below
-// in registers (it is the current row of the next iteration), so every u16 row is loaded once per column.
+__device__ __forceinline__ float2 lds_f2(uint32_t saddr) {
+    float2 v;
+    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(saddr));
+    return v;
+}
+
+struct NormRow { float o[4], g[4]; };
+
+// Frames whose p2..p98 range does not fit the LUT (> 4093 counts): direct fp64 evaluation, one pixel per thread.
 template <int REP>
+__device__ __noinline__ void normalize_band_direct(const uint16_t* __restrict__ s, float* __restrict__ d, int H, int W,
+                                                   int y0, int y1, double p2, double den, bool do_stats, float& tx, float& ty) {
+    const int n = H * W;
+    auto val = [&](int i) { const float o = normalize_px((double)__ldg(s + i), p2, den); return make_float2(o, (REP == 3) ? gray3(o, o, o) : o); };
+    for (int i = y0 * W + threadIdx.x; i < y1 * W; i += kNormThreads) {
+        const int y = i / W, x = i - y * W;
+        const float2 c = val(i);
+#pragma unroll
+        for (int r = 0; r < REP; ++r) d[(size_t)r * n + i] = c.x;
+        if (do_stats) {
+            if (x + 1 < W) tx += fabsf(val(i + 1).y - c.y);
+            if (y + 1 < H) ty += fabsf(val(i + W).y - c.y);
+        }
+    }
+}
+
+// CTA = one band of rows of one frame; a warp takes a 128-column strip x a run of rows and marches down it:
+// lane = 4 consecutive pixels (one 8-byte load per row, issued two rows ahead), the row below is looked up once
+// and becomes the current row of the next iteration (two register sets, ping-pong), the right neighbour's gray
+// comes from a shuffle (strip edge: one extra u16), outputs leave as 128-bit streaming stores.
+template <int REP, bool STATS>
 __global__ void __launch_bounds__(kNormThreads, 4) normalize_stats_u16_kernel(const uint16_t* __restrict__ src,
                                                                            const double* __restrict__ p,
                                                                            float* __restrict__ dst, int H, int W,
-                                                                           float* __restrict__ stats) {
-    extern __shared__ float2 lut[];                 // {normalised value, its gray} for v in [lo-1, hi+1]
-    __shared__ float red[kNormThreads / 32][2];
-    const int b = blockIdx.y, band = blockIdx.x, tid = threadIdx.x;
+                                                                           float* __restrict__ stats,
+                                                                           const float2* __restrict__ glut,
+                                                                           const int2* __restrict__ lutmeta) {
+    extern __shared__ float2 lut[];                 // {normalised value, its gray} for v in [floor(p2) - 1, ceil(p98) + 1]
+    __shared__ float red[kNormWarps][2];
+    const int b = blockIdx.y, band = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
     const int n = H * W;
-    const double p2 = p[2 * b], p98 = p[2 * b + 1], den = __dsub_rn(p98, p2);
-    auto gray = [&](float o) -> float { return (REP == 3) ? gray3(o, o, o) : o; };
-    // below floor(p2) the result clips to 0, above ceil(p98) to 1: one LUT entry each side covers the rest
-    const int lom1 = (int)floor(p2) - 1, hip1 = (int)ceil(p98) + 1;
-    const int range = hip1 - lom1 + 1;
-    const bool use_lut = range <= kLutMax;
-    if (use_lut)
-        for (int k = tid; k < range; k += kNormThreads) {
-            const float o = normalize_px((double)(lom1 + k), p2, den);
-            lut[k] = make_float2(o, gray(o));
-        }
-    __syncthreads();
-    auto look = [&](int v) -> float2 {
-        if (use_lut) return lut[min(max(v, lom1), hip1) - lom1];
-        const float o = normalize_px((double)v, p2, den);
-        return make_float2(o, gray(o));
-    };
+    const int2 lm = lutmeta[b];
+    const int lom1 = lm.x, range = lm.y;
     const uint16_t* __restrict__ s = src + (size_t)b * n;
     float* __restrict__ d = dst + (size_t)b * REP * n;
     const int rows_per = (H + kNormBands - 1) / kNormBands;
     const int y0 = band * rows_per, y1 = min(y0 + rows_per, H);
-    const int qw = W >> 2;
-    const int CQ = min(qw, 128), RL = kNormThreads / CQ;
-    const int cq0 = tid % CQ, rl = tid / CQ;
-    const int sub = (y1 - y0 + RL - 1) / RL;
-    const int ya = y0 + rl * sub, yb = min(ya + sub, y1);
     float tx = 0.f, ty = 0.f;
-    if (rl < RL && ya < yb) {
-        for (int cq = cq0; cq < qw; cq += CQ) {
-            const int j = 4 * cq;
-            const bool has_right = (j + 4 < W);
-            const uint16_t* col = s + j;
-            // row ya; the raw values of the row after next are always in flight (software prefetch)
-            ushort4 v = __ldg(reinterpret_cast<const ushort4*>(col + (size_t)ya * W));
-            float2 c0 = look(v.x), c1 = look(v.y), c2 = look(v.z), c3 = look(v.w);
-            float gr = has_right ? look(__ldg(col + (size_t)ya * W + 4)).y : c3.y;
-            const int last = (stats ? min(yb, H - 1) : yb - 1);          // last row that must be fetched as "below"
-            ushort4 pw = make_ushort4(0, 0, 0, 0); unsigned short pr = 0;
-            if (ya + 1 <= last) {
-                pw = __ldg(reinterpret_cast<const ushort4*>(col + (size_t)(ya + 1) * W));
-                if (has_right) pr = __ldg(col + (size_t)(ya + 1) * W + 4);
-            }
-            for (int i = ya; i < yb; ++i) {
-                const size_t idx = (size_t)i * W + j;
-                const ushort4 w = pw; const unsigned short wr = pr;
-                const bool have_next = (i + 1 <= last);
-                if (i + 2 <= last) {                                      // prefetch row i+2
-                    pw = __ldg(reinterpret_cast<const ushort4*>(col + (size_t)(i + 2) * W));
-                    if (has_right) pr = __ldg(col + (size_t)(i + 2) * W + 4);
+    if (range <= 0) {                                                 // block-uniform: no LUT for this frame
+        const double p2 = p[2 * b], den = __dsub_rn(p[2 * b + 1], p2);
+        normalize_band_direct<REP>(s, d, H, W, y0, y1, p2, den, STATS, tx, ty);
+    } else {
+        {
+            const float4* g4 = reinterpret_cast<const float4*>(glut + (size_t)b * kLutMax);
+            float4* l4 = reinterpret_cast<float4*>(lut);
+            for (int k = tid; k < (range + 1) / 2; k += kNormThreads) l4[k] = __ldg(g4 + k);
+        }
+        __syncthreads();
+        // lookup in the byte-address domain: addr = clamp(8 v + bias, first entry, last entry)
+        const int a_lo = (int)(uint32_t)__cvta_generic_to_shared(lut), a_hi = a_lo + 8 * (range - 1), a_bias = a_lo - 8 * lom1;
+        auto look = [&](unsigned int v8) -> float2 { return lds_f2((uint32_t)min(max((int)v8 + a_bias, a_lo), a_hi)); };
+        auto lookup = [&](const uint2 q, NormRow& r) {
+            const float2 a = look((q.x << 3) & 0x7fff8u), bq = look((q.x >> 13) & 0x7fff8u);
+            const float2 c = look((q.y << 3) & 0x7fff8u), e = look((q.y >> 13) & 0x7fff8u);
+            r.o[0] = a.x; r.o[1] = bq.x; r.o[2] = c.x; r.o[3] = e.x;
+            r.g[0] = a.y; r.g[1] = bq.y; r.g[2] = c.y; r.g[3] = e.y;
+        };
+        const int nstrips = (W + 127) >> 7;
+        const int RG = max(1, kNormWarps / nstrips);
+        const int rpr = (y1 - y0 + RG - 1) / RG;
+        const size_t rowb = (size_t)W * sizeof(uint16_t);
+        for (int task = wrp; task < nstrips * RG; task += kNormWarps) {
+            const int strip = task % nstrips, rg = task / nstrips;
+            const int ya = y0 + rg * rpr, yb = min(ya + rpr, y1);
+            const int x0 = (strip << 7) + 4 * lane;
+            if (ya >= yb) continue;                                       // warp-uniform
+            const bool active = x0 < W;
+            const bool has_right = x0 + 4 < W;                            // a pixel right of this quad exists
+            const bool edge_lane = STATS && active && has_right && lane == 31;   // right neighbour is in the next strip
+            // rows [ya, ym) have a row below inside the image; row H - 1 (if it is ours) is the zero-padded one
+            const int ym = STATS ? min(yb, H - 1) : ya;
+            const int last = STATS ? min(yb, H - 1) : yb - 1;             // last row that is fetched
+            const char* ld = reinterpret_cast<const char*>(s + (size_t)ya * W + (active ? x0 : 0));
+            float* out = d + (size_t)ya * W + x0;
+            auto fetch = [&](int y, uint2& q, unsigned int& hq) {          // raw quad (+ strip-edge pixel) of row y
+                if (y <= last) {
+                    q = __ldg(reinterpret_cast<const uint2*>(ld));
+                    if (edge_lane) hq = __ldg(reinterpret_cast<const uint16_t*>(ld) + 4);
                 }
-                float2 n0 = c0, n1 = c1, n2 = c2, n3 = c3;
-                float ngr = gr;
-                if (have_next) {
-                    n0 = look(w.x); n1 = look(w.y); n2 = look(w.z); n3 = look(w.w);
-                    ngr = has_right ? look(wr).y : n3.y;
-                }
-                const float4 o = make_float4(c0.x, c1.x, c2.x, c3.x);
+                ld += rowb;
+            };
+            auto right_gray = [&](const NormRow& r, unsigned int hq) -> float {   // gray right of the quad (dx = 0 at the image edge)
+                float gr = __shfl_down_sync(0xffffffffu, r.g[0], 1);
+                if (edge_lane) gr = look((hq << 3) & 0x7fff8u).y;
+                return has_right ? gr : r.g[3];
+            };
+            auto emit = [&](const NormRow& c) {
+                if (active) {
+                    const float4 o = make_float4(c.o[0], c.o[1], c.o[2], c.o[3]);
 #pragma unroll
-                for (int r = 0; r < REP; ++r) stg_stream_f4(d + (size_t)r * n + idx, o);
-                if (stats) {
-                    tx += fabsf(c1.y - c0.y) + fabsf(c2.y - c1.y) + fabsf(c3.y - c2.y) + fabsf(gr - c3.y);
-                    ty += fabsf(n0.y - c0.y) + fabsf(n1.y - c1.y) + fabsf(n2.y - c2.y) + fabsf(n3.y - c3.y);
+                    for (int r = 0; r < REP; ++r) stg_stream_f4(out + (size_t)r * n, o);
                 }
-                c0 = n0; c1 = n1; c2 = n2; c3 = n3; gr = ngr;
+                out += W;
+            };
+            auto dx_sum = [&](const NormRow& c, float gr) {
+                return fabsf(c.g[1] - c.g[0]) + fabsf(c.g[2] - c.g[1]) + fabsf(c.g[3] - c.g[2]) + fabsf(gr - c.g[3]);
+            };
+            auto dy_sum = [&](const NormRow& c, const NormRow& nx) {
+                return fabsf(nx.g[0] - c.g[0]) + fabsf(nx.g[1] - c.g[1]) + fabsf(nx.g[2] - c.g[2]) + fabsf(nx.g[3] - c.g[3]);
+            };
+            uint2 q0 = make_uint2(0u, 0u), q1 = q0, q2 = q0; unsigned int h0 = 0u, h1 = 0u, h2 = 0u;
+            fetch(ya, q0, h0); fetch(ya + 1, q1, h1); fetch(ya + 2, q2, h2);
+            NormRow A, Bq;
+            lookup(q0, A);
+            float grA = STATS ? right_gray(A, h0) : 0.f, grB = 0.f;
+            float sx = 0.f, sy = 0.f;
+            if (STATS) {
+                // rows with a row below: A = row y, q1 = raw of row y + 1, q2 = raw of row y + 2
+                int y = ya;
+                for (; y + 1 < ym; y += 2) {
+                    lookup(q1, Bq); grB = right_gray(Bq, h1); fetch(y + 3, q1, h1);
+                    emit(A); sx += dx_sum(A, grA); sy += dy_sum(A, Bq);
+                    lookup(q2, A); grA = right_gray(A, h2); fetch(y + 4, q2, h2);
+                    emit(Bq); sx += dx_sum(Bq, grB); sy += dy_sum(Bq, A);
+                }
+                if (y < ym) {                                             // odd row count: one more row with a row below
+                    lookup(q1, Bq); grB = right_gray(Bq, h1);
+                    emit(A); sx += dx_sum(A, grA); sy += dy_sum(A, Bq);
+                    A = Bq; grA = grB;
+                    ++y;
+                }
+                if (y < yb) { emit(A); sx += dx_sum(A, grA); }            // the image's last row: dy = 0
+                if (active) { tx += sx; ty += sy; }
+            } else {
+                int y = ya;
+                for (; y + 1 < yb; y += 2) {
+                    emit(A); lookup(q1, A); fetch(y + 3, q1, h1);
+                    emit(A); lookup(q2, A); fetch(y + 4, q2, h2);
+                }
+                if (y < yb) emit(A);
             }
         }
     }
-    if (stats) {
+    if (STATS) {
         tx = warp_sum(tx); ty = warp_sum(ty);
-        if ((tid & 31) == 0) { red[tid >> 5][0] = tx; red[tid >> 5][1] = ty; }
+        if (lane == 0) { red[wrp][0] = tx; red[wrp][1] = ty; }
         __syncthreads();
         if (tid < 2) {
             float v = 0.f;
 #pragma unroll
-            for (int w = 0; w < kNormThreads / 32; ++w) v += red[w][tid];
+            for (int w = 0; w < kNormWarps; ++w) v += red[w][tid];
             stats[((size_t)b * kNormBands + band) * 4 + tid] = v;
             stats[((size_t)b * kNormBands + band) * 4 + 2 + tid] = 0.f;      // scale-2 sums are not produced here
         }
@@ -615,72 +641,79 @@ int t3d_resize_nearest_f32(const float* src, float* dst, int B, int src_h, int s
 
 size_t t3d_preprocess_workspace_bytes(int B, int dst_h, int dst_w) {
     if (B < 1 || dst_h < 1 || dst_w < 1) return 0;
-    return t3d_align_up((size_t)B * dst_h * dst_w * sizeof(uint16_t), 256) +      // resized frames
-           t3d_align_up((size_t)(2 * B + 1) * sizeof(unsigned int), 256) +         // per-frame vmin / vmax
-           t3d_align_up((size_t)dst_w * sizeof(uint2), 256) +                      // x taps
-           t3d_align_up((size_t)dst_h * sizeof(uint4), 256);                       // y taps
+    return pre_ws_layout(nullptr, B, dst_h, dst_w).total;
 }
 
 int t3d_preprocess_train_u16(const uint16_t* raw, int B, int src_h, int src_w, int dst_h, int dst_w,
                              float* out, int out_channels, unsigned int* hist, double* percentiles,
                              float* grad_stats, void* workspace, size_t workspace_bytes, void* stream) {
-    T3D_REQUIRE(raw && out && hist && percentiles && workspace, "NULL pointer");
+    T3D_REQUIRE(raw && out && percentiles && workspace, "NULL pointer");
     T3D_REQUIRE(B >= 1 && src_h >= 1 && src_w >= 1 && dst_h >= 1 && dst_w >= 1, "bad dims");
     T3D_REQUIRE(out_channels == 1 || out_channels == 3, "out_channels must be 1 or 3");
     T3D_REQUIRE((size_t)dst_h * dst_w < (1u << 30), "frame too large");
-    if (workspace_bytes < t3d_preprocess_workspace_bytes(B, dst_h, dst_w)) {
+    T3D_REQUIRE(src_w <= 65535 && src_h <= 65535, "source frame too large (<= 65535 x 65535)");
+    const PreWs w = pre_ws_layout(workspace, B, dst_h, dst_w);
+    if (workspace_bytes < w.total) {
         t3d_set_error("workspace too small");
         return T3D_ERR_WORKSPACE;
     }
+    T3D_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255u) == 0, "workspace must be 256-byte aligned");
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    uint16_t* resized = reinterpret_cast<uint16_t*>(workspace);
+    uint16_t* resized = w.resized;
     const int npx = dst_h * dst_w;
-    unsigned int* meta = reinterpret_cast<unsigned int*>(reinterpret_cast<char*>(workspace) +
-                                                         t3d_align_up((size_t)B * npx * sizeof(uint16_t), 256));
+    unsigned int* meta = w.meta;
     const bool same = (src_h == dst_h && src_w == dst_w);
-    T3D_CUDA(cudaMemsetAsync(hist, 0, (size_t)B * 65536 * sizeof(unsigned int), st));
-    T3D_CUDA(cudaMemsetAsync(meta, 0xff, (size_t)B * sizeof(unsigned int), st));            // vmin = 0xffffffff
-    T3D_CUDA(cudaMemsetAsync(meta + B, 0, (size_t)(B + 1) * sizeof(unsigned int), st));     // vmax = 0, queue = 0
-    T3D_REQUIRE(dst_w <= kHistMaxW && src_w <= 65535, "frame too wide (dst_w <= 2044, src_w <= 65535)");
-    uint2* gxt = reinterpret_cast<uint2*>(reinterpret_cast<char*>(meta) + t3d_align_up((size_t)(2 * B + 1) * sizeof(unsigned int), 256));
-    uint4* gyt = reinterpret_cast<uint4*>(reinterpret_cast<char*>(gxt) + t3d_align_up((size_t)dst_w * sizeof(uint2), 256));
-    const int chunks = (dst_h + kHistRows - 1) / kHistRows;       // kHistRows * dst_w < 65 536: u16 bins cannot overflow
-    const size_t stage_bytes = same ? 0 : (size_t)(kHistThreads / 32) * 2 * ((src_w + 7) & ~7) * sizeof(uint16_t);
-    const size_t hsmem = (size_t)kWinWords * 4 + (same ? 0 : (size_t)((dst_w + 1) & ~1) * sizeof(uint2)) + stage_bytes;
-    T3D_REQUIRE(hsmem <= 200 * 1024, "source rows too wide for the shared-memory staging (src_w <= ~9000)");
-    static bool attr_set = false;
-    if (!attr_set) {
-        const int max_smem = 200 * 1024;
-        T3D_CUDA(cudaFuncSetAttribute(resize_hist_u16_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-        T3D_CUDA(cudaFuncSetAttribute(resize_hist_u16_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-        attr_set = true;
-    }
-    if (same) {
-        T3D_LAUNCH("resize_hist_u16_kernel", st, resize_hist_u16_kernel<false><<<B * chunks, kHistThreads, hsmem, st>>>(
-            raw, resized, hist, meta, gxt, gyt, B, src_h, src_w, dst_h, dst_w, chunks));
+    const int rep3 = (out_channels == 3);
+    if (hist == nullptr) {
+        // percentiles from sampled value windows: no per-pixel histogram atomic (t3d_preprocess_bracket.cu)
+        if (int rc = t3d_launch_bracket_percentiles(raw, B, src_h, src_w, dst_h, dst_w, same, w, rep3, percentiles, st)) return rc;
     } else {
-        const int tn = max(dst_w, dst_h);
-        T3D_LAUNCH("build_taps_kernel", st, build_taps_kernel<<<(tn + 255) / 256, 256, 0, st>>>(src_h, src_w, dst_h, dst_w, gxt, gyt));
-        T3D_LAUNCH("resize_hist_u16_kernel", st, resize_hist_u16_kernel<true><<<B * chunks, kHistThreads, hsmem, st>>>(
-            raw, resized, hist, meta, gxt, gyt, B, src_h, src_w, dst_h, dst_w, chunks));
+        // exact 65 536-bin histogram (an output) -> percentiles
+        if (!same) {
+            const int tn = max(dst_w, dst_h);
+            T3D_LAUNCH("build_taps_kernel", st, build_taps_kernel<<<(tn + 255) / 256, 256, 0, st>>>(src_h, src_w, dst_h, dst_w, w.gxt, w.gyt));
+        }
+        T3D_CUDA(cudaMemsetAsync(hist, 0, (size_t)B * 65536 * sizeof(unsigned int), st));
+        T3D_CUDA(cudaMemsetAsync(meta, 0xff, (size_t)B * sizeof(unsigned int), st));            // vmin = 0xffffffff
+        T3D_CUDA(cudaMemsetAsync(meta + B, 0, (size_t)(B + 1) * sizeof(unsigned int), st));     // vmax = 0
+        T3D_REQUIRE(dst_w <= kHistMaxW, "frame too wide for the histogram path (dst_w <= 2044)");
+        const int chunks = (dst_h + kHistRows - 1) / kHistRows;       // kHistRows * dst_w < 65 536: u16 bins cannot overflow
+        const size_t stage_bytes = same ? 0 : (size_t)(kHistThreads / 32) * 2 * ((src_w + 7) & ~7) * sizeof(uint16_t);
+        const size_t hsmem = (size_t)kWinWords * 4 + (same ? 0 : (size_t)((dst_w + 1) & ~1) * sizeof(uint2)) + stage_bytes;
+        T3D_REQUIRE(hsmem <= 200 * 1024, "source rows too wide for the shared-memory staging (src_w <= ~9000)");
+        static bool attr_set = false;
+        if (!attr_set) {
+            const int max_smem = 200 * 1024;
+            T3D_CUDA(cudaFuncSetAttribute(resize_hist_u16_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+            T3D_CUDA(cudaFuncSetAttribute(resize_hist_u16_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+            attr_set = true;
+        }
+        if (same)
+            T3D_LAUNCH("resize_hist_u16_kernel", st, resize_hist_u16_kernel<false><<<B * chunks, kHistThreads, hsmem, st>>>(
+                raw, resized, hist, meta, w.gxt, w.gyt, B, src_h, src_w, dst_h, dst_w, chunks));
+        else
+            T3D_LAUNCH("resize_hist_u16_kernel", st, resize_hist_u16_kernel<true><<<B * chunks, kHistThreads, hsmem, st>>>(
+                raw, resized, hist, meta, w.gxt, w.gyt, B, src_h, src_w, dst_h, dst_w, chunks));
+        T3D_LAUNCH("percentile_from_hist_kernel", st, percentile_from_hist_kernel<<<B, 1024, 0, st>>>(
+            hist, meta, B, npx, percentiles, rep3, w.lut, w.lutmeta));
     }
-    T3D_LAUNCH("percentile_from_hist_kernel", st, percentile_from_hist_kernel<<<B, 1024, 0, st>>>(hist, meta, B, npx, percentiles));
     const uint16_t* nsrc = same ? raw : resized;
     const int vec = (dst_w % 4 == 0) && t3d_aligned16(out) && ((reinterpret_cast<uintptr_t>(nsrc) & 7u) == 0);
     if (vec) {
         static bool nattr = false;
         if (!nattr) {
-            T3D_CUDA(cudaFuncSetAttribute(normalize_stats_u16_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kLutMax * 8));
-            T3D_CUDA(cudaFuncSetAttribute(normalize_stats_u16_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kLutMax * 8));
+            T3D_CUDA(cudaFuncSetAttribute(normalize_stats_u16_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kLutMax * 8));
+            T3D_CUDA(cudaFuncSetAttribute(normalize_stats_u16_kernel<3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kLutMax * 8));
+            T3D_CUDA(cudaFuncSetAttribute(normalize_stats_u16_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kLutMax * 8));
+            T3D_CUDA(cudaFuncSetAttribute(normalize_stats_u16_kernel<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kLutMax * 8));
             nattr = true;
         }
         dim3 grid(kNormBands, (unsigned)B);
-        if (out_channels == 3)
-            T3D_LAUNCH("normalize_stats_u16_kernel", st, normalize_stats_u16_kernel<3><<<grid, kNormThreads, kLutMax * 8, st>>>(
-                nsrc, percentiles, out, dst_h, dst_w, grad_stats));
-        else
-            T3D_LAUNCH("normalize_stats_u16_kernel", st, normalize_stats_u16_kernel<1><<<grid, kNormThreads, kLutMax * 8, st>>>(
-                nsrc, percentiles, out, dst_h, dst_w, grad_stats));
+#define T3D_NORM_LAUNCH(REP_, ST_) T3D_LAUNCH("normalize_stats_u16_kernel", st, (normalize_stats_u16_kernel<REP_, ST_><<<grid, kNormThreads, kLutMax * 8, st>>>( \
+            nsrc, percentiles, out, dst_h, dst_w, grad_stats, w.lut, w.lutmeta)))
+        if (out_channels == 3) { if (grad_stats) T3D_NORM_LAUNCH(3, true); else T3D_NORM_LAUNCH(3, false); }
+        else { if (grad_stats) T3D_NORM_LAUNCH(1, true); else T3D_NORM_LAUNCH(1, false); }
+#undef T3D_NORM_LAUNCH
     } else {
         T3D_REQUIRE(grad_stats == nullptr, "grad_stats needs dst_w %% 4 == 0 (t3d_preprocess_stats_tiles() == 0 here)");
         dim3 grid((unsigned)min((npx / 4 + 255) / 256 + 1, 64), (unsigned)B);

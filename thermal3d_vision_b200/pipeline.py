@@ -64,6 +64,9 @@ class HotPathStep:
         self.fork = torch.cuda.Event()
         self.joins = [torch.cuda.Event() for _ in range(2)]
         self.overlap = True
+        # percentiles from sampled value windows (bit-identical to the exact-histogram path, no per-pixel atomic);
+        # set True to also get the 65 536-bin histograms of the resized frames in pre_both["histogram"]
+        self.histogram = False
         self.result = torch.zeros(RESULT_SIZE, dtype=torch.float64, device=dev)
         self.result_host = torch.zeros(RESULT_SIZE, dtype=torch.float64).pin_memory()
         self.staging: Optional[Dict[str, torch.Tensor]] = None
@@ -96,11 +99,11 @@ class HotPathStep:
 
         def preprocess_all():
             if stacked:
-                tb = _pre.preprocess_thermal_batch(raw_both, size, path="train", out=self.pre_both)
+                tb = _pre.preprocess_thermal_batch(raw_both, size, path="train", out=self.pre_both, histogram=self.histogram)
                 gs = tb.grad_stats
                 return (tb.thermal[:B], tb.thermal[B:]), (None, None) if gs is None else (gs[:B], gs[B:])
-            a = _pre.preprocess_thermal_batch(raw1, size, path="train", out=self.pre_out[0])
-            b = _pre.preprocess_thermal_batch(raw2, size, path="train", out=self.pre_out[1])
+            a = _pre.preprocess_thermal_batch(raw1, size, path="train", out=self.pre_out[0], histogram=self.histogram)
+            b = _pre.preprocess_thermal_batch(raw2, size, path="train", out=self.pre_out[1], histogram=self.histogram)
             return (a.thermal, b.thermal), (a.grad_stats, b.grad_stats)
 
         if self.overlap:

@@ -75,12 +75,16 @@ class ThermalBatch(NamedTuple):
 
 
 def preprocess_thermal_batch(raw_u16: torch.Tensor, img_size=(224, 224), path: str = "train",
-                             out_channels: int = 3, out: Optional[dict] = None) -> ThermalBatch:
+                             out_channels: int = 3, out: Optional[dict] = None,
+                             histogram: bool = True) -> ThermalBatch:
     """16-bit radiometric frames [B,Hs,Ws] -> normalised thermal [B,3,h,w].
 
     img_size is (W, H) in cv2 order like the reference's --img_size.  path='train':
     data/dataset_loader.py:237-249 + enhance_thermal_contrast (u16 resize, raw counts);
-    path='inference': thermal_dustr_inference.py:25-60 (/65535, float resize)."""
+    path='inference': thermal_dustr_inference.py:25-60 (/65535, float resize).
+    histogram=True also returns the exact 65 536-bin histogram of every resized frame (the percentiles are
+    read off it); histogram=False computes the same percentiles, bit for bit, from sampled value windows
+    without a per-pixel histogram atomic (about twice as fast; the reference itself never builds a histogram)."""
     x = _to_cuda(raw_u16).contiguous()
     if x.dtype != torch.uint16:
         raise ValueError(f"raw frames must be uint16, got {x.dtype}")
@@ -99,9 +103,11 @@ def preprocess_thermal_batch(raw_u16: torch.Tensor, img_size=(224, 224), path: s
     if pct is None:
         pct = torch.empty(B, 2, dtype=torch.float64, device=dev)
     if path == "train":
-        hist = out.get("histogram")
-        if hist is None:
-            hist = torch.empty(B, 65536, dtype=torch.int32, device=dev)
+        hist = None
+        if histogram:
+            hist = out.get("histogram")
+            if hist is None:
+                hist = torch.empty(B, 65536, dtype=torch.int32, device=dev)
         ws_bytes = lib.t3d_preprocess_workspace_bytes(B, dh, dw)
         ws = out.get("workspace")
         if ws is None or ws.numel() < ws_bytes:
