@@ -225,6 +225,102 @@ depth_extract_kernel(const PixelSrc s, int pred_offset, float* __restrict__ vz, 
     }
 }
 
+// Fast form of X for the common case: no caller mask, GT at the prediction's size, 16-byte aligned, n % 4 == 0,
+// prediction either planar (PSTRIDE 1) or the Z channel of an AoS pointmap (PSTRIDE 3, offset 2).  A thread takes
+// 4 consecutive pixels: one 128-bit load of GT, one (planar) or three (AoS: all 48 bytes are fetched from DRAM
+// anyway) of the prediction, two 128-bit stores; the integer keys are compared as raw bits; every counter is a
+// predicated add.  Same outputs as depth_extract_kernel<false>.
+__device__ __forceinline__ unsigned int key_of_bits(unsigned int b) { return b ^ ((unsigned int)((int)b >> 31) | 0x80000000u); }
+
+template <int PSTRIDE>
+__global__ void __launch_bounds__(kChunkThreads, 6)
+depth_extract_fast_kernel(const float* __restrict__ pred, const float* __restrict__ gt, int n,
+                          float* __restrict__ vz, float* __restrict__ vg, int* __restrict__ counters,
+                          const unsigned int* __restrict__ bracket, unsigned int* __restrict__ cand) {
+    __shared__ unsigned int scand[2][kCtaCand];
+    __shared__ int scount[2], sbase[2], sred[5];
+    const int b = blockIdx.y, tid = threadIdx.x, lane = tid & 31;
+    const float4* __restrict__ g4 = reinterpret_cast<const float4*>(gt + (size_t)b * n);
+    const float4* __restrict__ p4 = reinterpret_cast<const float4*>(pred + (size_t)b * n * PSTRIDE);
+    float4* __restrict__ oz4 = reinterpret_cast<float4*>(vz + (size_t)b * n);
+    float4* __restrict__ og4 = reinterpret_cast<float4*>(vg + (size_t)b * n);
+    const uint4 br = __ldg(reinterpret_cast<const uint4*>(bracket) + b);
+    const unsigned int lo_g = br.x, w_g = br.y - br.x, lo_p = br.z, w_p = br.w - br.z;       // lo > hi (no bracket): w wraps,
+    const bool has_g = br.y >= br.x, has_p = br.w >= br.z;                                    // masked by has_*
+    if (tid < 2) scount[tid] = 0;
+    if (tid < 5) sred[tid] = 0;
+    __syncthreads();
+    int nv = 0, pnan = 0, lt_g = 0, lt_p = 0;
+    const int nq = n >> 2, per = (nq + gridDim.x - 1) / gridDim.x;
+    const int q_begin = blockIdx.x * per, q_end = min(q_begin + per, nq);
+    for (int q = q_begin + tid; q < q_end; q += kChunkThreads) {
+        const float4 g = __ldg(g4 + q);
+        float4 z;
+        if (PSTRIDE == 3) {
+            const float4 a = __ldg(p4 + 3 * q), bq = __ldg(p4 + 3 * q + 1), c = __ldg(p4 + 3 * q + 2);
+            z = make_float4(a.z, bq.y, c.x, c.w);
+        } else {
+            z = __ldg(p4 + q);
+        }
+        const float gv[4] = {g.x, g.y, g.z, g.w}, pv[4] = {z.x, z.y, z.z, z.w};
+        float og[4];
+        unsigned int kgs[4], kps[4], fg = 0, fp = 0;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const unsigned int gb = __float_as_uint(gv[u]), pb = __float_as_uint(pv[u]);
+            const bool ok = (gb - 1u) < 0x7f7fffffu;                     // gt > 0 & finite (utils/metrics.py:27)
+            const bool pn = pv[u] != pv[u];
+            const bool okp = ok && !pn;
+            og[u] = ok ? gv[u] : __int_as_float(0x7fc00000);
+            kgs[u] = gb | 0x80000000u;                                   // key of a positive float
+            kps[u] = key_of_bits(pb);
+            nv += ok; pnan += (ok && pn);
+            lt_g += (ok && kgs[u] < lo_g); lt_p += (okp && kps[u] < lo_p);
+            fg |= (unsigned)(ok && has_g && (kgs[u] - lo_g) <= w_g) << u;
+            fp |= (unsigned)(okp && has_p && (kps[u] - lo_p) <= w_p) << u;
+        }
+        oz4[q] = z;
+        og4[q] = make_float4(og[0], og[1], og[2], og[3]);
+        if (fg) {                       // one shared-memory atomic per thread with candidates
+            int slot = atomicAdd(&scount[0], __popc(fg));
+#pragma unroll
+            for (int u = 0; u < 4; ++u) if (fg & (1u << u)) { if (slot < kCtaCand) scand[0][slot] = kgs[u]; ++slot; }
+        }
+        if (fp) {
+            int slot = atomicAdd(&scount[1], __popc(fp));
+#pragma unroll
+            for (int u = 0; u < 4; ++u) if (fp & (1u << u)) { if (slot < kCtaCand) scand[1][slot] = kps[u]; ++slot; }
+        }
+    }
+    nv = __reduce_add_sync(0xffffffffu, nv); pnan = __reduce_add_sync(0xffffffffu, pnan);
+    lt_g = __reduce_add_sync(0xffffffffu, lt_g); lt_p = __reduce_add_sync(0xffffffffu, lt_p);
+    int* c = counters + 8 * b;
+    if (lane == 0) {                                   // CTA-level first: one global atomic per counter per CTA
+        if (nv) atomicAdd(&sred[0], nv);
+        if (pnan) atomicAdd(&sred[1], pnan);
+        if (lt_g) atomicAdd(&sred[3], lt_g);
+        if (lt_p) atomicAdd(&sred[4], lt_p);
+    }
+    __syncthreads();
+    if (tid < 5 && sred[tid]) atomicAdd(&c[tid < 3 ? tid : tid + 1], sred[tid]);
+    if (tid < 2) {
+        const int k = scount[tid];
+        if (k > kCtaCand) { atomicExch(&c[3], 1); sbase[tid] = -1; }         // local overflow -> fallback
+        else {
+            const int base = k ? atomicAdd(&c[6 + tid], k) : 0;
+            if (base + k > kCandCap) { atomicExch(&c[3], 1); sbase[tid] = -1; }
+            else sbase[tid] = base;
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int a = 0; a < 2; ++a) {
+        const int base = sbase[a], k = min(scount[a], kCtaCand);
+        if (base >= 0)
+            for (int q = tid; q < k; q += kChunkThreads) cand[((size_t)b * 2 + a) * kCandCap + base + q] = scand[a][q];
+    }
+}
+
 // ------------------------------------------------------------------ M: exact medians -> scale
 constexpr int kMedThreads = t3d_select::kThreads;
 
@@ -310,6 +406,26 @@ __device__ __forceinline__ void metric_terms(float gt, float z, float s, float a
     accf[3] += dl * dl;                                                      // :59
 }
 
+// Fast form of the per-pixel terms for the common case (no caller mask: gt is a positive finite number or the
+// NaN "invalid" marker; scaled prediction positive): branch-free, validity by select, counts by predicate.
+// Same arithmetic as metric_terms<false>: ONE IEEE division max/min keeps the delta-counts exact.
+__device__ __forceinline__ float lg2_fast(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+
+__device__ __forceinline__ void metric_terms_fast(float gt, float pr, float accf[4], int cnt[3]) {
+    const bool valid = (gt == gt);                                           // NaN marks an unselected pixel
+    const float g = valid ? gt : 1.0f, q = valid ? pr : 1.0f;               // -> th = 1, every term 0
+    const float th = __fdiv_rn(fmaxf(g, q), fminf(g, q));                    // :51 (exactly one of the two ratios is >= 1)
+    const float dl = 0.69314718f * lg2_fast(th);                             // |log gt - log pred|, th >= 1 is normal
+    cnt[0] += (valid && th < 1.25f); cnt[1] += (valid && th < 1.5625f); cnt[2] += (valid && th < 1.953125f);   // :52-54
+    const float d = g - q;
+    const float d2 = d * d;
+    const float rg = __fdividef(1.0f, g);
+    accf[0] = fmaf(fabsf(d), rg, accf[0]);                                   // :56  |gt - pred| / gt
+    accf[1] = fmaf(d2, rg, accf[1]);                                         // :57
+    accf[2] += d2;                                                           // :58
+    accf[3] = fmaf(dl, dl, accf[3]);                                         // :59
+}
+
 template <bool GENERAL>
 __global__ void __launch_bounds__(kChunkThreads)
 metrics_sum_kernel(const float* __restrict__ vz, const float* __restrict__ vg,
@@ -326,18 +442,32 @@ metrics_sum_kernel(const float* __restrict__ vz, const float* __restrict__ vg,
     if ((n & 3) == 0) {                       // 128-bit path; fp32 runs of 8 terms folded into fp64
         const int n4 = n >> 2, per = (n4 + chunks - 1) / chunks;
         const int q0 = chunk * per, q1 = min(q0 + per, n4);
+        const float4 qnan4 = make_float4(__int_as_float(0x7fc00000), __int_as_float(0x7fc00000),
+                                         __int_as_float(0x7fc00000), __int_as_float(0x7fc00000));
         for (int q = q0 + threadIdx.x; q < q1; q += 2 * kChunkThreads) {
             const int q2 = q + kChunkThreads;
             const float4 ga = __ldg(reinterpret_cast<const float4*>(g) + q);
             const float4 za = __ldg(reinterpret_cast<const float4*>(z) + q);
-            float4 gb = make_float4(__int_as_float(0x7fc00000), __int_as_float(0x7fc00000),
-                                    __int_as_float(0x7fc00000), __int_as_float(0x7fc00000)), zb = gb;
+            float4 gb = qnan4, zb = qnan4;
             if (q2 < q1) { gb = __ldg(reinterpret_cast<const float4*>(g) + q2); zb = __ldg(reinterpret_cast<const float4*>(z) + q2); }
+            const float gt[8] = {ga.x, ga.y, ga.z, ga.w, gb.x, gb.y, gb.z, gb.w};
+            float pr[8] = {za.x, za.y, za.z, za.w, zb.x, zb.y, zb.z, zb.w};
             float accf[4] = {0.f, 0.f, 0.f, 0.f};
-            metric_terms<GENERAL>(ga.x, za.x, s, accf, cnt); metric_terms<GENERAL>(ga.y, za.y, s, accf, cnt);
-            metric_terms<GENERAL>(ga.z, za.z, s, accf, cnt); metric_terms<GENERAL>(ga.w, za.w, s, accf, cnt);
-            metric_terms<GENERAL>(gb.x, zb.x, s, accf, cnt); metric_terms<GENERAL>(gb.y, zb.y, s, accf, cnt);
-            metric_terms<GENERAL>(gb.z, zb.z, s, accf, cnt); metric_terms<GENERAL>(gb.w, zb.w, s, accf, cnt);
+            float lowest = 1.0f;                                                         // NaN-propagating min of the scaled predictions
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                pr[e] = __fmul_rn(pr[e], s);                                             // pred *= scale   (:48)
+                const float m = (gt[e] == gt[e]) ? pr[e] : 1.0f;                         // unselected pixels do not matter
+                asm("min.NaN.f32 %0, %0, %1;" : "+f"(lowest) : "f"(m));
+            }
+            if (!GENERAL && lowest > 0.f) {                                              // all selected predictions positive (not NaN)
+#pragma unroll
+                for (int e = 0; e < 8; ++e) metric_terms_fast(gt[e], pr[e], accf, cnt);
+            } else {
+                const float za8[8] = {za.x, za.y, za.z, za.w, zb.x, zb.y, zb.z, zb.w};
+#pragma unroll 1
+                for (int e = 0; e < 8; ++e) metric_terms<GENERAL>(gt[e], za8[e], s, accf, cnt);
+            }
 #pragma unroll
             for (int k = 0; k < 4; ++k) acc[k] += (double)accf[k];
         }
@@ -524,7 +654,15 @@ int t3d_depth_metrics(const float* pred, int pred_stride, int pred_offset,
         T3D_LAUNCH("metrics_sample_kernel", st, metrics_sample_kernel<<<dim3(2, B), 1024, 0, st>>>(src, pred_offset, w.bracket));
     else
         T3D_CUDA(cudaMemsetAsync(w.bracket, 0xff, (size_t)B * 4 * sizeof(unsigned int), st));   // empty brackets
-    if (mask || src.resample)
+    const bool fast_x = !mask && !src.resample && (n % 4 == 0) && t3d_aligned16(pred) && t3d_aligned16(gt) &&
+                        ((pred_stride == 3 && pred_offset == 2) || (pred_stride == 1 && pred_offset == 0));
+    if (fast_x && pred_stride == 3)
+        T3D_LAUNCH("depth_extract_kernel", st, depth_extract_fast_kernel<3><<<g, kChunkThreads, 0, st>>>(
+            pred, gt, n, w.vz, w.vg, w.counters, w.bracket, w.cand));
+    else if (fast_x)
+        T3D_LAUNCH("depth_extract_kernel", st, depth_extract_fast_kernel<1><<<g, kChunkThreads, 0, st>>>(
+            pred, gt, n, w.vz, w.vg, w.counters, w.bracket, w.cand));
+    else if (mask || src.resample)
         T3D_LAUNCH("depth_extract_kernel", st, depth_extract_kernel<true><<<g, kChunkThreads, 0, st>>>(
             src, pred_offset, w.vz, w.vg, w.counters, w.bracket, w.cand));
     else
