@@ -43,6 +43,10 @@ def parse():
     ap.add_argument("--multi-scale", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample-pairs", type=int, default=2)
+    ap.add_argument("--workload", default="train", choices=["train", "eval"],
+                    help="train: BASELINE configs[2] (the metric's configuration, default); eval: configs[4] "
+                         "(640x512 u16 preprocessing + pointmap->depth + metrics over a dataset shard; extra line)")
+    ap.add_argument("--eval-frames", type=int, default=2560, help="frames per rank for --workload eval (8 ranks: 20 480)")
     return ap.parse_args()
 
 
@@ -391,10 +395,88 @@ def run_b200(a):
         dist.destroy_process_group()
 
 
+# --------------------------------------------------------------------------- configs[4]: evaluation shard
+def run_eval(a):
+    """frames/s of the evaluation path (BASELINE.json configs[4]): every step = one batch of `--batch` full-res
+    640x512 16-bit frames -> preprocessing to the model size + pointmap -> depth -> depth metrics vs 512x512 GT
+    depth (nearest resample), accumulated on the device; ONE all-reduce of the accumulator at the end.  `--steps`
+    is ignored: the shard (`--eval-frames` per rank) is processed once, timed on the device, max over ranks."""
+    import torch
+    import torch.distributed as dist
+    from thermal3d_vision_b200 import _lib
+    from thermal3d_vision_b200.pipeline import EvalStep
+
+    world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    B, H, W = a.batch, a.height, a.width
+    nb = max(1, a.eval_frames // B)
+    step = EvalStep(B, H, W, gt_hw=(512, 512), device=dev)
+    g = torch.Generator(device=dev).manual_seed(100 + rank)
+    # a pool of 4 distinct synthetic batches (1 GB) cycled over the shard: larger than L2, no flush needed
+    pool = []
+    for k in range(4):
+        d = make_inputs_torch(B, H, W, seed=1000 * rank + k, device=dev)
+        gt = 1.5 + 3 * torch.randn(B, 512, 512, device=dev, generator=g).abs()
+        pm = d["pred1"].clone()
+        pm[..., 2] = torch.nn.functional.interpolate(gt[:, None], size=(H, W), mode="nearest")[:, 0] * \
+            (1 + 0.05 * torch.randn(B, H, W, device=dev, generator=g)) * 0.7
+        pool.append((d["raw1"], pm, gt))
+    for k in range(max(a.warmup, 3)):
+        step.run_batch(*pool[k % 4])
+    step.acc.state.zero_()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    n0 = _lib.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for k in range(nb):
+        step.run_batch(*pool[k % 4])
+    e1.record()
+    res = step.finish()                      # the one all-reduce + host read
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = t.item()
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        frames = world * nb * B
+        ab = step.algorithmic_bytes() * nb
+        print(json.dumps({
+            "metric": "frames/sec of 640x512 u16 preprocessing + pointmap->depth + metrics (BASELINE configs[4])",
+            "value": frames / (ms * 1e-3), "unit": "frames/s", "n_gpus": world, "steps": nb, "warmup": max(a.warmup, 3),
+            "ms_per_step": ms / nb, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": {"workload": f"eval_shard_{nb * B}_frames_per_rank_640x512_u16_to_{W}x{H}+depth_metrics_gt512x512",
+                                            "per_rank_frames": nb * B, "global_frames": frames, "batch": B,
+                                            "l2_policy": "inputs_exceed_l2 (pool of 4 batches, 1 GB)"},
+            "roofline": {"bound": "hbm", "achieved": ab / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                         "frac": ab / (ms * 1e-3) / 1e9 / peak, "traffic": None,
+                         "note": "whole evaluation step (algorithmic bytes of preprocessing + metrics / step time)"},
+            "gpu_launches": int(_lib.launch_count() - n0), "check": {k: res[k] for k in ("abs_rel", "rmse", "acc_1")},
+        }), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     a = parse()
     if a.impl == "reference":
         run_reference(a)
+    elif a.workload == "eval":
+        run_eval(a)
     else:
         run_b200(a)
 

@@ -241,6 +241,12 @@ int t3d_depth_metrics(const float* pred, int pred_stride, int pred_offset,
                       float* out, double* out_f64, float* out_medians,
                       void* workspace, size_t workspace_bytes, void* stream);
 
+/* Dataset accumulator of utils/metrics.py:128-136 (evaluate_thermal_depth): state[0..6] += the finite
+ * per-image metrics of metrics_f64 [B][8] (t3d_depth_metrics' out_f64), state[7] += B (non-finite values are
+ * skipped but the image still counts).  `state` is 8 doubles on the device; all-reducing it (SUM) over ranks
+ * gives the data-parallel accumulator.  Deterministic (fixed summation order). */
+int t3d_metrics_accumulate(const double* metrics_f64, int B, double* state, void* stream);
+
 /* depth = pointmap[..., 2] materialised (thermal_dustr_inference.py:133-134). */
 int t3d_pointmap_to_depth(const float* pointmap, float* depth, size_t n_pixels, void* stream);
 

@@ -130,3 +130,36 @@ def test_accumulator_matches_reference_semantics(cuda_device, kat):
     ref = ref_metrics.accumulate_dataset(per)
     for k in K7[:4]:
         assert got[k] == pytest.approx(ref[k], rel=1e-5)
+
+
+def test_eval_step_config5_shape(cuda_device):
+    """BASELINE configs[4] at a reduced frame count: 640x512 u16 frames -> 512x384 model input, pointmap -> depth
+    -> metrics against GT depth of another size (nearest resample), dataset accumulator vs the oracle loop."""
+    from oracle import ref_preprocess
+    from thermal3d_vision_b200.pipeline import EvalStep
+    B, H, W, gh, gw = 3, 384, 512, 512, 512
+    rng = np.random.default_rng(3)
+    raw = ref_preprocess.make_raw_frames(2 * B, seed=31)
+    gts = (1.5 + 3 * np.abs(rng.standard_normal((2 * B, gh, gw)))).astype(np.float32)
+    gts[1, :40] = 0.0                                     # invalid region
+    gts[4] = 0.0                                          # an image with an empty mask (counted, contributes nothing)
+    pms = rng.standard_normal((2 * B, H, W, 3)).astype(np.float32)
+    step = EvalStep(B, H, W, gt_hw=(gh, gw), device=cuda_device)
+    per = []
+    for k in range(2):                                    # two batches
+        sl = slice(k * B, (k + 1) * B)
+        gt_small = np.stack([ref_preprocess.resize_nearest(g, (H, W)) for g in gts[sl]])
+        pms[sl, ..., 2] = gt_small * (1.0 + 0.05 * rng.standard_normal((B, H, W))).astype(np.float32) * 0.7
+        th = step.run_batch(torch.from_numpy(raw[sl]).to(cuda_device), torch.from_numpy(pms[sl]).to(cuda_device),
+                            torch.from_numpy(gts[sl]).to(cuda_device))
+        for i in range(B):
+            o, _, _, _ = ref_preprocess.train_path(raw[k * B + i], (H, W))
+            assert (th[i].cpu().numpy() == o).all()       # the model input is bit-exact
+            if (gt_small[i] > 0).any():
+                per.append(ref_metrics.compute_depth_metrics(pms[k * B + i, ..., 2], gt_small[i]))
+            else:
+                per.append({k7: np.nan for k7 in K7})
+    got = step.finish()
+    ref = ref_metrics.accumulate_dataset(per)
+    for k7 in K7:
+        assert got[k7] == pytest.approx(ref[k7], rel=1e-5), k7

@@ -232,15 +232,27 @@ depth_extract_kernel(const PixelSrc s, int pred_offset, float* __restrict__ vz, 
 // predicated add.  Same outputs as depth_extract_kernel<false>.
 __device__ __forceinline__ unsigned int key_of_bits(unsigned int b) { return b ^ ((unsigned int)((int)b >> 31) | 0x80000000u); }
 
-template <int PSTRIDE>
+constexpr int kResampleMaxDim = 2048;      // H + W limit of the in-kernel nearest-neighbour index tables (8 KB)
+
+template <int PSTRIDE, bool RESAMPLE>
 __global__ void __launch_bounds__(kChunkThreads, 6)
 depth_extract_fast_kernel(const float* __restrict__ pred, const float* __restrict__ gt, int n,
                           float* __restrict__ vz, float* __restrict__ vg, int* __restrict__ counters,
-                          const unsigned int* __restrict__ bracket, unsigned int* __restrict__ cand) {
+                          const unsigned int* __restrict__ bracket, unsigned int* __restrict__ cand,
+                          int H, int W, int gt_h, int gt_w) {
     __shared__ unsigned int scand[2][kCtaCand];
     __shared__ int scount[2], sbase[2], sred[5];
+    __shared__ int stab[RESAMPLE ? kResampleMaxDim : 1];          // cv2 INTER_NEAREST source column (W) / row offset (H)
     const int b = blockIdx.y, tid = threadIdx.x, lane = tid & 31;
-    const float4* __restrict__ g4 = reinterpret_cast<const float4*>(gt + (size_t)b * n);
+    if (RESAMPLE) {     // utils/evaluate_depth_metrics.py:321-323: sx = min(floor(x * gw / W), gw - 1), same for rows
+        const double fx = (double)gt_w / (double)W, fy = (double)gt_h / (double)H;
+        for (int i = tid; i < W + H; i += kChunkThreads) {
+            if (i < W) stab[i] = min((int)floor(__dmul_rn((double)i, fx)), gt_w - 1);
+            else stab[i] = min((int)floor(__dmul_rn((double)(i - W), fy)), gt_h - 1) * gt_w;
+        }
+    }
+    const float* __restrict__ gimg = gt + (size_t)b * gt_h * gt_w;
+    const float4* __restrict__ g4 = reinterpret_cast<const float4*>(gimg);
     const float4* __restrict__ p4 = reinterpret_cast<const float4*>(pred + (size_t)b * n * PSTRIDE);
     float4* __restrict__ oz4 = reinterpret_cast<float4*>(vz + (size_t)b * n);
     float4* __restrict__ og4 = reinterpret_cast<float4*>(vg + (size_t)b * n);
@@ -254,7 +266,14 @@ depth_extract_fast_kernel(const float* __restrict__ pred, const float* __restric
     const int nq = n >> 2, per = (nq + gridDim.x - 1) / gridDim.x;
     const int q_begin = blockIdx.x * per, q_end = min(q_begin + per, nq);
     for (int q = q_begin + tid; q < q_end; q += kChunkThreads) {
-        const float4 g = __ldg(g4 + q);
+        float4 g;
+        if (RESAMPLE) {                                   // W % 4 == 0: the quad lies in one row
+            const int y = (4 * q) / W, x = 4 * q - y * W;
+            const float* row = gimg + stab[W + y];
+            g = make_float4(__ldg(row + stab[x]), __ldg(row + stab[x + 1]), __ldg(row + stab[x + 2]), __ldg(row + stab[x + 3]));
+        } else {
+            g = __ldg(g4 + q);
+        }
         float4 z;
         if (PSTRIDE == 3) {
             const float4 a = __ldg(p4 + 3 * q), bq = __ldg(p4 + 3 * q + 1), c = __ldg(p4 + 3 * q + 2);
@@ -520,6 +539,16 @@ __global__ void metrics_finalize_kernel(const double* __restrict__ partials, con
     if (out_f64) out_f64[(size_t)b * 8 + k] = r;
 }
 
+// Dataset accumulator of utils/metrics.py:128-136: state[0..6] += finite per-image metrics, state[7] += images.
+// One warp per metric, fixed lane order (deterministic).
+__global__ void metrics_accumulate_kernel(const double* __restrict__ m, int B, double* __restrict__ state) {
+    const int k = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double s = 0;
+    if (k < 7) for (int b = lane; b < B; b += 32) { const double v = m[(size_t)b * 8 + k]; if (isfinite(v)) s += v; }
+    s = warp_sum(s);
+    if (lane == 0) state[k] += (k < 7) ? s : (double)B;
+}
+
 // ------------------------------------------------------------------ intrinsics: median focal estimate
 // scripts/pseudo_gt.py:151-184: fx = median((u - W/2) / (X/Z)), fy = median((v - H/2) / (Y/Z)) over Z > 0, fp32
 __global__ void __launch_bounds__(t3d_select::kThreads, 1)
@@ -654,14 +683,14 @@ int t3d_depth_metrics(const float* pred, int pred_stride, int pred_offset,
         T3D_LAUNCH("metrics_sample_kernel", st, metrics_sample_kernel<<<dim3(2, B), 1024, 0, st>>>(src, pred_offset, w.bracket));
     else
         T3D_CUDA(cudaMemsetAsync(w.bracket, 0xff, (size_t)B * 4 * sizeof(unsigned int), st));   // empty brackets
-    const bool fast_x = !mask && !src.resample && (n % 4 == 0) && t3d_aligned16(pred) && t3d_aligned16(gt) &&
+    const bool fast_x = !mask && (W % 4 == 0) && t3d_aligned16(pred) && t3d_aligned16(gt) &&
+                        (!src.resample || H + W <= kResampleMaxDim) && (src.resample || (gt_h * gt_w) % 4 == 0) &&
                         ((pred_stride == 3 && pred_offset == 2) || (pred_stride == 1 && pred_offset == 0));
-    if (fast_x && pred_stride == 3)
-        T3D_LAUNCH("depth_extract_kernel", st, depth_extract_fast_kernel<3><<<g, kChunkThreads, 0, st>>>(
-            pred, gt, n, w.vz, w.vg, w.counters, w.bracket, w.cand));
-    else if (fast_x)
-        T3D_LAUNCH("depth_extract_kernel", st, depth_extract_fast_kernel<1><<<g, kChunkThreads, 0, st>>>(
-            pred, gt, n, w.vz, w.vg, w.counters, w.bracket, w.cand));
+#define T3D_XFAST(PS_, RS_) T3D_LAUNCH("depth_extract_kernel", st, (depth_extract_fast_kernel<PS_, RS_><<<g, kChunkThreads, 0, st>>>( \
+            pred, gt, n, w.vz, w.vg, w.counters, w.bracket, w.cand, H, W, gt_h, gt_w)))
+    if (fast_x && pred_stride == 3) { if (src.resample) T3D_XFAST(3, true); else T3D_XFAST(3, false); }
+    else if (fast_x) { if (src.resample) T3D_XFAST(1, true); else T3D_XFAST(1, false); }
+#undef T3D_XFAST
     else if (mask || src.resample)
         T3D_LAUNCH("depth_extract_kernel", st, depth_extract_kernel<true><<<g, kChunkThreads, 0, st>>>(
             src, pred_offset, w.vz, w.vg, w.counters, w.bracket, w.cand));
@@ -678,6 +707,14 @@ int t3d_depth_metrics(const float* pred, int pred_stride, int pred_offset,
         T3D_LAUNCH("metrics_sum_kernel", st, metrics_sum_kernel<false><<<g, kChunkThreads, 0, st>>>(
             w.vz, w.vg, medians, w.counters, median_scaling, n, chunks, w.partials));
     T3D_LAUNCH("metrics_finalize_kernel", st, metrics_finalize_kernel<<<B, 32, 0, st>>>(w.partials, w.counters, chunks, out, out_f64));
+    return T3D_OK;
+}
+
+int t3d_metrics_accumulate(const double* metrics_f64, int B, double* state, void* stream) {
+    T3D_REQUIRE(metrics_f64 && state, "NULL pointer");
+    T3D_REQUIRE(B >= 1, "bad dims");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    T3D_LAUNCH("metrics_accumulate_kernel", st, metrics_accumulate_kernel<<<1, 256, 0, st>>>(metrics_f64, B, state));
     return T3D_OK;
 }
 

@@ -11,6 +11,8 @@
 #include "t3d_preprocess_internal.cuh"
 #include "t3d_select.cuh"
 
+#include <stdlib.h>
+
 namespace {
 
 template <typename SrcT, bool DIV65535>
@@ -426,11 +428,16 @@ __global__ void __launch_bounds__(kNormThreads, 4) normalize_stats_u16_kernel(co
                                                                            float* __restrict__ dst, int H, int W,
                                                                            float* __restrict__ stats,
                                                                            const float2* __restrict__ glut,
-                                                                           const int2* __restrict__ lutmeta) {
+                                                                           const int2* __restrict__ lutmeta, int nitems) {
     extern __shared__ float2 lut[];                 // {normalised value, its gray} for v in [floor(p2) - 1, ceil(p98) + 1]
     __shared__ float red[kNormWarps][2];
-    const int b = blockIdx.y, band = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
     const int n = H * W;
+    // persistent over (frame, band) items: the grid is sized by the launcher (SMs x CTAs per SM), so the kernel
+    // can be told to leave room on every SM for a concurrent kernel of another stream
+    for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+    const int b = item / kNormBands, band = item - b * kNormBands;
+    __syncthreads();                                                  // previous item's LUT / red are no longer read
     const int2 lm = lutmeta[b];
     const int lom1 = lm.x, range = lm.y;
     const uint16_t* __restrict__ s = src + (size_t)b * n;
@@ -545,6 +552,7 @@ __global__ void __launch_bounds__(kNormThreads, 4) normalize_stats_u16_kernel(co
             stats[((size_t)b * kNormBands + band) * 4 + 2 + tid] = 0.f;      // scale-2 sums are not produced here
         }
     }
+    }   // items
 }
 
 // float source [B, channels, n] (drop-in enhance_thermal_contrast); rep output planes
@@ -708,9 +716,11 @@ int t3d_preprocess_train_u16(const uint16_t* raw, int B, int src_h, int src_w, i
             T3D_CUDA(cudaFuncSetAttribute(normalize_stats_u16_kernel<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kLutMax * 8));
             nattr = true;
         }
-        dim3 grid(kNormBands, (unsigned)B);
+        static const int norm_ctas = [] { const char* e = getenv("T3D_NORM_CTAS"); const int v = e ? atoi(e) : 32; return v < 1 ? 1 : v; }();
+        const int nitems = B * kNormBands;
+        const int grid = min(nitems, t3d_sm_count() * norm_ctas);
 #define T3D_NORM_LAUNCH(REP_, ST_) T3D_LAUNCH("normalize_stats_u16_kernel", st, (normalize_stats_u16_kernel<REP_, ST_><<<grid, kNormThreads, kLutMax * 8, st>>>( \
-            nsrc, percentiles, out, dst_h, dst_w, grad_stats, w.lut, w.lutmeta)))
+            nsrc, percentiles, out, dst_h, dst_w, grad_stats, w.lut, w.lutmeta, nitems)))
         if (out_channels == 3) { if (grad_stats) T3D_NORM_LAUNCH(3, true); else T3D_NORM_LAUNCH(3, false); }
         else { if (grad_stats) T3D_NORM_LAUNCH(1, true); else T3D_NORM_LAUNCH(1, false); }
 #undef T3D_NORM_LAUNCH

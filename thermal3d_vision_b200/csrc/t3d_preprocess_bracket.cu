@@ -18,6 +18,8 @@
 #include "t3d_preprocess_internal.cuh"
 #include "t3d_select.cuh"
 
+#include <stdlib.h>
+
 namespace {
 
 constexpr int kSamp = 4096;
@@ -479,6 +481,8 @@ int t3d_launch_bracket_percentiles(const uint16_t* raw, int B, int sh, int sw, i
                 attr_smem[di] = smem;
                 T3D_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm[di], fn, kRzThreads, smem));
                 if (ctas_per_sm[di] < 1) ctas_per_sm[di] = 1;
+                const char* e = getenv("T3D_RZ_CTAS");          // tuning knob: leave room for a concurrent kernel
+                if (e && atoi(e) >= 1) ctas_per_sm[di] = min(ctas_per_sm[di], atoi(e));
             }
             const long long total = (long long)B * nstrips * dh;
             long long grid = (long long)t3d_sm_count() * ctas_per_sm[di];

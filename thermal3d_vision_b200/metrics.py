@@ -130,9 +130,11 @@ class MetricAccumulator:
         self.state = torch.zeros(8, dtype=torch.float64, device=device)   # 7 sums + image count
 
     def update(self, metrics_f64: torch.Tensor):
-        m = metrics_f64[:, :7]
-        self.state[:7] += torch.where(torch.isfinite(m), m, torch.zeros_like(m)).sum(0)
-        self.state[7] += metrics_f64.shape[0]
+        if metrics_f64.dtype != torch.float64 or not metrics_f64.is_contiguous() or metrics_f64.shape[1] != 8:
+            raise ValueError("metrics_f64 must be a contiguous float64 [B, 8] tensor (compute_depth_metrics_batch)")
+        rc = _lib.lib().t3d_metrics_accumulate(_lib.ptr(metrics_f64), int(metrics_f64.shape[0]), _lib.ptr(self.state),
+                                               _lib.current_stream_ptr())
+        _lib.check(rc, "t3d_metrics_accumulate")
 
     def all_reduce(self):
         import torch.distributed as dist

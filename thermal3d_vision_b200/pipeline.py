@@ -156,3 +156,55 @@ class HotPathStep:
     @staticmethod
     def summarize(result_host: torch.Tensor) -> Dict[str, float]:
         return _dist.summarize(result_host.tolist())
+
+
+class EvalStep:
+    """BASELINE.json configs[4]: full-resolution 16-bit frames -> preprocessing (the model's input) and, for the
+    model's pointmaps (the caller's; synthetic in bench.py), pointmap -> depth -> depth metrics against the GT
+    depth, accumulated over a dataset shard with the reference's semantics (utils/metrics.py:86-136: finite
+    per-image metrics summed, divided by the count of ALL images).  One rank = one contiguous shard
+    (distributed.shard_range); `finish()` does the single all-reduce of the 8-double accumulator.
+
+    path='train': data/dataset_loader.py:237-249 + enhance_thermal_contrast (u16 resize, raw counts);
+    path='inference': utils/evaluate_depth_metrics.py:162-197 (/65535, float resize, float percentiles).
+    GT depth of another size is nearest-resampled inside the metric kernels (utils/evaluate_depth_metrics.py:320-323).
+    """
+
+    def __init__(self, B: int, H: int, W: int, raw_hw=(512, 640), gt_hw=None, device=None, path: str = "train"):
+        self.B, self.H, self.W, self.raw_hw, self.path = B, H, W, tuple(raw_hw), path
+        self.gt_hw = tuple(gt_hw) if gt_hw is not None else (H, W)
+        self.device = torch.device(device if device is not None else "cuda")
+        dev, lib = self.device, _lib.lib()
+        f32 = dict(dtype=torch.float32, device=dev)
+        self.pre_out = {"thermal": torch.empty(B, 3, H, W, **f32),
+                        "percentiles": torch.empty(B, 2, dtype=torch.float64, device=dev),
+                        "workspace": torch.empty(lib.t3d_preprocess_workspace_bytes(B, H, W), dtype=torch.uint8, device=dev)}
+        self.met_out = {"workspace": torch.empty(lib.t3d_depth_metrics_workspace_bytes(B, H, W), dtype=torch.uint8, device=dev),
+                        "metrics": torch.empty(B, 8, **f32), "metrics_f64": torch.empty(B, 8, dtype=torch.float64, device=dev),
+                        "medians": torch.empty(B, 2, **f32)}
+        self.acc = _metrics.MetricAccumulator(dev)
+        self.side = torch.cuda.Stream(device=dev)
+        self.fork, self.join = torch.cuda.Event(), torch.cuda.Event()
+
+    def algorithmic_bytes(self) -> int:
+        """Per batch: u16 frame in + 3 fp32 planes out, AoS pointmap + GT depth in."""
+        n, raw, gt = self.H * self.W, self.raw_hw[0] * self.raw_hw[1], self.gt_hw[0] * self.gt_hw[1]
+        return self.B * ((2 * raw + 12 * n) + (12 * n + 4 * min(gt, n) + 64))
+
+    def run_batch(self, raw, pointmap, gt_depth):
+        """raw [B,Hs,Ws] uint16, pointmap [B,H,W,3] float32, gt_depth [B,gh,gw] float32, all on the device.
+        Returns the preprocessed thermal batch [B,3,H,W]; the metrics go into the accumulator.  No host sync."""
+        main = torch.cuda.current_stream(self.device)
+        self.fork.record(main)
+        with torch.cuda.stream(self.side):
+            self.side.wait_event(self.fork)
+            me = _metrics.compute_depth_metrics_batch(pointmap, gt_depth, out=self.met_out)
+            self.join.record(self.side)
+        tb = _pre.preprocess_thermal_batch(raw, (self.W, self.H), path=self.path, out=self.pre_out, histogram=False)
+        main.wait_event(self.join)
+        self.acc.update(me["metrics_f64"])
+        return tb.thermal
+
+    def finish(self) -> Dict[str, float]:
+        """All-reduce (SUM) the accumulator over the ranks and return the dataset-mean metrics (host sync)."""
+        return self.acc.all_reduce().result()
