@@ -198,6 +198,12 @@ int t3d_preprocess_train_u16(const uint16_t* raw, int B, int src_h, int src_w, i
 /* Number of statistic partials per frame written to grad_stats (0: not available for this shape). */
 int t3d_preprocess_stats_tiles(int dst_h, int dst_w);
 
+/* Diagnostics of the last t3d_preprocess_train_u16 call with hist == NULL on `workspace`: the number of frames
+ * whose percentile ranks fell outside the sampled value windows and were found by the exact per-frame select
+ * instead (same result, slower).  Synchronises `stream`; *count_host is host memory. */
+int t3d_preprocess_fallback_count(const void* workspace, int B, int dst_h, int dst_w, unsigned int* count_host,
+                                  void* stream);
+
 /* enhance_thermal_contrast on float data (utils/preprocessing.py:6-30): x is
  * [B,channels,n].  channels == 3: if np.allclose(c0,c1) and np.allclose(c0,c2)
  * the plane is c0, else the fp32 gray 0.299 c0 + 0.587 c1 + 0.114 c2 (:13-19;

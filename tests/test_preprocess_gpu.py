@@ -225,3 +225,21 @@ def test_bracket_percentiles_adversarial_frames(cuda_device):
         for i, f in enumerate(frames):
             o, p2, p98, _ = ref_preprocess.train_path(f, (size[1], size[0]))
             assert np.array_equal(b.thermal[i].cpu().numpy(), o, equal_nan=True), (size, i)
+
+
+def test_bracket_windows_hold_on_typical_frames(cuda_device):
+    """Performance guard: on ordinary frames (day / night + hot blobs, real-data-like smooth fields) the sampled
+    windows must contain the percentile ranks -- no frame may need the exact-select fallback."""
+    from thermal3d_vision_b200 import preprocessing as pp
+    raw = ref_preprocess.make_raw_frames(48, seed=77)
+    yy, xx = np.mgrid[0:512, 0:640]
+    smooth = (22500 + 600 * np.sin(xx / 97.0) * np.cos(yy / 61.0) + 40 * np.random.default_rng(5).standard_normal((512, 640)))
+    raw = np.concatenate([raw, smooth[None].astype(np.uint16), (smooth[None] * 0 + 23000 + (xx // 8 % 2) * 300).astype(np.uint16)])
+    d = torch.from_numpy(raw).to(cuda_device)
+    for size in ((512, 384), (224, 224)):
+        out2 = {"workspace": torch.empty(pp._lib.lib().t3d_preprocess_workspace_bytes(d.shape[0], size[1], size[0]),
+                                         dtype=torch.uint8, device=cuda_device)}
+        b = pp.preprocess_thermal_batch(d, size, path="train", histogram=False, out=out2)
+        assert pp.bracket_fallback_count(out2["workspace"], d.shape[0], size) == 0, size
+        h = pp.preprocess_thermal_batch(d, size, path="train", histogram=True)
+        assert torch.equal(b.percentiles, h.percentiles) and torch.equal(b.thermal, h.thermal)

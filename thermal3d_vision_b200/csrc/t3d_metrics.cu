@@ -23,7 +23,7 @@ constexpr int kNPart = 8;   // abs_rel, sq_rel, sq, log2, a1, a2, a3, (pad)
 
 // Batched exact medians in two passes over the data (np.median, utils/metrics.py:47):
 //   S  sample 4096 valid pixels per image, sort them in shared memory, and bracket the median of each
-//      stream (0 = gt, 1 = pred) by two sample order statistics 5 sigma apart;
+//      stream (0 = gt, 1 = pred) by two sample order statistics 7 sigma either side;
 //   X  the extraction pass (the only full read of the AoS pointmap) counts the elements below the bracket
 //      and collects the few percent that fall inside it;
 //   M  one CTA per image selects the exact middle order statistics among the candidates (radix select in
@@ -101,8 +101,9 @@ __global__ void __launch_bounds__(1024, 1) metrics_sample_kernel(const PixelSrc 
 #pragma unroll
     for (int q = 0; q < kSample / 1024; ++q) {
         const int k = q * 1024 + tid;
-        // n >= kSample: evenly strided distinct pixels; smaller images: every pixel exactly once
-        const int i = (n >= kSample) ? (int)(((long long)k * n) / kSample) : k;
+        // n >= kSample: 1024 evenly strided quads of 4 consecutive pixels (they share their cache lines: a
+        // quarter of the scattered DRAM reads); smaller images: every pixel exactly once
+        const int i = (n >= kSample) ? 4 * (int)(((long long)(k >> 2) * (n >> 2)) / (kSample >> 2)) + (k & 3) : k;
         unsigned int kk = 0xffffffffu;                             // sentinel: not part of the sample
         if (i < n) {
             float gv, pv; bool ok;
@@ -119,7 +120,7 @@ __global__ void __launch_bounds__(1024, 1) metrics_sample_kernel(const PixelSrc 
     const int mm = cnt;
     unsigned int lo = 1u, hi = 0u;                                 // no bracket -> fallback
     if (mm >= 64) {                                                // block-uniform
-        const int d = (int)ceilf(2.5f * sqrtf((float)mm)) + 2;
+        const int d = (int)ceilf(3.5f * sqrtf((float)mm)) + 2;      // +-7 sigma: neighbouring samples are correlated
         const int mid = mm / 2, rl = mid - d, rh = mid + d;
         auto get = [&](int i, float* v) { const unsigned int k = key[i]; *v = t3d_select::key_float(k); return k != 0xffffffffu; };
         lo = (rl <= 0) ? 0u : t3d_select::float_key(t3d_select::select_rank(sm, kSample, (unsigned)rl, get));

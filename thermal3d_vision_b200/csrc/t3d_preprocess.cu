@@ -732,6 +732,16 @@ int t3d_preprocess_train_u16(const uint16_t* raw, int B, int src_h, int src_w, i
     return T3D_OK;
 }
 
+int t3d_preprocess_fallback_count(const void* workspace, int B, int dst_h, int dst_w, unsigned int* count_host, void* stream) {
+    T3D_REQUIRE(workspace && count_host, "NULL pointer");
+    T3D_REQUIRE(B >= 1 && dst_h >= 1 && dst_w >= 1, "bad dims");
+    const PreWs w = pre_ws_layout(const_cast<void*>(workspace), B, dst_h, dst_w);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    T3D_CUDA(cudaMemcpyAsync(count_host, w.brhist + (size_t)B * 2 * kBrSlots, sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
+    T3D_CUDA(cudaStreamSynchronize(st));
+    return T3D_OK;
+}
+
 int t3d_preprocess_stats_tiles(int dst_h, int dst_w) {
     return (dst_h >= 1 && dst_w >= 4 && dst_w % 4 == 0) ? kNormBands : 0;
 }

@@ -4,8 +4,8 @@
 // (ranks k and k+1 around each quantile).  The exact-histogram path of t3d_preprocess.cu pays one
 // shared-memory atomic per pixel, which is what bounds it (ATOMS retires about one lane per clock per SM).
 // Here:
-//   S  bracket_sample_kernel: 4096 jittered-stride samples of the RESIZED frame (evaluated on the fly from
-//      the raw frame) -> sample order statistics 6 sigma either side of each quantile rank -> two inclusive
+//   S  bracket_sample_kernel: 4096 samples (1024 jittered-stride quads) of the RESIZED frame (evaluated on the fly from
+//      the raw frame) -> sample order statistics 9 sigma either side of each quantile rank -> two inclusive
 //      value windows [lo2, hi2], [lo98, hi98] (integers: at most kBrBins values each);
 //   A  resize_march_kernel: the cv2-exact bilinear resize (data/dataset_loader.py:242), fused with the
 //      classification of every output pixel: count(v < lo) per window in registers, and a histogram of only
@@ -140,7 +140,7 @@ bracket_sample_kernel(const uint16_t* __restrict__ src, int sh, int sw, int dh, 
     __shared__ short key[kSamp];
     __shared__ Select16 sel;
     const int b = blockIdx.x, tid = threadIdx.x;
-    const int n = dh * dw, m = min(n, kSamp), stride = n / m;
+    const int n = dh * dw, m = min(n, kSamp);
     const double scx = (double)sw / (double)dw, scy = (double)sh / (double)dh;
     if (!same && b == 0) {
         for (int i = tid; i < max(dw, dh); i += 1024) {
@@ -153,8 +153,14 @@ bracket_sample_kernel(const uint16_t* __restrict__ src, int sh, int sw, int dh, 
     for (int q = 0; q < kSamp / 1024; ++q) {
         const int k = q * 1024 + tid;
         if (k < m) {
-            // jittered stride: a plain stride aliases with column-periodic images
-            const int i = (n > kSamp) ? k * stride + (int)((((unsigned)k * 2654435761u) >> 8) % (unsigned)stride) : k;
+            // 1024 jittered-stride locations x 4 consecutive pixels: the 4 pixels share their source cache lines
+            // (a quarter of the scattered DRAM reads of 4096 single pixels); a plain stride would alias with
+            // column-periodic images.  Neighbours are correlated, hence the wider (9 sigma) windows below.
+            int i = k;
+            if (n > kSamp) {
+                const int l = k >> 2, qstride = (n >> 2) / (kSamp >> 2);
+                i = 4 * (l * qstride + (int)((((unsigned)l * 2654435761u) >> 8) % (unsigned)qstride)) + (k & 3);
+            }
             unsigned int v;
             if (same) v = __ldg(s + i);
             else { const int y = i / dw, x = i - y * dw; v = bilinear_u16(s, sw, linear_tap(y, sh, scy), linear_tap(x, sw, scx)); }
@@ -162,20 +168,19 @@ bracket_sample_kernel(const uint16_t* __restrict__ src, int sh, int sw, int dh, 
         }
     }
     __syncthreads();
-    // sample ranks 6 sigma either side of each quantile's rank
-    unsigned int ranks[4]; bool open_lo[2], open_hi[2];
+    // sample ranks 9 sigma either side of each quantile's rank
+    // (clamped to the sample's extremes: pixels beyond them are simply counted as below / above the window)
+    unsigned int ranks[4];
 #pragma unroll
     for (int w = 0; w < 2; ++w) {
         const float q = w ? 0.98f : 0.02f;
         const int r = (int)(q * (float)(m - 1) + 0.5f);
-        const int d = (int)ceilf(6.0f * sqrtf((float)m * q * (1.0f - q))) + 2;
-        open_lo[w] = (r - d < 0) && (m != n); open_hi[w] = (r + d > m - 1) && (m != n);
+        const int d = (int)ceilf(9.0f * sqrtf((float)m * q * (1.0f - q))) + 2;
         ranks[2 * w] = (unsigned)max(r - d, 0); ranks[2 * w + 1] = (unsigned)min(r + d, m - 1);
     }
     select16_x4(sel, m, ranks, [&](int i) { return (int)(unsigned short)key[i]; });
     if (tid == 0) {
-        unsigned int lo2 = open_lo[0] ? 0u : sel.os[0], hi2 = open_hi[0] ? 65535u : sel.os[1];
-        unsigned int lo98 = open_lo[1] ? 0u : sel.os[2], hi98 = open_hi[1] ? 65535u : sel.os[3];
+        unsigned int lo2 = sel.os[0], hi2 = sel.os[1], lo98 = sel.os[2], hi98 = sel.os[3];
         if (lo98 <= hi2 + 1) { hi2 = max(hi2, hi98); lo98 = 65536u; hi98 = 65535u; }      // merged into A, B empty
         if (hi2 - lo2 + 1 > (unsigned)kBrBins) hi2 = lo2 + kBrBins - 1;                    // too wide: P falls back if it matters
         if (lo98 <= 65535u && hi98 - lo98 + 1 > (unsigned)kBrBins) hi98 = lo98 + kBrBins - 1;
@@ -385,7 +390,7 @@ resize_march_kernel(const uint16_t* __restrict__ src, uint16_t* __restrict__ res
 __global__ void __launch_bounds__(1024, 1)
 percentile_from_brackets_kernel(const uint16_t* __restrict__ frames, int n, const unsigned int* __restrict__ bracket,
                                 const unsigned int* __restrict__ brhist, int rep3, double* __restrict__ out_p,
-                                float2* __restrict__ glut, int2* __restrict__ lutmeta) {
+                                float2* __restrict__ glut, int2* __restrict__ lutmeta, unsigned int* __restrict__ n_fallback) {
     __shared__ unsigned int warp_tot[33];
     __shared__ int found[4];
     __shared__ Select16 sel;
@@ -439,6 +444,7 @@ percentile_from_brackets_kernel(const uint16_t* __restrict__ frames, int n, cons
     if (found[0] < 0 || found[1] < 0 || found[2] < 0 || found[3] < 0) {
         // a rank fell outside the windows: exact two-level radix select over the frame (block-uniform branch)
         const uint16_t* x = frames + (size_t)b * n;
+        if (tid == 0) atomicAdd(n_fallback, 1u);
         select16_x4(sel, n, ranks, [&](int i) { return (int)__ldg(x + i); });
         if (tid < 4) found[tid] = (int)sel.os[tid];
         __syncthreads();
@@ -457,7 +463,7 @@ percentile_from_brackets_kernel(const uint16_t* __restrict__ frames, int n, cons
 int t3d_launch_bracket_percentiles(const uint16_t* raw, int B, int sh, int sw, int dh, int dw, bool same,
                                    const PreWs& w, int rep3, double* percentiles, cudaStream_t st) {
     const int n = dh * dw;
-    T3D_CUDA(cudaMemsetAsync(w.brhist, 0, (size_t)B * 2 * kBrStride * sizeof(unsigned int), st));
+    T3D_CUDA(cudaMemsetAsync(w.brhist, 0, ((size_t)B * 2 * kBrStride + 1) * sizeof(unsigned int), st));   // + fallback counter
     T3D_LAUNCH("bracket_sample_kernel", st, bracket_sample_kernel<<<B, 1024, 0, st>>>(
         raw, sh, sw, dh, dw, same ? 1 : 0, w.bracket, w.gxt, w.gyt));
     const bool fast = !same && (dw % 4 == 0) && (sw % 8 == 0) && t3d_aligned16(raw);
@@ -504,6 +510,6 @@ int t3d_launch_bracket_percentiles(const uint16_t* raw, int B, int sh, int sw, i
             raw, w.resized, w.gxt, w.gyt, w.bracket, w.brhist, sh, sw, dh, dw));
     }
     T3D_LAUNCH("percentile_from_brackets_kernel", st, percentile_from_brackets_kernel<<<B, 1024, 0, st>>>(
-        same ? raw : w.resized, n, w.bracket, w.brhist, rep3, percentiles, w.lut, w.lutmeta));
+        same ? raw : w.resized, n, w.bracket, w.brhist, rep3, percentiles, w.lut, w.lutmeta, w.brhist + (size_t)B * 2 * kBrStride));
     return T3D_OK;
 }

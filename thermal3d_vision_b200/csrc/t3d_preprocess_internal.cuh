@@ -82,7 +82,7 @@ struct PreWs {
     unsigned int* meta;          // [2B+1]  per-frame vmin / vmax (exact-histogram path)
     uint2* gxt; uint4* gyt;      // bilinear taps
     unsigned int* bracket;       // [B][4]  lo2, hi2, lo98, hi98 (inclusive value windows)
-    unsigned int* brhist;        // [B][2][kBrSlots]
+    unsigned int* brhist;        // [B][2][kBrSlots], then one uint: frames that took the exact-select fallback
     float2* lut;                 // [B][kLutMax]
     int2* lutmeta;               // [B]
     size_t total;
@@ -98,7 +98,7 @@ static inline PreWs pre_ws_layout(void* base, int B, int dh, int dw) {
     w.gxt = reinterpret_cast<uint2*>(take((size_t)dw * sizeof(uint2)));
     w.gyt = reinterpret_cast<uint4*>(take((size_t)dh * sizeof(uint4)));
     w.bracket = reinterpret_cast<unsigned int*>(take((size_t)B * 4 * sizeof(unsigned int)));
-    w.brhist = reinterpret_cast<unsigned int*>(take((size_t)B * 2 * kBrSlots * sizeof(unsigned int)));
+    w.brhist = reinterpret_cast<unsigned int*>(take(((size_t)B * 2 * kBrSlots + 1) * sizeof(unsigned int)));
     w.lut = reinterpret_cast<float2*>(take((size_t)B * kLutMax * sizeof(float2)));
     w.lutmeta = reinterpret_cast<int2*>(take((size_t)B * sizeof(int2)));
     w.total = off;

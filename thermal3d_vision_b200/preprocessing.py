@@ -12,6 +12,8 @@ from __future__ import annotations
 import os
 from typing import NamedTuple, Optional
 
+import ctypes as C
+
 import numpy as np
 import torch
 
@@ -133,6 +135,16 @@ def preprocess_thermal_batch(raw_u16: torch.Tensor, img_size=(224, 224), path: s
         _lib.check(rc, "t3d_contrast_normalize_f32")
         return ThermalBatch(thermal, pct, None)
     raise ValueError("path must be 'train' or 'inference'")
+
+
+def bracket_fallback_count(workspace: torch.Tensor, B: int, img_size) -> int:
+    """Diagnostics: frames of the last preprocess_thermal_batch(..., histogram=False, out={'workspace': ws}) call
+    whose percentiles needed the exact per-frame select (same result, slower).  Synchronises."""
+    n = C.c_uint(0)
+    rc = _lib.lib().t3d_preprocess_fallback_count(_lib.ptr(workspace), int(B), int(img_size[1]), int(img_size[0]),
+                                                  C.byref(n), _lib.current_stream_ptr())
+    _lib.check(rc, "t3d_preprocess_fallback_count")
+    return int(n.value)
 
 
 # ----------------------------------------------------------------------------- reference signatures
