@@ -360,12 +360,17 @@ def run_b200(a):
         kern_avg_ms = kern_ms / max(kern_n, 1)
         achieved = kern_bytes / (kern_avg_ms * 1e-3) / 1e9 if kern_n else None
         step_bytes = sum(ab.values())
-        # DRAM bytes of one loss_march_kernel launch from the committed ncu capture (profiles/); only valid
-        # for the exact configuration it was taken on
+        # DRAM bytes of one launch of the dominant kernel from the committed ncu capture (profiles/traffic.json);
+        # only valid for the exact configuration it was taken on
         traffic, traffic_src = None, None
-        if (B, H, W, bool(a.multi_scale)) == (64, 384, 512, False):
-            traffic = 1064839936 + 373636096
-            traffic_src = "profiles/r01_loss_march_v2_metrics.csv (dram__bytes_read.sum + dram__bytes_write.sum, 1 launch)"
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(dominant)
+            c = tj["config"]
+            if (c["batch"], c["height"], c["width"], bool(c["multi_scale"])) == (B, H, W, bool(a.multi_scale)):
+                traffic = int(tj["dram_read_bytes"]) + int(tj["dram_write_bytes"])
+                traffic_src = tj["source"] + " (dram__bytes_read.sum + dram__bytes_write.sum, 1 launch)"
+        except Exception:
+            pass
         out = {
             "metric": METRIC, "value": world * B * a.steps / (ms_dev * 1e-3), "unit": UNIT, "n_gpus": world,
             "steps": a.steps, "warmup": max(a.warmup, 3), "ms_per_step": ms_dev / a.steps,
