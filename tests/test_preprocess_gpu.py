@@ -243,3 +243,21 @@ def test_bracket_windows_hold_on_typical_frames(cuda_device):
         assert pp.bracket_fallback_count(out2["workspace"], d.shape[0], size) == 0, size
         h = pp.preprocess_thermal_batch(d, size, path="train", histogram=True)
         assert torch.equal(b.percentiles, h.percentiles) and torch.equal(b.thermal, h.thermal)
+
+
+def test_ingest_to_model_input(cuda_device, tmp_path):
+    """SURVEY 8f row 3 end to end: PNG-16 files -> native decode into pinned memory -> H2D -> GPU preprocessing
+    == cv2.imread + cv2.resize + enhance_thermal_contrast per frame (data/dataset_loader.py:110,237-249)."""
+    cv2 = pytest.importorskip("cv2")
+    from thermal3d_vision_b200 import ingest
+    raw = ref_preprocess.make_raw_frames(4, seed=9)
+    paths = []
+    for i in range(4):
+        p = str(tmp_path / f"fl_ir_aligned_{i}.png")
+        assert cv2.imwrite(p, raw[i])
+        paths.append(p)
+    tb = ingest.load_thermal_batch(paths, img_size=(224, 224), device=cuda_device)
+    for i in range(4):
+        o, p2, p98, _ = ref_preprocess.train_path(cv2.imread(paths[i], cv2.IMREAD_ANYDEPTH), (224, 224))
+        assert (tb.thermal[i].cpu().numpy() == o).all()
+        assert tuple(tb.percentiles[i].tolist()) == (p2, p98)

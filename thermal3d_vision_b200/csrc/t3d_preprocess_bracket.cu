@@ -473,7 +473,7 @@ int t3d_launch_bracket_percentiles(const uint16_t* raw, int B, int sh, int sw, i
         // widest source span of a strip (+ alignment slack), from the resize ratio
         const double scale = (double)sw / (double)dw;
         int slot_px = (int)(kRzStrip * scale) + 24;
-        slot_px = min((slot_px + 7) & ~7, (sw + 7) & ~7);
+        slot_px = min((slot_px + 7) & ~7, ((sw + 7) & ~7) + 8);    // + 8: the pixel after the row's last one is read (weight 0)
         const int slot_bytes = slot_px * (int)sizeof(uint16_t);
         const size_t smem = (size_t)kRzWarps * kRing * slot_bytes;
         const bool dense = sh <= 2 * dh;
