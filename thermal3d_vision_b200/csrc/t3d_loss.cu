@@ -551,14 +551,34 @@ __global__ void __launch_bounds__(128) loss_finalize_kernel(const FinalizeArgs a
     __shared__ double tot[2][kNTerms];
     __shared__ bool is_last;
     const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
-    // 16 (view, term) sums; warp w takes combos w, w+4, ...; lanes stride the tiles; fixed tree.
-    for (int combo = wrp; combo < 2 * kNTerms; combo += 4) {
-        const int view = combo / kNTerms, term = combo - view * kNTerms;
-        const float* p = a.partials + ((size_t)(2 * b + view) * a.tiles) * kNTerms + term;
-        double s = 0.0;
-        for (int t = lane; t < a.tiles; t += 32) s += (double)p[(size_t)t * kNTerms];
-        s = warp_sum(s);
-        if (lane == 0) tot[view][term] = s;
+    // 16 (view, term) sums.  Thread t owns the tiles t, t + 128, ... of each view (two 128-bit loads per
+    // partial), then a fixed butterfly per warp and a fixed order over the 4 warps: deterministic.
+    __shared__ double wsum[4][2][kNTerms];
+    double acc[2][kNTerms];
+#pragma unroll
+    for (int v = 0; v < 2; ++v)
+#pragma unroll
+        for (int k = 0; k < kNTerms; ++k) acc[v][k] = 0.0;
+#pragma unroll
+    for (int view = 0; view < 2; ++view) {
+        const float4* p = reinterpret_cast<const float4*>(a.partials + ((size_t)(2 * b + view) * a.tiles) * kNTerms);
+        for (int t = tid; t < a.tiles; t += 128) {
+            const float4 lo = p[2 * t], hi = p[2 * t + 1];
+            acc[view][0] += (double)lo.x; acc[view][1] += (double)lo.y; acc[view][2] += (double)lo.z; acc[view][3] += (double)lo.w;
+            acc[view][4] += (double)hi.x; acc[view][5] += (double)hi.y; acc[view][6] += (double)hi.z; acc[view][7] += (double)hi.w;
+        }
+    }
+#pragma unroll
+    for (int v = 0; v < 2; ++v)
+#pragma unroll
+        for (int k = 0; k < kNTerms - 1; ++k) {          // term 7 is padding
+            const double r = warp_sum(acc[v][k]);
+            if (lane == 0) wsum[wrp][v][k] = r;
+        }
+    __syncthreads();
+    if (tid < 2 * kNTerms) {
+        const int v = tid / kNTerms, k = tid - v * kNTerms;
+        tot[v][k] = (k < kNTerms - 1) ? ((wsum[0][v][k] + wsum[1][v][k]) + (wsum[2][v][k] + wsum[3][v][k])) : 0.0;
     }
     __syncthreads();
     if (tid == 0) {

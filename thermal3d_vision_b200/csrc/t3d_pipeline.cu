@@ -11,7 +11,7 @@ namespace {
 __global__ void __launch_bounds__(128) pack_step_result_kernel(const float* __restrict__ loss_per_sample,
                                                                const double* __restrict__ metrics_f64, int B,
                                                                int n_images, double* __restrict__ out) {
-    __shared__ double red[128][14];
+    __shared__ double red[4][14];
     const int tid = threadIdx.x;
     double v[14];
 #pragma unroll
@@ -33,16 +33,16 @@ __global__ void __launch_bounds__(128) pack_step_result_kernel(const float* __re
             for (int k = 0; k < 7; ++k) if (isfinite(m[k])) v[7 + k] += m[k];
         }
     }
+    // fixed butterfly per warp, fixed order over the 4 warps: deterministic
+    const int lane = tid & 31, wrp = tid >> 5;
 #pragma unroll
-    for (int k = 0; k < 14; ++k) red[tid][k] = v[k];
-    __syncthreads();
-    for (int s = 64; s > 0; s >>= 1) {           // fixed-shape tree: deterministic
-        if (tid < s) {
-#pragma unroll
-            for (int k = 0; k < 14; ++k) red[tid][k] += red[tid + s][k];
-        }
-        __syncthreads();
+    for (int k = 0; k < 14; ++k) {
+        const double r = warp_sum(v[k]);
+        if (lane == 0) red[wrp][k] = r;
     }
+    __syncthreads();
+    if (tid < 14) red[0][tid] = (red[0][tid] + red[1][tid]) + (red[2][tid] + red[3][tid]);
+    __syncthreads();
     if (tid < 16) {
         double r;
         if (tid == 6) r = loss_per_sample ? (double)B : 0.0;
