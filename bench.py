@@ -380,7 +380,12 @@ def run_b200(a):
                          "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": (achieved / peak) if achieved else None, "traffic": traffic,
                          "traffic_source": traffic_src,
-                         "algorithmic_bytes_per_launch": kern_bytes, "avg_launch_ms": kern_avg_ms,
+                         "algorithmic_bytes_per_launch": kern_bytes,
+                         "algorithmic_bytes_note": "96 B per pixel-pair: 2x12 pred + 2x12 gt + 2x4 conf + 2x4 thermal read, "
+                                                   "2x12 dpred + 2x4 dconf written; the three thermal planes are replicas by "
+                                                   "construction, so one is read (SURVEY.md 8d: 96 B with 1-channel thermal, "
+                                                   "112 B when all three planes are read)",
+                         "avg_launch_ms": kern_avg_ms,
                          "launches_timed": kern_n, "peak_source": peak_src,
                          "step_algorithmic_bytes": step_bytes,
                          "step_frac_of_peak": step_bytes / (ms_dev / a.steps * 1e-3) / 1e9 / peak},
