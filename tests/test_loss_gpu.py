@@ -285,8 +285,9 @@ def test_nan_thermal_poisons_only_that_sample(cuda_device):
         assert res.loss.item() == pytest.approx(mean.item(), rel=1e-5)
 
 
+@pytest.mark.parametrize("multi", [False, True])
 @pytest.mark.parametrize("H,W", [(48, 256), (33, 132)])
-def test_replicated_thermal_planes_read_once(cuda_device, H, W):
+def test_replicated_thermal_planes_read_once(cuda_device, H, W, multi):
     """T3D_THERMAL_REPLICATED: reading plane 0 only and evaluating gray3(v, v, v) is bit-identical to reading the
     three replicated planes enhance_thermal_contrast returns (utils/preprocessing.py:22-28)."""
     from thermal3d_vision_b200 import loss as t3d
@@ -295,9 +296,32 @@ def test_replicated_thermal_planes_read_once(cuda_device, H, W):
     T1 = T1[:, :1].repeat(1, 3, 1, 1).contiguous()
     T2 = T2[:, :1].repeat(1, 3, 1, 1).contiguous()
     d = [x.to(cuda_device) for x in (P1, P2, G1, G2, C1, C2, T1, T2)]
-    a = t3d.fused_thermal_loss_fwd_bwd(*d, multi_scale=False, **KW)
-    b = t3d.fused_thermal_loss_fwd_bwd(*d, multi_scale=False, thermal_replicated=True, **KW)
+    a = t3d.fused_thermal_loss_fwd_bwd(*d, multi_scale=multi, **KW)
+    b = t3d.fused_thermal_loss_fwd_bwd(*d, multi_scale=multi, thermal_replicated=True, **KW)
     for k in ("per_sample", "batch", "dpred1", "dpred2", "dconf1", "dconf2"):
         assert torch.equal(a[k], b[k]), k
-    mean, rows, _ = ref_loss.batched_loss_torch(P1, P2, G1, G2, C1, C2, T1, T2, multi_scale=False, **KW)
+    mean, rows, _ = ref_loss.batched_loss_torch(P1, P2, G1, G2, C1, C2, T1, T2, multi_scale=multi, **KW)
     np.testing.assert_allclose(b["per_sample"][:, :5].cpu().numpy(), rows, rtol=1e-5)
+
+
+@pytest.mark.parametrize("H,W", [(130, 516), (65, 132), (4, 8), (38, 52), (224, 224)])
+def test_multi_scale_split_path_edge_shapes(cuda_device, H, W):
+    """multi_scale=True on vector-aligned shapes runs the half-resolution pass (t3d_loss_scale2.cu) + the marching
+    kernel: odd heights (last row outside every pooled cell), partial pooled tiles, batch > 1, gradients included."""
+    from thermal3d_vision_b200 import loss as t3d
+    B = 2
+    P1, P2, G1, G2, C1, C2, T1, T2 = ref_loss.make_batch_inputs(B, H, W, seed=3 * H + W, stress_conf=True)
+    Pa, Pb, Ca, Cb = (x.clone().requires_grad_() for x in (P1, P2, C1, C2))
+    mean, rows, valid = ref_loss.batched_loss_torch(Pa, Pb, G1, G2, Ca, Cb, T1, T2, multi_scale=True, **KW)
+    mean.backward()
+    d = [x.to(cuda_device) for x in (P1, P2, G1, G2, C1, C2, T1, T2)]
+    for k in (0, 1, 4, 5):
+        d[k].requires_grad_()
+    res = t3d.fused_thermal_loss(*d, multi_scale=True, **KW)
+    res.loss.backward()
+    np.testing.assert_allclose(res.per_sample[:, :5].cpu().numpy(), rows, rtol=1e-5)
+    for got, ref in ((d[0].grad, Pa.grad), (d[1].grad, Pb.grad), (d[4].grad, Ca.grad), (d[5].grad, Cb.grad)):
+        torch.testing.assert_close(got.cpu(), ref, rtol=1e-4, atol=1e-6)
+    # forward-only entry (no gradient buffers) gives the same numbers
+    f = t3d.fused_thermal_loss(*(x.detach() for x in d), multi_scale=True, **KW)
+    assert torch.equal(f.per_sample[:, :5], res.per_sample[:, :5])

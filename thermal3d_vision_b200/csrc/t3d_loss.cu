@@ -31,7 +31,9 @@ struct StatsArgs {
     const float* thermal[2];
     float* partials;  // [B*2][stiles][4]  (sum tx1, ty1, tx2, ty2)
     int B, H, W, tch, tiles_x, tiles_y;
+    int replicated;   // tch == 3 and the planes are bit-identical: read plane 0, gray = gray3(v, v, v)
 };
+constexpr int kTchReplicated = 13;   // `tch` value of the gray loaders for that case
 
 template <bool VEC>
 __device__ __forceinline__ void load_gray_quad(const float* __restrict__ t, int tch, size_t plane,
@@ -39,7 +41,10 @@ __device__ __forceinline__ void load_gray_quad(const float* __restrict__ t, int 
     // idx: offset of the first pixel inside channel 0 of this image; plane = H*W
     if (VEC) {
         float4 c0 = ldg_stream_f4(t + idx);
-        if (tch == 3) {
+        if (tch == kTchReplicated) {
+            g[0] = gray3(c0.x, c0.x, c0.x); g[1] = gray3(c0.y, c0.y, c0.y);
+            g[2] = gray3(c0.z, c0.z, c0.z); g[3] = gray3(c0.w, c0.w, c0.w);
+        } else if (tch == 3) {
             float4 c1 = ldg_stream_f4(t + plane + idx);
             float4 c2 = ldg_stream_f4(t + 2 * plane + idx);
             g[0] = gray3(c0.x, c1.x, c2.x); g[1] = gray3(c0.y, c1.y, c2.y);
@@ -53,7 +58,8 @@ __device__ __forceinline__ void load_gray_quad(const float* __restrict__ t, int 
             g[e] = 0.f;
             if (e < nvalid) {
                 float c0 = ldg_stream_f1(t + idx + e);
-                g[e] = (tch == 3) ? gray3(c0, ldg_stream_f1(t + plane + idx + e),
+                g[e] = (tch == kTchReplicated) ? gray3(c0, c0, c0) :
+                       (tch == 3) ? gray3(c0, ldg_stream_f1(t + plane + idx + e),
                                           ldg_stream_f1(t + 2 * plane + idx + e)) : c0;
             }
         }
@@ -62,6 +68,7 @@ __device__ __forceinline__ void load_gray_quad(const float* __restrict__ t, int 
 
 __device__ __forceinline__ float load_gray_px(const float* __restrict__ t, int tch, size_t plane, size_t idx) {
     float c0 = ldg_f1(t + idx);
+    if (tch == kTchReplicated) return gray3(c0, c0, c0);
     return (tch == 3) ? gray3(c0, ldg_f1(t + plane + idx), ldg_f1(t + 2 * plane + idx)) : c0;
 }
 
@@ -80,6 +87,7 @@ __global__ void __launch_bounds__(kSThreads, 4) thermal_stats_kernel(const Stats
     const int H = a.H, W = a.W;
     const size_t plane = (size_t)H * W;
     const float* __restrict__ t = a.thermal[view] + (size_t)b * a.tch * plane;
+    const int ltch = a.replicated ? kTchReplicated : a.tch;
     constexpr int HALO = MULTI ? 2 : 1;
 
     // main quads
@@ -88,7 +96,7 @@ __global__ void __launch_bounds__(kSThreads, 4) thermal_stats_kernel(const Stats
         const int r = q / QPR, cq = q - r * QPR;
         const int i = i0 + r, j = j0 + 4 * cq;
         float g[4] = {0.f, 0.f, 0.f, 0.f};
-        if (i < H && j < W) load_gray_quad<VEC>(t, a.tch, plane, (size_t)i * W + j, min(4, W - j), g);
+        if (i < H && j < W) load_gray_quad<VEC>(t, ltch, plane, (size_t)i * W + j, min(4, W - j), g);
         *reinterpret_cast<float4*>(&sg[r][4 * cq]) = make_float4(g[0], g[1], g[2], g[3]);
     }
     // halo: HALO rows below, HALO cols to the right
@@ -98,7 +106,7 @@ __global__ void __launch_bounds__(kSThreads, 4) thermal_stats_kernel(const Stats
         if (h < NB) { r = kSTH + h / (kSTW + HALO); c = h % (kSTW + HALO); }
         else        { int k = h - NB; r = k / HALO; c = kSTW + k % HALO; }
         const int i = i0 + r, j = j0 + c;
-        sg[r][c] = (i < H && j < W) ? load_gray_px(t, a.tch, plane, (size_t)i * W + j) : 0.f;
+        sg[r][c] = (i < H && j < W) ? load_gray_px(t, ltch, plane, (size_t)i * W + j) : 0.f;
     }
     __syncthreads();
 
@@ -540,6 +548,8 @@ __global__ void __launch_bounds__(kThreads, MULTI ? 2 : 3) loss_tile_kernel(cons
 
 // ------------------------------------------------------------------ second stage
 struct FinalizeArgs {
+    const float* partials2;  // multi-scale split path: [B*2][tiles2][4] = E2, S2, D2, 0 (else NULL)
+    int tiles2;
     const float* partials;   // [B*2][tiles][kNTerms]
     float* out_sample; float* out_batch; double* out_f64;
     unsigned int* counter;
@@ -579,6 +589,14 @@ __global__ void __launch_bounds__(128) loss_finalize_kernel(const FinalizeArgs a
     if (tid < 2 * kNTerms) {
         const int v = tid / kNTerms, k = tid - v * kNTerms;
         tot[v][k] = (k < kNTerms - 1) ? ((wsum[0][v][k] + wsum[1][v][k]) + (wsum[2][v][k] + wsum[3][v][k])) : 0.0;
+    }
+    __syncthreads();
+    if (a.partials2 && tid < 6) {      // scale-2 sums of the split multi-scale path: fixed order over its tiles
+        const int v = tid / 3, k = tid - v * 3;
+        const float* p2 = a.partials2 + ((size_t)(2 * b + v) * a.tiles2) * 4 + k;
+        double s2 = 0.0;
+        for (int t = 0; t < a.tiles2; ++t) s2 += (double)p2[(size_t)t * 4];
+        tot[v][4 + k] = s2;
     }
     __syncthreads();
     if (tid == 0) {
@@ -754,10 +772,11 @@ __global__ void __launch_bounds__(256) loss_v1_kernel(const V1Args a) {
 // ------------------------------------------------------------------ host helpers
 struct WsLayout {
     size_t stats_partials, loss_partials, counter, total;
-    int stiles_x, stiles_y, tiles_x, tiles_y;
+    size_t s2_partials, s2_dzp;        // multi-scale only (appended: the other offsets do not depend on `multi`)
+    int stiles_x, stiles_y, tiles_x, tiles_y, s2_tiles_x, s2_tiles_y;
 };
 
-WsLayout ws_layout(int B, int H, int W) {
+WsLayout ws_layout(int B, int H, int W, int multi = 0) {
     WsLayout L;
     L.stiles_x = (W + kSTW - 1) / kSTW; L.stiles_y = (H + kSTH - 1) / kSTH;
     L.tiles_x = (W + kTW - 1) / kTW;    L.tiles_y = (H + kTH - 1) / kTH;
@@ -766,6 +785,12 @@ WsLayout ws_layout(int B, int H, int W) {
     L.stats_partials = off; off += t3d_align_up((size_t)B * 2 * L.stiles_x * L.stiles_y * 4 * sizeof(float), 256);
     // sized for the tile kernel (16-row tiles) and the marching kernel (>= 8-row bands)
     L.loss_partials = off;  off += t3d_align_up((size_t)B * 2 * L.tiles_x * ((H + 7) / 8) * kNTerms * sizeof(float), 256);
+    t3d_scale2_tiles(H, W, &L.s2_tiles_x, &L.s2_tiles_y);
+    L.s2_partials = L.s2_dzp = off;
+    if (multi) {
+        L.s2_partials = off; off += t3d_align_up((size_t)B * 2 * L.s2_tiles_x * L.s2_tiles_y * 4 * sizeof(float), 256);
+        L.s2_dzp = off;      off += t3d_align_up((size_t)B * 2 * (H >> 1) * (W >> 1) * sizeof(float), 256);
+    }
     L.total = off;
     return L;
 }
@@ -784,8 +809,9 @@ int launch_stats(const StatsArgs& sa, cudaStream_t st) {
 }
 
 int run_stats(const float* t1, const float* t2, int tch, int B, int H, int W, int multi,
-              float* partials, const WsLayout& L, cudaStream_t st) {
+              float* partials, const WsLayout& L, cudaStream_t st, int replicated = 0) {
     StatsArgs sa;
+    sa.replicated = (replicated && tch == 3) ? 1 : 0;
     sa.thermal[0] = t1; sa.thermal[1] = t2; sa.partials = partials;
     sa.B = B; sa.H = H; sa.W = W; sa.tch = tch; sa.tiles_x = L.stiles_x; sa.tiles_y = L.stiles_y;
     const bool vec = (W % 4 == 0) && t3d_aligned16(t1) && t3d_aligned16(t2);
@@ -821,7 +847,7 @@ int loss_impl(bool bwd, const float* pred1, const float* pred2, const float* gt1
     if (replicated) tch = 3;
     if (thermal_on) T3D_REQUIRE(tch == 1 || tch == 3, "thermal_channels must be 1, 3 or 3 | T3D_THERMAL_REPLICATED, got %d", tch);
     if (bwd) T3D_REQUIRE(dpred1 && dpred2, "dpred pointers must not be NULL");
-    const WsLayout L = ws_layout(B, H, W);
+    const WsLayout L = ws_layout(B, H, W, multi);
     if (ws_bytes < L.total) {
         t3d_set_error("workspace too small: %zu < %zu", ws_bytes, L.total);
         return T3D_ERR_WORKSPACE;
@@ -840,7 +866,7 @@ int loss_impl(bool bwd, const float* pred1, const float* pred2, const float* gt1
     int stiles = L.stiles_x * L.stiles_y;
     if (user_stats) { stats_v[0] = ustats1; stats_v[1] = ustats2; stiles = ustats_tiles; }
     else if (thermal_on) {
-        if (int rc = run_stats(thermal1, thermal2, tch, B, H, W, multi, stats_partials, L, st)) return rc;
+        if (int rc = run_stats(thermal1, thermal2, tch, B, H, W, multi, stats_partials, L, st, replicated)) return rc;
     }
 
     LossArgs la;
@@ -873,12 +899,30 @@ int loss_impl(bool bwd, const float* pred1, const float* pred2, const float* gt1
         const int v = e ? atoi(e) : 16;
         return (v == 0) ? 0 : (v < 8 ? 8 : v);
     }();
-    if (vec && thermal_on && !ms && march_rows > 0) {
-        // fast path: TMA-fed warp-marching kernel (t3d_loss_march.cu)
+    const float* partials2 = nullptr;
+    int tiles2 = 0;
+    if (vec && thermal_on && march_rows > 0 && (!ms || (H >= 4 && W >= 4))) {
+        // fast path: TMA-fed warp-marching kernel (t3d_loss_march.cu); multi-scale: the half-resolution terms run
+        // first as their own pass (t3d_loss_scale2.cu) and hand their gradient to the marching kernel
         MarchArgs ma;
         for (int v = 0; v < 2; ++v) {
             ma.pred[v] = la.pred[v]; ma.gt[v] = la.gt[v]; ma.conf[v] = la.conf[v]; ma.thermal[v] = la.thermal[v];
-            ma.dpred[v] = la.dpred[v]; ma.dconf[v] = la.dconf[v];
+            ma.dpred[v] = la.dpred[v]; ma.dconf[v] = la.dconf[v]; ma.dzp[v] = nullptr;
+        }
+        if (ms) {
+            Scale2Args sa;
+            float* dzp = reinterpret_cast<float*>(ws + L.s2_dzp);
+            for (int v = 0; v < 2; ++v) {
+                sa.pred[v] = la.pred[v]; sa.gt[v] = la.gt[v]; sa.thermal[v] = la.thermal[v]; sa.stats[v] = stats_v[v];
+                sa.dzp[v] = dzp + (size_t)v * B * (H >> 1) * (W >> 1);
+                if (bwd) ma.dzp[v] = sa.dzp[v];
+            }
+            sa.partials = reinterpret_cast<float*>(ws + L.s2_partials);
+            sa.B = B; sa.H = H; sa.W = W; sa.tch = tch; sa.replicated = replicated; sa.stiles = stiles;
+            sa.tiles_x = L.s2_tiles_x; sa.tiles_y = L.s2_tiles_y;
+            sa.kE = la.kE[1]; sa.kS = la.kS[1]; sa.kD = la.kD[1];
+            if (int rc2 = t3d_launch_loss_scale2(sa, bwd, st)) return rc2;
+            partials2 = sa.partials; tiles2 = sa.tiles_x * sa.tiles_y;
         }
         ma.stats[0] = stats_v[0]; ma.stats[1] = stats_v[1]; ma.partials = loss_partials; ma.queue = counter + 1;
         ma.B = B; ma.H = H; ma.W = W; ma.tch = tch; ma.stiles = la.stiles; ma.replicated = replicated;
@@ -897,6 +941,7 @@ int loss_impl(bool bwd, const float* pred1, const float* pred2, const float* gt1
 
     FinalizeArgs fa;
     fa.partials = loss_partials; fa.out_sample = out_sample; fa.out_batch = out_batch; fa.out_f64 = out_f64;
+    fa.partials2 = partials2; fa.tiles2 = tiles2;
     fa.counter = counter; fa.B = B; fa.H = H; fa.W = W; fa.tiles = n_partials;
     fa.multi = ms ? 1 : 0; fa.thermal_on = thermal_on ? 1 : 0; fa.ew = ew; fa.sw = sw; fa.dw = dw;
     T3D_LAUNCH("loss_finalize_kernel", st, loss_finalize_kernel<<<B, 128, 0, st>>>(fa));
@@ -908,9 +953,9 @@ int loss_impl(bool bwd, const float* pred1, const float* pred2, const float* gt1
 // ====================================================================== C ABI
 extern "C" {
 
-size_t t3d_loss_workspace_bytes(int B, int H, int W, int /*multi_scale*/) {
+size_t t3d_loss_workspace_bytes(int B, int H, int W, int multi_scale) {
     if (B < 1 || H < 1 || W < 1) return 0;
-    return ws_layout(B, H, W).total;
+    return ws_layout(B, H, W, multi_scale).total;
 }
 
 int t3d_thermal_grad_stats(const float* thermal1, const float* thermal2, int thermal_channels,
@@ -1021,6 +1066,7 @@ int t3d_loss_v1_fwd_bwd(const float* pred1, const float* pred2, const float* gt1
     else T3D_LAUNCH("loss_v1_kernel", st, loss_v1_kernel<false><<<grid, 256, 0, st>>>(a));
     FinalizeArgs fa;
     fa.partials = partials; fa.out_sample = out_sample; fa.out_batch = out_batch; fa.out_f64 = out_sample_f64;
+    fa.partials2 = nullptr; fa.tiles2 = 0;
     fa.counter = counter; fa.B = B; fa.H = H; fa.W = W; fa.tiles = blocks;
     fa.multi = 0; fa.thermal_on = thermal_on ? 1 : 0; fa.ew = edge_weight; fa.sw = smoothness_weight; fa.dw = 0.f;
     T3D_LAUNCH("loss_finalize_kernel", st, loss_finalize_kernel<<<B, 128, 0, st>>>(fa));

@@ -13,7 +13,20 @@ struct MarchArgs {
     int replicated;                // tch == 3 and the planes of every image are bit-identical: read plane 0 only
     int rows_per_band, nbands, nstrips;
     float alpha, kb, kc, kE, kS, kD;
+    const float* dzp[2];           // multi-scale: per view [B][H/2][W/2], added to d/d(pred z) of each cell's 4 pixels (or NULL)
 };
+
+// half-resolution (scale 2) terms of the multi-scale loss as their own pass (t3d_loss_scale2.cu)
+struct Scale2Args {
+    const float* pred[2]; const float* gt[2]; const float* thermal[2];
+    const float* stats[2];         // per view: [B][stiles][4], scale-2 sums in [2], [3]
+    float* dzp[2];                 // out, per view [B][H/2][W/2] (backward only)
+    float* partials;               // out [B*2][tiles_x*tiles_y][4]: E2, S2, D2, 0
+    int B, H, W, tch, replicated, stiles, tiles_x, tiles_y;
+    float kE, kS, kD;              // grad_scale * 0.35 * weight / (H/2 * W/2)
+};
+void t3d_scale2_tiles(int H, int W, int* tiles_x, int* tiles_y);
+int t3d_launch_loss_scale2(const Scale2Args& a, bool bwd, cudaStream_t st);
 
 // requires: W % 4 == 0, all pointers 16-byte aligned, tch in {1, 3}, single scale
 int t3d_launch_loss_march(const MarchArgs& a, bool bwd, cudaStream_t st);

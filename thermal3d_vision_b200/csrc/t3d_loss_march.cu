@@ -140,7 +140,8 @@ __device__ __forceinline__ void load_row(const float* __restrict__ st, int idx, 
 }
 
 // ------------------------------------------------------------------ kernel
-template <int TCH, bool REP, bool BWD, int NS, int WARPS>
+// S2: multi-scale -- the scale-2 pass (t3d_loss_scale2.cu) left 0.25 * d(loss)/d(pooled z) per 2x2 cell in a.dzp
+template <int TCH, bool REP, bool BWD, bool S2, int NS, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32, 1) loss_march_kernel(const MarchArgs a) {
     static_assert(!REP || TCH == 1, "replicated planes: one plane is staged");
     using St = Stage<TCH>;
@@ -194,6 +195,9 @@ __global__ void __launch_bounds__(WARPS * 32, 1) loss_march_kernel(const MarchAr
         // running output pointers of this lane's quad (row i_lo; advanced by one row per iteration)
         float* dp_ptr = BWD ? a.dpred[view] + ((size_t)b * plane + (size_t)i_lo * W + j) * 3 : nullptr;
         float* dc_ptr = (BWD && a.dconf[view]) ? a.dconf[view] + (size_t)b * plane + (size_t)i_lo * W + j : nullptr;
+        // multi-scale: this lane's two pooled cells per row pair (W % 4 == 0: columns j .. j+3 are always inside 2 * (W / 2))
+        const int w2 = W >> 1, rows2 = 2 * (H >> 1);
+        const float* dz2_ptr = (S2 && BWD) ? a.dzp[view] + (size_t)b * (H >> 1) * w2 + (j >> 1) : nullptr;
 
         // 1 / (mean + eps) of |Dx gray|, |Dy gray| of this image: fixed-order sum of the stats partials
         float inv_mx, inv_my;
@@ -308,6 +312,9 @@ __global__ void __launch_bounds__(WARPS * 32, 1) loss_march_kernel(const MarchAr
                 const float dzs[4] = {-qx[0] + qxl - qy[0] + qy_prev[0], -qx[1] + qx[0] - qy[1] + qy_prev[1],
                                       -qx[2] + qx[1] - qy[2] + qy_prev[2], -qx[3] + qx[2] - qy[3] + qy_prev[3]};
                 float gq[12], dc[4];
+                float2 d2 = make_float2(0.f, 0.f);
+                if (S2 && BWD && active && r < rows2) d2 = __ldg(reinterpret_cast<const float2*>(dz2_ptr + (size_t)(r >> 1) * w2));
+                const float dz2[4] = {d2.x, d2.x, d2.y, d2.y};
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
                     const float dx = cur.P[3 * e] - cur.G[3 * e], dy = cur.P[3 * e + 1] - cur.G[3 * e + 1],
@@ -320,7 +327,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) loss_march_kernel(const MarchAr
                         const float k3 = cc * kb;
                         gq[3 * e] = times_sgn(k3, dx);
                         gq[3 * e + 1] = times_sgn(k3, dy);
-                        gq[3 * e + 2] = times_sgn(k3, dz) + dzs[e];
+                        gq[3 * e + 2] = times_sgn(k3, dz) + dzs[e] + (S2 ? dz2[e] : 0.f);
                         const bool inside = (craw >= kConfMin) && (craw <= kConfMax);
                         dc[e] = inside ? (l - __fdividef(alpha, cc)) * kc : 0.f;
                     }
@@ -363,7 +370,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) loss_march_kernel(const MarchAr
     }
 }
 
-template <int TCH, bool REP, bool BWD>
+template <int TCH, bool REP, bool BWD, bool S2>
 int launch(const MarchArgs& a, cudaStream_t st) {
     constexpr int NS = 4;
     constexpr int WARPS = (TCH == 3) ? 10 : 12;
@@ -371,20 +378,26 @@ int launch(const MarchArgs& a, cudaStream_t st) {
     static_assert(smem <= 227 * 1024, "ring does not fit in shared memory");
     static bool attr_set = false;
     if (!attr_set) {
-        T3D_CUDA(cudaFuncSetAttribute(loss_march_kernel<TCH, REP, BWD, NS, WARPS>,
+        T3D_CUDA(cudaFuncSetAttribute(loss_march_kernel<TCH, REP, BWD, S2, NS, WARPS>,
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set = true;
     }
     const int grid = t3d_sm_count();
     T3D_LAUNCH("loss_march_kernel", st,
-               loss_march_kernel<TCH, REP, BWD, NS, WARPS><<<grid, WARPS * 32, smem, st>>>(a));
+               loss_march_kernel<TCH, REP, BWD, S2, NS, WARPS><<<grid, WARPS * 32, smem, st>>>(a));
     return T3D_OK;
 }
 
 }  // namespace
 
 int t3d_launch_loss_march(const MarchArgs& a, bool bwd, cudaStream_t st) {
-    if (a.tch == 3 && a.replicated) return bwd ? launch<1, true, true>(a, st) : launch<1, true, false>(a, st);
-    if (a.tch == 3) return bwd ? launch<3, false, true>(a, st) : launch<3, false, false>(a, st);
-    return bwd ? launch<1, false, true>(a, st) : launch<1, false, false>(a, st);
+    const bool s2 = bwd && a.dzp[0] != nullptr && a.dzp[1] != nullptr;
+    if (s2) {       // multi-scale backward: add the scale-2 gradient
+        if (a.tch == 3 && a.replicated) return launch<1, true, true, true>(a, st);
+        if (a.tch == 3) return launch<3, false, true, true>(a, st);
+        return launch<1, false, true, true>(a, st);
+    }
+    if (a.tch == 3 && a.replicated) return bwd ? launch<1, true, true, false>(a, st) : launch<1, true, false, false>(a, st);
+    if (a.tch == 3) return bwd ? launch<3, false, true, false>(a, st) : launch<3, false, false, false>(a, st);
+    return bwd ? launch<1, false, true, false>(a, st) : launch<1, false, false, false>(a, st);
 }

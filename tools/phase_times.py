@@ -45,4 +45,5 @@ t0 = time.perf_counter()
 for _ in range(20): step.run_device(*args)
 res["host_enqueue_us_per_step"] = (time.perf_counter() - t0) / 20 * 1e6
 torch.cuda.synchronize()
+res["loss_multiscale_replicated"] = timeit(lambda: tl.fused_thermal_loss_fwd_bwd(d["pred1"], d["pred2"], d["gt1"], d["gt2"], d["conf1"], d["conf2"], tb1.thermal, tb2.thermal, out=step.loss_out, thermal_replicated=True, **kwm))
 print(json.dumps(res, indent=1))
