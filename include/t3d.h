@@ -208,11 +208,14 @@ int t3d_preprocess_fallback_count(const void* workspace, int B, int dst_h, int d
  * [B,channels,n].  channels == 3: if np.allclose(c0,c1) and np.allclose(c0,c2)
  * the plane is c0, else the fp32 gray 0.299 c0 + 0.587 c1 + 0.114 c2 (:13-19;
  * close_flags[B] int32 receives the decision); any other channel count: the
- * whole array is one plane of channels*n values.  Percentiles by exact radix
- * select on the float keys; out [B,out_channels,plane] float32;
- * percentiles [B,2] float64. */
+ * whole array is one plane of channels*n values.  Percentiles are exact (sampled
+ * brackets + candidate select on the monotone float keys, full radix select as
+ * the fallback); out [B,out_channels,plane] float32; percentiles [B,2] float64.
+ * workspace: t3d_contrast_normalize_workspace_bytes(B) bytes, 16-byte aligned. */
+size_t t3d_contrast_normalize_workspace_bytes(int B);
 int t3d_contrast_normalize_f32(const float* x, int B, int channels, int n, float* out, int out_channels,
-                               double* percentiles, int* close_flags, void* stream);
+                               double* percentiles, int* close_flags, void* workspace, size_t workspace_bytes,
+                               void* stream);
 
 /* close_flags[b] = np.allclose(c0, c1) and np.allclose(c0, c2) for x [B,3,n]
  * (rtol 1e-5, atol 1e-8, float32; utils/preprocessing.py:15,40). */

@@ -261,3 +261,35 @@ def test_ingest_to_model_input(cuda_device, tmp_path):
         o, p2, p98, _ = ref_preprocess.train_path(cv2.imread(paths[i], cv2.IMREAD_ANYDEPTH), (224, 224))
         assert (tb.thermal[i].cpu().numpy() == o).all()
         assert tuple(tb.percentiles[i].tolist()) == (p2, p98)
+
+
+def test_float_percentiles_bracket_and_fallback_paths(cuda_device):
+    """enhance_thermal_contrast on float data at sizes where the sampled brackets are used, including inputs that
+    overflow the candidate buffers (two-valued, constant, heavy duplicates) and take the exact fallback; a real
+    3-channel (non-replicated) image goes through the fp32 gray plane.  Bit-exact vs numpy (oracle)."""
+    from thermal3d_vision_b200 import preprocessing as pp
+    rng = np.random.default_rng(21)
+    H, W = 192, 256
+    base = rng.random((H, W)).astype(np.float32)
+    cases = {
+        "uniform": np.repeat(base[None], 3, 0),
+        "gray3": rng.random((3, H, W)).astype(np.float32),
+        "quantised": np.repeat((rng.integers(21800, 25000, (H, W)) / 65535.0).astype(np.float32)[None], 3, 0),
+        "two_valued": np.repeat(np.where(base < 0.5, 0.25, 0.75).astype(np.float32)[None], 3, 0),
+        "constant": np.full((3, H, W), 0.5, np.float32),
+        "heavy_dups": np.repeat(np.where(base < 0.9, 0.1, base).astype(np.float32)[None], 3, 0),
+        "negative_and_large": np.repeat(((base - 0.5) * 1e6).astype(np.float32)[None], 3, 0),
+        "one_channel_2d": base,
+    }
+    for name, x in cases.items():
+        ref, p2, p98 = ref_preprocess.enhance_thermal_contrast(x)
+        got = pp.enhance_thermal_contrast(torch.from_numpy(x).to(cuda_device)).cpu().numpy()
+        assert got.shape == ref.shape, name
+        assert np.array_equal(got, ref, equal_nan=True), name
+    # batched inference path (u16 -> /65535 -> float resize -> float percentiles) vs the oracle
+    raw = ref_preprocess.make_raw_frames(3, seed=5)
+    tb = pp.preprocess_thermal_batch(torch.from_numpy(raw).to(cuda_device), (512, 384), path="inference")
+    for i in range(3):
+        o = ref_preprocess.inference_path(raw[i], (384, 512))
+        o = o[0] if isinstance(o, tuple) else o
+        assert np.array_equal(tb.thermal[i].cpu().numpy(), o)

@@ -49,8 +49,9 @@ _SIGNATURES = {
                                                                     c_ptr, C.c_size_t, c_ptr]),
     "t3d_preprocess_stats_tiles": (C.c_int, [C.c_int, C.c_int]),
     "t3d_preprocess_fallback_count": (C.c_int, [c_ptr, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_uint), c_ptr]),
+    "t3d_contrast_normalize_workspace_bytes": (C.c_size_t, [C.c_int]),
     "t3d_contrast_normalize_f32": (C.c_int, [c_ptr, C.c_int, C.c_int, C.c_int, c_ptr, C.c_int,
-                                             c_ptr, c_ptr, c_ptr]),
+                                             c_ptr, c_ptr, c_ptr, C.c_size_t, c_ptr]),
     "t3d_channels_close": (C.c_int, [c_ptr, C.c_int, C.c_int, c_ptr, c_ptr]),
     "t3d_fixed_range_normalize": (C.c_int, [c_ptr, c_ptr, C.c_size_t, C.c_size_t, c_ptr, C.c_int, c_ptr]),
     "t3d_depth_metrics_workspace_bytes": (C.c_size_t, [C.c_int] * 3),

@@ -320,40 +320,172 @@ __device__ __forceinline__ float plane_value(const float* __restrict__ img, int 
     return gray3(__ldg(img + i), __ldg(img + n + i), __ldg(img + 2 * (size_t)n + i));
 }
 
-// ------------------------------------------------------------------ K2c: percentiles of arbitrary float data (radix select)
-// one CTA per image; out_p[b] = {p2, p98} as np.percentile(plane, (2, 98)) would return (fp64).
+// ------------------------------------------------------------------ K2c: percentiles of arbitrary float data
+// np.percentile(plane, (2, 98)) (utils/preprocessing.py:22) on float data, exact, in three small kernels -- the same
+// scheme as the medians of t3d_metrics.cu:
+//   F1 sample 4096 values (1024 jittered-stride quads), bracket each quantile's rank by two sample order statistics
+//      9 sigma apart (monotone uint32 keys);
+//   F2 one pass over the plane: count NaNs and the values below each bracket, collect the few percent inside;
+//   F3 one CTA per image selects the exact order statistics among the candidates (radix select in shared memory) and
+//      applies numpy's fp64 two-sided lerp.  If a bracket misses, or candidates overflow, that image falls back to a
+//      full 3-pass radix select per rank over the plane: slower, same bits.
+constexpr int kFSamp = 4096;
+constexpr int kFCandCap = 32768;     // candidates per (image, window)
+constexpr int kFCtaCand = 2048;      // staged per CTA per window
+constexpr int kFThreads = 256;
+constexpr int kFChunks = 24;
+
+struct FpctWs {
+    unsigned int* bracket;   // [B][4]  lo2, hi2, lo98, hi98 (keys, inclusive; lo > hi: no bracket)
+    int* counters;           // [B][8]  n_nan, below2, below98, ncand2, ncand98, overflow, -, -
+    unsigned int* cand;      // [B][2][kFCandCap]
+    size_t total;
+};
+FpctWs fpct_ws(void* base, int B) {
+    FpctWs w; size_t off = 0; char* p = reinterpret_cast<char*>(base);
+    auto take = [&](size_t bytes) { char* r = p ? p + off : nullptr; off += t3d_align_up(bytes, 256); return r; };
+    w.bracket = reinterpret_cast<unsigned int*>(take((size_t)B * 4 * sizeof(unsigned int)));
+    w.counters = reinterpret_cast<int*>(take((size_t)B * 8 * sizeof(int)));
+    w.cand = reinterpret_cast<unsigned int*>(take((size_t)B * 2 * kFCandCap * sizeof(unsigned int)));
+    w.total = off;
+    return w;
+}
+
 __global__ void __launch_bounds__(t3d_select::kThreads, 1)
-percentile_select_kernel(const float* __restrict__ x, int n, int channels, const int* __restrict__ close_flag,
-                         double* __restrict__ out_p) {
+fpct_sample_kernel(const float* __restrict__ x, int n, int channels, const int* __restrict__ close_flag,
+                   unsigned int* __restrict__ bracket) {
+    __shared__ float key[kFSamp];
     __shared__ t3d_select::Smem sm;
-    __shared__ int s_nan;
-    const int b = blockIdx.x;
+    __shared__ int s_valid;
+    const int b = blockIdx.x, tid = threadIdx.x;
+    const float* img = x + (size_t)b * channels * n;
+    const int collapse = (channels == 3) ? close_flag[b] : 0;
+    const int count = (channels == 3) ? n : n * channels;
+    const int m = min(count, kFSamp);
+    if (tid == 0) s_valid = 0;
+    __syncthreads();
+    int nv = 0;
+#pragma unroll
+    for (int q = 0; q < kFSamp / t3d_select::kThreads; ++q) {
+        const int k = q * t3d_select::kThreads + tid;
+        float v = __int_as_float(0x7fc00000);                 // NaN = not part of the sample
+        if (k < m) {
+            int i = k;
+            if (count > kFSamp) {
+                const int l = k >> 2, qstride = (count >> 2) / (kFSamp >> 2);
+                i = 4 * (l * qstride + (int)((((unsigned)l * 2654435761u) >> 8) % (unsigned)qstride)) + (k & 3);
+            }
+            v = plane_value(img, n, channels, collapse, i);
+        }
+        key[k] = v;
+        nv += !isnan(v);
+    }
+    nv = __reduce_add_sync(0xffffffffu, nv);
+    if ((tid & 31) == 0) atomicAdd(&s_valid, nv);
+    __syncthreads();
+    const int mv = s_valid;                                    // block-uniform
+    auto get = [&](int i, float* v) { *v = key[i]; return !isnan(key[i]); };
+    for (int w = 0; w < 2; ++w) {
+        unsigned int lo = 1u, hi = 0u;                         // no bracket -> F3 falls back
+        if (mv >= 64) {
+            const float q = w ? 0.98f : 0.02f;
+            const int r = (int)(q * (float)(mv - 1) + 0.5f);
+            const int d = (int)ceilf(9.0f * sqrtf((float)mv * q * (1.0f - q))) + 2;
+            lo = t3d_select::float_key(t3d_select::select_rank(sm, kFSamp, (unsigned)max(r - d, 0), get));
+            hi = t3d_select::float_key(t3d_select::select_rank(sm, kFSamp, (unsigned)min(r + d, mv - 1), get));
+        }
+        if (tid == 0) { bracket[4 * b + 2 * w] = lo; bracket[4 * b + 2 * w + 1] = hi; }
+    }
+}
+
+__global__ void __launch_bounds__(kFThreads)
+fpct_classify_kernel(const float* __restrict__ x, int n, int channels, const int* __restrict__ close_flag,
+                     const unsigned int* __restrict__ bracket, int* __restrict__ counters, unsigned int* __restrict__ cand) {
+    __shared__ unsigned int scand[2][kFCtaCand];
+    __shared__ int scount[2], sbase[2], sred[3];
+    const int b = blockIdx.y, tid = threadIdx.x, lane = tid & 31;
+    const float* img = x + (size_t)b * channels * n;
+    const int collapse = (channels == 3) ? close_flag[b] : 0;
+    const int count = (channels == 3) ? n : n * channels;
+    const uint4 br = __ldg(reinterpret_cast<const uint4*>(bracket) + b);
+    const bool has2 = br.y >= br.x, has98 = br.w >= br.z;
+    const unsigned int w2 = br.y - br.x, w98 = br.w - br.z;
+    if (tid < 2) scount[tid] = 0;
+    if (tid < 3) sred[tid] = 0;
+    __syncthreads();
+    int nan = 0, lt2 = 0, lt98 = 0;
+    const int per = (count + gridDim.x - 1) / gridDim.x;
+    const int i0 = blockIdx.x * per, i1 = min(i0 + per, count);
+    for (int i = i0 + tid; i < i1; i += kFThreads) {
+        const float v = plane_value(img, n, channels, collapse, i);
+        if (isnan(v)) { ++nan; continue; }
+        const unsigned int k = t3d_select::float_key(v);
+        lt2 += k < br.x; lt98 += k < br.z;
+        if (has2 && (k - br.x) <= w2) { const int slot = atomicAdd(&scount[0], 1); if (slot < kFCtaCand) scand[0][slot] = k; }
+        if (has98 && (k - br.z) <= w98) { const int slot = atomicAdd(&scount[1], 1); if (slot < kFCtaCand) scand[1][slot] = k; }
+    }
+    nan = __reduce_add_sync(0xffffffffu, nan); lt2 = __reduce_add_sync(0xffffffffu, lt2); lt98 = __reduce_add_sync(0xffffffffu, lt98);
+    if (lane == 0) { if (nan) atomicAdd(&sred[0], nan); if (lt2) atomicAdd(&sred[1], lt2); if (lt98) atomicAdd(&sred[2], lt98); }
+    __syncthreads();
+    int* c = counters + 8 * b;
+    if (tid < 3 && sred[tid]) atomicAdd(&c[tid], sred[tid]);
+    if (tid < 2) {
+        const int k = scount[tid];
+        if (k > kFCtaCand) { atomicExch(&c[5], 1); sbase[tid] = -1; }
+        else {
+            const int base = k ? atomicAdd(&c[3 + tid], k) : 0;
+            if (base + k > kFCandCap) { atomicExch(&c[5], 1); sbase[tid] = -1; }
+            else sbase[tid] = base;
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int a = 0; a < 2; ++a) {
+        const int base = sbase[a], k = min(scount[a], kFCtaCand);
+        if (base >= 0)
+            for (int q = tid; q < k; q += kFThreads) cand[((size_t)b * 2 + a) * kFCandCap + base + q] = scand[a][q];
+    }
+}
+
+// one CTA per image; out_p[b] = {p2, p98} as np.percentile(plane, (2, 98)) would return (fp64)
+__global__ void __launch_bounds__(t3d_select::kThreads, 1)
+fpct_select_kernel(const float* __restrict__ x, int n, int channels, const int* __restrict__ close_flag,
+                   const int* __restrict__ counters, const unsigned int* __restrict__ cand, double* __restrict__ out_p) {
+    extern __shared__ unsigned int skeys[];                     // kFCandCap keys
+    __shared__ t3d_select::Smem sm;
+    const int b = blockIdx.x, tid = threadIdx.x;
     const float* img = x + (size_t)b * channels * n;
     const int collapse = (channels == 3) ? close_flag[b] : 0;
     const int count = (channels == 3) ? n : n * channels;     // non-3-channel input: the whole array
-    auto value = [&](int i) { return plane_value(img, n, channels, collapse, i); };
-    if (threadIdx.x == 0) s_nan = 0;
-    __syncthreads();
-    bool has_nan = false;
-    for (int i = threadIdx.x; i < count; i += blockDim.x) has_nan |= isnan(value(i));
-    if (has_nan) s_nan = 1;
-    __syncthreads();
-    if (s_nan) {                                                // np.percentile propagates NaN
-        if (threadIdx.x == 0) { out_p[2 * b] = __longlong_as_double(0x7ff8000000000000LL); out_p[2 * b + 1] = out_p[2 * b]; }
+    const int* c = counters + 8 * b;
+    if (c[0] > 0) {                                             // np.percentile propagates NaN
+        if (tid == 0) { out_p[2 * b] = __longlong_as_double(0x7ff8000000000000LL); out_p[2 * b + 1] = out_p[2 * b]; }
         return;
     }
-    auto get = [&](int i, float* v) { *v = value(i); return true; };
     unsigned int k[2]; double g[2];
     percentile_ranks(count, 2.0, &k[0], &g[0]);
     percentile_ranks(count, 98.0, &k[1], &g[1]);
     float os[4];
-#pragma unroll
-    for (int r = 0; r < 2; ++r) {
-        os[2 * r] = t3d_select::select_rank(sm, count, k[r], get);
-        const unsigned int k1 = min(k[r] + 1, (unsigned)count - 1);
-        os[2 * r + 1] = (g[r] == 0.0 || k1 == k[r]) ? os[2 * r] : t3d_select::select_rank(sm, count, k1, get);
+    for (int w = 0; w < 2; ++w) {                               // block-uniform control flow throughout
+        const unsigned int r0 = k[w], r1 = min(k[w] + 1, (unsigned)count - 1);
+        const bool need1 = (g[w] != 0.0) && (r1 != r0);
+        const int lt = c[1 + w], nc = c[3 + w];
+        const bool ok = (c[5] == 0) && nc > 0 && nc <= kFCandCap && (int)r0 >= lt && (int)r1 < lt + nc;
+        if (ok) {
+            const unsigned int* src = cand + ((size_t)b * 2 + w) * kFCandCap;
+            __syncthreads();
+            for (int q = tid; q < nc; q += t3d_select::kThreads) skeys[q] = src[q];
+            __syncthreads();
+            auto get = [&](int i, float* v) { *v = t3d_select::key_float(skeys[i]); return true; };
+            os[2 * w] = t3d_select::select_rank(sm, nc, r0 - (unsigned)lt, get);
+            os[2 * w + 1] = need1 ? t3d_select::select_rank(sm, nc, r1 - (unsigned)lt, get) : os[2 * w];
+        } else {                                                // fallback: full radix select over the plane
+            auto get = [&](int i, float* v) { *v = plane_value(img, n, channels, collapse, i); return true; };
+            os[2 * w] = t3d_select::select_rank(sm, count, r0, get);
+            os[2 * w + 1] = need1 ? t3d_select::select_rank(sm, count, r1, get) : os[2 * w];
+        }
     }
-    if (threadIdx.x == 0) {
+    if (tid == 0) {
         out_p[2 * b] = lerp_percentile(os[0], os[1], g[0]);
         out_p[2 * b + 1] = lerp_percentile(os[2], os[3], g[1]);
     }
@@ -746,11 +878,20 @@ int t3d_preprocess_stats_tiles(int dst_h, int dst_w) {
     return (dst_h >= 1 && dst_w >= 4 && dst_w % 4 == 0) ? kNormBands : 0;
 }
 
+size_t t3d_contrast_normalize_workspace_bytes(int B) {
+    if (B < 1) return 0;
+    return fpct_ws(nullptr, B).total;
+}
+
 int t3d_contrast_normalize_f32(const float* x, int B, int channels, int n, float* out, int out_channels,
-                               double* percentiles, int* close_flags, void* stream) {
-    T3D_REQUIRE(x && out && percentiles && close_flags, "NULL pointer");
+                               double* percentiles, int* close_flags, void* workspace, size_t workspace_bytes,
+                               void* stream) {
+    T3D_REQUIRE(x && out && percentiles && close_flags && workspace, "NULL pointer");
     T3D_REQUIRE(B >= 1 && channels >= 1 && n >= 1, "bad dims");
     T3D_REQUIRE((double)channels * n < 2.0e9, "image too large");
+    const FpctWs w = fpct_ws(workspace, B);
+    if (workspace_bytes < w.total) { t3d_set_error("workspace too small"); return T3D_ERR_WORKSPACE; }
+    T3D_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 15u) == 0, "workspace must be 16-byte aligned");
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     const int count = (channels == 3) ? n : n * channels;
     if (channels == 3) {
@@ -758,7 +899,17 @@ int t3d_contrast_normalize_f32(const float* x, int B, int channels, int n, float
         dim3 g((unsigned)min((n + 255) / 256, 32), (unsigned)B);
         T3D_LAUNCH("channels_close_kernel", st, channels_close_kernel<<<g, 256, 0, st>>>(x, n, close_flags));
     }
-    T3D_LAUNCH("percentile_select_kernel", st, percentile_select_kernel<<<B, t3d_select::kThreads, 0, st>>>(x, n, channels, close_flags, percentiles));
+    T3D_CUDA(cudaMemsetAsync(w.counters, 0, (size_t)B * 8 * sizeof(int), st));
+    static bool attr_set = false;
+    if (!attr_set) {
+        T3D_CUDA(cudaFuncSetAttribute(fpct_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFCandCap * (int)sizeof(unsigned int)));
+        attr_set = true;
+    }
+    T3D_LAUNCH("fpct_sample_kernel", st, fpct_sample_kernel<<<B, t3d_select::kThreads, 0, st>>>(x, n, channels, close_flags, w.bracket));
+    dim3 gc((unsigned)max(1, min(kFChunks, (count + 4095) / 4096)), (unsigned)B);
+    T3D_LAUNCH("fpct_classify_kernel", st, fpct_classify_kernel<<<gc, kFThreads, 0, st>>>(x, n, channels, close_flags, w.bracket, w.counters, w.cand));
+    T3D_LAUNCH("fpct_select_kernel", st, fpct_select_kernel<<<B, t3d_select::kThreads, kFCandCap * sizeof(unsigned int), st>>>(
+        x, n, channels, close_flags, w.counters, w.cand, percentiles));
     dim3 g2((unsigned)min((count + 255) / 256, 64), (unsigned)B);
     T3D_LAUNCH("normalize_f32_kernel", st, normalize_f32_kernel<<<g2, 256, 0, st>>>(x, n, channels, close_flags, percentiles, out, out_channels, count));
     return T3D_OK;

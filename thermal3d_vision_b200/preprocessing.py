@@ -130,8 +130,9 @@ def preprocess_thermal_batch(raw_u16: torch.Tensor, img_size=(224, 224), path: s
         rc = lib.t3d_resize_bilinear(_lib.ptr(x), _lib.ptr(resized), 1, B, sh, sw, dh, dw, stream)
         _lib.check(rc, "t3d_resize_bilinear")
         flags = torch.empty(B, dtype=torch.int32, device=dev)
+        fws = torch.empty(lib.t3d_contrast_normalize_workspace_bytes(B), dtype=torch.uint8, device=dev)
         rc = lib.t3d_contrast_normalize_f32(_lib.ptr(resized), B, 1, dh * dw, _lib.ptr(thermal), out_channels,
-                                            _lib.ptr(pct), _lib.ptr(flags), stream)
+                                            _lib.ptr(pct), _lib.ptr(flags), _lib.ptr(fws), fws.numel(), stream)
         _lib.check(rc, "t3d_contrast_normalize_f32")
         return ThermalBatch(thermal, pct, None)
     raise ValueError("path must be 'train' or 'inference'")
@@ -173,8 +174,10 @@ def enhance_thermal_contrast(thermal_tensor):
                       dtype=torch.float32, device=x.device)
     pct = torch.empty(1, 2, dtype=torch.float64, device=x.device)
     flags = torch.empty(1, dtype=torch.int32, device=x.device)
+    fws = torch.empty(_lib.lib().t3d_contrast_normalize_workspace_bytes(1), dtype=torch.uint8, device=x.device)
     rc = _lib.lib().t3d_contrast_normalize_f32(_lib.ptr(x), 1, channels, n, _lib.ptr(out), rep,
-                                               _lib.ptr(pct), _lib.ptr(flags), _lib.current_stream_ptr())
+                                               _lib.ptr(pct), _lib.ptr(flags), _lib.ptr(fws), fws.numel(),
+                                               _lib.current_stream_ptr())
     _lib.check(rc, "t3d_contrast_normalize_f32")
     return out if src_cuda else out.cpu()
 
