@@ -87,7 +87,8 @@ __device__ __forceinline__ void read_pixel(const PixelSrc& s, const float* __res
 // ------------------------------------------------------------------ S: sample + bracket
 // grid (2, B): blockIdx.x = stream (0 = gt, 1 = pred)
 __global__ void __launch_bounds__(1024, 1) metrics_sample_kernel(const PixelSrc s, int pred_offset,
-                                                                 unsigned int* __restrict__ bracket) {
+                                                                 unsigned int* __restrict__ bracket,
+                                                                 int* __restrict__ counters) {
     __shared__ unsigned int key[kSample];
     __shared__ t3d_select::Smem sm;
     __shared__ int cnt;
@@ -96,6 +97,7 @@ __global__ void __launch_bounds__(1024, 1) metrics_sample_kernel(const PixelSrc 
     const float* p = s.pred + (size_t)b * n * s.pred_stride + pred_offset;
     const unsigned char* m = s.mask ? s.mask + (size_t)b * n : nullptr;
     if (tid == 0) cnt = 0;
+    if (a == 0 && tid < 8) counters[8 * b + tid] = 0;        // this image's counters for the extraction pass
     __syncthreads();
     int c = 0;
 #pragma unroll
@@ -668,7 +670,6 @@ int t3d_depth_metrics(const float* pred, int pred_stride, int pred_offset,
     MetricsWs w = metrics_ws(workspace, B, n, chunks);
     if (workspace_bytes < w.total) { t3d_set_error("workspace too small"); return T3D_ERR_WORKSPACE; }
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    T3D_CUDA(cudaMemsetAsync(w.counters, 0, (size_t)B * 8 * sizeof(int), st));
     PixelSrc src;
     src.pred = pred; src.gt = gt; src.mask = mask; src.pred_stride = pred_stride;
     src.gt_h = gt_h; src.gt_w = gt_w; src.H = H; src.W = W; src.resample = (gt_h != H) || (gt_w != W);
@@ -681,9 +682,11 @@ int t3d_depth_metrics(const float* pred, int pred_stride, int pred_offset,
         attr_set = true;
     }
     if (median_scaling)
-        T3D_LAUNCH("metrics_sample_kernel", st, metrics_sample_kernel<<<dim3(2, B), 1024, 0, st>>>(src, pred_offset, w.bracket));
-    else
+        T3D_LAUNCH("metrics_sample_kernel", st, metrics_sample_kernel<<<dim3(2, B), 1024, 0, st>>>(src, pred_offset, w.bracket, w.counters));
+    else {
+        T3D_CUDA(cudaMemsetAsync(w.counters, 0, (size_t)B * 8 * sizeof(int), st));
         T3D_CUDA(cudaMemsetAsync(w.bracket, 0xff, (size_t)B * 4 * sizeof(unsigned int), st));   // empty brackets
+    }
     const bool fast_x = !mask && (W % 4 == 0) && t3d_aligned16(pred) && t3d_aligned16(gt) &&
                         (!src.resample || H + W <= kResampleMaxDim) && (src.resample || (gt_h * gt_w) % 4 == 0) &&
                         ((pred_stride == 3 && pred_offset == 2) || (pred_stride == 1 && pred_offset == 0));

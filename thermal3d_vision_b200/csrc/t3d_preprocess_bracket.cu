@@ -136,7 +136,8 @@ __device__ __forceinline__ void select16_x4(Select16& sm, int n, const unsigned 
 // empty (lo98 = 65536), so a pixel is in at most one window.  CTA 0 also publishes the resize tap tables.
 __global__ void __launch_bounds__(1024, 1)
 bracket_sample_kernel(const uint16_t* __restrict__ src, int sh, int sw, int dh, int dw, int same,
-                      unsigned int* __restrict__ bracket, uint2* __restrict__ gxt, uint4* __restrict__ gyt) {
+                      unsigned int* __restrict__ bracket, uint2* __restrict__ gxt, uint4* __restrict__ gyt,
+                      unsigned int* __restrict__ brhist, int B) {
     __shared__ short key[kSamp];
     __shared__ Select16 sel;
     const int b = blockIdx.x, tid = threadIdx.x;
@@ -148,6 +149,9 @@ bracket_sample_kernel(const uint16_t* __restrict__ src, int sh, int sw, int dh, 
             if (i < dh) { const Tap t = linear_tap(i, sh, scy); gyt[i] = make_uint4((unsigned)t.s0, (unsigned)t.s1, __float_as_uint(t.c0), __float_as_uint(t.c1)); }
         }
     }
+    // zero this frame's windowed histograms (and, CTA 0, the fallback counter) for the classification pass
+    for (int i = tid; i < 2 * kBrStride; i += 1024) brhist[(size_t)b * 2 * kBrStride + i] = 0u;
+    if (b == 0 && tid == 0) brhist[(size_t)B * 2 * kBrStride] = 0u;
     const uint16_t* s = src + (size_t)b * sh * sw;
 #pragma unroll
     for (int q = 0; q < kSamp / 1024; ++q) {
@@ -463,9 +467,8 @@ percentile_from_brackets_kernel(const uint16_t* __restrict__ frames, int n, cons
 int t3d_launch_bracket_percentiles(const uint16_t* raw, int B, int sh, int sw, int dh, int dw, bool same,
                                    const PreWs& w, int rep3, double* percentiles, cudaStream_t st) {
     const int n = dh * dw;
-    T3D_CUDA(cudaMemsetAsync(w.brhist, 0, ((size_t)B * 2 * kBrStride + 1) * sizeof(unsigned int), st));   // + fallback counter
     T3D_LAUNCH("bracket_sample_kernel", st, bracket_sample_kernel<<<B, 1024, 0, st>>>(
-        raw, sh, sw, dh, dw, same ? 1 : 0, w.bracket, w.gxt, w.gyt));
+        raw, sh, sw, dh, dw, same ? 1 : 0, w.bracket, w.gxt, w.gyt, w.brhist, B));
     const bool fast = !same && (dw % 4 == 0) && (sw % 8 == 0) && t3d_aligned16(raw);
     bool launched = false;
     if (fast) {
