@@ -284,6 +284,9 @@ def run_b200(a):
         raise SystemExit("bench.py --impl b200 needs a CUDA device (there is no CPU fallback)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    from thermal3d_vision_b200.distributed import bind_to_gpu_numa_node
+    all_cpus = os.sched_getaffinity(0)
+    numa_bound = bind_to_gpu_numa_node(local)          # before any pinned allocation (matters for the e2e leg at N > 1)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
@@ -297,6 +300,7 @@ def run_b200(a):
     d = make_inputs_torch(B, H, W, seed=rank, device=dev)
     args = (d["raw1"], d["raw2"], d["pred1"], d["pred2"], d["gt1"], d["gt2"], d["conf1"], d["conf2"], d["gt_depth"])
     host = {k: v.cpu().pin_memory() for k, v in d.items()}
+    os.sched_setaffinity(0, all_cpus)                  # the pinned pages are placed; the CPU baseline leg uses every core
 
     def barrier():
         if world > 1:
@@ -328,13 +332,14 @@ def run_b200(a):
     e0.record()
     for _ in range(a.steps):
         step.run_device(*args)
+    step.finish()                        # outstanding (asynchronous) result all-reduces belong to the timed region
     e1.record()
     barrier()
     launches = _lib.launch_count() - n0
     kern_ms, kern_n = _lib.profile_end()
     ms_dev = max_over_ranks(e0.elapsed_time(e1))
     clocks = sampler.stop() if rank == 0 else None
-    summary = HotPathStep.summarize(step.result.cpu())
+    summary = HotPathStep.summarize(step.wait_result().cpu())
 
     # ---------------- end to end through the public API with HOST buffers ("e2e")
     for _ in range(2):
@@ -393,6 +398,7 @@ def run_b200(a):
                     "h2d_bytes_per_step": HotPathStep.h2d_bytes(host), "d2h_bytes_per_step": 16 * 8,
                     "ms_per_step": ms_e2e / a.steps},
             "gpu_launches": int(launches),
+            "host_numa_bound": bool(numa_bound),
             "clocks": clocks,
             "check": {k: summary[k] for k in ("loss", "abs_rel", "acc_1", "n_valid")},
         }

@@ -31,14 +31,37 @@ def shard_range(n: int, rank: int, world_size: int) -> Tuple[int, int]:
     return lo, lo + base + (1 if rank < rem else 0)
 
 
-def all_reduce_result(vec: torch.Tensor) -> torch.Tensor:
-    """In-place SUM all-reduce of the packed result vector (no-op for a single process)."""
+def all_reduce_result(vec: torch.Tensor, async_op: bool = False):
+    """In-place SUM all-reduce of the packed result vector (no-op for a single process).
+    async_op=True returns the work handle (None for a single process): the collective then runs on the backend's
+    own stream and overlaps whatever the caller enqueues next; `handle.wait()` orders the current stream after it."""
     if vec.numel() != RESULT_SIZE:
         raise ValueError(f"packed result must have {RESULT_SIZE} elements")
     _, w = world()
     if w > 1:
-        dist.all_reduce(vec, op=dist.ReduceOp.SUM)
-    return vec
+        h = dist.all_reduce(vec, op=dist.ReduceOp.SUM, async_op=async_op)
+        return h if async_op else vec
+    return None if async_op else vec
+
+
+def bind_to_gpu_numa_node(device_index: int) -> bool:
+    """Pin the calling process to the CPUs closest to its GPU (NVML's ideal CPU affinity) so that pinned host
+    buffers allocated afterwards live on the GPU's NUMA node: with 8 ranks staging 0.8 GB per step each, remote-node
+    pinned memory halves the aggregate H2D rate.  Returns False when NVML is unavailable."""
+    try:
+        import os
+        import pynvml
+        pynvml.nvmlInit()
+        phys = device_index
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            ids = [v.strip() for v in vis.split(",") if v.strip()]
+            if device_index < len(ids) and ids[device_index].isdigit():
+                phys = int(ids[device_index])
+        pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(phys))
+        return True
+    except Exception:
+        return False
 
 
 def global_grad_scale(local_batch: int) -> float:

@@ -67,7 +67,12 @@ class HotPathStep:
         # percentiles from sampled value windows (bit-identical to the exact-histogram path, no per-pixel atomic);
         # set True to also get the 65 536-bin histograms of the resized frames in pre_both["histogram"]
         self.histogram = False
-        self.result = torch.zeros(RESULT_SIZE, dtype=torch.float64, device=dev)
+        # two packed-result vectors used alternately: with distributed=True the all-reduce of step i is asynchronous
+        # and overlaps the kernels of step i + 1 (it is a 128-byte, latency-bound collective)
+        self.results = [torch.zeros(RESULT_SIZE, dtype=torch.float64, device=dev) for _ in range(2)]
+        self.pending = [None, None]
+        self.calls = 0
+        self.result = self.results[0]
         self.result_host = torch.zeros(RESULT_SIZE, dtype=torch.float64).pin_memory()
         self.staging = None        # two device staging sets of run_host (allocated on first use)
 
@@ -123,13 +128,36 @@ class HotPathStep:
                                               thermal_replicated=True,   # preprocess_thermal_batch wrote 3 identical planes
                                               grad_scale=_dist.global_grad_scale(self.B) if self.distributed else None,
                                               **self.kw)
-        r = self.result
+        i = self.calls & 1
+        self.calls += 1
+        if self.pending[i] is not None:
+            self.pending[i].wait()                 # the all-reduce of step - 2 is done with this vector
+            self.pending[i] = None
+        r = self.results[i]
         rc = _lib.lib().t3d_pack_step_result(_lib.ptr(lo["per_sample"]), _lib.ptr(me["metrics_f64"]), self.B, self.B,
                                              _lib.ptr(r), _lib.current_stream_ptr())
         _lib.check(rc, "t3d_pack_step_result")
         if self.distributed:
-            _dist.all_reduce_result(r)
+            self.pending[i] = _dist.all_reduce_result(r, async_op=True)
+        self.result = r
         return r
+
+    def wait_result(self, r: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Order the current stream after the (asynchronous) all-reduce of `r` (default: the latest result).
+        Call before reading a result of a distributed step; a no-op otherwise."""
+        r = self.result if r is None else r
+        for i in range(2):
+            if self.results[i] is r and self.pending[i] is not None:
+                self.pending[i].wait()
+                self.pending[i] = None
+        return r
+
+    def finish(self):
+        """Order the current stream after every outstanding all-reduce (end of a run / of a timed region)."""
+        for i in range(2):
+            if self.pending[i] is not None:
+                self.pending[i].wait()
+                self.pending[i] = None
 
     # ------------------------------------------------------------------ host-buffer step (e2e)
     def run_host(self, host: Dict[str, torch.Tensor]):
@@ -167,6 +195,7 @@ class HotPathStep:
         r = self.run_device(s["raw1"], s["raw2"], s["pred1"], s["pred2"], s["gt1"], s["gt2"], s["conf1"], s["conf2"],
                             s["gt_depth"])
         self.consumed[i].record(main)
+        self.wait_result(r)
         self.result_host.copy_(r, non_blocking=True)
         self.host_calls += 1
         return self.result_host
