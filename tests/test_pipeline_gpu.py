@@ -79,3 +79,23 @@ def test_hot_path_step_full_size_is_deterministic(cuda_device):
     assert (step.pre_both["histogram"].sum(1) == H * W).all()
     s = HotPathStep.summarize(a.cpu())
     assert s["n_valid"] == B and 0 < s["loss"] < 100 and 0 <= s["abs_rel"] < 1
+
+
+def test_graph_replay_equals_stream_launches(cuda_device):
+    """HotPathStep.capture_graph: the whole step as one CUDA-graph launch gives the bits of the eager step."""
+    from thermal3d_vision_b200.pipeline import HotPathStep
+    import bench
+    B, H, W = 8, 224, 224                               # BASELINE configs[1] shape: launch-bound
+    d = bench.make_inputs_torch(B, H, W, seed=2, device=cuda_device)
+    args = (d["raw1"], d["raw2"], d["pred1"], d["pred2"], d["gt1"], d["gt2"], d["conf1"], d["conf2"], d["gt_depth"])
+    step = HotPathStep(B, H, W, device=cuda_device)
+    eager = step.run_device(*args).clone()
+    grads = [step.loss_out[k].clone() for k in ("dpred1", "dconf2")]
+    replay = step.capture_graph(*args)
+    for _ in range(3):
+        for k in ("dpred1", "dconf2"):
+            step.loss_out[k].zero_()
+        r = replay()
+        torch.cuda.synchronize()
+        assert torch.equal(r, eager)
+        assert torch.equal(step.loss_out["dpred1"], grads[0]) and torch.equal(step.loss_out["dconf2"], grads[1])

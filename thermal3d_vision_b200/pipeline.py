@@ -142,6 +142,33 @@ class HotPathStep:
         self.result = r
         return r
 
+    def capture_graph(self, raw1, raw2, pred1, pred2, gt1, gt2, conf1, conf2, gt_depth):
+        """Capture one `run_device` on these (static) device tensors into a CUDA graph and return `replay()`, which
+        re-runs the whole step (both streams, ~15 kernels) with one launch and returns the packed result vector.
+        For launch-bound shapes (BASELINE configs[1]: batch 8 at 224x224 is ~45 MB of traffic, a few microseconds
+        of HBM time) this is what removes the per-kernel launch latency.  Single-process only (the all-reduce of a
+        distributed step is issued outside any graph)."""
+        if self.distributed:
+            raise ValueError("capture_graph is for single-process steps")
+        args = (raw1, raw2, pred1, pred2, gt1, gt2, conf1, conf2, gt_depth)
+        cur = torch.cuda.current_stream(self.device)
+        warm = torch.cuda.Stream(device=self.device)
+        warm.wait_stream(cur)
+        with torch.cuda.stream(warm):
+            for _ in range(2):                     # one-time attribute / occupancy queries happen outside the capture
+                self.run_device(*args)
+        cur.wait_stream(warm)
+        torch.cuda.synchronize(self.device)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            r = self.run_device(*args)
+
+        def replay():
+            graph.replay()
+            return r
+        replay.graph = graph
+        return replay
+
     def wait_result(self, r: Optional[torch.Tensor] = None) -> torch.Tensor:
         """Order the current stream after the (asynchronous) all-reduce of `r` (default: the latest result).
         Call before reading a result of a distributed step; a no-op otherwise."""

@@ -1,15 +1,11 @@
-"""Developer tool: HotPathStep captured in a CUDA graph vs stream launches."""
+"""Developer tool: HotPathStep as stream launches vs one CUDA-graph launch, at the launch-bound and the large shape."""
 import sys, os, json
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import bench
 from thermal3d_vision_b200.pipeline import HotPathStep
 dev = torch.device("cuda:0")
-B, H, W = 64, 384, 512
-d = bench.make_inputs_torch(B, H, W, 0, dev)
-step = HotPathStep(B, H, W, device=dev)
-args = (d["raw1"], d["raw2"], d["pred1"], d["pred2"], d["gt1"], d["gt2"], d["conf1"], d["conf2"], d["gt_depth"])
-def timeit(fn, n=100):
+def timeit(fn, n=200):
     for _ in range(10): fn()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -19,19 +15,13 @@ def timeit(fn, n=100):
         for _ in range(n): fn()
         e1.record(); torch.cuda.synchronize()
         best = min(best, e0.elapsed_time(e1) / n * 1e3)
-    return best
-res = {"stream_us": timeit(lambda: step.run_device(*args))}
-ref = step.result.clone()
-s = torch.cuda.Stream()
-s.wait_stream(torch.cuda.current_stream())
-with torch.cuda.stream(s):
-    for _ in range(3): step.run_device(*args)
-torch.cuda.current_stream().wait_stream(s)
-torch.cuda.synchronize()
-g = torch.cuda.CUDAGraph()
-with torch.cuda.graph(g):
-    step.run_device(*args)
-res["graph_us"] = timeit(g.replay)
-torch.cuda.synchronize()
-res["same_result"] = bool(torch.equal(ref, step.result))
+    return round(best, 1)
+res = {}
+for (B, H, W) in ((8, 224, 224), (64, 384, 512)):
+    d = bench.make_inputs_torch(B, H, W, 0, dev)
+    step = HotPathStep(B, H, W, device=dev)
+    args = (d["raw1"], d["raw2"], d["pred1"], d["pred2"], d["gt1"], d["gt2"], d["conf1"], d["conf2"], d["gt_depth"])
+    res[f"B{B}_{W}x{H}_stream_us"] = timeit(lambda: step.run_device(*args))
+    replay = step.capture_graph(*args)
+    res[f"B{B}_{W}x{H}_graph_us"] = timeit(replay)
 print(json.dumps(res))

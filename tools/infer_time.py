@@ -23,3 +23,13 @@ res["enhance_thermal_contrast_1img_us"] = timeit(lambda: pp.enhance_thermal_cont
 x1 = x[:1].repeat(3, 1, 1).contiguous()
 res["enhance_thermal_contrast_1img_replicated_us"] = timeit(lambda: pp.enhance_thermal_contrast(x1))
 print(json.dumps(res))
+from thermal3d_vision_b200 import _lib
+fn = lambda: pp.preprocess_thermal_batch(raw, (512, 384), path="inference")
+out = {}
+for nm in ["resize_bilinear", "fpct_sample", "fpct_classify", "fpct_select", "normalize_f32", "channels_close", "set_int"]:
+    _lib.profile_begin(nm, 4096)
+    for _ in range(10): fn()
+    torch.cuda.synchronize()
+    ms, n = _lib.profile_end()
+    out[nm] = round(ms / 10 * 1e3, 1)
+print(json.dumps(out))
