@@ -449,7 +449,7 @@ __device__ __forceinline__ void metric_terms_fast(float gt, float pr, float accf
 }
 
 template <bool GENERAL>
-__global__ void __launch_bounds__(kChunkThreads)
+__global__ void __launch_bounds__(kChunkThreads, 4)
 metrics_sum_kernel(const float* __restrict__ vz, const float* __restrict__ vg,
                    const float* __restrict__ medians, const int* __restrict__ counters, int median_scaling,
                    int n, int chunks, double* __restrict__ partials) {
