@@ -60,7 +60,9 @@ class HotPathStep:
         # side streams: the two preprocessing calls and the metric pipeline are independent of each other
         # (many short, latency-bound kernels) and overlap; the loss needs both thermal batches and then
         # runs alone on the caller's stream
-        self.side = [torch.cuda.Stream(device=dev) for _ in range(2)]
+        # (high priority: the metric pipeline's small one-CTA-per-image kernels then get the next free SM slots
+        # instead of queueing behind the preprocessing kernels' remaining CTAs -- 0.465 -> 0.455 ms per step)
+        self.side = [torch.cuda.Stream(device=dev, priority=-1) for _ in range(2)]
         self.fork = torch.cuda.Event()
         self.joins = [torch.cuda.Event() for _ in range(2)]
         self.overlap = True
@@ -261,7 +263,7 @@ class EvalStep:
                         "metrics": torch.empty(B, 8, **f32), "metrics_f64": torch.empty(B, 8, dtype=torch.float64, device=dev),
                         "medians": torch.empty(B, 2, **f32)}
         self.acc = _metrics.MetricAccumulator(dev)
-        self.side = torch.cuda.Stream(device=dev)
+        self.side = torch.cuda.Stream(device=dev, priority=-1)
         self.fork, self.join = torch.cuda.Event(), torch.cuda.Event()
 
     def algorithmic_bytes(self) -> int:

@@ -9,6 +9,9 @@ B, H, W = 64, 384, 512
 d = bench.make_inputs_torch(B, H, W, 0, dev)
 step = HotPathStep(B, H, W, device=dev)
 args = (d["raw1"], d["raw2"], d["pred1"], d["pred2"], d["gt1"], d["gt2"], d["conf1"], d["conf2"], d["gt_depth"])
+main_prio = int(os.environ.get("T3D_MAIN_PRIO", "0"))
+ms = torch.cuda.Stream(device=dev, priority=main_prio)
+torch.cuda.set_stream(ms)
 for _ in range(10): step.run_device(*args)
 torch.cuda.synchronize()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
