@@ -23,14 +23,14 @@ def _oracle_step(raw1, raw2, P1, P2, G1, G2, C1, C2, gt_depth, H, W, multi):
     return T1, T2, mean.item(), rows, valid, [x.grad for x in lead], ref_metrics.accumulate_dataset(per)
 
 
+@pytest.mark.parametrize("B,H,W", [(3, 96, 160), (1, 224, 224), (2, 100, 260)])
 @pytest.mark.parametrize("multi", [False, True])
-def test_hot_path_step_matches_oracle_loop(cuda_device, multi):
+def test_hot_path_step_matches_oracle_loop(cuda_device, multi, B, H, W):
     from thermal3d_vision_b200.pipeline import HotPathStep
-    B, H, W = 3, 96, 160
     raw = ref_preprocess.make_raw_frames(2 * B, seed=13, hw=(128, 200))
     P1, P2, G1, G2, C1, C2, _, _ = ref_loss.make_batch_inputs(B, H, W, seed=17, stress_conf=True)
     gt_depth = G1[..., 2].clone()
-    gt_depth[1, :7] = 0.0                                   # invalid GT region in one image
+    gt_depth[B - 1, :7] = 0.0                               # invalid GT region in one image
     T1, T2, mean, rows, valid, grads, metrics = _oracle_step(raw[:B], raw[B:], P1, P2, G1, G2, C1, C2, gt_depth, H, W, multi)
 
     step = HotPathStep(B, H, W, raw_hw=(128, 200), device=cuda_device, multi_scale=multi, **KW)
