@@ -251,7 +251,8 @@ __global__ void __launch_bounds__(256) resize_classify_generic_kernel(const uint
 //     and the final round-half-even go through the FP32 pipe (magic-number adds), not the conversion pipe.
 constexpr int kRzThreads = 256;
 constexpr int kRzWarps = kRzThreads / 32;
-constexpr int kRzStrip = 128;
+constexpr int kRzU = 8;                 // consecutive output pixels per lane
+constexpr int kRzStrip = 32 * kRzU;
 constexpr int kRing = 4;
 
 // one warp: resize + classify output rows [ya, yb) of strip `strip` of frame `f`
@@ -262,18 +263,19 @@ __device__ __forceinline__ void resize_march_rows(const uint16_t* __restrict__ s
                                                   int sh, int sw, int dh, int dw, int f, int strip, int ya, int yb,
                                                   uint32_t ring, uint32_t slot_bytes, int lane) {
     const int X0 = strip * kRzStrip;
-    const int x0 = X0 + 4 * lane;
+    const int x0 = X0 + kRzU * lane;
     const bool active = x0 < dw;
     // ---- x taps of this lane's 4 pixels as shared-memory byte offsets inside a ring slot
     const int xl = min(X0 + kRzStrip, dw) - 1;
     const int span0 = (int)(__ldg(gxt + X0).x & 0xffffu) & ~7;          // 8-aligned first source column
     const int span1 = (int)(__ldg(gxt + xl).x >> 16) + 1;               // one past the last source column used
-    const bool copier = lane < ((span1 - span0 + 7) >> 3);              // <= 32 16-byte chunks per source row (launcher)
+    const int nvec = (span1 - span0 + 7) >> 3;                          // <= 64 16-byte chunks per source row (launcher)
+    const bool copier = lane < nvec, copier2 = lane + 32 < nvec;
     // the second tap is the next source pixel; where cv2 clamps it to the same pixel (right border) its weight
     // is exactly 0, so reading the (finite) u16 after the row's last pixel instead changes nothing
-    uint32_t o0[4]; float fx[4], cx[4];
+    uint32_t o0[kRzU]; float fx[kRzU], cx[kRzU];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < kRzU; ++u) {
         const uint2 t = __ldg(gxt + min(x0 + u, dw - 1));
         o0[u] = ring + 2u * (uint32_t)((int)(t.x & 0xffffu) - span0);
         fx[u] = __uint_as_float(t.y); cx[u] = __fsub_rn(1.0f, fx[u]);
@@ -296,6 +298,7 @@ __device__ __forceinline__ void resize_march_rows(const uint16_t* __restrict__ s
         if (DENSE) {
             if (inext <= rlast) {
                 if (copier) cp_async16(lane_dst + issue_off, next_src);
+                if (copier2) cp_async16(lane_dst + issue_off + 512u, next_src + 512);
                 next_src += src_rowb; ++inext;
                 issue_off += slot_bytes; if (issue_off == ring_bytes) issue_off = 0;
             }
@@ -309,17 +312,18 @@ __device__ __forceinline__ void resize_march_rows(const uint16_t* __restrict__ s
             if (r >= 0) {
                 ilast = r;
                 if (copier) cp_async16(lane_dst + issue_off, lane_src + (size_t)r * src_rowb);
+                if (copier2) cp_async16(lane_dst + issue_off + 512u, lane_src + (size_t)r * src_rowb + 512);
                 issue_off += slot_bytes; if (issue_off == ring_bytes) issue_off = 0;
             }
         }
         cp_async_commit();                                              // possibly empty: keeps the group count in step
     };
-    auto load_h = [&](float h[4]) {
+    auto load_h = [&](float h[kRzU]) {
         cp_async_wait<kRing - 2>();
         __syncwarp();                 // the row has landed for every lane; everyone is done with the previous row
         issue_next();                 // ... whose slot is the one this issue refills
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < kRzU; ++u) {
             const uint32_t ad = o0[u] + load_off;
             const float a = (float)lds_u16(ad), bq = (float)lds_u16(ad + 2u);
             h[u] = __fadd_rn(__fmul_rn(a, cx[u]), __fmul_rn(bq, fx[u]));
@@ -330,7 +334,7 @@ __device__ __forceinline__ void resize_march_rows(const uint16_t* __restrict__ s
 #pragma unroll
     for (int p = 0; p < kRing - 1; ++p) issue_next();
 
-    float hA_[4], hB_[4];
+    float hA_[kRzU], hB_[kRzU];
     int tagA = -1, tagB = -1;
     uint16_t* out = resized + ((size_t)f * dh + ya) * dw + x0;
     uint4 ty = __ldg(gyt + ya);
@@ -342,31 +346,31 @@ __device__ __forceinline__ void resize_march_rows(const uint16_t* __restrict__ s
         if (s0 != tagA) {
             if (s0 == tagB) {
 #pragma unroll
-                for (int u = 0; u < 4; ++u) hA_[u] = hB_[u];
+                for (int u = 0; u < kRzU; ++u) hA_[u] = hB_[u];
             } else load_h(hA_);
             tagA = s0;
         }
         if (s1 != tagB) {
             if (s1 == tagA) {
 #pragma unroll
-                for (int u = 0; u < 4; ++u) hB_[u] = hA_[u];
+                for (int u = 0; u < kRzU; ++u) hB_[u] = hA_[u];
             } else load_h(hB_);
             tagB = s1;
         }
-        unsigned int v[4];
+        unsigned int v[kRzU];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) v[u] = round_u16(__fadd_rn(__fmul_rn(hA_[u], cy0), __fmul_rn(hB_[u], cy1)));
+        for (int u = 0; u < kRzU; ++u) v[u] = round_u16(__fadd_rn(__fmul_rn(hA_[u], cy0), __fmul_rn(hB_[u], cy1)));
         if (active) {
-            *reinterpret_cast<uint2*>(out) = make_uint2(v[0] | (v[1] << 16), v[2] | (v[3] << 16));
+            *reinterpret_cast<uint4*>(out) = make_uint4(v[0] | (v[1] << 16), v[2] | (v[3] << 16), v[4] | (v[5] << 16), v[6] | (v[7] << 16));
 #pragma unroll
-            for (int u = 0; u < 4; ++u) if (!is_mid(v[u], w)) count_edge(v[u], w, hA);
+            for (int u = 0; u < kRzU; ++u) if (!is_mid(v[u], w)) count_edge(v[u], w, hA);
         }
     }
     cp_async_wait<0>();
 }
 
 template <bool DENSE>
-__global__ void __launch_bounds__(kRzThreads, 4)
+__global__ void __launch_bounds__(kRzThreads, 3)
 resize_march_kernel(const uint16_t* __restrict__ src, uint16_t* __restrict__ resized,
                     const uint2* __restrict__ gxt, const uint4* __restrict__ gyt,
                     const unsigned int* __restrict__ bracket, unsigned int* __restrict__ brhist,
@@ -469,7 +473,7 @@ int t3d_launch_bracket_percentiles(const uint16_t* raw, int B, int sh, int sw, i
     const int n = dh * dw;
     T3D_LAUNCH("bracket_sample_kernel", st, bracket_sample_kernel<<<B, 1024, 0, st>>>(
         raw, sh, sw, dh, dw, same ? 1 : 0, w.bracket, w.gxt, w.gyt, w.brhist, B));
-    const bool fast = !same && (dw % 4 == 0) && (sw % 8 == 0) && t3d_aligned16(raw);
+    const bool fast = !same && (dw % 8 == 0) && (sw % 8 == 0) && t3d_aligned16(raw);
     bool launched = false;
     if (fast) {
         const int nstrips = (dw + kRzStrip - 1) / kRzStrip;
@@ -480,7 +484,7 @@ int t3d_launch_bracket_percentiles(const uint16_t* raw, int B, int sh, int sw, i
         const int slot_bytes = slot_px * (int)sizeof(uint16_t);
         const size_t smem = (size_t)kRzWarps * kRing * slot_bytes;
         const bool dense = sh <= 2 * dh;
-        if (smem <= 96 * 1024 && slot_px <= 256 && (long long)B * nstrips * dh < (1ll << 31)) {
+        if (smem <= 96 * 1024 && slot_px <= 512 && (long long)B * nstrips * dh < (1ll << 31)) {
             static int ctas_per_sm[2] = {0, 0};
             static size_t attr_smem[2] = {0, 0};
             const int di = dense ? 1 : 0;
