@@ -57,6 +57,11 @@ uint64_t t3d_launch_count(void);
  * time and the number of launches timed. */
 int t3d_profile_begin(const char* kernel_name_substr, int max_launches);
 int t3d_profile_end(double* total_ms, int* launches);
+/* Developer instrumentation: call BEFORE t3d_profile_end.  Start / stop times
+ * (ms, relative to the first timed launch's start event) and names of the
+ * launches timed since t3d_profile_begin; `names` holds cap strings of
+ * name_stride bytes.  Stops further timing; t3d_profile_end then frees. */
+int t3d_profile_timeline(char* names, int name_stride, double* start_ms, double* stop_ms, int cap, int* launches);
 
 /* -------------------------------------------------------------------- loss */
 /* Replaces utils/loss.py:75-98 (confidence_weighted_regression_loss) and

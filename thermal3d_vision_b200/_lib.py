@@ -29,6 +29,8 @@ _SIGNATURES = {
     "t3d_launch_count": (C.c_uint64, []),
     "t3d_profile_begin": (C.c_int, [C.c_char_p, C.c_int]),
     "t3d_profile_end": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_int)]),
+    "t3d_profile_timeline": (C.c_int, [C.c_char_p, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_int,
+                                       C.POINTER(C.c_int)]),
     "t3d_loss_workspace_bytes": (C.c_size_t, [C.c_int] * 4),
     "t3d_thermal_grad_stats": (C.c_int, [c_ptr, c_ptr, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                          c_ptr, c_ptr, C.c_size_t, c_ptr]),
@@ -128,6 +130,16 @@ def profile_end():
     ms, n = C.c_double(0.0), C.c_int(0)
     check(lib().t3d_profile_end(C.byref(ms), C.byref(n)), "t3d_profile_end")
     return ms.value, n.value
+
+
+def profile_timeline(cap: int = 4096):
+    """-> [(kernel name, start ms, stop ms)] of the launches timed since profile_begin (then call profile_end)."""
+    stride = 64
+    names = C.create_string_buffer(cap * stride)
+    t0, t1, n = (C.c_double * cap)(), (C.c_double * cap)(), C.c_int(0)
+    check(lib().t3d_profile_timeline(names, stride, t0, t1, cap, C.byref(n)), "t3d_profile_timeline")
+    raw = names.raw
+    return [(raw[i * stride:(i + 1) * stride].split(b"\0", 1)[0].decode(), t0[i], t1[i]) for i in range(n.value)]
 
 
 def ptr(t):

@@ -36,6 +36,7 @@ struct Prof {
     bool active = false;
     char pattern[96] = "";
     std::vector<cudaEvent_t> ev;   // start/stop pairs
+    std::vector<const char*> names; // kernel name of each pair (string literals)
     int used = 0, cap = 0;
 } g_prof;
 }  // namespace
@@ -45,6 +46,7 @@ bool t3d_prof_before(const char* name, cudaStream_t st) {
     std::lock_guard<std::mutex> lk(g_prof.mu);
     if (!g_prof.active || g_prof.used >= g_prof.cap || !strstr(name, g_prof.pattern)) return false;
     cudaEventRecord(g_prof.ev[2 * g_prof.used], st);
+    g_prof.names[g_prof.used] = name;
     return true;
 }
 
@@ -88,9 +90,28 @@ int t3d_profile_begin(const char* kernel_name_substr, int max_launches) {
     for (cudaEvent_t e : g_prof.ev) cudaEventDestroy(e);
     g_prof.ev.assign((size_t)2 * max_launches, nullptr);
     for (auto& e : g_prof.ev) T3D_CUDA(cudaEventCreate(&e));
+    g_prof.names.assign((size_t)max_launches, nullptr);
     strncpy(g_prof.pattern, kernel_name_substr, sizeof(g_prof.pattern) - 1);
     g_prof.pattern[sizeof(g_prof.pattern) - 1] = 0;
     g_prof.used = 0; g_prof.cap = max_launches; g_prof.active = true;
+    return T3D_OK;
+}
+
+int t3d_profile_timeline(char* names, int name_stride, double* start_ms, double* stop_ms, int cap, int* launches) {
+    T3D_REQUIRE(names && name_stride > 1 && start_ms && stop_ms && cap > 0 && launches, "bad arguments");
+    std::lock_guard<std::mutex> lk(g_prof.mu);
+    g_prof.active = false;
+    const int n = g_prof.used < cap ? g_prof.used : cap;
+    for (int i = 0; i < n; ++i) {
+        T3D_CUDA(cudaEventSynchronize(g_prof.ev[2 * i + 1]));
+        float a = 0.f, b = 0.f;
+        T3D_CUDA(cudaEventElapsedTime(&a, g_prof.ev[0], g_prof.ev[2 * i]));
+        T3D_CUDA(cudaEventElapsedTime(&b, g_prof.ev[0], g_prof.ev[2 * i + 1]));
+        start_ms[i] = a; stop_ms[i] = b;
+        strncpy(names + (size_t)i * name_stride, g_prof.names[i] ? g_prof.names[i] : "", name_stride - 1);
+        names[(size_t)i * name_stride + name_stride - 1] = 0;
+    }
+    *launches = n;
     return T3D_OK;
 }
 

@@ -530,6 +530,23 @@ __device__ __forceinline__ float2 lds_f2(uint32_t saddr) {
     return v;
 }
 
+__device__ __forceinline__ uint2 lds_u2(uint32_t saddr) {
+    uint2 v;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(saddr));
+    return v;
+}
+__device__ __forceinline__ unsigned int lds_h(uint32_t saddr) {
+    unsigned short v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(saddr));
+    return v;
+}
+__device__ __forceinline__ void cpa16(uint32_t dst_saddr, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(dst_saddr), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cpa_commit_wait_all() {
+    asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+}
+
 struct NormRow { float o[4], g[4]; };
 
 // Frames whose p2..p98 range does not fit the LUT (> 4093 counts): direct fp64 evaluation, one pixel per thread.
@@ -554,7 +571,10 @@ __device__ __noinline__ void normalize_band_direct(const uint16_t* __restrict__ 
 // lane = 4 consecutive pixels (one 8-byte load per row, issued two rows ahead), the row below is looked up once
 // and becomes the current row of the next iteration (two register sets, ping-pong), the right neighbour's gray
 // comes from a shuffle (strip edge: one extra u16), outputs leave as 128-bit streaming stores.
-template <int REP, bool STATS>
+// STAGED (W % 8 == 0, the band fits): the band's raw rows (+ the row below) and the LUT arrive in shared memory as
+// ONE batch of cp.async copies -- a single exposed memory latency per CTA instead of one per marched row (the
+// marches are short: 8 rows per warp at 384 rows), and the march itself then reads shared memory only.
+template <int REP, bool STATS, bool STAGED>
 __global__ void __launch_bounds__(kNormThreads, 4) normalize_stats_u16_kernel(const uint16_t* __restrict__ src,
                                                                            const double* __restrict__ p,
                                                                            float* __restrict__ dst, int H, int W,
@@ -581,7 +601,17 @@ __global__ void __launch_bounds__(kNormThreads, 4) normalize_stats_u16_kernel(co
         const double p2 = p[2 * b], den = __dsub_rn(p[2 * b + 1], p2);
         normalize_band_direct<REP>(s, d, H, W, y0, y1, p2, den, STATS, tx, ty);
     } else {
-        {
+        const uint32_t sraw = (uint32_t)__cvta_generic_to_shared(lut) + (uint32_t)kLutMax * 8u;   // STAGED: rows [y0, yl)
+        if (STAGED) {
+            const uint32_t slut = (uint32_t)__cvta_generic_to_shared(lut);
+            const char* gl = reinterpret_cast<const char*>(glut + (size_t)b * kLutMax);
+            for (int k = tid; k < (range + 1) / 2; k += kNormThreads) cpa16(slut + 16u * k, gl + 16 * (size_t)k);
+            const int yl = STATS ? min(y1 + 1, H) : y1;
+            const int nchunk = ((yl - y0) * W) >> 3;                  // the band is one contiguous block of the frame
+            const char* gs = reinterpret_cast<const char*>(s + (size_t)y0 * W);
+            for (int k = tid; k < nchunk; k += kNormThreads) cpa16(sraw + 16u * k, gs + 16 * (size_t)k);
+            cpa_commit_wait_all();
+        } else {
             const float4* g4 = reinterpret_cast<const float4*>(glut + (size_t)b * kLutMax);
             float4* l4 = reinterpret_cast<float4*>(lut);
             for (int k = tid; k < (range + 1) / 2; k += kNormThreads) l4[k] = __ldg(g4 + k);
@@ -612,13 +642,19 @@ __global__ void __launch_bounds__(kNormThreads, 4) normalize_stats_u16_kernel(co
             const int ym = STATS ? min(yb, H - 1) : ya;
             const int last = STATS ? min(yb, H - 1) : yb - 1;             // last row that is fetched
             const char* ld = reinterpret_cast<const char*>(s + (size_t)ya * W + (active ? x0 : 0));
+            uint32_t lds_ = sraw + 2u * (uint32_t)((ya - y0) * W + (active ? x0 : 0));
             float* out = d + (size_t)ya * W + x0;
             auto fetch = [&](int y, uint2& q, unsigned int& hq) {          // raw quad (+ strip-edge pixel) of row y
                 if (y <= last) {
-                    q = __ldg(reinterpret_cast<const uint2*>(ld));
-                    if (edge_lane) hq = __ldg(reinterpret_cast<const uint16_t*>(ld) + 4);
+                    if (STAGED) {
+                        q = lds_u2(lds_);
+                        if (edge_lane) hq = lds_h(lds_ + 8u);
+                    } else {
+                        q = __ldg(reinterpret_cast<const uint2*>(ld));
+                        if (edge_lane) hq = __ldg(reinterpret_cast<const uint16_t*>(ld) + 4);
+                    }
                 }
-                ld += rowb;
+                ld += rowb; lds_ += (uint32_t)rowb;
             };
             auto right_gray = [&](const NormRow& r, unsigned int hq) -> float {   // gray right of the quad (dx = 0 at the image edge)
                 float gr = __shfl_down_sync(0xffffffffu, r.g[0], 1);
@@ -840,19 +876,28 @@ int t3d_preprocess_train_u16(const uint16_t* raw, int B, int src_h, int src_w, i
     const uint16_t* nsrc = same ? raw : resized;
     const int vec = (dst_w % 4 == 0) && t3d_aligned16(out) && ((reinterpret_cast<uintptr_t>(nsrc) & 7u) == 0);
     if (vec) {
+        constexpr int kStageMax = 24 * 1024;      // staged band bytes: LUT 32 KB + band <= 56 KB per CTA, 4 CTAs per SM
         static bool nattr = false;
         if (!nattr) {
-            T3D_CUDA(cudaFuncSetAttribute(normalize_stats_u16_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kLutMax * 8));
-            T3D_CUDA(cudaFuncSetAttribute(normalize_stats_u16_kernel<3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kLutMax * 8));
-            T3D_CUDA(cudaFuncSetAttribute(normalize_stats_u16_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kLutMax * 8));
-            T3D_CUDA(cudaFuncSetAttribute(normalize_stats_u16_kernel<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kLutMax * 8));
+#define T3D_NORM_ATTR(REP_, ST_) \
+            T3D_CUDA(cudaFuncSetAttribute(normalize_stats_u16_kernel<REP_, ST_, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kLutMax * 8)); \
+            T3D_CUDA(cudaFuncSetAttribute(normalize_stats_u16_kernel<REP_, ST_, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kLutMax * 8 + kStageMax))
+            T3D_NORM_ATTR(1, true); T3D_NORM_ATTR(3, true); T3D_NORM_ATTR(1, false); T3D_NORM_ATTR(3, false);
+#undef T3D_NORM_ATTR
             nattr = true;
         }
         static const int norm_ctas = [] { const char* e = getenv("T3D_NORM_CTAS"); const int v = e ? atoi(e) : 32; return v < 1 ? 1 : v; }();
+        static const bool norm_stage = [] { const char* e = getenv("T3D_NORM_STAGE"); return e ? atoi(e) != 0 : true; }();
         const int nitems = B * kNormBands;
         const int grid = min(nitems, t3d_sm_count() * norm_ctas);
-#define T3D_NORM_LAUNCH(REP_, ST_) T3D_LAUNCH("normalize_stats_u16_kernel", st, (normalize_stats_u16_kernel<REP_, ST_><<<grid, kNormThreads, kLutMax * 8, st>>>( \
-            nsrc, percentiles, out, dst_h, dst_w, grad_stats, w.lut, w.lutmeta, nitems)))
+        const int band_rows = (dst_h + kNormBands - 1) / kNormBands + 1;           // + the row below (gradient statistics)
+        const size_t stage_bytes = (size_t)band_rows * dst_w * sizeof(uint16_t);
+        const bool staged = norm_stage && (dst_w % 8 == 0) && stage_bytes <= (size_t)kStageMax && t3d_aligned16(nsrc);
+#define T3D_NORM_LAUNCH(REP_, ST_) do { \
+            if (staged) T3D_LAUNCH("normalize_stats_u16_kernel", st, (normalize_stats_u16_kernel<REP_, ST_, true><<<grid, kNormThreads, kLutMax * 8 + stage_bytes, st>>>( \
+                nsrc, percentiles, out, dst_h, dst_w, grad_stats, w.lut, w.lutmeta, nitems))); \
+            else T3D_LAUNCH("normalize_stats_u16_kernel", st, (normalize_stats_u16_kernel<REP_, ST_, false><<<grid, kNormThreads, kLutMax * 8, st>>>( \
+                nsrc, percentiles, out, dst_h, dst_w, grad_stats, w.lut, w.lutmeta, nitems))); } while (0)
         if (out_channels == 3) { if (grad_stats) T3D_NORM_LAUNCH(3, true); else T3D_NORM_LAUNCH(3, false); }
         else { if (grad_stats) T3D_NORM_LAUNCH(1, true); else T3D_NORM_LAUNCH(1, false); }
 #undef T3D_NORM_LAUNCH
