@@ -295,6 +295,12 @@ int t3d_sobel_enhance_bwd_params(const float* x, const float* params, const floa
  * vector a data-parallel job all-reduces per step. */
 int t3d_pack_step_result(const float* loss_per_sample, const double* metrics_f64, int B, int n_images,
                          double* out16, void* stream);
+/* t3d_loss_rescale_invalid + t3d_pack_step_result as ONE launch (the tail of a training step,
+ * train_thermal_dustr.py:320,359-360): out16 as above; when some samples are invalid their
+ * gradients are zeroed and the others rescaled by B / n_valid (dconf may be NULL). */
+int t3d_step_epilogue(float* dpred1, float* dpred2, float* dconf1, float* dconf2,
+                      const float* loss_per_sample, const float* loss_batch, const double* metrics_f64,
+                      int B, int H, int W, int n_images, double* out16, void* stream);
 
 #ifdef __cplusplus
 }

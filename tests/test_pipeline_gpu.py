@@ -99,3 +99,29 @@ def test_graph_replay_equals_stream_launches(cuda_device):
         torch.cuda.synchronize()
         assert torch.equal(r, eager)
         assert torch.equal(step.loss_out["dpred1"], grads[0]) and torch.equal(step.loss_out["dconf2"], grads[1])
+
+
+def test_hot_path_step_invalid_sample(cuda_device):
+    """A sample whose loss is not finite is skipped as train_thermal_dustr.py:320 does: it drops out of the mean,
+    its gradients are exact zeros and the other samples' gradients carry 1 / n_valid (loss_finalize_kernel +
+    t3d_step_epilogue do this on the device, without a host round trip)."""
+    from thermal3d_vision_b200.pipeline import HotPathStep
+    B, H, W = 3, 64, 128
+    raw = ref_preprocess.make_raw_frames(2 * B, seed=3, hw=(96, 160))
+    P1, P2, G1, G2, C1, C2, _, _ = ref_loss.make_batch_inputs(B, H, W, seed=23)
+    P1[1, 5, 7, 2] = float("nan")
+    gt_depth = G1[..., 2].clone()
+    T1, T2, mean, rows, valid, grads, metrics = _oracle_step(raw[:B], raw[B:], P1, P2, G1, G2, C1, C2, gt_depth, H, W, False)
+    assert valid.tolist() == [True, False, True]
+    step = HotPathStep(B, H, W, raw_hw=(96, 160), device=cuda_device, **KW)
+    both = torch.from_numpy(raw).to(cuda_device)
+    d = [x.to(cuda_device) for x in (P1, P2, G1, G2, C1, C2, gt_depth)]
+    for _ in range(2):                                      # second call: the workspace counters were reset
+        s = HotPathStep.summarize(step.run_device(both[:B], both[B:], *d).cpu())
+        assert s["n_valid"] == 2.0 and s["n_pairs"] == B
+        assert s["loss"] == pytest.approx(mean, rel=1e-5)
+        for name, got, ref in (("dpred1", step.loss_out["dpred1"], grads[0]), ("dpred2", step.loss_out["dpred2"], grads[1]),
+                               ("dconf1", step.loss_out["dconf1"], grads[2]), ("dconf2", step.loss_out["dconf2"], grads[3])):
+            ref = torch.zeros_like(got.cpu()) if ref is None else ref
+            assert torch.count_nonzero(got[1]) == 0, name
+            torch.testing.assert_close(got.cpu(), ref, rtol=1e-4, atol=1e-6, msg=lambda m: f"{name}: {m}")

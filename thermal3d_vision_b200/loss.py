@@ -195,7 +195,7 @@ def fused_thermal_loss_fwd_bwd(pred_pts1, pred_pts2, gt_pts1, gt_pts2, confidenc
                                thermal_img1=None, thermal_img2=None, *, alpha=0.2, edge_weight=0.5,
                                smoothness_weight=0.3, detail_weight=0.3, multi_scale=True,
                                conf_grad=True, out=None, thermal_stats=None, grad_scale=None,
-                               thermal_replicated=False):
+                               thermal_replicated=False, rescale_invalid=True):
     """Functional (no autograd) fused step on prepared contiguous fp32 CUDA tensors.
 
     Returns dict(per_sample, batch, dpred1, dpred2, dconf1, dconf2); gradients are those of the
@@ -205,7 +205,9 @@ def fused_thermal_loss_fwd_bwd(pred_pts1, pred_pts2, gt_pts1, gt_pts2, confidenc
     ``grad_scale`` (default 1/B) is the a-priori upstream gradient, e.g. 1/(B * world_size) for the mean
     over a data-parallel global batch.  ``thermal_replicated``: promise that the 3 planes of every thermal
     image are bit-identical (ThermalBatch.replicated; what enhance_thermal_contrast always returns): the
-    kernel then reads one plane instead of three, same results.
+    kernel then reads one plane instead of three, same results.  ``rescale_invalid=False`` leaves the
+    validity fix-up of the gradients to the caller (pipeline.HotPathStep: t3d_step_epilogue does it together
+    with the result packing in one launch).
     """
     _lib.require_cuda(pred_pts1, pred_pts2, gt_pts1, gt_pts2, confidences1, confidences2, thermal_img1, thermal_img2)
     B = pred_pts1.shape[0]
@@ -213,7 +215,7 @@ def fused_thermal_loss_fwd_bwd(pred_pts1, pred_pts2, gt_pts1, gt_pts2, confidenc
     ps, bt, dp1, dp2, dc1, dc2 = _launch(
         True, pred_pts1, pred_pts2, gt_pts1, gt_pts2, confidences1, confidences2, thermal_img1, thermal_img2,
         need_dconf, float(alpha), float(edge_weight), float(smoothness_weight), float(detail_weight),
-        bool(multi_scale), (1.0 / B) if grad_scale is None else float(grad_scale), rescale_invalid=True, out=out,
+        bool(multi_scale), (1.0 / B) if grad_scale is None else float(grad_scale), rescale_invalid=bool(rescale_invalid), out=out,
         thermal_stats=thermal_stats, thermal_replicated=thermal_replicated)
     return {"per_sample": ps, "batch": bt, "dpred1": dp1, "dpred2": dp2, "dconf1": dc1, "dconf2": dc2}
 

@@ -129,6 +129,7 @@ class HotPathStep:
                                               out=self.loss_out, thermal_stats=stats,
                                               thermal_replicated=True,   # preprocess_thermal_batch wrote 3 identical planes
                                               grad_scale=_dist.global_grad_scale(self.B) if self.distributed else None,
+                                              rescale_invalid=False,     # done by t3d_step_epilogue below
                                               **self.kw)
         i = self.calls & 1
         self.calls += 1
@@ -136,9 +137,12 @@ class HotPathStep:
             self.pending[i].wait()                 # the all-reduce of step - 2 is done with this vector
             self.pending[i] = None
         r = self.results[i]
-        rc = _lib.lib().t3d_pack_step_result(_lib.ptr(lo["per_sample"]), _lib.ptr(me["metrics_f64"]), self.B, self.B,
-                                             _lib.ptr(r), _lib.current_stream_ptr())
-        _lib.check(rc, "t3d_pack_step_result")
+        # validity fix-up of the gradients + packing of the step's scalars: one launch
+        rc = _lib.lib().t3d_step_epilogue(_lib.ptr(lo["dpred1"]), _lib.ptr(lo["dpred2"]), _lib.ptr(lo["dconf1"]),
+                                          _lib.ptr(lo["dconf2"]), _lib.ptr(lo["per_sample"]), _lib.ptr(lo["batch"]),
+                                          _lib.ptr(me["metrics_f64"]), self.B, self.H, self.W, self.B,
+                                          _lib.ptr(r), _lib.current_stream_ptr())
+        _lib.check(rc, "t3d_step_epilogue")
         if self.distributed:
             self.pending[i] = _dist.all_reduce_result(r, async_op=True)
         self.result = r
