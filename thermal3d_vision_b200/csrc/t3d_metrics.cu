@@ -90,7 +90,7 @@ __global__ void __launch_bounds__(1024, 1) metrics_sample_kernel(const PixelSrc 
                                                                  unsigned int* __restrict__ bracket,
                                                                  int* __restrict__ counters) {
     __shared__ unsigned int key[kSample];
-    __shared__ t3d_select::Smem sm;
+    __shared__ t3d_select::Smem sm, sm2;
     __shared__ int cnt;
     const int a = blockIdx.x, b = blockIdx.y, tid = threadIdx.x, n = s.H * s.W;
     const float* g = s.gt + (size_t)b * s.gt_h * s.gt_w;
@@ -100,33 +100,74 @@ __global__ void __launch_bounds__(1024, 1) metrics_sample_kernel(const PixelSrc 
     if (a == 0 && tid < 8) counters[8 * b + tid] = 0;        // this image's counters for the extraction pass
     __syncthreads();
     int c = 0;
+    // n >= kSample: 1024 evenly strided quads of 4 consecutive pixels (they share their cache lines: a
+    // quarter of the scattered DRAM reads); smaller images: every pixel exactly once.
+    // All of a thread's samples are loaded before the first one is used: ONE exposed DRAM latency.
+    constexpr int kQ = kSample / 1024;
+    float gvs[kQ], pvs[kQ]; unsigned char mks[kQ];
 #pragma unroll
-    for (int q = 0; q < kSample / 1024; ++q) {
+    for (int q = 0; q < kQ; ++q) {
         const int k = q * 1024 + tid;
-        // n >= kSample: 1024 evenly strided quads of 4 consecutive pixels (they share their cache lines: a
-        // quarter of the scattered DRAM reads); smaller images: every pixel exactly once
-        const int i = (n >= kSample) ? 4 * (int)(((long long)(k >> 2) * (n >> 2)) / (kSample >> 2)) + (k & 3) : k;
-        unsigned int kk = 0xffffffffu;                             // sentinel: not part of the sample
-        if (i < n) {
-            float gv, pv; bool ok;
-            read_pixel(s, g, p, m, i, gv, pv, ok);
-            const float v = (a == 0) ? gv : pv;
-            if (ok && !isnan(v)) { kk = t3d_select::float_key(v); ++c; }
+        const int i0 = (n >= kSample) ? 4 * (int)(((long long)(k >> 2) * (n >> 2)) / (kSample >> 2)) + (k & 3) : k;
+        const int i = min(i0, n - 1);
+        size_t gi = (size_t)i;
+        if (s.resample) {   // cv2 INTER_NEAREST (utils/evaluate_depth_metrics.py:321-323), as read_pixel
+            const int y = i / s.W, x = i - y * s.W;
+            const int sx = min((int)floor(__dmul_rn((double)x, s.fx)), s.gt_w - 1);
+            const int sy = min((int)floor(__dmul_rn((double)y, s.fy)), s.gt_h - 1);
+            gi = (size_t)sy * s.gt_w + sx;
         }
+        gvs[q] = __ldg(g + gi);
+        pvs[q] = __ldg(p + (size_t)i * s.pred_stride);
+        mks[q] = m ? m[i] : (unsigned char)1;
+    }
+#pragma unroll
+    for (int q = 0; q < kQ; ++q) {
+        const int k = q * 1024 + tid;
+        const int i0 = (n >= kSample) ? 4 * (int)(((long long)(k >> 2) * (n >> 2)) / (kSample >> 2)) + (k & 3) : k;
+        const bool ok = (i0 < n) && (m ? (mks[q] != 0) : (gvs[q] > 0.f && isfinite(gvs[q])));     // utils/metrics.py:27
+        const float v = (a == 0) ? gvs[q] : pvs[q];
+        unsigned int kk = 0xffffffffu;                             // sentinel: not part of the sample
+        if (ok && !isnan(v)) { kk = t3d_select::float_key(v); ++c; }
         key[k] = kk;
     }
     c = __reduce_add_sync(0xffffffffu, c);
     if ((tid & 31) == 0) atomicAdd(&cnt, c);
     __syncthreads();
-    // two order statistics of the sample, +-5 sigma around the sample median rank (radix select in smem)
+    // two sample order statistics 7 sigma either side of the sample median rank, to 22 bits of the key (radix
+    // select in smem: 11 + 11 bits; the pass over the top 11 bits is shared by the two ranks).  lo is rounded
+    // down and hi up to the 22-bit prefix: the bracket only has to CONTAIN the median (the extraction pass counts
+    // what lies below it and the select among the candidates is exact), not to be a sample statistic itself.
     const int mm = cnt;
     unsigned int lo = 1u, hi = 0u;                                 // no bracket -> fallback
     if (mm >= 64) {                                                // block-uniform
         const int d = (int)ceilf(3.5f * sqrtf((float)mm)) + 2;      // +-7 sigma: neighbouring samples are correlated
         const int mid = mm / 2, rl = mid - d, rh = mid + d;
-        auto get = [&](int i, float* v) { const unsigned int k = key[i]; *v = t3d_select::key_float(k); return k != 0xffffffffu; };
-        lo = (rl <= 0) ? 0u : t3d_select::float_key(t3d_select::select_rank(sm, kSample, (unsigned)rl, get));
-        hi = (rh >= mm - 1) ? 0xfffffffeu : t3d_select::float_key(t3d_select::select_rank(sm, kSample, (unsigned)rh, get));
+        const bool need_lo = rl > 0, need_hi = rh < mm - 1;
+        lo = 0u; hi = 0xfffffffeu;
+        unsigned int kq[kQ];
+#pragma unroll
+        for (int q = 0; q < kQ; ++q) kq[q] = key[q * 1024 + tid];
+        for (int i = tid; i < t3d_select::kBins; i += 1024) { sm.hist[i] = 0u; sm2.hist[i] = 0u; }
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < kQ; ++q) if (kq[q] != 0xffffffffu) atomicAdd(&sm.hist[kq[q] >> 21], 1u);
+        __syncthreads();
+        unsigned int b_lo = 0u, r_lo = 0u, b_hi = 0u, r_hi = 0u;
+        if (need_lo) { t3d_select::pick_bin(sm, (unsigned)rl, 2048); b_lo = sm.sel_bin; r_lo = sm.sel_rank; __syncthreads(); }
+        if (need_hi) { t3d_select::pick_bin(sm, (unsigned)rh, 2048); b_hi = sm.sel_bin; r_hi = sm.sel_rank; __syncthreads(); }
+        for (int i = tid; i < t3d_select::kBins; i += 1024) sm.hist[i] = 0u;
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < kQ; ++q) {
+            if (kq[q] == 0xffffffffu) continue;
+            const unsigned int top = kq[q] >> 21, nxt = (kq[q] >> 10) & 2047u;
+            if (need_lo && top == b_lo) atomicAdd(&sm.hist[nxt], 1u);
+            if (need_hi && top == b_hi) atomicAdd(&sm2.hist[nxt], 1u);
+        }
+        __syncthreads();
+        if (need_lo) { t3d_select::pick_bin(sm, r_lo, 2048); lo = (b_lo << 21) | (sm.sel_bin << 10); __syncthreads(); }
+        if (need_hi) { t3d_select::pick_bin(sm2, r_hi, 2048); hi = (b_hi << 21) | (sm2.sel_bin << 10) | 0x3ffu; hi = min(hi, 0xfffffffeu); }
     }
     if (tid == 0) { bracket[4 * b + 2 * a] = lo; bracket[4 * b + 2 * a + 1] = hi; }
 }
@@ -349,7 +390,8 @@ constexpr int kMedThreads = t3d_select::kThreads;
 // grid (2, B): blockIdx.x = stream (0 = gt, 1 = pred); writes medians[b][stream]
 __global__ void __launch_bounds__(kMedThreads, 1)
 median_scale_kernel(const float* __restrict__ vz, const float* __restrict__ vg, const int* __restrict__ counters,
-                    const unsigned int* __restrict__ cand, int n, int median_scaling, float* __restrict__ medians) {
+                    const unsigned int* __restrict__ cand, const unsigned int* __restrict__ bracket, int n,
+                    int median_scaling, float* __restrict__ medians) {
     extern __shared__ unsigned int skeys[];                       // kCandCap keys
     __shared__ t3d_select::Smem sm;
     const int a = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
@@ -364,14 +406,17 @@ median_scale_kernel(const float* __restrict__ vz, const float* __restrict__ vg, 
             const bool bracket_ok = (c[3] == 0) && ((int)r0 >= lt) && ((int)r1 < lt + nc) && nc <= kCandCap;
             float x0, x1;
             if (bracket_ok) {
+                // candidates as offsets from the bracket's lower key (all lie in [lo, hi]): the select then runs
+                // over the ~20 significant bits of the bracket width instead of 32 bits whose top 11 are shared
                 const unsigned int* src = cand + ((size_t)b * 2 + a) * kCandCap;
-                for (int q = tid; q < nc; q += kMedThreads) skeys[q] = src[q];
+                const unsigned int lo = bracket[4 * b + 2 * a], width = bracket[4 * b + 2 * a + 1] - lo;
+                const int nbits = 32 - __clz(width | 1u);
+                for (int q = tid; q < nc; q += kMedThreads) skeys[q] = src[q] - lo;
                 __syncthreads();
-                auto get = [&](int i, float* v) { *v = t3d_select::key_float(skeys[i]); return true; };
-                x0 = t3d_select::select_rank(sm, nc, r0 - lt, get);
+                const unsigned int k0 = t3d_select::select_rank_offsets(sm, skeys, nc, r0 - lt, nbits);
+                x0 = t3d_select::key_float(k0 + lo);
                 x1 = x0;
                 if (r1 != r0) {      // x_(r0+1): x0 again if it has duplicates past rank r0, else the next larger key
-                    const unsigned int k0 = t3d_select::float_key(x0);
                     unsigned int le = 0, nxt = 0xffffffffu;
                     for (int q = tid; q < nc; q += kMedThreads) {
                         const unsigned int k = skeys[q];
@@ -384,7 +429,7 @@ median_scale_kernel(const float* __restrict__ vz, const float* __restrict__ vg, 
                     le = 0; nxt = 0xffffffffu;
                     for (int w = 0; w < kMedThreads / 32; ++w) { le += sm.hist[w]; nxt = min(nxt, sm.hist[64 + w]); }
                     __syncthreads();
-                    x1 = (le > r1 - lt) ? x0 : t3d_select::key_float(nxt);
+                    x1 = (le > r1 - lt) ? x0 : t3d_select::key_float(nxt + lo);
                 }
             } else {                                              // fallback: full radix select, same result
                 const float* v = (a == 0 ? vg : vz) + (size_t)b * n;
@@ -523,12 +568,14 @@ metrics_sum_kernel(const float* __restrict__ vz, const float* __restrict__ vg,
 // ------------------------------------------------------------------ M4: finalize
 // out[b] = abs_rel, sq_rel, rmse, rmse_log, a1, a2, a3, n_valid  (float32 like numpy's results;
 // out_f64 keeps a_k = count / n in fp64 as numpy returns them)
-__global__ void metrics_finalize_kernel(const double* __restrict__ partials, const int* __restrict__ counters,
+__global__ void __launch_bounds__(32 * kNPart) metrics_finalize_kernel(const double* __restrict__ partials, const int* __restrict__ counters,
                                         int chunks, float* __restrict__ out, double* __restrict__ out_f64) {
-    const int b = blockIdx.x, k = threadIdx.x;
-    if (k >= kNPart) return;
+    // one warp per metric: lane c owns the chunks c, c + 32, ... (all loads in flight at once), fixed butterfly
+    const int b = blockIdx.x, k = threadIdx.x >> 5, lane = threadIdx.x & 31;
     double s = 0;
-    for (int c = 0; c < chunks; ++c) s += partials[((size_t)b * chunks + c) * kNPart + k];
+    for (int c = lane; c < chunks; c += 32) s += partials[((size_t)b * chunks + c) * kNPart + k];
+    s = warp_sum(s);
+    if (lane != 0) return;
     const int nv = counters[8 * b];
     const double qnan = __longlong_as_double(0x7ff8000000000000LL);
     if (counters[8 * b + 2] > 0 && k < 4) s = qnan;                              // a selected NaN GT poisons every mean
@@ -703,14 +750,14 @@ int t3d_depth_metrics(const float* pred, int pred_stride, int pred_offset,
             src, pred_offset, w.vz, w.vg, w.counters, w.bracket, w.cand));
     float* medians = out_medians ? out_medians : w.scale;       // [B][2]: median(gt), median(pred)
     T3D_LAUNCH("median_scale_kernel", st, median_scale_kernel<<<dim3(2, B), kMedThreads, kCandCap * sizeof(unsigned int), st>>>(
-        w.vz, w.vg, w.counters, w.cand, n, median_scaling, medians));
+        w.vz, w.vg, w.counters, w.cand, w.bracket, n, median_scaling, medians));
     if (mask)       // a caller-supplied mask may select non-positive / non-finite GT: literal formulas
         T3D_LAUNCH("metrics_sum_kernel", st, metrics_sum_kernel<true><<<g, kChunkThreads, 0, st>>>(
             w.vz, w.vg, medians, w.counters, median_scaling, n, chunks, w.partials));
     else
         T3D_LAUNCH("metrics_sum_kernel", st, metrics_sum_kernel<false><<<g, kChunkThreads, 0, st>>>(
             w.vz, w.vg, medians, w.counters, median_scaling, n, chunks, w.partials));
-    T3D_LAUNCH("metrics_finalize_kernel", st, metrics_finalize_kernel<<<B, 32, 0, st>>>(w.partials, w.counters, chunks, out, out_f64));
+    T3D_LAUNCH("metrics_finalize_kernel", st, metrics_finalize_kernel<<<B, 32 * kNPart, 0, st>>>(w.partials, w.counters, chunks, out, out_f64));
     return T3D_OK;
 }
 

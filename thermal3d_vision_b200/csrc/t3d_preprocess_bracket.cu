@@ -153,23 +153,50 @@ bracket_sample_kernel(const uint16_t* __restrict__ src, int sh, int sw, int dh, 
     for (int i = tid; i < 2 * kBrStride; i += 1024) brhist[(size_t)b * 2 * kBrStride + i] = 0u;
     if (b == 0 && tid == 0) brhist[(size_t)B * 2 * kBrStride] = 0u;
     const uint16_t* s = src + (size_t)b * sh * sw;
+    // 1024 jittered-stride locations x 4 consecutive pixels: the 4 pixels share their source cache lines
+    // (a quarter of the scattered DRAM reads of 4096 single pixels); a plain stride would alias with
+    // column-periodic images.  Neighbours are correlated, hence the wider (9 sigma) windows below.
+    // All taps of a thread's samples are loaded before the first one is used: ONE exposed DRAM latency.
+    constexpr int kQ = kSamp / 1024;
+    Tap ty[kQ], tx[kQ];
+    unsigned int raw[kQ][4];
 #pragma unroll
-    for (int q = 0; q < kSamp / 1024; ++q) {
-        const int k = q * 1024 + tid;
-        if (k < m) {
-            // 1024 jittered-stride locations x 4 consecutive pixels: the 4 pixels share their source cache lines
-            // (a quarter of the scattered DRAM reads of 4096 single pixels); a plain stride would alias with
-            // column-periodic images.  Neighbours are correlated, hence the wider (9 sigma) windows below.
-            int i = k;
-            if (n > kSamp) {
-                const int l = k >> 2, qstride = (n >> 2) / (kSamp >> 2);
-                i = 4 * (l * qstride + (int)((((unsigned)l * 2654435761u) >> 8) % (unsigned)qstride)) + (k & 3);
-            }
-            unsigned int v;
-            if (same) v = __ldg(s + i);
-            else { const int y = i / dw, x = i - y * dw; v = bilinear_u16(s, sw, linear_tap(y, sh, scy), linear_tap(x, sw, scx)); }
-            key[k] = (short)v;                               // bit pattern of the u16
+    for (int q = 0; q < kQ; ++q) {
+        const int k = min(q * 1024 + tid, m - 1);
+        int i = k;
+        if (n > kSamp) {
+            const int l = k >> 2, qstride = (n >> 2) / (kSamp >> 2);
+            i = 4 * (l * qstride + (int)((((unsigned)l * 2654435761u) >> 8) % (unsigned)qstride)) + (k & 3);
         }
+        if (same) {
+            raw[q][0] = __ldg(s + i);
+        } else {
+            const int y = i / dw, x = i - y * dw;
+            ty[q] = linear_tap(y, sh, scy); tx[q] = linear_tap(x, sw, scx);
+            const uint16_t* r0 = s + (size_t)ty[q].s0 * sw;
+            const uint16_t* r1 = s + (size_t)ty[q].s1 * sw;
+            raw[q][0] = __ldg(r0 + tx[q].s0); raw[q][1] = __ldg(r0 + tx[q].s1);
+            raw[q][2] = __ldg(r1 + tx[q].s0); raw[q][3] = __ldg(r1 + tx[q].s1);
+        }
+    }
+    if (!same) {
+        // make every use depend on every load, or ptxas schedules the first conversion (and its stall) between
+        // the loads of consecutive samples; raw values are u16, so the fold can never equal the constant
+        unsigned int fold = 0u;
+#pragma unroll
+        for (int q = 0; q < kQ; ++q) fold |= raw[q][0] | raw[q][1] | raw[q][2] | raw[q][3];
+        if (fold == 0xffffffffu) raw[0][0] = 0u;
+    }
+#pragma unroll
+    for (int q = 0; q < kQ; ++q) {
+        const int k = q * 1024 + tid;
+        unsigned int v = raw[q][0];
+        if (!same) {                                         // bilinear_u16 on the loaded taps
+            const float h0 = __fadd_rn(__fmul_rn((float)raw[q][0], tx[q].c0), __fmul_rn((float)raw[q][1], tx[q].c1));
+            const float h1 = __fadd_rn(__fmul_rn((float)raw[q][2], tx[q].c0), __fmul_rn((float)raw[q][3], tx[q].c1));
+            v = sat_u16(__fadd_rn(__fmul_rn(h0, ty[q].c0), __fmul_rn(h1, ty[q].c1)));
+        }
+        if (k < m) key[k] = (short)v;                        // bit pattern of the u16
     }
     __syncthreads();
     // sample ranks 9 sigma either side of each quantile's rank

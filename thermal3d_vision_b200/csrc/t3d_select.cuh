@@ -90,4 +90,31 @@ __device__ float select_rank(Smem& sm, int n, unsigned int rank, Get get) {
     return key_float(prefix);
 }
 
+// Exact k-th smallest (0-based) of n uint32 values < 2^nbits held in shared memory, `vals[i]` = key - base.
+// Two (nbits <= 22) or three 11-bit passes from bit nbits - 1 down.  Selecting on the OFFSET inside a narrow
+// bracket keeps the first pass well spread: on the raw keys every candidate shares the top bits and all
+// shared-memory atomics of the first pass hit one bin (serialised).
+__device__ __forceinline__ uint32_t select_rank_offsets(Smem& sm, const unsigned int* vals, int n, unsigned int rank, int nbits) {
+    const int tid = threadIdx.x;
+    uint32_t prefix = 0, mask = 0;
+    int hi = nbits;                                   // bits [hi, 32) are resolved (zero above nbits)
+    while (hi > 0) {
+        const int w = hi < 11 ? hi : 11, sh = hi - w, nb = 1 << w;
+        for (int i = tid; i < nb; i += kThreads) sm.hist[i] = 0u;
+        __syncthreads();
+        for (int i = tid; i < n; i += kThreads) {
+            const uint32_t k = vals[i];
+            if ((k & mask) == prefix) atomicAdd(&sm.hist[(k >> sh) & (nb - 1)], 1u);
+        }
+        __syncthreads();
+        pick_bin(sm, rank, nb);
+        prefix |= sm.sel_bin << sh;
+        mask |= (uint32_t)(nb - 1) << sh;
+        rank = sm.sel_rank;
+        __syncthreads();
+        hi = sh;
+    }
+    return prefix;
+}
+
 }  // namespace t3d_select
