@@ -202,6 +202,10 @@ int t3d_preprocess_train_u16(const uint16_t* raw, int B, int src_h, int src_w, i
                              float* grad_stats, void* workspace, size_t workspace_bytes, void* stream);
 /* Number of statistic partials per frame written to grad_stats (0: not available for this shape). */
 int t3d_preprocess_stats_tiles(int dst_h, int dst_w);
+/* Scheduling hint (process-wide, default 0): shared != 0 says the caller runs other kernels
+ * concurrently with t3d_preprocess_train_u16 (another stream), so its issue-bound resize
+ * kernel leaves registers on every SM for them.  Results do not depend on it. */
+int t3d_preprocess_set_shared(int shared);
 
 /* Diagnostics of the last t3d_preprocess_train_u16 call with hist == NULL on `workspace`: the number of frames
  * whose percentile ranks fell outside the sampled value windows and were found by the exact per-frame select

@@ -9,6 +9,7 @@
 // numpy/OpenCV (IPP off): no FMA contraction in the interpolation, fp64 in
 // the normalisation, integer histograms.
 #include "t3d_preprocess_internal.cuh"
+#include <atomic>
 #include "t3d_select.cuh"
 
 #include <stdlib.h>
@@ -919,6 +920,9 @@ int t3d_preprocess_fallback_count(const void* workspace, int B, int dst_h, int d
     return T3D_OK;
 }
 
+static std::atomic<int> g_pre_shared{0};
+int t3d_preprocess_set_shared(int shared) { g_pre_shared.store(shared ? 1 : 0, std::memory_order_relaxed); return T3D_OK; }
+
 int t3d_preprocess_stats_tiles(int dst_h, int dst_w) {
     return (dst_h >= 1 && dst_w >= 4 && dst_w % 4 == 0) ? kNormBands : 0;
 }
@@ -991,3 +995,5 @@ int t3d_interp_bilinear_f32(const float* src, float* dst, int B, int channels_la
 }
 
 }  // extern "C"
+
+bool t3d_preprocess_shared() { return g_pre_shared.load(std::memory_order_relaxed) != 0; }

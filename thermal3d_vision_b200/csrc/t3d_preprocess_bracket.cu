@@ -512,20 +512,24 @@ int t3d_launch_bracket_percentiles(const uint16_t* raw, int B, int sh, int sw, i
         const size_t smem = (size_t)kRzWarps * kRing * slot_bytes;
         const bool dense = sh <= 2 * dh;
         if (smem <= 96 * 1024 && slot_px <= 512 && (long long)B * nstrips * dh < (1ll << 31)) {
-            static int ctas_per_sm[2] = {0, 0};
+            static int max_ctas[2] = {0, 0};
             static size_t attr_smem[2] = {0, 0};
             const int di = dense ? 1 : 0;
             const void* fn = dense ? (const void*)resize_march_kernel<true> : (const void*)resize_march_kernel<false>;
-            if (smem > attr_smem[di] || ctas_per_sm[di] == 0) {
+            if (smem > attr_smem[di] || max_ctas[di] == 0) {
                 T3D_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                 attr_smem[di] = smem;
-                T3D_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm[di], fn, kRzThreads, smem));
-                if (ctas_per_sm[di] < 1) ctas_per_sm[di] = 1;
-                const char* e = getenv("T3D_RZ_CTAS");          // tuning knob: leave room for a concurrent kernel
-                if (e && atoi(e) >= 1) ctas_per_sm[di] = min(ctas_per_sm[di], atoi(e));
+                T3D_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&max_ctas[di], fn, kRzThreads, smem));
+                if (max_ctas[di] < 1) max_ctas[di] = 1;
             }
+            // Shared machine (t3d_preprocess_set_shared(1): the caller runs other kernels concurrently, as
+            // pipeline.HotPathStep does with the metric pipeline): 2 of the 3 CTAs per SM that fit -- the registers
+            // left over let the memory-bound kernels of the other stream co-reside with this issue-bound one
+            // (436.6 -> 432.9 us per step); alone, 3 CTAs per SM are faster (56.7 vs 65.8 us).
+            static const int env_ctas = [] { const char* e = getenv("T3D_RZ_CTAS"); return (e && atoi(e) >= 1) ? atoi(e) : 0; }();
+            const int ctas = min(max_ctas[di], env_ctas ? env_ctas : (t3d_preprocess_shared() ? 2 : max_ctas[di]));
             const long long total = (long long)B * nstrips * dh;
-            long long grid = (long long)t3d_sm_count() * ctas_per_sm[di];
+            long long grid = (long long)t3d_sm_count() * ctas;
             if (grid * kRzWarps > total) grid = (total + kRzWarps - 1) / kRzWarps;
             if (dense)
                 T3D_LAUNCH("resize_march_kernel", st, resize_march_kernel<true><<<(unsigned)grid, kRzThreads, smem, st>>>(

@@ -72,6 +72,8 @@ __device__ __forceinline__ void build_norm_lut(int b, double p2, double p98, int
     if (threadIdx.x == 0) lutmeta[b] = make_int2(lom1, use ? range : 0);
 }
 
+bool t3d_preprocess_shared();      // t3d_preprocess_set_shared(): other kernels run concurrently with the preprocessing
+
 // ------------------------------------------------------------------ percentile brackets (t3d_preprocess_bracket.cu)
 constexpr int kBrBins = 2048;        // bins of each windowed histogram (p2 window, p98 window)
 constexpr int kBrSlots = kBrBins + 32;  // + the below / above slot (t3d_preprocess_bracket.cu: kBrStride)

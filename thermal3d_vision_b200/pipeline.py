@@ -66,6 +66,7 @@ class HotPathStep:
         self.fork = torch.cuda.Event()
         self.joins = [torch.cuda.Event() for _ in range(2)]
         self.overlap = True
+        self._shared_hint = None
         # percentiles from sampled value windows (bit-identical to the exact-histogram path, no per-pixel atomic);
         # set True to also get the 65 536-bin histograms of the resized frames in pre_both["histogram"]
         self.histogram = False
@@ -113,6 +114,9 @@ class HotPathStep:
             b = _pre.preprocess_thermal_batch(raw2, size, path="train", out=self.pre_out[1], histogram=self.histogram)
             return (a.thermal, b.thermal), (a.grad_stats, b.grad_stats)
 
+        if self.overlap != self._shared_hint:       # the metric pipeline shares the SMs with the preprocessing
+            self._shared_hint = self.overlap
+            _lib.lib().t3d_preprocess_set_shared(1 if self.overlap else 0)
         if self.overlap:
             self.fork.record(main)
             with torch.cuda.stream(self.side[1]):           # depth metrics (Z of pred1 read in place)
@@ -269,6 +273,7 @@ class EvalStep:
         self.acc = _metrics.MetricAccumulator(dev)
         self.side = torch.cuda.Stream(device=dev, priority=-1)
         self.fork, self.join = torch.cuda.Event(), torch.cuda.Event()
+        lib.t3d_preprocess_set_shared(1)            # the metric pipeline runs beside the preprocessing (run_batch)
 
     def algorithmic_bytes(self) -> int:
         """Per batch: u16 frame in + 3 fp32 planes out, AoS pointmap + GT depth in."""
