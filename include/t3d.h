@@ -57,6 +57,9 @@ uint64_t t3d_launch_count(void);
  * time and the number of launches timed. */
 int t3d_profile_begin(const char* kernel_name_substr, int max_launches);
 int t3d_profile_end(double* total_ms, int* launches);
+/* After t3d_profile_begin: bracket only every every_nth-th matching launch (the two event records per
+ * launch cost a few microseconds of stream time; a sample keeps the timed region close to an untimed run). */
+int t3d_profile_stride(int every_nth);
 /* Developer instrumentation: call BEFORE t3d_profile_end.  Start / stop times
  * (ms, relative to the first timed launch's start event) and names of the
  * launches timed since t3d_profile_begin; `names` holds cap strings of

@@ -29,6 +29,7 @@ _SIGNATURES = {
     "t3d_launch_count": (C.c_uint64, []),
     "t3d_profile_begin": (C.c_int, [C.c_char_p, C.c_int]),
     "t3d_profile_end": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_int)]),
+    "t3d_profile_stride": (C.c_int, [C.c_int]),
     "t3d_profile_timeline": (C.c_int, [C.c_char_p, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_int,
                                        C.POINTER(C.c_int)]),
     "t3d_loss_workspace_bytes": (C.c_size_t, [C.c_int] * 4),
@@ -123,8 +124,10 @@ def launch_count() -> int:
     return int(lib().t3d_launch_count())
 
 
-def profile_begin(kernel_substr: str, max_launches: int = 4096) -> None:
+def profile_begin(kernel_substr: str, max_launches: int = 4096, every_nth: int = 1) -> None:
     check(lib().t3d_profile_begin(kernel_substr.encode(), int(max_launches)), "t3d_profile_begin")
+    if every_nth > 1:
+        check(lib().t3d_profile_stride(int(every_nth)), "t3d_profile_stride")
 
 
 def profile_end():

@@ -38,6 +38,7 @@ struct Prof {
     std::vector<cudaEvent_t> ev;   // start/stop pairs
     std::vector<const char*> names; // kernel name of each pair (string literals)
     int used = 0, cap = 0;
+    int stride = 1, seen = 0;       // only every stride-th matching launch is bracketed
 } g_prof;
 }  // namespace
 
@@ -45,6 +46,7 @@ bool t3d_prof_before(const char* name, cudaStream_t st) {
     if (!g_prof.active) return false;
     std::lock_guard<std::mutex> lk(g_prof.mu);
     if (!g_prof.active || g_prof.used >= g_prof.cap || !strstr(name, g_prof.pattern)) return false;
+    if ((g_prof.seen++ % g_prof.stride) != 0) return false;
     cudaEventRecord(g_prof.ev[2 * g_prof.used], st);
     g_prof.names[g_prof.used] = name;
     return true;
@@ -94,6 +96,14 @@ int t3d_profile_begin(const char* kernel_name_substr, int max_launches) {
     strncpy(g_prof.pattern, kernel_name_substr, sizeof(g_prof.pattern) - 1);
     g_prof.pattern[sizeof(g_prof.pattern) - 1] = 0;
     g_prof.used = 0; g_prof.cap = max_launches; g_prof.active = true;
+    g_prof.stride = 1; g_prof.seen = 0;
+    return T3D_OK;
+}
+
+int t3d_profile_stride(int every_nth) {
+    T3D_REQUIRE(every_nth >= 1, "bad stride");
+    std::lock_guard<std::mutex> lk(g_prof.mu);
+    g_prof.stride = every_nth;
     return T3D_OK;
 }
 
