@@ -10,8 +10,8 @@ fwd+bwd over B pointmap pairs -> pointmap->depth + depth metrics of B frames
 (thermal3d_vision_b200.pipeline.HotPathStep).  Workload = BASELINE.json
 configs[2] ("DUSt3R-512 shape: batch=64 512x384 pointmap pairs"), the
 configuration the metric's 70 %-of-HBM target is quoted on; per-rank batch is
-fixed as N grows (weak scaling, sharded by image, one packed NCCL all-reduce
-of 16 doubles per step).  One JSON line on stdout (rank 0).
+fixed as N grows (weak scaling, sharded by image; the 16 packed doubles of a step
+are exchanged over NVLink peer memory by the step's own epilogue kernel).  One JSON line on stdout (rank 0).
 """
 from __future__ import annotations
 
@@ -58,7 +58,7 @@ def config_dict(a, world):
     return {"workload": workload_name(a), "per_rank_batch": a.batch, "global_batch": a.batch * world,
             "pointmap_hw": [a.height, a.width], "raw_frame_hw": [512, 640], "multi_scale": bool(a.multi_scale),
             "edge_weight": EDGE_W, "smoothness_weight": SMOOTH_W, "detail_weight": DETAIL_W, "alpha": ALPHA,
-            "parallelism": f"dp{world} (sharded by image, one packed 128-byte all-reduce per step)",
+            "parallelism": f"dp{world} (sharded by image; per step one 128-byte exchange of the packed scalars over NVLink peer memory, no NCCL call)",
             "l2_policy": "inputs_exceed_l2 (1.2 GB of inputs per step vs 126 MB L2; no flush needed)"}
 
 

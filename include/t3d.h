@@ -308,6 +308,22 @@ int t3d_pack_step_result(const float* loss_per_sample, const double* metrics_f64
 int t3d_step_epilogue(float* dpred1, float* dpred2, float* dconf1, float* dconf2,
                       const float* loss_per_sample, const float* loss_batch, const double* metrics_f64,
                       int B, int H, int W, int n_images, double* out16, void* stream);
+/* Data-parallel variant over peer memory (one process per GPU, one NVLink / NVSwitch node; replaces the per-step
+ * NCCL all-reduce of out16 -- SURVEY.md 8e): every rank owns a mailbox of t3d_mailbox_bytes() zero-initialised bytes
+ * that its peers can address (CUDA IPC / symmetric memory); peer_mailboxes = HOST array of the `world` device
+ * addresses under which THIS process sees them, in rank order.  t3d_step_epilogue_peers does what
+ * t3d_step_epilogue does and also stores the rank's 16 doubles into every rank's mailbox (step = 0, 1, 2, ...);
+ * t3d_mailbox_reduce waits (on the device) for the world's vectors of `step` and adds them in rank order into
+ * out16.  Per rank, reduce(step) must be enqueued before epilogue(step + 1) -- that is what makes the two
+ * alternating slots safe to reuse. */
+#define T3D_MAX_PEERS 16
+size_t t3d_mailbox_bytes(void);
+int t3d_step_epilogue_peers(float* dpred1, float* dpred2, float* dconf1, float* dconf2,
+                            const float* loss_per_sample, const float* loss_batch, const double* metrics_f64,
+                            int B, int H, int W, int n_images, double* out16_local,
+                            const unsigned long long* peer_mailboxes, int world, int rank,
+                            unsigned long long step, void* stream);
+int t3d_mailbox_reduce(const void* my_mailbox, int world, unsigned long long step, double* out16, void* stream);
 
 #ifdef __cplusplus
 }

@@ -125,3 +125,40 @@ def test_hot_path_step_invalid_sample(cuda_device):
             ref = torch.zeros_like(got.cpu()) if ref is None else ref
             assert torch.count_nonzero(got[1]) == 0, name
             torch.testing.assert_close(got.cpu(), ref, rtol=1e-4, atol=1e-6, msg=lambda m: f"{name}: {m}")
+
+
+def test_peer_mailbox_exchange_world_of_one(cuda_device):
+    """t3d_step_epilogue_peers + t3d_mailbox_reduce (the data-parallel exchange over peer memory) with this process as
+    the only rank: the reduced vector is the packed vector of t3d_step_epilogue, step after step (both parities of
+    the mailbox get reused); with two "ranks" pointing at the same mailbox the slots add up in rank order."""
+    import ctypes as C
+    from thermal3d_vision_b200 import _lib
+    lib = _lib.lib()
+    B, H, W = 3, 8, 16
+    g = torch.Generator().manual_seed(5)
+    per_sample = torch.rand(B, 8, generator=g).to(cuda_device)
+    per_sample[:, 5] = torch.tensor([1.0, 0.0, 1.0])                         # sample 1 invalid
+    batch = torch.tensor([0, 0, 0, 0, 0, 2.0, float(B), 0], dtype=torch.float32, device=cuda_device)
+    m64 = torch.rand(B, 8, generator=g, dtype=torch.float64).to(cuda_device)
+    grads = [torch.ones(B, H, W, 3, device=cuda_device), torch.ones(B, H, W, 3, device=cuda_device),
+             torch.ones(B, H, W, device=cuda_device), torch.ones(B, H, W, device=cuda_device)]
+    ref = torch.zeros(16, dtype=torch.float64, device=cuda_device)
+    st = _lib.current_stream_ptr()
+    _lib.check(lib.t3d_step_epilogue(*[_lib.ptr(x) for x in grads], _lib.ptr(per_sample), _lib.ptr(batch), _lib.ptr(m64),
+                                     B, H, W, B, _lib.ptr(ref), st), "t3d_step_epilogue")
+    assert torch.count_nonzero(grads[0][1]) == 0 and torch.all(grads[0][0] == 1.5)    # fix-up: B / n_valid = 3 / 2
+    mailbox = torch.zeros(int(lib.t3d_mailbox_bytes()) // 8, dtype=torch.float64, device=cuda_device)
+    batch_ok = batch.clone(); batch_ok[5] = float(B)                              # no second fix-up of the gradients
+    for world in (1, 2):
+        mailbox.zero_()
+        peers = (C.c_uint64 * world)(*([mailbox.data_ptr()] * world))
+        for step in range(5):
+            local = torch.zeros(16, dtype=torch.float64, device=cuda_device)
+            out = torch.full((16,), -1.0, dtype=torch.float64, device=cuda_device)
+            for rank in range(world):                                             # every "rank" posts into the one mailbox
+                _lib.check(lib.t3d_step_epilogue_peers(*[_lib.ptr(x) for x in grads], _lib.ptr(per_sample), _lib.ptr(batch_ok),
+                                                       _lib.ptr(m64), B, H, W, B, _lib.ptr(local), peers, world, rank, step, st),
+                           "t3d_step_epilogue_peers")
+            _lib.check(lib.t3d_mailbox_reduce(_lib.ptr(mailbox), world, step, _lib.ptr(out), st), "t3d_mailbox_reduce")
+            assert torch.equal(local, ref)
+            assert torch.equal(out, ref * world), (world, step)

@@ -55,13 +55,27 @@ __global__ void __launch_bounds__(128) pack_step_result_kernel(const float* __re
 
 // pack + the validity fix-up of the loss gradients (scale_grads_kernel<0> of t3d_loss.cu) as ONE launch: block 0
 // packs, every block then checks the batch's valid count and returns at once when all samples are valid.
+// Peer-memory exchange of the packed vector (one process per GPU on one NVLink / NVSwitch node): every rank owns a
+// mailbox  { double slots[2][T3D_MAX_PEERS][16]; unsigned long long flags[2][T3D_MAX_PEERS]; }  in memory its peers
+// can address (CUDA IPC / symmetric memory).  Step s uses parity p = s & 1: rank r's epilogue stores its 16 doubles
+// into slot [p][r] of EVERY rank's mailbox (128-byte peer stores), fences, then publishes flags[p][r] = s + 1 with
+// release semantics; mailbox_reduce_kernel on each rank waits for the world's flags and adds the slots in rank order
+// (the same bits on every rank).  No NCCL call and no host work per step beyond the two launches.
+// Slot reuse: a rank runs reduce(s) before its epilogue(s + 1) in stream order, so by the time a peer may write
+// step s + 2 into parity p (after its own reduce(s + 1), which needed this rank's epilogue(s + 1)) the step-s slots
+// have been read here.
+constexpr int kMaxPeers = T3D_MAX_PEERS;
+struct Mailbox { double slots[2][kMaxPeers][16]; unsigned long long flags[2][kMaxPeers]; };
+struct PeerArgs { Mailbox* box[kMaxPeers]; int world, rank; unsigned long long step; };
+
 struct EpilogueArgs {
     float* dpred[2]; float* dconf[2];
     const float* out_sample; const float* out_batch; const double* metrics_f64;
     int B, n_images; size_t plane; double* out16;
 };
 
-__global__ void __launch_bounds__(128) step_epilogue_kernel(const EpilogueArgs a) {
+template <bool PEERS>
+__global__ void __launch_bounds__(128) step_epilogue_kernel(const EpilogueArgs a, const PeerArgs pa) {
     if (blockIdx.x == 0) {
         __shared__ double red[4][14];
         const int tid = threadIdx.x;
@@ -97,6 +111,17 @@ __global__ void __launch_bounds__(128) step_epilogue_kernel(const EpilogueArgs a
             else if (tid == 15) r = 0.0;
             else r = (red[0][tid] + red[1][tid]) + (red[2][tid] + red[3][tid]);
             a.out16[tid] = r;
+            if (PEERS) {
+                const int p = (int)(pa.step & 1ull);
+                for (int q = 0; q < pa.world; ++q) pa.box[q]->slots[p][pa.rank][tid] = r;       // peer stores (NVLink)
+                __threadfence_system();
+                __syncwarp(0x0000ffffu);
+                if (tid < pa.world) {
+                    unsigned long long* f = &pa.box[tid]->flags[p][pa.rank];
+                    const unsigned long long v = pa.step + 1ull;
+                    asm volatile("st.release.sys.global.u64 [%0], %1;" :: "l"(f), "l"(v) : "memory");
+                }
+            }
         }
     }
     const float nv = a.out_batch[5];
@@ -129,7 +154,63 @@ extern "C" int t3d_step_epilogue(float* dpred1, float* dpred2, float* dconf1, fl
     a.out_sample = loss_per_sample; a.out_batch = loss_batch; a.metrics_f64 = metrics_f64;
     a.B = B; a.n_images = n_images; a.plane = (size_t)H * W; a.out16 = out16;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    T3D_LAUNCH("step_epilogue_kernel", st, step_epilogue_kernel<<<t3d_sm_count() * 8, 128, 0, st>>>(a));
+    PeerArgs pa;
+    pa.world = 0; pa.rank = 0; pa.step = 0;
+    T3D_LAUNCH("step_epilogue_kernel", st, step_epilogue_kernel<false><<<t3d_sm_count() * 8, 128, 0, st>>>(a, pa));
+    return T3D_OK;
+}
+
+__global__ void __launch_bounds__(32) mailbox_reduce_kernel(const Mailbox* __restrict__ box, int world, unsigned long long step,
+                                                            double* __restrict__ out16) {
+    const int lane = threadIdx.x, p = (int)(step & 1ull);
+    if (lane < world) {
+        const unsigned long long* f = &box->flags[p][lane];
+        unsigned long long v;
+        do {
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(f) : "memory");
+            if (v < step + 1ull) __nanosleep(200);
+        } while (v < step + 1ull);
+    }
+    __syncwarp();
+    if (lane < 16) {
+        double s = 0.0;
+        for (int r = 0; r < world; ++r) {                       // rank order: the same bits on every rank
+            double x;
+            asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(x) : "l"(&box->slots[p][r][lane]) : "memory");
+            s += x;
+        }
+        out16[lane] = s;
+    }
+}
+
+extern "C" size_t t3d_mailbox_bytes(void) { return sizeof(Mailbox); }
+
+extern "C" int t3d_step_epilogue_peers(float* dpred1, float* dpred2, float* dconf1, float* dconf2,
+                                       const float* loss_per_sample, const float* loss_batch, const double* metrics_f64,
+                                       int B, int H, int W, int n_images, double* out16_local,
+                                       const unsigned long long* peer_mailboxes, int world, int rank,
+                                       unsigned long long step, void* stream) {
+    T3D_REQUIRE(loss_per_sample && loss_batch && out16_local && peer_mailboxes, "NULL pointer");
+    T3D_REQUIRE(B >= 1 && H >= 1 && W >= 1 && n_images >= 0, "bad dims");
+    T3D_REQUIRE(world >= 1 && world <= kMaxPeers && rank >= 0 && rank < world, "bad world / rank (at most %d peers)", kMaxPeers);
+    EpilogueArgs a;
+    a.dpred[0] = dpred1; a.dpred[1] = dpred2; a.dconf[0] = dconf1; a.dconf[1] = dconf2;
+    a.out_sample = loss_per_sample; a.out_batch = loss_batch; a.metrics_f64 = metrics_f64;
+    a.B = B; a.n_images = n_images; a.plane = (size_t)H * W; a.out16 = out16_local;
+    PeerArgs pa;
+    for (int q = 0; q < kMaxPeers; ++q) pa.box[q] = (q < world) ? reinterpret_cast<Mailbox*>(peer_mailboxes[q]) : nullptr;
+    pa.world = world; pa.rank = rank; pa.step = step;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    T3D_LAUNCH("step_epilogue_kernel", st, step_epilogue_kernel<true><<<t3d_sm_count() * 8, 128, 0, st>>>(a, pa));
+    return T3D_OK;
+}
+
+extern "C" int t3d_mailbox_reduce(const void* my_mailbox, int world, unsigned long long step, double* out16, void* stream) {
+    T3D_REQUIRE(my_mailbox && out16, "NULL pointer");
+    T3D_REQUIRE(world >= 1 && world <= kMaxPeers, "bad world");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    T3D_LAUNCH("mailbox_reduce_kernel", st, mailbox_reduce_kernel<<<1, 32, 0, st>>>(
+        reinterpret_cast<const Mailbox*>(my_mailbox), world, step, out16));
     return T3D_OK;
 }
 

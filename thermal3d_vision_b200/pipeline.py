@@ -24,7 +24,8 @@ RESULT_SIZE = 16   # packed result vector (float64): see HotPathStep.run_device
 
 class HotPathStep:
     def __init__(self, B: int, H: int, W: int, raw_hw=(512, 640), device=None, multi_scale: bool = False,
-                 alpha=0.2, edge_weight=0.5, smoothness_weight=0.3, detail_weight=0.4, distributed: bool = False):
+                 alpha=0.2, edge_weight=0.5, smoothness_weight=0.3, detail_weight=0.4, distributed: bool = False,
+                 exchange: str = "peer"):
         self.B, self.H, self.W, self.raw_hw = B, H, W, tuple(raw_hw)
         self.device = torch.device(device if device is not None else "cuda")
         self.kw = dict(alpha=alpha, edge_weight=edge_weight, smoothness_weight=smoothness_weight,
@@ -78,6 +79,36 @@ class HotPathStep:
         self.result = self.results[0]
         self.result_host = torch.zeros(RESULT_SIZE, dtype=torch.float64).pin_memory()
         self.staging = None        # two device staging sets of run_host (allocated on first use)
+        # Data-parallel exchange of the packed result.  "peer" (NCCL process group on one NVLink node): every rank
+        # owns a 4 KB mailbox in symmetric memory; the step's epilogue kernel stores the rank's 16 doubles straight
+        # into every peer's mailbox and a one-warp kernel adds them up one step later -- no collective call and no
+        # host work per step beyond two launches (a per-step dist.all_reduce costs enough host time to make the
+        # 0.43 ms step host-bound: 0.458 vs 0.435 ms).  "nccl": one asynchronous dist.all_reduce per step.
+        self.exchange = None
+        if distributed and _dist.world()[1] > 1:
+            import os
+            exchange = os.environ.get("T3D_EXCHANGE", exchange)      # tuning knob
+            if exchange not in ("peer", "nccl"):
+                raise ValueError("exchange must be 'peer' or 'nccl'")
+            self.exchange = exchange
+        if self.exchange == "peer":
+            import ctypes as C
+            import torch.distributed as dist
+            import torch.distributed._symmetric_memory as symm_mem
+            rank, world = _dist.world()
+            if world > 16:
+                raise ValueError("peer exchange: at most 16 ranks on one node (include/t3d.h T3D_MAX_PEERS)")
+            nbytes = int(lib.t3d_mailbox_bytes())
+            self.mailbox = symm_mem.empty(nbytes // 8, dtype=torch.float64, device=dev)
+            self.mailbox.zero_()
+            hdl = symm_mem.rendezvous(self.mailbox, dist.group.WORLD.group_name)
+            self.peer_ptrs = (C.c_uint64 * world)(*[int(p) for p in hdl.buffer_ptrs])
+            self._symm_handle = hdl
+            self.local = [torch.zeros(RESULT_SIZE, dtype=torch.float64, device=dev) for _ in range(2)]
+            self.reduced = [True, True]     # results[i] holds the global vector of the step that last used slot i
+            self.step_of = [-1, -1]
+            torch.cuda.synchronize(dev)
+            dist.barrier()                  # every mailbox is zeroed before anybody's first peer store
 
     # ------------------------------------------------------------------ bytes
     def algorithmic_bytes(self) -> Dict[str, int]:
@@ -95,7 +126,8 @@ class HotPathStep:
         """All inputs already in HBM.  Returns the packed device result vector (float64):
         [0] sum of valid per-sample losses  [1..4] sums of components  [5] n_valid  [6] B
         [7..13] sums of finite per-image metrics (abs_rel..acc_3)  [14] n_images  [15] unused.
-        With distributed=True the vector is all-reduced (SUM) over ranks: ONE small NCCL call."""
+        With distributed=True the vector is summed over the ranks (peer-memory mailboxes, or one NCCL all-reduce with
+        exchange="nccl"); it holds the global sums once wait_result() / finish() / the next call has been enqueued."""
         size = (self.W, self.H)
         B = self.B
         main = torch.cuda.current_stream(self.device)
@@ -136,18 +168,34 @@ class HotPathStep:
                                               rescale_invalid=False,     # done by t3d_step_epilogue below
                                               **self.kw)
         i = self.calls & 1
+        step_no = self.calls
         self.calls += 1
+        lib = _lib.lib()
+        stream = _lib.current_stream_ptr()
+        if self.exchange == "peer":
+            # reduce(step - 1) is enqueued before epilogue(step): the order that makes the two mailbox slots reusable
+            self._reduce_pending()
+            rank, world = _dist.world()
+            rc = lib.t3d_step_epilogue_peers(_lib.ptr(lo["dpred1"]), _lib.ptr(lo["dpred2"]), _lib.ptr(lo["dconf1"]),
+                                             _lib.ptr(lo["dconf2"]), _lib.ptr(lo["per_sample"]), _lib.ptr(lo["batch"]),
+                                             _lib.ptr(me["metrics_f64"]), self.B, self.H, self.W, self.B,
+                                             _lib.ptr(self.local[i]), self.peer_ptrs, world, rank, step_no, stream)
+            _lib.check(rc, "t3d_step_epilogue_peers")
+            self.reduced[i] = False
+            self.step_of[i] = step_no
+            self.result = self.results[i]          # global once wait_result() / the next step has enqueued the reduction
+            return self.result
         if self.pending[i] is not None:
             self.pending[i].wait()                 # the all-reduce of step - 2 is done with this vector
             self.pending[i] = None
         r = self.results[i]
         # validity fix-up of the gradients + packing of the step's scalars: one launch
-        rc = _lib.lib().t3d_step_epilogue(_lib.ptr(lo["dpred1"]), _lib.ptr(lo["dpred2"]), _lib.ptr(lo["dconf1"]),
-                                          _lib.ptr(lo["dconf2"]), _lib.ptr(lo["per_sample"]), _lib.ptr(lo["batch"]),
-                                          _lib.ptr(me["metrics_f64"]), self.B, self.H, self.W, self.B,
-                                          _lib.ptr(r), _lib.current_stream_ptr())
+        rc = lib.t3d_step_epilogue(_lib.ptr(lo["dpred1"]), _lib.ptr(lo["dpred2"]), _lib.ptr(lo["dconf1"]),
+                                   _lib.ptr(lo["dconf2"]), _lib.ptr(lo["per_sample"]), _lib.ptr(lo["batch"]),
+                                   _lib.ptr(me["metrics_f64"]), self.B, self.H, self.W, self.B,
+                                   _lib.ptr(r), stream)
         _lib.check(rc, "t3d_step_epilogue")
-        if self.distributed:
+        if self.exchange == "nccl":
             self.pending[i] = _dist.all_reduce_result(r, async_op=True)
         self.result = r
         return r
@@ -179,10 +227,22 @@ class HotPathStep:
         replay.graph = graph
         return replay
 
+    def _reduce_pending(self):
+        """peer exchange: enqueue the reduction of every step whose global vector has not been formed yet (oldest first)."""
+        if self.exchange != "peer":
+            return
+        lib, stream, world = _lib.lib(), _lib.current_stream_ptr(), _dist.world()[1]
+        for i in sorted(range(2), key=lambda k: self.step_of[k]):
+            if not self.reduced[i]:
+                rc = lib.t3d_mailbox_reduce(_lib.ptr(self.mailbox), world, self.step_of[i], _lib.ptr(self.results[i]), stream)
+                _lib.check(rc, "t3d_mailbox_reduce")
+                self.reduced[i] = True
+
     def wait_result(self, r: Optional[torch.Tensor] = None) -> torch.Tensor:
         """Order the current stream after the (asynchronous) all-reduce of `r` (default: the latest result).
         Call before reading a result of a distributed step; a no-op otherwise."""
         r = self.result if r is None else r
+        self._reduce_pending()
         for i in range(2):
             if self.results[i] is r and self.pending[i] is not None:
                 self.pending[i].wait()
@@ -191,6 +251,7 @@ class HotPathStep:
 
     def finish(self):
         """Order the current stream after every outstanding all-reduce (end of a run / of a timed region)."""
+        self._reduce_pending()
         for i in range(2):
             if self.pending[i] is not None:
                 self.pending[i].wait()

@@ -1,0 +1,32 @@
+"""Developer tool: tools/timeline.py under torchrun (distributed=True: one asynchronous all-reduce per step); rank 0 prints."""
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch, torch.distributed as dist
+import bench
+from thermal3d_vision_b200.pipeline import HotPathStep
+from thermal3d_vision_b200 import _lib
+rank, local = int(os.environ["RANK"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local)
+dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+dev = torch.device("cuda", local)
+B, H, W = 64, 384, 512
+d = bench.make_inputs_torch(B, H, W, rank, dev)
+step = HotPathStep(B, H, W, device=dev, distributed=True)
+args = (d["raw1"], d["raw2"], d["pred1"], d["pred2"], d["gt1"], d["gt2"], d["conf1"], d["conf2"], d["gt_depth"])
+for _ in range(10): step.run_device(*args)
+step.finish(); torch.cuda.synchronize(); dist.barrier()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+for _ in range(100): step.run_device(*args)
+step.finish(); e1.record(); torch.cuda.synchronize()
+if rank == 0: print("step_us", e0.elapsed_time(e1) * 10)
+dist.barrier()
+_lib.profile_begin("", 4096)
+for _ in range(3): step.run_device(*args)
+step.finish(); torch.cuda.synchronize()
+tl = _lib.profile_timeline()
+_lib.profile_end()
+if rank == 0:
+    for nm, a, b in sorted(tl, key=lambda r: r[1])[-26:]:
+        print(f"{a*1e3:9.1f} {b*1e3:9.1f} {(b-a)*1e3:7.1f}  {nm}")
+dist.barrier(); dist.destroy_process_group()
