@@ -93,22 +93,34 @@ class HotPathStep:
             self.exchange = exchange
         if self.exchange == "peer":
             import ctypes as C
+            import warnings
             import torch.distributed as dist
-            import torch.distributed._symmetric_memory as symm_mem
             rank, world = _dist.world()
             if world > 16:
                 raise ValueError("peer exchange: at most 16 ranks on one node (include/t3d.h T3D_MAX_PEERS)")
             nbytes = int(lib.t3d_mailbox_bytes())
-            self.mailbox = symm_mem.empty(nbytes // 8, dtype=torch.float64, device=dev)
-            self.mailbox.zero_()
-            hdl = symm_mem.rendezvous(self.mailbox, dist.group.WORLD.group_name)
-            self.peer_ptrs = (C.c_uint64 * world)(*[int(p) for p in hdl.buffer_ptrs])
-            self._symm_handle = hdl
-            self.local = [torch.zeros(RESULT_SIZE, dtype=torch.float64, device=dev) for _ in range(2)]
-            self.reduced = [True, True]     # results[i] holds the global vector of the step that last used slot i
-            self.step_of = [-1, -1]
-            torch.cuda.synchronize(dev)
-            dist.barrier()                  # every mailbox is zeroed before anybody's first peer store
+            err = None
+            try:
+                import torch.distributed._symmetric_memory as symm_mem
+                self.mailbox = symm_mem.empty(nbytes // 8, dtype=torch.float64, device=dev)
+                self.mailbox.zero_()
+                hdl = symm_mem.rendezvous(self.mailbox, dist.group.WORLD.group_name)
+                self.peer_ptrs = (C.c_uint64 * world)(*[int(p) for p in hdl.buffer_ptrs])
+                self._symm_handle = hdl
+            except Exception as e:      # no peer-addressable memory on this system (e.g. GPUs without P2P access)
+                err = e
+            # the ranks must agree: one that cannot map its peers takes everybody to the NCCL exchange (still on the GPUs)
+            ok = torch.tensor([0 if err is not None else 1], dtype=torch.int32, device=dev)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            if int(ok.item()) == 0:
+                warnings.warn(f"peer-memory exchange unavailable ({err!r}); using one NCCL all-reduce per step")
+                self.exchange = "nccl"
+            else:
+                self.local = [torch.zeros(RESULT_SIZE, dtype=torch.float64, device=dev) for _ in range(2)]
+                self.reduced = [True, True]     # results[i] holds the global vector of the step that last used slot i
+                self.step_of = [-1, -1]
+                torch.cuda.synchronize(dev)
+                dist.barrier()                  # every mailbox is zeroed before anybody's first peer store
 
     # ------------------------------------------------------------------ bytes
     def algorithmic_bytes(self) -> Dict[str, int]:
