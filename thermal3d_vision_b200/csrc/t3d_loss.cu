@@ -896,7 +896,7 @@ int loss_impl(bool bwd, const float* pred1, const float* pred2, const float* gt1
     int rc;
     static const int march_rows = [] {
         const char* e = getenv("T3D_MARCH_ROWS");           // tuning knob; 0 disables the fast path
-        const int v = e ? atoi(e) : 16;
+        const int v = e ? atoi(e) : 32;
         return (v == 0) ? 0 : (v < 8 ? 8 : v);
     }();
     const float* partials2 = nullptr;
@@ -926,9 +926,18 @@ int loss_impl(bool bwd, const float* pred1, const float* pred2, const float* gt1
         }
         ma.stats[0] = stats_v[0]; ma.stats[1] = stats_v[1]; ma.partials = loss_partials; ma.queue = counter + 1;
         ma.B = B; ma.H = H; ma.W = W; ma.tch = tch; ma.stiles = la.stiles; ma.replicated = replicated;
-        ma.rows_per_band = march_rows; ma.nbands = (H + march_rows - 1) / march_rows; ma.nstrips = (W + 127) / 128;
+        // bands of march_rows rows (a band re-reads the row above and the row below it: taller = less overfetch), the
+        // last ~1/8 of the image in 8-row bands queued behind all the large ones (shorter tail of the persistent grid)
+        static const int tail_div = [] { const char* e = getenv("T3D_MARCH_TAIL"); const int v = e ? atoi(e) : 8; return v < 0 ? 0 : v; }();
+        const int small_target = tail_div > 0 ? ((H / tail_div + 7) / 8) * 8 : 0;
+        ma.rows_l = march_rows; ma.rows_s = 8;
+        ma.nbands_l = (small_target > 0) ? max(0, H - small_target) / march_rows : (H + march_rows - 1) / march_rows;
+        if (small_target == 0) { ma.nbands_s = 0; /* the last large band may be ragged: handle it as one small band */
+            if (ma.nbands_l * march_rows > H) { ma.nbands_l -= 1; ma.rows_s = march_rows; ma.nbands_s = 1; } }
+        else ma.nbands_s = (H - ma.nbands_l * march_rows + 7) / 8;
+        ma.nstrips = (W + 127) / 128;
         ma.alpha = alpha; ma.kb = la.kb; ma.kc = la.kc; ma.kE = la.kE[0]; ma.kS = la.kS[0]; ma.kD = la.kD[0];
-        n_partials = ma.nbands * ma.nstrips;
+        n_partials = (ma.nbands_l + ma.nbands_s) * ma.nstrips;
         rc = t3d_launch_loss_march(ma, bwd, st);
     } else if (bwd) {
         if (ms) rc = vec ? launch_loss<true, true, true>(la, st) : launch_loss<true, false, true>(la, st);

@@ -11,7 +11,10 @@ struct MarchArgs {
     unsigned int* queue;           // work-item counter, zero on entry
     int B, H, W, tch, stiles;
     int replicated;                // tch == 3 and the planes of every image are bit-identical: read plane 0 only
-    int rows_per_band, nbands, nstrips;
+    // work items: nbands_l bands of rows_l rows from the top of the image, then nbands_s bands of rows_s rows down to
+    // the last row; ALL large items of the batch are queued before the small ones (the fine-grained items fill the
+    // tail of the persistent grid: a warp spends ~20-30 us on a large item)
+    int rows_l, nbands_l, rows_s, nbands_s, nstrips;
     float alpha, kb, kc, kE, kS, kD;
     const float* dzp[2];           // multi-scale: per view [B][H/2][W/2], added to d/d(pred z) of each cell's 4 pixels (or NULL)
 };

@@ -160,7 +160,9 @@ __global__ void __launch_bounds__(WARPS * 32, 1) loss_march_kernel(const MarchAr
 
     const int H = a.H, W = a.W;
     const size_t plane = (size_t)H * W;
-    const int ntasks = a.B * 2 * a.nbands * a.nstrips;
+    const int nbands = a.nbands_l + a.nbands_s;
+    const int n_large = a.B * 2 * a.nbands_l * a.nstrips;
+    const int ntasks = a.B * 2 * nbands * a.nstrips;
     const float kE = a.kE, kS2 = 2.0f * a.kS, kD = a.kD, kb = a.kb, kc = a.kc, alpha = a.alpha;
     const float alpha_ln2 = alpha * 0.69314718055994531f;
     uint32_t pos = 0;                                  // rows streamed so far by this warp (ring position)
@@ -170,12 +172,17 @@ __global__ void __launch_bounds__(WARPS * 32, 1) loss_march_kernel(const MarchAr
         if (lane == 0) task = (int)atomicAdd(a.queue, 1u);
         task = __shfl_sync(0xffffffffu, task, 0);
         if (task >= ntasks) break;
-        const int s = task % a.nstrips;
-        const int t2 = task / a.nstrips;
-        const int k = t2 % a.nbands;
-        const int img = t2 / a.nbands;
+        const bool large = task < n_large;
+        const int t1 = large ? task : task - n_large;
+        const int nb = large ? a.nbands_l : a.nbands_s;
+        const int s = t1 % a.nstrips;
+        const int t2 = t1 / a.nstrips;
+        const int k = t2 % nb;
+        const int img = t2 / nb;
         const int b = img >> 1, view = img & 1;
-        const int ra = k * a.rows_per_band, rb = min(ra + a.rows_per_band, H);
+        const int ra = large ? k * a.rows_l : a.nbands_l * a.rows_l + k * a.rows_s;
+        const int rb = large ? ra + a.rows_l : min(ra + a.rows_s, H);          // the large bands end at nbands_l * rows_l <= H
+        const int pidx = (img * nbands + (large ? k : a.nbands_l + k)) * a.nstrips + s;     // partials: per image-view, band-major
         const int i_lo = max(ra - 1, 0), i_hi = min(rb, H - 1);
         const int n_rows = i_hi - i_lo + 1;
         const int col0 = s * kStripPx;
@@ -363,7 +370,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) loss_march_kernel(const MarchAr
         tot.E = warp_sum(tot.E); tot.S = warp_sum(tot.S); tot.D = warp_sum(tot.D);
         if (lane == 0) {
             if (thermal_bad) tot.E = __int_as_float(0x7fc00000);
-            float4* o = reinterpret_cast<float4*>(a.partials + (size_t)task * 8);
+            float4* o = reinterpret_cast<float4*>(a.partials + (size_t)pidx * 8);
             o[0] = make_float4(sum_b, tot.E, tot.S, tot.D);
             o[1] = make_float4(0.f, 0.f, 0.f, 0.f);
         }
