@@ -42,7 +42,8 @@ def parse():
     ap.add_argument("--width", type=int, default=512)
     ap.add_argument("--multi-scale", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cpu-sample-pairs", type=int, default=2)
+    ap.add_argument("--cpu-sample-pairs", type=int, default=4)
+    ap.add_argument("--no-extras", action="store_true", help="skip the extra blocks (multi-scale, configs[1], eval shard)")
     ap.add_argument("--workload", default="train", choices=["train", "eval"],
                     help="train: BASELINE configs[2] (the metric's configuration, default); eval: configs[4] "
                          "(640x512 u16 preprocessing + pointmap->depth + metrics over a dataset shard; extra line)")
@@ -54,17 +55,27 @@ def workload_name(a):
     return f"dust3r512_batch{a.batch}_{a.width}x{a.height}_pairs_loss_fwd_bwd+preproc_640x512_u16+depth_metrics"
 
 
-def config_dict(a, world):
+EXCHANGE_TEXT = {
+    None: "single process, no exchange",
+    "peer": "per step one 128-byte exchange of the packed scalars over NVLink peer memory (symmetric-memory mailboxes written by "
+            "the step's epilogue kernel), no NCCL call in the step",
+    "nccl": "per step one asynchronous NCCL all-reduce of the packed scalars (16 doubles)",
+    "cpu": "host cores only",
+}
+
+
+def config_dict(a, world, exchange=None):
     return {"workload": workload_name(a), "per_rank_batch": a.batch, "global_batch": a.batch * world,
             "pointmap_hw": [a.height, a.width], "raw_frame_hw": [512, 640], "multi_scale": bool(a.multi_scale),
             "edge_weight": EDGE_W, "smoothness_weight": SMOOTH_W, "detail_weight": DETAIL_W, "alpha": ALPHA,
-            "parallelism": f"dp{world} (sharded by image; per step one 128-byte exchange of the packed scalars over NVLink peer memory, no NCCL call)",
+            "parallelism": f"dp{world} (sharded by image; {EXCHANGE_TEXT[exchange]})",
             "l2_policy": "inputs_exceed_l2 (1.2 GB of inputs per step vs 126 MB L2; no flush needed)"}
 
 
 # --------------------------------------------------------------------------- synthetic inputs
-def make_inputs_torch(B, H, W, seed, device):
+def make_inputs_torch(B, H, W, seed, device, raw_hw=(512, 640)):
     import torch
+    RH, RW = raw_hw
     g = torch.Generator(device=device).manual_seed(seed)
     r = lambda *s: torch.randn(*s, device=device, generator=g)
     gt1, gt2 = r(B, H, W, 3), r(B, H, W, 3)
@@ -77,9 +88,9 @@ def make_inputs_torch(B, H, W, seed, device):
     raws = []
     for _ in range(2):          # day: N(22800, 400); night: N(22300, 250) + hot blobs -- inside the Freiburg window
         night = torch.rand(B, 1, 1, device=device, generator=g) < 0.4
-        f = torch.where(night, 22300 + 250 * r(B, 512, 640), 22800 + 400 * r(B, 512, 640))
-        blobs = (torch.rand(B, 512 // 32, 640 // 32, device=device, generator=g) < 0.01).float()
-        blobs = blobs.repeat_interleave(32, 1).repeat_interleave(32, 2) * 1500.0
+        f = torch.where(night, 22300 + 250 * r(B, RH, RW), 22800 + 400 * r(B, RH, RW))
+        blobs = (torch.rand(B, (RH + 31) // 32, (RW + 31) // 32, device=device, generator=g) < 0.01).float()
+        blobs = blobs.repeat_interleave(32, 1).repeat_interleave(32, 2)[:, :RH, :RW] * 1500.0
         f = f + torch.where(night, blobs, torch.zeros_like(blobs))
         raws.append(f.clamp(0, 65535).to(torch.int32).to(torch.uint16))
     gt_depth = gt1[..., 2].contiguous()
@@ -189,9 +200,9 @@ class ClockSampler:
 
 
 # --------------------------------------------------------------------------- CPU arm (oracle port of the reference)
-def cpu_step_fn(a):
-    """Returns (fn(n_pairs) -> None, description).  The unmodified reference cannot travel to the GPU box,
-    so this is the oracle port (oracle/): same per-sample loop as train_thermal_dustr.py:182-360 (loss per
+def cpu_step_fn(a, n, H=None, W=None):
+    """Returns (fn() -> None, description): one CPU step over n pairs.  The unmodified reference cannot travel to the
+    GPU box, so this is the oracle port (oracle/): same per-sample loop as train_thermal_dustr.py:182-360 (loss per
     sample -> mean over valid -> one backward), cv2.resize + percentile normalisation per frame as
     data/dataset_loader.py:237-249 / utils/preprocessing.py:6-30, compute_depth_metrics per frame."""
     import numpy as np
@@ -203,8 +214,7 @@ def cpu_step_fn(a):
     except Exception:
         resize = ref_preprocess.resize_bilinear
     torch.set_num_threads(os.cpu_count() or 1)
-    H, W = a.height, a.width
-    n = a.cpu_sample_pairs
+    H, W = H or a.height, W or a.width
     P1, P2, G1, G2, C1, C2, _, _ = ref_loss.make_batch_inputs(n, H, W, seed=0, smooth=False)
     raw = ref_preprocess.make_raw_frames(2 * n, seed=0)
     kw = dict(alpha=ALPHA, edge_weight=EDGE_W, smoothness_weight=SMOOTH_W, detail_weight=DETAIL_W,
@@ -229,11 +239,11 @@ def cpu_step_fn(a):
         for i in range(n):
             ref_metrics.compute_depth_metrics(p1[i, ..., 2].detach().numpy(), G1[i, ..., 2].numpy())
 
-    return step, n, f"{n} of {a.batch} pairs ({W}x{H}) per step: per-sample loss loop + backward, 2 frames/pair preprocessed, metrics per pair"
+    return step, f"{n} pairs ({W}x{H}) per step: per-sample loss loop + backward, 2 frames/pair preprocessed (640x512 u16), metrics per pair"
 
 
-def time_cpu(a, min_seconds=12.0, max_iters=2000, warmup=1):
-    step, n, desc = cpu_step_fn(a)
+def time_cpu(a, n, H=None, W=None, min_seconds=10.0, max_iters=2000, warmup=1):
+    step, desc = cpu_step_fn(a, n, H, W)
     for _ in range(warmup):
         step()
     t0, it = time.perf_counter(), 0
@@ -247,22 +257,38 @@ def time_cpu(a, min_seconds=12.0, max_iters=2000, warmup=1):
 
 
 def run_reference(a):
+    """The reference arm: the oracle port of the reference's CPU path on the host cores, EXACTLY --warmup + --steps
+    steps; every step processes `sample_pairs` pairs of the workload -- the whole batch when warmup + steps full
+    batches fit the time budget on this host, otherwise the largest sample (>= 8 pairs) that does."""
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if rank != 0:
         return
-    step, n, desc = cpu_step_fn(a)
-    steps = min(a.steps, 12)          # bounded so the run ends within minutes on host cores
-    for _ in range(min(a.warmup, 2)):
+    # size the per-step sample from a 2-pair probe of this host (untimed): the whole batch when warmup + steps full
+    # batches fit in ~150 s at half the probed rate (a batch-64 graph runs slower per pair than a 2-pair one:
+    # its saved activations no longer fit the caches), never fewer than 8 pairs
+    probe, _ = cpu_step_fn(a, 2)
+    probe()
+    t0 = time.perf_counter()
+    probe()
+    rate = 2.0 / max(time.perf_counter() - t0, 1e-3)
+    n = int(max(min(a.batch, 8), min(a.batch, (150.0 * 0.5 * rate) // max(a.steps + a.warmup, 1))))
+    step, desc = cpu_step_fn(a, n)
+    for _ in range(a.warmup):
         step()
     t0 = time.perf_counter()
-    for _ in range(steps):
+    for _ in range(a.steps):
         step()
     el = time.perf_counter() - t0
-    v = n * steps / el
-    out = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": a.gpus, "steps": steps,
-           "warmup": min(a.warmup, 2), "ms_per_step": 1e3 * el / steps, "higher_is_better": True, "scaling": "weak",
-           "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config_dict(a, world),
+    v = n * a.steps / el
+    cfg = config_dict(a, world, "cpu")
+    cfg["sample_pairs"] = n
+    cfg["sample_note"] = (f"each timed step runs {n} of the {a.batch} pairs of the batch" if n < a.batch
+                          else "each timed step runs the whole batch")
+    out = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
+           "warmup": a.warmup, "ms_per_step": 1e3 * el / a.steps, "ms_per_full_batch_extrapolated": 1e3 * el / a.steps * a.batch / n,
+           "higher_is_better": True, "scaling": "weak",
+           "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg,
            "cpu_baseline": {"value": v, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port", "sample": desc},
            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0, "note": "oracle port of the reference's CPU path on the host cores; the python reference "
@@ -271,6 +297,108 @@ def run_reference(a):
 
 
 # --------------------------------------------------------------------------- our arm
+KEYS = ("raw1", "raw2", "pred1", "pred2", "gt1", "gt2", "conf1", "conf2", "gt_depth")
+
+
+def load_peak():
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    src = "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    return peak, src
+
+
+def time_steps(fn, steps, warmup, finish=None):
+    """CUDA-event time of `steps` calls of fn() after `warmup` untimed ones (ms per call)."""
+    import torch
+    for _ in range(warmup):
+        fn()
+    if finish:
+        finish()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    if finish:
+        finish()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / steps
+
+
+def extra_multi_scale(a, dev, d, peak):
+    """multi_scale=True (the reference function's default, utils/loss.py:104): the same step, device-timed, plus the
+    summed duration of the loss kernels (half-resolution pass + marching kernel + second stage) per step."""
+    from thermal3d_vision_b200 import _lib
+    from thermal3d_vision_b200.pipeline import HotPathStep
+    B, H, W = a.batch, a.height, a.width
+    step = HotPathStep(B, H, W, device=dev, multi_scale=True, alpha=ALPHA, edge_weight=EDGE_W, smoothness_weight=SMOOTH_W,
+                       detail_weight=DETAIL_W, pipelined=True)
+    args = [d[k] for k in KEYS]
+    ms = time_steps(lambda: step.run_device(*args), 20, 3, step.finish)
+    _lib.profile_begin("loss_", 256)
+    for _ in range(10):
+        step.run_device(*args)
+    step.finish()
+    tl = _lib.profile_timeline()
+    _lib.profile_end()
+    per = {}
+    for name, t0, t1 in tl:
+        per[name] = per.get(name, 0.0) + (t1 - t0) / 10.0
+    loss_ms = sum(per.values())
+    ab = step.algorithmic_bytes()
+    s = HotPathStep.summarize(step.wait_result().cpu())
+    return {"ms_per_step": ms, "pairs_per_s": B / (ms * 1e-3), "loss_kernels_ms": loss_ms, "loss_kernels": per,
+            "loss_frac_of_peak": ab["loss"] / (loss_ms * 1e-3) / 1e9 / peak if loss_ms > 0 else None,
+            "step_frac_of_peak": sum(ab.values()) / (ms * 1e-3) / 1e9 / peak,
+            "check": {"loss": s["loss"], "n_valid": s["n_valid"]},
+            "note": "same workload with multi_scale=True; loss_kernels_ms = CUDA-event time of every kernel named loss_* per step "
+                    "(bracketing events serialise the streams, so the step itself is timed separately without them)"}
+
+
+def extra_cfg2(a, dev, peak):
+    """BASELINE configs[1] (batch 8, 224x224) replayed as one CUDA graph, and configs[0]: the same step on the host
+    cores (oracle port)."""
+    import torch
+    from thermal3d_vision_b200.pipeline import HotPathStep
+    B, H, W = 8, 224, 224
+    d = make_inputs_torch(B, H, W, seed=2, device=dev)
+    step = HotPathStep(B, H, W, device=dev, alpha=ALPHA, edge_weight=EDGE_W, smoothness_weight=SMOOTH_W, detail_weight=DETAIL_W)
+    replay = step.capture_graph(*[d[k] for k in KEYS])
+    # 45 MB of inputs + 13 MB of outputs per step fit the 126 MB L2: flush it between replays (write 256 MB) and
+    # time only the replays
+    flush = torch.empty(64 * 1024 * 1024, dtype=torch.float32, device=dev)
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(30)]
+    for _ in range(5):
+        replay()
+    for e0, e1 in ev:
+        flush.fill_(1.0)
+        e0.record(); replay(); e1.record()
+    torch.cuda.synchronize()
+    ms_cold = sorted(e0.elapsed_time(e1) for e0, e1 in ev)[len(ev) // 2]
+    ms_warm = time_steps(replay, 200, 5)
+    ab = sum(step.algorithmic_bytes().values())
+    s = HotPathStep.summarize(replay().cpu())
+    eager = HotPathStep(B, H, W, device=dev, alpha=ALPHA, edge_weight=EDGE_W, smoothness_weight=SMOOTH_W, detail_weight=DETAIL_W,
+                        pipelined=True)
+    ms_eager = time_steps(lambda: eager.run_device(*[d[k] for k in KEYS]), 200, 5, eager.finish)
+    out = {"workload": "batch8_224x224_pairs_loss_fwd_bwd+preproc_640x512_u16+depth_metrics (BASELINE configs[1], CUDA-graph replay)",
+           "ms_per_step": ms_cold, "pairs_per_s": B / (ms_cold * 1e-3), "ms_per_step_l2_warm": ms_warm,
+           "ms_per_step_stream_launches_pipelined": ms_eager,
+           "l2_policy": "flushed between replays (256 MB fill), median of 30; l2_warm = 200 back-to-back replays",
+           "roofline": {"bound": "hbm", "achieved": ab / (ms_cold * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                        "frac": ab / (ms_cold * 1e-3) / 1e9 / peak, "step_algorithmic_bytes": ab,
+                        "note": "launch-/latency-bound shape: 58 MB of traffic is ~9 us of HBM time"},
+           "check": {"loss": s["loss"], "abs_rel": s["abs_rel"], "n_valid": s["n_valid"]}}
+    if not a.no_cpu_baseline:
+        out["cpu_baseline_cfg0"] = time_cpu(a, B, H, W, min_seconds=6.0)
+    return out
+
+
 def run_b200(a):
     import torch
     import torch.distributed as dist
@@ -295,10 +423,12 @@ def run_b200(a):
     _lib.lib()
 
     B, H, W = a.batch, a.height, a.width
+    # pipelined: consecutive steps overlap on the step's internal streams (every step does all of its own work on
+    # its own output set); the timed region ends with finish(), i.e. after the last step's last kernel
     step = HotPathStep(B, H, W, device=dev, multi_scale=bool(a.multi_scale), alpha=ALPHA, edge_weight=EDGE_W,
-                       smoothness_weight=SMOOTH_W, detail_weight=DETAIL_W, distributed=world > 1)
+                       smoothness_weight=SMOOTH_W, detail_weight=DETAIL_W, distributed=world > 1, pipelined=True)
     d = make_inputs_torch(B, H, W, seed=rank, device=dev)
-    args = (d["raw1"], d["raw2"], d["pred1"], d["pred2"], d["gt1"], d["gt2"], d["conf1"], d["conf2"], d["gt_depth"])
+    args = tuple(d[k] for k in KEYS)
     host = {k: v.cpu().pin_memory() for k, v in d.items()}
     os.sched_setaffinity(0, all_cpus)                  # the pinned pages are placed; the CPU baseline leg uses every core
 
@@ -317,6 +447,7 @@ def run_b200(a):
     # ---------------- device-resident timing ("value")
     for _ in range(max(a.warmup, 3)):
         step.run_device(*args)
+    step.finish()
     barrier()
     sampler = ClockSampler(local)
     if rank == 0:
@@ -334,14 +465,29 @@ def run_b200(a):
     e0.record()
     for _ in range(a.steps):
         step.run_device(*args)
-    step.finish()                        # outstanding (asynchronous) result all-reduces belong to the timed region
+    step.finish()                        # every step's last kernel and outstanding exchange belong to the timed region
     e1.record()
     barrier()
     launches = _lib.launch_count() - n0
     kern_ms, kern_n = _lib.profile_end()
     ms_dev = max_over_ranks(e0.elapsed_time(e1))
     clocks = sampler.stop() if rank == 0 else None
-    summary = HotPathStep.summarize(step.wait_result().cpu())
+    result_vec = step.wait_result().clone()
+    summary = HotPathStep.summarize(result_vec.cpu())
+
+    # ---------------- data parallel: the exchanged vector against an independent all-gather of the local vectors
+    check_exchange = {"exchange": step.exchange or "none"}
+    if world > 1:
+        last = (step.calls - 1) & 1
+        gathered = [torch.zeros_like(step.local[last]) for _ in range(world)]
+        dist.all_gather(gathered, step.local[last].contiguous())
+        total = torch.zeros_like(gathered[0])
+        for g in gathered:                  # rank order, the order the exchange adds in
+            total = total + g
+        check_exchange["exchange_bitwise_ok"] = bool(torch.equal(total, result_vec))
+        check_exchange["ranks_seen"] = int(round(total[6].item() / B))
+        if step.exchange_fallback:
+            check_exchange["peer_unavailable"] = step.exchange_fallback
 
     # ---------------- end to end through the public API with HOST buffers ("e2e")
     for _ in range(2):
@@ -355,13 +501,7 @@ def run_b200(a):
     ms_e2e = max_over_ranks(e0.elapsed_time(e1))
 
     if rank == 0:
-        peaks = {}
-        try:
-            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        except Exception:
-            pass
-        peak = float(peaks.get("hbm_gbs", 6650.0))
-        peak_src = "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+        peak, peak_src = load_peak()
         ab = step.algorithmic_bytes()
         kern_bytes = ab["loss"]
         kern_avg_ms = kern_ms / max(kern_n, 1)
@@ -378,11 +518,14 @@ def run_b200(a):
                 traffic_src = tj["source"] + " (dram__bytes_read.sum + dram__bytes_write.sum, 1 launch)"
         except Exception:
             pass
+        cfg = config_dict(a, world, step.exchange)
+        cfg["step_overlap"] = ("pipelined: the preprocessing / metric kernels of step i+1 run while the tail of step i drains "
+                               "(internal streams, two alternating output sets); every step does all of its own work")
         out = {
             "metric": METRIC, "value": world * B * a.steps / (ms_dev * 1e-3), "unit": UNIT, "n_gpus": world,
             "steps": a.steps, "warmup": max(a.warmup, 3), "ms_per_step": ms_dev / a.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": config_dict(a, world),
+            "config": cfg,
             "roofline": {"bound": "hbm", "kernel": dominant + " (fused loss fwd+bwd, both views)",
                          "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": (achieved / peak) if achieved else None, "traffic": traffic,
@@ -398,40 +541,53 @@ def run_b200(a):
                          "step_frac_of_peak": step_bytes / (ms_dev / a.steps * 1e-3) / 1e9 / peak},
             "e2e": {"value": world * B * a.steps / (ms_e2e * 1e-3), "unit": UNIT,
                     "h2d_bytes_per_step": HotPathStep.h2d_bytes(host), "d2h_bytes_per_step": 16 * 8,
-                    "ms_per_step": ms_e2e / a.steps},
+                    "ms_per_step": ms_e2e / a.steps,
+                    "h2d_gbs_aggregate": world * HotPathStep.h2d_bytes(host) / (ms_e2e / a.steps * 1e-3) / 1e9},
             "gpu_launches": int(launches),
             "host_numa_bound": bool(numa_bound),
             "clocks": clocks,
-            "check": {k: summary[k] for k in ("loss", "abs_rel", "acc_1", "n_valid")},
+            "check": dict({k: summary[k] for k in ("loss", "abs_rel", "acc_1", "n_valid")}, **check_exchange),
         }
         if world == 1 and not a.no_cpu_baseline:
-            out["cpu_baseline"] = time_cpu(a)
+            n_cpu = max(1, min(a.cpu_sample_pairs, B))
+            out["cpu_baseline"] = time_cpu(a, n_cpu)
         else:
             out["cpu_baseline"] = None
+    del step, host
+    torch.cuda.empty_cache()
+    # ---------------- extra blocks: the other BASELINE configs, device-timed in the same run
+    extra = {}
+    if not a.no_extras and not a.multi_scale:
+        if world == 1:
+            peak, _ = load_peak()
+            extra["multi_scale"] = extra_multi_scale(a, dev, d, peak)
+            extra["cfg2"] = extra_cfg2(a, dev, peak)
+        if world in (1, 8):
+            del d
+            torch.cuda.empty_cache()
+            ev = eval_shard(a, dev, rank, world, local)
+            if rank == 0:
+                extra["eval"] = ev
+    if rank == 0:
+        if extra:
+            out["extra"] = extra
         print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
 
 # --------------------------------------------------------------------------- configs[4]: evaluation shard
-def run_eval(a):
+def eval_shard(a, dev, rank, world, local):
     """frames/s of the evaluation path (BASELINE.json configs[4]): every step = one batch of `--batch` full-res
     640x512 16-bit frames -> preprocessing to the model size + pointmap -> depth -> depth metrics vs 512x512 GT
-    depth (nearest resample), accumulated on the device; ONE all-reduce of the accumulator at the end.  `--steps`
-    is ignored: the shard (`--eval-frames` per rank) is processed once, timed on the device, max over ranks."""
+    depth (nearest resample), accumulated on the device; ONE all-reduce of the accumulator at the end.  The shard
+    (`--eval-frames` per rank; 8 ranks x 2 560 = the 20 480 frames of configs[4]) is processed once, timed on the
+    device, max over ranks.  Returns the JSON block (rank 0) or None."""
     import torch
     import torch.distributed as dist
     from thermal3d_vision_b200 import _lib
     from thermal3d_vision_b200.pipeline import EvalStep
 
-    world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0")); local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback)")
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
     B, H, W = a.batch, a.height, a.width
     nb = max(1, a.eval_frames // B)
     step = EvalStep(B, H, W, gt_hw=(512, 512), device=dev)
@@ -445,6 +601,7 @@ def run_eval(a):
         pm[..., 2] = torch.nn.functional.interpolate(gt[:, None], size=(H, W), mode="nearest")[:, 0] * \
             (1 + 0.05 * torch.randn(B, H, W, device=dev, generator=g)) * 0.7
         pool.append((d["raw1"], pm, gt))
+        del d
     for k in range(max(a.warmup, 3)):
         step.run_batch(*pool[k % 4])
     step.acc.state.zero_()
@@ -464,27 +621,40 @@ def run_eval(a):
         t = torch.tensor([ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = t.item()
+    if rank != 0:
+        return None
+    peak, _ = load_peak()
+    frames = world * nb * B
+    ab = step.algorithmic_bytes() * nb
+    return {
+        "metric": "frames/sec of 640x512 u16 preprocessing + pointmap->depth + metrics (BASELINE configs[4])",
+        "value": frames / (ms * 1e-3), "unit": "frames/s", "n_gpus": world, "steps": nb, "warmup": max(a.warmup, 3),
+        "ms_per_step": ms / nb, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "config": {"workload": f"eval_shard_{nb * B}_frames_per_rank_640x512_u16_to_{W}x{H}+depth_metrics_gt512x512",
+                                        "per_rank_frames": nb * B, "global_frames": frames, "batch": B,
+                                        "l2_policy": "inputs_exceed_l2 (pool of 4 batches, 1 GB)"},
+        "roofline": {"bound": "hbm", "achieved": world * ab / (ms * 1e-3) / 1e9 / world, "peak": peak, "unit": "GB/s",
+                     "frac": ab / (ms * 1e-3) / 1e9 / peak, "traffic": None,
+                     "note": "per GPU: whole evaluation step (algorithmic bytes of preprocessing + metrics / step time)"},
+        "gpu_launches": int(_lib.launch_count() - n0), "check": {k: res[k] for k in ("abs_rel", "rmse", "acc_1")},
+    }
+
+
+def run_eval(a):
+    """`--workload eval`: only the evaluation shard (see eval_shard), printed as its own JSON line."""
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    out = eval_shard(a, dev, rank, world, local)
     if rank == 0:
-        peaks = {}
-        try:
-            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        except Exception:
-            pass
-        peak = float(peaks.get("hbm_gbs", 6650.0))
-        frames = world * nb * B
-        ab = step.algorithmic_bytes() * nb
-        print(json.dumps({
-            "metric": "frames/sec of 640x512 u16 preprocessing + pointmap->depth + metrics (BASELINE configs[4])",
-            "value": frames / (ms * 1e-3), "unit": "frames/s", "n_gpus": world, "steps": nb, "warmup": max(a.warmup, 3),
-            "ms_per_step": ms / nb, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic", "config": {"workload": f"eval_shard_{nb * B}_frames_per_rank_640x512_u16_to_{W}x{H}+depth_metrics_gt512x512",
-                                            "per_rank_frames": nb * B, "global_frames": frames, "batch": B,
-                                            "l2_policy": "inputs_exceed_l2 (pool of 4 batches, 1 GB)"},
-            "roofline": {"bound": "hbm", "achieved": ab / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-                         "frac": ab / (ms * 1e-3) / 1e9 / peak, "traffic": None,
-                         "note": "whole evaluation step (algorithmic bytes of preprocessing + metrics / step time)"},
-            "gpu_launches": int(_lib.launch_count() - n0), "check": {k: res[k] for k in ("abs_rel", "rmse", "acc_1")},
-        }), flush=True)
+        print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()
 

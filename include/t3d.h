@@ -40,7 +40,7 @@ typedef enum {
     T3D_ERR_DEVICE = -4       /* not an sm_100 device */
 } t3d_status;
 
-#define T3D_ABI_VERSION 1
+#define T3D_ABI_VERSION 2
 
 /* ------------------------------------------------------------------ library */
 int t3d_version(void);
@@ -84,7 +84,12 @@ int t3d_profile_timeline(char* names, int name_stride, double* start_ms, double*
  */
 #define T3D_LOSS_OUT_STRIDE 8
 
-size_t t3d_loss_workspace_bytes(int B, int H, int W, int multi_scale);
+/* `flags` of the loss entry points: */
+#define T3D_LOSS_MULTI_SCALE 0x1   /* utils/loss.py:104,133: also evaluate the 2x2 average-pooled scale (weight 0.35) */
+#define T3D_LOSS_CONF_MIN_ONLY 0x2 /* clamp the confidence from below only (>= 1e-5, no upper clamp at 10): the
+                                    * "original loss calculation" of train_thermal_dustr.py:278-279,305-318, which
+                                    * never goes through utils/loss.py's clamp(conf, 1e-5, 10) */
+size_t t3d_loss_workspace_bytes(int B, int H, int W, int flags);
 
 /* Thermal-gradient statistics (utils/loss.py:184-201,239-249): for every
  * sample, view and scale, mean|Dx gray| and mean|Dy gray| over all h*w entries
@@ -120,7 +125,7 @@ int t3d_loss_fwd_bwd(const float* pred1, const float* pred2,
                      const float* thermal1, const float* thermal2, int thermal_channels,
                      const float* thermal_stats1, const float* thermal_stats2, int stats_tiles,
                      float* dpred1, float* dpred2, float* dconf1, float* dconf2,
-                     int B, int H, int W, int multi_scale,
+                     int B, int H, int W, int flags,
                      float alpha, float edge_weight, float smoothness_weight, float detail_weight,
                      float grad_scale,
                      float* out_sample, float* out_batch, double* out_sample_f64,
@@ -132,7 +137,7 @@ int t3d_loss_fwd(const float* pred1, const float* pred2,
                  const float* conf1, const float* conf2,
                  const float* thermal1, const float* thermal2, int thermal_channels,
                  const float* thermal_stats1, const float* thermal_stats2, int stats_tiles,
-                 int B, int H, int W, int multi_scale,
+                 int B, int H, int W, int flags,
                  float alpha, float edge_weight, float smoothness_weight, float detail_weight,
                  float* out_sample, float* out_batch, double* out_sample_f64,
                  void* workspace, size_t workspace_bytes, void* stream);
@@ -304,10 +309,15 @@ int t3d_pack_step_result(const float* loss_per_sample, const double* metrics_f64
                          double* out16, void* stream);
 /* t3d_loss_rescale_invalid + t3d_pack_step_result as ONE launch (the tail of a training step,
  * train_thermal_dustr.py:320,359-360): out16 as above; when some samples are invalid their
- * gradients are zeroed and the others rescaled by B / n_valid (dconf may be NULL). */
+ * gradients are zeroed and the others rescaled by B / n_valid (dconf may be NULL).
+ * defer_rescale != 0 (data parallel, the batch spans several ranks): only the zeroing happens here; after the
+ * vector has been summed over the ranks, t3d_rescale_global multiplies this rank's gradients by
+ * out16_global[6] / out16_global[5] = (samples / valid samples) of the GLOBAL batch (a no-op kernel when equal). */
 int t3d_step_epilogue(float* dpred1, float* dpred2, float* dconf1, float* dconf2,
                       const float* loss_per_sample, const float* loss_batch, const double* metrics_f64,
-                      int B, int H, int W, int n_images, double* out16, void* stream);
+                      int B, int H, int W, int n_images, int defer_rescale, double* out16, void* stream);
+int t3d_rescale_global(float* dpred1, float* dpred2, float* dconf1, float* dconf2, const float* loss_per_sample,
+                       const double* out16_global, int B, int H, int W, void* stream);
 /* Data-parallel variant over peer memory (one process per GPU, one NVLink / NVSwitch node; replaces the per-step
  * NCCL all-reduce of out16 -- SURVEY.md 8e): every rank owns a mailbox of t3d_mailbox_bytes() zero-initialised bytes
  * that its peers can address (CUDA IPC / symmetric memory); peer_mailboxes = HOST array of the `world` device
@@ -315,7 +325,12 @@ int t3d_step_epilogue(float* dpred1, float* dpred2, float* dconf1, float* dconf2
  * t3d_step_epilogue does and also stores the rank's 16 doubles into every rank's mailbox (step = 0, 1, 2, ...);
  * t3d_mailbox_reduce waits (on the device) for the world's vectors of `step` and adds them in rank order into
  * out16.  Per rank, reduce(step) must be enqueued before epilogue(step + 1) -- that is what makes the two
- * alternating slots safe to reuse. */
+ * alternating slots safe to reuse.
+ * Validity across ranks (train_thermal_dustr.py:320,357-360 over the GLOBAL batch): the gradients carry the a-priori
+ * scale 1 / (B * world); t3d_step_epilogue_peers zeroes the gradients of this rank's invalid samples, and
+ * t3d_mailbox_reduce -- given the gradient buffers of that step (dpred1 != NULL) -- multiplies this rank's gradients
+ * by (B * world) / n_valid_global when any sample of any rank was invalid (all blocks return at once otherwise).
+ * The gradients of a data-parallel step are therefore final once its reduction has run. */
 #define T3D_MAX_PEERS 16
 size_t t3d_mailbox_bytes(void);
 int t3d_step_epilogue_peers(float* dpred1, float* dpred2, float* dconf1, float* dconf2,
@@ -323,7 +338,9 @@ int t3d_step_epilogue_peers(float* dpred1, float* dpred2, float* dconf1, float* 
                             int B, int H, int W, int n_images, double* out16_local,
                             const unsigned long long* peer_mailboxes, int world, int rank,
                             unsigned long long step, void* stream);
-int t3d_mailbox_reduce(const void* my_mailbox, int world, unsigned long long step, double* out16, void* stream);
+int t3d_mailbox_reduce(const void* my_mailbox, int world, unsigned long long step, double* out16,
+                       float* dpred1, float* dpred2, float* dconf1, float* dconf2,
+                       const float* loss_per_sample, int B, int H, int W, void* stream);
 
 #ifdef __cplusplus
 }

@@ -39,6 +39,17 @@ def confidence_weighted_regression_loss_torch(p1, p2, g1, g2, c1=None, c2=None, 
     return total
 
 
+def plain_confidence_loss_torch(p1, p2, g1, g2, conf1, conf2, alpha=0.2):
+    """train_thermal_dustr.py:278-279,305-318 ("original loss calculation", --use_thermal_aware_loss off): the
+    confidence is clamped from below only (clamp(min=1e-5)); no upper clamp at 10 as in utils/loss.py:91-92."""
+    conf1, conf2 = torch.clamp(conf1, min=1e-5), torch.clamp(conf2, min=1e-5)        # :278-279
+    loss1 = torch.abs(p1 - g1).mean(dim=-1)                                          # :307
+    loss2 = torch.abs(p2 - g2).mean(dim=-1)                                          # :308
+    w1 = (conf1 * loss1 - alpha * torch.log(conf1)).mean()                           # :313
+    w2 = (conf2 * loss2 - alpha * torch.log(conf2)).mean()                           # :314
+    return w1 + w2                                                                   # :317
+
+
 def _gray_torch(t):
     """utils/loss.py:119-124 (left-to-right fp32 sum)."""
     if t.shape[0] == 3:

@@ -3,6 +3,7 @@ import sys
 
 import pytest
 
+os.environ.setdefault("T3D_DEBUG_CHECKS", "1")     # verify caller promises (thermal_replicated) on the device in tests
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)

@@ -304,6 +304,32 @@ def test_replicated_thermal_planes_read_once(cuda_device, H, W, multi):
     np.testing.assert_allclose(b["per_sample"][:, :5].cpu().numpy(), rows, rtol=1e-5)
 
 
+def test_wrong_replicated_promise_is_caught_in_debug_mode(cuda_device):
+    """thermal_replicated=True is a caller promise; in debug / test mode (T3D_DEBUG_CHECKS=1, tests/conftest.py) it is
+    verified on the device, so a wrong flag raises instead of silently changing the result."""
+    from thermal3d_vision_b200 import loss as t3d
+    assert t3d.DEBUG_CHECKS
+    d = [x.to(cuda_device) for x in ref_loss.make_batch_inputs(2, 32, 64, seed=1)]
+    t3d.fused_thermal_loss_fwd_bwd(*d, multi_scale=False, thermal_replicated=True, **KW)     # replicas: fine
+    d[6][1, 2, 5, 7] += 1e-3                                  # one pixel of one plane differs
+    with pytest.raises(ValueError, match="not bit-identical"):
+        t3d.fused_thermal_loss_fwd_bwd(*d, multi_scale=False, thermal_replicated=True, **KW)
+
+
+def test_second_backward_raises(cuda_device):
+    """The precomputed gradients are scaled in place and handed over once: a second backward through the same node
+    raises instead of silently contributing zeros."""
+    from thermal3d_vision_b200 import loss as t3d
+    d = [x.to(cuda_device) for x in ref_loss.make_batch_inputs(1, 16, 32, seed=2)]
+    d[0].requires_grad_()
+    res = t3d.fused_thermal_loss(*d, multi_scale=False, **KW)
+    res.loss.backward(retain_graph=True)
+    with pytest.raises(RuntimeError, match="already consumed"):
+        res.loss.backward()
+    f = t3d.fused_thermal_loss(*(x.detach() for x in d), multi_scale=False, **KW)      # no grad: nothing to hand back
+    assert not f.loss.requires_grad
+
+
 @pytest.mark.parametrize("H,W", [(130, 516), (65, 132), (4, 8), (38, 52), (224, 224)])
 def test_multi_scale_split_path_edge_shapes(cuda_device, H, W):
     """multi_scale=True on vector-aligned shapes runs the half-resolution pass (t3d_loss_scale2.cu) + the marching

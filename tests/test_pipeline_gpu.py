@@ -140,25 +140,175 @@ def test_peer_mailbox_exchange_world_of_one(cuda_device):
     per_sample[:, 5] = torch.tensor([1.0, 0.0, 1.0])                         # sample 1 invalid
     batch = torch.tensor([0, 0, 0, 0, 0, 2.0, float(B), 0], dtype=torch.float32, device=cuda_device)
     m64 = torch.rand(B, 8, generator=g, dtype=torch.float64).to(cuda_device)
-    grads = [torch.ones(B, H, W, 3, device=cuda_device), torch.ones(B, H, W, 3, device=cuda_device),
-             torch.ones(B, H, W, device=cuda_device), torch.ones(B, H, W, device=cuda_device)]
+    mk = lambda: [torch.ones(B, H, W, 3, device=cuda_device), torch.ones(B, H, W, 3, device=cuda_device),
+                  torch.ones(B, H, W, device=cuda_device), torch.ones(B, H, W, device=cuda_device)]
+    grads = mk()
     ref = torch.zeros(16, dtype=torch.float64, device=cuda_device)
     st = _lib.current_stream_ptr()
     _lib.check(lib.t3d_step_epilogue(*[_lib.ptr(x) for x in grads], _lib.ptr(per_sample), _lib.ptr(batch), _lib.ptr(m64),
-                                     B, H, W, B, _lib.ptr(ref), st), "t3d_step_epilogue")
+                                     B, H, W, B, 0, _lib.ptr(ref), st), "t3d_step_epilogue")
     assert torch.count_nonzero(grads[0][1]) == 0 and torch.all(grads[0][0] == 1.5)    # fix-up: B / n_valid = 3 / 2
+    # deferred variant (data parallel): zeros only; t3d_rescale_global applies samples / valid of the all-reduced vector
+    g2 = mk()
+    out = torch.zeros(16, dtype=torch.float64, device=cuda_device)
+    _lib.check(lib.t3d_step_epilogue(*[_lib.ptr(x) for x in g2], _lib.ptr(per_sample), _lib.ptr(batch), _lib.ptr(m64),
+                                     B, H, W, B, 1, _lib.ptr(out), st), "t3d_step_epilogue")
+    assert torch.equal(out, ref) and torch.count_nonzero(g2[0][1]) == 0 and torch.all(g2[0][0] == 1.0)
+    glob = out.clone(); glob[5] += 3; glob[6] += 3                                  # a second rank with 3 valid samples
+    _lib.check(lib.t3d_rescale_global(*[_lib.ptr(x) for x in g2], _lib.ptr(per_sample), _lib.ptr(glob), B, H, W, st),
+               "t3d_rescale_global")
+    assert torch.count_nonzero(g2[2][1]) == 0 and torch.all(g2[0][2] == 1.2) and torch.all(g2[3][0] == 1.2)   # 6 / 5
     mailbox = torch.zeros(int(lib.t3d_mailbox_bytes()) // 8, dtype=torch.float64, device=cuda_device)
-    batch_ok = batch.clone(); batch_ok[5] = float(B)                              # no second fix-up of the gradients
+    null = [None] * 5
     for world in (1, 2):
         mailbox.zero_()
         peers = (C.c_uint64 * world)(*([mailbox.data_ptr()] * world))
         for step in range(5):
+            grads = mk()
             local = torch.zeros(16, dtype=torch.float64, device=cuda_device)
             out = torch.full((16,), -1.0, dtype=torch.float64, device=cuda_device)
             for rank in range(world):                                             # every "rank" posts into the one mailbox
-                _lib.check(lib.t3d_step_epilogue_peers(*[_lib.ptr(x) for x in grads], _lib.ptr(per_sample), _lib.ptr(batch_ok),
+                _lib.check(lib.t3d_step_epilogue_peers(*[_lib.ptr(x) for x in grads], _lib.ptr(per_sample), _lib.ptr(batch),
                                                        _lib.ptr(m64), B, H, W, B, _lib.ptr(local), peers, world, rank, step, st),
                            "t3d_step_epilogue_peers")
-            _lib.check(lib.t3d_mailbox_reduce(_lib.ptr(mailbox), world, step, _lib.ptr(out), st), "t3d_mailbox_reduce")
+            assert torch.count_nonzero(grads[0][1]) == 0 and torch.all(grads[0][0] == 1.0)     # zeros only
+            if step % 2 == 0:       # vector only
+                _lib.check(lib.t3d_mailbox_reduce(_lib.ptr(mailbox), world, step, _lib.ptr(out), *null, 0, 0, 0, st), "t3d_mailbox_reduce")
+            else:                   # + the global validity factor: world * 3 samples, world * 2 valid
+                _lib.check(lib.t3d_mailbox_reduce(_lib.ptr(mailbox), world, step, _lib.ptr(out), *[_lib.ptr(x) for x in grads],
+                                                  _lib.ptr(per_sample), B, H, W, st), "t3d_mailbox_reduce")
+                assert torch.count_nonzero(grads[1][1]) == 0 and torch.all(grads[0][0] == 1.5) and torch.all(grads[3][2] == 1.5)
             assert torch.equal(local, ref)
             assert torch.equal(out, ref * world), (world, step)
+
+
+def test_two_rank_validity_matches_single_process(cuda_device):
+    """Global validity semantics (train_thermal_dustr.py:320,357-360 over the data-parallel batch): two "ranks" of B
+    samples each, one sample invalid on rank 1, exchanged through one shared mailbox, give every rank the gradients
+    a single process computes on the 2B batch -- bit for bit (same kernels, same 1 / (2B) a-priori scale, same
+    (2B) / n_valid factor) -- and the reduced vector equals the single process's packed vector."""
+    import ctypes as C
+    from thermal3d_vision_b200 import _lib
+    from thermal3d_vision_b200 import loss as t3d
+    lib = _lib.lib()
+    B, H, W = 2, 40, 128
+    P1, P2, G1, G2, C1, C2, T1, T2 = ref_loss.make_batch_inputs(2 * B, H, W, seed=31)
+    P2[3, 4, 5, 0] = float("inf")                                    # global sample 3 = rank 1's sample 1
+    d = [x.to(cuda_device) for x in (P1, P2, G1, G2, C1, C2, T1, T2)]
+    st = _lib.current_stream_ptr()
+    names = ("dpred1", "dpred2", "dconf1", "dconf2")
+
+    # single process, batch 2B
+    whole = t3d.fused_thermal_loss_fwd_bwd(*d, multi_scale=False, rescale_invalid=False, **KW)
+    ref16 = torch.zeros(16, dtype=torch.float64, device=cuda_device)
+    _lib.check(lib.t3d_step_epilogue(*[_lib.ptr(whole[k]) for k in names], _lib.ptr(whole["per_sample"]), _lib.ptr(whole["batch"]),
+                                     None, 2 * B, H, W, 0, 0, _lib.ptr(ref16), st), "t3d_step_epilogue")
+    assert whole["per_sample"][:, 5].tolist() == [1.0, 1.0, 1.0, 0.0]
+
+    # two ranks of B samples: a-priori scale 1 / (B * world)
+    mailbox = torch.zeros(int(lib.t3d_mailbox_bytes()) // 8, dtype=torch.float64, device=cuda_device)
+    peers = (C.c_uint64 * 2)(mailbox.data_ptr(), mailbox.data_ptr())
+    parts = []
+    for rank in range(2):
+        sl = slice(rank * B, (rank + 1) * B)
+        r = t3d.fused_thermal_loss_fwd_bwd(*[x[sl].contiguous() for x in d], multi_scale=False, rescale_invalid=False,
+                                           grad_scale=1.0 / (2 * B), **KW)
+        local = torch.zeros(16, dtype=torch.float64, device=cuda_device)
+        _lib.check(lib.t3d_step_epilogue_peers(*[_lib.ptr(r[k]) for k in names], _lib.ptr(r["per_sample"]), _lib.ptr(r["batch"]),
+                                               None, B, H, W, 0, _lib.ptr(local), peers, 2, rank, 0, st), "t3d_step_epilogue_peers")
+        parts.append(r)
+    for rank in range(2):
+        r = parts[rank]
+        out = torch.zeros(16, dtype=torch.float64, device=cuda_device)
+        _lib.check(lib.t3d_mailbox_reduce(_lib.ptr(mailbox), 2, 0, _lib.ptr(out), *[_lib.ptr(r[k]) for k in names],
+                                          _lib.ptr(r["per_sample"]), B, H, W, st), "t3d_mailbox_reduce")
+        assert out[5].item() == 3.0 and out[6].item() == 4.0
+        torch.testing.assert_close(out[:5], ref16[:5], rtol=1e-12, atol=0)      # sums of the same fp32 numbers, other order
+        sl = slice(rank * B, (rank + 1) * B)
+        for k in names:
+            assert torch.equal(r[k], whole[k][sl]), (rank, k)
+    assert torch.count_nonzero(parts[1]["dpred1"][1]) == 0 and torch.count_nonzero(parts[0]["dpred1"]) > 0
+
+
+def test_pipelined_steps_equal_plain_steps(cuda_device):
+    """pipelined=True (consecutive steps overlap on the internal streams, outputs alternate between two sets) gives
+    the bits of the plain step, for every step of a sequence with changing inputs."""
+    from thermal3d_vision_b200.pipeline import HotPathStep
+    import bench
+    B, H, W = 3, 96, 128
+    seqs = [bench.make_inputs_torch(B, H, W, seed=40 + k, device=cuda_device, raw_hw=(128, 160)) for k in range(3)]
+    order = [0, 1, 2, 1, 0]
+    key = ("raw1", "raw2", "pred1", "pred2", "gt1", "gt2", "conf1", "conf2", "gt_depth")
+    plain = HotPathStep(B, H, W, raw_hw=(128, 160), device=cuda_device, **KW)
+    want = []
+    for k in order:
+        r = plain.run_device(*[seqs[k][n] for n in key]).clone()
+        want.append((r, plain.loss_out["dpred1"].clone(), plain.loss_out["dconf2"].clone(), plain.pre_both["thermal"].clone()))
+    piped = HotPathStep(B, H, W, raw_hw=(128, 160), device=cuda_device, pipelined=True, **KW)
+    got = []
+    for k in order:
+        r = piped.run_device(*[seqs[k][n] for n in key])
+        piped.wait_result(r)
+        got.append((r.clone(), piped.loss_out["dpred1"].clone(), piped.loss_out["dconf2"].clone(), piped.pre_both["thermal"].clone()))
+    # and without waiting in between: only the last two steps' sets are still around
+    for k in order:
+        r = piped.run_device(*[seqs[k][n] for n in key])
+    piped.finish()
+    torch.cuda.synchronize()
+    for (a, b) in zip(want, got):
+        for x, y in zip(a, b):
+            assert torch.equal(x, y)
+    assert torch.equal(r, want[-1][0]) and torch.equal(piped.loss_out["dpred1"], want[-1][1])
+
+
+def test_bench_configuration_matches_oracle(cuda_device):
+    """The exact thing bench.py times -- HotPathStep at batch 64, 512x384 pointmaps, 640x512 raw frames from
+    bench.make_inputs_torch, replicated-plane flag, statistics hand-off, internal streams, epilogue -- against the
+    oracle loop (train_thermal_dustr.py:182-360 + utils/metrics.py:72-138 restated) on the same inputs."""
+    from thermal3d_vision_b200.pipeline import HotPathStep
+    import bench
+    B, H, W = 64, 384, 512
+    d = bench.make_inputs_torch(B, H, W, seed=0, device=cuda_device)
+    key = ("raw1", "raw2", "pred1", "pred2", "gt1", "gt2", "conf1", "conf2", "gt_depth")
+    step = HotPathStep(B, H, W, device=cuda_device, pipelined=True, **KW)
+    for _ in range(3):                                   # as in the bench: steps in flight behind each other
+        r = step.run_device(*[d[n] for n in key])
+    step.finish()
+    s = HotPathStep.summarize(r.cpu())
+    c = {n: d[n].cpu() for n in key}
+    T1, T2, mean, rows, valid, grads, metrics = _oracle_step(c["raw1"].numpy(), c["raw2"].numpy(), c["pred1"], c["pred2"],
+                                                             c["gt1"], c["gt2"], c["conf1"], c["conf2"], c["gt_depth"], H, W, False)
+    assert np.array_equal(step.pre_both["thermal"][:B].cpu().numpy(), T1.numpy())        # bit-exact preprocessing
+    assert np.array_equal(step.pre_both["thermal"][B:].cpu().numpy(), T2.numpy())
+    assert s["n_valid"] == B == float(valid.sum()) and s["n_images"] == B
+    assert s["loss"] == pytest.approx(mean, rel=1e-5)
+    np.testing.assert_allclose(step.loss_out["per_sample"][:, :5].cpu().numpy(), rows, rtol=1e-5)
+    for name, ref in zip(("dpred1", "dpred2", "dconf1", "dconf2"), grads):
+        got = step.loss_out[name].cpu()
+        torch.testing.assert_close(got, ref, rtol=1e-4, atol=1e-6, msg=lambda m: f"{name}: {m}")
+        # atol 1e-6 is loose at this size (|g| ~ 5e-6): also bound the error relative to the gradient's own scale
+        scale = ref.abs().mean().item()
+        assert (got - ref).abs().max().item() <= 2e-3 * scale, name
+    for k in ref_metrics.KEYS7:
+        assert s[k] == pytest.approx(metrics[k], rel=1e-5), k
+
+
+def test_second_device(cuda_device):
+    """Tensors on cuda:1 while cuda:0 is the current device: every entry point launches on the tensors' device
+    (the library launches on the CURRENT device; the host side guards it).  Needs two GPUs."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    from thermal3d_vision_b200.pipeline import HotPathStep
+    import bench
+    B, H, W = 2, 64, 128
+    key = ("raw1", "raw2", "pred1", "pred2", "gt1", "gt2", "conf1", "conf2", "gt_depth")
+    d0 = bench.make_inputs_torch(B, H, W, seed=3, device=torch.device("cuda:0"), raw_hw=(96, 160))
+    a = HotPathStep(B, H, W, raw_hw=(96, 160), device="cuda:0", **KW).run_device(*[d0[n] for n in key]).cpu()
+    assert torch.cuda.current_device() == 0
+    d1 = {n: v.to("cuda:1") for n, v in d0.items()}
+    both = torch.cat([d1["raw1"], d1["raw2"]])
+    d1["raw1"], d1["raw2"] = both[:B], both[B:]
+    step1 = HotPathStep(B, H, W, raw_hw=(96, 160), device="cuda:1", **KW)
+    b = step1.run_device(*[d1[n] for n in key]).cpu()
+    assert torch.cuda.current_device() == 0 and step1.loss_out["dpred1"].device.index == 1
+    assert torch.equal(a, b)

@@ -70,6 +70,36 @@ def test_training_batch_loss_matches_reference_loop(cuda_device, conf_source):
         torch.testing.assert_close(k1.grad.cpu(), c1.grad, rtol=1e-4, atol=1e-6)
 
 
+def test_plain_loss_path_clamps_confidence_from_below_only(cuda_device):
+    """use_thermal_aware_loss=False (train_thermal_dustr.py:305-318): confidences above 10 (DUSt3R's 1 + exp routinely
+    is) are NOT clamped, unlike utils/loss.py:91-92; below 1e-5 they are (and take no gradient)."""
+    from thermal3d_vision_b200.training import training_batch_loss
+    B, H, W = 3, 36, 44
+    P1, P2, G1, G2, *_ = ref_loss.make_batch_inputs(B, H, W, seed=4)
+    g = torch.Generator().manual_seed(9)
+    C1 = 30 * torch.rand(B, H, W, generator=g) - 1.0        # spans < 1e-5 (incl. negative) ... 29
+    C2 = 1 + torch.exp(3 * torch.randn(B, H, W, generator=g))
+    p1, p2 = P1.clone().requires_grad_(), P2.clone().requires_grad_()
+    c1, c2 = C1.clone().requires_grad_(), C2.clone().requires_grad_()
+    tot, nv = 0.0, 0
+    for i in range(B):
+        loss = ref_loss.plain_confidence_loss_torch(p1[i], p2[i], G1[i], G2[i], c1[i], c2[i])
+        if torch.isfinite(loss) and loss > 0:
+            tot = tot + loss; nv += 1
+    assert nv == B and (C1 > 10).any() and (C2 > 10).any() and (C1 < 1e-5).any()
+    (tot / nv).backward()
+    d = lambda t: t.to(cuda_device)
+    q1, q2, k1, k2 = d(P1).requires_grad_(), d(P2).requires_grad_(), d(C1).requires_grad_(), d(C2).requires_grad_()
+    res = training_batch_loss(q1, q2, d(G1), d(G2), pred_conf1=k1, pred_conf2=k2, use_thermal_aware_loss=False)
+    res.loss.backward()
+    assert res.loss.item() == pytest.approx((tot / nv).item(), rel=1e-5)
+    for got, ref in ((q1.grad, p1.grad), (q2.grad, p2.grad), (k1.grad, c1.grad), (k2.grad, c2.grad)):
+        torch.testing.assert_close(got.cpu(), ref, rtol=1e-4, atol=1e-6)
+    # the thermal-aware path keeps utils/loss.py's clamp to [1e-5, 10]: a different number on the same inputs
+    clamped = training_batch_loss(d(P1), d(P2), d(G1), d(G2), pred_conf1=d(C1), pred_conf2=d(C2), thermal1=None, thermal2=None)
+    assert abs(clamped.loss.item() - res.loss.item()) > 1e-3
+
+
 def test_validation_batch_loss(cuda_device):
     from thermal3d_vision_b200.training import validation_batch_loss
     B, H, W = 4, 32, 36

@@ -15,6 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libt3d_sm100.so")
 CSRC_DIR = os.path.join(_HERE, "csrc")
 
+ABI_VERSION = 2    # T3D_ABI_VERSION of include/t3d.h
 _lock = threading.Lock()
 _lib = None
 
@@ -68,10 +69,11 @@ _SIGNATURES = {
     "t3d_sobel_enhance_fwd": (C.c_int, [c_ptr, c_ptr] + [C.c_int] * 5 + [c_ptr, c_ptr, C.c_size_t, c_ptr]),
     "t3d_sobel_enhance_bwd_params": (C.c_int, [c_ptr, c_ptr, c_ptr] + [C.c_int] * 5 + [c_ptr, c_ptr, C.c_size_t, c_ptr]),
     "t3d_pack_step_result": (C.c_int, [c_ptr, c_ptr, C.c_int, C.c_int, c_ptr, c_ptr]),
-    "t3d_step_epilogue": (C.c_int, [c_ptr] * 7 + [C.c_int] * 4 + [c_ptr, c_ptr]),
+    "t3d_step_epilogue": (C.c_int, [c_ptr] * 7 + [C.c_int] * 5 + [c_ptr, c_ptr]),
+    "t3d_rescale_global": (C.c_int, [c_ptr] * 6 + [C.c_int] * 3 + [c_ptr]),
     "t3d_mailbox_bytes": (C.c_size_t, []),
     "t3d_step_epilogue_peers": (C.c_int, [c_ptr] * 7 + [C.c_int] * 4 + [c_ptr, c_ptr, C.c_int, C.c_int, C.c_uint64, c_ptr]),
-    "t3d_mailbox_reduce": (C.c_int, [c_ptr, C.c_int, C.c_uint64, c_ptr, c_ptr]),
+    "t3d_mailbox_reduce": (C.c_int, [c_ptr, C.c_int, C.c_uint64, c_ptr] + [c_ptr] * 5 + [C.c_int] * 3 + [c_ptr]),
     "t3d_project_points": (C.c_int, [c_ptr] + [C.c_float] * 4 + [c_ptr, C.c_size_t, c_ptr]),
 }
 
@@ -111,7 +113,7 @@ def lib():
                 fn = getattr(handle, name)      # AttributeError if a symbol is missing
                 fn.restype = res
                 fn.argtypes = args
-            if handle.t3d_version() != 1:
+            if handle.t3d_version() != ABI_VERSION:
                 raise T3DError("libt3d_sm100.so ABI version mismatch")
             _lib = handle
     return _lib
@@ -155,9 +157,57 @@ def ptr(t):
     return None if t is None else t.data_ptr()
 
 
-def current_stream_ptr():
+def current_stream_ptr(device=None):
+    """cudaStream_t of torch's current stream on `device` (default: the current device; inside `on_tensor_device`
+    / `device_guard` that is the device the tensors live on)."""
     import torch
-    return torch.cuda.current_stream().cuda_stream
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def _first_cuda_device(objs):
+    import torch
+    for o in objs:
+        if isinstance(o, torch.Tensor):
+            if o.is_cuda:
+                return o.device
+        elif isinstance(o, dict):
+            d = _first_cuda_device(o.values())
+            if d is not None:
+                return d
+        elif isinstance(o, (list, tuple)):
+            d = _first_cuda_device(o)
+            if d is not None:
+                return d
+    return None
+
+
+def device_guard(device):
+    """Context manager making `device` the current CUDA device: the library launches on the CURRENT device (it never
+    calls cudaSetDevice) and takes the stream from torch's current stream, so every entry point runs under the guard
+    of the device its tensors live on -- tensors on cuda:1 while cuda:0 is current would otherwise get kernels
+    launched on device 0 with device-1 pointers."""
+    import contextlib
+    import torch
+    if device is None:
+        return contextlib.nullcontext()
+    device = torch.device(device)
+    if device.type != "cuda" or device.index is None or device.index == torch.cuda.current_device():
+        return contextlib.nullcontext()
+    return torch.cuda.device(device)
+
+
+def on_tensor_device(fn):
+    """Decorator: run `fn` with the device of its first CUDA tensor argument as the current device."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapped(*args, **kwargs):
+        dev = _first_cuda_device(args) or _first_cuda_device(kwargs.values())
+        if dev is None:
+            return fn(*args, **kwargs)
+        with device_guard(dev):
+            return fn(*args, **kwargs)
+    return wrapped
 
 
 def require_cuda(*tensors):

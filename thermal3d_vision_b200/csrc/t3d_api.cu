@@ -66,6 +66,12 @@ int t3d_sm_count() {
     return g_sm_count > 0 ? g_sm_count : 148;
 }
 
+int t3d_device_slot() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0) dev = 0;
+    return dev % kT3dMaxDevices;
+}
+
 extern "C" {
 
 int t3d_version(void) { return T3D_ABI_VERSION; }

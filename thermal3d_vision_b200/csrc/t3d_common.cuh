@@ -44,7 +44,11 @@ void t3d_count_launch(int n = 1);
         t3d_count_launch();                                                          \
     } while (0)
 
-int t3d_sm_count();   // cached per process (current device at first call)
+int t3d_sm_count();   // cached per process (current device at first call; every device of a B200 box is the same part)
+// Index of the calling thread's current CUDA device, for per-device one-time setup (cudaFuncSetAttribute is per
+// device: a process that drives several GPUs must repeat it on each).
+constexpr int kT3dMaxDevices = 64;
+int t3d_device_slot();
 
 // Optional per-kernel CUDA-event timing (t3d_profile_begin / t3d_profile_end in include/t3d.h).
 bool t3d_prof_before(const char* name, cudaStream_t st);

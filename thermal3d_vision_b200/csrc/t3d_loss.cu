@@ -12,6 +12,7 @@
 //   loss_finalize_kernel   deterministic fixed-order fp64 second stage
 //   rescale / scale        device-conditional gradient rescaling (no host sync)
 #include "t3d_loss_internal.cuh"
+#include <string.h>
 
 #include <stdlib.h>
 
@@ -182,6 +183,7 @@ struct LossArgs {
     float kb;                     // grad_scale / (3 H W)
     float kc;                     // grad_scale / (H W)
     float kE[2], kS[2], kD[2];    // grad_scale * lambda_s * weight / n_s
+    float conf_max;               // upper clamp of the confidence: 10 (utils/loss.py:91), +inf with T3D_LOSS_CONF_MIN_ONLY
 };
 
 template <bool MULTI>
@@ -317,7 +319,7 @@ __global__ void __launch_bounds__(kThreads, MULTI ? 2 : 3) loss_tile_kernel(cons
                 const float dx = p[3 * e] - g[3 * e], dy = p[3 * e + 1] - g[3 * e + 1], dz = p[3 * e + 2] - g[3 * e + 2];
                 const float l = ((fabsf(dx) + fabsf(dy)) + fabsf(dz)) / 3.0f;             // utils/loss.py:82
                 const float craw = c[e];
-                const float cc = (craw < kConfMin) ? kConfMin : ((craw > kConfMax) ? kConfMax : craw);   // :91, NaN passes
+                const float cc = (craw < kConfMin) ? kConfMin : ((craw > a.conf_max) ? a.conf_max : craw);   // :91, NaN passes
                 const bool ok = e < nvalid;
                 if (ok) sum_basic += cc * l - a.alpha * logf(cc);                          // :95
                 zq[e] = p[3 * e + 2];
@@ -327,7 +329,7 @@ __global__ void __launch_bounds__(kThreads, MULTI ? 2 : 3) loss_tile_kernel(cons
                     gq[k][3 * e] = sgnf(dx) * kc3;
                     gq[k][3 * e + 1] = sgnf(dy) * kc3;
                     gq[k][3 * e + 2] = sgnf(dz) * kc3;
-                    const bool inside = (craw >= kConfMin) && (craw <= kConfMax);         // clamp grad mask (inclusive)
+                    const bool inside = (craw >= kConfMin) && (craw <= a.conf_max);       // clamp grad mask (inclusive)
                     dc[e] = inside ? (l - a.alpha / cc) * a.kc : 0.f;
                 }
             }
@@ -795,6 +797,8 @@ WsLayout ws_layout(int B, int H, int W, int multi = 0) {
     return L;
 }
 
+inline float __int_as_float_host(unsigned int u) { float f; memcpy(&f, &u, sizeof(f)); return f; }
+
 int check_dims(int B, int H, int W) {
     T3D_REQUIRE(B >= 1 && H >= 1 && W >= 1, "bad dims B=%d H=%d W=%d", B, H, W);
     T3D_REQUIRE((double)B * 2.0 * H * W < 2.0e9, "problem too large for 32-bit tile indexing");
@@ -821,7 +825,8 @@ int run_stats(const float* t1, const float* t2, int tch, int B, int H, int W, in
 
 template <bool MULTI, bool VEC, bool BWD>
 int launch_loss(const LossArgs& la, cudaStream_t st) {
-    static bool attr_set = false;   // benign race: idempotent
+    static bool attr_done[kT3dMaxDevices] = {};   // per device; benign race: idempotent
+    bool& attr_set = attr_done[t3d_device_slot()];
     constexpr size_t smem = loss_smem_bytes<MULTI>();
     if (!attr_set) {
         T3D_CUDA(cudaFuncSetAttribute(loss_tile_kernel<MULTI, VEC, BWD>,
@@ -836,10 +841,13 @@ int launch_loss(const LossArgs& la, cudaStream_t st) {
 int loss_impl(bool bwd, const float* pred1, const float* pred2, const float* gt1, const float* gt2,
               const float* conf1, const float* conf2, const float* thermal1, const float* thermal2,
               int tch, const float* ustats1, const float* ustats2, int ustats_tiles, float* dpred1, float* dpred2, float* dconf1, float* dconf2,
-              int B, int H, int W, int multi, float alpha, float ew, float sw, float dw, float gscale,
+              int B, int H, int W, int flags, float alpha, float ew, float sw, float dw, float gscale,
               float* out_sample, float* out_batch, double* out_f64,
               void* workspace, size_t ws_bytes, void* stream) {
     if (int rc = check_dims(B, H, W)) return rc;
+    T3D_REQUIRE((flags & ~(T3D_LOSS_MULTI_SCALE | T3D_LOSS_CONF_MIN_ONLY)) == 0, "unknown loss flags 0x%x", flags);
+    const int multi = (flags & T3D_LOSS_MULTI_SCALE) ? 1 : 0;
+    const bool conf_min_only = (flags & T3D_LOSS_CONF_MIN_ONLY) != 0;
     T3D_REQUIRE(pred1 && pred2 && gt1 && gt2, "pred/gt pointers must not be NULL");
     T3D_REQUIRE(out_sample && out_batch && workspace, "output / workspace pointers must not be NULL");
     const bool thermal_on = thermal1 != nullptr && thermal2 != nullptr;   // utils/loss.py:116
@@ -878,6 +886,7 @@ int loss_impl(bool bwd, const float* pred1, const float* pred2, const float* gt1
     la.B = B; la.H = H; la.W = W; la.tch = thermal_on ? tch : 0;
     la.tiles_x = L.tiles_x; la.tiles_y = L.tiles_y; la.stiles = stiles;
     la.alpha = alpha;
+    la.conf_max = conf_min_only ? __int_as_float_host(0x7f800000u) : kConfMax;
     const double N = (double)H * W, n2 = (double)(H / 2) * (W / 2);
     la.kb = (float)((double)gscale / (3.0 * N));
     la.kc = (float)((double)gscale / N);
@@ -901,7 +910,7 @@ int loss_impl(bool bwd, const float* pred1, const float* pred2, const float* gt1
     }();
     const float* partials2 = nullptr;
     int tiles2 = 0;
-    if (vec && thermal_on && march_rows > 0 && (!ms || (H >= 4 && W >= 4))) {
+    if (vec && thermal_on && march_rows > 0 && !conf_min_only && (!ms || (H >= 4 && W >= 4))) {
         // fast path: TMA-fed warp-marching kernel (t3d_loss_march.cu); multi-scale: the half-resolution terms run
         // first as their own pass (t3d_loss_scale2.cu) and hand their gradient to the marching kernel
         MarchArgs ma;
@@ -962,9 +971,9 @@ int loss_impl(bool bwd, const float* pred1, const float* pred2, const float* gt1
 // ====================================================================== C ABI
 extern "C" {
 
-size_t t3d_loss_workspace_bytes(int B, int H, int W, int multi_scale) {
+size_t t3d_loss_workspace_bytes(int B, int H, int W, int flags) {
     if (B < 1 || H < 1 || W < 1) return 0;
-    return ws_layout(B, H, W, multi_scale).total;
+    return ws_layout(B, H, W, (flags & T3D_LOSS_MULTI_SCALE) ? 1 : 0).total;
 }
 
 int t3d_thermal_grad_stats(const float* thermal1, const float* thermal2, int thermal_channels,

@@ -383,7 +383,8 @@ int launch(const MarchArgs& a, cudaStream_t st) {
     constexpr int WARPS = (TCH == 3) ? 10 : 12;
     constexpr size_t smem = (size_t)WARPS * NS * Stage<TCH>::kFloats * sizeof(float) + (size_t)WARPS * NS * 8;
     static_assert(smem <= 227 * 1024, "ring does not fit in shared memory");
-    static bool attr_set = false;
+    static bool attr_done[kT3dMaxDevices] = {};
+    bool& attr_set = attr_done[t3d_device_slot()];
     if (!attr_set) {
         T3D_CUDA(cudaFuncSetAttribute(loss_march_kernel<TCH, REP, BWD, S2, NS, WARPS>,
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -722,7 +722,8 @@ int t3d_depth_metrics(const float* pred, int pred_stride, int pred_offset,
     src.gt_h = gt_h; src.gt_w = gt_w; src.H = H; src.W = W; src.resample = (gt_h != H) || (gt_w != W);
     src.fx = (double)gt_w / (double)W; src.fy = (double)gt_h / (double)H;
     dim3 g((unsigned)chunks, (unsigned)B);
-    static bool attr_set = false;
+    static bool attr_done[kT3dMaxDevices] = {};
+    bool& attr_set = attr_done[t3d_device_slot()];
     if (!attr_set) {
         T3D_CUDA(cudaFuncSetAttribute(median_scale_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       kCandCap * (int)sizeof(unsigned int)));

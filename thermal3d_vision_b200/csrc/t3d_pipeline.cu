@@ -72,7 +72,27 @@ struct EpilogueArgs {
     float* dpred[2]; float* dconf[2];
     const float* out_sample; const float* out_batch; const double* metrics_f64;
     int B, n_images; size_t plane; double* out16;
+    int defer_rescale;      // data parallel: only zero the invalid samples here, the global factor comes later
 };
+
+// gradients of sample b *= valid_b ? scale : 0 (exact zeros: an invalid sample's gradients may hold NaN / Inf)
+__device__ __forceinline__ void rescale_samples(float* const dpred[2], float* const dconf[2], const float* __restrict__ out_sample,
+                                                int B, size_t plane, float scale) {
+    const size_t per_sample[2] = {plane * 3, plane};
+#pragma unroll
+    for (int which = 0; which < 4; ++which) {
+        float* base = (which < 2) ? dpred[which] : dconf[which - 2];
+        if (!base) continue;
+        const size_t n = per_sample[which >> 1];
+        const size_t total = n * B;
+        for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+            const int b = (int)(idx / n);
+            const bool valid = out_sample[(size_t)b * T3D_LOSS_OUT_STRIDE + 5] != 0.f;
+            const float f = valid ? scale : 0.f;
+            base[idx] = (f == 0.f) ? 0.f : ((f == 1.0f) ? base[idx] : base[idx] * f);
+        }
+    }
+}
 
 template <bool PEERS>
 __global__ void __launch_bounds__(128) step_epilogue_kernel(const EpilogueArgs a, const PeerArgs pa) {
@@ -126,33 +146,24 @@ __global__ void __launch_bounds__(128) step_epilogue_kernel(const EpilogueArgs a
     }
     const float nv = a.out_batch[5];
     if (nv == (float)a.B) return;                      // every sample valid: the a-priori 1/B scale is right
-    const size_t per_sample[2] = {a.plane * 3, a.plane};
-#pragma unroll
-    for (int which = 0; which < 4; ++which) {
-        float* base = (which < 2) ? a.dpred[which] : a.dconf[which - 2];
-        if (!base) continue;
-        const size_t n = per_sample[which >> 1];
-        const size_t total = n * a.B;
-        for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
-            const int b = (int)(idx / n);
-            const bool valid = a.out_sample[(size_t)b * T3D_LOSS_OUT_STRIDE + 5] != 0.f;
-            const float f = (valid && nv > 0.f) ? (float)a.B / nv : 0.f;
-            base[idx] = (f == 0.f) ? 0.f : base[idx] * f;          // invalid samples may hold NaN / Inf: exact zeros
-        }
-    }
+    // single process: valid samples * B / n_valid, invalid samples -> exact zeros.  Data parallel (PEERS): only the
+    // zeros here -- the factor is (B * world) / n_valid over the GLOBAL batch (train_thermal_dustr.py:320,357-360
+    // applied to the whole batch), which mailbox_reduce_kernel applies once it has the world's counts.
+    const float scale = (PEERS || a.defer_rescale) ? 1.0f : ((nv > 0.f) ? (float)a.B / nv : 0.f);
+    rescale_samples(a.dpred, a.dconf, a.out_sample, a.B, a.plane, scale);
 }
 
 }  // namespace
 
 extern "C" int t3d_step_epilogue(float* dpred1, float* dpred2, float* dconf1, float* dconf2,
                                  const float* loss_per_sample, const float* loss_batch, const double* metrics_f64,
-                                 int B, int H, int W, int n_images, double* out16, void* stream) {
+                                 int B, int H, int W, int n_images, int defer_rescale, double* out16, void* stream) {
     T3D_REQUIRE(loss_per_sample && loss_batch && out16, "NULL pointer");
     T3D_REQUIRE(B >= 1 && H >= 1 && W >= 1 && n_images >= 0, "bad dims");
     EpilogueArgs a;
     a.dpred[0] = dpred1; a.dpred[1] = dpred2; a.dconf[0] = dconf1; a.dconf[1] = dconf2;
     a.out_sample = loss_per_sample; a.out_batch = loss_batch; a.metrics_f64 = metrics_f64;
-    a.B = B; a.n_images = n_images; a.plane = (size_t)H * W; a.out16 = out16;
+    a.B = B; a.n_images = n_images; a.plane = (size_t)H * W; a.out16 = out16; a.defer_rescale = defer_rescale ? 1 : 0;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     PeerArgs pa;
     pa.world = 0; pa.rank = 0; pa.step = 0;
@@ -160,27 +171,46 @@ extern "C" int t3d_step_epilogue(float* dpred1, float* dpred2, float* dconf1, fl
     return T3D_OK;
 }
 
-__global__ void __launch_bounds__(32) mailbox_reduce_kernel(const Mailbox* __restrict__ box, int world, unsigned long long step,
-                                                            double* __restrict__ out16) {
-    const int lane = threadIdx.x, p = (int)(step & 1ull);
-    if (lane < world) {
-        const unsigned long long* f = &box->flags[p][lane];
-        unsigned long long v;
-        do {
-            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(f) : "memory");
-            if (v < step + 1ull) __nanosleep(200);
-        } while (v < step + 1ull);
-    }
-    __syncwarp();
-    if (lane < 16) {
-        double s = 0.0;
-        for (int r = 0; r < world; ++r) {                       // rank order: the same bits on every rank
-            double x;
-            asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(x) : "l"(&box->slots[p][r][lane]) : "memory");
-            s += x;
+struct ReduceArgs {
+    const Mailbox* box; int world; unsigned long long step; double* out16;
+    float* dpred[2]; float* dconf[2]; const float* out_sample; int B; size_t plane;     // this rank's step-`step` gradients (or NULL)
+};
+
+// Waits for the world's vectors of `step`, adds them in rank order (the same bits on every rank) and -- the global
+// validity semantics of train_thermal_dustr.py:320,357-360 over the data-parallel batch -- when any sample of ANY rank
+// was invalid, rescales this rank's gradients (a-priori scale 1 / (B * world), invalid samples already zeroed by the
+// epilogue) by (B * world) / n_valid_global.  Every block reads the flags and the two counts itself (world <= 16
+// loads); in the common all-valid case all but block 0 return at once.
+__global__ void __launch_bounds__(128) mailbox_reduce_kernel(const ReduceArgs a) {
+    const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5, p = (int)(a.step & 1ull);
+    __shared__ double counts[2];
+    if (wrp == 0) {
+        if (lane < a.world) {
+            const unsigned long long* f = &a.box->flags[p][lane];
+            unsigned long long v;
+            do {
+                asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(f) : "memory");
+                if (v < a.step + 1ull) __nanosleep(200);
+            } while (v < a.step + 1ull);
         }
-        out16[lane] = s;
+        __syncwarp();
+        if (lane < 16) {
+            double s = 0.0;
+            for (int r = 0; r < a.world; ++r) {                       // rank order: the same bits on every rank
+                double x;
+                asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(x) : "l"(&a.box->slots[p][r][lane]) : "memory");
+                s += x;
+            }
+            if (blockIdx.x == 0) a.out16[lane] = s;
+            if (lane == 5) counts[0] = s;                             // n_valid over the world
+            if (lane == 6) counts[1] = s;                             // samples over the world
+        }
     }
+    __syncthreads();
+    if (!a.dpred[0] || counts[0] == counts[1]) return;                // every sample of every rank valid
+    const float nv = (float)counts[0];
+    const float scale = (nv > 0.f) ? (float)counts[1] / nv : 0.f;
+    rescale_samples(a.dpred, a.dconf, a.out_sample, a.B, a.plane, scale);
 }
 
 extern "C" size_t t3d_mailbox_bytes(void) { return sizeof(Mailbox); }
@@ -196,7 +226,7 @@ extern "C" int t3d_step_epilogue_peers(float* dpred1, float* dpred2, float* dcon
     EpilogueArgs a;
     a.dpred[0] = dpred1; a.dpred[1] = dpred2; a.dconf[0] = dconf1; a.dconf[1] = dconf2;
     a.out_sample = loss_per_sample; a.out_batch = loss_batch; a.metrics_f64 = metrics_f64;
-    a.B = B; a.n_images = n_images; a.plane = (size_t)H * W; a.out16 = out16_local;
+    a.B = B; a.n_images = n_images; a.plane = (size_t)H * W; a.out16 = out16_local; a.defer_rescale = 1;
     PeerArgs pa;
     for (int q = 0; q < kMaxPeers; ++q) pa.box[q] = (q < world) ? reinterpret_cast<Mailbox*>(peer_mailboxes[q]) : nullptr;
     pa.world = world; pa.rank = rank; pa.step = step;
@@ -205,12 +235,41 @@ extern "C" int t3d_step_epilogue_peers(float* dpred1, float* dpred2, float* dcon
     return T3D_OK;
 }
 
-extern "C" int t3d_mailbox_reduce(const void* my_mailbox, int world, unsigned long long step, double* out16, void* stream) {
+extern "C" int t3d_mailbox_reduce(const void* my_mailbox, int world, unsigned long long step, double* out16,
+                                  float* dpred1, float* dpred2, float* dconf1, float* dconf2,
+                                  const float* loss_per_sample, int B, int H, int W, void* stream) {
     T3D_REQUIRE(my_mailbox && out16, "NULL pointer");
     T3D_REQUIRE(world >= 1 && world <= kMaxPeers, "bad world");
+    const bool fixup = dpred1 != nullptr;
+    if (fixup) T3D_REQUIRE(dpred2 && loss_per_sample && B >= 1 && H >= 1 && W >= 1, "gradient fix-up needs dpred1/2, loss_per_sample and dims");
+    ReduceArgs a;
+    a.box = reinterpret_cast<const Mailbox*>(my_mailbox); a.world = world; a.step = step; a.out16 = out16;
+    a.dpred[0] = dpred1; a.dpred[1] = fixup ? dpred2 : nullptr; a.dconf[0] = fixup ? dconf1 : nullptr; a.dconf[1] = fixup ? dconf2 : nullptr;
+    a.out_sample = loss_per_sample; a.B = B; a.plane = fixup ? (size_t)H * W : 0;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    T3D_LAUNCH("mailbox_reduce_kernel", st, mailbox_reduce_kernel<<<1, 32, 0, st>>>(
-        reinterpret_cast<const Mailbox*>(my_mailbox), world, step, out16));
+    const int grid = fixup ? t3d_sm_count() * 4 : 1;
+    T3D_LAUNCH("mailbox_reduce_kernel", st, mailbox_reduce_kernel<<<grid, 128, 0, st>>>(a));
+    return T3D_OK;
+}
+
+// the deferred factor of t3d_step_epilogue(defer_rescale = 1) from an already all-reduced vector (NCCL exchange)
+__global__ void __launch_bounds__(128) rescale_global_kernel(const ReduceArgs a) {
+    const double nv = a.out16[5], tot = a.out16[6];
+    if (nv == tot) return;
+    const float nvf = (float)nv;
+    rescale_samples(a.dpred, a.dconf, a.out_sample, a.B, a.plane, (nvf > 0.f) ? (float)tot / nvf : 0.f);
+}
+
+extern "C" int t3d_rescale_global(float* dpred1, float* dpred2, float* dconf1, float* dconf2, const float* loss_per_sample,
+                                  const double* out16_global, int B, int H, int W, void* stream) {
+    T3D_REQUIRE(dpred1 && dpred2 && loss_per_sample && out16_global, "NULL pointer");
+    T3D_REQUIRE(B >= 1 && H >= 1 && W >= 1, "bad dims");
+    ReduceArgs a;
+    a.box = nullptr; a.world = 0; a.step = 0; a.out16 = const_cast<double*>(out16_global);
+    a.dpred[0] = dpred1; a.dpred[1] = dpred2; a.dconf[0] = dconf1; a.dconf[1] = dconf2;
+    a.out_sample = loss_per_sample; a.B = B; a.plane = (size_t)H * W;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    T3D_LAUNCH("rescale_global_kernel", st, rescale_global_kernel<<<t3d_sm_count() * 4, 128, 0, st>>>(a));
     return T3D_OK;
 }
 

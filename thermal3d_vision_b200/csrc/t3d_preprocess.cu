@@ -858,7 +858,8 @@ int t3d_preprocess_train_u16(const uint16_t* raw, int B, int src_h, int src_w, i
         const size_t stage_bytes = same ? 0 : (size_t)(kHistThreads / 32) * 2 * ((src_w + 7) & ~7) * sizeof(uint16_t);
         const size_t hsmem = (size_t)kWinWords * 4 + (same ? 0 : (size_t)((dst_w + 1) & ~1) * sizeof(uint2)) + stage_bytes;
         T3D_REQUIRE(hsmem <= 200 * 1024, "source rows too wide for the shared-memory staging (src_w <= ~9000)");
-        static bool attr_set = false;
+        static bool attr_done[kT3dMaxDevices] = {};
+        bool& attr_set = attr_done[t3d_device_slot()];
         if (!attr_set) {
             const int max_smem = 200 * 1024;
             T3D_CUDA(cudaFuncSetAttribute(resize_hist_u16_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
@@ -878,7 +879,8 @@ int t3d_preprocess_train_u16(const uint16_t* raw, int B, int src_h, int src_w, i
     const int vec = (dst_w % 4 == 0) && t3d_aligned16(out) && ((reinterpret_cast<uintptr_t>(nsrc) & 7u) == 0);
     if (vec) {
         constexpr int kStageMax = 24 * 1024;      // staged band bytes: LUT 32 KB + band <= 56 KB per CTA, 4 CTAs per SM
-        static bool nattr = false;
+        static bool nattr_done[kT3dMaxDevices] = {};
+        bool& nattr = nattr_done[t3d_device_slot()];
         if (!nattr) {
 #define T3D_NORM_ATTR(REP_, ST_) \
             T3D_CUDA(cudaFuncSetAttribute(normalize_stats_u16_kernel<REP_, ST_, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kLutMax * 8)); \
@@ -949,7 +951,8 @@ int t3d_contrast_normalize_f32(const float* x, int B, int channels, int n, float
         T3D_LAUNCH("channels_close_kernel", st, channels_close_kernel<<<g, 256, 0, st>>>(x, n, close_flags));
     }
     T3D_CUDA(cudaMemsetAsync(w.counters, 0, (size_t)B * 8 * sizeof(int), st));
-    static bool attr_set = false;
+    static bool attr_done[kT3dMaxDevices] = {};
+    bool& attr_set = attr_done[t3d_device_slot()];
     if (!attr_set) {
         T3D_CUDA(cudaFuncSetAttribute(fpct_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFCandCap * (int)sizeof(unsigned int)));
         attr_set = true;

@@ -512,8 +512,11 @@ int t3d_launch_bracket_percentiles(const uint16_t* raw, int B, int sh, int sw, i
         const size_t smem = (size_t)kRzWarps * kRing * slot_bytes;
         const bool dense = sh <= 2 * dh;
         if (smem <= 96 * 1024 && slot_px <= 512 && (long long)B * nstrips * dh < (1ll << 31)) {
-            static int max_ctas[2] = {0, 0};
-            static size_t attr_smem[2] = {0, 0};
+            static int max_ctas_dev[kT3dMaxDevices][2] = {};
+            static size_t attr_smem_dev[kT3dMaxDevices][2] = {};
+            const int slot = t3d_device_slot();
+            int* max_ctas = max_ctas_dev[slot];
+            size_t* attr_smem = attr_smem_dev[slot];
             const int di = dense ? 1 : 0;
             const void* fn = dense ? (const void*)resize_march_kernel<true> : (const void*)resize_march_kernel<false>;
             if (smem > attr_smem[di] || max_ctas[di] == 0) {

@@ -18,6 +18,7 @@ from . import _lib
 from .metrics import _as_cuda
 
 
+@_lib.on_tensor_device
 def pointmap_to_depth(pointmap):
     """depth = pointmap[..., 2] as a dense array (same container type/device as the input)."""
     is_np = isinstance(pointmap, np.ndarray)
@@ -55,6 +56,7 @@ def load_thermal_calibration(calib_path):
     raise ValueError(f"Unsupported calibration file format: {calib_path}")
 
 
+@_lib.on_tensor_device
 def estimate_camera_intrinsics(pointmap, depth, calib_path=None):
     """Drop-in for scripts/pseudo_gt.py:137-184: K from the calibration file when given,
     else the median-focal estimate (on the GPU, exact float64 medians)."""
@@ -76,6 +78,7 @@ def estimate_camera_intrinsics(pointmap, depth, calib_path=None):
     return K.cpu().numpy().reshape(3, 3)
 
 
+@_lib.on_tensor_device
 def project_points(pointmap, K):
     """EXTENSION (not in the reference): pixel coordinates u = fx X/Z + cx, v = fy Y/Z + cy -> [...,2]."""
     pm = _as_cuda(pointmap, torch.float32).contiguous()

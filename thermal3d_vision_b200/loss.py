@@ -14,6 +14,7 @@ tensors and reproduce the training loop's "mean over valid samples"
 """
 from __future__ import annotations
 
+import os
 from typing import NamedTuple, Optional
 
 import torch
@@ -22,6 +23,10 @@ from . import _lib
 
 OUT_STRIDE = 8  # T3D_LOSS_OUT_STRIDE
 THERMAL_REPLICATED = 0x100  # T3D_THERMAL_REPLICATED
+LOSS_MULTI_SCALE, LOSS_CONF_MIN_ONLY = 0x1, 0x2   # T3D_LOSS_* flags
+# Debug / test mode (T3D_DEBUG_CHECKS=1, set by tests/conftest.py): caller promises are verified on the device --
+# today `thermal_replicated` (a wrong flag would silently change the results).  Costs a pass + a host sync per call.
+DEBUG_CHECKS = os.environ.get("T3D_DEBUG_CHECKS", "0") not in ("", "0")
 
 
 class FusedLossResult(NamedTuple):
@@ -40,8 +45,9 @@ def _prep(t: Optional[torch.Tensor], device) -> Optional[torch.Tensor]:
     return t.contiguous()
 
 
+@_lib.on_tensor_device
 def _launch(bwd, p1, p2, g1, g2, c1, c2, t1, t2, need_dconf, alpha, ew, sw, dw, multi, grad_scale,
-            rescale_invalid, out=None, thermal_stats=None, thermal_replicated=False):
+            rescale_invalid, out=None, thermal_stats=None, thermal_replicated=False, conf_min_only=False):
     """Raw call into the C ABI on already-prepared [B,H,W,3] CUDA tensors."""
     lib = _lib.lib()
     B, H, W, _ = p1.shape
@@ -49,7 +55,8 @@ def _launch(bwd, p1, p2, g1, g2, c1, c2, t1, t2, need_dconf, alpha, ew, sw, dw, 
     tch = 0 if t1 is None or t2 is None else int(t1.shape[1])
     if thermal_replicated and tch == 3:
         tch |= THERMAL_REPLICATED          # include/t3d.h: the kernel reads plane 0 only
-    ws_bytes = lib.t3d_loss_workspace_bytes(B, H, W, int(multi))
+    flags = (LOSS_MULTI_SCALE if multi else 0) | (LOSS_CONF_MIN_ONLY if conf_min_only else 0)
+    ws_bytes = lib.t3d_loss_workspace_bytes(B, H, W, flags)
     if out is None:
         out = {}
     ws = out.get("workspace")
@@ -93,7 +100,7 @@ def _launch(bwd, p1, p2, g1, g2, c1, c2, t1, t2, need_dconf, alpha, ew, sw, dw, 
             _lib.ptr(p1), _lib.ptr(p2), _lib.ptr(g1), _lib.ptr(g2), _lib.ptr(c1), _lib.ptr(c2),
             _lib.ptr(t1), _lib.ptr(t2), tch, _lib.ptr(st1), _lib.ptr(st2), st_tiles,
             _lib.ptr(dp1), _lib.ptr(dp2), _lib.ptr(dc1), _lib.ptr(dc2),
-            B, H, W, int(multi), alpha, ew, sw, dw, grad_scale,
+            B, H, W, flags, alpha, ew, sw, dw, grad_scale,
             _lib.ptr(per_sample), _lib.ptr(batch), _lib.ptr(f64), _lib.ptr(ws), ws.numel(), stream)
         _lib.check(rc, "t3d_loss_fwd_bwd")
         if rescale_invalid:
@@ -104,10 +111,34 @@ def _launch(bwd, p1, p2, g1, g2, c1, c2, t1, t2, need_dconf, alpha, ew, sw, dw, 
         rc = lib.t3d_loss_fwd(
             _lib.ptr(p1), _lib.ptr(p2), _lib.ptr(g1), _lib.ptr(g2), _lib.ptr(c1), _lib.ptr(c2),
             _lib.ptr(t1), _lib.ptr(t2), tch, _lib.ptr(st1), _lib.ptr(st2), st_tiles,
-            B, H, W, int(multi), alpha, ew, sw, dw,
+            B, H, W, flags, alpha, ew, sw, dw,
             _lib.ptr(per_sample), _lib.ptr(batch), _lib.ptr(f64), _lib.ptr(ws), ws.numel(), stream)
         _lib.check(rc, "t3d_loss_fwd")
     return per_sample, batch, dp1, dp2, dc1, dc2
+
+
+def _hand_back_grads(ctx, g_loss):
+    """backward of the fused losses: the forward kernel already produced d(loss)/d(inputs); scale them by
+    grad_output on the device (a no-op kernel when it is 1) and hand them to autograd.  The buffers are scaled in
+    place, so they can be consumed once: a second backward through the same node (retain_graph=True, two losses
+    sharing the graph) raises instead of silently contributing zeros."""
+    if ctx.grads == "none":             # forward ran without any input requiring grad
+        return (None,) * 9
+    if ctx.grads is None:
+        raise RuntimeError("thermal3d_vision_b200: the fused loss gradients of this node were already consumed by a "
+                           "previous backward (they are scaled in place); call the loss again instead of "
+                           "backpropagating twice through it")
+    dp1, dp2, dc1, dc2 = ctx.grads
+    ctx.grads = None
+    B, H, W, _ = ctx.shape
+    with _lib.device_guard(dp1.device):
+        go = g_loss.detach().to(dtype=torch.float32, device=dp1.device).reshape(1).contiguous()
+        rc = _lib.lib().t3d_scale_grads(_lib.ptr(dp1), _lib.ptr(dp2), _lib.ptr(dc1), _lib.ptr(dc2),
+                                       _lib.ptr(go), B, H, W, _lib.current_stream_ptr())
+        _lib.check(rc, "t3d_scale_grads")
+    need = ctx.needs_input_grad
+    return (dp1 if need[0] else None, dp2 if need[1] else None,
+            dc1 if need[2] else None, dc2 if need[3] else None, None, None, None, None, None)
 
 
 class _FusedLoss(torch.autograd.Function):
@@ -115,16 +146,16 @@ class _FusedLoss(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, p1, p2, c1, c2, g1, g2, t1, t2, cfg):
-        alpha, ew, sw, dw, multi, batch_mean = cfg
+        alpha, ew, sw, dw, multi, batch_mean, conf_min_only = cfg
         need = ctx.needs_input_grad
         bwd = bool(need[0] or need[1] or need[2] or need[3])
         need_dconf = (bool(need[2]) and c1 is not None, bool(need[3]) and c2 is not None)
         B = p1.shape[0]
         per_sample, batch, dp1, dp2, dc1, dc2 = _launch(
             bwd, p1, p2, g1, g2, c1, c2, t1, t2, need_dconf, alpha, ew, sw, dw, multi,
-            (1.0 / B) if batch_mean else 1.0, rescale_invalid=batch_mean)
+            (1.0 / B) if batch_mean else 1.0, rescale_invalid=batch_mean, conf_min_only=conf_min_only)
         ctx.shape = tuple(p1.shape)
-        ctx.grads = (dp1, dp2, dc1, dc2) if bwd else None
+        ctx.grads = (dp1, dp2, dc1, dc2) if bwd else "none"
         ctx.mark_non_differentiable(per_sample, batch)
         # B == 1 per-sample call: the loss itself (no validity filter, as utils/loss.py:295)
         loss = batch[0] if batch_mean else per_sample[0, 0]
@@ -132,18 +163,7 @@ class _FusedLoss(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g_loss, _g_ps, _g_b):
-        if ctx.grads is None:
-            return (None,) * 9
-        dp1, dp2, dc1, dc2 = ctx.grads
-        ctx.grads = None    # the gradients are scaled in place: single use
-        B, H, W, _ = ctx.shape
-        go = g_loss.detach().to(dtype=torch.float32, device=dp1.device).reshape(1).contiguous()
-        rc = _lib.lib().t3d_scale_grads(_lib.ptr(dp1), _lib.ptr(dp2), _lib.ptr(dc1), _lib.ptr(dc2),
-                                       _lib.ptr(go), B, H, W, _lib.current_stream_ptr())
-        _lib.check(rc, "t3d_scale_grads")
-        need = ctx.needs_input_grad
-        return (dp1 if need[0] else None, dp2 if need[1] else None,
-                dc1 if need[2] else None, dc2 if need[3] else None, None, None, None, None, None)
+        return _hand_back_grads(ctx, g_loss)
 
 
 def _device_of(*ts):
@@ -158,12 +178,13 @@ def _device_of(*ts):
 def fused_thermal_loss(pred_pts1, pred_pts2, gt_pts1, gt_pts2, confidences1=None, confidences2=None,
                        thermal_img1=None, thermal_img2=None, *, alpha=0.2, edge_weight=0.5,
                        smoothness_weight=0.3, detail_weight=0.3, multi_scale=True,
-                       batch_mean=True) -> FusedLossResult:
+                       batch_mean=True, conf_min_only=False) -> FusedLossResult:
     """Batched fused loss: tensors are [B,H,W,3] / [B,H,W] / [B,C,H,W].
 
     ``loss`` = mean over VALID samples (finite and > 0) of the per-sample
     enhanced_thermal_aware_loss; gradients w.r.t. pred and confidences flow
-    through autograd.  No host synchronisation.
+    through autograd.  No host synchronisation.  ``conf_min_only``: clamp the confidence from below only
+    (train_thermal_dustr.py:278-279,305-318, the plain confidence-weighted L1 without utils/loss.py's upper clamp at 10).
     """
     dev = _device_of(pred_pts1, pred_pts2, gt_pts1, gt_pts2)
     p1, p2, g1, g2 = (_prep(t, dev) for t in (pred_pts1, pred_pts2, gt_pts1, gt_pts2))
@@ -186,7 +207,7 @@ def fused_thermal_loss(pred_pts1, pred_pts2, gt_pts1, gt_pts2, confidences1=None
         if multi_scale and (H < 4 or W < 4):
             raise ValueError("multi_scale needs H, W >= 4 (the reference breaks on squeezed dims; SURVEY.md D.7)")
     cfg = (float(alpha), float(edge_weight), float(smoothness_weight), float(detail_weight),
-           bool(multi_scale), bool(batch_mean))
+           bool(multi_scale), bool(batch_mean), bool(conf_min_only))
     loss, per_sample, batch = _FusedLoss.apply(p1, p2, c1, c2, g1, g2, t1, t2, cfg)
     return FusedLossResult(loss, per_sample, batch)
 
@@ -210,6 +231,8 @@ def fused_thermal_loss_fwd_bwd(pred_pts1, pred_pts2, gt_pts1, gt_pts2, confidenc
     with the result packing in one launch).
     """
     _lib.require_cuda(pred_pts1, pred_pts2, gt_pts1, gt_pts2, confidences1, confidences2, thermal_img1, thermal_img2)
+    if thermal_replicated and DEBUG_CHECKS and not torch.cuda.is_current_stream_capturing():
+        check_thermal_replicated(thermal_img1, thermal_img2)
     B = pred_pts1.shape[0]
     need_dconf = (conf_grad and confidences1 is not None, conf_grad and confidences2 is not None)
     ps, bt, dp1, dp2, dc1, dc2 = _launch(
@@ -218,6 +241,17 @@ def fused_thermal_loss_fwd_bwd(pred_pts1, pred_pts2, gt_pts1, gt_pts2, confidenc
         bool(multi_scale), (1.0 / B) if grad_scale is None else float(grad_scale), rescale_invalid=bool(rescale_invalid), out=out,
         thermal_stats=thermal_stats, thermal_replicated=thermal_replicated)
     return {"per_sample": ps, "batch": bt, "dpred1": dp1, "dpred2": dp2, "dconf1": dc1, "dconf2": dc2}
+
+
+def check_thermal_replicated(*thermal):
+    """Raise unless the 3 planes of every image are bit-identical (the promise behind thermal_replicated=True)."""
+    for t in thermal:
+        if t is None or t.shape[1] != 3:
+            continue
+        with _lib.device_guard(t.device):
+            bits = t.view(torch.int32)
+            if not (torch.equal(bits[:, 0], bits[:, 1]) and torch.equal(bits[:, 0], bits[:, 2])):
+                raise ValueError("thermal_replicated=True but the three thermal planes are not bit-identical")
 
 
 # ----------------------------------------------------------------------------- reference signatures
@@ -272,6 +306,7 @@ def enhanced_thermal_aware_loss(pred_pts1, pred_pts2, gt_pts1, gt_pts2,
 
 class _LossV1(torch.autograd.Function):
     @staticmethod
+    @_lib.on_tensor_device
     def forward(ctx, p1, p2, c1, c2, g1, g2, t1, t2, cfg):
         alpha, ew, sw = cfg
         lib = _lib.lib()
@@ -293,24 +328,13 @@ class _LossV1(torch.autograd.Function):
                                      None, _lib.ptr(ws), ws.numel(), _lib.current_stream_ptr())
         _lib.check(rc, "t3d_loss_v1_fwd_bwd")
         ctx.shape = tuple(p1.shape)
-        ctx.grads = (dp1, dp2, dc1, dc2) if bwd else None
+        ctx.grads = (dp1, dp2, dc1, dc2) if bwd else "none"
         ctx.mark_non_differentiable(per_sample)
         return per_sample[0, 0].clone(), per_sample
 
     @staticmethod
     def backward(ctx, g_loss, _g_ps):
-        if ctx.grads is None:
-            return (None,) * 9
-        dp1, dp2, dc1, dc2 = ctx.grads
-        ctx.grads = None
-        B, H, W, _ = ctx.shape
-        go = g_loss.detach().to(dtype=torch.float32, device=dp1.device).reshape(1).contiguous()
-        rc = _lib.lib().t3d_scale_grads(_lib.ptr(dp1), _lib.ptr(dp2), _lib.ptr(dc1), _lib.ptr(dc2),
-                                       _lib.ptr(go), B, H, W, _lib.current_stream_ptr())
-        _lib.check(rc, "t3d_scale_grads")
-        need = ctx.needs_input_grad
-        return (dp1 if need[0] else None, dp2 if need[1] else None,
-                dc1 if need[2] else None, dc2 if need[3] else None, None, None, None, None, None)
+        return _hand_back_grads(ctx, g_loss)
 
 
 def thermal_aware_loss(pred_pts1, pred_pts2, gt_pts1, gt_pts2,

@@ -32,6 +32,7 @@ def _as_cuda(x, dtype=None):
     return x.detach()
 
 
+@_lib.on_tensor_device
 def compute_depth_metrics_batch(pred, gt_depth, mask=None, median_scaling=True, out: Optional[dict] = None):
     """Batched metrics on the device, no host sync.
 
@@ -129,6 +130,7 @@ class MetricAccumulator:
     def __init__(self, device):
         self.state = torch.zeros(8, dtype=torch.float64, device=device)   # 7 sums + image count
 
+    @_lib.on_tensor_device
     def update(self, metrics_f64: torch.Tensor):
         if metrics_f64.dtype != torch.float64 or not metrics_f64.is_contiguous() or metrics_f64.shape[1] != 8:
             raise ValueError("metrics_f64 must be a contiguous float64 [B, 8] tensor (compute_depth_metrics_batch)")

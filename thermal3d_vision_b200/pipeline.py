@@ -23,68 +23,96 @@ RESULT_SIZE = 16   # packed result vector (float64): see HotPathStep.run_device
 
 
 class HotPathStep:
+    """One training-side step of the hot path on B pairs (see the module docstring).
+
+    Streams.  The step runs on three internal streams -- preprocessing (the loss needs its thermal batches: the
+    critical path), depth metrics (needed only by the step's epilogue) and loss + epilogue -- forked from the
+    caller's stream at call time (the inputs are ready there).  Every per-step output exists twice and the two sets
+    alternate, so consecutive steps may overlap: with ``pipelined=True`` the caller's stream is NOT ordered after the
+    step by `run_device` itself but lazily (by the next call, after that call has forked its own work, or by
+    `wait_result()` / `finish()`), which lets the preprocessing and metric kernels of step i + 1 fill the machine
+    while the tail of step i (the loss kernel's last work items, its second-stage reduction, the epilogue) drains,
+    and hides the one-CTA-per-image sampling kernels that would otherwise run alone at the head of every step.
+    Every step still does all of its work on its own inputs.  With ``pipelined=False`` (default) the caller's stream
+    waits for the step before `run_device` returns: plain stream semantics.  `loss_out`, `pre_both`, `met_out` and
+    `result` always name the set of the latest call.
+    """
+
     def __init__(self, B: int, H: int, W: int, raw_hw=(512, 640), device=None, multi_scale: bool = False,
                  alpha=0.2, edge_weight=0.5, smoothness_weight=0.3, detail_weight=0.4, distributed: bool = False,
-                 exchange: str = "peer"):
+                 exchange: str = "peer", pipelined: bool = False):
         self.B, self.H, self.W, self.raw_hw = B, H, W, tuple(raw_hw)
         self.device = torch.device(device if device is not None else "cuda")
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
         self.kw = dict(alpha=alpha, edge_weight=edge_weight, smoothness_weight=smoothness_weight,
                        detail_weight=detail_weight, multi_scale=multi_scale)
         self.distributed = distributed
+        self.pipelined = bool(pipelined)
         dev = self.device
         lib = _lib.lib()
         f32 = dict(dtype=torch.float32, device=dev)
-        # outputs / workspaces are allocated once (the library never allocates)
-        self.loss_out = {
-            "workspace": torch.empty(lib.t3d_loss_workspace_bytes(B, H, W, 1), dtype=torch.uint8, device=dev),
+        with _lib.device_guard(dev):
+            self._alloc(lib, dev, f32, B, H, W, multi_scale)
+            self._init_exchange(lib, dev, distributed, exchange)
+
+    def _alloc(self, lib, dev, f32, B, H, W, multi_scale):
+        # outputs / workspaces are allocated once (the library never allocates), twice each: steps alternate
+        flags = _loss.LOSS_MULTI_SCALE if multi_scale else 0
+        self.loss_sets = [{
+            "workspace": torch.empty(lib.t3d_loss_workspace_bytes(B, H, W, flags), dtype=torch.uint8, device=dev),
             "per_sample": torch.empty(B, 8, **f32), "batch": torch.empty(8, **f32),
             "dpred1": torch.empty(B, H, W, 3, **f32), "dpred2": torch.empty(B, H, W, 3, **f32),
             "dconf1": torch.empty(B, H, W, **f32), "dconf2": torch.empty(B, H, W, **f32),
-        }
+        } for _ in range(2)]
         # both views are preprocessed by ONE call when the caller hands them over as the two halves of a single
         # [2B,...] tensor (what run_host's staging does): outputs are halves of one buffer as well
-        self.pre_both = {
+        self.pre_sets = [{
             "thermal": torch.empty(2 * B, 3, H, W, **f32),
             "percentiles": torch.empty(2 * B, 2, dtype=torch.float64, device=dev),
-            "histogram": torch.empty(2 * B, 65536, dtype=torch.int32, device=dev),
             "grad_stats": torch.empty(2 * B, max(lib.t3d_preprocess_stats_tiles(H, W), 1), 4, **f32),
             "workspace": torch.empty(lib.t3d_preprocess_workspace_bytes(2 * B, H, W), dtype=torch.uint8, device=dev),
-        }
-        self.pre_out = [{k: (v[:B] if i == 0 else v[B:]) if k != "workspace" else
-                         torch.empty(lib.t3d_preprocess_workspace_bytes(B, H, W), dtype=torch.uint8, device=dev)
-                         for k, v in self.pre_both.items()} for i in range(2)]
-        self.met_out = {
+        } for _ in range(2)]
+        self._pre_halves = [None, None]      # separate-view fallback: allocated on first use
+        self.met_sets = [{
             "workspace": torch.empty(lib.t3d_depth_metrics_workspace_bytes(B, H, W), dtype=torch.uint8, device=dev),
             "metrics": torch.empty(B, 8, **f32), "metrics_f64": torch.empty(B, 8, dtype=torch.float64, device=dev),
             "medians": torch.empty(B, 2, **f32),
-        }
-        # side streams: the two preprocessing calls and the metric pipeline are independent of each other
-        # (many short, latency-bound kernels) and overlap; the loss needs both thermal batches and then
-        # runs alone on the caller's stream
-        # (high priority: the metric pipeline's small one-CTA-per-image kernels then get the next free SM slots
-        # instead of queueing behind the preprocessing kernels' remaining CTAs -- 0.465 -> 0.455 ms per step)
-        self.side = [torch.cuda.Stream(device=dev, priority=-1) for _ in range(2)]
-        self.fork = torch.cuda.Event()
-        self.joins = [torch.cuda.Event() for _ in range(2)]
-        self.overlap = True
+        } for _ in range(2)]
+        self.loss_out, self.pre_both, self.met_out = self.loss_sets[0], self.pre_sets[0], self.met_sets[0]
+        # preprocessing first in line for free SMs (the loss waits for it), the metric chain last (it has a whole
+        # step of slack: only the epilogue needs it)
+        self.s_pre = torch.cuda.Stream(device=dev, priority=-1)
+        self.s_loss = torch.cuda.Stream(device=dev, priority=-1)
+        self.s_met = torch.cuda.Stream(device=dev, priority=0)
+        self.ev_ready = [torch.cuda.Event() for _ in range(2)]
+        self.ev_pre = [torch.cuda.Event() for _ in range(2)]
+        self.ev_met = [torch.cuda.Event() for _ in range(2)]
+        self.ev_done = [torch.cuda.Event() for _ in range(2)]
+        self._joined = [True, True]          # the caller's stream has been ordered after the step that last used set i
         self._shared_hint = None
         # percentiles from sampled value windows (bit-identical to the exact-histogram path, no per-pixel atomic);
         # set True to also get the 65 536-bin histograms of the resized frames in pre_both["histogram"]
         self.histogram = False
-        # two packed-result vectors used alternately: with distributed=True the all-reduce of step i is asynchronous
-        # and overlaps the kernels of step i + 1 (it is a 128-byte, latency-bound collective)
         self.results = [torch.zeros(RESULT_SIZE, dtype=torch.float64, device=dev) for _ in range(2)]
         self.pending = [None, None]
         self.calls = 0
         self.result = self.results[0]
         self.result_host = torch.zeros(RESULT_SIZE, dtype=torch.float64).pin_memory()
         self.staging = None        # two device staging sets of run_host (allocated on first use)
+
+    def _init_exchange(self, lib, dev, distributed, exchange):
         # Data-parallel exchange of the packed result.  "peer" (NCCL process group on one NVLink node): every rank
         # owns a 4 KB mailbox in symmetric memory; the step's epilogue kernel stores the rank's 16 doubles straight
-        # into every peer's mailbox and a one-warp kernel adds them up one step later -- no collective call and no
+        # into every peer's mailbox and a small kernel adds them up one step later -- no collective call and no
         # host work per step beyond two launches (a per-step dist.all_reduce costs enough host time to make the
         # 0.43 ms step host-bound: 0.458 vs 0.435 ms).  "nccl": one asynchronous dist.all_reduce per step.
+        # Either way the reduction also applies the GLOBAL validity factor to this rank's gradients
+        # (train_thermal_dustr.py:320,357-360 over the whole data-parallel batch).
         self.exchange = None
+        self.exchange_fallback = None
+        self.reduced = [True, True]     # results[i] holds the global vector of the step that last used set i
+        self.step_of = [-1, -1]
         if distributed and _dist.world()[1] > 1:
             import os
             exchange = os.environ.get("T3D_EXCHANGE", exchange)      # tuning knob
@@ -115,12 +143,13 @@ class HotPathStep:
             if int(ok.item()) == 0:
                 warnings.warn(f"peer-memory exchange unavailable ({err!r}); using one NCCL all-reduce per step")
                 self.exchange = "nccl"
+                self.exchange_fallback = repr(err)
             else:
                 self.local = [torch.zeros(RESULT_SIZE, dtype=torch.float64, device=dev) for _ in range(2)]
-                self.reduced = [True, True]     # results[i] holds the global vector of the step that last used slot i
-                self.step_of = [-1, -1]
                 torch.cuda.synchronize(dev)
                 dist.barrier()                  # every mailbox is zeroed before anybody's first peer store
+        if self.exchange == "nccl":
+            self.local = [torch.zeros(RESULT_SIZE, dtype=torch.float64, device=dev) for _ in range(2)]
 
     # ------------------------------------------------------------------ bytes
     def algorithmic_bytes(self) -> Dict[str, int]:
@@ -134,140 +163,190 @@ class HotPathStep:
         }
 
     # ------------------------------------------------------------------ device-resident step
-    def run_device(self, raw1, raw2, pred1, pred2, gt1, gt2, conf1, conf2, gt_depth):
-        """All inputs already in HBM.  Returns the packed device result vector (float64):
-        [0] sum of valid per-sample losses  [1..4] sums of components  [5] n_valid  [6] B
+    def run_device(self, raw1, raw2, pred1, pred2, gt1, gt2, conf1, conf2, gt_depth, _ready=None):
+        """All inputs already in HBM (ready on the caller's current stream).  Returns the packed device result vector
+        (float64): [0] sum of valid per-sample losses  [1..4] sums of components  [5] n_valid  [6] B
         [7..13] sums of finite per-image metrics (abs_rel..acc_3)  [14] n_images  [15] unused.
         With distributed=True the vector is summed over the ranks (peer-memory mailboxes, or one NCCL all-reduce with
-        exchange="nccl"); it holds the global sums once wait_result() / finish() / the next call has been enqueued."""
+        exchange="nccl") and the gradients carry the global validity factor once `wait_result()` / `finish()` / the
+        next call has enqueued the reduction.  pipelined=True: see the class docstring -- call `wait_result()`
+        before consuming this step's outputs on the caller's stream."""
+        with _lib.device_guard(self.device):
+            return self._run_device(raw1, raw2, pred1, pred2, gt1, gt2, conf1, conf2, gt_depth, _ready)
+
+    def _run_device(self, raw1, raw2, pred1, pred2, gt1, gt2, conf1, conf2, gt_depth, ready):
         size = (self.W, self.H)
         B = self.B
+        lib = _lib.lib()
         main = torch.cuda.current_stream(self.device)
-        stacked = (raw1.is_contiguous() and raw2.is_contiguous() and raw1.shape == raw2.shape and
-                   raw1.untyped_storage().data_ptr() == raw2.untyped_storage().data_ptr() and
-                   raw2.storage_offset() == raw1.storage_offset() + raw1.numel())      # halves of one tensor
-        if stacked:
-            raw_both = torch.as_strided(raw1, (2 * B,) + tuple(raw1.shape[1:]), raw1.stride(), raw1.storage_offset())
-
-        def preprocess_all():
-            if stacked:
-                tb = _pre.preprocess_thermal_batch(raw_both, size, path="train", out=self.pre_both, histogram=self.histogram)
-                gs = tb.grad_stats
-                return (tb.thermal[:B], tb.thermal[B:]), (None, None) if gs is None else (gs[:B], gs[B:])
-            a = _pre.preprocess_thermal_batch(raw1, size, path="train", out=self.pre_out[0], histogram=self.histogram)
-            b = _pre.preprocess_thermal_batch(raw2, size, path="train", out=self.pre_out[1], histogram=self.histogram)
-            return (a.thermal, b.thermal), (a.grad_stats, b.grad_stats)
-
-        if self.overlap != self._shared_hint:       # the metric pipeline shares the SMs with the preprocessing
-            self._shared_hint = self.overlap
-            _lib.lib().t3d_preprocess_set_shared(1 if self.overlap else 0)
-        if self.overlap:
-            self.fork.record(main)
-            with torch.cuda.stream(self.side[1]):           # depth metrics (Z of pred1 read in place)
-                self.side[1].wait_event(self.fork)
-                me = _metrics.compute_depth_metrics_batch(pred1, gt_depth, out=self.met_out)
-                self.joins[1].record(self.side[1])
-            (t1, t2), stats = preprocess_all()
-            main.wait_event(self.joins[1])
-        else:
-            (t1, t2), stats = preprocess_all()
-            me = _metrics.compute_depth_metrics_batch(pred1, gt_depth, out=self.met_out)
-        # the normalisation kernel already summed the thermal gradients: the loss skips its statistics pass
-        lo = _loss.fused_thermal_loss_fwd_bwd(pred1, pred2, gt1, gt2, conf1, conf2, t1, t2,
-                                              out=self.loss_out, thermal_stats=stats,
-                                              thermal_replicated=True,   # preprocess_thermal_batch wrote 3 identical planes
-                                              grad_scale=_dist.global_grad_scale(self.B) if self.distributed else None,
-                                              rescale_invalid=False,     # done by t3d_step_epilogue below
-                                              **self.kw)
         i = self.calls & 1
         step_no = self.calls
         self.calls += 1
-        lib = _lib.lib()
-        stream = _lib.current_stream_ptr()
-        if self.exchange == "peer":
-            # reduce(step - 1) is enqueued before epilogue(step): the order that makes the two mailbox slots reusable
-            self._reduce_pending()
-            rank, world = _dist.world()
-            rc = lib.t3d_step_epilogue_peers(_lib.ptr(lo["dpred1"]), _lib.ptr(lo["dpred2"]), _lib.ptr(lo["dconf1"]),
-                                             _lib.ptr(lo["dconf2"]), _lib.ptr(lo["per_sample"]), _lib.ptr(lo["batch"]),
-                                             _lib.ptr(me["metrics_f64"]), self.B, self.H, self.W, self.B,
-                                             _lib.ptr(self.local[i]), self.peer_ptrs, world, rank, step_no, stream)
-            _lib.check(rc, "t3d_step_epilogue_peers")
-            self.reduced[i] = False
-            self.step_of[i] = step_no
-            self.result = self.results[i]          # global once wait_result() / the next step has enqueued the reduction
-            return self.result
-        if self.pending[i] is not None:
-            self.pending[i].wait()                 # the all-reduce of step - 2 is done with this vector
-            self.pending[i] = None
-        r = self.results[i]
-        # validity fix-up of the gradients + packing of the step's scalars: one launch
-        rc = lib.t3d_step_epilogue(_lib.ptr(lo["dpred1"]), _lib.ptr(lo["dpred2"]), _lib.ptr(lo["dconf1"]),
-                                   _lib.ptr(lo["dconf2"]), _lib.ptr(lo["per_sample"]), _lib.ptr(lo["batch"]),
-                                   _lib.ptr(me["metrics_f64"]), self.B, self.H, self.W, self.B,
-                                   _lib.ptr(r), stream)
-        _lib.check(rc, "t3d_step_epilogue")
-        if self.exchange == "nccl":
-            self.pending[i] = _dist.all_reduce_result(r, async_op=True)
-        self.result = r
-        return r
+        lo, pre, met = self.loss_sets[i], self.pre_sets[i], self.met_sets[i]
+        self.loss_out, self.pre_both, self.met_out = lo, pre, met
+        # fork: the inputs are ready on the caller's stream as of now (or, from run_host, when the H2D copies are done)
+        if ready is None:
+            ready = self.ev_ready[i]
+            ready.record(main)
+        # ... and only now order the caller's stream after the PREVIOUS step (lazy join): its tail overlaps this
+        # step's preprocessing / metric kernels.  Set i was last used by step - 2, which the join of call - 1 covered.
+        self._join(main)
+        stacked = (raw1.is_contiguous() and raw2.is_contiguous() and raw1.shape == raw2.shape and
+                   raw1.untyped_storage().data_ptr() == raw2.untyped_storage().data_ptr() and
+                   raw2.storage_offset() == raw1.storage_offset() + raw1.numel())      # halves of one tensor
+        if self._shared_hint is None:               # the metric chain shares the SMs with the preprocessing
+            self._shared_hint = True
+            lib.t3d_preprocess_set_shared(1)
+        if self.histogram and "histogram" not in pre:
+            pre["histogram"] = torch.empty(2 * B, 65536, dtype=torch.int32, device=self.device)
+
+        with torch.cuda.stream(self.s_met):                 # depth metrics (Z of pred1 read in place)
+            self.s_met.wait_event(ready)
+            me = _metrics.compute_depth_metrics_batch(pred1, gt_depth, out=met)
+            self.ev_met[i].record(self.s_met)
+        with torch.cuda.stream(self.s_pre):
+            self.s_pre.wait_event(ready)
+            if stacked:
+                raw_both = torch.as_strided(raw1, (2 * B,) + tuple(raw1.shape[1:]), raw1.stride(), raw1.storage_offset())
+                tb = _pre.preprocess_thermal_batch(raw_both, size, path="train", out=pre, histogram=self.histogram)
+                gs = tb.grad_stats
+                (t1, t2), stats = (tb.thermal[:B], tb.thermal[B:]), ((None, None) if gs is None else (gs[:B], gs[B:]))
+            else:
+                if self._pre_halves[i] is None:
+                    self._pre_halves[i] = [{k: (v[:B] if h == 0 else v[B:]) if k != "workspace" else
+                                            torch.empty(lib.t3d_preprocess_workspace_bytes(B, self.H, self.W), dtype=torch.uint8,
+                                                        device=self.device) for k, v in pre.items()} for h in range(2)]
+                a = _pre.preprocess_thermal_batch(raw1, size, path="train", out=self._pre_halves[i][0], histogram=self.histogram)
+                b = _pre.preprocess_thermal_batch(raw2, size, path="train", out=self._pre_halves[i][1], histogram=self.histogram)
+                (t1, t2), stats = (a.thermal, b.thermal), (a.grad_stats, b.grad_stats)
+            self.ev_pre[i].record(self.s_pre)
+        with torch.cuda.stream(self.s_loss):
+            self.s_loss.wait_event(ready)                   # pred / gt / conf
+            self.s_loss.wait_event(self.ev_pre[i])
+            # the normalisation kernel already summed the thermal gradients: the loss skips its statistics pass
+            _loss.fused_thermal_loss_fwd_bwd(pred1, pred2, gt1, gt2, conf1, conf2, t1, t2,
+                                             out=lo, thermal_stats=stats,
+                                             thermal_replicated=True,   # preprocess_thermal_batch wrote 3 identical planes
+                                             grad_scale=_dist.global_grad_scale(self.B) if self.distributed else None,
+                                             rescale_invalid=False,     # done by the epilogue below
+                                             **self.kw)
+            self.s_loss.wait_event(self.ev_met[i])
+            stream = _lib.current_stream_ptr()
+            grads = [_lib.ptr(lo[k]) for k in ("dpred1", "dpred2", "dconf1", "dconf2")]
+            if self.exchange == "peer":
+                # reduce(step - 1) is enqueued before epilogue(step): the order that makes the two mailbox slots reusable
+                self._reduce_pending()
+                rank, world = _dist.world()
+                rc = lib.t3d_step_epilogue_peers(*grads, _lib.ptr(lo["per_sample"]), _lib.ptr(lo["batch"]),
+                                                 _lib.ptr(me["metrics_f64"]), B, self.H, self.W, B,
+                                                 _lib.ptr(self.local[i]), self.peer_ptrs, world, rank, step_no, stream)
+                _lib.check(rc, "t3d_step_epilogue_peers")
+                self.reduced[i] = False
+                self.step_of[i] = step_no
+            elif self.exchange == "nccl":
+                self._reduce_pending()
+                # validity: zero the invalid samples now, the global factor follows the all-reduce (t3d_rescale_global)
+                rc = lib.t3d_step_epilogue(*grads, _lib.ptr(lo["per_sample"]), _lib.ptr(lo["batch"]),
+                                           _lib.ptr(me["metrics_f64"]), B, self.H, self.W, B, 1,
+                                           _lib.ptr(self.results[i]), stream)
+                _lib.check(rc, "t3d_step_epilogue")
+                self.local[i].copy_(self.results[i])
+                self.pending[i] = _dist.all_reduce_result(self.results[i], async_op=True)
+                self.reduced[i] = False
+                self.step_of[i] = step_no
+            else:
+                # validity fix-up of the gradients + packing of the step's scalars: one launch
+                rc = lib.t3d_step_epilogue(*grads, _lib.ptr(lo["per_sample"]), _lib.ptr(lo["batch"]),
+                                           _lib.ptr(me["metrics_f64"]), B, self.H, self.W, B, 0,
+                                           _lib.ptr(self.results[i]), stream)
+                _lib.check(rc, "t3d_step_epilogue")
+            self.ev_done[i].record(self.s_loss)
+        self._joined[i] = False
+        self.result = self.results[i]
+        if not self.pipelined:
+            self._join(main)
+        return self.result
+
+    def _join(self, main):
+        """Order `main` after every step it has not been ordered after yet (not after their pending reductions)."""
+        for k in range(2):
+            if not self._joined[k]:
+                main.wait_event(self.ev_done[k])
+                self._joined[k] = True
 
     def capture_graph(self, raw1, raw2, pred1, pred2, gt1, gt2, conf1, conf2, gt_depth):
         """Capture one `run_device` on these (static) device tensors into a CUDA graph and return `replay()`, which
-        re-runs the whole step (both streams, ~15 kernels) with one launch and returns the packed result vector.
+        re-runs the whole step (three streams, ~15 kernels) with one launch and returns the packed result vector.
         For launch-bound shapes (BASELINE configs[1]: batch 8 at 224x224 is ~45 MB of traffic, a few microseconds
-        of HBM time) this is what removes the per-kernel launch latency.  Single-process only (the all-reduce of a
-        distributed step is issued outside any graph)."""
+        of HBM time) this is what removes the per-kernel launch latency.  Single-process only (the exchange of a
+        distributed step is issued outside any graph).  The captured step always uses output set 0."""
         if self.distributed:
             raise ValueError("capture_graph is for single-process steps")
         args = (raw1, raw2, pred1, pred2, gt1, gt2, conf1, conf2, gt_depth)
-        cur = torch.cuda.current_stream(self.device)
-        warm = torch.cuda.Stream(device=self.device)
-        warm.wait_stream(cur)
-        with torch.cuda.stream(warm):
-            for _ in range(2):                     # one-time attribute / occupancy queries happen outside the capture
-                self.run_device(*args)
-        cur.wait_stream(warm)
-        torch.cuda.synchronize(self.device)
-        graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph):
-            r = self.run_device(*args)
+        pipelined, self.pipelined = self.pipelined, False
+        with _lib.device_guard(self.device):
+            cur = torch.cuda.current_stream(self.device)
+            warm = torch.cuda.Stream(device=self.device)
+            warm.wait_stream(cur)
+            with torch.cuda.stream(warm):
+                for _ in range(2):                     # one-time attribute / occupancy queries happen outside the capture
+                    self.run_device(*args)
+            cur.wait_stream(warm)
+            torch.cuda.synchronize(self.device)
+            self.calls = 0                             # the captured step writes set 0
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                r = self.run_device(*args)
+        self.pipelined = pipelined
+        sets = (self.loss_sets[0], self.pre_sets[0], self.met_sets[0])
 
         def replay():
             graph.replay()
+            self.loss_out, self.pre_both, self.met_out = sets
+            self.result = r
             return r
         replay.graph = graph
         return replay
 
     def _reduce_pending(self):
-        """peer exchange: enqueue the reduction of every step whose global vector has not been formed yet (oldest first)."""
-        if self.exchange != "peer":
+        """Data parallel: enqueue (on the loss stream) the reduction of every step whose global vector has not been
+        formed yet, oldest first -- it also applies the global validity factor to that step's gradients."""
+        if self.exchange is None:
             return
-        lib, stream, world = _lib.lib(), _lib.current_stream_ptr(), _dist.world()[1]
-        for i in sorted(range(2), key=lambda k: self.step_of[k]):
-            if not self.reduced[i]:
-                rc = lib.t3d_mailbox_reduce(_lib.ptr(self.mailbox), world, self.step_of[i], _lib.ptr(self.results[i]), stream)
-                _lib.check(rc, "t3d_mailbox_reduce")
+        lib, world = _lib.lib(), _dist.world()[1]
+        with torch.cuda.stream(self.s_loss):
+            stream = _lib.current_stream_ptr()
+            for i in sorted(range(2), key=lambda k: self.step_of[k]):
+                if self.reduced[i]:
+                    continue
+                lo = self.loss_sets[i]
+                grads = [_lib.ptr(lo[k]) for k in ("dpred1", "dpred2", "dconf1", "dconf2")]
+                if self.exchange == "peer":
+                    rc = lib.t3d_mailbox_reduce(_lib.ptr(self.mailbox), world, self.step_of[i], _lib.ptr(self.results[i]),
+                                                *grads, _lib.ptr(lo["per_sample"]), self.B, self.H, self.W, stream)
+                    _lib.check(rc, "t3d_mailbox_reduce")
+                else:
+                    self.pending[i].wait()             # orders the loss stream after the all-reduce
+                    self.pending[i] = None
+                    rc = lib.t3d_rescale_global(*grads, _lib.ptr(lo["per_sample"]), _lib.ptr(self.results[i]),
+                                                self.B, self.H, self.W, stream)
+                    _lib.check(rc, "t3d_rescale_global")
                 self.reduced[i] = True
+                self.ev_done[i].record(self.s_loss)    # "done" now includes the reduction
+                self._joined[i] = False
 
     def wait_result(self, r: Optional[torch.Tensor] = None) -> torch.Tensor:
-        """Order the current stream after the (asynchronous) all-reduce of `r` (default: the latest result).
-        Call before reading a result of a distributed step; a no-op otherwise."""
+        """Order the current stream after the step that produced `r` (default: the latest), including -- data
+        parallel -- its reduction over the ranks and the global validity fix-up of its gradients."""
         r = self.result if r is None else r
-        self._reduce_pending()
-        for i in range(2):
-            if self.results[i] is r and self.pending[i] is not None:
-                self.pending[i].wait()
-                self.pending[i] = None
+        with _lib.device_guard(self.device):
+            self._reduce_pending()
+            self._join(torch.cuda.current_stream(self.device))
         return r
 
     def finish(self):
-        """Order the current stream after every outstanding all-reduce (end of a run / of a timed region)."""
-        self._reduce_pending()
-        for i in range(2):
-            if self.pending[i] is not None:
-                self.pending[i].wait()
-                self.pending[i] = None
+        """Order the current stream after every outstanding step / reduction (end of a run / of a timed region)."""
+        self.wait_result()
 
     # ------------------------------------------------------------------ host-buffer step (e2e)
     def run_host(self, host: Dict[str, torch.Tensor]):
@@ -278,6 +357,10 @@ class HotPathStep:
         The H2D copies go through a dedicated copy stream into one of two staging sets, so the copies of call
         i + 1 overlap the kernels of call i (the step is PCIe-bound: 839 MB of inputs per call at batch 64);
         every call still copies all of its own inputs and reads its own result back."""
+        with _lib.device_guard(self.device):
+            return self._run_host(host)
+
+    def _run_host(self, host):
         dev = self.device
         main = torch.cuda.current_stream(dev)
         if self.staging is None:
@@ -301,11 +384,10 @@ class HotPathStep:
             for k, v in host.items():
                 s[k].copy_(v, non_blocking=True)
             self.copied[i].record(self.copy_stream)
-        main.wait_event(self.copied[i])
-        r = self.run_device(s["raw1"], s["raw2"], s["pred1"], s["pred2"], s["gt1"], s["gt2"], s["conf1"], s["conf2"],
-                            s["gt_depth"])
-        self.consumed[i].record(main)
+        r = self._run_device(s["raw1"], s["raw2"], s["pred1"], s["pred2"], s["gt1"], s["gt2"], s["conf1"], s["conf2"],
+                             s["gt_depth"], self.copied[i])
         self.wait_result(r)
+        self.consumed[i].record(main)
         self.result_host.copy_(r, non_blocking=True)
         self.host_calls += 1
         return self.result_host
@@ -356,16 +438,17 @@ class EvalStep:
     def run_batch(self, raw, pointmap, gt_depth):
         """raw [B,Hs,Ws] uint16, pointmap [B,H,W,3] float32, gt_depth [B,gh,gw] float32, all on the device.
         Returns the preprocessed thermal batch [B,3,H,W]; the metrics go into the accumulator.  No host sync."""
-        main = torch.cuda.current_stream(self.device)
-        self.fork.record(main)
-        with torch.cuda.stream(self.side):
-            self.side.wait_event(self.fork)
-            me = _metrics.compute_depth_metrics_batch(pointmap, gt_depth, out=self.met_out)
-            self.join.record(self.side)
-        tb = _pre.preprocess_thermal_batch(raw, (self.W, self.H), path=self.path, out=self.pre_out, histogram=False)
-        main.wait_event(self.join)
-        self.acc.update(me["metrics_f64"])
-        return tb.thermal
+        with _lib.device_guard(self.device):
+            main = torch.cuda.current_stream(self.device)
+            self.fork.record(main)
+            with torch.cuda.stream(self.side):
+                self.side.wait_event(self.fork)
+                me = _metrics.compute_depth_metrics_batch(pointmap, gt_depth, out=self.met_out)
+                self.join.record(self.side)
+            tb = _pre.preprocess_thermal_batch(raw, (self.W, self.H), path=self.path, out=self.pre_out, histogram=False)
+            main.wait_event(self.join)
+            self.acc.update(me["metrics_f64"])
+            return tb.thermal
 
     def finish(self) -> Dict[str, float]:
         """All-reduce (SUM) the accumulator over the ranks and return the dataset-mean metrics (host sync)."""

@@ -31,6 +31,7 @@ def _to_cuda(t: torch.Tensor):
 
 
 # ----------------------------------------------------------------------------- resize
+@_lib.on_tensor_device
 def resize_bilinear(src: torch.Tensor, size_hw, mode: Optional[str] = None) -> torch.Tensor:
     """cv2.resize(src, (w, h)) INTER_LINEAR (IPP-off recipe), bit-exact.
 
@@ -55,6 +56,7 @@ def resize_bilinear(src: torch.Tensor, size_hw, mode: Optional[str] = None) -> t
     return out if src.is_cuda else out.cpu()
 
 
+@_lib.on_tensor_device
 def resize_nearest(src: torch.Tensor, size_hw) -> torch.Tensor:
     """cv2.resize(..., INTER_NEAREST) of float32 maps (utils/evaluate_depth_metrics.py:320-323)."""
     squeeze = src.dim() == 2
@@ -76,6 +78,7 @@ class ThermalBatch(NamedTuple):
     grad_stats: Optional[torch.Tensor] = None  # [B, tiles, 4] partial sums of |Dx gray|, |Dy gray| (train path)
 
 
+@_lib.on_tensor_device
 def preprocess_thermal_batch(raw_u16: torch.Tensor, img_size=(224, 224), path: str = "train",
                              out_channels: int = 3, out: Optional[dict] = None,
                              histogram: bool = True) -> ThermalBatch:
@@ -138,6 +141,7 @@ def preprocess_thermal_batch(raw_u16: torch.Tensor, img_size=(224, 224), path: s
     raise ValueError("path must be 'train' or 'inference'")
 
 
+@_lib.on_tensor_device
 def bracket_fallback_count(workspace: torch.Tensor, B: int, img_size) -> int:
     """Diagnostics: frames of the last preprocess_thermal_batch(..., histogram=False, out={'workspace': ws}) call
     whose percentiles needed the exact per-frame select (same result, slower).  Synchronises."""
@@ -149,6 +153,7 @@ def bracket_fallback_count(workspace: torch.Tensor, B: int, img_size) -> int:
 
 
 # ----------------------------------------------------------------------------- reference signatures
+@_lib.on_tensor_device
 def enhance_thermal_contrast(thermal_tensor):
     """Drop-in for utils/preprocessing.py:6-30 (percentile clip-normalise, 3-channel output)."""
     if thermal_tensor is None:
@@ -182,6 +187,7 @@ def enhance_thermal_contrast(thermal_tensor):
     return out if src_cuda else out.cpu()
 
 
+@_lib.on_tensor_device
 def enhance_thermal_fixed_range(thermal_tensor, normalized=True):
     """Drop-in for utils/preprocessing.py:32-73 (Freiburg fixed window 21800..25000).
 

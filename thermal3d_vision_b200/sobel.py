@@ -16,6 +16,7 @@ from . import _lib
 
 class _SobelEnhance(torch.autograd.Function):
     @staticmethod
+    @_lib.on_tensor_device
     def forward(ctx, x, edge_weight, temp_scale, local_norm):
         B, C, H, W = x.shape
         lib = _lib.lib()
@@ -31,6 +32,7 @@ class _SobelEnhance(torch.autograd.Function):
         return out
 
     @staticmethod
+    @_lib.on_tensor_device
     def backward(ctx, dout):
         x, params = ctx.saved_tensors
         if ctx.needs_input_grad[0]:

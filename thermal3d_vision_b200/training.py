@@ -15,6 +15,7 @@ from . import _lib
 from . import loss as _loss
 
 
+@_lib.on_tensor_device
 def resample_bilinear(x: torch.Tensor, size_hw) -> torch.Tensor:
     """F.interpolate(mode='bilinear', align_corners=False) for channels-last maps.
 
@@ -54,7 +55,10 @@ def training_batch_loss(pred_pts1, pred_pts2, gt_pts1, gt_pts2, pred_conf1=None,
     # torch.clamp(conf, min=1e-5) (:278-279) composes idempotently with the loss's own clamp to [1e-5, 10]
     # (same values, same inclusive gradient mask), so it needs no extra pass.
     if not use_thermal_aware_loss:
-        thermal1 = thermal2 = None                               # :305-318: plain confidence-weighted L1
+        # :305-318: plain confidence-weighted L1 on the conf clamped from BELOW only (:278-279) -- it never passes
+        # through utils/loss.py's clamp(conf, 1e-5, 10); DUSt3R confidences (1 + exp) routinely exceed 10
+        return _loss.fused_thermal_loss(pred_pts1, pred_pts2, gt_pts1, gt_pts2, conf1, conf2, None, None,
+                                        alpha=alpha, multi_scale=False, batch_mean=True, conf_min_only=True)
     return _loss.fused_thermal_loss(pred_pts1, pred_pts2, gt_pts1, gt_pts2, conf1, conf2, thermal1, thermal2,
                                     alpha=alpha, edge_weight=edge_weight, smoothness_weight=smoothness_weight,
                                     detail_weight=detail_weight, multi_scale=multi_scale, batch_mean=True)
