@@ -85,6 +85,78 @@ def test_pointmap_z_in_place_batched(cuda_device, H, W):
         assert med[b, 0] == np.median(gt[b][mk]) and med[b, 1] == np.median(pm[b, ..., 2][mk])
 
 
+def _check_batch(tm, pm_or_depth, gt, cuda_device, **kw):
+    d = torch.from_numpy(pm_or_depth).to(cuda_device)
+    r = tm.compute_depth_metrics_batch(d, torch.from_numpy(gt).to(cuda_device), **kw)
+    got, med = r["metrics_f64"].cpu().numpy(), r["medians"].cpu().numpy()
+    z = pm_or_depth[..., 2] if pm_or_depth.ndim == 4 else pm_or_depth
+    for b in range(gt.shape[0]):
+        ref = ref_metrics.compute_depth_metrics(z[b], gt[b], median_scaling=kw.get("median_scaling", True))
+        _close(got[b, :7], _vec(ref))
+        mk = (gt[b] > 0) & np.isfinite(gt[b])
+        if kw.get("median_scaling", True) and mk.any():
+            assert med[b, 0] == np.median(gt[b][mk]) and med[b, 1] == np.median(z[b][mk]), b
+
+
+@pytest.mark.parametrize("kind", ["walls", "ties", "constant", "two_values", "ramp", "tiny_spread"])
+def test_one_kernel_path_on_clustered_depth(cuda_device, kind):
+    """The one-kernel fast path (t3d_metrics_fused.cu) on distributions that stress its bucketed median candidates:
+    spatially coherent depth (whole chunks inside one bucket), heavy ties (every candidate the same key), constant
+    images (the bracket holds everything -> candidate overflow -> exact fallback), an even split between two values
+    (the two middle order statistics differ and live in different buckets), a ramp, a spread of a few ulps."""
+    from thermal3d_vision_b200 import metrics as tm
+    rng = np.random.default_rng(11)
+    B, H, W = 11, 96, 128                      # B not a multiple of the wave size
+    gt = np.empty((B, H, W), np.float32)
+    for b in range(B):
+        if kind == "walls":                    # piecewise-constant planes + tiny noise, sorted spatially
+            levels = np.sort(rng.uniform(1.0, 9.0, 6)).astype(np.float32)
+            gt[b] = np.repeat(levels, H * W // 6 + 1)[:H * W].reshape(H, W) + 1e-4 * rng.standard_normal((H, W)).astype(np.float32)
+        elif kind == "ties":
+            gt[b] = rng.integers(2, 5, (H, W)).astype(np.float32)
+        elif kind == "constant":
+            gt[b] = 3.25
+        elif kind == "two_values":
+            gt[b] = np.where(np.arange(H * W).reshape(H, W) % 2 == 0, 2.0, 5.0)
+        elif kind == "ramp":
+            gt[b] = np.linspace(0.5, 20.0, H * W, dtype=np.float32).reshape(H, W)
+        else:
+            gt[b] = np.float32(4.0) + np.float32(4.7683716e-07) * rng.integers(0, 6, (H, W)).astype(np.float32)
+    gt[1, :5] = 0.0
+    gt[2, 3, 7] = np.inf
+    pm = rng.standard_normal((B, H, W, 3)).astype(np.float32)
+    noise = 0.15          # a noiseless prediction makes every term pure rounding noise, in the reference too
+    pm[..., 2] = np.abs(gt * (1.0 + noise * rng.standard_normal(gt.shape)).astype(np.float32)) * np.float32(0.8) + np.float32(0.01)
+    pm[..., 2][~np.isfinite(pm[..., 2])] = 1.0
+    _check_batch(tm, pm, gt, cuda_device)
+    _check_batch(tm, np.ascontiguousarray(pm[..., 2]), gt, cuda_device)                 # planar prediction
+    _check_batch(tm, pm, gt, cuda_device, median_scaling=False)
+
+
+def test_one_kernel_path_resampled_gt_many_images(cuda_device):
+    """GT at another size (nearest resample inside the kernel) and enough images for several waves of the queue."""
+    from oracle import ref_preprocess
+    from thermal3d_vision_b200 import metrics as tm
+    rng = np.random.default_rng(5)
+    B, H, W, gh, gw = 19, 48, 64, 80, 72
+    big = (1.5 + 3 * np.abs(rng.standard_normal((B, gh, gw)))).astype(np.float32)
+    big[3, :9] = 0.0
+    big[7] = 0.0                                   # empty mask
+    small = np.stack([ref_preprocess.resize_nearest(g, (H, W)) for g in big])
+    pm = rng.standard_normal((B, H, W, 3)).astype(np.float32)
+    pm[..., 2] = np.abs(small * (1 + 0.2 * rng.standard_normal(small.shape)).astype(np.float32)) + 0.02
+    r = tm.compute_depth_metrics_batch(torch.from_numpy(pm).to(cuda_device), torch.from_numpy(big).to(cuda_device))
+    got = r["metrics_f64"].cpu().numpy()
+    for b in range(B):
+        if b == 7:
+            assert np.isnan(got[b, :4]).all() and (got[b, 4:8] == 0).all()
+            continue
+        _close(got[b, :7], _vec(ref_metrics.compute_depth_metrics(pm[b, ..., 2], small[b])))
+    # two runs: bit-identical (fixed-order sums, exact selection)
+    r2 = tm.compute_depth_metrics_batch(torch.from_numpy(pm).to(cuda_device), torch.from_numpy(big).to(cuda_device))
+    assert torch.equal(torch.nan_to_num(r["metrics_f64"]), torch.nan_to_num(r2["metrics_f64"]))
+
+
 def test_nan_and_degenerate_predictions(cuda_device):
     from thermal3d_vision_b200 import metrics as tm
     rng = np.random.default_rng(3)

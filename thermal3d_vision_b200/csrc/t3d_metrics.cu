@@ -11,15 +11,15 @@
 // medians of gt[mask] and pred[mask] by radix select; pred *= med_gt/med_pred;
 // then every per-pixel term in float32 exactly as numpy evaluates it
 // (IEEE div/mul, no FMA), summed in fp64 in a fixed order (deterministic).
-#include "t3d_common.cuh"
-#include "t3d_select.cuh"
+#include "t3d_metrics_internal.cuh"
 
 #include <stdlib.h>
 
 namespace {
 
+using namespace t3d_metrics;
+
 constexpr int kChunkThreads = 256;
-constexpr int kNPart = 8;   // abs_rel, sq_rel, sq, log2, a1, a2, a3, (pad)
 
 // Batched exact medians in two passes over the data (np.median, utils/metrics.py:47):
 //   S  sample 4096 valid pixels per image, sort them in shared memory, and bracket the median of each
@@ -40,6 +40,7 @@ struct MetricsWs {
     unsigned int* cand;     // [B][2][kCandCap] keys
     float* scale;           // [B]
     double* partials;       // [B][chunks][kNPart]
+    void* fused;            // workspace of the one-kernel fast path (t3d_metrics_fused.cu)
     size_t total;
 };
 
@@ -55,6 +56,7 @@ MetricsWs metrics_ws(void* base, int B, int n, int chunks) {
     w.cand = reinterpret_cast<unsigned int*>(take((size_t)B * 2 * kCandCap * sizeof(unsigned int)));
     w.scale = reinterpret_cast<float*>(take((size_t)B * 2 * sizeof(float)));
     w.partials = reinterpret_cast<double*>(take((size_t)B * chunks * kNPart * sizeof(double)));
+    w.fused = take(fused_ws_bytes(B, chunks));
     w.total = off;
     return w;
 }
@@ -274,9 +276,6 @@ depth_extract_kernel(const PixelSrc s, int pred_offset, float* __restrict__ vz, 
 // 4 consecutive pixels: one 128-bit load of GT, one (planar) or three (AoS: all 48 bytes are fetched from DRAM
 // anyway) of the prediction, two 128-bit stores; the integer keys are compared as raw bits; every counter is a
 // predicated add.  Same outputs as depth_extract_kernel<false>.
-__device__ __forceinline__ unsigned int key_of_bits(unsigned int b) { return b ^ ((unsigned int)((int)b >> 31) | 0x80000000u); }
-
-constexpr int kResampleMaxDim = 2048;      // H + W limit of the in-kernel nearest-neighbour index tables (8 KB)
 
 template <int PSTRIDE, bool RESAMPLE>
 __global__ void __launch_bounds__(kChunkThreads, 6)
@@ -444,55 +443,7 @@ median_scale_kernel(const float* __restrict__ vz, const float* __restrict__ vg, 
     if (tid == 0) medians[2 * b + a] = med;
 }
 
-// ------------------------------------------------------------------ M3: per-pixel terms
-__device__ __forceinline__ float np_maximum(float a, float b) { return (isnan(a) || isnan(b)) ? __int_as_float(0x7fc00000) : fmaxf(a, b); }
-
-// Per-pixel terms of utils/metrics.py:48-59.  GENERAL == false (mask = gt > 0 & finite, so gt is a positive
-// finite number): exactly one of gt/pred, pred/gt is >= 1, hence max(gt/pred, pred/gt) = max(gt,p) / min(gt,p)
-// -- ONE IEEE division keeps the delta-counts exact -- and (log gt - log p)^2 = log(thresh)^2.  Non-positive or
-// NaN predictions take the literal two-division form (same results as numpy: NaN / inf propagate).
-template <bool GENERAL>
-__device__ __forceinline__ void metric_terms(float gt, float z, float s, float accf[4], int cnt[3]) {
-    if (isnan(gt)) return;                                                   // invalid pixel marker
-    const float pr = __fmul_rn(z, s);                                        // pred *= scale   (:48)
-    float th, dl;
-    if (!GENERAL && pr > 0.f) {
-        th = __fdiv_rn(fmaxf(gt, pr), fminf(gt, pr));                        // :51
-        dl = 0.69314718f * __log2f(th);                                      // |log gt - log pred|
-    } else {
-        th = np_maximum(__fdiv_rn(gt, pr), __fdiv_rn(pr, gt));
-        dl = __logf(gt) - __logf(pr);
-    }
-    cnt[0] += th < 1.25f; cnt[1] += th < 1.5625f; cnt[2] += th < 1.953125f;  // :52-54
-    const float d = __fsub_rn(gt, pr);
-    const float d2 = __fmul_rn(d, d);
-    const float rg = __fdividef(1.0f, gt);
-    accf[0] += fabsf(d) * rg;                                                // :56  |gt - pred| / gt
-    accf[1] += d2 * rg;                                                      // :57
-    accf[2] += d2;                                                           // :58
-    accf[3] += dl * dl;                                                      // :59
-}
-
-// Fast form of the per-pixel terms for the common case (no caller mask: gt is a positive finite number or the
-// NaN "invalid" marker; scaled prediction positive): branch-free, validity by select, counts by predicate.
-// Same arithmetic as metric_terms<false>: ONE IEEE division max/min keeps the delta-counts exact.
-__device__ __forceinline__ float lg2_fast(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
-
-__device__ __forceinline__ void metric_terms_fast(float gt, float pr, float accf[4], int cnt[3]) {
-    const bool valid = (gt == gt);                                           // NaN marks an unselected pixel
-    const float g = valid ? gt : 1.0f, q = valid ? pr : 1.0f;               // -> th = 1, every term 0
-    const float th = __fdiv_rn(fmaxf(g, q), fminf(g, q));                    // :51 (exactly one of the two ratios is >= 1)
-    const float dl = 0.69314718f * lg2_fast(th);                             // |log gt - log pred|, th >= 1 is normal
-    cnt[0] += (valid && th < 1.25f); cnt[1] += (valid && th < 1.5625f); cnt[2] += (valid && th < 1.953125f);   // :52-54
-    const float d = g - q;
-    const float d2 = d * d;
-    const float rg = __fdividef(1.0f, g);
-    accf[0] = fmaf(fabsf(d), rg, accf[0]);                                   // :56  |gt - pred| / gt
-    accf[1] = fmaf(d2, rg, accf[1]);                                         // :57
-    accf[2] += d2;                                                           // :58
-    accf[3] = fmaf(dl, dl, accf[3]);                                         // :59
-}
-
+// ------------------------------------------------------------------ M3: per-pixel terms (t3d_metrics_internal.cuh)
 template <bool GENERAL>
 __global__ void __launch_bounds__(kChunkThreads, 4)
 metrics_sum_kernel(const float* __restrict__ vz, const float* __restrict__ vg,
@@ -738,6 +689,15 @@ int t3d_depth_metrics(const float* pred, int pred_stride, int pred_offset,
     const bool fast_x = !mask && (W % 4 == 0) && t3d_aligned16(pred) && t3d_aligned16(gt) &&
                         (!src.resample || H + W <= kResampleMaxDim) && (src.resample || (gt_h * gt_w) % 4 == 0) &&
                         ((pred_stride == 3 && pred_offset == 2) || (pred_stride == 1 && pred_offset == 0));
+    float* medians_out = out_medians ? out_medians : w.scale;       // [B][2]: median(gt), median(pred)
+    static const bool use_fused = [] { const char* e = getenv("T3D_METRIC_FUSED"); return e ? atoi(e) != 0 : true; }();
+    if (fast_x && use_fused) {
+        // one persistent kernel: the pointmap is read from DRAM once, the second pass of an image follows its first
+        // a few images later and hits the L2 (t3d_metrics_fused.cu)
+        if (!median_scaling) T3D_CUDA(cudaMemsetAsync(medians_out, 0, (size_t)B * 2 * sizeof(float), st));
+        return launch_fused(pred, pred_stride, gt, gt_h, gt_w, B, H, W, median_scaling, w.bracket, medians_out, w.partials,
+                            chunks, out, out_f64, w.fused, st);
+    }
 #define T3D_XFAST(PS_, RS_) T3D_LAUNCH("depth_extract_kernel", st, (depth_extract_fast_kernel<PS_, RS_><<<g, kChunkThreads, 0, st>>>( \
             pred, gt, n, w.vz, w.vg, w.counters, w.bracket, w.cand, H, W, gt_h, gt_w)))
     if (fast_x && pred_stride == 3) { if (src.resample) T3D_XFAST(3, true); else T3D_XFAST(3, false); }
@@ -749,7 +709,7 @@ int t3d_depth_metrics(const float* pred, int pred_stride, int pred_offset,
     else
         T3D_LAUNCH("depth_extract_kernel", st, depth_extract_kernel<false><<<g, kChunkThreads, 0, st>>>(
             src, pred_offset, w.vz, w.vg, w.counters, w.bracket, w.cand));
-    float* medians = out_medians ? out_medians : w.scale;       // [B][2]: median(gt), median(pred)
+    float* medians = medians_out;
     T3D_LAUNCH("median_scale_kernel", st, median_scale_kernel<<<dim3(2, B), kMedThreads, kCandCap * sizeof(unsigned int), st>>>(
         w.vz, w.vg, w.counters, w.cand, w.bracket, n, median_scaling, medians));
     if (mask)       // a caller-supplied mask may select non-positive / non-finite GT: literal formulas

@@ -1,0 +1,70 @@
+// t3d_metrics_internal.cuh -- shared between t3d_metrics.cu (entry points, general multi-kernel chain) and
+// t3d_metrics_fused.cu (the one-kernel fast path): the per-pixel arithmetic of utils/metrics.py:48-59.
+#pragma once
+#include "t3d_common.cuh"
+#include "t3d_select.cuh"
+
+namespace t3d_metrics {
+
+constexpr int kNPart = 8;                  // abs_rel, sq_rel, sq, log2, a1, a2, a3, (pad)
+constexpr int kResampleMaxDim = 2048;      // H + W limit of the in-kernel nearest-neighbour index tables (8 KB)
+constexpr int kBucketCap = 8192;           // fused path: candidates per (image, stream, bucket)
+
+__device__ __forceinline__ unsigned int key_of_bits(unsigned int b) { return b ^ ((unsigned int)((int)b >> 31) | 0x80000000u); }
+
+__device__ __forceinline__ float np_maximum(float a, float b) { return (isnan(a) || isnan(b)) ? __int_as_float(0x7fc00000) : fmaxf(a, b); }
+
+// Per-pixel terms of utils/metrics.py:48-59.  GENERAL == false (mask = gt > 0 & finite, so gt is a positive
+// finite number): exactly one of gt/pred, pred/gt is >= 1, hence max(gt/pred, pred/gt) = max(gt,p) / min(gt,p)
+// -- ONE IEEE division keeps the delta-counts exact -- and (log gt - log p)^2 = log(thresh)^2.  Non-positive or
+// NaN predictions take the literal two-division form (same results as numpy: NaN / inf propagate).
+template <bool GENERAL>
+__device__ __forceinline__ void metric_terms(float gt, float z, float s, float accf[4], int cnt[3]) {
+    if (isnan(gt)) return;                                                   // invalid pixel marker
+    const float pr = __fmul_rn(z, s);                                        // pred *= scale   (:48)
+    float th, dl;
+    if (!GENERAL && pr > 0.f) {
+        th = __fdiv_rn(fmaxf(gt, pr), fminf(gt, pr));                        // :51
+        dl = 0.69314718f * __log2f(th);                                      // |log gt - log pred|
+    } else {
+        th = np_maximum(__fdiv_rn(gt, pr), __fdiv_rn(pr, gt));
+        dl = __logf(gt) - __logf(pr);
+    }
+    cnt[0] += th < 1.25f; cnt[1] += th < 1.5625f; cnt[2] += th < 1.953125f;  // :52-54
+    const float d = __fsub_rn(gt, pr);
+    const float d2 = __fmul_rn(d, d);
+    const float rg = __fdividef(1.0f, gt);
+    accf[0] += fabsf(d) * rg;                                                // :56  |gt - pred| / gt
+    accf[1] += d2 * rg;                                                      // :57
+    accf[2] += d2;                                                           // :58
+    accf[3] += dl * dl;                                                      // :59
+}
+
+// Fast form of the per-pixel terms for the common case (no caller mask: gt is a positive finite number or the
+// NaN "invalid" marker; scaled prediction positive): branch-free, validity by select, counts by predicate.
+// Same arithmetic as metric_terms<false>: ONE IEEE division max/min keeps the delta-counts exact.
+__device__ __forceinline__ float lg2_fast(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+
+__device__ __forceinline__ void metric_terms_fast(float gt, float pr, float accf[4], int cnt[3]) {
+    const bool valid = (gt == gt);                                           // NaN marks an unselected pixel
+    const float g = valid ? gt : 1.0f, q = valid ? pr : 1.0f;               // -> th = 1, every term 0
+    const float th = __fdiv_rn(fmaxf(g, q), fminf(g, q));                    // :51 (exactly one of the two ratios is >= 1)
+    const float dl = 0.69314718f * lg2_fast(th);                             // |log gt - log pred|, th >= 1 is normal
+    cnt[0] += (valid && th < 1.25f); cnt[1] += (valid && th < 1.5625f); cnt[2] += (valid && th < 1.953125f);   // :52-54
+    const float d = g - q;
+    const float d2 = d * d;
+    const float rg = __fdividef(1.0f, g);
+    accf[0] = fmaf(fabsf(d), rg, accf[0]);                                   // :56  |gt - pred| / gt
+    accf[1] = fmaf(d2, rg, accf[1]);                                         // :57
+    accf[2] += d2;                                                           // :58
+    accf[3] = fmaf(dl, dl, accf[3]);                                         // :59
+}
+
+
+// fused fast path (t3d_metrics_fused.cu)
+size_t fused_ws_bytes(int B, int chunks);
+int launch_fused(const float* pred, int pred_stride, const float* gt, int gt_h, int gt_w, int B, int H, int W,
+                 int median_scaling, const unsigned int* bracket, float* medians, double* partials, int chunks,
+                 float* out, double* out_f64, void* ws, cudaStream_t st);
+
+}  // namespace t3d_metrics

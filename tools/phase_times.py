@@ -19,18 +19,20 @@ def timeit(fn, n=50):
     e1.record(); torch.cuda.synchronize()
     return e0.elapsed_time(e1) / n * 1e3
 res = {}
-for ov in (True, False):
-    step.overlap = ov
-    res[f"step_overlap={ov}"] = timeit(lambda: step.run_device(*args))
+for pl in (True, False):
+    step.pipelined = pl
+    res[f"step_pipelined={pl}"] = timeit(lambda: step.run_device(*args))
+    step.finish()
 size = (W, H)
-res["pre1"] = timeit(lambda: pp.preprocess_thermal_batch(d["raw1"], size, out=step.pre_out[0]))
+pre_half = [{}, {}]
+res["pre1"] = timeit(lambda: pp.preprocess_thermal_batch(d["raw1"], size, out=pre_half[0]))
 raw2 = torch.cat([d["raw1"], d["raw2"]])
 out2 = {}
 t = pp.preprocess_thermal_batch(raw2, size, out=out2)
 out2.update({"thermal": t.thermal, "percentiles": t.percentiles, "histogram": t.histogram, "grad_stats": t.grad_stats})
 res["pre_both_128"] = timeit(lambda: pp.preprocess_thermal_batch(raw2, size, out=out2))
 res["metrics"] = timeit(lambda: tm.compute_depth_metrics_batch(d["pred1"], d["gt_depth"], out=step.met_out))
-tb1 = pp.preprocess_thermal_batch(d["raw1"], size, out=step.pre_out[0]); tb2 = pp.preprocess_thermal_batch(d["raw2"], size, out=step.pre_out[1])
+tb1 = pp.preprocess_thermal_batch(d["raw1"], size, out=pre_half[0]); tb2 = pp.preprocess_thermal_batch(d["raw2"], size, out=pre_half[1])
 kw = dict(alpha=0.2, edge_weight=0.5, smoothness_weight=0.3, detail_weight=0.4, multi_scale=False)
 res["loss_with_stats"] = timeit(lambda: tl.fused_thermal_loss_fwd_bwd(d["pred1"], d["pred2"], d["gt1"], d["gt2"], d["conf1"], d["conf2"], tb1.thermal, tb2.thermal, out=step.loss_out, thermal_stats=(tb1.grad_stats, tb2.grad_stats), **kw))
 res["loss_with_stats_replicated"] = timeit(lambda: tl.fused_thermal_loss_fwd_bwd(d["pred1"], d["pred2"], d["gt1"], d["gt2"], d["conf1"], d["conf2"], tb1.thermal, tb2.thermal, out=step.loss_out, thermal_stats=(tb1.grad_stats, tb2.grad_stats), thermal_replicated=True, **kw))
@@ -39,7 +41,7 @@ kwm = dict(kw); kwm["multi_scale"] = True
 res["loss_multiscale"] = timeit(lambda: tl.fused_thermal_loss_fwd_bwd(d["pred1"], d["pred2"], d["gt1"], d["gt2"], d["conf1"], d["conf2"], tb1.thermal, tb2.thermal, out=step.loss_out, **kwm))
 # host-side enqueue cost of one step (no sync inside; the launch queue is deep enough for 20 steps)
 import time
-step.overlap = True
+step.pipelined = True
 torch.cuda.synchronize()
 t0 = time.perf_counter()
 for _ in range(20): step.run_device(*args)

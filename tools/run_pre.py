@@ -15,7 +15,6 @@ with_loss = len(sys.argv) > 1 and sys.argv[1] == "loss"
 args = (d["raw1"], d["raw2"], d["pred1"], d["pred2"], d["gt1"], d["gt2"], d["conf1"], d["conf2"], d["gt_depth"])
 for _ in range(3):
     if with_loss:
-        step.overlap = False          # one stream: the ncu launch order is the program order
         step.run_device(*args)
     else:
         pp.preprocess_thermal_batch(raw2, (W, H), out=step.pre_both, histogram=hist)
