@@ -93,6 +93,24 @@ __device__ __forceinline__ void stg_stream_f1(float* p, float v) {
     asm volatile("st.global.cs.f32 [%0], %1;" :: "l"(p), "f"(v) : "memory");
 }
 
+// L2 residency control (createpolicy + .L2::cache_hint): scratch that one kernel writes and the next one reads is
+// kept in the 126 MB L2 ("evict_last") while the streaming traffic around it passes through with normal priority.
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ void stg_f4_l2hint(float* p, float4 v, uint64_t policy) {
+    asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1,%2,%3,%4}, %5;"
+                 :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "l"(policy) : "memory");
+}
+__device__ __forceinline__ float4 ldg_f4_l2hint(const float* p, uint64_t policy) {
+    float4 v;
+    asm volatile("ld.global.L1::no_allocate.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p), "l"(policy));
+    return v;
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

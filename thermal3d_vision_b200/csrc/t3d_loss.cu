@@ -593,12 +593,17 @@ __global__ void __launch_bounds__(128) loss_finalize_kernel(const FinalizeArgs a
         tot[v][k] = (k < kNTerms - 1) ? ((wsum[0][v][k] + wsum[1][v][k]) + (wsum[2][v][k] + wsum[3][v][k])) : 0.0;
     }
     __syncthreads();
-    if (a.partials2 && tid < 6) {      // scale-2 sums of the split multi-scale path: fixed order over its tiles
-        const int v = tid / 3, k = tid - v * 3;
-        const float* p2 = a.partials2 + ((size_t)(2 * b + v) * a.tiles2) * 4 + k;
-        double s2 = 0.0;
-        for (int t = 0; t < a.tiles2; ++t) s2 += (double)p2[(size_t)t * 4];
-        tot[v][4 + k] = s2;
+    if (a.partials2) {                 // scale-2 sums of the split multi-scale path: lane t owns tiles t, t + 32, ...
+        const int v = wrp >> 1;        // of one view (2 warps per view: 6 (view, term) sums over 4 warps), fixed butterfly
+        const float4* p2 = reinterpret_cast<const float4*>(a.partials2 + ((size_t)(2 * b + v) * a.tiles2) * 4);
+        double s2[3] = {0.0, 0.0, 0.0};
+        if ((wrp & 1) == 0)
+            for (int t = lane; t < a.tiles2; t += 32) { const float4 x = p2[t]; s2[0] += (double)x.x; s2[1] += (double)x.y; s2[2] += (double)x.z; }
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const double r = warp_sum(s2[k]);
+            if ((wrp & 1) == 0 && lane == 0) tot[v][4 + k] = r;
+        }
     }
     __syncthreads();
     if (tid == 0) {

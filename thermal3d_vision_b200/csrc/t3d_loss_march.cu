@@ -19,6 +19,7 @@
 //    (q_y of the row above is carried, q_x of the left neighbour is shuffled),
 //    gradients are gathered (no atomics) and written once with 128-bit stores.
 #include "t3d_loss_internal.cuh"
+#include <stdlib.h>
 
 namespace {
 
@@ -142,7 +143,7 @@ __device__ __forceinline__ void load_row(const float* __restrict__ st, int idx, 
 // ------------------------------------------------------------------ kernel
 // S2: multi-scale -- the scale-2 pass (t3d_loss_scale2.cu) left 0.25 * d(loss)/d(pooled z) per 2x2 cell in a.dzp
 template <int TCH, bool REP, bool BWD, bool S2, int NS, int WARPS>
-__global__ void __launch_bounds__(WARPS * 32, 1) loss_march_kernel(const MarchArgs a) {
+__global__ void __launch_bounds__((TCH == 3) ? 320 : 384, 1) loss_march_kernel(const MarchArgs a) {
     static_assert(!REP || TCH == 1, "replicated planes: one plane is staged");
     using St = Stage<TCH>;
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -377,10 +378,9 @@ __global__ void __launch_bounds__(WARPS * 32, 1) loss_march_kernel(const MarchAr
     }
 }
 
-template <int TCH, bool REP, bool BWD, bool S2>
-int launch(const MarchArgs& a, cudaStream_t st) {
+template <int TCH, bool REP, bool BWD, bool S2, int WARPS>
+int launch_w(const MarchArgs& a, cudaStream_t st) {
     constexpr int NS = 4;
-    constexpr int WARPS = (TCH == 3) ? 10 : 12;
     constexpr size_t smem = (size_t)WARPS * NS * Stage<TCH>::kFloats * sizeof(float) + (size_t)WARPS * NS * 8;
     static_assert(smem <= 227 * 1024, "ring does not fit in shared memory");
     static bool attr_done[kT3dMaxDevices] = {};
@@ -394,6 +394,20 @@ int launch(const MarchArgs& a, cudaStream_t st) {
     T3D_LAUNCH("loss_march_kernel", st,
                loss_march_kernel<TCH, REP, BWD, S2, NS, WARPS><<<grid, WARPS * 32, smem, st>>>(a));
     return T3D_OK;
+}
+
+// Warps per CTA (one CTA per SM).  Default: as many as the register file / shared memory hold (12; 10 with three
+// staged thermal planes).  T3D_MARCH_WARPS=8 / 10 (tuning knob): fewer warps leave registers and shared memory for
+// other streams' kernels to run UNDER this DRAM-bound one.  Measured (round 2): the kernel alone 212 -> 230 us with 8
+// warps, and with the next step's sampling + resize kernels co-resident 262 us -- what the step gains by hiding them
+// it loses here (they compete for the same issue slots): not used.
+template <int TCH, bool REP, bool BWD, bool S2>
+int launch(const MarchArgs& a, cudaStream_t st) {
+    static const int env_warps = [] { const char* e = getenv("T3D_MARCH_WARPS"); return e ? atoi(e) : 0; }();
+    const int want = env_warps ? env_warps : 12;
+    if (want <= 8) return launch_w<TCH, REP, BWD, S2, 8>(a, st);
+    if (want <= 10 || TCH == 3) return launch_w<TCH, REP, BWD, S2, 10>(a, st);
+    return launch_w<TCH, REP, BWD, S2, (TCH == 3) ? 10 : 12>(a, st);
 }
 
 }  // namespace

@@ -40,7 +40,6 @@ struct MetricsWs {
     unsigned int* cand;     // [B][2][kCandCap] keys
     float* scale;           // [B]
     double* partials;       // [B][chunks][kNPart]
-    void* fused;            // workspace of the one-kernel fast path (t3d_metrics_fused.cu)
     size_t total;
 };
 
@@ -56,7 +55,6 @@ MetricsWs metrics_ws(void* base, int B, int n, int chunks) {
     w.cand = reinterpret_cast<unsigned int*>(take((size_t)B * 2 * kCandCap * sizeof(unsigned int)));
     w.scale = reinterpret_cast<float*>(take((size_t)B * 2 * sizeof(float)));
     w.partials = reinterpret_cast<double*>(take((size_t)B * chunks * kNPart * sizeof(double)));
-    w.fused = take(fused_ws_bytes(B, chunks));
     w.total = off;
     return w;
 }
@@ -271,16 +269,18 @@ depth_extract_kernel(const PixelSrc s, int pred_offset, float* __restrict__ vz, 
     }
 }
 
-// Fast form of X for the common case: no caller mask, GT at the prediction's size, 16-byte aligned, n % 4 == 0,
-// prediction either planar (PSTRIDE 1) or the Z channel of an AoS pointmap (PSTRIDE 3, offset 2).  A thread takes
-// 4 consecutive pixels: one 128-bit load of GT, one (planar) or three (AoS: all 48 bytes are fetched from DRAM
-// anyway) of the prediction, two 128-bit stores; the integer keys are compared as raw bits; every counter is a
-// predicated add.  Same outputs as depth_extract_kernel<false>.
+// Fast form of X for the common case: no caller mask, 16-byte aligned, n % 4 == 0, prediction either planar
+// (PSTRIDE 1) or the Z channel of an AoS pointmap (PSTRIDE 3, offset 2), GT optionally nearest-resampled.  A thread
+// takes 4 consecutive pixels: one 128-bit load of GT, one (planar) or three (AoS: all 48 bytes are fetched from DRAM
+// anyway) of the prediction; the integer keys are compared as raw bits; every counter is a predicated add.
+// Only the planar Z copy is written (the sum pass re-reads the caller's GT and re-derives the validity from it),
+// with an L2 evict_last policy: the 4 bytes / pixel the second pass needs stay in the L2 between the two passes and
+// are overwritten there by the next call -- they never travel to DRAM.  Counters / candidates as depth_extract_kernel.
 
 template <int PSTRIDE, bool RESAMPLE>
 __global__ void __launch_bounds__(kChunkThreads, 6)
 depth_extract_fast_kernel(const float* __restrict__ pred, const float* __restrict__ gt, int n,
-                          float* __restrict__ vz, float* __restrict__ vg, int* __restrict__ counters,
+                          float* __restrict__ vz, int* __restrict__ counters,
                           const unsigned int* __restrict__ bracket, unsigned int* __restrict__ cand,
                           int H, int W, int gt_h, int gt_w) {
     __shared__ unsigned int scand[2][kCtaCand];
@@ -297,8 +297,8 @@ depth_extract_fast_kernel(const float* __restrict__ pred, const float* __restric
     const float* __restrict__ gimg = gt + (size_t)b * gt_h * gt_w;
     const float4* __restrict__ g4 = reinterpret_cast<const float4*>(gimg);
     const float4* __restrict__ p4 = reinterpret_cast<const float4*>(pred + (size_t)b * n * PSTRIDE);
-    float4* __restrict__ oz4 = reinterpret_cast<float4*>(vz + (size_t)b * n);
-    float4* __restrict__ og4 = reinterpret_cast<float4*>(vg + (size_t)b * n);
+    float* __restrict__ oz = vz + (size_t)b * n;
+    const uint64_t keep = l2_policy_evict_last();
     const uint4 br = __ldg(reinterpret_cast<const uint4*>(bracket) + b);
     const unsigned int lo_g = br.x, w_g = br.y - br.x, lo_p = br.z, w_p = br.w - br.z;       // lo > hi (no bracket): w wraps,
     const bool has_g = br.y >= br.x, has_p = br.w >= br.z;                                    // masked by has_*
@@ -325,7 +325,6 @@ depth_extract_fast_kernel(const float* __restrict__ pred, const float* __restric
             z = __ldg(p4 + q);
         }
         const float gv[4] = {g.x, g.y, g.z, g.w}, pv[4] = {z.x, z.y, z.z, z.w};
-        float og[4];
         unsigned int kgs[4], kps[4], fg = 0, fp = 0;
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
@@ -333,7 +332,6 @@ depth_extract_fast_kernel(const float* __restrict__ pred, const float* __restric
             const bool ok = (gb - 1u) < 0x7f7fffffu;                     // gt > 0 & finite (utils/metrics.py:27)
             const bool pn = pv[u] != pv[u];
             const bool okp = ok && !pn;
-            og[u] = ok ? gv[u] : __int_as_float(0x7fc00000);
             kgs[u] = gb | 0x80000000u;                                   // key of a positive float
             kps[u] = key_of_bits(pb);
             nv += ok; pnan += (ok && pn);
@@ -341,8 +339,7 @@ depth_extract_fast_kernel(const float* __restrict__ pred, const float* __restric
             fg |= (unsigned)(ok && has_g && (kgs[u] - lo_g) <= w_g) << u;
             fp |= (unsigned)(okp && has_p && (kps[u] - lo_p) <= w_p) << u;
         }
-        oz4[q] = z;
-        og4[q] = make_float4(og[0], og[1], og[2], og[3]);
+        if (PSTRIDE == 3) stg_f4_l2hint(oz + 4 * (size_t)q, z, keep);      // planar: the caller's array IS the Z plane
         if (fg) {                       // one shared-memory atomic per thread with candidates
             int slot = atomicAdd(&scount[0], __popc(fg));
 #pragma unroll
@@ -390,7 +387,7 @@ constexpr int kMedThreads = t3d_select::kThreads;
 __global__ void __launch_bounds__(kMedThreads, 1)
 median_scale_kernel(const float* __restrict__ vz, const float* __restrict__ vg, const int* __restrict__ counters,
                     const unsigned int* __restrict__ cand, const unsigned int* __restrict__ bracket, int n,
-                    int median_scaling, float* __restrict__ medians) {
+                    int median_scaling, float* __restrict__ medians, const PixelSrc src, int pred_offset) {
     extern __shared__ unsigned int skeys[];                       // kCandCap keys
     __shared__ t3d_select::Smem sm;
     const int a = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
@@ -431,11 +428,24 @@ median_scale_kernel(const float* __restrict__ vz, const float* __restrict__ vg, 
                     x1 = (le > r1 - lt) ? x0 : t3d_select::key_float(nxt + lo);
                 }
             } else {                                              // fallback: full radix select, same result
-                const float* v = (a == 0 ? vg : vz) + (size_t)b * n;
-                const float* gm = vg + (size_t)b * n;
-                auto get = [&](int i, float* o) { *o = v[i]; return !isnan(gm[i]); };
-                x0 = t3d_select::select_rank(sm, n, r0, get);
-                x1 = (r1 == r0) ? x0 : t3d_select::select_rank(sm, n, r1, get);
+                if (vg) {                                         // general path: planar copies, NaN marks an unselected pixel
+                    const float* v = (a == 0 ? vg : vz) + (size_t)b * n;
+                    const float* gm = vg + (size_t)b * n;
+                    auto get = [&](int i, float* o) { *o = v[i]; return !isnan(gm[i]); };
+                    x0 = t3d_select::select_rank(sm, n, r0, get);
+                    x1 = (r1 == r0) ? x0 : t3d_select::select_rank(sm, n, r1, get);
+                } else {                                          // fast path: straight from the caller's arrays
+                    const float* g = src.gt + (size_t)b * src.gt_h * src.gt_w;
+                    const float* p = src.pred + (size_t)b * n * src.pred_stride + pred_offset;
+                    auto get = [&](int i, float* o) {
+                        float gv, pv; bool ok;
+                        read_pixel(src, g, p, nullptr, i, gv, pv, ok);
+                        *o = (a == 0) ? gv : pv;
+                        return ok;
+                    };
+                    x0 = t3d_select::select_rank(sm, n, r0, get);
+                    x1 = (r1 == r0) ? x0 : t3d_select::select_rank(sm, n, r1, get);
+                }
             }
             med = (r1 == r0) ? x0 : __fmul_rn(__fadd_rn(x0, x1), 0.5f);   // np.median: fp32 mean of the middles
         }
@@ -513,6 +523,98 @@ metrics_sum_kernel(const float* __restrict__ vz, const float* __restrict__ vg,
 #pragma unroll
         for (int w = 0; w < kChunkThreads / 32; ++w) t += red[w][threadIdx.x];
         partials[((size_t)b * chunks + chunk) * kNPart + threadIdx.x] = t;
+    }
+}
+
+// Fast form of the sum pass (pairs with depth_extract_fast_kernel): GT straight from the caller's array (nearest-
+// resampled through the same index tables), validity re-derived from it, Z from the planar copy the extraction pass
+// left in the L2 (or the caller's planar prediction).  Same arithmetic and summation order as metrics_sum_kernel<false>.
+template <bool RESAMPLE>
+__global__ void __launch_bounds__(kChunkThreads, 4)
+metrics_sum_fast_kernel(const float* __restrict__ zplane, const float* __restrict__ gt,
+                        const float* __restrict__ medians, const int* __restrict__ counters, int median_scaling,
+                        int n, int chunks, double* __restrict__ partials, int H, int W, int gt_h, int gt_w) {
+    __shared__ double red[kChunkThreads / 32][kNPart];
+    __shared__ int stab[RESAMPLE ? kResampleMaxDim : 1];
+    const int b = blockIdx.y, chunk = blockIdx.x, tid = threadIdx.x;
+    if (RESAMPLE) {
+        const double fx = (double)gt_w / (double)W, fy = (double)gt_h / (double)H;
+        for (int i = tid; i < W + H; i += kChunkThreads) {
+            if (i < W) stab[i] = min((int)floor(__dmul_rn((double)i, fx)), gt_w - 1);
+            else stab[i] = min((int)floor(__dmul_rn((double)(i - W), fy)), gt_h - 1) * gt_w;
+        }
+        __syncthreads();
+    }
+    // scale = median(gt) / median(pred)  (utils/metrics.py:47)
+    const float s = (median_scaling && counters[8 * b] > 0) ? __fdiv_rn(medians[2 * b], medians[2 * b + 1]) : 1.0f;
+    const float* gimg = gt + (size_t)b * gt_h * gt_w;
+    const float* z = zplane + (size_t)b * n;
+    const uint64_t keep = l2_policy_evict_last();
+    const float qnan = __int_as_float(0x7fc00000);
+    auto load_g = [&](int q) {
+        if (RESAMPLE) {                                   // W % 4 == 0: the quad lies in one row
+            const int y = (4 * q) / W, x = 4 * q - y * W;
+            const float* row = gimg + stab[W + y];
+            return make_float4(__ldg(row + stab[x]), __ldg(row + stab[x + 1]), __ldg(row + stab[x + 2]), __ldg(row + stab[x + 3]));
+        }
+        return ldg_stream_f4(gimg + 4 * (size_t)q);
+    };
+    double acc[4] = {0, 0, 0, 0};
+    int cnt[3] = {0, 0, 0};
+    const int n4 = n >> 2, per = (n4 + chunks - 1) / chunks;
+    const int q0 = chunk * per, q1 = min(q0 + per, n4);
+    for (int q = q0 + tid; q < q1; q += 2 * kChunkThreads) {
+        const int q2 = q + kChunkThreads;
+        const bool two = q2 < q1;
+        const float4 ga = load_g(q);
+        const float4 za = ldg_f4_l2hint(z + 4 * (size_t)q, keep);
+        float4 gb = make_float4(qnan, qnan, qnan, qnan), zb = gb;
+        if (two) { gb = load_g(q2); zb = ldg_f4_l2hint(z + 4 * (size_t)q2, keep); }
+        float gtv[8] = {ga.x, ga.y, ga.z, ga.w, gb.x, gb.y, gb.z, gb.w};
+        const float za8[8] = {za.x, za.y, za.z, za.w, zb.x, zb.y, zb.z, zb.w};
+        float pr[8];
+        bool ok[8];
+        bool all_normal = true;        // every selected pixel: gt and scaled prediction positive, normal, finite
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            pr[e] = __fmul_rn(za8[e], s);                                            // pred *= scale   (:48)
+            const unsigned int gbits = __float_as_uint(gtv[e]), pbits = __float_as_uint(pr[e]);
+            ok[e] = (gbits - 1u) < 0x7f7fffffu;                                      // gt > 0 & finite (:27)
+            const bool normal = ((gbits - 0x00800000u) < 0x7f000000u) && ((pbits - 0x00800000u) < 0x7f000000u);
+            all_normal = all_normal && (normal || !ok[e]);
+        }
+        float accf[4] = {0.f, 0.f, 0.f, 0.f};
+        if (all_normal) {
+            float accl2 = 0.f;
+            int unselected = 0;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                metric_terms_nodiv(ok[e] ? gtv[e] : 1.0f, ok[e] ? pr[e] : 1.0f, accf, accl2, cnt);
+                unselected += ok[e] ? 0 : 1;
+            }
+            cnt[0] -= unselected; cnt[1] -= unselected; cnt[2] -= unselected;        // g = q = 1 counted as "inside"
+            accf[3] = accl2 * 0.48045301391820144f;                                  // ln(2)^2
+        } else {                                                                     // zero / negative / NaN / Inf / subnormal: literal formulas
+#pragma unroll 1
+            for (int e = 0; e < 8; ++e) metric_terms<false>(ok[e] ? gtv[e] : qnan, za8[e], s, accf, cnt);
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) acc[k] += (double)accf[k];
+    }
+    double v[kNPart] = {acc[0], acc[1], acc[2], acc[3], (double)cnt[0], (double)cnt[1], (double)cnt[2], 0.0};
+#pragma unroll
+    for (int k = 0; k < kNPart - 1; ++k) v[k] = warp_sum(v[k]);
+    const int lane = tid & 31, wrp = tid >> 5;
+    if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < kNPart; ++k) red[wrp][k] = v[k];
+    }
+    __syncthreads();
+    if (tid < kNPart) {
+        double t = 0;
+#pragma unroll
+        for (int w = 0; w < kChunkThreads / 32; ++w) t += red[w][tid];
+        partials[((size_t)b * chunks + chunk) * kNPart + tid] = t;
     }
 }
 
@@ -690,16 +792,8 @@ int t3d_depth_metrics(const float* pred, int pred_stride, int pred_offset,
                         (!src.resample || H + W <= kResampleMaxDim) && (src.resample || (gt_h * gt_w) % 4 == 0) &&
                         ((pred_stride == 3 && pred_offset == 2) || (pred_stride == 1 && pred_offset == 0));
     float* medians_out = out_medians ? out_medians : w.scale;       // [B][2]: median(gt), median(pred)
-    static const bool use_fused = [] { const char* e = getenv("T3D_METRIC_FUSED"); return e ? atoi(e) != 0 : true; }();
-    if (fast_x && use_fused) {
-        // one persistent kernel: the pointmap is read from DRAM once, the second pass of an image follows its first
-        // a few images later and hits the L2 (t3d_metrics_fused.cu)
-        if (!median_scaling) T3D_CUDA(cudaMemsetAsync(medians_out, 0, (size_t)B * 2 * sizeof(float), st));
-        return launch_fused(pred, pred_stride, gt, gt_h, gt_w, B, H, W, median_scaling, w.bracket, medians_out, w.partials,
-                            chunks, out, out_f64, w.fused, st);
-    }
 #define T3D_XFAST(PS_, RS_) T3D_LAUNCH("depth_extract_kernel", st, (depth_extract_fast_kernel<PS_, RS_><<<g, kChunkThreads, 0, st>>>( \
-            pred, gt, n, w.vz, w.vg, w.counters, w.bracket, w.cand, H, W, gt_h, gt_w)))
+            pred, gt, n, w.vz, w.counters, w.bracket, w.cand, H, W, gt_h, gt_w)))
     if (fast_x && pred_stride == 3) { if (src.resample) T3D_XFAST(3, true); else T3D_XFAST(3, false); }
     else if (fast_x) { if (src.resample) T3D_XFAST(1, true); else T3D_XFAST(1, false); }
 #undef T3D_XFAST
@@ -711,8 +805,16 @@ int t3d_depth_metrics(const float* pred, int pred_stride, int pred_offset,
             src, pred_offset, w.vz, w.vg, w.counters, w.bracket, w.cand));
     float* medians = medians_out;
     T3D_LAUNCH("median_scale_kernel", st, median_scale_kernel<<<dim3(2, B), kMedThreads, kCandCap * sizeof(unsigned int), st>>>(
-        w.vz, w.vg, w.counters, w.cand, w.bracket, n, median_scaling, medians));
-    if (mask)       // a caller-supplied mask may select non-positive / non-finite GT: literal formulas
+        w.vz, fast_x ? nullptr : w.vg, w.counters, w.cand, w.bracket, n, median_scaling, medians, src, pred_offset));
+    if (fast_x) {
+        const float* zplane = (pred_stride == 3) ? w.vz : pred;       // a planar prediction is its own Z plane
+        if (src.resample)
+            T3D_LAUNCH("metrics_sum_kernel", st, metrics_sum_fast_kernel<true><<<g, kChunkThreads, 0, st>>>(
+                zplane, gt, medians, w.counters, median_scaling, n, chunks, w.partials, H, W, gt_h, gt_w));
+        else
+            T3D_LAUNCH("metrics_sum_kernel", st, metrics_sum_fast_kernel<false><<<g, kChunkThreads, 0, st>>>(
+                zplane, gt, medians, w.counters, median_scaling, n, chunks, w.partials, H, W, gt_h, gt_w));
+    } else if (mask)       // a caller-supplied mask may select non-positive / non-finite GT: literal formulas
         T3D_LAUNCH("metrics_sum_kernel", st, metrics_sum_kernel<true><<<g, kChunkThreads, 0, st>>>(
             w.vz, w.vg, medians, w.counters, median_scaling, n, chunks, w.partials));
     else

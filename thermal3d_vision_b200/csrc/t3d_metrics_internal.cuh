@@ -1,5 +1,4 @@
-// t3d_metrics_internal.cuh -- shared between t3d_metrics.cu (entry points, general multi-kernel chain) and
-// t3d_metrics_fused.cu (the one-kernel fast path): the per-pixel arithmetic of utils/metrics.py:48-59.
+// t3d_metrics_internal.cuh -- the per-pixel arithmetic of utils/metrics.py:48-59 (used by t3d_metrics.cu).
 #pragma once
 #include "t3d_common.cuh"
 #include "t3d_select.cuh"
@@ -8,7 +7,6 @@ namespace t3d_metrics {
 
 constexpr int kNPart = 8;                  // abs_rel, sq_rel, sq, log2, a1, a2, a3, (pad)
 constexpr int kResampleMaxDim = 2048;      // H + W limit of the in-kernel nearest-neighbour index tables (8 KB)
-constexpr int kBucketCap = 8192;           // fused path: candidates per (image, stream, bucket)
 
 __device__ __forceinline__ unsigned int key_of_bits(unsigned int b) { return b ^ ((unsigned int)((int)b >> 31) | 0x80000000u); }
 
@@ -60,11 +58,35 @@ __device__ __forceinline__ void metric_terms_fast(float gt, float pr, float accf
     accf[3] = fmaf(dl, dl, accf[3]);                                         // :59
 }
 
+// Division-free form of the same terms for g, q positive NORMAL finite numbers (valid pixels; invalid ones are
+// passed as g = q = 1).  numpy: thresh = max(gt/pred, pred/gt) = fl(a / b), a = max, b = min
+// (IEEE division is monotone), counted against T in {1.25, 1.5625, 1.953125} (:51-54).  For such T (in (1, 2), even
+// mantissa) fl(a / b) < T  <=>  a / b < T - 2^-24 (the midpoint below T; a tie rounds to even = T)
+// <=>  a - T b + 2^-24 b < 0, and that sign is computed EXACTLY by two FMAs: r = fma(-T, b, a) is exact whenever
+// |a - T b| < b / 64 (a and T b are multiples of ulp(b) / 64) and otherwise so much larger than 2^-24 b that its
+// rounding cannot change the sign of the sum; fma(2^-24, b, r) rounds once, which never flips a sign.
+// -> the delta-counts are those of the correctly rounded quotient, without dividing.
+// log: u = q / g to ~1 ulp (reciprocal + one Newton step), |log gt - log pred| = ln2 |lg2 u|; the caller folds
+// ln2^2 into the sum of lg2(u)^2 (accl2).
+__device__ __forceinline__ float rcp_fast(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 
-// fused fast path (t3d_metrics_fused.cu)
-size_t fused_ws_bytes(int B, int chunks);
-int launch_fused(const float* pred, int pred_stride, const float* gt, int gt_h, int gt_w, int B, int H, int W,
-                 int median_scaling, const unsigned int* bracket, float* medians, double* partials, int chunks,
-                 float* out, double* out_f64, void* ws, cudaStream_t st);
+// An unselected pixel (g = q = 1) adds 0 to every sum and 1 to every count: the caller subtracts their number.
+__device__ __forceinline__ void metric_terms_nodiv(float g, float q, float accf[3], float& accl2, int cnt[3]) {
+    const float a = fmaxf(g, q), b = fminf(g, q);
+    const float c = 5.9604644775390625e-08f;                                 // 2^-24
+    cnt[0] += (fmaf(c, b, fmaf(-1.25f, b, a)) < 0.f) ? 1 : 0;                // :52
+    cnt[1] += (fmaf(c, b, fmaf(-1.5625f, b, a)) < 0.f) ? 1 : 0;              // :53
+    cnt[2] += (fmaf(c, b, fmaf(-1.953125f, b, a)) < 0.f) ? 1 : 0;            // :54
+    const float rg = rcp_fast(g);
+    float u = q * rg;
+    u = fmaf(fmaf(-u, g, q), rg, u);                                         // Newton: u = q / g to ~1 ulp
+    const float l2 = lg2_fast(u);
+    accl2 = fmaf(l2, l2, accl2);                                             // :59 (in log2 units)
+    const float d = g - q;
+    const float d2 = d * d;
+    accf[0] = fmaf(fabsf(d), rg, accf[0]);                                   // :56  |gt - pred| / gt
+    accf[1] = fmaf(d2, rg, accf[1]);                                         // :57
+    accf[2] += d2;                                                           // :58
+}
 
 }  // namespace t3d_metrics

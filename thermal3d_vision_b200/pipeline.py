@@ -79,18 +79,27 @@ class HotPathStep:
             "metrics": torch.empty(B, 8, **f32), "metrics_f64": torch.empty(B, 8, dtype=torch.float64, device=dev),
             "medians": torch.empty(B, 2, **f32),
         } for _ in range(2)]
+        # scratch that lives inside one chain is shared by the two sets: the chains of consecutive steps run in order
+        # on their own stream, only what the loss / the epilogue consume later exists twice.  (One metric workspace
+        # also means ONE planar-Z scratch: the extraction pass parks it in the L2 for the sum pass, t3d_metrics.cu.)
+        self.met_sets[1]["workspace"] = self.met_sets[0]["workspace"]
+        self.pre_sets[1]["workspace"] = self.pre_sets[0]["workspace"]
         self.loss_out, self.pre_both, self.met_out = self.loss_sets[0], self.pre_sets[0], self.met_sets[0]
         # preprocessing first in line for free SMs (the loss waits for it), the metric chain last (it has a whole
         # step of slack: only the epilogue needs it)
-        self.s_pre = torch.cuda.Stream(device=dev, priority=-1)
-        self.s_loss = torch.cuda.Stream(device=dev, priority=-1)
-        self.s_met = torch.cuda.Stream(device=dev, priority=0)
+        try:
+            lo_pri, hi_pri = torch.cuda.Stream.priority_range()      # (least, greatest), e.g. (0, -5)
+        except Exception:
+            lo_pri, hi_pri = 0, -1
+        # the persistent loss kernel first (its CTAs must not queue behind the next step's preprocessing CTAs)
+        self.s_loss = torch.cuda.Stream(device=dev, priority=hi_pri)
+        self.s_pre = torch.cuda.Stream(device=dev, priority=min(hi_pri + 1, lo_pri))
+        self.s_met = torch.cuda.Stream(device=dev, priority=lo_pri)
         self.ev_ready = [torch.cuda.Event() for _ in range(2)]
         self.ev_pre = [torch.cuda.Event() for _ in range(2)]
         self.ev_met = [torch.cuda.Event() for _ in range(2)]
         self.ev_done = [torch.cuda.Event() for _ in range(2)]
         self._joined = [True, True]          # the caller's stream has been ordered after the step that last used set i
-        self._shared_hint = None
         # percentiles from sampled value windows (bit-identical to the exact-histogram path, no per-pixel atomic);
         # set True to also get the 65 536-bin histograms of the resized frames in pre_both["histogram"]
         self.histogram = False
@@ -194,9 +203,7 @@ class HotPathStep:
         stacked = (raw1.is_contiguous() and raw2.is_contiguous() and raw1.shape == raw2.shape and
                    raw1.untyped_storage().data_ptr() == raw2.untyped_storage().data_ptr() and
                    raw2.storage_offset() == raw1.storage_offset() + raw1.numel())      # halves of one tensor
-        if self._shared_hint is None:               # the metric chain shares the SMs with the preprocessing
-            self._shared_hint = True
-            lib.t3d_preprocess_set_shared(1)
+        lib.t3d_preprocess_set_shared(1)            # the metric chain runs beside the preprocessing
         if self.histogram and "histogram" not in pre:
             pre["histogram"] = torch.empty(2 * B, 65536, dtype=torch.int32, device=self.device)
 
