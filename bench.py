@@ -337,7 +337,7 @@ def extra_multi_scale(a, dev, d, peak):
     from thermal3d_vision_b200.pipeline import HotPathStep
     B, H, W = a.batch, a.height, a.width
     step = HotPathStep(B, H, W, device=dev, multi_scale=True, alpha=ALPHA, edge_weight=EDGE_W, smoothness_weight=SMOOTH_W,
-                       detail_weight=DETAIL_W, pipelined=True)
+                       detail_weight=DETAIL_W)
     args = [d[k] for k in KEYS]
     ms = time_steps(lambda: step.run_device(*args), 20, 3, step.finish)
     _lib.profile_begin("loss_", 256)
@@ -383,12 +383,11 @@ def extra_cfg2(a, dev, peak):
     ms_warm = time_steps(replay, 200, 5)
     ab = sum(step.algorithmic_bytes().values())
     s = HotPathStep.summarize(replay().cpu())
-    eager = HotPathStep(B, H, W, device=dev, alpha=ALPHA, edge_weight=EDGE_W, smoothness_weight=SMOOTH_W, detail_weight=DETAIL_W,
-                        pipelined=True)
+    eager = HotPathStep(B, H, W, device=dev, alpha=ALPHA, edge_weight=EDGE_W, smoothness_weight=SMOOTH_W, detail_weight=DETAIL_W)
     ms_eager = time_steps(lambda: eager.run_device(*[d[k] for k in KEYS]), 200, 5, eager.finish)
     out = {"workload": "batch8_224x224_pairs_loss_fwd_bwd+preproc_640x512_u16+depth_metrics (BASELINE configs[1], CUDA-graph replay)",
            "ms_per_step": ms_cold, "pairs_per_s": B / (ms_cold * 1e-3), "ms_per_step_l2_warm": ms_warm,
-           "ms_per_step_stream_launches_pipelined": ms_eager,
+           "ms_per_step_stream_launches": ms_eager,
            "l2_policy": "flushed between replays (256 MB fill), median of 30; l2_warm = 200 back-to-back replays",
            "roofline": {"bound": "hbm", "achieved": ab / (ms_cold * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                         "frac": ab / (ms_cold * 1e-3) / 1e9 / peak, "step_algorithmic_bytes": ab,
@@ -423,10 +422,12 @@ def run_b200(a):
     _lib.lib()
 
     B, H, W = a.batch, a.height, a.width
-    # pipelined: consecutive steps overlap on the step's internal streams (every step does all of its own work on
-    # its own output set); the timed region ends with finish(), i.e. after the last step's last kernel
+    # plain stream semantics: every step completes on the caller's stream before the next one is enqueued behind it
+    # (T3D_PIPELINED=1: consecutive steps overlap on the step's internal streams -- measured no faster);
+    # the timed region ends with finish(), i.e. after the last step's last kernel and exchange
+    pipelined = os.environ.get("T3D_PIPELINED", "0") not in ("", "0")
     step = HotPathStep(B, H, W, device=dev, multi_scale=bool(a.multi_scale), alpha=ALPHA, edge_weight=EDGE_W,
-                       smoothness_weight=SMOOTH_W, detail_weight=DETAIL_W, distributed=world > 1, pipelined=True)
+                       smoothness_weight=SMOOTH_W, detail_weight=DETAIL_W, distributed=world > 1, pipelined=pipelined)
     d = make_inputs_torch(B, H, W, seed=rank, device=dev)
     args = tuple(d[k] for k in KEYS)
     host = {k: v.cpu().pin_memory() for k, v in d.items()}
@@ -473,6 +474,7 @@ def run_b200(a):
     ms_dev = max_over_ranks(e0.elapsed_time(e1))
     clocks = sampler.stop() if rank == 0 else None
     result_vec = step.wait_result().clone()
+    step_result_size = result_vec.numel()
     summary = HotPathStep.summarize(result_vec.cpu())
 
     # ---------------- data parallel: the exchanged vector against an independent all-gather of the local vectors
@@ -519,8 +521,8 @@ def run_b200(a):
         except Exception:
             pass
         cfg = config_dict(a, world, step.exchange)
-        cfg["step_overlap"] = ("pipelined: the preprocessing / metric kernels of step i+1 run while the tail of step i drains "
-                               "(internal streams, two alternating output sets); every step does all of its own work")
+        cfg["step_overlap"] = ("pipelined across steps (internal streams, two alternating output sets)" if pipelined else
+                               "none across steps; inside a step the preprocessing and metric chains run on two streams beside each other")
         out = {
             "metric": METRIC, "value": world * B * a.steps / (ms_dev * 1e-3), "unit": UNIT, "n_gpus": world,
             "steps": a.steps, "warmup": max(a.warmup, 3), "ms_per_step": ms_dev / a.steps,
@@ -540,7 +542,7 @@ def run_b200(a):
                          "step_algorithmic_bytes": step_bytes,
                          "step_frac_of_peak": step_bytes / (ms_dev / a.steps * 1e-3) / 1e9 / peak},
             "e2e": {"value": world * B * a.steps / (ms_e2e * 1e-3), "unit": UNIT,
-                    "h2d_bytes_per_step": HotPathStep.h2d_bytes(host), "d2h_bytes_per_step": 16 * 8,
+                    "h2d_bytes_per_step": HotPathStep.h2d_bytes(host), "d2h_bytes_per_step": 8 * int(step_result_size),
                     "ms_per_step": ms_e2e / a.steps,
                     "h2d_gbs_aggregate": world * HotPathStep.h2d_bytes(host) / (ms_e2e / a.steps * 1e-3) / 1e9},
             "gpu_launches": int(launches),

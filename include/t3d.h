@@ -300,31 +300,37 @@ int t3d_sobel_enhance_bwd_params(const float* x, const float* params, const floa
                                  int local_norm, float* dparams, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------ step result packing */
-/* out16 (float64[16]) = [0] sum over VALID samples of the per-sample loss, [1..4] sums
- * of basic/edge/smoothness/detail, [5] n_valid, [6] B (train_thermal_dustr.py:320,359);
- * [7..13] sums of the FINITE per-image metrics abs_rel..acc_3, [14] n_images
- * (utils/metrics.py:128-136); [15] 0.  Either input may be NULL.  This is the one
- * vector a data-parallel job all-reduces per step. */
+/* The packed step vector: T3D_RESULT_SIZE doubles.
+ *   [0] sum over VALID samples of the per-sample loss, [1..4] sums of basic/edge/smoothness/detail,
+ *   [5] n_valid, [6] B (train_thermal_dustr.py:320,359);
+ *   [7..13] sums of the FINITE per-image metrics abs_rel..acc_3, [14] n_images (utils/metrics.py:128-136); [15] 0;
+ *   [16..23] parameter gradients riding along (data-parallel training sums parameter gradients over the ranks --
+ *   DDP's gradient all-reduce; on this path the only parameters are ThermalDUSt3R's two scalars edge_weight and
+ *   temp_scale, thermal_dustr_model.py:104-107: slots 16, 17), else 0.
+ * This is the one vector a data-parallel job sums over its ranks per step.
+ * t3d_pack_step_result: either input may be NULL; slots 15.. are 0. */
+#define T3D_RESULT_SIZE 24
 int t3d_pack_step_result(const float* loss_per_sample, const double* metrics_f64, int B, int n_images,
-                         double* out16, void* stream);
+                         double* out_vec, void* stream);
 /* t3d_loss_rescale_invalid + t3d_pack_step_result as ONE launch (the tail of a training step,
- * train_thermal_dustr.py:320,359-360): out16 as above; when some samples are invalid their
+ * train_thermal_dustr.py:320,359-360): out_vec as above; when some samples are invalid their
  * gradients are zeroed and the others rescaled by B / n_valid (dconf may be NULL).
  * defer_rescale != 0 (data parallel, the batch spans several ranks): only the zeroing happens here; after the
  * vector has been summed over the ranks, t3d_rescale_global multiplies this rank's gradients by
- * out16_global[6] / out16_global[5] = (samples / valid samples) of the GLOBAL batch (a no-op kernel when equal). */
+ * out_vec_global[6] / out_vec_global[5] = (samples / valid samples) of the GLOBAL batch (a no-op kernel when equal). */
 int t3d_step_epilogue(float* dpred1, float* dpred2, float* dconf1, float* dconf2,
                       const float* loss_per_sample, const float* loss_batch, const double* metrics_f64,
-                      int B, int H, int W, int n_images, int defer_rescale, double* out16, void* stream);
+                      int B, int H, int W, int n_images, int defer_rescale,
+                      const float* param_grads, int n_param_grads, double* out_vec, void* stream);
 int t3d_rescale_global(float* dpred1, float* dpred2, float* dconf1, float* dconf2, const float* loss_per_sample,
-                       const double* out16_global, int B, int H, int W, void* stream);
+                       const double* out_vec_global, int B, int H, int W, void* stream);
 /* Data-parallel variant over peer memory (one process per GPU, one NVLink / NVSwitch node; replaces the per-step
- * NCCL all-reduce of out16 -- SURVEY.md 8e): every rank owns a mailbox of t3d_mailbox_bytes() zero-initialised bytes
+ * NCCL all-reduce of the packed vector -- SURVEY.md 8e): every rank owns a mailbox of t3d_mailbox_bytes() zero-initialised bytes
  * that its peers can address (CUDA IPC / symmetric memory); peer_mailboxes = HOST array of the `world` device
  * addresses under which THIS process sees them, in rank order.  t3d_step_epilogue_peers does what
- * t3d_step_epilogue does and also stores the rank's 16 doubles into every rank's mailbox (step = 0, 1, 2, ...);
+ * t3d_step_epilogue does and also stores the rank's vector into every rank's mailbox (step = 0, 1, 2, ...);
  * t3d_mailbox_reduce waits (on the device) for the world's vectors of `step` and adds them in rank order into
- * out16.  Per rank, reduce(step) must be enqueued before epilogue(step + 1) -- that is what makes the two
+ * out_vec.  Per rank, reduce(step) must be enqueued before epilogue(step + 1) -- that is what makes the two
  * alternating slots safe to reuse.
  * Validity across ranks (train_thermal_dustr.py:320,357-360 over the GLOBAL batch): the gradients carry the a-priori
  * scale 1 / (B * world); t3d_step_epilogue_peers zeroes the gradients of this rank's invalid samples, and
@@ -335,10 +341,11 @@ int t3d_rescale_global(float* dpred1, float* dpred2, float* dconf1, float* dconf
 size_t t3d_mailbox_bytes(void);
 int t3d_step_epilogue_peers(float* dpred1, float* dpred2, float* dconf1, float* dconf2,
                             const float* loss_per_sample, const float* loss_batch, const double* metrics_f64,
-                            int B, int H, int W, int n_images, double* out16_local,
+                            int B, int H, int W, int n_images,
+                            const float* param_grads, int n_param_grads, double* out_vec_local,
                             const unsigned long long* peer_mailboxes, int world, int rank,
                             unsigned long long step, void* stream);
-int t3d_mailbox_reduce(const void* my_mailbox, int world, unsigned long long step, double* out16,
+int t3d_mailbox_reduce(const void* my_mailbox, int world, unsigned long long step, double* out_vec,
                        float* dpred1, float* dpred2, float* dconf1, float* dconf2,
                        const float* loss_per_sample, int B, int H, int W, void* stream);
 

@@ -176,6 +176,19 @@ def gen_sobel(ref):
                         small_dts=m.temp_scale.grad.numpy(), versions=versions(ref))
 
 
+def gen_evaluate(ref):
+    """evaluate_thermal_depth (utils/metrics.py:72-138) on the fake model / loader of oracle/fake_eval.py."""
+    from oracle import fake_eval
+    out = {"versions": versions(ref)}
+    for conv in fake_eval.CONVENTIONS:
+        model = fake_eval.FakeModel(conv)
+        res = ref.metrics.evaluate_thermal_depth(model, fake_eval.make_loader(seed=7), torch.device("cpu"))
+        out[conv] = fake_eval.as_vector(res)
+        out[conv + "_calls"] = np.array(model.calls)
+        assert not model.training
+    np.savez_compressed(os.path.join(OUT, "evaluate_kat.npz"), **out)
+
+
 def main():
     ref = reference_bridge.load()
     os.makedirs(OUT, exist_ok=True)
@@ -183,6 +196,7 @@ def main():
     gen_preprocess(ref)
     gen_metrics(ref)
     gen_sobel(ref)
+    gen_evaluate(ref)
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 

@@ -17,7 +17,8 @@ KW = dict(alpha=0.2, edge_weight=0.5, smoothness_weight=0.3, detail_weight=0.4, 
 
 def _pack(rows, valid, metrics):
     """Host mirror of the device packing (test helper, same layout as t3d_pack_step_result)."""
-    v = np.zeros(16)
+    from thermal3d_vision_b200.distributed import RESULT_SIZE
+    v = np.zeros(RESULT_SIZE)
     for r, ok in zip(rows, valid):
         if ok:
             v[0:5] += r[0:5]; v[5] += 1

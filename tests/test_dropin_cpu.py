@@ -55,6 +55,8 @@ def test_shim_resolution():
             "print(utils.loss.enhanced_thermal_aware_loss.__module__);"
             "print(utils.preprocessing.enhance_thermal_contrast.__module__);"
             "print(utils.metrics.compute_depth_metrics.__module__)")
+    code += (";import thermal_dustr_model as m; print(m.ThermalDUSt3R.__module__); print(m.load_dustr_model.__module__);"
+             "import inspect; print(inspect.signature(m.load_dustr_model))")
     if os.path.isdir(REF):
         code += ";import utils.data_utils; print(utils.data_utils.__file__)"
     out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=120)
@@ -62,5 +64,9 @@ def test_shim_resolution():
     lines = out.stdout.strip().splitlines()
     assert lines[0] == "thermal3d_vision_b200.loss" and lines[1] == "thermal3d_vision_b200.preprocessing"
     assert lines[2] == "thermal3d_vision_b200.metrics"
+    # thermal_dustr_inference.py:21,95-96: ThermalDUSt3R is ours, load_dustr_model stays the reference's own function
+    assert lines[3] == "thermal3d_vision_b200.sobel"
+    assert lines[5] == "(weights_path, device=None, is_thermal=False)"
     if os.path.isdir(REF):
-        assert lines[3].startswith(REF)
+        assert lines[4] == "_t3d_reference_thermal_dustr_model"
+        assert lines[6].startswith(REF)

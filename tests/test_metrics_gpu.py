@@ -235,3 +235,23 @@ def test_eval_step_config5_shape(cuda_device):
     ref = ref_metrics.accumulate_dataset(per)
     for k7 in K7:
         assert got[k7] == pytest.approx(ref[k7], rel=1e-5), k7
+
+
+@pytest.mark.parametrize("conv", ["tuple_dict_batched", "dict_pred1", "tuple_tensor"])
+def test_evaluate_thermal_depth_matches_reference_run(cuda_device, conv):
+    """evaluate_thermal_depth(model, dataloader, device) (utils/metrics.py:72-138) with a fake model and loader
+    (oracle/fake_eval.py) against what the LIVE reference function returned for the same model and data in the build
+    container (tests/golden/evaluate_kat.npz, written by oracle/gen_golden.py): every output convention of the
+    model the loop accepts, batches without depth skipped, a sample with non-finite metrics skipped but counted."""
+    from oracle import fake_eval
+    from thermal3d_vision_b200 import metrics as tm
+    gold = np.load(os.path.join(G, "evaluate_kat.npz"))
+    model = fake_eval.FakeModel(conv).to(cuda_device)
+    model.train()
+    got = tm.evaluate_thermal_depth(model, fake_eval.make_loader(seed=7), cuda_device)
+    assert not model.training and model.calls == int(gold[conv + "_calls"])
+    assert list(got) == list(fake_eval.KEYS)
+    np.testing.assert_allclose(fake_eval.as_vector(got), gold[conv], rtol=1e-5)
+    # nothing to evaluate -> NaNs (sample_count == 0, :134-135)
+    empty = tm.evaluate_thermal_depth(model, [{"thermal1": torch.rand(1, 3, 8, 8)}], cuda_device)
+    assert all(np.isnan(v) for v in empty.values())

@@ -64,3 +64,27 @@ def test_sobel_equals_live_reference(ref):
     m = ref.model.ThermalDUSt3R(torch.nn.Identity())
     x = torch.rand(1, 1, 31, 45)
     assert torch.equal(m.preprocess_thermal(x), ref_sobel.preprocess_thermal_torch(x, m.edge_weight, m.temp_scale))
+
+
+def test_evaluate_golden_is_the_live_reference(ref):
+    """tests/golden/evaluate_kat.npz (what the GPU test of evaluate_thermal_depth compares with) is what the live
+    reference function returns for the fake model / loader of oracle/fake_eval.py, and equals the oracle's
+    accumulate_dataset over per-sample oracle metrics."""
+    import os
+    from oracle import fake_eval
+    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "evaluate_kat.npz"))
+    for conv in fake_eval.CONVENTIONS:
+        model = fake_eval.FakeModel(conv)
+        res = ref.metrics.evaluate_thermal_depth(model, fake_eval.make_loader(seed=7), torch.device("cpu"))
+        np.testing.assert_array_equal(fake_eval.as_vector(res), gold[conv])
+    per = []
+    model = fake_eval.FakeModel("tuple_tensor")
+    for batch in fake_eval.make_loader(seed=7):
+        if batch.get("depth1") is None:
+            continue
+        for i in range(batch["thermal1"].shape[0]):
+            view = {"img": batch["thermal1"][i:i + 1], "instance": []}
+            pm = model(view, view)[0][0]
+            per.append(ref_metrics.compute_depth_metrics(pm[..., 2].numpy(), batch["depth1"][i].numpy()))
+    acc = ref_metrics.accumulate_dataset(per)
+    np.testing.assert_allclose([acc[k] for k in fake_eval.KEYS], gold["tuple_tensor"], rtol=1e-6)

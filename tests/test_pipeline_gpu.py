@@ -9,6 +9,7 @@ from oracle import ref_loss, ref_metrics, ref_preprocess
 
 pytestmark = pytest.mark.gpu
 KW = dict(alpha=0.2, edge_weight=0.5, smoothness_weight=0.3, detail_weight=0.4)
+NVEC = 24        # T3D_RESULT_SIZE
 
 
 def _oracle_step(raw1, raw2, P1, P2, G1, G2, C1, C2, gt_depth, H, W, multi):
@@ -143,16 +144,16 @@ def test_peer_mailbox_exchange_world_of_one(cuda_device):
     mk = lambda: [torch.ones(B, H, W, 3, device=cuda_device), torch.ones(B, H, W, 3, device=cuda_device),
                   torch.ones(B, H, W, device=cuda_device), torch.ones(B, H, W, device=cuda_device)]
     grads = mk()
-    ref = torch.zeros(16, dtype=torch.float64, device=cuda_device)
+    ref = torch.zeros(NVEC, dtype=torch.float64, device=cuda_device)
     st = _lib.current_stream_ptr()
     _lib.check(lib.t3d_step_epilogue(*[_lib.ptr(x) for x in grads], _lib.ptr(per_sample), _lib.ptr(batch), _lib.ptr(m64),
-                                     B, H, W, B, 0, _lib.ptr(ref), st), "t3d_step_epilogue")
+                                     B, H, W, B, 0, None, 0, _lib.ptr(ref), st), "t3d_step_epilogue")
     assert torch.count_nonzero(grads[0][1]) == 0 and torch.all(grads[0][0] == 1.5)    # fix-up: B / n_valid = 3 / 2
     # deferred variant (data parallel): zeros only; t3d_rescale_global applies samples / valid of the all-reduced vector
     g2 = mk()
-    out = torch.zeros(16, dtype=torch.float64, device=cuda_device)
+    out = torch.zeros(NVEC, dtype=torch.float64, device=cuda_device)
     _lib.check(lib.t3d_step_epilogue(*[_lib.ptr(x) for x in g2], _lib.ptr(per_sample), _lib.ptr(batch), _lib.ptr(m64),
-                                     B, H, W, B, 1, _lib.ptr(out), st), "t3d_step_epilogue")
+                                     B, H, W, B, 1, None, 0, _lib.ptr(out), st), "t3d_step_epilogue")
     assert torch.equal(out, ref) and torch.count_nonzero(g2[0][1]) == 0 and torch.all(g2[0][0] == 1.0)
     glob = out.clone(); glob[5] += 3; glob[6] += 3                                  # a second rank with 3 valid samples
     _lib.check(lib.t3d_rescale_global(*[_lib.ptr(x) for x in g2], _lib.ptr(per_sample), _lib.ptr(glob), B, H, W, st),
@@ -165,11 +166,11 @@ def test_peer_mailbox_exchange_world_of_one(cuda_device):
         peers = (C.c_uint64 * world)(*([mailbox.data_ptr()] * world))
         for step in range(5):
             grads = mk()
-            local = torch.zeros(16, dtype=torch.float64, device=cuda_device)
-            out = torch.full((16,), -1.0, dtype=torch.float64, device=cuda_device)
+            local = torch.zeros(NVEC, dtype=torch.float64, device=cuda_device)
+            out = torch.full((NVEC,), -1.0, dtype=torch.float64, device=cuda_device)
             for rank in range(world):                                             # every "rank" posts into the one mailbox
                 _lib.check(lib.t3d_step_epilogue_peers(*[_lib.ptr(x) for x in grads], _lib.ptr(per_sample), _lib.ptr(batch),
-                                                       _lib.ptr(m64), B, H, W, B, _lib.ptr(local), peers, world, rank, step, st),
+                                                       _lib.ptr(m64), B, H, W, B, None, 0, _lib.ptr(local), peers, world, rank, step, st),
                            "t3d_step_epilogue_peers")
             assert torch.count_nonzero(grads[0][1]) == 0 and torch.all(grads[0][0] == 1.0)     # zeros only
             if step % 2 == 0:       # vector only
@@ -200,9 +201,9 @@ def test_two_rank_validity_matches_single_process(cuda_device):
 
     # single process, batch 2B
     whole = t3d.fused_thermal_loss_fwd_bwd(*d, multi_scale=False, rescale_invalid=False, **KW)
-    ref16 = torch.zeros(16, dtype=torch.float64, device=cuda_device)
+    ref16 = torch.zeros(NVEC, dtype=torch.float64, device=cuda_device)
     _lib.check(lib.t3d_step_epilogue(*[_lib.ptr(whole[k]) for k in names], _lib.ptr(whole["per_sample"]), _lib.ptr(whole["batch"]),
-                                     None, 2 * B, H, W, 0, 0, _lib.ptr(ref16), st), "t3d_step_epilogue")
+                                     None, 2 * B, H, W, 0, 0, None, 0, _lib.ptr(ref16), st), "t3d_step_epilogue")
     assert whole["per_sample"][:, 5].tolist() == [1.0, 1.0, 1.0, 0.0]
 
     # two ranks of B samples: a-priori scale 1 / (B * world)
@@ -213,13 +214,13 @@ def test_two_rank_validity_matches_single_process(cuda_device):
         sl = slice(rank * B, (rank + 1) * B)
         r = t3d.fused_thermal_loss_fwd_bwd(*[x[sl].contiguous() for x in d], multi_scale=False, rescale_invalid=False,
                                            grad_scale=1.0 / (2 * B), **KW)
-        local = torch.zeros(16, dtype=torch.float64, device=cuda_device)
+        local = torch.zeros(NVEC, dtype=torch.float64, device=cuda_device)
         _lib.check(lib.t3d_step_epilogue_peers(*[_lib.ptr(r[k]) for k in names], _lib.ptr(r["per_sample"]), _lib.ptr(r["batch"]),
-                                               None, B, H, W, 0, _lib.ptr(local), peers, 2, rank, 0, st), "t3d_step_epilogue_peers")
+                                               None, B, H, W, 0, None, 0, _lib.ptr(local), peers, 2, rank, 0, st), "t3d_step_epilogue_peers")
         parts.append(r)
     for rank in range(2):
         r = parts[rank]
-        out = torch.zeros(16, dtype=torch.float64, device=cuda_device)
+        out = torch.zeros(NVEC, dtype=torch.float64, device=cuda_device)
         _lib.check(lib.t3d_mailbox_reduce(_lib.ptr(mailbox), 2, 0, _lib.ptr(out), *[_lib.ptr(r[k]) for k in names],
                                           _lib.ptr(r["per_sample"]), B, H, W, st), "t3d_mailbox_reduce")
         assert out[5].item() == 3.0 and out[6].item() == 4.0
@@ -312,3 +313,53 @@ def test_second_device(cuda_device):
     b = step1.run_device(*[d1[n] for n in key]).cpu()
     assert torch.cuda.current_device() == 0 and step1.loss_out["dpred1"].device.index == 1
     assert torch.equal(a, b)
+
+
+def test_sobel_parameter_gradients_ride_the_exchange(cuda_device):
+    """HotPathStep(sobel=True): ThermalDUSt3R's Sobel enhancer (thermal_dustr_model.py:110-142) in front of the model;
+    the gradients of its two scalars -- the only parameters on this path -- travel in slots 16, 17 of the packed
+    vector.  Single process: the enhanced batch and the gradients equal the reference arithmetic (oracle/ref_sobel +
+    autograd) on the preprocessed thermal.  Two "ranks" of B pairs posting into one mailbox: the reduced slots are
+    the sum over the ranks = the gradients of the 2B batch (the data-parallel gradient all-reduce of this path)."""
+    import ctypes as C
+    from oracle import ref_sobel
+    from thermal3d_vision_b200 import _lib
+    from thermal3d_vision_b200.pipeline import HotPathStep
+    import bench
+    lib = _lib.lib()
+    B, H, W = 2, 64, 96
+    key = ("raw1", "raw2", "pred1", "pred2", "gt1", "gt2", "conf1", "conf2", "gt_depth")
+    g = torch.Generator(device=cuda_device).manual_seed(3)
+    parts, want_e, want_t = [], 0.0, 0.0
+    for rank in range(2):
+        d = bench.make_inputs_torch(B, H, W, seed=70 + rank, device=cuda_device, raw_hw=(96, 160))
+        dout = torch.randn(2 * B, 3, H, W, device=cuda_device, generator=g) / (2 * B * H * W)
+        step = HotPathStep(B, H, W, raw_hw=(96, 160), device=cuda_device, sobel=True, **KW)
+        r = step.run_device(*[d[n] for n in key], sobel_dout=dout).clone()
+        # reference arithmetic on the same (bit-exact) preprocessed thermal
+        th = step.pre_both["thermal"].cpu()
+        ew, ts = torch.tensor(0.5, requires_grad=True), torch.tensor(1.0, requires_grad=True)
+        ref = ref_sobel.preprocess_thermal_torch(th, ew, ts)
+        (ref * dout.cpu()).sum().backward()
+        torch.testing.assert_close(step.sobel_out["enhanced"].cpu(), ref.detach(), rtol=1e-6, atol=1e-6)
+        assert r[16].item() == pytest.approx(ew.grad.item(), rel=1e-4, abs=1e-9)
+        assert r[17].item() == pytest.approx(ts.grad.item(), rel=1e-4, abs=1e-9)
+        assert r[18:].abs().sum().item() == 0.0 and r[15].item() == 0.0
+        want_e += r[16].item(); want_t += r[17].item()
+        parts.append((step, r))
+    # the same two local vectors through the peer-memory exchange
+    mailbox = torch.zeros(int(lib.t3d_mailbox_bytes()) // 8, dtype=torch.float64, device=cuda_device)
+    peers = (C.c_uint64 * 2)(mailbox.data_ptr(), mailbox.data_ptr())
+    st = _lib.current_stream_ptr()
+    for rank, (step, r) in enumerate(parts):
+        lo, me = step.loss_out, step.met_out
+        local = torch.zeros(NVEC, dtype=torch.float64, device=cuda_device)
+        _lib.check(lib.t3d_step_epilogue_peers(*[_lib.ptr(lo[k]) for k in ("dpred1", "dpred2", "dconf1", "dconf2")],
+                                               _lib.ptr(lo["per_sample"]), _lib.ptr(lo["batch"]), _lib.ptr(me["metrics_f64"]),
+                                               B, H, W, B, _lib.ptr(step.sobel_out["dparams"]), 2, _lib.ptr(local), peers, 2, rank, 0, st),
+                   "t3d_step_epilogue_peers")
+        assert torch.equal(local, r)
+    out = torch.zeros(NVEC, dtype=torch.float64, device=cuda_device)
+    _lib.check(lib.t3d_mailbox_reduce(_lib.ptr(mailbox), 2, 0, _lib.ptr(out), None, None, None, None, None, 0, 0, 0, st), "t3d_mailbox_reduce")
+    assert torch.equal(out, parts[0][1] + parts[1][1])
+    assert out[16].item() == want_e and out[17].item() == want_t and out[6].item() == 2 * B

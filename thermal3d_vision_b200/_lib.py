@@ -69,10 +69,10 @@ _SIGNATURES = {
     "t3d_sobel_enhance_fwd": (C.c_int, [c_ptr, c_ptr] + [C.c_int] * 5 + [c_ptr, c_ptr, C.c_size_t, c_ptr]),
     "t3d_sobel_enhance_bwd_params": (C.c_int, [c_ptr, c_ptr, c_ptr] + [C.c_int] * 5 + [c_ptr, c_ptr, C.c_size_t, c_ptr]),
     "t3d_pack_step_result": (C.c_int, [c_ptr, c_ptr, C.c_int, C.c_int, c_ptr, c_ptr]),
-    "t3d_step_epilogue": (C.c_int, [c_ptr] * 7 + [C.c_int] * 5 + [c_ptr, c_ptr]),
+    "t3d_step_epilogue": (C.c_int, [c_ptr] * 7 + [C.c_int] * 5 + [c_ptr, C.c_int] + [c_ptr, c_ptr]),
     "t3d_rescale_global": (C.c_int, [c_ptr] * 6 + [C.c_int] * 3 + [c_ptr]),
     "t3d_mailbox_bytes": (C.c_size_t, []),
-    "t3d_step_epilogue_peers": (C.c_int, [c_ptr] * 7 + [C.c_int] * 4 + [c_ptr, c_ptr, C.c_int, C.c_int, C.c_uint64, c_ptr]),
+    "t3d_step_epilogue_peers": (C.c_int, [c_ptr] * 7 + [C.c_int] * 4 + [c_ptr, C.c_int] + [c_ptr, c_ptr, C.c_int, C.c_int, C.c_uint64, c_ptr]),
     "t3d_mailbox_reduce": (C.c_int, [c_ptr, C.c_int, C.c_uint64, c_ptr] + [c_ptr] * 5 + [C.c_int] * 3 + [c_ptr]),
     "t3d_project_points": (C.c_int, [c_ptr] + [C.c_float] * 4 + [c_ptr, C.c_size_t, c_ptr]),
 }

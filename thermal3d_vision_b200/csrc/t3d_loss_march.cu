@@ -30,12 +30,13 @@ constexpr float kConfMin = 1e-5f, kConfMax = 10.0f;
 constexpr int kStripPx = 128;            // 32 lanes x 4 pixels
 constexpr int kSegPx = kStripPx + 8;     // + 4-pixel halo each side (keeps 16-byte alignment of AoS rows)
 
-template <int TCH> struct Stage {
+template <int TCH, bool S2 = false> struct Stage {
     static constexpr int kPred = 0;
     static constexpr int kGt = kSegPx * 3;
     static constexpr int kConf = 2 * kSegPx * 3;
     static constexpr int kTh = kConf + kStripPx;
-    static constexpr int kFloats = kTh + TCH * kSegPx;     // 1352 floats (TCH = 3)
+    static constexpr int kDz = kTh + TCH * kSegPx;         // multi-scale: the strip's 64 pooled-cell gradients of this row pair
+    static constexpr int kFloats = kDz + (S2 ? kStripPx / 2 : 0);     // 1352 floats (TCH = 3, single scale)
 };
 
 // ------------------------------------------------------------------ PTX helpers (sm_100a)
@@ -137,7 +138,7 @@ __device__ __forceinline__ void load_row(const float* __restrict__ st, int idx, 
     r.P[8] = c.x; r.P[9] = c.y; r.P[10] = c.z; r.P[11] = c.w;
     r.G[0] = d.x; r.G[1] = d.y; r.G[2] = d.z; r.G[3] = d.w; r.G[4] = e.x; r.G[5] = e.y; r.G[6] = e.z; r.G[7] = e.w;
     r.G[8] = f.x; r.G[9] = f.y; r.G[10] = f.z; r.G[11] = f.w;
-    gray_quad<TCH, REP>(st + Stage<TCH>::kTh, idx, r.g);
+    gray_quad<TCH, REP>(st + Stage<TCH>::kTh, idx, r.g);       // (offsets up to kTh do not depend on S2)
 }
 
 // ------------------------------------------------------------------ kernel
@@ -145,7 +146,7 @@ __device__ __forceinline__ void load_row(const float* __restrict__ st, int idx, 
 template <int TCH, bool REP, bool BWD, bool S2, int NS, int WARPS>
 __global__ void __launch_bounds__((TCH == 3) ? 320 : 384, 1) loss_march_kernel(const MarchArgs a) {
     static_assert(!REP || TCH == 1, "replicated planes: one plane is staged");
-    using St = Stage<TCH>;
+    using St = Stage<TCH, S2>;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
     float* ring = reinterpret_cast<float*>(smem_raw) + (size_t)wrp * NS * St::kFloats;
@@ -206,6 +207,10 @@ __global__ void __launch_bounds__((TCH == 3) ? 320 : 384, 1) loss_march_kernel(c
         // multi-scale: this lane's two pooled cells per row pair (W % 4 == 0: columns j .. j+3 are always inside 2 * (W / 2))
         const int w2 = W >> 1, rows2 = 2 * (H >> 1);
         const float* dz2_ptr = (S2 && BWD) ? a.dzp[view] + (size_t)b * (H >> 1) * w2 + (j >> 1) : nullptr;
+        // W % 8 == 0: a pooled row segment is 16-byte aligned and a multiple of 16 bytes -> it travels with the
+        // row's other segments through the bulk-copy ring; else each lane loads its two cells itself
+        const bool dz_staged = S2 && BWD && ((W & 7) == 0);
+        const float* dz2_strip = dz_staged ? a.dzp[view] + (size_t)b * (H >> 1) * w2 + (col0 >> 1) : nullptr;
 
         // 1 / (mean + eps) of |Dx gray|, |Dy gray| of this image: fixed-order sum of the stats partials
         float inv_mx, inv_my;
@@ -228,7 +233,9 @@ __global__ void __launch_bounds__((TCH == 3) ? 320 : 384, 1) loss_march_kernel(c
             float* st = ring + (size_t)(p % NS) * St::kFloats;
             uint64_t* bar = &bars[p % NS];
             const size_t rowpix = (size_t)(i_lo + ri) * W;
-            mbar_arrive_expect_tx(bar, row_bytes);
+            const bool with_dz = dz_staged && (i_lo + ri) < rows2;
+            mbar_arrive_expect_tx(bar, row_bytes + (with_dz ? (uint32_t)own_n * 2u : 0u));
+            if (with_dz) bulk_g2s(st + St::kDz, dz2_strip + (size_t)((i_lo + ri) >> 1) * w2, (uint32_t)own_n * 2u, bar);
             bulk_g2s(st + St::kPred, pred + (rowpix + c0) * 3, (uint32_t)npx * 12u, bar);
             bulk_g2s(st + St::kGt, gt + (rowpix + c0) * 3, (uint32_t)npx * 12u, bar);
             if (conf) bulk_g2s(st + St::kConf, conf + rowpix + col0, (uint32_t)own_n * 4u, bar);
@@ -321,7 +328,9 @@ __global__ void __launch_bounds__((TCH == 3) ? 320 : 384, 1) loss_march_kernel(c
                                       -qx[2] + qx[1] - qy[2] + qy_prev[2], -qx[3] + qx[2] - qy[3] + qy_prev[3]};
                 float gq[12], dc[4];
                 float2 d2 = make_float2(0.f, 0.f);
-                if (S2 && BWD && active && r < rows2) d2 = __ldg(reinterpret_cast<const float2*>(dz2_ptr + (size_t)(r >> 1) * w2));
+                if (S2 && BWD && active && r < rows2)
+                    d2 = dz_staged ? *reinterpret_cast<const float2*>(st + St::kDz + 2 * lane)
+                                   : __ldg(reinterpret_cast<const float2*>(dz2_ptr + (size_t)(r >> 1) * w2));
                 const float dz2[4] = {d2.x, d2.x, d2.y, d2.y};
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
@@ -381,7 +390,7 @@ __global__ void __launch_bounds__((TCH == 3) ? 320 : 384, 1) loss_march_kernel(c
 template <int TCH, bool REP, bool BWD, bool S2, int WARPS>
 int launch_w(const MarchArgs& a, cudaStream_t st) {
     constexpr int NS = 4;
-    constexpr size_t smem = (size_t)WARPS * NS * Stage<TCH>::kFloats * sizeof(float) + (size_t)WARPS * NS * 8;
+    constexpr size_t smem = (size_t)WARPS * NS * Stage<TCH, S2>::kFloats * sizeof(float) + (size_t)WARPS * NS * 8;
     static_assert(smem <= 227 * 1024, "ring does not fit in shared memory");
     static bool attr_done[kT3dMaxDevices] = {};
     bool& attr_set = attr_done[t3d_device_slot()];

@@ -60,12 +60,13 @@ __global__ void __launch_bounds__(kS2Threads) loss_scale2_kernel(const Scale2Arg
     const int tch = a.replicated ? 1 : a.tch;
 
     // 1 / (mean + eps) of the pooled thermal gradients of this image (fixed-order sum of the stats partials)
-    if (tid < 2) {
+    if (wrp < 2) {                      // warp 0: Dx sums, warp 1: Dy sums; lane t owns partials t, t + 32, ...; fixed butterfly
         double s = 0.0;
-        const float* sp = a.stats[view] + (size_t)b * a.stiles * 4 + 2 + tid;
-        for (int t = 0; t < a.stiles; ++t) s += (double)sp[(size_t)t * 4];
+        const float* sp = a.stats[view] + (size_t)b * a.stiles * 4 + 2 + wrp;
+        for (int t = lane; t < a.stiles; t += 32) s += (double)sp[(size_t)t * 4];
+        s = warp_sum(s);
         const double n2 = (double)h2 * w2;
-        s_inv[tid] = 1.0f / ((float)(s / n2) + 1e-5f);
+        if (lane == 0) s_inv[wrp] = 1.0f / ((float)(s / n2) + 1e-5f);
     }
     // ---- pooled planes of cells I0-1 .. I0+kT2H, J0-2 .. J0+kT2W+1 (cells outside the pooled image: 0).
     // One work item = two horizontally adjacent cells = 4 pixels x 2 rows: 128-bit loads (W % 4 == 0, aligned).

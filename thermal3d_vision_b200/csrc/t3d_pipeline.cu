@@ -43,11 +43,11 @@ __global__ void __launch_bounds__(128) pack_step_result_kernel(const float* __re
     __syncthreads();
     if (tid < 14) red[0][tid] = (red[0][tid] + red[1][tid]) + (red[2][tid] + red[3][tid]);
     __syncthreads();
-    if (tid < 16) {
+    if (tid < T3D_RESULT_SIZE) {
         double r;
         if (tid == 6) r = loss_per_sample ? (double)B : 0.0;
         else if (tid == 14) r = metrics_f64 ? (double)n_images : 0.0;
-        else if (tid == 15) r = 0.0;
+        else if (tid >= 15) r = 0.0;
         else r = red[0][tid];
         out[tid] = r;
     }
@@ -56,8 +56,8 @@ __global__ void __launch_bounds__(128) pack_step_result_kernel(const float* __re
 // pack + the validity fix-up of the loss gradients (scale_grads_kernel<0> of t3d_loss.cu) as ONE launch: block 0
 // packs, every block then checks the batch's valid count and returns at once when all samples are valid.
 // Peer-memory exchange of the packed vector (one process per GPU on one NVLink / NVSwitch node): every rank owns a
-// mailbox  { double slots[2][T3D_MAX_PEERS][16]; unsigned long long flags[2][T3D_MAX_PEERS]; }  in memory its peers
-// can address (CUDA IPC / symmetric memory).  Step s uses parity p = s & 1: rank r's epilogue stores its 16 doubles
+// mailbox  { double slots[2][T3D_MAX_PEERS][T3D_RESULT_SIZE]; unsigned long long flags[2][T3D_MAX_PEERS]; }  in memory its peers
+// can address (CUDA IPC / symmetric memory).  Step s uses parity p = s & 1: rank r's epilogue stores its doubles
 // into slot [p][r] of EVERY rank's mailbox (128-byte peer stores), fences, then publishes flags[p][r] = s + 1 with
 // release semantics; mailbox_reduce_kernel on each rank waits for the world's flags and adds the slots in rank order
 // (the same bits on every rank).  No NCCL call and no host work per step beyond the two launches.
@@ -65,7 +65,9 @@ __global__ void __launch_bounds__(128) pack_step_result_kernel(const float* __re
 // step s + 2 into parity p (after its own reduce(s + 1), which needed this rank's epilogue(s + 1)) the step-s slots
 // have been read here.
 constexpr int kMaxPeers = T3D_MAX_PEERS;
-struct Mailbox { double slots[2][kMaxPeers][16]; unsigned long long flags[2][kMaxPeers]; };
+constexpr int kVec = T3D_RESULT_SIZE;      // doubles in the packed step vector
+struct Mailbox { double slots[2][kMaxPeers][kVec]; unsigned long long flags[2][kMaxPeers]; };
+static_assert(kVec <= 32 && kVec >= 16 && kMaxPeers <= kVec, "one warp handles the vector and the flags");
 struct PeerArgs { Mailbox* box[kMaxPeers]; int world, rank; unsigned long long step; };
 
 struct EpilogueArgs {
@@ -73,6 +75,7 @@ struct EpilogueArgs {
     const float* out_sample; const float* out_batch; const double* metrics_f64;
     int B, n_images; size_t plane; double* out16;
     int defer_rescale;      // data parallel: only zero the invalid samples here, the global factor comes later
+    const float* param_grads; int n_param_grads;     // parameter gradients riding along in slots 16.. (or NULL)
 };
 
 // gradients of sample b *= valid_b ? scale : 0 (exact zeros: an invalid sample's gradients may hold NaN / Inf)
@@ -124,18 +127,19 @@ __global__ void __launch_bounds__(128) step_epilogue_kernel(const EpilogueArgs a
             if (lane == 0) red[wrp][k] = r;
         }
         __syncthreads();
-        if (tid < 16) {
+        if (tid < kVec) {
             double r;
             if (tid == 6) r = (double)a.B;
             else if (tid == 14) r = a.metrics_f64 ? (double)a.n_images : 0.0;
             else if (tid == 15) r = 0.0;
+            else if (tid >= 16) r = (a.param_grads && tid - 16 < a.n_param_grads) ? (double)a.param_grads[tid - 16] : 0.0;
             else r = (red[0][tid] + red[1][tid]) + (red[2][tid] + red[3][tid]);
             a.out16[tid] = r;
             if (PEERS) {
                 const int p = (int)(pa.step & 1ull);
                 for (int q = 0; q < pa.world; ++q) pa.box[q]->slots[p][pa.rank][tid] = r;       // peer stores (NVLink)
                 __threadfence_system();
-                __syncwarp(0x0000ffffu);
+                __syncwarp(0x00ffffffu);
                 if (tid < pa.world) {
                     unsigned long long* f = &pa.box[tid]->flags[p][pa.rank];
                     const unsigned long long v = pa.step + 1ull;
@@ -157,13 +161,16 @@ __global__ void __launch_bounds__(128) step_epilogue_kernel(const EpilogueArgs a
 
 extern "C" int t3d_step_epilogue(float* dpred1, float* dpred2, float* dconf1, float* dconf2,
                                  const float* loss_per_sample, const float* loss_batch, const double* metrics_f64,
-                                 int B, int H, int W, int n_images, int defer_rescale, double* out16, void* stream) {
+                                 int B, int H, int W, int n_images, int defer_rescale,
+                                 const float* param_grads, int n_param_grads, double* out16, void* stream) {
     T3D_REQUIRE(loss_per_sample && loss_batch && out16, "NULL pointer");
     T3D_REQUIRE(B >= 1 && H >= 1 && W >= 1 && n_images >= 0, "bad dims");
     EpilogueArgs a;
     a.dpred[0] = dpred1; a.dpred[1] = dpred2; a.dconf[0] = dconf1; a.dconf[1] = dconf2;
     a.out_sample = loss_per_sample; a.out_batch = loss_batch; a.metrics_f64 = metrics_f64;
+    T3D_REQUIRE(n_param_grads >= 0 && n_param_grads <= kVec - 16 && (n_param_grads == 0 || param_grads), "at most %d parameter gradients", kVec - 16);
     a.B = B; a.n_images = n_images; a.plane = (size_t)H * W; a.out16 = out16; a.defer_rescale = defer_rescale ? 1 : 0;
+    a.param_grads = param_grads; a.n_param_grads = n_param_grads;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     PeerArgs pa;
     pa.world = 0; pa.rank = 0; pa.step = 0;
@@ -194,7 +201,7 @@ __global__ void __launch_bounds__(128) mailbox_reduce_kernel(const ReduceArgs a)
             } while (v < a.step + 1ull);
         }
         __syncwarp();
-        if (lane < 16) {
+        if (lane < kVec) {
             double s = 0.0;
             for (int r = 0; r < a.world; ++r) {                       // rank order: the same bits on every rank
                 double x;
@@ -217,7 +224,8 @@ extern "C" size_t t3d_mailbox_bytes(void) { return sizeof(Mailbox); }
 
 extern "C" int t3d_step_epilogue_peers(float* dpred1, float* dpred2, float* dconf1, float* dconf2,
                                        const float* loss_per_sample, const float* loss_batch, const double* metrics_f64,
-                                       int B, int H, int W, int n_images, double* out16_local,
+                                       int B, int H, int W, int n_images,
+                                       const float* param_grads, int n_param_grads, double* out16_local,
                                        const unsigned long long* peer_mailboxes, int world, int rank,
                                        unsigned long long step, void* stream) {
     T3D_REQUIRE(loss_per_sample && loss_batch && out16_local && peer_mailboxes, "NULL pointer");
@@ -226,7 +234,9 @@ extern "C" int t3d_step_epilogue_peers(float* dpred1, float* dpred2, float* dcon
     EpilogueArgs a;
     a.dpred[0] = dpred1; a.dpred[1] = dpred2; a.dconf[0] = dconf1; a.dconf[1] = dconf2;
     a.out_sample = loss_per_sample; a.out_batch = loss_batch; a.metrics_f64 = metrics_f64;
+    T3D_REQUIRE(n_param_grads >= 0 && n_param_grads <= kVec - 16 && (n_param_grads == 0 || param_grads), "at most %d parameter gradients", kVec - 16);
     a.B = B; a.n_images = n_images; a.plane = (size_t)H * W; a.out16 = out16_local; a.defer_rescale = 1;
+    a.param_grads = param_grads; a.n_param_grads = n_param_grads;
     PeerArgs pa;
     for (int q = 0; q < kMaxPeers; ++q) pa.box[q] = (q < world) ? reinterpret_cast<Mailbox*>(peer_mailboxes[q]) : nullptr;
     pa.world = world; pa.rank = rank; pa.step = step;

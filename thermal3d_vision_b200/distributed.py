@@ -2,7 +2,7 @@
 
 The path shards by image: rank r owns a contiguous slice of the batch / dataset and runs the
 kernels on it with no data-path collective.  The only exchange per step is ONE all-reduce (SUM)
-of the packed 16-double result vector that ``t3d_pack_step_result`` produces on the device
+of the packed result vector (RESULT_SIZE doubles) that ``t3d_pack_step_result`` produces on the device
 (SURVEY.md section 8e): sums of valid losses / components / counts and sums of finite metrics /
 image count, i.e. exactly the accumulators of train_thermal_dustr.py:320,359 and
 utils/metrics.py:128-136.  Gradients w.r.t. pointmaps stay local to the rank.
@@ -14,7 +14,7 @@ from typing import Dict, Tuple
 import torch
 import torch.distributed as dist
 
-RESULT_SIZE = 16
+RESULT_SIZE = 24
 METRIC_KEYS = ("abs_rel", "sq_rel", "rmse", "rmse_log", "acc_1", "acc_2", "acc_3")
 
 
@@ -80,4 +80,7 @@ def summarize(vec) -> Dict[str, float]:
            "detail_loss": r[4] / nv, "n_valid": r[5], "n_pairs": r[6], "n_images": r[14]}
     for i, k in enumerate(METRIC_KEYS):
         out[k] = r[7 + i] / n_img
+    # parameter gradients summed over the ranks (slots 16..): with the a-priori 1 / (B * world) scale of the loss
+    # gradients upstream, the sum IS the gradient of the global batch mean (what DDP's all-reduce produces)
+    out["param_grads"] = r[16:RESULT_SIZE]
     return out

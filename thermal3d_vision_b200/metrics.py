@@ -151,22 +151,32 @@ class MetricAccumulator:
 
 
 def evaluate_thermal_depth(model, dataloader, device):
-    """Drop-in for utils/metrics.py:72-138.  The model forward is the caller's (out of scope);
-    z-extraction + metrics run batched on the GPU."""
+    """Drop-in for utils/metrics.py:72-138.  The model forward is the caller's (out of scope); the loop, the
+    output conventions it accepts (:105-117) and the accumulator semantics (:128-136: non-finite metrics are
+    skipped, the sample still counts) are the reference's; z-extraction + metrics run on the GPU and the per-sample
+    metrics stay on the device until the single read at the end (the reference syncs once per sample)."""
     model.eval()
-    acc = MetricAccumulator(device)
+    dev = torch.device(device)
+    if dev.type != "cuda":
+        dev = torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else dev
+    acc = None
     with torch.no_grad():
         for batch in dataloader:
             thermal1 = batch["thermal1"].to(device)
             if "depth1" in batch and batch["depth1"] is not None:
                 gt_depth = batch["depth1"].to(device)
                 for i in range(thermal1.size(0)):
-                    view = {"img": thermal1[i:i + 1], "instance": []}
+                    view = {"img": thermal1[i:i + 1], "instance": []}        # monocular mode (:103-104)
                     output = model(view, view)
                     pred = output[0] if isinstance(output, tuple) else output.get("pred1", {})
-                    pm = pred.get("pts3d") if isinstance(pred, dict) else pred
-                    if pm.dim() == 3:
-                        pm = pm.unsqueeze(0)
-                    r = compute_depth_metrics_batch(pm, gt_depth[i:i + 1])
+                    pred_pointmap = pred.get("pts3d") if isinstance(pred, dict) else pred
+                    if len(pred_pointmap.shape) == 4:                        # [B,H,W,3] -> first element (:116-117)
+                        pred_pointmap = pred_pointmap[0]
+                    if acc is None:
+                        acc = MetricAccumulator(dev)
+                    # pointmap -> depth happens inside the metric kernels (Z read in place, stride 3)
+                    r = compute_depth_metrics_batch(pred_pointmap.unsqueeze(0), gt_depth[i:i + 1])
                     acc.update(r["metrics_f64"])
+    if acc is None:                                                          # sample_count == 0 (:134-135)
+        return {k: np.nan for k in KEYS7}
     return acc.result()

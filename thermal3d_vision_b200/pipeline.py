@@ -19,7 +19,7 @@ from . import loss as _loss
 from . import metrics as _metrics
 from . import preprocessing as _pre
 
-RESULT_SIZE = 16   # packed result vector (float64): see HotPathStep.run_device
+RESULT_SIZE = 24   # packed result vector (float64): see HotPathStep.run_device
 
 
 class HotPathStep:
@@ -40,8 +40,9 @@ class HotPathStep:
 
     def __init__(self, B: int, H: int, W: int, raw_hw=(512, 640), device=None, multi_scale: bool = False,
                  alpha=0.2, edge_weight=0.5, smoothness_weight=0.3, detail_weight=0.4, distributed: bool = False,
-                 exchange: str = "peer", pipelined: bool = False):
+                 exchange: str = "peer", pipelined: bool = False, sobel: bool = False):
         self.B, self.H, self.W, self.raw_hw = B, H, W, tuple(raw_hw)
+        self.sobel = bool(sobel)
         self.device = torch.device(device if device is not None else "cuda")
         if self.device.index is None:
             self.device = torch.device("cuda", torch.cuda.current_device())
@@ -85,6 +86,15 @@ class HotPathStep:
         self.met_sets[1]["workspace"] = self.met_sets[0]["workspace"]
         self.pre_sets[1]["workspace"] = self.pre_sets[0]["workspace"]
         self.loss_out, self.pre_both, self.met_out = self.loss_sets[0], self.pre_sets[0], self.met_sets[0]
+        if self.sobel:
+            # ThermalDUSt3R's Sobel enhancer in front of the model (thermal_dustr_model.py:110-142): its output is the
+            # model's input, its two scalars (edge_weight 0.5, temp_scale 1.0, :104-107) are the only parameters on this
+            # path -- their gradients ride along in the packed vector (slots 16, 17) and are summed over the ranks
+            # with it: the data-parallel gradient all-reduce of this path.
+            self.sobel_params = torch.tensor([0.5, 1.0], **f32)
+            self.sobel_sets = [{"enhanced": torch.empty(2 * B, 3, H, W, **f32), "dparams": torch.zeros(2, **f32)} for _ in range(2)]
+            self.sobel_ws = torch.empty(lib.t3d_sobel_workspace_bytes(2 * B, 3, H, W), dtype=torch.uint8, device=dev)
+            self.sobel_out = self.sobel_sets[0]
         # preprocessing first in line for free SMs (the loss waits for it), the metric chain last (it has a whole
         # step of slack: only the epilogue needs it)
         try:
@@ -172,18 +182,19 @@ class HotPathStep:
         }
 
     # ------------------------------------------------------------------ device-resident step
-    def run_device(self, raw1, raw2, pred1, pred2, gt1, gt2, conf1, conf2, gt_depth, _ready=None):
+    def run_device(self, raw1, raw2, pred1, pred2, gt1, gt2, conf1, conf2, gt_depth, _ready=None, sobel_dout=None):
         """All inputs already in HBM (ready on the caller's current stream).  Returns the packed device result vector
         (float64): [0] sum of valid per-sample losses  [1..4] sums of components  [5] n_valid  [6] B
-        [7..13] sums of finite per-image metrics (abs_rel..acc_3)  [14] n_images  [15] unused.
+        [7..13] sums of finite per-image metrics (abs_rel..acc_3)  [14] n_images  [15] unused
+        [16, 17] with sobel=True and `sobel_dout`: gradients of ThermalDUSt3R's edge_weight / temp_scale  [18..23] 0.
         With distributed=True the vector is summed over the ranks (peer-memory mailboxes, or one NCCL all-reduce with
         exchange="nccl") and the gradients carry the global validity factor once `wait_result()` / `finish()` / the
         next call has enqueued the reduction.  pipelined=True: see the class docstring -- call `wait_result()`
         before consuming this step's outputs on the caller's stream."""
         with _lib.device_guard(self.device):
-            return self._run_device(raw1, raw2, pred1, pred2, gt1, gt2, conf1, conf2, gt_depth, _ready)
+            return self._run_device(raw1, raw2, pred1, pred2, gt1, gt2, conf1, conf2, gt_depth, _ready, sobel_dout)
 
-    def _run_device(self, raw1, raw2, pred1, pred2, gt1, gt2, conf1, conf2, gt_depth, ready):
+    def _run_device(self, raw1, raw2, pred1, pred2, gt1, gt2, conf1, conf2, gt_depth, ready, sobel_dout=None):
         size = (self.W, self.H)
         B = self.B
         lib = _lib.lib()
@@ -226,6 +237,27 @@ class HotPathStep:
                 a = _pre.preprocess_thermal_batch(raw1, size, path="train", out=self._pre_halves[i][0], histogram=self.histogram)
                 b = _pre.preprocess_thermal_batch(raw2, size, path="train", out=self._pre_halves[i][1], histogram=self.histogram)
                 (t1, t2), stats = (a.thermal, b.thermal), (a.grad_stats, b.grad_stats)
+            pgrads, n_pgrads = None, 0
+            if self.sobel:
+                # the model's input: Sobel-enhanced thermal of both views ([2B,3,H,W], view 1 first); given the
+                # upstream gradient w.r.t. it (`sobel_dout`, what the model's backward hands back), the gradients
+                # of the enhancer's two scalars
+                so = self.sobel_sets[i]
+                self.sobel_out = so
+                th_both = pre["thermal"] if stacked else torch.cat([t1, t2])
+                st = _lib.current_stream_ptr()
+                rc = lib.t3d_sobel_enhance_fwd(_lib.ptr(th_both), _lib.ptr(self.sobel_params), 2 * B, 3, self.H, self.W, 1,
+                                               _lib.ptr(so["enhanced"]), _lib.ptr(self.sobel_ws), self.sobel_ws.numel(), st)
+                _lib.check(rc, "t3d_sobel_enhance_fwd")
+                if sobel_dout is not None:
+                    if tuple(sobel_dout.shape) != (2 * B, 3, self.H, self.W) or sobel_dout.dtype != torch.float32 \
+                            or not sobel_dout.is_contiguous():
+                        raise ValueError("sobel_dout must be a contiguous float32 [2B,3,H,W] tensor")
+                    rc = lib.t3d_sobel_enhance_bwd_params(_lib.ptr(th_both), _lib.ptr(self.sobel_params), _lib.ptr(sobel_dout),
+                                                          2 * B, 3, self.H, self.W, 1, _lib.ptr(so["dparams"]),
+                                                          _lib.ptr(self.sobel_ws), self.sobel_ws.numel(), st)
+                    _lib.check(rc, "t3d_sobel_enhance_bwd_params")
+                    pgrads, n_pgrads = _lib.ptr(so["dparams"]), 2
             self.ev_pre[i].record(self.s_pre)
         with torch.cuda.stream(self.s_loss):
             self.s_loss.wait_event(ready)                   # pred / gt / conf
@@ -245,7 +277,7 @@ class HotPathStep:
                 self._reduce_pending()
                 rank, world = _dist.world()
                 rc = lib.t3d_step_epilogue_peers(*grads, _lib.ptr(lo["per_sample"]), _lib.ptr(lo["batch"]),
-                                                 _lib.ptr(me["metrics_f64"]), B, self.H, self.W, B,
+                                                 _lib.ptr(me["metrics_f64"]), B, self.H, self.W, B, pgrads, n_pgrads,
                                                  _lib.ptr(self.local[i]), self.peer_ptrs, world, rank, step_no, stream)
                 _lib.check(rc, "t3d_step_epilogue_peers")
                 self.reduced[i] = False
@@ -254,7 +286,7 @@ class HotPathStep:
                 self._reduce_pending()
                 # validity: zero the invalid samples now, the global factor follows the all-reduce (t3d_rescale_global)
                 rc = lib.t3d_step_epilogue(*grads, _lib.ptr(lo["per_sample"]), _lib.ptr(lo["batch"]),
-                                           _lib.ptr(me["metrics_f64"]), B, self.H, self.W, B, 1,
+                                           _lib.ptr(me["metrics_f64"]), B, self.H, self.W, B, 1, pgrads, n_pgrads,
                                            _lib.ptr(self.results[i]), stream)
                 _lib.check(rc, "t3d_step_epilogue")
                 self.local[i].copy_(self.results[i])
@@ -264,7 +296,7 @@ class HotPathStep:
             else:
                 # validity fix-up of the gradients + packing of the step's scalars: one launch
                 rc = lib.t3d_step_epilogue(*grads, _lib.ptr(lo["per_sample"]), _lib.ptr(lo["batch"]),
-                                           _lib.ptr(me["metrics_f64"]), B, self.H, self.W, B, 0,
+                                           _lib.ptr(me["metrics_f64"]), B, self.H, self.W, B, 0, pgrads, n_pgrads,
                                            _lib.ptr(self.results[i]), stream)
                 _lib.check(rc, "t3d_step_epilogue")
             self.ev_done[i].record(self.s_loss)
