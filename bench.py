@@ -57,9 +57,9 @@ def workload_name(a):
 
 EXCHANGE_TEXT = {
     None: "single process, no exchange",
-    "peer": "per step one 128-byte exchange of the packed scalars over NVLink peer memory (symmetric-memory mailboxes written by "
+    "peer": "per step one 192-byte exchange of the packed scalars over NVLink peer memory (symmetric-memory mailboxes written by "
             "the step's epilogue kernel), no NCCL call in the step",
-    "nccl": "per step one asynchronous NCCL all-reduce of the packed scalars (16 doubles)",
+    "nccl": "per step one asynchronous NCCL all-reduce of the packed scalars (24 doubles)",
     "cpu": "host cores only",
 }
 
@@ -422,10 +422,11 @@ def run_b200(a):
     _lib.lib()
 
     B, H, W = a.batch, a.height, a.width
-    # plain stream semantics: every step completes on the caller's stream before the next one is enqueued behind it
-    # (T3D_PIPELINED=1: consecutive steps overlap on the step's internal streams -- measured no faster);
-    # the timed region ends with finish(), i.e. after the last step's last kernel and exchange
-    pipelined = os.environ.get("T3D_PIPELINED", "0") not in ("", "0")
+    # pipelined: the next step's side chains (preprocessing, metrics) start when this step's loss kernel has left the
+    # machine, i.e. beside its second-stage reduction, epilogue and exchange instead of behind them; every step does all
+    # of its own work on its own output set (T3D_PIPELINED=0: plain stream semantics, a few microseconds slower per
+    # step).  The timed region ends with finish(), i.e. after the last step's last kernel and exchange.
+    pipelined = os.environ.get("T3D_PIPELINED", "1") not in ("", "0")
     step = HotPathStep(B, H, W, device=dev, multi_scale=bool(a.multi_scale), alpha=ALPHA, edge_weight=EDGE_W,
                        smoothness_weight=SMOOTH_W, detail_weight=DETAIL_W, distributed=world > 1, pipelined=pipelined)
     d = make_inputs_torch(B, H, W, seed=rank, device=dev)
@@ -521,7 +522,8 @@ def run_b200(a):
         except Exception:
             pass
         cfg = config_dict(a, world, step.exchange)
-        cfg["step_overlap"] = ("pipelined across steps (internal streams, two alternating output sets)" if pipelined else
+        cfg["step_overlap"] = ("the next step's preprocessing / metric chains start when this step's loss kernel ends, beside its "
+                               "second-stage reduction, epilogue and exchange (internal streams, two alternating output sets)" if pipelined else
                                "none across steps; inside a step the preprocessing and metric chains run on two streams beside each other")
         out = {
             "metric": METRIC, "value": world * B * a.steps / (ms_dev * 1e-3), "unit": UNIT, "n_gpus": world,

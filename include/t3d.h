@@ -131,6 +131,12 @@ int t3d_loss_fwd_bwd(const float* pred1, const float* pred2,
                      float* out_sample, float* out_batch, double* out_sample_f64,
                      void* workspace, size_t workspace_bytes, void* stream);
 
+/* Scheduling hook: `cuda_event` (a cudaEvent_t, or NULL to cancel) is recorded on the stream of the NEXT
+ * t3d_loss_fwd_bwd / t3d_loss_fwd call of the calling thread right behind its main kernel, i.e. BEFORE the small
+ * second-stage reduction: the moment the machine is free again.  A caller that overlaps consecutive steps lets the
+ * next batch's preprocessing wait for this event instead of for the end of the call.  One-shot. */
+int t3d_loss_set_main_done_event(void* cuda_event);
+
 /* Forward only (no gradient writes): same outputs as above. */
 int t3d_loss_fwd(const float* pred1, const float* pred2,
                  const float* gt1, const float* gt2,

@@ -34,6 +34,7 @@ _SIGNATURES = {
     "t3d_profile_timeline": (C.c_int, [C.c_char_p, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_int,
                                        C.POINTER(C.c_int)]),
     "t3d_loss_workspace_bytes": (C.c_size_t, [C.c_int] * 4),
+    "t3d_loss_set_main_done_event": (C.c_int, [c_ptr]),
     "t3d_thermal_grad_stats": (C.c_int, [c_ptr, c_ptr, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                          c_ptr, c_ptr, C.c_size_t, c_ptr]),
     "t3d_loss_fwd_bwd": (C.c_int, [c_ptr] * 8 + [C.c_int] + [c_ptr, c_ptr, C.c_int] + [c_ptr] * 4 + [C.c_int] * 4

@@ -804,6 +804,9 @@ WsLayout ws_layout(int B, int H, int W, int multi = 0) {
 
 inline float __int_as_float_host(unsigned int u) { float f; memcpy(&f, &u, sizeof(f)); return f; }
 
+// optional event recorded right behind the main (marching / tile) kernel of the next loss call of this thread
+thread_local cudaEvent_t g_main_done_event = nullptr;
+
 int check_dims(int B, int H, int W) {
     T3D_REQUIRE(B >= 1 && H >= 1 && W >= 1, "bad dims B=%d H=%d W=%d", B, H, W);
     T3D_REQUIRE((double)B * 2.0 * H * W < 2.0e9, "problem too large for 32-bit tile indexing");
@@ -961,6 +964,10 @@ int loss_impl(bool bwd, const float* pred1, const float* pred2, const float* gt1
         else    rc = vec ? launch_loss<false, true, false>(la, st) : launch_loss<false, false, false>(la, st);
     }
     if (rc) return rc;
+    if (g_main_done_event) {            // t3d_loss_set_main_done_event: lets a caller overlap the second stage with other work
+        T3D_CUDA(cudaEventRecord(g_main_done_event, st));
+        g_main_done_event = nullptr;
+    }
 
     FinalizeArgs fa;
     fa.partials = loss_partials; fa.out_sample = out_sample; fa.out_batch = out_batch; fa.out_f64 = out_f64;
@@ -975,6 +982,11 @@ int loss_impl(bool bwd, const float* pred1, const float* pred2, const float* gt1
 
 // ====================================================================== C ABI
 extern "C" {
+
+int t3d_loss_set_main_done_event(void* cuda_event) {
+    g_main_done_event = reinterpret_cast<cudaEvent_t>(cuda_event);
+    return T3D_OK;
+}
 
 size_t t3d_loss_workspace_bytes(int B, int H, int W, int flags) {
     if (B < 1 || H < 1 || W < 1) return 0;

@@ -109,6 +109,8 @@ class HotPathStep:
         self.ev_pre = [torch.cuda.Event() for _ in range(2)]
         self.ev_met = [torch.cuda.Event() for _ in range(2)]
         self.ev_done = [torch.cuda.Event() for _ in range(2)]
+        self.ev_main = [torch.cuda.Event() for _ in range(2)]     # the loss's main kernel of the step on set i has finished
+        self._main_recorded = [False, False]
         self._joined = [True, True]          # the caller's stream has been ordered after the step that last used set i
         # percentiles from sampled value windows (bit-identical to the exact-histogram path, no per-pixel atomic);
         # set True to also get the 65 536-bin histograms of the resized frames in pre_both["histogram"]
@@ -218,12 +220,20 @@ class HotPathStep:
         if self.histogram and "histogram" not in pre:
             pre["histogram"] = torch.empty(2 * B, 65536, dtype=torch.int32, device=self.device)
 
+        # pipelined: this step's side chains start when the PREVIOUS step's loss kernel has left the machine -- not
+        # earlier (their CTAs would take SMs away from that persistent kernel), not later (its second-stage
+        # reduction and epilogue, and this step's one-CTA-per-image sampling kernels, then run beside each other)
+        gate = self.ev_main[i ^ 1] if (self.pipelined and self._main_recorded[i ^ 1]) else None
         with torch.cuda.stream(self.s_met):                 # depth metrics (Z of pred1 read in place)
             self.s_met.wait_event(ready)
+            if gate is not None:
+                self.s_met.wait_event(gate)
             me = _metrics.compute_depth_metrics_batch(pred1, gt_depth, out=met)
             self.ev_met[i].record(self.s_met)
         with torch.cuda.stream(self.s_pre):
             self.s_pre.wait_event(ready)
+            if gate is not None:
+                self.s_pre.wait_event(gate)
             if stacked:
                 raw_both = torch.as_strided(raw1, (2 * B,) + tuple(raw1.shape[1:]), raw1.stride(), raw1.storage_offset())
                 tb = _pre.preprocess_thermal_batch(raw_both, size, path="train", out=pre, histogram=self.histogram)
@@ -263,6 +273,11 @@ class HotPathStep:
             self.s_loss.wait_event(ready)                   # pred / gt / conf
             self.s_loss.wait_event(self.ev_pre[i])
             # the normalisation kernel already summed the thermal gradients: the loss skips its statistics pass
+            if self.pipelined:
+                if not self._main_recorded[i]:
+                    self.ev_main[i].record(self.s_loss)          # creates the CUDA event behind the torch object
+                    self._main_recorded[i] = True
+                lib.t3d_loss_set_main_done_event(self.ev_main[i].cuda_event)
             _loss.fused_thermal_loss_fwd_bwd(pred1, pred2, gt1, gt2, conf1, conf2, t1, t2,
                                              out=lo, thermal_stats=stats,
                                              thermal_replicated=True,   # preprocess_thermal_batch wrote 3 identical planes
