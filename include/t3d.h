@@ -131,6 +131,25 @@ int t3d_loss_fwd_bwd(const float* pred1, const float* pred2,
                      float* out_sample, float* out_batch, double* out_sample_f64,
                      void* workspace, size_t workspace_bytes, void* stream);
 
+/* The same with the pseudo-GT (and, optionally, its confidence) at ANOTHER resolution than the prediction -- the normal
+ * case in training: 512x512 pseudo-GT (scripts/pseudo_gt.py:620) against 224x224 predictions.  The reference resamples
+ * both to the prediction's size first (train_thermal_dustr.py:234-271: F.interpolate(mode='bilinear',
+ * align_corners=False) on [1,3,H,W] / [1,1,H,W] views); here the four bilinear taps are evaluated inside the loss
+ * kernel's loads (same ATen arithmetic), so the resampled pointmaps are never written or re-read.
+ * gt1/gt2 [B,gt_h,gt_w,3]; conf1/conf2 [B,conf_h,conf_w] (NULL -> ones; conf_h x conf_w = H x W for a predicted
+ * confidence, which may take a gradient, = gt_h x gt_w for a pseudo-GT confidence, which never does).
+ * dpred1/dpred2 NULL -> forward only.  Runs on the general tile kernel. */
+int t3d_loss_fwd_bwd_resampled(const float* pred1, const float* pred2,
+                               const float* gt1, const float* gt2, int gt_h, int gt_w,
+                               const float* conf1, const float* conf2, int conf_h, int conf_w,
+                               const float* thermal1, const float* thermal2, int thermal_channels,
+                               float* dpred1, float* dpred2, float* dconf1, float* dconf2,
+                               int B, int H, int W, int flags,
+                               float alpha, float edge_weight, float smoothness_weight, float detail_weight,
+                               float grad_scale,
+                               float* out_sample, float* out_batch, double* out_sample_f64,
+                               void* workspace, size_t workspace_bytes, void* stream);
+
 /* Scheduling hook: `cuda_event` (a cudaEvent_t, or NULL to cancel) is recorded on the stream of the NEXT
  * t3d_loss_fwd_bwd / t3d_loss_fwd call of the calling thread right behind its main kernel, i.e. BEFORE the small
  * second-stage reduction: the moment the machine is free again.  A caller that overlaps consecutive steps lets the

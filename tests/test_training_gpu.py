@@ -100,6 +100,54 @@ def test_plain_loss_path_clamps_confidence_from_below_only(cuda_device):
     assert abs(clamped.loss.item() - res.loss.item()) > 1e-3
 
 
+@pytest.mark.parametrize("multi", [False, True])
+@pytest.mark.parametrize("H,W,GH,GW", [(224, 224, 512, 512), (37, 50, 64, 48), (48, 64, 24, 40)])
+def test_fused_gt_resampling_equals_resample_then_loss(cuda_device, H, W, GH, GW, multi):
+    """The pseudo-GT at another resolution (the normal case: 512x512 vs 224x224, train_thermal_dustr.py:234-271): the
+    taps fused into the loss kernel's loads give what resampling first (F.interpolate semantics, checked above) and
+    then evaluating the loss gives -- loss, components and all gradients -- and both match the reference loop."""
+    from thermal3d_vision_b200 import loss as t3d
+    from thermal3d_vision_b200.training import resample_bilinear
+    B = 2
+    P1, P2, _, _, C1, C2, T1, T2 = ref_loss.make_batch_inputs(B, H, W, seed=H + GW)
+    g = torch.Generator().manual_seed(GH)
+    G1 = torch.randn(B, GH, GW, 3, generator=g); G1[..., 2] = 1.5 + 3 * G1[..., 2].abs()
+    G2 = torch.randn(B, GH, GW, 3, generator=g); G2[..., 2] = 1.5 + 3 * G2[..., 2].abs()
+    GC1, GC2 = 1 + 4 * torch.rand(B, GH, GW, generator=g), 1 + 4 * torch.rand(B, GH, GW, generator=g)
+    d = lambda t: t.to(cuda_device)
+    kw = dict(KW, multi_scale=multi)
+    for conf_src in ("pred", "gt"):
+        cA, cB = (C1, C2) if conf_src == "pred" else (GC1, GC2)
+        q = [d(P1).requires_grad_(), d(P2).requires_grad_()]
+        k = [d(cA).requires_grad_(conf_src == "pred"), d(cB).requires_grad_(conf_src == "pred")]
+        fused = t3d.fused_thermal_loss(q[0], q[1], d(G1), d(G2), k[0], k[1], d(T1), d(T2), **kw)
+        fused.loss.backward()
+        q2 = [d(P1).requires_grad_(), d(P2).requires_grad_()]
+        c2 = [d(cA), d(cB)] if conf_src == "pred" else [resample_bilinear(d(cA), (H, W)), resample_bilinear(d(cB), (H, W))]
+        k2 = [c.requires_grad_(conf_src == "pred") for c in c2]
+        two = t3d.fused_thermal_loss(q2[0], q2[1], resample_bilinear(d(G1), (H, W)), resample_bilinear(d(G2), (H, W)),
+                                     k2[0], k2[1], d(T1), d(T2), **kw)
+        two.loss.backward()
+        torch.testing.assert_close(fused.per_sample[:, :5], two.per_sample[:, :5], rtol=2e-6, atol=1e-7)
+        torch.testing.assert_close(q[0].grad, q2[0].grad, rtol=1e-4, atol=1e-7)
+        torch.testing.assert_close(q[1].grad, q2[1].grad, rtol=1e-4, atol=1e-7)
+        if conf_src == "pred":
+            torch.testing.assert_close(k[0].grad, k2[0].grad, rtol=1e-4, atol=1e-7)
+    # against the reference arithmetic on the CPU (resample with F.interpolate, loss per sample)
+    p1 = P1.clone().requires_grad_()
+    tot = 0.0
+    for i in range(B):
+        g1, g2 = _interp_like_reference(G1[i:i + 1], (H, W))[0], _interp_like_reference(G2[i:i + 1], (H, W))[0]
+        loss, _ = ref_loss.enhanced_thermal_aware_loss_torch(p1[i], P2[i], g1, g2, C1[i], C2[i], T1[i], T2[i], **kw)
+        tot = tot + loss
+    (tot / B).backward()
+    q = d(P1).requires_grad_()
+    r = t3d.fused_thermal_loss(q, d(P2), d(G1), d(G2), d(C1), d(C2), d(T1), d(T2), **kw)
+    r.loss.backward()
+    assert r.loss.item() == pytest.approx((tot / B).item(), rel=1e-5)
+    torch.testing.assert_close(q.grad.cpu(), p1.grad, rtol=1e-4, atol=1e-6)
+
+
 def test_validation_batch_loss(cuda_device):
     from thermal3d_vision_b200.training import validation_batch_loss
     B, H, W = 4, 32, 36

@@ -184,7 +184,27 @@ struct LossArgs {
     float kc;                     // grad_scale / (H W)
     float kE[2], kS[2], kD[2];    // grad_scale * lambda_s * weight / n_s
     float conf_max;               // upper clamp of the confidence: 10 (utils/loss.py:91), +inf with T3D_LOSS_CONF_MIN_ONLY
+    // GT (and GT confidence) at another resolution: bilinear taps fused into the loads (train_thermal_dustr.py:234-271)
+    int gt_h, gt_w;               // size of the gt arrays; 0 = the prediction's size (read directly)
+    int conf_h, conf_w;           // size of the conf arrays; 0 = the prediction's size
 };
+
+// F.interpolate(mode='bilinear', align_corners=False) tap of one output coordinate (ATen: scale = in / out in fp32;
+// src = max(scale * (dst + 0.5) - 0.5, 0); i0 = (int)src; i1 = i0 + (i0 < in - 1); l1 = src - i0; l0 = 1 - l1)
+struct BTap { int i0, i1; float l0, l1; };
+__device__ __forceinline__ BTap btap(int dst, int in, float scale) {
+    const float f = fmaxf(scale * ((float)dst + 0.5f) - 0.5f, 0.f);
+    BTap t;
+    t.i0 = (int)f; t.i1 = t.i0 + ((t.i0 < in - 1) ? 1 : 0);
+    t.l1 = f - (float)t.i0; t.l0 = 1.f - t.l1;
+    return t;
+}
+// one channel-last value: l0y (l0x v00 + l1x v01) + l1y (l0x v10 + l1x v11), as interp_bilinear_kernel (t3d_preprocess.cu)
+__device__ __forceinline__ float bsample(const float* __restrict__ img, int sw, int C, int c, const BTap& ty, const BTap& tx) {
+    const float v00 = __ldg(img + ((size_t)ty.i0 * sw + tx.i0) * C + c), v01 = __ldg(img + ((size_t)ty.i0 * sw + tx.i1) * C + c);
+    const float v10 = __ldg(img + ((size_t)ty.i1 * sw + tx.i0) * C + c), v11 = __ldg(img + ((size_t)ty.i1 * sw + tx.i1) * C + c);
+    return ty.l0 * (tx.l0 * v00 + tx.l1 * v01) + ty.l1 * (tx.l0 * v10 + tx.l1 * v11);
+}
 
 template <bool MULTI>
 constexpr size_t loss_smem_bytes() {
@@ -257,8 +277,11 @@ __global__ void __launch_bounds__(kThreads, MULTI ? 2 : 3) loss_tile_kernel(cons
     const bool thermal_on = a.tch != 0;
 
     const float* __restrict__ pred = a.pred[view] + (size_t)b * plane * 3;
-    const float* __restrict__ gt = a.gt[view] + (size_t)b * plane * 3;
-    const float* __restrict__ conf = a.conf[view] ? a.conf[view] + (size_t)b * plane : nullptr;
+    const bool gt_rs = a.gt_h != 0, conf_rs = a.conf_h != 0;        // block-uniform: bilinear taps instead of direct reads
+    const float* __restrict__ gt = a.gt[view] + (size_t)b * (gt_rs ? (size_t)a.gt_h * a.gt_w : plane) * 3;
+    const float* __restrict__ conf = a.conf[view] ? a.conf[view] + (size_t)b * (conf_rs ? (size_t)a.conf_h * a.conf_w : plane) : nullptr;
+    const float gsy = gt_rs ? (float)a.gt_h / (float)H : 1.f, gsx = gt_rs ? (float)a.gt_w / (float)W : 1.f;
+    const float csy = conf_rs ? (float)a.conf_h / (float)H : 1.f, csx = conf_rs ? (float)a.conf_w / (float)W : 1.f;
     const float* __restrict__ th = thermal_on ? a.thermal[view] + (size_t)b * a.tch * plane : nullptr;
     float* __restrict__ dpred = BWD ? a.dpred[view] + (size_t)b * plane * 3 : nullptr;
     float* __restrict__ dconf = (BWD && a.dconf[view]) ? a.dconf[view] + (size_t)b * plane : nullptr;
@@ -292,13 +315,13 @@ __global__ void __launch_bounds__(kThreads, MULTI ? 2 : 3) loss_tile_kernel(cons
                 const float4* gp = reinterpret_cast<const float4*>(gt + pix * 3);
                 float4 p0 = ldg_stream_f4((const float*)(pp)), p1 = ldg_stream_f4((const float*)(pp + 1)),
                        p2 = ldg_stream_f4((const float*)(pp + 2));
-                float4 g0 = ldg_stream_f4((const float*)(gp)), g1 = ldg_stream_f4((const float*)(gp + 1)),
-                       g2 = ldg_stream_f4((const float*)(gp + 2));
+                float4 g0 = make_float4(0.f, 0.f, 0.f, 0.f), g1 = g0, g2 = g0;
+                if (!gt_rs) { g0 = ldg_stream_f4((const float*)(gp)); g1 = ldg_stream_f4((const float*)(gp + 1)); g2 = ldg_stream_f4((const float*)(gp + 2)); }
                 p[0] = p0.x; p[1] = p0.y; p[2] = p0.z; p[3] = p0.w; p[4] = p1.x; p[5] = p1.y;
                 p[6] = p1.z; p[7] = p1.w; p[8] = p2.x; p[9] = p2.y; p[10] = p2.z; p[11] = p2.w;
                 g[0] = g0.x; g[1] = g0.y; g[2] = g0.z; g[3] = g0.w; g[4] = g1.x; g[5] = g1.y;
                 g[6] = g1.z; g[7] = g1.w; g[8] = g2.x; g[9] = g2.y; g[10] = g2.z; g[11] = g2.w;
-                if (conf) {
+                if (conf && !conf_rs) {
                     float4 cc = ldg_stream_f4(conf + pix);
                     c[0] = cc.x; c[1] = cc.y; c[2] = cc.z; c[3] = cc.w;
                 } else { c[0] = c[1] = c[2] = c[3] = 1.f; }
@@ -307,10 +330,23 @@ __global__ void __launch_bounds__(kThreads, MULTI ? 2 : 3) loss_tile_kernel(cons
                 for (int e = 0; e < 12; ++e) {
                     const bool ok = e < nvalid * 3;
                     p[e] = ok ? ldg_stream_f1(pred + pix * 3 + e) : 0.f;
-                    g[e] = ok ? ldg_stream_f1(gt + pix * 3 + e) : 0.f;
+                    g[e] = (ok && !gt_rs) ? ldg_stream_f1(gt + pix * 3 + e) : 0.f;
                 }
 #pragma unroll
-                for (int e = 0; e < 4; ++e) c[e] = (conf && e < nvalid) ? ldg_stream_f1(conf + pix + e) : 1.f;
+                for (int e = 0; e < 4; ++e) c[e] = (conf && !conf_rs && e < nvalid) ? ldg_stream_f1(conf + pix + e) : 1.f;
+            }
+            if (gt_rs || conf_rs) {                            // taps of this row / these 4 columns
+                const BTap gty = btap(i, a.gt_h, gsy), cty = btap(i, a.conf_h, csy);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    if (e >= nvalid) continue;
+                    if (gt_rs) {
+                        const BTap gtx = btap(j + e, a.gt_w, gsx);
+#pragma unroll
+                        for (int ch = 0; ch < 3; ++ch) g[3 * e + ch] = bsample(gt, a.gt_w, 3, ch, gty, gtx);
+                    }
+                    if (conf_rs && conf) c[e] = bsample(conf, a.conf_w, 1, 0, cty, btap(j + e, a.conf_w, csx));
+                }
             }
             if (thermal_on) load_gray_quad<VEC>(th, a.tch, plane, pix, nvalid, grq);
             float dc[4];
@@ -371,7 +407,7 @@ __global__ void __launch_bounds__(kThreads, MULTI ? 2 : 3) loss_tile_kernel(cons
             if (i >= 0 && i < H && j >= 0 && j < W) {
                 const size_t pix = (size_t)i * W + j;
                 zv = ldg_f1(pred + pix * 3 + 2);
-                gzv = ldg_f1(gt + pix * 3 + 2);
+                gzv = gt_rs ? bsample(gt, a.gt_w, 3, 2, btap(i, a.gt_h, gsy), btap(j, a.gt_w, gsx)) : ldg_f1(gt + pix * 3 + 2);
                 gv = load_gray_px(th, a.tch, plane, pix);
             }
             sz[r][c] = zv; sgz[r][c] = gzv; sg[r][c] = gv;
@@ -851,9 +887,14 @@ int loss_impl(bool bwd, const float* pred1, const float* pred2, const float* gt1
               int tch, const float* ustats1, const float* ustats2, int ustats_tiles, float* dpred1, float* dpred2, float* dconf1, float* dconf2,
               int B, int H, int W, int flags, float alpha, float ew, float sw, float dw, float gscale,
               float* out_sample, float* out_batch, double* out_f64,
-              void* workspace, size_t ws_bytes, void* stream) {
+              void* workspace, size_t ws_bytes, void* stream,
+              int gt_h = 0, int gt_w = 0, int conf_h = 0, int conf_w = 0) {
     if (int rc = check_dims(B, H, W)) return rc;
     T3D_REQUIRE((flags & ~(T3D_LOSS_MULTI_SCALE | T3D_LOSS_CONF_MIN_ONLY)) == 0, "unknown loss flags 0x%x", flags);
+    if (gt_h == H && gt_w == W) gt_h = gt_w = 0;                    // same size: direct reads
+    if (conf_h == H && conf_w == W) conf_h = conf_w = 0;
+    T3D_REQUIRE((gt_h == 0) == (gt_w == 0) && gt_h >= 0 && (conf_h == 0) == (conf_w == 0) && conf_h >= 0, "bad gt / conf size");
+    const bool resampled = gt_h != 0 || conf_h != 0;
     const int multi = (flags & T3D_LOSS_MULTI_SCALE) ? 1 : 0;
     const bool conf_min_only = (flags & T3D_LOSS_CONF_MIN_ONLY) != 0;
     T3D_REQUIRE(pred1 && pred2 && gt1 && gt2, "pred/gt pointers must not be NULL");
@@ -895,6 +936,7 @@ int loss_impl(bool bwd, const float* pred1, const float* pred2, const float* gt1
     la.tiles_x = L.tiles_x; la.tiles_y = L.tiles_y; la.stiles = stiles;
     la.alpha = alpha;
     la.conf_max = conf_min_only ? __int_as_float_host(0x7f800000u) : kConfMax;
+    la.gt_h = gt_h; la.gt_w = gt_w; la.conf_h = conf_h; la.conf_w = conf_w;
     const double N = (double)H * W, n2 = (double)(H / 2) * (W / 2);
     la.kb = (float)((double)gscale / (3.0 * N));
     la.kc = (float)((double)gscale / N);
@@ -904,8 +946,8 @@ int loss_impl(bool bwd, const float* pred1, const float* pred2, const float* gt1
     la.kE[1] = (float)((double)gscale * ew * l2); la.kS[1] = (float)((double)gscale * sw * l2);
     la.kD[1] = (float)((double)gscale * dw * l2);
 
-    bool vec = (W % 4 == 0) && t3d_aligned16(pred1) && t3d_aligned16(pred2) && t3d_aligned16(gt1) &&
-               t3d_aligned16(gt2) && t3d_aligned16(conf1) && t3d_aligned16(conf2) &&
+    bool vec = (W % 4 == 0) && t3d_aligned16(pred1) && t3d_aligned16(pred2) && (gt_h != 0 || (t3d_aligned16(gt1) &&
+               t3d_aligned16(gt2))) && (conf_h != 0 || (t3d_aligned16(conf1) && t3d_aligned16(conf2))) &&
                t3d_aligned16(thermal1) && t3d_aligned16(thermal2) && t3d_aligned16(dpred1) &&
                t3d_aligned16(dpred2) && t3d_aligned16(dconf1) && t3d_aligned16(dconf2);
     const bool ms = multi && thermal_on;
@@ -918,7 +960,7 @@ int loss_impl(bool bwd, const float* pred1, const float* pred2, const float* gt1
     }();
     const float* partials2 = nullptr;
     int tiles2 = 0;
-    if (vec && thermal_on && march_rows > 0 && !conf_min_only && (!ms || (H >= 4 && W >= 4))) {
+    if (vec && thermal_on && march_rows > 0 && !conf_min_only && !resampled && (!ms || (H >= 4 && W >= 4))) {
         // fast path: TMA-fed warp-marching kernel (t3d_loss_march.cu); multi-scale: the half-resolution terms run
         // first as their own pass (t3d_loss_scale2.cu) and hand their gradient to the marching kernel
         MarchArgs ma;
@@ -1021,6 +1063,24 @@ int t3d_loss_fwd_bwd(const float* pred1, const float* pred2, const float* gt1, c
                      thermal_stats1, thermal_stats2, stats_tiles, dpred1, dpred2, dconf1, dconf2, B, H, W, multi_scale, alpha, edge_weight,
                      smoothness_weight, detail_weight, grad_scale, out_sample, out_batch, out_sample_f64,
                      workspace, workspace_bytes, stream);
+}
+
+int t3d_loss_fwd_bwd_resampled(const float* pred1, const float* pred2, const float* gt1, const float* gt2, int gt_h, int gt_w,
+                               const float* conf1, const float* conf2, int conf_h, int conf_w,
+                               const float* thermal1, const float* thermal2, int thermal_channels,
+                               float* dpred1, float* dpred2, float* dconf1, float* dconf2,
+                               int B, int H, int W, int flags,
+                               float alpha, float edge_weight, float smoothness_weight, float detail_weight,
+                               float grad_scale, float* out_sample, float* out_batch, double* out_sample_f64,
+                               void* workspace, size_t workspace_bytes, void* stream) {
+    T3D_REQUIRE(gt_h >= 1 && gt_w >= 1, "bad gt size");
+    T3D_REQUIRE((conf1 == nullptr && conf2 == nullptr) || (conf_h >= 1 && conf_w >= 1), "bad conf size");
+    T3D_REQUIRE(!(dconf1 || dconf2) || (conf_h == H && conf_w == W), "a confidence that takes a gradient has the prediction's size");
+    const bool bwd = dpred1 != nullptr && dpred2 != nullptr;
+    return loss_impl(bwd, pred1, pred2, gt1, gt2, conf1, conf2, thermal1, thermal2, thermal_channels,
+                     nullptr, nullptr, 0, dpred1, dpred2, dconf1, dconf2, B, H, W, flags, alpha, edge_weight,
+                     smoothness_weight, detail_weight, grad_scale, out_sample, out_batch, out_sample_f64,
+                     workspace, workspace_bytes, stream, gt_h, gt_w, conf1 ? conf_h : 0, conf1 ? conf_w : 0);
 }
 
 int t3d_loss_fwd(const float* pred1, const float* pred2, const float* gt1, const float* gt2,

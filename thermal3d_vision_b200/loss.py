@@ -81,7 +81,34 @@ def _launch(bwd, p1, p2, g1, g2, c1, c2, t1, t2, need_dconf, alpha, ew, sw, dw, 
             st_tiles = int(st1.shape[1])
         else:
             st1 = st2 = None
+    resampled = tuple(g1.shape[1:3]) != (H, W) or (c1 is not None and tuple(c1.shape[1:3]) != (H, W))
     dp1 = dp2 = dc1 = dc2 = None
+    if resampled:
+        # pseudo-GT (and its confidence) at another resolution: bilinear taps inside the loss kernel's loads
+        # (train_thermal_dustr.py:234-271); a confidence at the GT's size never takes a gradient
+        gh, gw = int(g1.shape[1]), int(g1.shape[2])
+        ch, cw = (int(c1.shape[1]), int(c1.shape[2])) if c1 is not None else (H, W)
+        if bwd:
+            dp1 = out.get("dpred1"); dp2 = out.get("dpred2")
+            dp1 = torch.empty_like(p1) if dp1 is None else dp1
+            dp2 = torch.empty_like(p2) if dp2 is None else dp2
+            if need_dconf[0] and (ch, cw) == (H, W):
+                dc1 = out.get("dconf1")
+                dc1 = torch.empty(B, H, W, dtype=torch.float32, device=dev) if dc1 is None else dc1
+            if need_dconf[1] and (ch, cw) == (H, W):
+                dc2 = out.get("dconf2")
+                dc2 = torch.empty(B, H, W, dtype=torch.float32, device=dev) if dc2 is None else dc2
+        rc = lib.t3d_loss_fwd_bwd_resampled(
+            _lib.ptr(p1), _lib.ptr(p2), _lib.ptr(g1), _lib.ptr(g2), gh, gw, _lib.ptr(c1), _lib.ptr(c2), ch, cw,
+            _lib.ptr(t1), _lib.ptr(t2), tch, _lib.ptr(dp1), _lib.ptr(dp2), _lib.ptr(dc1), _lib.ptr(dc2),
+            B, H, W, flags, alpha, ew, sw, dw, grad_scale,
+            _lib.ptr(per_sample), _lib.ptr(batch), _lib.ptr(f64), _lib.ptr(ws), ws.numel(), stream)
+        _lib.check(rc, "t3d_loss_fwd_bwd_resampled")
+        if bwd and rescale_invalid:
+            rc = lib.t3d_loss_rescale_invalid(_lib.ptr(dp1), _lib.ptr(dp2), _lib.ptr(dc1), _lib.ptr(dc2),
+                                              _lib.ptr(per_sample), _lib.ptr(batch), B, H, W, stream)
+            _lib.check(rc, "t3d_loss_rescale_invalid")
+        return per_sample, batch, dp1, dp2, dc1, dc2
     if bwd:
         dp1 = out.get("dpred1"); dp2 = out.get("dpred2")
         if dp1 is None:
@@ -191,13 +218,18 @@ def fused_thermal_loss(pred_pts1, pred_pts2, gt_pts1, gt_pts2, confidences1=None
     c1, c2, t1, t2 = (_prep(t, dev) for t in (confidences1, confidences2, thermal_img1, thermal_img2))
     if p1.dim() != 4 or p1.shape[-1] != 3:
         raise ValueError(f"pointmaps must be [B,H,W,3], got {tuple(p1.shape)}")
-    for name, t in (("pred_pts2", p2), ("gt_pts1", g1), ("gt_pts2", g2)):
-        if t.shape != p1.shape:
-            raise ValueError(f"{name} shape {tuple(t.shape)} != pred_pts1 shape {tuple(p1.shape)}")
+    if p2.shape != p1.shape:
+        raise ValueError(f"pred_pts2 shape {tuple(p2.shape)} != pred_pts1 shape {tuple(p1.shape)}")
     B, H, W, _ = p1.shape
+    # the pseudo-GT may come at another resolution (train_thermal_dustr.py:234-271 resamples it to the prediction's
+    # size; here the taps are fused into the kernel's loads): [B,gh,gw,3], both views alike
+    if g1.dim() != 4 or g1.shape[-1] != 3 or g1.shape[0] != B or g2.shape != g1.shape:
+        raise ValueError(f"gt pointmaps must be two [B,h,w,3] tensors with B={B}, got {tuple(g1.shape)} / {tuple(g2.shape)}")
     for name, t in (("confidences1", c1), ("confidences2", c2)):
-        if t is not None and tuple(t.shape) != (B, H, W):
-            raise ValueError(f"{name} must be [B,H,W]={B, H, W}, got {tuple(t.shape)}")
+        if t is not None and tuple(t.shape) not in ((B, H, W), (B,) + tuple(g1.shape[1:3])):
+            raise ValueError(f"{name} must be [B,H,W]={B, H, W} (or the GT's size), got {tuple(t.shape)}")
+    if c1 is not None and c2 is not None and c1.shape != c2.shape:
+        raise ValueError("confidences1 / confidences2 must have the same size")
     if (t1 is None) != (t2 is None):
         t1 = t2 = None                                     # utils/loss.py:116: both or nothing
     if t1 is not None:

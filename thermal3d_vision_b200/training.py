@@ -43,15 +43,15 @@ def training_batch_loss(pred_pts1, pred_pts2, gt_pts1, gt_pts2, pred_conf1=None,
 
     Returns FusedLossResult (loss = mean over valid samples; gradients flow to pred_pts and, when they are
     the chosen confidence, to pred_conf).  Defaults are the CLI defaults (:52-55)."""
-    H, W = pred_pts1.shape[1], pred_pts1.shape[2]
-    if tuple(gt_pts1.shape[1:3]) != (H, W):                     # :234-271
-        gt_pts1, gt_pts2 = resample_bilinear(gt_pts1, (H, W)), resample_bilinear(gt_pts2, (H, W))
-        if gt_conf1 is not None:
-            gt_conf1 = resample_bilinear(gt_conf1, (H, W))
-        if gt_conf2 is not None:
-            gt_conf2 = resample_bilinear(gt_conf2, (H, W))
+    # pseudo-GT at another resolution than the prediction (:234-271, the normal case: 512x512 vs 224x224): the
+    # bilinear taps of the pointmaps -- and of the GT confidence when that is the one used -- are evaluated inside the
+    # loss kernel's loads, the resampled arrays are never materialised (`resample_bilinear` is the stand-alone form)
     conf1 = pred_conf1 if pred_conf1 is not None else gt_conf1   # :274-275 (ones when both are None)
     conf2 = pred_conf2 if pred_conf2 is not None else gt_conf2
+    if (conf1 is None) != (conf2 is None) or (conf1 is not None and conf1.shape != conf2.shape):
+        H, W = pred_pts1.shape[1], pred_pts1.shape[2]            # mixed sources: bring the GT-sized one to the prediction's size
+        conf1 = resample_bilinear(conf1, (H, W)) if conf1 is not None and tuple(conf1.shape[1:3]) != (H, W) else conf1
+        conf2 = resample_bilinear(conf2, (H, W)) if conf2 is not None and tuple(conf2.shape[1:3]) != (H, W) else conf2
     # torch.clamp(conf, min=1e-5) (:278-279) composes idempotently with the loss's own clamp to [1e-5, 10]
     # (same values, same inclusive gradient mask), so it needs no extra pass.
     if not use_thermal_aware_loss:
@@ -67,9 +67,7 @@ def training_batch_loss(pred_pts1, pred_pts2, gt_pts1, gt_pts2, pred_conf1=None,
 def validation_batch_loss(pred_pts1, pred_pts2, gt_pts1, gt_pts2):
     """train_thermal_dustr.py:465-492: per sample (mean|p1-g1| + mean|p2-g2|) / 2, averaged over the finite,
     positive samples.  Returns FusedLossResult with that mean in `.loss`."""
-    H, W = pred_pts1.shape[1], pred_pts1.shape[2]
-    if tuple(gt_pts1.shape[1:3]) != (H, W):
-        gt_pts1, gt_pts2 = resample_bilinear(gt_pts1, (H, W)), resample_bilinear(gt_pts2, (H, W))
+    # (a GT of another size is resampled inside the kernel's loads, :465-481)
     # with confidence 1 and alpha 0 the basic term is mean|p1-g1| + mean|p2-g2| (utils/loss.py:81-98)
     r = _loss.fused_thermal_loss(pred_pts1, pred_pts2, gt_pts1, gt_pts2, None, None, None, None, alpha=0.0,
                                  multi_scale=False, batch_mean=True)
