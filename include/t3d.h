@@ -324,6 +324,43 @@ int t3d_sobel_enhance_fwd(const float* x, const float* params, int B, int C, int
 int t3d_sobel_enhance_bwd_params(const float* x, const float* params, const float* dout, int B, int C, int H, int W,
                                  int local_norm, float* dparams, void* workspace, size_t workspace_bytes, void* stream);
 
+/* ------------------------------------------- experimental fire-scene pipeline */
+/* Image operators of thermal_dustr_inference_for_experiment.py:62-377.  The reference builds
+ * them from OpenCV / NumPy / SciPy calls; these restate the libraries' algorithms: byte / integer results are
+ * bit-identical (CLAHE, Canny, histogram), float results agree to rounding (Sobel, bilateral). */
+/* np.percentile(x[b], (pct_lo, pct_hi)), float64 results [B][2] (:95); workspace: t3d_contrast_normalize_workspace_bytes(B). */
+int t3d_percentiles_f32(const float* x, int B, int n, double pct_lo, double pct_hi, double* percentiles,
+                        void* workspace, size_t workspace_bytes, void* stream);
+/* cv2.createCLAHE(clipLimit, (tiles_x, tiles_y)).apply(src) on uint8 images [B,H,W] (:108-109, :220-221). */
+size_t t3d_clahe_workspace_bytes(int B, int tiles_x, int tiles_y);
+int t3d_clahe_u8(const unsigned char* src, unsigned char* dst, int B, int H, int W, double clip_limit, int tiles_x, int tiles_y,
+                 void* workspace, size_t workspace_bytes, void* stream);
+/* cv2.Canny(src, low, high) on one uint8 image (aperture 3, L1 gradient; :135, :225).  Synchronises `stream`. */
+size_t t3d_canny_workspace_bytes(int H, int W);
+int t3d_canny_u8(const unsigned char* src, unsigned char* dst, int H, int W, double low_thresh, double high_thresh,
+                 void* workspace, size_t workspace_bytes, void* stream);
+/* cv2.Sobel(src, CV_32F, 1, 0, ksize=3) -> dx and cv2.Sobel(src, CV_32F, 0, 1, ksize=3) -> dy (:228-229). */
+int t3d_sobel3_f32(const float* src, float* dx, float* dy, int H, int W, void* stream);
+/* np.histogram(x, bins=100, range=(0, 1))[0] -> hist100 (uint32[100]) (:188). */
+int t3d_histogram100(const float* x, size_t n, unsigned int* hist100, void* stream);
+/* cv2.bilateralFilter(src, d, sigma_color, sigma_space), float32, channels LAST [H,W,channels], channels 1 or 3
+ * (:273, :375); scratch2: 2 floats. */
+int t3d_bilateral_f32(const float* src, float* dst, int H, int W, int channels, int d, double sigma_color, double sigma_space,
+                      float* scratch2, void* stream);
+/* depth_refinement_with_outlier_removal step 1 (:335-356): stats2 <- {nanmean, nanstd}; out <- depth with the 3-sigma
+ * outliers replaced by the median of their 5x5 inlier neighbours (the mean when there is none); mask (nullable). */
+int t3d_depth_outlier_median(const float* depth, float* out, int H, int W, float* stats2, unsigned char* mask, void* stream);
+/* Per-pixel stages of preprocess_fire_scene_thermal (:62-152) and advanced_fire_scene_processing (:154-282); the host
+ * side (thermal3d_vision_b200/fire.py) strings them together with the operators above. */
+int t3d_fire_gray(const float* img_chw, int channels, int H, int W, float* gray, void* stream);
+int t3d_fire_norm_u8(const float* gray, int H, int W, const double* percentiles2, unsigned char* base_u8, unsigned char* norm_u8, void* stream);
+int t3d_fire_compose(const float* gray, int H, int W, const double* percentiles2, const unsigned char* clahe_u8,
+                     const unsigned char* canny_u8, const float* noise, float* out_chw, void* stream);
+int t3d_fire_adv_u8(const float* gray, int H, int W, unsigned char* inverted_u8, unsigned char* gray_u8, void* stream);
+int t3d_fire_adv_compose(const float* gray, int H, int W, double fire_threshold, const unsigned char* clahe_u8,
+                         const unsigned char* canny_u8, const float* noise, float* out_hwc, float* scratch, void* stream);
+int t3d_hwc_to_chw_clip01(const float* hwc, int H, int W, float* chw, void* stream);
+
 /* ------------------------------------------------------ step result packing */
 /* The packed step vector: T3D_RESULT_SIZE doubles.
  *   [0] sum over VALID samples of the per-sample loss, [1..4] sums of basic/edge/smoothness/detail,

@@ -189,6 +189,47 @@ def gen_evaluate(ref):
     np.savez_compressed(os.path.join(OUT, "evaluate_kat.npz"), **out)
 
 
+def gen_fire(ref):
+    """Experimental fire-scene pipeline (thermal_dustr_inference_for_experiment.py:62-377): the LIVE reference functions
+    (np.random seeded before each call) and the stock cv2 / numpy operators on the frames of ref_fire.make_fire_frame."""
+    import importlib
+    import sys
+    import cv2
+    from oracle import ref_fire
+    sys.path.insert(0, ref.root)
+    try:
+        m = importlib.import_module("thermal_dustr_inference_for_experiment")
+    finally:
+        sys.path.remove(ref.root)
+    out = {"versions": versions(ref), "sizes": np.array([[96, 128], [75, 100]])}
+    for (h, w) in out["sizes"]:
+        tag = f"{h}x{w}"
+        f = ref_fire.make_fire_frame(int(h), int(w), seed=int(h))
+        np.random.seed(11)
+        out["pre_" + tag] = m.preprocess_fire_scene_thermal(torch.from_numpy(f)).numpy()
+        np.random.seed(12)
+        out["adv_" + tag] = m.advanced_fire_scene_processing(torch.from_numpy(f)).numpy()
+        rng = np.random.default_rng(int(w))
+        d = (3 + rng.standard_normal((int(h), int(w)))).astype(np.float32)
+        d[rng.random(d.shape) < 0.01] += 30
+        d[2:5, 3:6] += 40                                            # a clump: windows with few / no inliers
+        out["depth_" + tag] = d
+        out["refined_" + tag] = m.depth_refinement_with_outlier_removal(d.copy(), f, guided_filter=False)
+        g = f[0]
+        u8 = (g * 255).astype(np.uint8)
+        out["u8_" + tag] = u8
+        for clip in (2.5, 3.0):
+            out[f"clahe{clip}_" + tag] = cv2.createCLAHE(clipLimit=clip, tileGridSize=(8, 8)).apply(u8)
+        for lo in (30, 50):
+            out[f"canny{lo}_" + tag] = cv2.Canny(u8, lo, 150)
+        out["sobelx_" + tag] = cv2.Sobel(g, cv2.CV_32F, 1, 0, ksize=3)
+        out["sobely_" + tag] = cv2.Sobel(g, cv2.CV_32F, 0, 1, ksize=3)
+        out["hist_" + tag] = np.histogram(g.flatten(), bins=100, range=(0, 1))[0]
+        out["bil5_" + tag] = cv2.bilateralFilter(d, 5, 50, 50)
+        out["pct_" + tag] = np.array(np.percentile(g, (5, 95)))
+    np.savez_compressed(os.path.join(OUT, "fire_kat.npz"), **out)
+
+
 def main():
     ref = reference_bridge.load()
     os.makedirs(OUT, exist_ok=True)
@@ -197,6 +238,7 @@ def main():
     gen_metrics(ref)
     gen_sobel(ref)
     gen_evaluate(ref)
+    gen_fire(ref)
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 

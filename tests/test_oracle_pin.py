@@ -88,3 +88,46 @@ def test_evaluate_golden_is_the_live_reference(ref):
             per.append(ref_metrics.compute_depth_metrics(pm[..., 2].numpy(), batch["depth1"][i].numpy()))
     acc = ref_metrics.accumulate_dataset(per)
     np.testing.assert_allclose([acc[k] for k in fake_eval.KEYS], gold["tuple_tensor"], rtol=1e-6)
+
+
+def test_fire_restatements_equal_live_libraries(ref):
+    """oracle/ref_fire.py: the NumPy restatements of cv2 CLAHE / Canny / np.histogram / scipy find_peaks are identical
+    to the live libraries, Sobel / bilateral agree to rounding; the three reference functions restated on the stock
+    libraries equal the live reference (np.random seeded); tests/golden/fire_kat.npz is what the live reference gives."""
+    import importlib, os, sys
+    from scipy.signal import find_peaks
+    from oracle import ref_fire
+    cv2 = ref.cv2
+    rng = np.random.default_rng(0)
+    for (h, w) in ((96, 128), (75, 100), (224, 224)):
+        f = ref_fire.make_fire_frame(h, w, seed=h)
+        u8 = np.clip(f[0] * 255 + rng.integers(-6, 6, (h, w)), 0, 255).astype(np.uint8)
+        for clip in (2.5, 3.0):
+            assert np.array_equal(cv2.createCLAHE(clipLimit=clip, tileGridSize=(8, 8)).apply(u8), ref_fire.clahe_u8(u8, clip))
+        for lo in (30, 50):
+            assert np.array_equal(cv2.Canny(u8, lo, 150), ref_fire.canny_u8(u8, lo, 150))
+        assert np.array_equal(np.histogram(f[0].flatten(), bins=100, range=(0, 1))[0], ref_fire.histogram100(f[0]))
+        dx, dy = ref_fire.sobel3(f[0])
+        assert np.abs(dx - cv2.Sobel(f[0], cv2.CV_32F, 1, 0, ksize=3)).max() < 1e-6
+        assert np.abs(dy - cv2.Sobel(f[0], cv2.CV_32F, 0, 1, ksize=3)).max() < 1e-6
+        d = (3 + rng.standard_normal((h, w))).astype(np.float32)
+        np.testing.assert_allclose(ref_fire.bilateral(d, 5, 50, 50), cv2.bilateralFilter(d, 5, 50, 50), rtol=2e-6, atol=2e-6)
+    for _ in range(300):
+        hh = rng.integers(0, rng.integers(3, 60), 100)
+        assert list(find_peaks(hh, height=hh.max() * 0.3, distance=10)[0]) == list(ref_fire.find_peaks_height_distance(hh, hh.max() * 0.3, 10))
+    sys.path.insert(0, ref.root)
+    try:
+        m = importlib.import_module("thermal_dustr_inference_for_experiment")
+    finally:
+        sys.path.remove(ref.root)
+    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "fire_kat.npz"))
+    for (h, w) in ((96, 128), (75, 100)):
+        tag = f"{h}x{w}"
+        f = ref_fire.make_fire_frame(h, w, seed=h)
+        np.random.seed(11); live = m.preprocess_fire_scene_thermal(torch.from_numpy(f)).numpy()
+        np.random.seed(11); nz = np.random.rand(h, w)
+        assert np.array_equal(live, gold["pre_" + tag]) and np.array_equal(ref_fire.preprocess_fire_scene_thermal(f, nz), live)
+        np.random.seed(12); live = m.advanced_fire_scene_processing(torch.from_numpy(f)).numpy()
+        np.random.seed(12); nz = np.random.rand(h, w)
+        assert np.array_equal(live, gold["adv_" + tag]) and np.array_equal(ref_fire.advanced_fire_scene_processing(f, nz), live)
+        assert np.array_equal(ref_fire.depth_refinement(gold["depth_" + tag]), gold["refined_" + tag])

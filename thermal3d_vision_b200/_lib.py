@@ -71,6 +71,21 @@ _SIGNATURES = {
     "t3d_sobel_workspace_bytes": (C.c_size_t, [C.c_int] * 4),
     "t3d_sobel_enhance_fwd": (C.c_int, [c_ptr, c_ptr] + [C.c_int] * 5 + [c_ptr, c_ptr, C.c_size_t, c_ptr]),
     "t3d_sobel_enhance_bwd_params": (C.c_int, [c_ptr, c_ptr, c_ptr] + [C.c_int] * 5 + [c_ptr, c_ptr, C.c_size_t, c_ptr]),
+    "t3d_percentiles_f32": (C.c_int, [c_ptr, C.c_int, C.c_int, C.c_double, C.c_double, c_ptr, c_ptr, C.c_size_t, c_ptr]),
+    "t3d_clahe_workspace_bytes": (C.c_size_t, [C.c_int] * 3),
+    "t3d_clahe_u8": (C.c_int, [c_ptr, c_ptr, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, c_ptr, C.c_size_t, c_ptr]),
+    "t3d_canny_workspace_bytes": (C.c_size_t, [C.c_int] * 2),
+    "t3d_canny_u8": (C.c_int, [c_ptr, c_ptr, C.c_int, C.c_int, C.c_double, C.c_double, c_ptr, C.c_size_t, c_ptr]),
+    "t3d_sobel3_f32": (C.c_int, [c_ptr, c_ptr, c_ptr, C.c_int, C.c_int, c_ptr]),
+    "t3d_histogram100": (C.c_int, [c_ptr, C.c_size_t, c_ptr, c_ptr]),
+    "t3d_bilateral_f32": (C.c_int, [c_ptr, c_ptr, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, c_ptr, c_ptr]),
+    "t3d_depth_outlier_median": (C.c_int, [c_ptr, c_ptr, C.c_int, C.c_int, c_ptr, c_ptr, c_ptr]),
+    "t3d_fire_gray": (C.c_int, [c_ptr, C.c_int, C.c_int, C.c_int, c_ptr, c_ptr]),
+    "t3d_fire_norm_u8": (C.c_int, [c_ptr, C.c_int, C.c_int, c_ptr, c_ptr, c_ptr, c_ptr]),
+    "t3d_fire_compose": (C.c_int, [c_ptr, C.c_int, C.c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),
+    "t3d_fire_adv_u8": (C.c_int, [c_ptr, C.c_int, C.c_int, c_ptr, c_ptr, c_ptr]),
+    "t3d_fire_adv_compose": (C.c_int, [c_ptr, C.c_int, C.c_int, C.c_double, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),
+    "t3d_hwc_to_chw_clip01": (C.c_int, [c_ptr, C.c_int, C.c_int, c_ptr, c_ptr]),
     "t3d_pack_step_result": (C.c_int, [c_ptr, c_ptr, C.c_int, C.c_int, c_ptr, c_ptr]),
     "t3d_step_epilogue": (C.c_int, [c_ptr] * 7 + [C.c_int] * 5 + [c_ptr, C.c_int] + [c_ptr, c_ptr]),
     "t3d_rescale_global": (C.c_int, [c_ptr] * 6 + [C.c_int] * 3 + [c_ptr]),

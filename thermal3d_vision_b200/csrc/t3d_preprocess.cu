@@ -354,7 +354,7 @@ FpctWs fpct_ws(void* base, int B) {
 
 __global__ void __launch_bounds__(t3d_select::kThreads, 1)
 fpct_sample_kernel(const float* __restrict__ x, int n, int channels, const int* __restrict__ close_flag,
-                   unsigned int* __restrict__ bracket) {
+                   unsigned int* __restrict__ bracket, float q_lo, float q_hi) {
     __shared__ float key[kFSamp];
     __shared__ t3d_select::Smem sm;
     __shared__ int s_valid;
@@ -389,7 +389,7 @@ fpct_sample_kernel(const float* __restrict__ x, int n, int channels, const int* 
     for (int w = 0; w < 2; ++w) {
         unsigned int lo = 1u, hi = 0u;                         // no bracket -> F3 falls back
         if (mv >= 64) {
-            const float q = w ? 0.98f : 0.02f;
+            const float q = w ? q_hi : q_lo;                  // quantile as a fraction (0.02 / 0.98 for enhance_thermal_contrast)
             const int r = (int)(q * (float)(mv - 1) + 0.5f);
             const int d = (int)ceilf(9.0f * sqrtf((float)mv * q * (1.0f - q))) + 2;
             lo = t3d_select::float_key(t3d_select::select_rank(sm, kFSamp, (unsigned)max(r - d, 0), get));
@@ -451,7 +451,8 @@ fpct_classify_kernel(const float* __restrict__ x, int n, int channels, const int
 // one CTA per image; out_p[b] = {p2, p98} as np.percentile(plane, (2, 98)) would return (fp64)
 __global__ void __launch_bounds__(t3d_select::kThreads, 1)
 fpct_select_kernel(const float* __restrict__ x, int n, int channels, const int* __restrict__ close_flag,
-                   const int* __restrict__ counters, const unsigned int* __restrict__ cand, double* __restrict__ out_p) {
+                   const int* __restrict__ counters, const unsigned int* __restrict__ cand, double* __restrict__ out_p,
+                   double pct_lo, double pct_hi) {
     extern __shared__ unsigned int skeys[];                     // kFCandCap keys
     __shared__ t3d_select::Smem sm;
     const int b = blockIdx.x, tid = threadIdx.x;
@@ -464,8 +465,8 @@ fpct_select_kernel(const float* __restrict__ x, int n, int channels, const int* 
         return;
     }
     unsigned int k[2]; double g[2];
-    percentile_ranks(count, 2.0, &k[0], &g[0]);
-    percentile_ranks(count, 98.0, &k[1], &g[1]);
+    percentile_ranks(count, pct_lo, &k[0], &g[0]);               // (2, 98) for enhance_thermal_contrast
+    percentile_ranks(count, pct_hi, &k[1], &g[1]);
     float os[4];
     for (int w = 0; w < 2; ++w) {                               // block-uniform control flow throughout
         const unsigned int r0 = k[w], r1 = min(k[w] + 1, (unsigned)count - 1);
@@ -929,6 +930,40 @@ int t3d_preprocess_stats_tiles(int dst_h, int dst_w) {
     return (dst_h >= 1 && dst_w >= 4 && dst_w % 4 == 0) ? kNormBands : 0;
 }
 
+// np.percentile(plane, (pct_lo, pct_hi)) of B float planes: sampled brackets -> counting / collecting pass -> exact
+// select among the candidates (full radix select as the fallback); percentiles [B][2] float64.
+static int run_float_percentiles(const float* x, int B, int channels, int n, const int* close_flags, double pct_lo, double pct_hi,
+                                 double* percentiles, const FpctWs& w, cudaStream_t st) {
+    const int count = (channels == 3) ? n : n * channels;
+    T3D_CUDA(cudaMemsetAsync(w.counters, 0, (size_t)B * 8 * sizeof(int), st));
+    static bool attr_done[kT3dMaxDevices] = {};
+    bool& attr_set = attr_done[t3d_device_slot()];
+    if (!attr_set) {
+        T3D_CUDA(cudaFuncSetAttribute(fpct_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFCandCap * (int)sizeof(unsigned int)));
+        attr_set = true;
+    }
+    T3D_LAUNCH("fpct_sample_kernel", st, fpct_sample_kernel<<<B, t3d_select::kThreads, 0, st>>>(
+        x, n, channels, close_flags, w.bracket, (float)(pct_lo / 100.0), (float)(pct_hi / 100.0)));
+    dim3 gc((unsigned)max(1, min(kFChunks, (count + 4095) / 4096)), (unsigned)B);
+    T3D_LAUNCH("fpct_classify_kernel", st, fpct_classify_kernel<<<gc, kFThreads, 0, st>>>(x, n, channels, close_flags, w.bracket, w.counters, w.cand));
+    T3D_LAUNCH("fpct_select_kernel", st, fpct_select_kernel<<<B, t3d_select::kThreads, kFCandCap * sizeof(unsigned int), st>>>(
+        x, n, channels, close_flags, w.counters, w.cand, percentiles, pct_lo, pct_hi));
+    return T3D_OK;
+}
+
+/* np.percentile(x[b], (pct_lo, pct_hi)) for B float32 arrays of n values (method 'linear', float64 results);
+ * workspace as t3d_contrast_normalize_workspace_bytes(B). */
+int t3d_percentiles_f32(const float* x, int B, int n, double pct_lo, double pct_hi, double* percentiles,
+                        void* workspace, size_t workspace_bytes, void* stream) {
+    T3D_REQUIRE(x && percentiles && workspace, "NULL pointer");
+    T3D_REQUIRE(B >= 1 && n >= 1 && (double)n < 2.0e9, "bad dims");
+    T3D_REQUIRE(pct_lo > 0.0 && pct_lo < pct_hi && pct_hi < 100.0, "percentiles must satisfy 0 < lo < hi < 100");
+    const FpctWs w = fpct_ws(workspace, B);
+    if (workspace_bytes < w.total) { t3d_set_error("workspace too small"); return T3D_ERR_WORKSPACE; }
+    T3D_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 15u) == 0, "workspace must be 16-byte aligned");
+    return run_float_percentiles(x, B, 1, n, nullptr, pct_lo, pct_hi, percentiles, w, reinterpret_cast<cudaStream_t>(stream));
+}
+
 size_t t3d_contrast_normalize_workspace_bytes(int B) {
     if (B < 1) return 0;
     return fpct_ws(nullptr, B).total;
@@ -950,18 +985,7 @@ int t3d_contrast_normalize_f32(const float* x, int B, int channels, int n, float
         dim3 g((unsigned)min((n + 255) / 256, 32), (unsigned)B);
         T3D_LAUNCH("channels_close_kernel", st, channels_close_kernel<<<g, 256, 0, st>>>(x, n, close_flags));
     }
-    T3D_CUDA(cudaMemsetAsync(w.counters, 0, (size_t)B * 8 * sizeof(int), st));
-    static bool attr_done[kT3dMaxDevices] = {};
-    bool& attr_set = attr_done[t3d_device_slot()];
-    if (!attr_set) {
-        T3D_CUDA(cudaFuncSetAttribute(fpct_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFCandCap * (int)sizeof(unsigned int)));
-        attr_set = true;
-    }
-    T3D_LAUNCH("fpct_sample_kernel", st, fpct_sample_kernel<<<B, t3d_select::kThreads, 0, st>>>(x, n, channels, close_flags, w.bracket));
-    dim3 gc((unsigned)max(1, min(kFChunks, (count + 4095) / 4096)), (unsigned)B);
-    T3D_LAUNCH("fpct_classify_kernel", st, fpct_classify_kernel<<<gc, kFThreads, 0, st>>>(x, n, channels, close_flags, w.bracket, w.counters, w.cand));
-    T3D_LAUNCH("fpct_select_kernel", st, fpct_select_kernel<<<B, t3d_select::kThreads, kFCandCap * sizeof(unsigned int), st>>>(
-        x, n, channels, close_flags, w.counters, w.cand, percentiles));
+    if (int rc = run_float_percentiles(x, B, channels, n, close_flags, 2.0, 98.0, percentiles, w, st)) return rc;
     dim3 g2((unsigned)min((count + 255) / 256, 64), (unsigned)B);
     T3D_LAUNCH("normalize_f32_kernel", st, normalize_f32_kernel<<<g2, 256, 0, st>>>(x, n, channels, close_flags, percentiles, out, out_channels, count));
     return T3D_OK;
