@@ -154,3 +154,25 @@ def test_npy_matches_numpy(ingest, tmp_path):
     pi = str(tmp_path / "i.npy"); np.save(pi, np.zeros(shape, np.int32))
     with pytest.raises(ingest.IngestError):
         ingest.read_npy_batch_f32([pi], shape, pin=False)
+
+
+def test_malformed_npy_headers_are_errors_not_crashes(ingest, tmp_path):
+    """Hand-made corrupt .npy headers: every one comes back as an IngestError from the worker pool (no exception
+    escapes a worker thread, no wrapped shape product passes for the expected element count)."""
+    def write(name, header: bytes, payload: bytes = b"\\0" * 64):
+        hdr = header + b" " * ((64 - (10 + len(header) + 1) % 64) % 64) + b"\\n"
+        p = str(tmp_path / name)
+        with open(p, "wb") as fh:
+            fh.write(b"\\x93NUMPY\\x01\\x00" + len(hdr).to_bytes(2, "little") + hdr + payload)
+        return p
+    bad = [
+        write("no_colon.npy", b"{'descr' '<f4', 'fortran_order': False, 'shape': (4,), }"),
+        write("fortran_blank.npy", b"{'descr': '<f4', 'shape': (4,), 'fortran_order':"),
+        write("neg.npy", b"{'descr': '<f4', 'fortran_order': False, 'shape': (-4, -1), }"),
+        write("junk_shape.npy", b"{'descr': '<f4', 'fortran_order': False, 'shape': (x, y), }"),
+        write("overflow.npy", b"{'descr': '<f4', 'fortran_order': False, 'shape': (4294967296, 4294967296, 4), }"),
+        write("no_shape_close.npy", b"{'descr': '<f4', 'fortran_order': False, 'shape': (4, "),
+    ]
+    for p in bad:
+        with pytest.raises(ingest.IngestError):
+            ingest.read_npy_batch_f32([p, p], (4,), threads=2, pin=False)

@@ -100,9 +100,36 @@ class T3DError(RuntimeError):
     pass
 
 
-def build(verbose: bool = False) -> str:
-    """Compile libt3d_sm100.so in-tree with nvcc for sm_100a (cross-compiles without a GPU)."""
-    out = subprocess.run(["make", "-C", CSRC_DIR, "-j8"], capture_output=True, text=True)
+def source_hash() -> str:
+    """SHA-256 over every source the library is built from (kernels, headers, Makefile)."""
+    import glob
+    import hashlib
+    h = hashlib.sha256()
+    files = sorted(glob.glob(os.path.join(CSRC_DIR, "*.cu")) + glob.glob(os.path.join(CSRC_DIR, "*.cuh")) +
+                   glob.glob(os.path.join(_HERE, "..", "include", "*.h")) + [os.path.join(CSRC_DIR, "Makefile")])
+    for f in files:
+        h.update(os.path.basename(f).encode())
+        with open(f, "rb") as fh:
+            h.update(fh.read())
+    return h.hexdigest()
+
+
+def build(verbose: bool = False, force: bool = False) -> str:
+    """Compile libt3d_sm100.so in-tree with nvcc for sm_100a (cross-compiles without a GPU).
+
+    Incremental by default (make); `force=True` recompiles every object (`make -B`).  The hash of the sources the
+    library was built from is kept next to it: a library whose recorded hash differs from the tree's sources (objects
+    shipped from elsewhere, clock skew) is rebuilt from scratch as well."""
+    stamp = LIB_PATH + ".srchash"
+    want = source_hash()
+    have = open(stamp).read().strip() if os.path.isfile(stamp) else ""
+    if os.path.isfile(LIB_PATH) and have != want:
+        force = True
+    cmd = ["make", "-C", CSRC_DIR, "-j8"] + (["-B"] if force else [])
+    out = subprocess.run(cmd, capture_output=True, text=True)
+    if out.returncode == 0:
+        with open(stamp, "w") as fh:
+            fh.write(want + "\n")
     if verbose or out.returncode != 0:
         print(out.stdout[-4000:])
         print(out.stderr[-4000:])

@@ -12,6 +12,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <exception>
 #include <thread>
 #include <vector>
 
@@ -149,7 +150,8 @@ int parse_npy(const uint8_t* d, size_t n, char descr[16], int* fortran, int* ndi
     auto find_val = [&](const char* key) -> size_t {
         const size_t k = h.find(key);
         if (k == std::string::npos) return k;
-        return h.find(':', k) + 1;
+        const size_t colon = h.find(':', k);
+        return (colon == std::string::npos) ? colon : colon + 1;
     };
     size_t p = find_val("'descr'");
     if (p == std::string::npos) return fail(T3D_INGEST_CORRUPT, ".npy: no descr");
@@ -160,7 +162,9 @@ int parse_npy(const uint8_t* d, size_t n, char descr[16], int* fortran, int* ndi
     memcpy(descr, h.data() + q0 + 1, q1 - q0 - 1); descr[q1 - q0 - 1] = 0;
     p = find_val("'fortran_order'");
     if (p == std::string::npos) return fail(T3D_INGEST_CORRUPT, ".npy: no fortran_order");
-    *fortran = h.compare(h.find_first_not_of(' ', p), 4, "True") == 0 ? 1 : 0;
+    const size_t fo = h.find_first_not_of(' ', p);
+    if (fo == std::string::npos) return fail(T3D_INGEST_CORRUPT, ".npy: bad fortran_order");
+    *fortran = h.compare(fo, 4, "True") == 0 ? 1 : 0;
     p = find_val("'shape'");
     if (p == std::string::npos) return fail(T3D_INGEST_CORRUPT, ".npy: no shape");
     const size_t s0 = h.find('(', p), s1 = h.find(')', p);
@@ -172,7 +176,10 @@ int parse_npy(const uint8_t* d, size_t n, char descr[16], int* fortran, int* ndi
         if (c >= s1) break;
         if (*ndim >= 8) return fail(T3D_INGEST_UNSUPPORTED, ".npy: more than 8 dimensions");
         char* end = nullptr;
-        shape[(*ndim)++] = strtoll(h.c_str() + c, &end, 10);
+        const long long dim = strtoll(h.c_str() + c, &end, 10);
+        if (end == h.c_str() + c) return fail(T3D_INGEST_CORRUPT, ".npy: bad shape");        // not a number: no progress
+        if (dim < 0) return fail(T3D_INGEST_CORRUPT, ".npy: negative dimension");
+        shape[(*ndim)++] = dim;
         c = (size_t)(end - h.c_str());
     }
     *off = hoff + hlen;
@@ -201,7 +208,11 @@ int read_npy_f32(const char* path, float* out, size_t elems) {
     char descr[16]; int fortran, ndim; int64_t shape[8]; size_t off;
     if (int rc = parse_npy(buf.data(), buf.size(), descr, &fortran, &ndim, shape, &off)) return rc;
     size_t count = 1;
-    for (int i = 0; i < ndim; ++i) count *= (size_t)shape[i];
+    for (int i = 0; i < ndim; ++i) {                        // overflow-checked product (a wrapped product could equal `elems`)
+        const size_t dim = (size_t)shape[i];
+        if (dim != 0 && count > SIZE_MAX / dim) return fail(T3D_INGEST_CORRUPT, "%s: shape overflows", path);
+        count *= dim;
+    }
     if (count != elems) return fail(T3D_INGEST_CORRUPT, "%s holds %zu elements, expected %zu", path, count, elems);
     if (fortran && ndim > 1) return fail(T3D_INGEST_UNSUPPORTED, "%s: Fortran-order arrays are not supported", path);
     const uint8_t* src = buf.data() + off;
@@ -231,7 +242,13 @@ int run_pool(int count, int threads, int* status, Fn fn) {
         for (;;) {
             const int i = next.fetch_add(1);
             if (i >= count) break;
-            st[i] = fn(i);
+            try {                                   // an exception escaping a worker thread would terminate the process
+                st[i] = fn(i);
+            } catch (const std::exception& e) {
+                st[i] = fail(T3D_INGEST_CORRUPT, "item %d: %s", i, e.what());
+            } catch (...) {
+                st[i] = fail(T3D_INGEST_CORRUPT, "item %d: unknown exception", i);
+            }
             if (st[i]) msgs[i] = g_err;            // thread-local message of the worker
         }
     };
