@@ -194,6 +194,11 @@ depth_extract_kernel(const PixelSrc s, int pred_offset, float* __restrict__ vz, 
     if (tid < 2) scount[tid] = 0;
     if (tid < 5) sred[tid] = 0;
     __syncthreads();
+    // the CTA's stage is full (spatially coherent depth: a whole chunk inside the bracket): append straight to the list
+    auto spill = [&](int s, unsigned int key) {
+        const int g = atomicAdd(&counters[8 * b + 6 + s], 1);
+        if (g < kCandCap) cand[((size_t)b * 2 + s) * kCandCap + g] = key; else atomicExch(&counters[8 * b + 3], 1);
+    };
     int nv = 0, pnan = 0, gnan = 0, lt_g = 0, lt_p = 0;
     const int per = (n + gridDim.x - 1) / gridDim.x;
     const int i_begin = blockIdx.x * per, i_end = min(i_begin + per, n);
@@ -230,12 +235,12 @@ depth_extract_kernel(const PixelSrc s, int pred_offset, float* __restrict__ vz, 
         if (fg) {                       // one shared-memory atomic per thread with candidates (~1 in 4)
             int slot = atomicAdd(&scount[0], __popc(fg));
 #pragma unroll
-            for (int u = 0; u < U; ++u) if (fg & (1u << u)) { if (slot < kCtaCand) scand[0][slot] = kgs[u]; ++slot; }
+            for (int u = 0; u < U; ++u) if (fg & (1u << u)) { if (slot < kCtaCand) scand[0][slot] = kgs[u]; else spill(0, kgs[u]); ++slot; }
         }
         if (fp) {
             int slot = atomicAdd(&scount[1], __popc(fp));
 #pragma unroll
-            for (int u = 0; u < U; ++u) if (fp & (1u << u)) { if (slot < kCtaCand) scand[1][slot] = kps[u]; ++slot; }
+            for (int u = 0; u < U; ++u) if (fp & (1u << u)) { if (slot < kCtaCand) scand[1][slot] = kps[u]; else spill(1, kps[u]); ++slot; }
         }
     }
     nv = __reduce_add_sync(0xffffffffu, nv); pnan = __reduce_add_sync(0xffffffffu, pnan);
@@ -252,13 +257,10 @@ depth_extract_kernel(const PixelSrc s, int pred_offset, float* __restrict__ vz, 
     __syncthreads();
     if (tid < 5 && sred[tid]) atomicAdd(&c[tid < 3 ? tid : tid + 1], sred[tid]);
     if (tid < 2) {
-        const int k = scount[tid];
-        if (k > kCtaCand) { atomicExch(&c[3], 1); sbase[tid] = -1; }         // local overflow -> fallback
-        else {
-            const int base = k ? atomicAdd(&c[6 + tid], k) : 0;
-            if (base + k > kCandCap) { atomicExch(&c[3], 1); sbase[tid] = -1; }
-            else sbase[tid] = base;
-        }
+        const int k = min(scount[tid], kCtaCand);        // what did not fit the stage went to the list directly (spill)
+        const int base = k ? atomicAdd(&c[6 + tid], k) : 0;
+        if (base + k > kCandCap) { atomicExch(&c[3], 1); sbase[tid] = -1; }      // list overflow (heavy ties) -> exact fallback
+        else sbase[tid] = base;
     }
     __syncthreads();
 #pragma unroll
@@ -305,6 +307,11 @@ depth_extract_fast_kernel(const float* __restrict__ pred, const float* __restric
     if (tid < 2) scount[tid] = 0;
     if (tid < 5) sred[tid] = 0;
     __syncthreads();
+    // the CTA's stage is full (spatially coherent depth: a whole chunk inside the bracket): append straight to the list
+    auto spill = [&](int s, unsigned int key) {
+        const int g = atomicAdd(&counters[8 * b + 6 + s], 1);
+        if (g < kCandCap) cand[((size_t)b * 2 + s) * kCandCap + g] = key; else atomicExch(&counters[8 * b + 3], 1);
+    };
     int nv = 0, pnan = 0, lt_g = 0, lt_p = 0;
     const int nq = n >> 2, per = (nq + gridDim.x - 1) / gridDim.x;
     const int q_begin = blockIdx.x * per, q_end = min(q_begin + per, nq);
@@ -313,7 +320,10 @@ depth_extract_fast_kernel(const float* __restrict__ pred, const float* __restric
         if (RESAMPLE) {                                   // W % 4 == 0: the quad lies in one row
             const int y = (4 * q) / W, x = 4 * q - y * W;
             const float* row = gimg + stab[W + y];
-            g = make_float4(__ldg(row + stab[x]), __ldg(row + stab[x + 1]), __ldg(row + stab[x + 2]), __ldg(row + stab[x + 3]));
+            // same width (only the height differs, e.g. 512x512 GT for 384x512 predictions): the column map is the
+            // identity and the quad is one aligned 128-bit load of the source row (gt_w % 4 == 0 with W)
+            if (gt_w == W) g = __ldg(reinterpret_cast<const float4*>(row + x));
+            else g = make_float4(__ldg(row + stab[x]), __ldg(row + stab[x + 1]), __ldg(row + stab[x + 2]), __ldg(row + stab[x + 3]));
         } else {
             g = __ldg(g4 + q);
         }
@@ -343,12 +353,12 @@ depth_extract_fast_kernel(const float* __restrict__ pred, const float* __restric
         if (fg) {                       // one shared-memory atomic per thread with candidates
             int slot = atomicAdd(&scount[0], __popc(fg));
 #pragma unroll
-            for (int u = 0; u < 4; ++u) if (fg & (1u << u)) { if (slot < kCtaCand) scand[0][slot] = kgs[u]; ++slot; }
+            for (int u = 0; u < 4; ++u) if (fg & (1u << u)) { if (slot < kCtaCand) scand[0][slot] = kgs[u]; else spill(0, kgs[u]); ++slot; }
         }
         if (fp) {
             int slot = atomicAdd(&scount[1], __popc(fp));
 #pragma unroll
-            for (int u = 0; u < 4; ++u) if (fp & (1u << u)) { if (slot < kCtaCand) scand[1][slot] = kps[u]; ++slot; }
+            for (int u = 0; u < 4; ++u) if (fp & (1u << u)) { if (slot < kCtaCand) scand[1][slot] = kps[u]; else spill(1, kps[u]); ++slot; }
         }
     }
     nv = __reduce_add_sync(0xffffffffu, nv); pnan = __reduce_add_sync(0xffffffffu, pnan);
@@ -363,13 +373,10 @@ depth_extract_fast_kernel(const float* __restrict__ pred, const float* __restric
     __syncthreads();
     if (tid < 5 && sred[tid]) atomicAdd(&c[tid < 3 ? tid : tid + 1], sred[tid]);
     if (tid < 2) {
-        const int k = scount[tid];
-        if (k > kCtaCand) { atomicExch(&c[3], 1); sbase[tid] = -1; }         // local overflow -> fallback
-        else {
-            const int base = k ? atomicAdd(&c[6 + tid], k) : 0;
-            if (base + k > kCandCap) { atomicExch(&c[3], 1); sbase[tid] = -1; }
-            else sbase[tid] = base;
-        }
+        const int k = min(scount[tid], kCtaCand);        // what did not fit the stage went to the list directly (spill)
+        const int base = k ? atomicAdd(&c[6 + tid], k) : 0;
+        if (base + k > kCandCap) { atomicExch(&c[3], 1); sbase[tid] = -1; }      // list overflow (heavy ties) -> exact fallback
+        else sbase[tid] = base;
     }
     __syncthreads();
 #pragma unroll
@@ -555,6 +562,7 @@ metrics_sum_fast_kernel(const float* __restrict__ zplane, const float* __restric
         if (RESAMPLE) {                                   // W % 4 == 0: the quad lies in one row
             const int y = (4 * q) / W, x = 4 * q - y * W;
             const float* row = gimg + stab[W + y];
+            if (gt_w == W) return __ldg(reinterpret_cast<const float4*>(row + x));         // identity column map
             return make_float4(__ldg(row + stab[x]), __ldg(row + stab[x + 1]), __ldg(row + stab[x + 2]), __ldg(row + stab[x + 3]));
         }
         return ldg_stream_f4(gimg + 4 * (size_t)q);
