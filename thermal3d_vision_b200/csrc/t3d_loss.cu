@@ -152,6 +152,130 @@ __global__ void __launch_bounds__(kSThreads, 4) thermal_stats_kernel(const Stats
     }
 }
 
+// Fast path of the statistics (W % 4 == 0, 16-byte aligned planes): a warp marches down a 128-pixel strip of a
+// 32-row band, 4 pixels per lane, 128-bit loads, vertical neighbours in registers, horizontal ones from shuffles
+// (the strip's right edge: one 8-byte load); the half-resolution sums ride along on row pairs.  No shared memory.
+// MODE 0: one plane, 1: three planes, 2: three bit-identical planes (plane 0 is read, gray = gray3(v, v, v)).
+constexpr int kSMRows = 32, kSMWarps = 4;
+struct SRow { float g[4], e0, e1; };     // gray of the lane's quad and of the two pixels right of it
+
+template <bool MULTI, int MODE>
+__global__ void __launch_bounds__(kSMWarps * 32) thermal_stats_march_kernel(const StatsArgs a, int nbands, int nstrips) {
+    const int lane = threadIdx.x & 31;
+    const int per_img = nbands * nstrips;
+    const int item = blockIdx.x * kSMWarps + (threadIdx.x >> 5);
+    if (item >= a.B * 2 * per_img) return;
+    const int img = item / per_img, t = item - img * per_img;
+    const int band = t / nstrips, strip = t - band * nstrips;
+    const int b = img >> 1, view = img & 1;
+    const int H = a.H, W = a.W, h2 = H >> 1;
+    const size_t plane = (size_t)H * W;
+    const float* __restrict__ th = a.thermal[view] + (size_t)b * a.tch * plane;
+    const int ra = band * kSMRows, rb = min(ra + kSMRows, H);
+    const int x0 = strip * 128 + 4 * lane;
+    const bool active = x0 < W, has_right = x0 + 4 < W;
+    const bool edge_lane = active && has_right && lane == 31;       // the pixels right of the quad belong to the next strip
+    const float* __restrict__ px = th + (active ? x0 : 0);
+
+    auto gray = [&](float c0, float c1, float c2) { return MODE == 0 ? c0 : gray3(c0, c1, c2); };
+    struct Raw { float4 c0, c1, c2; float2 h0, h1, h2; };
+    auto fetch = [&](int y, Raw& r) {                                // issue the loads of row y (nothing if outside the image)
+        if (y < H && active) {
+            const float* p = px + (size_t)y * W;
+            r.c0 = ldg_stream_f4(p);
+            if (MODE == 1) { r.c1 = ldg_stream_f4(p + plane); r.c2 = ldg_stream_f4(p + 2 * plane); }
+            if (edge_lane) {
+                r.h0 = __ldg(reinterpret_cast<const float2*>(p + 4));
+                if (MODE == 1) { r.h1 = __ldg(reinterpret_cast<const float2*>(p + plane + 4)); r.h2 = __ldg(reinterpret_cast<const float2*>(p + 2 * plane + 4)); }
+            }
+        }
+    };
+    auto finish = [&](const Raw& r, SRow& o) {                       // gray values + right neighbours of a fetched row
+        if (MODE == 1) {
+            o.g[0] = gray(r.c0.x, r.c1.x, r.c2.x); o.g[1] = gray(r.c0.y, r.c1.y, r.c2.y);
+            o.g[2] = gray(r.c0.z, r.c1.z, r.c2.z); o.g[3] = gray(r.c0.w, r.c1.w, r.c2.w);
+        } else {
+            o.g[0] = gray(r.c0.x, r.c0.x, r.c0.x); o.g[1] = gray(r.c0.y, r.c0.y, r.c0.y);
+            o.g[2] = gray(r.c0.z, r.c0.z, r.c0.z); o.g[3] = gray(r.c0.w, r.c0.w, r.c0.w);
+        }
+        o.e0 = __shfl_down_sync(0xffffffffu, o.g[0], 1);
+        o.e1 = MULTI ? __shfl_down_sync(0xffffffffu, o.g[1], 1) : 0.f;
+        if (edge_lane) {
+            if (MODE == 1) { o.e0 = gray(r.h0.x, r.h1.x, r.h2.x); o.e1 = gray(r.h0.y, r.h1.y, r.h2.y); }
+            else { o.e0 = gray(r.h0.x, r.h0.x, r.h0.x); o.e1 = gray(r.h0.y, r.h0.y, r.h0.y); }
+        }
+        if (!has_right) { o.e0 = o.g[3]; o.e1 = o.g[3]; }           // zero-padded last column: dx == 0
+    };
+    auto dx_sum = [&](const SRow& c) { return fabsf(c.g[1] - c.g[0]) + fabsf(c.g[2] - c.g[1]) + fabsf(c.g[3] - c.g[2]) + fabsf(c.e0 - c.g[3]); };
+    auto dy_sum = [&](const SRow& c, const SRow& n) { return fabsf(n.g[0] - c.g[0]) + fabsf(n.g[1] - c.g[1]) + fabsf(n.g[2] - c.g[2]) + fabsf(n.g[3] - c.g[3]); };
+    auto pool = [&](float a0, float a1, float b0, float b1) { return 0.25f * (((a0 + a1) + b0) + b1); };
+    struct Pooled { float c0, c1, cr; };
+    auto pool_rows = [&](const SRow& u, const SRow& v) {
+        Pooled p;
+        p.c0 = pool(u.g[0], u.g[1], v.g[0], v.g[1]); p.c1 = pool(u.g[2], u.g[3], v.g[2], v.g[3]);
+        p.cr = has_right ? pool(u.e0, u.e1, v.e0, v.e1) : p.c1;     // zero-padded last pooled column
+        return p;
+    };
+
+    float s[4] = {0.f, 0.f, 0.f, 0.f};
+    // rows ra, ra+1 first; then per pair (y, y+1): rows y+2, y+3 were fetched two pairs ago (four rows of loads in
+    // flight per lane), are finished now, and the pair is evaluated
+    Raw qa0 = {}, qa1 = {}, qb0 = {}, qb1 = {};
+    SRow r0, r1, r2, r3;
+    r1 = SRow{{0.f, 0.f, 0.f, 0.f}, 0.f, 0.f}; r2 = r1; r3 = r1;
+    const int y_end = rb + 2;                                        // rows rb, rb+1: the pooled row below the band
+    fetch(ra, qa0); fetch(ra + 1, qa1);
+    fetch(ra + 2, qb0); fetch(ra + 3, qb1);
+    finish(qa0, r0);
+    if (ra + 1 < H) finish(qa1, r1);
+    if (ra + 4 < y_end) { fetch(ra + 4, qa0); fetch(ra + 5, qa1); }
+    Pooled pc = {0.f, 0.f, 0.f};
+    if (MULTI && (ra >> 1) < h2) pc = pool_rows(r0, r1);
+    auto pair = [&](int y, Raw& f0, Raw& f1) {                       // f0, f1: the fetched rows y+2, y+3; refilled with y+6, y+7
+        const bool has2 = y + 2 < H, has3 = y + 3 < H;
+        if (has2) finish(f0, r2);
+        if (has3) finish(f1, r3);
+        if (y + 6 < y_end) { fetch(y + 6, f0); fetch(y + 7, f1); }
+        if (active) {                                                // rows y+10, y+11 on their way into L2 (no register cost)
+#pragma unroll
+            for (int d = 10; d < 12; ++d)
+                if (y + d < min(y_end, H)) {
+                    const float* p = px + (size_t)(y + d) * W;
+                    asm volatile("prefetch.global.L2 [%0];" :: "l"(p));
+                    if (MODE == 1) { asm volatile("prefetch.global.L2 [%0];" :: "l"(p + plane)); asm volatile("prefetch.global.L2 [%0];" :: "l"(p + 2 * plane)); }
+                }
+        }
+        // scale 1: rows y and y+1 (zero-padded last row: dy == 0)
+        s[0] += dx_sum(r0);
+        if (y + 1 < H) s[1] += dy_sum(r0, r1);
+        if (y + 1 < rb) {
+            s[0] += dx_sum(r1);
+            if (has2) s[1] += dy_sum(r1, r2);
+        }
+        if (MULTI) {
+            const int I = y >> 1;
+            if (I < h2) {
+                s[2] += fabsf(pc.c1 - pc.c0) + fabsf(pc.cr - pc.c1);
+                if (I + 1 < h2) {                                    // rows y+2, y+3 exist
+                    const Pooled pn = pool_rows(r2, r3);
+                    s[3] += fabsf(pn.c0 - pc.c0) + fabsf(pn.c1 - pc.c1);
+                    pc = pn;
+                }
+            }
+        }
+        r0 = r2; r1 = r3;
+    };
+    for (int y = ra; y < rb; y += 4) {                               // ra even, rb even or == H
+        pair(y, qb0, qb1);
+        if (y + 2 < rb) pair(y + 2, qa0, qa1);
+    }
+    if (!active) { s[0] = 0.f; s[1] = 0.f; s[2] = 0.f; s[3] = 0.f; }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) s[k] = warp_sum(s[k]);
+    if (lane == 0)
+        *reinterpret_cast<float4*>(a.partials + (((size_t)view * a.B + b) * per_img + t) * 4) = make_float4(s[0], s[1], s[2], s[3]);
+}
+
 // out_stats[B][2][2][2] = means (public API of t3d_thermal_grad_stats)
 __global__ void thermal_stats_finalize_kernel(const float* __restrict__ partials, int stiles, int B,
                                               int H, int W, int multi, float* __restrict__ out) {
@@ -817,6 +941,7 @@ struct WsLayout {
     size_t stats_partials, loss_partials, counter, total;
     size_t s2_partials, s2_dzp;        // multi-scale only (appended: the other offsets do not depend on `multi`)
     int stiles_x, stiles_y, tiles_x, tiles_y, s2_tiles_x, s2_tiles_y;
+    int sm_bands, sm_strips;           // work items per image-view of the marching statistics kernel
 };
 
 WsLayout ws_layout(int B, int H, int W, int multi = 0) {
@@ -825,7 +950,9 @@ WsLayout ws_layout(int B, int H, int W, int multi = 0) {
     L.tiles_x = (W + kTW - 1) / kTW;    L.tiles_y = (H + kTH - 1) / kTH;
     size_t off = 0;
     L.counter = off;        off += 256;
-    L.stats_partials = off; off += t3d_align_up((size_t)B * 2 * L.stiles_x * L.stiles_y * 4 * sizeof(float), 256);
+    L.sm_bands = (H + kSMRows - 1) / kSMRows; L.sm_strips = (W + 127) / 128;
+    const size_t stats_tiles = (size_t)max(L.stiles_x * L.stiles_y, L.sm_bands * L.sm_strips);
+    L.stats_partials = off; off += t3d_align_up((size_t)B * 2 * stats_tiles * 4 * sizeof(float), 256);
     // sized for the tile kernel (16-row tiles) and the marching kernel (>= 8-row bands)
     L.loss_partials = off;  off += t3d_align_up((size_t)B * 2 * L.tiles_x * ((H + 7) / 8) * kNTerms * sizeof(float), 256);
     t3d_scale2_tiles(H, W, &L.s2_tiles_x, &L.s2_tiles_y);
@@ -849,6 +976,16 @@ int check_dims(int B, int H, int W) {
     return T3D_OK;
 }
 
+template <bool MULTI>
+int launch_stats_march(const StatsArgs& sa, int nbands, int nstrips, cudaStream_t st) {
+    const int items = sa.B * 2 * nbands * nstrips;
+    const int grid = (items + kSMWarps - 1) / kSMWarps;
+    if (sa.replicated) T3D_LAUNCH("thermal_stats_march_kernel", st, (thermal_stats_march_kernel<MULTI, 2><<<grid, kSMWarps * 32, 0, st>>>(sa, nbands, nstrips)));
+    else if (sa.tch == 3) T3D_LAUNCH("thermal_stats_march_kernel", st, (thermal_stats_march_kernel<MULTI, 1><<<grid, kSMWarps * 32, 0, st>>>(sa, nbands, nstrips)));
+    else T3D_LAUNCH("thermal_stats_march_kernel", st, (thermal_stats_march_kernel<MULTI, 0><<<grid, kSMWarps * 32, 0, st>>>(sa, nbands, nstrips)));
+    return T3D_OK;
+}
+
 template <bool MULTI, bool VEC>
 int launch_stats(const StatsArgs& sa, cudaStream_t st) {
     const int grid = sa.B * 2 * sa.tiles_x * sa.tiles_y;
@@ -856,15 +993,20 @@ int launch_stats(const StatsArgs& sa, cudaStream_t st) {
     return T3D_OK;
 }
 
+// *stiles_out = partial sums per image-view this run leaves in `partials` ([view][b][stiles][4])
 int run_stats(const float* t1, const float* t2, int tch, int B, int H, int W, int multi,
-              float* partials, const WsLayout& L, cudaStream_t st, int replicated = 0) {
+              float* partials, const WsLayout& L, cudaStream_t st, int replicated, int* stiles_out) {
     StatsArgs sa;
     sa.replicated = (replicated && tch == 3) ? 1 : 0;
     sa.thermal[0] = t1; sa.thermal[1] = t2; sa.partials = partials;
     sa.B = B; sa.H = H; sa.W = W; sa.tch = tch; sa.tiles_x = L.stiles_x; sa.tiles_y = L.stiles_y;
     const bool vec = (W % 4 == 0) && t3d_aligned16(t1) && t3d_aligned16(t2);
-    if (multi) return vec ? launch_stats<true, true>(sa, st) : launch_stats<true, false>(sa, st);
-    return vec ? launch_stats<false, true>(sa, st) : launch_stats<false, false>(sa, st);
+    if (vec) {
+        *stiles_out = L.sm_bands * L.sm_strips;
+        return multi ? launch_stats_march<true>(sa, L.sm_bands, L.sm_strips, st) : launch_stats_march<false>(sa, L.sm_bands, L.sm_strips, st);
+    }
+    *stiles_out = L.stiles_x * L.stiles_y;
+    return multi ? launch_stats<true, false>(sa, st) : launch_stats<false, false>(sa, st);
 }
 
 template <bool MULTI, bool VEC, bool BWD>
@@ -919,11 +1061,12 @@ int loss_impl(bool bwd, const float* pred1, const float* pred2, const float* gt1
     T3D_CUDA(cudaMemsetAsync(counter, 0, 2 * sizeof(unsigned int), st));   // [0] finalize ticket, [1] work queue
     // thermal-gradient statistics: supplied by the caller (fused into the preprocessing) or computed here
     const bool user_stats = thermal_on && !multi && ustats1 && ustats2 && ustats_tiles > 0;
-    const float* stats_v[2] = {stats_partials, stats_partials + (size_t)B * L.stiles_x * L.stiles_y * 4};
-    int stiles = L.stiles_x * L.stiles_y;
+    const float* stats_v[2] = {stats_partials, stats_partials};
+    int stiles = 0;
     if (user_stats) { stats_v[0] = ustats1; stats_v[1] = ustats2; stiles = ustats_tiles; }
     else if (thermal_on) {
-        if (int rc = run_stats(thermal1, thermal2, tch, B, H, W, multi, stats_partials, L, st, replicated)) return rc;
+        if (int rc = run_stats(thermal1, thermal2, tch, B, H, W, multi, stats_partials, L, st, replicated, &stiles)) return rc;
+        stats_v[1] = stats_partials + (size_t)B * stiles * 4;
     }
 
     LossArgs la;
@@ -968,7 +1111,10 @@ int loss_impl(bool bwd, const float* pred1, const float* pred2, const float* gt1
             ma.pred[v] = la.pred[v]; ma.gt[v] = la.gt[v]; ma.conf[v] = la.conf[v]; ma.thermal[v] = la.thermal[v];
             ma.dpred[v] = la.dpred[v]; ma.dconf[v] = la.dconf[v]; ma.dzp[v] = nullptr;
         }
-        if (ms) {
+        // multi-scale with one staged thermal plane: both scales in one pass over the rows (loss_march_ms_kernel)
+        static const bool ms_one_pass = [] { const char* e = getenv("T3D_MS_ONE_PASS"); return e ? atoi(e) != 0 : true; }();
+        const bool fused_ms = ms && ms_one_pass && (tch == 1 || replicated);
+        if (ms && !fused_ms) {
             Scale2Args sa;
             float* dzp = reinterpret_cast<float*>(ws + L.s2_dzp);
             for (int v = 0; v < 2; ++v) {
@@ -988,16 +1134,19 @@ int loss_impl(bool bwd, const float* pred1, const float* pred2, const float* gt1
         // bands of march_rows rows (a band re-reads the row above and the row below it: taller = less overfetch), the
         // last ~1/8 of the image in 8-row bands queued behind all the large ones (shorter tail of the persistent grid)
         static const int tail_div = [] { const char* e = getenv("T3D_MARCH_TAIL"); const int v = e ? atoi(e) : 8; return v < 0 ? 0 : v; }();
-        const int small_target = tail_div > 0 ? ((H / tail_div + 7) / 8) * 8 : 0;
-        ma.rows_l = march_rows; ma.rows_s = 8;
-        ma.nbands_l = (small_target > 0) ? max(0, H - small_target) / march_rows : (H + march_rows - 1) / march_rows;
-        if (small_target == 0) { ma.nbands_s = 0; /* the last large band may be ragged: handle it as one small band */
-            if (ma.nbands_l * march_rows > H) { ma.nbands_l -= 1; ma.rows_s = march_rows; ma.nbands_s = 1; } }
-        else ma.nbands_s = (H - ma.nbands_l * march_rows + 7) / 8;
+        // (one-pass multi-scale: a band brings 4 halo rows instead of 2 and must start on an even row: 16-row tail bands)
+        const int rows_l = fused_ms ? ((march_rows + 1) & ~1) : march_rows, rows_s = fused_ms ? 16 : 8;
+        const int small_rows = tail_div > 0 ? ((H / tail_div + rows_s - 1) / rows_s) * rows_s : 0;
+        ma.rows_l = rows_l; ma.rows_s = rows_s;
+        ma.nbands_l = (small_rows > 0) ? max(0, H - small_rows) / rows_l : (H + rows_l - 1) / rows_l;
+        if (small_rows == 0) { ma.nbands_s = 0; /* the last large band may be ragged: handle it as one small band */
+            if (ma.nbands_l * rows_l > H) { ma.nbands_l -= 1; ma.rows_s = rows_l; ma.nbands_s = 1; } }
+        else ma.nbands_s = (H - ma.nbands_l * rows_l + rows_s - 1) / rows_s;
         ma.nstrips = (W + 127) / 128;
         ma.alpha = alpha; ma.kb = la.kb; ma.kc = la.kc; ma.kE = la.kE[0]; ma.kS = la.kS[0]; ma.kD = la.kD[0];
+        ma.kE2 = la.kE[1]; ma.kS2 = la.kS[1]; ma.kD2 = la.kD[1];
         n_partials = (ma.nbands_l + ma.nbands_s) * ma.nstrips;
-        rc = t3d_launch_loss_march(ma, bwd, st);
+        rc = fused_ms ? t3d_launch_loss_march_ms(ma, bwd, st) : t3d_launch_loss_march(ma, bwd, st);
     } else if (bwd) {
         if (ms) rc = vec ? launch_loss<true, true, true>(la, st) : launch_loss<true, false, true>(la, st);
         else    rc = vec ? launch_loss<false, true, true>(la, st) : launch_loss<false, false, true>(la, st);
@@ -1045,8 +1194,9 @@ int t3d_thermal_grad_stats(const float* thermal1, const float* thermal2, int the
     if (workspace_bytes < L.total) { t3d_set_error("workspace too small"); return T3D_ERR_WORKSPACE; }
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     float* partials = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + L.stats_partials);
-    if (int rc = run_stats(thermal1, thermal2, thermal_channels, B, H, W, multi_scale, partials, L, st)) return rc;
-    T3D_LAUNCH("thermal_stats_finalize_kernel", st, thermal_stats_finalize_kernel<<<B * 2, 32, 0, st>>>(partials, L.stiles_x * L.stiles_y, B, H, W, multi_scale, out_stats));
+    int stiles = 0;
+    if (int rc = run_stats(thermal1, thermal2, thermal_channels, B, H, W, multi_scale, partials, L, st, 0, &stiles)) return rc;
+    T3D_LAUNCH("thermal_stats_finalize_kernel", st, thermal_stats_finalize_kernel<<<B * 2, 32, 0, st>>>(partials, stiles, B, H, W, multi_scale, out_stats));
     return T3D_OK;
 }
 

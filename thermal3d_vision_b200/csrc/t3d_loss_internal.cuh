@@ -16,6 +16,7 @@ struct MarchArgs {
     // tail of the persistent grid: a warp spends ~20-30 us on a large item)
     int rows_l, nbands_l, rows_s, nbands_s, nstrips;
     float alpha, kb, kc, kE, kS, kD;
+    float kE2, kS2, kD2;           // scale-2 constants of the one-pass multi-scale kernel
     const float* dzp[2];           // multi-scale: per view [B][H/2][W/2], added to d/d(pred z) of each cell's 4 pixels (or NULL)
 };
 
@@ -33,3 +34,5 @@ int t3d_launch_loss_scale2(const Scale2Args& a, bool bwd, cudaStream_t st);
 
 // requires: W % 4 == 0, all pointers 16-byte aligned, tch in {1, 3}, single scale
 int t3d_launch_loss_march(const MarchArgs& a, bool bwd, cudaStream_t st);
+// multi-scale, full and half resolution in one pass (tch == 1 or replicated planes; H >= 4; even band heights)
+int t3d_launch_loss_march_ms(const MarchArgs& a, bool bwd, cudaStream_t st);
