@@ -333,7 +333,7 @@ def time_steps(fn, steps, warmup, finish=None):
 
 def extra_multi_scale(a, dev, d, peak):
     """multi_scale=True (the reference function's default, utils/loss.py:104): the same step, device-timed, plus the
-    summed duration of the loss kernels (half-resolution pass + marching kernel + second stage) per step."""
+    summed duration of the loss call's kernels (thermal statistics + one-pass marching kernel + second stage) per step."""
     from thermal3d_vision_b200 import _lib
     from thermal3d_vision_b200.pipeline import HotPathStep
     B, H, W = a.batch, a.height, a.width
@@ -341,7 +341,7 @@ def extra_multi_scale(a, dev, d, peak):
                        detail_weight=DETAIL_W)
     args = [d[k] for k in KEYS]
     ms = time_steps(lambda: step.run_device(*args), 20, 3, step.finish)
-    _lib.profile_begin("loss_", 256)
+    _lib.profile_begin("loss_|thermal_stats", 256)
     for _ in range(10):
         step.run_device(*args)
     step.finish()
@@ -357,7 +357,8 @@ def extra_multi_scale(a, dev, d, peak):
             "loss_frac_of_peak": ab["loss"] / (loss_ms * 1e-3) / 1e9 / peak if loss_ms > 0 else None,
             "step_frac_of_peak": sum(ab.values()) / (ms * 1e-3) / 1e9 / peak,
             "check": {"loss": s["loss"], "n_valid": s["n_valid"]},
-            "note": "same workload with multi_scale=True; loss_kernels_ms = CUDA-event time of every kernel named loss_* per step "
+            "note": "same workload with multi_scale=True; loss_kernels_ms = CUDA-event time of every kernel of the loss call per step "
+                    "(thermal gradient statistics at both scales + the one-pass marching kernel + second stage) "
                     "(bracketing events serialise the streams, so the step itself is timed separately without them)"}
 
 

@@ -51,7 +51,8 @@ int t3d_device_info(int* sm_count, int* cc_major, int* cc_minor);
  * (monotonic; bench.py reports the delta over the timed region). */
 uint64_t t3d_launch_count(void);
 /* Per-kernel device timing for roofline reports: between begin and end, every
- * launch of a kernel whose name contains `kernel_name_substr` is bracketed by
+ * launch of a kernel whose name contains `kernel_name_substr` (several
+ * alternatives may be given separated by '|') is bracketed by
  * CUDA events on its launching stream (at most max_launches of them).
  * t3d_profile_end synchronises on the last event and returns the summed kernel
  * time and the number of launches timed. */

@@ -42,10 +42,26 @@ struct Prof {
 } g_prof;
 }  // namespace
 
+// `pattern`: one substring, or several separated by '|'
+static bool prof_matches(const char* name, const char* pattern) {
+    const char* p = pattern;
+    for (;;) {
+        const char* bar = strchr(p, '|');
+        const size_t len = bar ? (size_t)(bar - p) : strlen(p);
+        if (len > 0 && len < 64) {
+            char sub[64];
+            memcpy(sub, p, len); sub[len] = 0;
+            if (strstr(name, sub)) return true;
+        }
+        if (!bar) return false;
+        p = bar + 1;
+    }
+}
+
 bool t3d_prof_before(const char* name, cudaStream_t st) {
     if (!g_prof.active) return false;
     std::lock_guard<std::mutex> lk(g_prof.mu);
-    if (!g_prof.active || g_prof.used >= g_prof.cap || !strstr(name, g_prof.pattern)) return false;
+    if (!g_prof.active || g_prof.used >= g_prof.cap || !prof_matches(name, g_prof.pattern)) return false;
     if ((g_prof.seen++ % g_prof.stride) != 0) return false;
     cudaEventRecord(g_prof.ev[2 * g_prof.used], st);
     g_prof.names[g_prof.used] = name;

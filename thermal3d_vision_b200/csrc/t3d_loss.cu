@@ -12,6 +12,7 @@
 //   loss_finalize_kernel   deterministic fixed-order fp64 second stage
 //   rescale / scale        device-conditional gradient rescaling (no host sync)
 #include "t3d_loss_internal.cuh"
+#include <type_traits>
 #include <string.h>
 
 #include <stdlib.h>
@@ -156,11 +157,16 @@ __global__ void __launch_bounds__(kSThreads, 4) thermal_stats_kernel(const Stats
 // 32-row band, 4 pixels per lane, 128-bit loads, vertical neighbours in registers, horizontal ones from shuffles
 // (the strip's right edge: one 8-byte load); the half-resolution sums ride along on row pairs.  No shared memory.
 // MODE 0: one plane, 1: three planes, 2: three bit-identical planes (plane 0 is read, gray = gray3(v, v, v)).
-constexpr int kSMRows = 32, kSMWarps = 4;
+constexpr int kSMWarps = 4;
+// rows per work item (even; tuning knob T3D_STATS_ROWS): shorter marches = finer load balance, more halo rows
+static int stats_march_rows() {
+    static const int v = [] { const char* e = getenv("T3D_STATS_ROWS"); const int r = e ? atoi(e) : 32; return r < 4 ? 4 : (r & ~3); }();
+    return v;
+}
 struct SRow { float g[4], e0, e1; };     // gray of the lane's quad and of the two pixels right of it
 
 template <bool MULTI, int MODE>
-__global__ void __launch_bounds__(kSMWarps * 32) thermal_stats_march_kernel(const StatsArgs a, int nbands, int nstrips) {
+__global__ void __launch_bounds__(kSMWarps * 32, (MODE == 1) ? 3 : 6) thermal_stats_march_kernel(const StatsArgs a, int nbands, int nstrips, int rows) {
     const int lane = threadIdx.x & 31;
     const int per_img = nbands * nstrips;
     const int item = blockIdx.x * kSMWarps + (threadIdx.x >> 5);
@@ -171,7 +177,7 @@ __global__ void __launch_bounds__(kSMWarps * 32) thermal_stats_march_kernel(cons
     const int H = a.H, W = a.W, h2 = H >> 1;
     const size_t plane = (size_t)H * W;
     const float* __restrict__ th = a.thermal[view] + (size_t)b * a.tch * plane;
-    const int ra = band * kSMRows, rb = min(ra + kSMRows, H);
+    const int ra = band * rows, rb = min(ra + rows, H);
     const int x0 = strip * 128 + 4 * lane;
     const bool active = x0 < W, has_right = x0 + 4 < W;
     const bool edge_lane = active && has_right && lane == 31;       // the pixels right of the quad belong to the next strip
@@ -231,43 +237,43 @@ __global__ void __launch_bounds__(kSMWarps * 32) thermal_stats_march_kernel(cons
     if (ra + 4 < y_end) { fetch(ra + 4, qa0); fetch(ra + 5, qa1); }
     Pooled pc = {0.f, 0.f, 0.f};
     if (MULTI && (ra >> 1) < h2) pc = pool_rows(r0, r1);
-    auto pair = [&](int y, Raw& f0, Raw& f1) {                       // f0, f1: the fetched rows y+2, y+3; refilled with y+6, y+7
-        const bool has2 = y + 2 < H, has3 = y + 3 < H;
-        if (has2) finish(f0, r2);
-        if (has3) finish(f1, r3);
+    // one row pair (y, y+1) held in (c0, c1); (n0, n1) receive rows y+2, y+3 from the fetched (f0, f1), which are
+    // refilled with rows y+6, y+7.  INTERIOR: every row up to y+3 exists and pooled row y/2 + 1 does -- no guards.
+    auto pair = [&](int y, Raw& f0, Raw& f1, const SRow& c0, const SRow& c1, SRow& n0, SRow& n1, auto interior_tag) {
+        constexpr bool INTERIOR = decltype(interior_tag)::value;
+        const bool has2 = INTERIOR || y + 2 < H, has3 = INTERIOR || y + 3 < H;
+        if (has2) finish(f0, n0);
+        if (has3) finish(f1, n1);
         if (y + 6 < y_end) { fetch(y + 6, f0); fetch(y + 7, f1); }
-        if (active) {                                                // rows y+10, y+11 on their way into L2 (no register cost)
-#pragma unroll
-            for (int d = 10; d < 12; ++d)
-                if (y + d < min(y_end, H)) {
-                    const float* p = px + (size_t)(y + d) * W;
-                    asm volatile("prefetch.global.L2 [%0];" :: "l"(p));
-                    if (MODE == 1) { asm volatile("prefetch.global.L2 [%0];" :: "l"(p + plane)); asm volatile("prefetch.global.L2 [%0];" :: "l"(p + 2 * plane)); }
-                }
-        }
         // scale 1: rows y and y+1 (zero-padded last row: dy == 0)
-        s[0] += dx_sum(r0);
-        if (y + 1 < H) s[1] += dy_sum(r0, r1);
-        if (y + 1 < rb) {
-            s[0] += dx_sum(r1);
-            if (has2) s[1] += dy_sum(r1, r2);
+        s[0] += dx_sum(c0);
+        if (INTERIOR || y + 1 < H) s[1] += dy_sum(c0, c1);
+        if (INTERIOR || y + 1 < rb) {
+            s[0] += dx_sum(c1);
+            if (has2) s[1] += dy_sum(c1, n0);
         }
         if (MULTI) {
             const int I = y >> 1;
-            if (I < h2) {
+            if (INTERIOR || I < h2) {
                 s[2] += fabsf(pc.c1 - pc.c0) + fabsf(pc.cr - pc.c1);
-                if (I + 1 < h2) {                                    // rows y+2, y+3 exist
-                    const Pooled pn = pool_rows(r2, r3);
+                if (INTERIOR || I + 1 < h2) {                        // rows y+2, y+3 exist
+                    const Pooled pn = pool_rows(n0, n1);
                     s[3] += fabsf(pn.c0 - pc.c0) + fabsf(pn.c1 - pc.c1);
                     pc = pn;
                 }
             }
         }
-        r0 = r2; r1 = r3;
     };
-    for (int y = ra; y < rb; y += 4) {                               // ra even, rb even or == H
-        pair(y, qb0, qb1);
-        if (y + 2 < rb) pair(y + 2, qa0, qa1);
+    if (rb + 2 <= H && ((rb - ra) & 3) == 0) {                       // rows rb, rb+1 exist (so does pooled row rb / 2)
+        for (int y = ra; y < rb; y += 4) {
+            pair(y, qb0, qb1, r0, r1, r2, r3, std::true_type{});
+            pair(y + 2, qa0, qa1, r2, r3, r0, r1, std::true_type{});
+        }
+    } else {
+        for (int y = ra; y < rb; y += 4) {                           // ra even, rb even or == H
+            pair(y, qb0, qb1, r0, r1, r2, r3, std::false_type{});
+            if (y + 2 < rb) pair(y + 2, qa0, qa1, r2, r3, r0, r1, std::false_type{});
+        }
     }
     if (!active) { s[0] = 0.f; s[1] = 0.f; s[2] = 0.f; s[3] = 0.f; }
 #pragma unroll
@@ -950,7 +956,7 @@ WsLayout ws_layout(int B, int H, int W, int multi = 0) {
     L.tiles_x = (W + kTW - 1) / kTW;    L.tiles_y = (H + kTH - 1) / kTH;
     size_t off = 0;
     L.counter = off;        off += 256;
-    L.sm_bands = (H + kSMRows - 1) / kSMRows; L.sm_strips = (W + 127) / 128;
+    L.sm_bands = (H + stats_march_rows() - 1) / stats_march_rows(); L.sm_strips = (W + 127) / 128;
     const size_t stats_tiles = (size_t)max(L.stiles_x * L.stiles_y, L.sm_bands * L.sm_strips);
     L.stats_partials = off; off += t3d_align_up((size_t)B * 2 * stats_tiles * 4 * sizeof(float), 256);
     // sized for the tile kernel (16-row tiles) and the marching kernel (>= 8-row bands)
@@ -980,9 +986,9 @@ template <bool MULTI>
 int launch_stats_march(const StatsArgs& sa, int nbands, int nstrips, cudaStream_t st) {
     const int items = sa.B * 2 * nbands * nstrips;
     const int grid = (items + kSMWarps - 1) / kSMWarps;
-    if (sa.replicated) T3D_LAUNCH("thermal_stats_march_kernel", st, (thermal_stats_march_kernel<MULTI, 2><<<grid, kSMWarps * 32, 0, st>>>(sa, nbands, nstrips)));
-    else if (sa.tch == 3) T3D_LAUNCH("thermal_stats_march_kernel", st, (thermal_stats_march_kernel<MULTI, 1><<<grid, kSMWarps * 32, 0, st>>>(sa, nbands, nstrips)));
-    else T3D_LAUNCH("thermal_stats_march_kernel", st, (thermal_stats_march_kernel<MULTI, 0><<<grid, kSMWarps * 32, 0, st>>>(sa, nbands, nstrips)));
+    if (sa.replicated) T3D_LAUNCH("thermal_stats_march_kernel", st, (thermal_stats_march_kernel<MULTI, 2><<<grid, kSMWarps * 32, 0, st>>>(sa, nbands, nstrips, stats_march_rows())));
+    else if (sa.tch == 3) T3D_LAUNCH("thermal_stats_march_kernel", st, (thermal_stats_march_kernel<MULTI, 1><<<grid, kSMWarps * 32, 0, st>>>(sa, nbands, nstrips, stats_march_rows())));
+    else T3D_LAUNCH("thermal_stats_march_kernel", st, (thermal_stats_march_kernel<MULTI, 0><<<grid, kSMWarps * 32, 0, st>>>(sa, nbands, nstrips, stats_march_rows())));
     return T3D_OK;
 }
 
