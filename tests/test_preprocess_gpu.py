@@ -227,6 +227,31 @@ def test_bracket_percentiles_adversarial_frames(cuda_device):
             assert np.array_equal(b.thermal[i].cpu().numpy(), o, equal_nan=True), (size, i)
 
 
+def test_resize_5_to_4_fast_path_adversarial(cuda_device):
+    """The dataset geometry (5:4 on both axes, e.g. 640x512 -> 512x384) takes resize54_march_kernel (compile-time
+    taps, below / above counts in registers): bits must equal the histogram path and the oracle on frames that
+    stress the windows (full-range noise, two-valued, ramps) and on strips / row ranges of odd sizes."""
+    from thermal3d_vision_b200 import preprocessing as pp
+    rng = np.random.default_rng(21)
+    for (H, W), size in (((80, 160), (128, 64)), ((200, 360), (288, 160)), ((512, 640), (512, 384))):
+        frames = [
+            rng.integers(0, 65536, (H, W)).astype(np.uint16),
+            np.where(rng.random((H, W)) < 0.5, 100, 60000).astype(np.uint16),
+            np.sort(rng.integers(0, 65536, H * W)).reshape(H, W).astype(np.uint16),
+            rng.normal(22800, 300, (H, W)).clip(0, 65535).astype(np.uint16),
+            np.where(rng.random((H, W)) < 0.03, 65535, rng.integers(20000, 20040, (H, W))).astype(np.uint16),
+        ]
+        raw = torch.from_numpy(np.stack(frames)).to(cuda_device)
+        a = pp.preprocess_thermal_batch(raw, size, path="train", histogram=True)
+        b = pp.preprocess_thermal_batch(raw, size, path="train", histogram=False)
+        assert torch.equal(a.percentiles, b.percentiles), size
+        assert torch.equal(a.thermal.view(torch.int32), b.thermal.view(torch.int32)), size
+        for i, f in enumerate(frames):
+            o, p2, p98, _ = ref_preprocess.train_path(f, (size[1], size[0]))
+            assert tuple(b.percentiles[i].tolist()) == (p2, p98), (size, i)
+            assert np.array_equal(b.thermal[i].cpu().numpy(), o, equal_nan=True), (size, i)
+
+
 def test_bracket_windows_hold_on_typical_frames(cuda_device):
     """Performance guard: on ordinary frames (day / night + hot blobs, real-data-like smooth fields) the sampled
     windows must contain the percentile ranks -- no frame may need the exact-select fallback."""

@@ -282,8 +282,34 @@ constexpr int kRzU = 8;                 // consecutive output pixels per lane
 constexpr int kRzStrip = 32 * kRzU;
 constexpr int kRing = 4;
 
+// H54 -- the dataset's horizontal geometry.  640 -> 512 columns (data/dataset_loader.py:242 with the training size of
+// train_thermal_dustr.py) is a 5:4 reduction: scale = 1.25 exactly, so cv2's x taps are periodic -- 4 outputs from 5
+// inputs, weights {1/8, 3/8, 5/8, 7/8}, no border clamping -- and become compile-time constants: a lane's 8 output
+// pixels read 10 consecutive source pixels (five 32-bit shared loads instead of sixteen 16-bit ones, no tap
+// registers).  Same arithmetic, same order, same bits.  (The vertical 512 -> 384 is 4:3: its taps are not exactly
+// periodic in floating point and stay in the table.)
+template <int K> struct W54 { static constexpr float f = (2 * (K & 3) + 1) * 0.125f; static constexpr float c = 1.0f - f; };
+
+__device__ __forceinline__ void hpass54(uint32_t saddr, float h[8]) {
+    unsigned int w[5];
+#pragma unroll
+    for (int i = 0; i < 5; ++i) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w[i]) : "r"(saddr + 4u * i));
+    float p[10];
+#pragma unroll
+    for (int i = 0; i < 5; ++i) { p[2 * i] = (float)(w[i] & 0xffffu); p[2 * i + 1] = (float)(w[i] >> 16); }
+    // output u reads source pixels u + u / 4 and the next one
+    h[0] = __fadd_rn(__fmul_rn(p[0], W54<0>::c), __fmul_rn(p[1], W54<0>::f));
+    h[1] = __fadd_rn(__fmul_rn(p[1], W54<1>::c), __fmul_rn(p[2], W54<1>::f));
+    h[2] = __fadd_rn(__fmul_rn(p[2], W54<2>::c), __fmul_rn(p[3], W54<2>::f));
+    h[3] = __fadd_rn(__fmul_rn(p[3], W54<3>::c), __fmul_rn(p[4], W54<3>::f));
+    h[4] = __fadd_rn(__fmul_rn(p[5], W54<0>::c), __fmul_rn(p[6], W54<0>::f));
+    h[5] = __fadd_rn(__fmul_rn(p[6], W54<1>::c), __fmul_rn(p[7], W54<1>::f));
+    h[6] = __fadd_rn(__fmul_rn(p[7], W54<2>::c), __fmul_rn(p[8], W54<2>::f));
+    h[7] = __fadd_rn(__fmul_rn(p[8], W54<3>::c), __fmul_rn(p[9], W54<3>::f));
+}
+
 // one warp: resize + classify output rows [ya, yb) of strip `strip` of frame `f`
-template <bool DENSE>
+template <bool DENSE, bool H54>
 __device__ __forceinline__ void resize_march_rows(const uint16_t* __restrict__ src, uint16_t* __restrict__ resized,
                                                   const uint2* __restrict__ gxt, const uint4* __restrict__ gyt,
                                                   const unsigned int* __restrict__ bracket, unsigned int* __restrict__ brhist,
@@ -294,19 +320,22 @@ __device__ __forceinline__ void resize_march_rows(const uint16_t* __restrict__ s
     const bool active = x0 < dw;
     // ---- x taps of this lane's 4 pixels as shared-memory byte offsets inside a ring slot
     const int xl = min(X0 + kRzStrip, dw) - 1;
-    const int span0 = (int)(__ldg(gxt + X0).x & 0xffffu) & ~7;          // 8-aligned first source column
-    const int span1 = (int)(__ldg(gxt + xl).x >> 16) + 1;               // one past the last source column used
+    const int span0 = H54 ? (X0 >> 2) * 5 : ((int)(__ldg(gxt + X0).x & 0xffffu) & ~7);          // 8-aligned first source column
+    const int span1 = H54 ? ((xl + 1) >> 2) * 5 : ((int)(__ldg(gxt + xl).x >> 16) + 1);         // one past the last source column used
     const int nvec = (span1 - span0 + 7) >> 3;                          // <= 64 16-byte chunks per source row (launcher)
     const bool copier = lane < nvec, copier2 = lane + 32 < nvec;
     // the second tap is the next source pixel; where cv2 clamps it to the same pixel (right border) its weight
     // is exactly 0, so reading the (finite) u16 after the row's last pixel instead changes nothing
     uint32_t o0[kRzU]; float fx[kRzU], cx[kRzU];
+    if (!H54) {
 #pragma unroll
-    for (int u = 0; u < kRzU; ++u) {
-        const uint2 t = __ldg(gxt + min(x0 + u, dw - 1));
-        o0[u] = ring + 2u * (uint32_t)((int)(t.x & 0xffffu) - span0);
-        fx[u] = __uint_as_float(t.y); cx[u] = __fsub_rn(1.0f, fx[u]);
+        for (int u = 0; u < kRzU; ++u) {
+            const uint2 t = __ldg(gxt + min(x0 + u, dw - 1));
+            o0[u] = ring + 2u * (uint32_t)((int)(t.x & 0xffffu) - span0);
+            fx[u] = __uint_as_float(t.y); cx[u] = __fsub_rn(1.0f, fx[u]);
+        }
     }
+    const uint32_t lane_ld = ring + 20u * lane;                         // H54: this lane's 10 source pixels inside a slot
     const Windows w = load_windows(bracket, f);
     unsigned int* hA = brhist + (size_t)f * 2 * kBrStride;
     const char* lane_src = reinterpret_cast<const char*>(src + (size_t)f * sh * sw + span0 + 8 * lane);
@@ -349,11 +378,14 @@ __device__ __forceinline__ void resize_march_rows(const uint16_t* __restrict__ s
         cp_async_wait<kRing - 2>();
         __syncwarp();                 // the row has landed for every lane; everyone is done with the previous row
         issue_next();                 // ... whose slot is the one this issue refills
+        if (H54) hpass54(lane_ld + load_off, h);
+        else {
 #pragma unroll
-        for (int u = 0; u < kRzU; ++u) {
-            const uint32_t ad = o0[u] + load_off;
-            const float a = (float)lds_u16(ad), bq = (float)lds_u16(ad + 2u);
-            h[u] = __fadd_rn(__fmul_rn(a, cx[u]), __fmul_rn(bq, fx[u]));
+            for (int u = 0; u < kRzU; ++u) {
+                const uint32_t ad = o0[u] + load_off;
+                const float a = (float)lds_u16(ad), bq = (float)lds_u16(ad + 2u);
+                h[u] = __fadd_rn(__fmul_rn(a, cx[u]), __fmul_rn(bq, fx[u]));
+            }
         }
         load_off += slot_bytes; if (load_off == ring_bytes) load_off = 0;
     };
@@ -396,7 +428,7 @@ __device__ __forceinline__ void resize_march_rows(const uint16_t* __restrict__ s
     cp_async_wait<0>();
 }
 
-template <bool DENSE>
+template <bool DENSE, bool H54>
 __global__ void __launch_bounds__(kRzThreads, 3)
 resize_march_kernel(const uint16_t* __restrict__ src, uint16_t* __restrict__ resized,
                     const uint2* __restrict__ gxt, const uint4* __restrict__ gyt,
@@ -416,7 +448,7 @@ resize_march_kernel(const uint16_t* __restrict__ src, uint16_t* __restrict__ res
         const int yb = (int)min((unsigned)dh, ya + (L1 - L));
         L += yb - ya;
         const int f = (int)(col / (unsigned)nstrips), strip = (int)(col - f * nstrips);
-        resize_march_rows<DENSE>(src, resized, gxt, gyt, bracket, brhist, sh, sw, dh, dw, f, strip, ya, yb,
+        resize_march_rows<DENSE, H54>(src, resized, gxt, gyt, bracket, brhist, sh, sw, dh, dw, f, strip, ya, yb,
                                  ring, (uint32_t)slot_bytes, lane);
     }
 }
@@ -512,13 +544,17 @@ int t3d_launch_bracket_percentiles(const uint16_t* raw, int B, int sh, int sw, i
         const size_t smem = (size_t)kRzWarps * kRing * slot_bytes;
         const bool dense = sh <= 2 * dh;
         if (smem <= 96 * 1024 && slot_px <= 512 && (long long)B * nstrips * dh < (1ll << 31)) {
-            static int max_ctas_dev[kT3dMaxDevices][2] = {};
-            static size_t attr_smem_dev[kT3dMaxDevices][2] = {};
+            static int max_ctas_dev[kT3dMaxDevices][3] = {};
+            static size_t attr_smem_dev[kT3dMaxDevices][3] = {};
             const int slot = t3d_device_slot();
             int* max_ctas = max_ctas_dev[slot];
             size_t* attr_smem = attr_smem_dev[slot];
-            const int di = dense ? 1 : 0;
-            const void* fn = dense ? (const void*)resize_march_kernel<true> : (const void*)resize_march_kernel<false>;
+            // the dataset's 5:4 horizontal geometry: compile-time x taps (dense only: 5:4 implies scale < 2)
+            static const bool use54 = [] { const char* e = getenv("T3D_RZ_54"); return e ? atoi(e) != 0 : true; }();
+            const bool h54 = use54 && dense && sw * 4 == dw * 5 && (dw & 31) == 0;
+            const int di = h54 ? 2 : (dense ? 1 : 0);
+            const void* fn = h54 ? (const void*)resize_march_kernel<true, true> :
+                             dense ? (const void*)resize_march_kernel<true, false> : (const void*)resize_march_kernel<false, false>;
             if (smem > attr_smem[di] || max_ctas[di] == 0) {
                 T3D_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                 attr_smem[di] = smem;
@@ -534,12 +570,15 @@ int t3d_launch_bracket_percentiles(const uint16_t* raw, int B, int sh, int sw, i
             const long long total = (long long)B * nstrips * dh;
             long long grid = (long long)t3d_sm_count() * ctas;
             if (grid * kRzWarps > total) grid = (total + kRzWarps - 1) / kRzWarps;
-            if (dense)
-                T3D_LAUNCH("resize_march_kernel", st, resize_march_kernel<true><<<(unsigned)grid, kRzThreads, smem, st>>>(
-                    raw, w.resized, w.gxt, w.gyt, w.bracket, w.brhist, B, sh, sw, dh, dw, nstrips, slot_bytes));
+            if (h54)
+                T3D_LAUNCH("resize_march_kernel", st, (resize_march_kernel<true, true><<<(unsigned)grid, kRzThreads, smem, st>>>(
+                    raw, w.resized, w.gxt, w.gyt, w.bracket, w.brhist, B, sh, sw, dh, dw, nstrips, slot_bytes)));
+            else if (dense)
+                T3D_LAUNCH("resize_march_kernel", st, (resize_march_kernel<true, false><<<(unsigned)grid, kRzThreads, smem, st>>>(
+                    raw, w.resized, w.gxt, w.gyt, w.bracket, w.brhist, B, sh, sw, dh, dw, nstrips, slot_bytes)));
             else
-                T3D_LAUNCH("resize_march_kernel", st, resize_march_kernel<false><<<(unsigned)grid, kRzThreads, smem, st>>>(
-                    raw, w.resized, w.gxt, w.gyt, w.bracket, w.brhist, B, sh, sw, dh, dw, nstrips, slot_bytes));
+                T3D_LAUNCH("resize_march_kernel", st, (resize_march_kernel<false, false><<<(unsigned)grid, kRzThreads, smem, st>>>(
+                    raw, w.resized, w.gxt, w.gyt, w.bracket, w.brhist, B, sh, sw, dh, dw, nstrips, slot_bytes)));
             launched = true;
         }
     }
