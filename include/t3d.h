@@ -90,6 +90,9 @@ int t3d_profile_timeline(char* names, int name_stride, double* start_ms, double*
 #define T3D_LOSS_CONF_MIN_ONLY 0x2 /* clamp the confidence from below only (>= 1e-5, no upper clamp at 10): the
                                     * "original loss calculation" of train_thermal_dustr.py:278-279,305-318, which
                                     * never goes through utils/loss.py's clamp(conf, 1e-5, 10) */
+#define T3D_LOSS_STATS_TWO_SCALES 0x4 /* the caller's thermal_stats hold the half-resolution sums too ([..][2], [3];
+                                    * t3d_preprocess_set_stats_scales): with T3D_LOSS_MULTI_SCALE they are used instead
+                                    * of a statistics pass (without this flag, multi-scale ignores thermal_stats) */
 size_t t3d_loss_workspace_bytes(int B, int H, int W, int flags);
 
 /* Thermal-gradient statistics (utils/loss.py:184-201,239-249): for every
@@ -236,6 +239,13 @@ int t3d_preprocess_train_u16(const uint16_t* raw, int B, int src_h, int src_w, i
                              float* grad_stats, void* workspace, size_t workspace_bytes, void* stream);
 /* Number of statistic partials per frame written to grad_stats (0: not available for this shape). */
 int t3d_preprocess_stats_tiles(int dst_h, int dst_w);
+/* Half-resolution statistics for the multi-scale loss (utils/loss.py:133-174).  t3d_preprocess_set_stats_scales(2)
+ * makes the following t3d_preprocess_train_u16 calls OF THE CALLING THREAD also leave the sums of |Dx|, |Dy| of the
+ * 2x2 average-pooled gray image in grad_stats[..][2], [3] -- where t3d_preprocess_stats_scales(dst_h, dst_w)
+ * returns 2 (else those slots stay 0 and the loss computes its own statistics).  Pass such statistics to
+ * t3d_loss_fwd_bwd with T3D_LOSS_STATS_TWO_SCALES. */
+int t3d_preprocess_set_stats_scales(int scales);
+int t3d_preprocess_stats_scales(int dst_h, int dst_w);
 /* Scheduling hint (process-wide, default 0): shared != 0 says the caller runs other kernels
  * concurrently with t3d_preprocess_train_u16 (another stream), so its issue-bound resize
  * kernel leaves registers on every SM for them.  Results do not depend on it. */

@@ -182,6 +182,50 @@ def test_grad_stats_feed_the_loss(cuda_device):
     np.testing.assert_allclose(b["per_sample"][:, :5].cpu().numpy(), rows, rtol=1e-5)
 
 
+@pytest.mark.parametrize("w,h,hist", [(160, 96, True), (512, 384, False), (224, 224, False), (136, 50, False)])
+def test_half_resolution_grad_stats_feed_the_multi_scale_loss(cuda_device, w, h, hist):
+    """half_res_stats=True: the normalisation kernel also sums |Dx|, |Dy| of the 2x2 average-pooled gray image
+    (utils/loss.py:133-174); they equal numpy on the produced image, and a multi-scale loss call that consumes them
+    matches the oracle.  Shapes the half-resolution pass does not take (odd bands) report stats_scales == 1 and the
+    loss computes its own statistics."""
+    from oracle import ref_loss
+    from thermal3d_vision_b200 import loss as t3d
+    from thermal3d_vision_b200 import preprocessing as pp
+    B = 2
+    raw = torch.from_numpy(ref_preprocess.make_raw_frames(2 * B, seed=15)).to(cuda_device)
+    tb1 = pp.preprocess_thermal_batch(raw[:B], (w, h), path="train", histogram=hist, half_res_stats=True)
+    tb2 = pp.preprocess_thermal_batch(raw[B:], (w, h), path="train", histogram=hist, half_res_stats=True)
+    plain = pp.preprocess_thermal_batch(raw[:B], (w, h), path="train", histogram=hist)
+    assert plain.stats_scales == 1 and torch.equal(plain.thermal, tb1.thermal)
+    assert torch.equal(plain.grad_stats[..., :2], tb1.grad_stats[..., :2])
+    assert float(plain.grad_stats[..., 2:].abs().sum()) == 0.0
+    rows_per = -(-h // 24)
+    assert tb1.stats_scales == (2 if rows_per % 2 == 0 else 1)
+    if tb1.stats_scales == 2:
+        th = tb1.thermal.cpu().numpy()
+        g = (np.float32(0.299) * th[:, 0] + np.float32(0.587) * th[:, 1]) + np.float32(0.114) * th[:, 2]
+        h2, w2 = h // 2, w // 2
+        q = g[:, :2 * h2, :2 * w2].reshape(B, h2, 2, w2, 2)
+        pooled = (((q[:, :, 0, :, 0] + q[:, :, 0, :, 1]) + q[:, :, 1, :, 0]) + q[:, :, 1, :, 1]) * np.float32(0.25)
+        sx2 = np.abs(np.diff(pooled.astype(np.float64), axis=2)).sum(axis=(1, 2))
+        sy2 = np.abs(np.diff(pooled.astype(np.float64), axis=1)).sum(axis=(1, 2))
+        got = tb1.grad_stats.double().sum(1).cpu().numpy()
+        np.testing.assert_allclose(got[:, 2], sx2, rtol=1e-5)
+        np.testing.assert_allclose(got[:, 3], sy2, rtol=1e-5)
+    P1, P2, G1, G2, C1, C2, _, _ = ref_loss.make_batch_inputs(B, h, w, seed=19)
+    d = [x.to(cuda_device) for x in (P1, P2, G1, G2, C1, C2)]
+    kw = dict(alpha=0.2, edge_weight=0.5, smoothness_weight=0.3, detail_weight=0.4, multi_scale=True)
+    out = t3d.fused_thermal_loss_fwd_bwd(*d, tb1.thermal, tb2.thermal, thermal_stats=(tb1.grad_stats, tb2.grad_stats),
+                                         thermal_stats_scales=min(tb1.stats_scales, tb2.stats_scales),
+                                         thermal_replicated=True, **kw)
+    Pa, Pb = P1.clone().requires_grad_(), P2.clone().requires_grad_()
+    mean, rows, _ = ref_loss.batched_loss_torch(Pa, Pb, G1, G2, C1, C2, tb1.thermal.cpu(), tb2.thermal.cpu(), **kw)
+    mean.backward()
+    np.testing.assert_allclose(out["per_sample"][:, :5].cpu().numpy(), rows, rtol=1e-5)
+    torch.testing.assert_close(out["dpred1"].cpu(), Pa.grad, rtol=1e-4, atol=1e-6)
+    torch.testing.assert_close(out["dpred2"].cpu(), Pb.grad, rtol=1e-4, atol=1e-6)
+
+
 @pytest.mark.parametrize("w,h", [(224, 224), (512, 384), (333, 217), (640, 512)])
 def test_bracket_percentiles_match_histogram_path(cuda_device, w, h):
     """histogram=False (sampled value windows, t3d_preprocess_bracket.cu) must give the same bits as the

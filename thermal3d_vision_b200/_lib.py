@@ -55,6 +55,8 @@ _SIGNATURES = {
     "t3d_preprocess_train_u16": (C.c_int, [c_ptr] + [C.c_int] * 5 + [c_ptr, C.c_int, c_ptr, c_ptr, c_ptr,
                                                                     c_ptr, C.c_size_t, c_ptr]),
     "t3d_preprocess_stats_tiles": (C.c_int, [C.c_int, C.c_int]),
+    "t3d_preprocess_set_stats_scales": (C.c_int, [C.c_int]),
+    "t3d_preprocess_stats_scales": (C.c_int, [C.c_int, C.c_int]),
     "t3d_preprocess_set_shared": (C.c_int, [C.c_int]),
     "t3d_preprocess_fallback_count": (C.c_int, [c_ptr, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_uint), c_ptr]),
     "t3d_contrast_normalize_workspace_bytes": (C.c_size_t, [C.c_int]),

@@ -1038,7 +1038,7 @@ int loss_impl(bool bwd, const float* pred1, const float* pred2, const float* gt1
               void* workspace, size_t ws_bytes, void* stream,
               int gt_h = 0, int gt_w = 0, int conf_h = 0, int conf_w = 0) {
     if (int rc = check_dims(B, H, W)) return rc;
-    T3D_REQUIRE((flags & ~(T3D_LOSS_MULTI_SCALE | T3D_LOSS_CONF_MIN_ONLY)) == 0, "unknown loss flags 0x%x", flags);
+    T3D_REQUIRE((flags & ~(T3D_LOSS_MULTI_SCALE | T3D_LOSS_CONF_MIN_ONLY | T3D_LOSS_STATS_TWO_SCALES)) == 0, "unknown loss flags 0x%x", flags);
     if (gt_h == H && gt_w == W) gt_h = gt_w = 0;                    // same size: direct reads
     if (conf_h == H && conf_w == W) conf_h = conf_w = 0;
     T3D_REQUIRE((gt_h == 0) == (gt_w == 0) && gt_h >= 0 && (conf_h == 0) == (conf_w == 0) && conf_h >= 0, "bad gt / conf size");
@@ -1066,7 +1066,7 @@ int loss_impl(bool bwd, const float* pred1, const float* pred2, const float* gt1
 
     T3D_CUDA(cudaMemsetAsync(counter, 0, 2 * sizeof(unsigned int), st));   // [0] finalize ticket, [1] work queue
     // thermal-gradient statistics: supplied by the caller (fused into the preprocessing) or computed here
-    const bool user_stats = thermal_on && !multi && ustats1 && ustats2 && ustats_tiles > 0;
+    const bool user_stats = thermal_on && (!multi || (flags & T3D_LOSS_STATS_TWO_SCALES)) && ustats1 && ustats2 && ustats_tiles > 0;
     const float* stats_v[2] = {stats_partials, stats_partials};
     int stiles = 0;
     if (user_stats) { stats_v[0] = ustats1; stats_v[1] = ustats2; stiles = ustats_tiles; }

@@ -524,6 +524,17 @@ __global__ void __launch_bounds__(256) normalize_u16_kernel(const uint16_t* __re
 // when the output is replicated to 3 planes).
 constexpr int kNormBands = 24;       // CTAs per frame == statistic partials per frame (T3D_STATS_TILES)
 constexpr int kNormThreads = 256;
+constexpr int kNormStageMax = 24 * 1024;  // staged band bytes: LUT 32 KB + band <= 56 KB per CTA, 4 CTAs per SM
+// t3d_preprocess_set_stats_scales: 2 = the next calls of this thread also leave the half-resolution sums in grad_stats
+thread_local int g_pre_stats_scales = 1;
+// shapes whose bands the half-resolution pass handles: even bands of <= 16 rows, W / 2 columns <= one per thread,
+// the band + two rows below fit the staging area
+static bool norm_s2_supported(int H, int W) {
+    static const bool stage_on = [] { const char* e = getenv("T3D_NORM_STAGE"); return e ? atoi(e) != 0 : true; }();
+    const int rows_per = (H + kNormBands - 1) / kNormBands;
+    return stage_on && H >= 2 && W >= 8 && (W % 8) == 0 && (W / 2) <= kNormThreads && (rows_per % 2) == 0 && rows_per / 2 + 1 <= 9 /* kS2MaxPool */ &&
+           (size_t)(rows_per + 2) * W * sizeof(uint16_t) <= (size_t)kNormStageMax;
+}
 constexpr int kNormWarps = kNormThreads / 32;
 
 __device__ __forceinline__ float2 lds_f2(uint32_t saddr) {
@@ -576,15 +587,48 @@ __device__ __noinline__ void normalize_band_direct(const uint16_t* __restrict__ 
 // STAGED (W % 8 == 0, the band fits): the band's raw rows (+ the row below) and the LUT arrive in shared memory as
 // ONE batch of cp.async copies -- a single exposed memory latency per CTA instead of one per marched row (the
 // marches are short: 8 rows per warp at 384 rows), and the march itself then reads shared memory only.
-template <int REP, bool STATS, bool STAGED>
+// Half-resolution sums of a band (utils/loss.py:133-174: |Dx|, |Dy| of the 2x2 average-pooled gray image, zero-padded
+// last column / row), for the multi-scale loss.  Thread = pooled column (W / 2 <= kNormThreads), the band's pooled rows
+// (+ the one below) in registers; the right neighbour comes from a shuffle, across warps from shared memory.
+constexpr int kS2MaxPool = 9;            // pooled rows of a band + 1 (bands of <= 16 rows)
+template <typename Pooled>
+__device__ __forceinline__ void half_res_band_sums(int y0, int y1, int H, int W, float (*edge)[kS2MaxPool],
+                                                   Pooled pooled, float& tx2, float& ty2) {
+    const int tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
+    const int h2 = H >> 1, w2 = W >> 1;
+    const int I0 = y0 >> 1, I1 = min(y1, 2 * h2) >> 1;               // y0 is even: the band's own pooled rows [I0, I1)
+    const int nown = I1 - I0, npool = nown + ((I1 < h2) ? 1 : 0);
+    const int J = tid;
+    float pv[kS2MaxPool];
+#pragma unroll
+    for (int r = 0; r < kS2MaxPool; ++r) pv[r] = (r < npool && J < w2) ? pooled(I0 + r, J) : 0.f;
+    if (lane == 0) {
+#pragma unroll
+        for (int r = 0; r < kS2MaxPool; ++r) edge[wrp][r] = pv[r];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < kS2MaxPool - 1; ++r) {
+        float right = __shfl_down_sync(0xffffffffu, pv[r], 1);
+        if (lane == 31) right = edge[wrp + 1][r];
+        if (r < nown && J < w2) {
+            if (J + 1 < w2) tx2 += fabsf(right - pv[r]);
+            if (I0 + r + 1 < h2) ty2 += fabsf(pv[r + 1] - pv[r]);
+        }
+    }
+}
+
+template <int REP, bool STATS, bool STAGED, bool S2 = false>
 __global__ void __launch_bounds__(kNormThreads, 4) normalize_stats_u16_kernel(const uint16_t* __restrict__ src,
                                                                            const double* __restrict__ p,
                                                                            float* __restrict__ dst, int H, int W,
                                                                            float* __restrict__ stats,
                                                                            const float2* __restrict__ glut,
                                                                            const int2* __restrict__ lutmeta, int nitems) {
+    static_assert(!S2 || (STATS && STAGED), "half-resolution sums ride on the staged statistics variant");
     extern __shared__ float2 lut[];                 // {normalised value, its gray} for v in [floor(p2) - 1, ceil(p98) + 1]
-    __shared__ float red[kNormWarps][2];
+    __shared__ float red[kNormWarps][4];
+    __shared__ float edge[S2 ? kNormWarps + 1 : 1][kS2MaxPool];
     const int tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
     const int n = H * W;
     // persistent over (frame, band) items: the grid is sized by the launcher (SMs x CTAs per SM), so the kernel
@@ -598,17 +642,24 @@ __global__ void __launch_bounds__(kNormThreads, 4) normalize_stats_u16_kernel(co
     float* __restrict__ d = dst + (size_t)b * REP * n;
     const int rows_per = (H + kNormBands - 1) / kNormBands;
     const int y0 = band * rows_per, y1 = min(y0 + rows_per, H);
-    float tx = 0.f, ty = 0.f;
+    float tx = 0.f, ty = 0.f, tx2 = 0.f, ty2 = 0.f;
     if (range <= 0) {                                                 // block-uniform: no LUT for this frame
         const double p2 = p[2 * b], den = __dsub_rn(p[2 * b + 1], p2);
         normalize_band_direct<REP>(s, d, H, W, y0, y1, p2, den, STATS, tx, ty);
+        if (S2) {
+            auto gray = [&](int i) { const float o = normalize_px((double)__ldg(s + i), p2, den); return (REP == 3) ? gray3(o, o, o) : o; };
+            half_res_band_sums(y0, y1, H, W, edge, [&](int I, int J) {
+                const int i = 2 * I * W + 2 * J;
+                return 0.25f * (((gray(i) + gray(i + 1)) + gray(i + W)) + gray(i + W + 1));
+            }, tx2, ty2);
+        }
     } else {
         const uint32_t sraw = (uint32_t)__cvta_generic_to_shared(lut) + (uint32_t)kLutMax * 8u;   // STAGED: rows [y0, yl)
         if (STAGED) {
             const uint32_t slut = (uint32_t)__cvta_generic_to_shared(lut);
             const char* gl = reinterpret_cast<const char*>(glut + (size_t)b * kLutMax);
             for (int k = tid; k < (range + 1) / 2; k += kNormThreads) cpa16(slut + 16u * k, gl + 16 * (size_t)k);
-            const int yl = STATS ? min(y1 + 1, H) : y1;
+            const int yl = STATS ? min(y1 + (S2 ? 2 : 1), H) : y1;      // + the row(s) below: vertical differences
             const int nchunk = ((yl - y0) * W) >> 3;                  // the band is one contiguous block of the frame
             const char* gs = reinterpret_cast<const char*>(s + (size_t)y0 * W);
             for (int k = tid; k < nchunk; k += kNormThreads) cpa16(sraw + 16u * k, gs + 16 * (size_t)k);
@@ -709,17 +760,28 @@ __global__ void __launch_bounds__(kNormThreads, 4) normalize_stats_u16_kernel(co
                 if (y < yb) emit(A);
             }
         }
+        if (S2) {                                                         // the staged band + LUT are still in shared memory
+            half_res_band_sums(y0, y1, H, W, edge, [&](int I, int J) {
+                const uint32_t a = sraw + 2u * (uint32_t)((2 * I - y0) * W + 2 * J);
+                unsigned int r0, r1;
+                asm volatile("ld.shared.u32 %0, [%1];" : "=r"(r0) : "r"(a));
+                asm volatile("ld.shared.u32 %0, [%1];" : "=r"(r1) : "r"(a + 2u * (uint32_t)W));
+                const float g00 = look((r0 << 3) & 0x7fff8u).y, g01 = look((r0 >> 13) & 0x7fff8u).y;
+                const float g10 = look((r1 << 3) & 0x7fff8u).y, g11 = look((r1 >> 13) & 0x7fff8u).y;
+                return 0.25f * (((g00 + g01) + g10) + g11);
+            }, tx2, ty2);
+        }
     }
     if (STATS) {
         tx = warp_sum(tx); ty = warp_sum(ty);
-        if (lane == 0) { red[wrp][0] = tx; red[wrp][1] = ty; }
+        if (S2) { tx2 = warp_sum(tx2); ty2 = warp_sum(ty2); }
+        if (lane == 0) { red[wrp][0] = tx; red[wrp][1] = ty; red[wrp][2] = tx2; red[wrp][3] = ty2; }
         __syncthreads();
-        if (tid < 2) {
+        if (tid < 4) {
             float v = 0.f;
 #pragma unroll
             for (int w = 0; w < kNormWarps; ++w) v += red[w][tid];
-            stats[((size_t)b * kNormBands + band) * 4 + tid] = v;
-            stats[((size_t)b * kNormBands + band) * 4 + 2 + tid] = 0.f;      // scale-2 sums are not produced here
+            stats[((size_t)b * kNormBands + band) * 4 + tid] = v;       // [2], [3]: the half-resolution sums (S2), else 0
         }
     }
     }   // items
@@ -879,7 +941,7 @@ int t3d_preprocess_train_u16(const uint16_t* raw, int B, int src_h, int src_w, i
     const uint16_t* nsrc = same ? raw : resized;
     const int vec = (dst_w % 4 == 0) && t3d_aligned16(out) && ((reinterpret_cast<uintptr_t>(nsrc) & 7u) == 0);
     if (vec) {
-        constexpr int kStageMax = 24 * 1024;      // staged band bytes: LUT 32 KB + band <= 56 KB per CTA, 4 CTAs per SM
+        constexpr int kStageMax = kNormStageMax;
         static bool nattr_done[kT3dMaxDevices] = {};
         bool& nattr = nattr_done[t3d_device_slot()];
         if (!nattr) {
@@ -888,13 +950,18 @@ int t3d_preprocess_train_u16(const uint16_t* raw, int B, int src_h, int src_w, i
             T3D_CUDA(cudaFuncSetAttribute(normalize_stats_u16_kernel<REP_, ST_, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kLutMax * 8 + kStageMax))
             T3D_NORM_ATTR(1, true); T3D_NORM_ATTR(3, true); T3D_NORM_ATTR(1, false); T3D_NORM_ATTR(3, false);
 #undef T3D_NORM_ATTR
+            T3D_CUDA(cudaFuncSetAttribute(normalize_stats_u16_kernel<1, true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kLutMax * 8 + kStageMax));
+            T3D_CUDA(cudaFuncSetAttribute(normalize_stats_u16_kernel<3, true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kLutMax * 8 + kStageMax));
             nattr = true;
         }
         static const int norm_ctas = [] { const char* e = getenv("T3D_NORM_CTAS"); const int v = e ? atoi(e) : 32; return v < 1 ? 1 : v; }();
         static const bool norm_stage = [] { const char* e = getenv("T3D_NORM_STAGE"); return e ? atoi(e) != 0 : true; }();
         const int nitems = B * kNormBands;
         const int grid = min(nitems, t3d_sm_count() * norm_ctas);
-        const int band_rows = (dst_h + kNormBands - 1) / kNormBands + 1;           // + the row below (gradient statistics)
+        // half-resolution sums too (t3d_preprocess_set_stats_scales(2)) where the shape allows: two rows below the band
+        const bool s2 = grad_stats && g_pre_stats_scales == 2 && norm_s2_supported(dst_h, dst_w);
+        if (s2) T3D_REQUIRE(t3d_aligned16(nsrc), "half-resolution statistics need 16-byte aligned frames");
+        const int band_rows = (dst_h + kNormBands - 1) / kNormBands + (s2 ? 2 : 1);  // + the row(s) below (gradient statistics)
         const size_t stage_bytes = (size_t)band_rows * dst_w * sizeof(uint16_t);
         const bool staged = norm_stage && (dst_w % 8 == 0) && stage_bytes <= (size_t)kStageMax && t3d_aligned16(nsrc);
 #define T3D_NORM_LAUNCH(REP_, ST_) do { \
@@ -902,7 +969,13 @@ int t3d_preprocess_train_u16(const uint16_t* raw, int B, int src_h, int src_w, i
                 nsrc, percentiles, out, dst_h, dst_w, grad_stats, w.lut, w.lutmeta, nitems))); \
             else T3D_LAUNCH("normalize_stats_u16_kernel", st, (normalize_stats_u16_kernel<REP_, ST_, false><<<grid, kNormThreads, kLutMax * 8, st>>>( \
                 nsrc, percentiles, out, dst_h, dst_w, grad_stats, w.lut, w.lutmeta, nitems))); } while (0)
-        if (out_channels == 3) { if (grad_stats) T3D_NORM_LAUNCH(3, true); else T3D_NORM_LAUNCH(3, false); }
+        if (s2) {           // implies staged
+            if (out_channels == 3) T3D_LAUNCH("normalize_stats_u16_kernel", st, (normalize_stats_u16_kernel<3, true, true, true><<<grid, kNormThreads, kLutMax * 8 + stage_bytes, st>>>(
+                nsrc, percentiles, out, dst_h, dst_w, grad_stats, w.lut, w.lutmeta, nitems)));
+            else T3D_LAUNCH("normalize_stats_u16_kernel", st, (normalize_stats_u16_kernel<1, true, true, true><<<grid, kNormThreads, kLutMax * 8 + stage_bytes, st>>>(
+                nsrc, percentiles, out, dst_h, dst_w, grad_stats, w.lut, w.lutmeta, nitems)));
+        }
+        else if (out_channels == 3) { if (grad_stats) T3D_NORM_LAUNCH(3, true); else T3D_NORM_LAUNCH(3, false); }
         else { if (grad_stats) T3D_NORM_LAUNCH(1, true); else T3D_NORM_LAUNCH(1, false); }
 #undef T3D_NORM_LAUNCH
     } else {
@@ -925,6 +998,16 @@ int t3d_preprocess_fallback_count(const void* workspace, int B, int dst_h, int d
 
 static std::atomic<int> g_pre_shared{0};
 int t3d_preprocess_set_shared(int shared) { g_pre_shared.store(shared ? 1 : 0, std::memory_order_relaxed); return T3D_OK; }
+
+int t3d_preprocess_set_stats_scales(int scales) {
+    T3D_REQUIRE(scales == 1 || scales == 2, "scales must be 1 or 2");
+    g_pre_stats_scales = scales;
+    return T3D_OK;
+}
+
+int t3d_preprocess_stats_scales(int dst_h, int dst_w) {
+    return (dst_h >= 1 && dst_w >= 4 && dst_w % 4 == 0) ? (norm_s2_supported(dst_h, dst_w) ? 2 : 1) : 0;
+}
 
 int t3d_preprocess_stats_tiles(int dst_h, int dst_w) {
     return (dst_h >= 1 && dst_w >= 4 && dst_w % 4 == 0) ? kNormBands : 0;

@@ -23,7 +23,7 @@ from . import _lib
 
 OUT_STRIDE = 8  # T3D_LOSS_OUT_STRIDE
 THERMAL_REPLICATED = 0x100  # T3D_THERMAL_REPLICATED
-LOSS_MULTI_SCALE, LOSS_CONF_MIN_ONLY = 0x1, 0x2   # T3D_LOSS_* flags
+LOSS_MULTI_SCALE, LOSS_CONF_MIN_ONLY, LOSS_STATS_TWO_SCALES = 0x1, 0x2, 0x4   # T3D_LOSS_* flags
 # Debug / test mode (T3D_DEBUG_CHECKS=1, set by tests/conftest.py): caller promises are verified on the device --
 # today `thermal_replicated` (a wrong flag would silently change the results).  Costs a pass + a host sync per call.
 DEBUG_CHECKS = os.environ.get("T3D_DEBUG_CHECKS", "0") not in ("", "0")
@@ -47,7 +47,8 @@ def _prep(t: Optional[torch.Tensor], device) -> Optional[torch.Tensor]:
 
 @_lib.on_tensor_device
 def _launch(bwd, p1, p2, g1, g2, c1, c2, t1, t2, need_dconf, alpha, ew, sw, dw, multi, grad_scale,
-            rescale_invalid, out=None, thermal_stats=None, thermal_replicated=False, conf_min_only=False):
+            rescale_invalid, out=None, thermal_stats=None, thermal_replicated=False, conf_min_only=False,
+            thermal_stats_scales=1):
     """Raw call into the C ABI on already-prepared [B,H,W,3] CUDA tensors."""
     lib = _lib.lib()
     B, H, W, _ = p1.shape
@@ -72,7 +73,7 @@ def _launch(bwd, p1, p2, g1, g2, c1, c2, t1, t2, need_dconf, alpha, ew, sw, dw, 
     stream = _lib.current_stream_ptr()
     st1 = st2 = None
     st_tiles = 0
-    if thermal_stats is not None and tch and not multi:
+    if thermal_stats is not None and tch and (not multi or thermal_stats_scales == 2):
         st1, st2 = thermal_stats
         if st1 is not None and st2 is not None:
             if st1.shape != st2.shape or st1.dim() != 3 or st1.shape[0] != B or st1.shape[2] != 4 \
@@ -81,6 +82,8 @@ def _launch(bwd, p1, p2, g1, g2, c1, c2, t1, t2, need_dconf, alpha, ew, sw, dw, 
             st_tiles = int(st1.shape[1])
         else:
             st1 = st2 = None
+    if multi and st1 is not None:
+        flags |= LOSS_STATS_TWO_SCALES     # the statistics carry the half-resolution sums (thermal_stats_scales == 2)
     resampled = tuple(g1.shape[1:3]) != (H, W) or (c1 is not None and tuple(c1.shape[1:3]) != (H, W))
     dp1 = dp2 = dc1 = dc2 = None
     if resampled:
@@ -248,13 +251,15 @@ def fused_thermal_loss_fwd_bwd(pred_pts1, pred_pts2, gt_pts1, gt_pts2, confidenc
                                thermal_img1=None, thermal_img2=None, *, alpha=0.2, edge_weight=0.5,
                                smoothness_weight=0.3, detail_weight=0.3, multi_scale=True,
                                conf_grad=True, out=None, thermal_stats=None, grad_scale=None,
-                               thermal_replicated=False, rescale_invalid=True):
+                               thermal_replicated=False, rescale_invalid=True, thermal_stats_scales=1):
     """Functional (no autograd) fused step on prepared contiguous fp32 CUDA tensors.
 
     Returns dict(per_sample, batch, dpred1, dpred2, dconf1, dconf2); gradients are those of the
     mean over valid samples.  ``out`` may hold preallocated buffers of the same names (+ 'workspace').
     ``thermal_stats`` = (ThermalBatch.grad_stats of view 1, of view 2): the thermal-gradient sums the
-    preprocessing kernel already produced; the loss then skips its own pass over the thermal images.
+    preprocessing kernel already produced; the loss then skips its own pass over the thermal images
+    (``multi_scale``: only if they carry the half-resolution sums too, ``thermal_stats_scales=2`` =
+    ThermalBatch.stats_scales of a batch preprocessed with ``half_res_stats=True``).
     ``grad_scale`` (default 1/B) is the a-priori upstream gradient, e.g. 1/(B * world_size) for the mean
     over a data-parallel global batch.  ``thermal_replicated``: promise that the 3 planes of every thermal
     image are bit-identical (ThermalBatch.replicated; what enhance_thermal_contrast always returns): the
@@ -271,7 +276,7 @@ def fused_thermal_loss_fwd_bwd(pred_pts1, pred_pts2, gt_pts1, gt_pts2, confidenc
         True, pred_pts1, pred_pts2, gt_pts1, gt_pts2, confidences1, confidences2, thermal_img1, thermal_img2,
         need_dconf, float(alpha), float(edge_weight), float(smoothness_weight), float(detail_weight),
         bool(multi_scale), (1.0 / B) if grad_scale is None else float(grad_scale), rescale_invalid=bool(rescale_invalid), out=out,
-        thermal_stats=thermal_stats, thermal_replicated=thermal_replicated)
+        thermal_stats=thermal_stats, thermal_replicated=thermal_replicated, thermal_stats_scales=int(thermal_stats_scales))
     return {"per_sample": ps, "batch": bt, "dpred1": dp1, "dpred2": dp2, "dconf1": dc1, "dconf2": dc2}
 
 

@@ -46,6 +46,7 @@ class HotPathStep:
         self.device = torch.device(device if device is not None else "cuda")
         if self.device.index is None:
             self.device = torch.device("cuda", torch.cuda.current_device())
+        self.multi_scale = bool(multi_scale)
         self.kw = dict(alpha=alpha, edge_weight=edge_weight, smoothness_weight=smoothness_weight,
                        detail_weight=detail_weight, multi_scale=multi_scale)
         self.distributed = distributed
@@ -236,17 +237,22 @@ class HotPathStep:
                 self.s_pre.wait_event(gate)
             if stacked:
                 raw_both = torch.as_strided(raw1, (2 * B,) + tuple(raw1.shape[1:]), raw1.stride(), raw1.storage_offset())
-                tb = _pre.preprocess_thermal_batch(raw_both, size, path="train", out=pre, histogram=self.histogram)
+                tb = _pre.preprocess_thermal_batch(raw_both, size, path="train", out=pre, histogram=self.histogram,
+                                                   half_res_stats=self.multi_scale)
                 gs = tb.grad_stats
+                stats_scales = tb.stats_scales
                 (t1, t2), stats = (tb.thermal[:B], tb.thermal[B:]), ((None, None) if gs is None else (gs[:B], gs[B:]))
             else:
                 if self._pre_halves[i] is None:
                     self._pre_halves[i] = [{k: (v[:B] if h == 0 else v[B:]) if k != "workspace" else
                                             torch.empty(lib.t3d_preprocess_workspace_bytes(B, self.H, self.W), dtype=torch.uint8,
                                                         device=self.device) for k, v in pre.items()} for h in range(2)]
-                a = _pre.preprocess_thermal_batch(raw1, size, path="train", out=self._pre_halves[i][0], histogram=self.histogram)
-                b = _pre.preprocess_thermal_batch(raw2, size, path="train", out=self._pre_halves[i][1], histogram=self.histogram)
+                a = _pre.preprocess_thermal_batch(raw1, size, path="train", out=self._pre_halves[i][0], histogram=self.histogram,
+                                                  half_res_stats=self.multi_scale)
+                b = _pre.preprocess_thermal_batch(raw2, size, path="train", out=self._pre_halves[i][1], histogram=self.histogram,
+                                                  half_res_stats=self.multi_scale)
                 (t1, t2), stats = (a.thermal, b.thermal), (a.grad_stats, b.grad_stats)
+                stats_scales = min(a.stats_scales, b.stats_scales)
             pgrads, n_pgrads = None, 0
             if self.sobel:
                 # the model's input: Sobel-enhanced thermal of both views ([2B,3,H,W], view 1 first); given the
@@ -279,7 +285,7 @@ class HotPathStep:
                     self._main_recorded[i] = True
                 lib.t3d_loss_set_main_done_event(self.ev_main[i].cuda_event)
             _loss.fused_thermal_loss_fwd_bwd(pred1, pred2, gt1, gt2, conf1, conf2, t1, t2,
-                                             out=lo, thermal_stats=stats,
+                                             out=lo, thermal_stats=stats, thermal_stats_scales=stats_scales,
                                              thermal_replicated=True,   # preprocess_thermal_batch wrote 3 identical planes
                                              grad_scale=_dist.global_grad_scale(self.B) if self.distributed else None,
                                              rescale_invalid=False,     # done by the epilogue below

@@ -76,12 +76,13 @@ class ThermalBatch(NamedTuple):
     percentiles: torch.Tensor                  # [B, 2] float64 (p2, p98)
     histogram: Optional[torch.Tensor] = None   # [B, 65536] int32 view of the uint32 counts (train path)
     grad_stats: Optional[torch.Tensor] = None  # [B, tiles, 4] partial sums of |Dx gray|, |Dy gray| (train path)
+    stats_scales: int = 1                      # 2: grad_stats[..., 2:4] hold the half-resolution sums (multi-scale loss)
 
 
 @_lib.on_tensor_device
 def preprocess_thermal_batch(raw_u16: torch.Tensor, img_size=(224, 224), path: str = "train",
                              out_channels: int = 3, out: Optional[dict] = None,
-                             histogram: bool = True) -> ThermalBatch:
+                             histogram: bool = True, half_res_stats: bool = False) -> ThermalBatch:
     """16-bit radiometric frames [B,Hs,Ws] -> normalised thermal [B,3,h,w].
 
     img_size is (W, H) in cv2 order like the reference's --img_size.  path='train':
@@ -89,7 +90,9 @@ def preprocess_thermal_batch(raw_u16: torch.Tensor, img_size=(224, 224), path: s
     path='inference': thermal_dustr_inference.py:25-60 (/65535, float resize).
     histogram=True also returns the exact 65 536-bin histogram of every resized frame (the percentiles are
     read off it); histogram=False computes the same percentiles, bit for bit, from sampled value windows
-    without a per-pixel histogram atomic (about twice as fast; the reference itself never builds a histogram)."""
+    without a per-pixel histogram atomic (about twice as fast; the reference itself never builds a histogram).
+    half_res_stats=True (train path): grad_stats also carries the thermal-gradient sums of the 2x2 average-pooled image
+    the multi-scale loss needs (utils/loss.py:133-174), where the shape allows (ThermalBatch.stats_scales == 2)."""
     x = _to_cuda(raw_u16).contiguous()
     if x.dtype != torch.uint16:
         raise ValueError(f"raw frames must be uint16, got {x.dtype}")
@@ -123,11 +126,19 @@ def preprocess_thermal_batch(raw_u16: torch.Tensor, img_size=(224, 224), path: s
             stats = out.get("grad_stats")
             if stats is None:
                 stats = torch.empty(B, tiles, 4, dtype=torch.float32, device=dev)
-        rc = lib.t3d_preprocess_train_u16(_lib.ptr(x), B, sh, sw, dh, dw, _lib.ptr(thermal), out_channels,
-                                          _lib.ptr(hist), _lib.ptr(pct), _lib.ptr(stats), _lib.ptr(ws), ws.numel(),
-                                          stream)
+        scales = 1
+        if half_res_stats and stats is not None and lib.t3d_preprocess_stats_scales(dh, dw) == 2:
+            scales = 2
+        lib.t3d_preprocess_set_stats_scales(scales)          # thread-local: applies to this thread's next call
+        try:
+            rc = lib.t3d_preprocess_train_u16(_lib.ptr(x), B, sh, sw, dh, dw, _lib.ptr(thermal), out_channels,
+                                              _lib.ptr(hist), _lib.ptr(pct), _lib.ptr(stats), _lib.ptr(ws), ws.numel(),
+                                              stream)
+        finally:
+            if scales != 1:
+                lib.t3d_preprocess_set_stats_scales(1)
         _lib.check(rc, "t3d_preprocess_train_u16")
-        return ThermalBatch(thermal, pct, hist, stats)
+        return ThermalBatch(thermal, pct, hist, stats, scales)
     if path == "inference":
         resized = torch.empty(B, dh, dw, dtype=torch.float32, device=dev)
         rc = lib.t3d_resize_bilinear(_lib.ptr(x), _lib.ptr(resized), 1, B, sh, sw, dh, dw, stream)
