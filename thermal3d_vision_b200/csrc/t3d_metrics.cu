@@ -172,6 +172,25 @@ __global__ void __launch_bounds__(1024, 1) metrics_sample_kernel(const PixelSrc 
     if (tid == 0) { bracket[4 * b + 2 * a] = lo; bracket[4 * b + 2 * a + 1] = hi; }
 }
 
+// The CTA's candidate stage is full (spatially coherent depth: a whole chunk inside the bracket): the thread's
+// candidates of this iteration go to the stage while it lasts, the rest straight to the image's list.  Rare: kept
+// out of line so that the hot loop pays one compare per thread and iteration for it.
+template <int U>
+__device__ __noinline__ void spill_candidates(unsigned int* __restrict__ stage, int slot, unsigned int flags, const unsigned int (&keys)[U],
+                                              int* __restrict__ list_count, int* __restrict__ overflow_flag,
+                                              unsigned int* __restrict__ list) {
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+        if (flags & (1u << u)) {
+            if (slot < kCtaCand) stage[slot] = keys[u];
+            else {
+                const int g = atomicAdd(list_count, 1);
+                if (g < kCandCap) list[g] = keys[u]; else atomicExch(overflow_flag, 1);
+            }
+            ++slot;
+        }
+}
+
 // ------------------------------------------------------------------ X: extract (K5) + count + collect
 // pred element (b, i) lives at pred[(b*n + i) * pred_stride + pred_offset]: stride 3 / offset 2 reads
 // the Z channel of an AoS pointmap in place (depth is never materialised by the caller).
@@ -194,11 +213,6 @@ depth_extract_kernel(const PixelSrc s, int pred_offset, float* __restrict__ vz, 
     if (tid < 2) scount[tid] = 0;
     if (tid < 5) sred[tid] = 0;
     __syncthreads();
-    // the CTA's stage is full (spatially coherent depth: a whole chunk inside the bracket): append straight to the list
-    auto spill = [&](int s, unsigned int key) {
-        const int g = atomicAdd(&counters[8 * b + 6 + s], 1);
-        if (g < kCandCap) cand[((size_t)b * 2 + s) * kCandCap + g] = key; else atomicExch(&counters[8 * b + 3], 1);
-    };
     int nv = 0, pnan = 0, gnan = 0, lt_g = 0, lt_p = 0;
     const int per = (n + gridDim.x - 1) / gridDim.x;
     const int i_begin = blockIdx.x * per, i_end = min(i_begin + per, n);
@@ -234,13 +248,17 @@ depth_extract_kernel(const PixelSrc s, int pred_offset, float* __restrict__ vz, 
         }
         if (fg) {                       // one shared-memory atomic per thread with candidates (~1 in 4)
             int slot = atomicAdd(&scount[0], __popc(fg));
+            if (slot + U <= kCtaCand) {
 #pragma unroll
-            for (int u = 0; u < U; ++u) if (fg & (1u << u)) { if (slot < kCtaCand) scand[0][slot] = kgs[u]; else spill(0, kgs[u]); ++slot; }
+                for (int u = 0; u < U; ++u) if (fg & (1u << u)) scand[0][slot++] = kgs[u];
+            } else spill_candidates<U>(scand[0], slot, fg, kgs, &counters[8 * b + 6], &counters[8 * b + 3], cand + ((size_t)b * 2) * kCandCap);
         }
         if (fp) {
             int slot = atomicAdd(&scount[1], __popc(fp));
+            if (slot + U <= kCtaCand) {
 #pragma unroll
-            for (int u = 0; u < U; ++u) if (fp & (1u << u)) { if (slot < kCtaCand) scand[1][slot] = kps[u]; else spill(1, kps[u]); ++slot; }
+                for (int u = 0; u < U; ++u) if (fp & (1u << u)) scand[1][slot++] = kps[u];
+            } else spill_candidates<U>(scand[1], slot, fp, kps, &counters[8 * b + 7], &counters[8 * b + 3], cand + ((size_t)b * 2 + 1) * kCandCap);
         }
     }
     nv = __reduce_add_sync(0xffffffffu, nv); pnan = __reduce_add_sync(0xffffffffu, pnan);
@@ -307,11 +325,6 @@ depth_extract_fast_kernel(const float* __restrict__ pred, const float* __restric
     if (tid < 2) scount[tid] = 0;
     if (tid < 5) sred[tid] = 0;
     __syncthreads();
-    // the CTA's stage is full (spatially coherent depth: a whole chunk inside the bracket): append straight to the list
-    auto spill = [&](int s, unsigned int key) {
-        const int g = atomicAdd(&counters[8 * b + 6 + s], 1);
-        if (g < kCandCap) cand[((size_t)b * 2 + s) * kCandCap + g] = key; else atomicExch(&counters[8 * b + 3], 1);
-    };
     int nv = 0, pnan = 0, lt_g = 0, lt_p = 0;
     const int nq = n >> 2, per = (nq + gridDim.x - 1) / gridDim.x;
     const int q_begin = blockIdx.x * per, q_end = min(q_begin + per, nq);
@@ -352,13 +365,17 @@ depth_extract_fast_kernel(const float* __restrict__ pred, const float* __restric
         if (PSTRIDE == 3) stg_f4_l2hint(oz + 4 * (size_t)q, z, keep);      // planar: the caller's array IS the Z plane
         if (fg) {                       // one shared-memory atomic per thread with candidates
             int slot = atomicAdd(&scount[0], __popc(fg));
+            if (slot + 4 <= kCtaCand) {
 #pragma unroll
-            for (int u = 0; u < 4; ++u) if (fg & (1u << u)) { if (slot < kCtaCand) scand[0][slot] = kgs[u]; else spill(0, kgs[u]); ++slot; }
+                for (int u = 0; u < 4; ++u) if (fg & (1u << u)) scand[0][slot++] = kgs[u];
+            } else spill_candidates<4>(scand[0], slot, fg, kgs, &counters[8 * b + 6], &counters[8 * b + 3], cand + ((size_t)b * 2) * kCandCap);
         }
         if (fp) {
             int slot = atomicAdd(&scount[1], __popc(fp));
+            if (slot + 4 <= kCtaCand) {
 #pragma unroll
-            for (int u = 0; u < 4; ++u) if (fp & (1u << u)) { if (slot < kCtaCand) scand[1][slot] = kps[u]; else spill(1, kps[u]); ++slot; }
+                for (int u = 0; u < 4; ++u) if (fp & (1u << u)) scand[1][slot++] = kps[u];
+            } else spill_candidates<4>(scand[1], slot, fp, kps, &counters[8 * b + 7], &counters[8 * b + 3], cand + ((size_t)b * 2 + 1) * kCandCap);
         }
     }
     nv = __reduce_add_sync(0xffffffffu, nv); pnan = __reduce_add_sync(0xffffffffu, pnan);
