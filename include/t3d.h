@@ -237,6 +237,11 @@ size_t t3d_preprocess_workspace_bytes(int B, int dst_h, int dst_w);
 int t3d_preprocess_train_u16(const uint16_t* raw, int B, int src_h, int src_w, int dst_h, int dst_w,
                              float* out, int out_channels, unsigned int* hist, double* percentiles,
                              float* grad_stats, void* workspace, size_t workspace_bytes, void* stream);
+/* The same call in phases (hist == NULL only; see T3D_PHASE_* at t3d_depth_metrics_phase): T3D_PHASE_SAMPLE launches
+ * only the window-sampling kernel (its outputs stay in `workspace`), T3D_PHASE_REST everything after it. */
+int t3d_preprocess_train_u16_phase(const uint16_t* raw, int B, int src_h, int src_w, int dst_h, int dst_w,
+                                   float* out, int out_channels, unsigned int* hist, double* percentiles,
+                                   float* grad_stats, void* workspace, size_t workspace_bytes, int phase, void* stream);
 /* Number of statistic partials per frame written to grad_stats (0: not available for this shape). */
 int t3d_preprocess_stats_tiles(int dst_h, int dst_w);
 /* Half-resolution statistics for the multi-scale loss (utils/loss.py:133-174).  t3d_preprocess_set_stats_scales(2)
@@ -302,6 +307,23 @@ int t3d_depth_metrics(const float* pred, int pred_stride, int pred_offset,
                       int B, int H, int W, int median_scaling,
                       float* out, double* out_f64, float* out_medians,
                       void* workspace, size_t workspace_bytes, void* stream);
+
+/* The two side chains in phases (extensions for pipeline.HotPathStep): T3D_PHASE_SAMPLE launches only the chain's
+ * sampling kernel (the value windows / brackets the streaming passes classify against), as a thin CTA shape that fits
+ * beside other kernels; T3D_PHASE_REST everything after it.  A caller that knows step i+1's inputs while step i is still
+ * running samples them ahead of time, off the step's critical path; results are identical to T3D_PHASE_ALL.
+ * `state` (t3d_depth_metrics_state_bytes(B) bytes, 16-byte aligned, nullable): where the sampling pass leaves its
+ * outputs (brackets, zeroed counters) -- per step, so that the big scratch in `workspace` can be shared by steps in
+ * flight; NULL = inside `workspace`.  Both phases of a step take the same workspace / state. */
+#define T3D_PHASE_ALL 0
+#define T3D_PHASE_SAMPLE 1
+#define T3D_PHASE_REST 2
+size_t t3d_depth_metrics_state_bytes(int B);
+int t3d_depth_metrics_phase(const float* pred, int pred_stride, int pred_offset,
+                            const float* gt, int gt_h, int gt_w, const unsigned char* mask,
+                            int B, int H, int W, int median_scaling,
+                            float* out, double* out_f64, float* out_medians,
+                            void* workspace, size_t workspace_bytes, void* state, int phase, void* stream);
 
 /* Dataset accumulator of utils/metrics.py:128-136 (evaluate_thermal_depth): state[0..6] += the finite
  * per-image metrics of metrics_f64 [B][8] (t3d_depth_metrics' out_f64), state[7] += B (non-finite values are

@@ -363,3 +363,45 @@ def test_sobel_parameter_gradients_ride_the_exchange(cuda_device):
     _lib.check(lib.t3d_mailbox_reduce(_lib.ptr(mailbox), 2, 0, _lib.ptr(out), None, None, None, None, None, 0, 0, 0, st), "t3d_mailbox_reduce")
     assert torch.equal(out, parts[0][1] + parts[1][1])
     assert out[16].item() == want_e and out[17].item() == want_t and out[6].item() == 2 * B
+
+
+def test_chain_phases_equal_the_whole_call(cuda_device):
+    """T3D_PHASE_SAMPLE (thin sampling kernels, launched ahead of time by the pipelined step) followed by T3D_PHASE_REST
+    gives the bits of the one-call form: same samples, same windows / brackets, same everything after."""
+    from oracle import ref_preprocess
+    from thermal3d_vision_b200 import _lib, metrics as tm, preprocessing as pp
+    lib = _lib.lib()
+    B, H, W = 6, 96, 160
+    g = torch.Generator().manual_seed(5)
+    pm = (torch.rand(B, H, W, 3, generator=g) * 5 + 0.3).to(cuda_device)
+    gt = (torch.rand(B, H, W, generator=g) * 5).to(cuda_device)
+    gt[1, :7] = 0.0
+    pm[2, 3, 4, 2] = float("nan")
+    a = tm.compute_depth_metrics_batch(pm, gt)
+    out = {"state": torch.empty(lib.t3d_depth_metrics_state_bytes(B), dtype=torch.uint8, device=cuda_device),
+           "workspace": torch.empty(lib.t3d_depth_metrics_workspace_bytes(B, H, W), dtype=torch.uint8, device=cuda_device)}
+    assert tm.compute_depth_metrics_batch(pm, gt, out=out, phase=tm.PHASE_SAMPLE) is None
+    b = tm.compute_depth_metrics_batch(pm, gt, out=out, phase=tm.PHASE_REST)
+    assert torch.equal(a["metrics_f64"].view(torch.int64), b["metrics_f64"].view(torch.int64))
+    assert torch.equal(a["medians"].view(torch.int32), b["medians"].view(torch.int32))
+    # without a state block the sampling outputs live in the workspace
+    out2 = {"workspace": out["workspace"]}
+    tm.compute_depth_metrics_batch(pm, gt, out=out2, phase=tm.PHASE_SAMPLE)
+    c = tm.compute_depth_metrics_batch(pm, gt, out=out2, phase=tm.PHASE_REST)
+    assert torch.equal(a["metrics_f64"].view(torch.int64), c["metrics_f64"].view(torch.int64))
+
+    raw = torch.from_numpy(ref_preprocess.make_raw_frames(4, seed=8)).to(cuda_device)
+    for size in ((512, 384), (224, 224), (640, 512)):
+        w, h = size
+        ref = pp.preprocess_thermal_batch(raw, size, path="train", histogram=False)
+        o = {"workspace": torch.empty(lib.t3d_preprocess_workspace_bytes(4, h, w), dtype=torch.uint8, device=cuda_device),
+             "thermal": torch.empty(4, 3, h, w, device=cuda_device), "percentiles": torch.empty(4, 2, dtype=torch.float64, device=cuda_device),
+             "grad_stats": torch.empty_like(ref.grad_stats) if ref.grad_stats is not None else None}
+        pp.preprocess_thermal_batch(raw, size, path="train", histogram=False, out=o, phase=1)
+        got = pp.preprocess_thermal_batch(raw, size, path="train", histogram=False, out=o, phase=2)
+        assert torch.equal(ref.percentiles, got.percentiles), size
+        assert torch.equal(ref.thermal, got.thermal), size
+        if ref.grad_stats is not None:
+            assert torch.equal(ref.grad_stats, got.grad_stats), size
+    with pytest.raises(_lib.T3DError, match="phases"):
+        pp.preprocess_thermal_batch(raw, (224, 224), path="train", histogram=True, phase=1)

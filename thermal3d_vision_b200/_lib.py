@@ -54,6 +54,8 @@ _SIGNATURES = {
     "t3d_preprocess_workspace_bytes": (C.c_size_t, [C.c_int] * 3),
     "t3d_preprocess_train_u16": (C.c_int, [c_ptr] + [C.c_int] * 5 + [c_ptr, C.c_int, c_ptr, c_ptr, c_ptr,
                                                                     c_ptr, C.c_size_t, c_ptr]),
+    "t3d_preprocess_train_u16_phase": (C.c_int, [c_ptr] + [C.c_int] * 5 + [c_ptr, C.c_int, c_ptr, c_ptr, c_ptr,
+                                                                          c_ptr, C.c_size_t, C.c_int, c_ptr]),
     "t3d_preprocess_stats_tiles": (C.c_int, [C.c_int, C.c_int]),
     "t3d_preprocess_set_stats_scales": (C.c_int, [C.c_int]),
     "t3d_preprocess_stats_scales": (C.c_int, [C.c_int, C.c_int]),
@@ -67,6 +69,9 @@ _SIGNATURES = {
     "t3d_depth_metrics_workspace_bytes": (C.c_size_t, [C.c_int] * 3),
     "t3d_depth_metrics": (C.c_int, [c_ptr, C.c_int, C.c_int, c_ptr, C.c_int, C.c_int, c_ptr]
                           + [C.c_int] * 4 + [c_ptr] * 3 + [c_ptr, C.c_size_t, c_ptr]),
+    "t3d_depth_metrics_state_bytes": (C.c_size_t, [C.c_int]),
+    "t3d_depth_metrics_phase": (C.c_int, [c_ptr, C.c_int, C.c_int, c_ptr, C.c_int, C.c_int, c_ptr]
+                                + [C.c_int] * 4 + [c_ptr] * 3 + [c_ptr, C.c_size_t, c_ptr, C.c_int, c_ptr]),
     "t3d_metrics_accumulate": (C.c_int, [c_ptr, C.c_int, c_ptr, c_ptr]),
     "t3d_pointmap_to_depth": (C.c_int, [c_ptr, c_ptr, C.c_size_t, c_ptr]),
     "t3d_estimate_focal": (C.c_int, [c_ptr, c_ptr, C.c_int, C.c_int, C.c_int, c_ptr, c_ptr]),

@@ -85,8 +85,11 @@ __device__ __forceinline__ void read_pixel(const PixelSrc& s, const float* __res
 }
 
 // ------------------------------------------------------------------ S: sample + bracket
-// grid (2, B): blockIdx.x = stream (0 = gt, 1 = pred)
-__global__ void __launch_bounds__(1024, 1) metrics_sample_kernel(const PixelSrc s, int pred_offset,
+// grid (2, B): blockIdx.x = stream (0 = gt, 1 = pred).  THREADS = 1024: one CTA fills an SM and is done after one
+// exposed memory latency (the chain is waiting for it); THREADS = 256: the thin form for sampling AHEAD of time
+// (T3D_PHASE_SAMPLE), few enough registers to run beside any other kernel, four latencies.  Same samples, same brackets.
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS, THREADS == 1024 ? 1 : 4) metrics_sample_kernel(const PixelSrc s, int pred_offset,
                                                                  unsigned int* __restrict__ bracket,
                                                                  int* __restrict__ counters) {
     __shared__ unsigned int key[kSample];
@@ -103,33 +106,36 @@ __global__ void __launch_bounds__(1024, 1) metrics_sample_kernel(const PixelSrc 
     // n >= kSample: 1024 evenly strided quads of 4 consecutive pixels (they share their cache lines: a
     // quarter of the scattered DRAM reads); smaller images: every pixel exactly once.
     // All of a thread's samples are loaded before the first one is used: ONE exposed DRAM latency.
-    constexpr int kQ = kSample / 1024;
-    float gvs[kQ], pvs[kQ]; unsigned char mks[kQ];
+    constexpr int kQ = 4, kRounds = kSample / (kQ * THREADS);        // kQ loads of gt and pred in flight per thread and round
+#pragma unroll 1
+    for (int round = 0; round < kRounds; ++round) {
+        float gvs[kQ], pvs[kQ]; unsigned char mks[kQ];
 #pragma unroll
-    for (int q = 0; q < kQ; ++q) {
-        const int k = q * 1024 + tid;
-        const int i0 = (n >= kSample) ? 4 * (int)(((long long)(k >> 2) * (n >> 2)) / (kSample >> 2)) + (k & 3) : k;
-        const int i = min(i0, n - 1);
-        size_t gi = (size_t)i;
-        if (s.resample) {   // cv2 INTER_NEAREST (utils/evaluate_depth_metrics.py:321-323), as read_pixel
-            const int y = i / s.W, x = i - y * s.W;
-            const int sx = min((int)floor(__dmul_rn((double)x, s.fx)), s.gt_w - 1);
-            const int sy = min((int)floor(__dmul_rn((double)y, s.fy)), s.gt_h - 1);
-            gi = (size_t)sy * s.gt_w + sx;
+        for (int q = 0; q < kQ; ++q) {
+            const int k = (round * kQ + q) * THREADS + tid;
+            const int i0 = (n >= kSample) ? 4 * (int)(((long long)(k >> 2) * (n >> 2)) / (kSample >> 2)) + (k & 3) : k;
+            const int i = min(i0, n - 1);
+            size_t gi = (size_t)i;
+            if (s.resample) {   // cv2 INTER_NEAREST (utils/evaluate_depth_metrics.py:321-323), as read_pixel
+                const int y = i / s.W, x = i - y * s.W;
+                const int sx = min((int)floor(__dmul_rn((double)x, s.fx)), s.gt_w - 1);
+                const int sy = min((int)floor(__dmul_rn((double)y, s.fy)), s.gt_h - 1);
+                gi = (size_t)sy * s.gt_w + sx;
+            }
+            gvs[q] = __ldg(g + gi);
+            pvs[q] = __ldg(p + (size_t)i * s.pred_stride);
+            mks[q] = m ? m[i] : (unsigned char)1;
         }
-        gvs[q] = __ldg(g + gi);
-        pvs[q] = __ldg(p + (size_t)i * s.pred_stride);
-        mks[q] = m ? m[i] : (unsigned char)1;
-    }
 #pragma unroll
-    for (int q = 0; q < kQ; ++q) {
-        const int k = q * 1024 + tid;
-        const int i0 = (n >= kSample) ? 4 * (int)(((long long)(k >> 2) * (n >> 2)) / (kSample >> 2)) + (k & 3) : k;
-        const bool ok = (i0 < n) && (m ? (mks[q] != 0) : (gvs[q] > 0.f && isfinite(gvs[q])));     // utils/metrics.py:27
-        const float v = (a == 0) ? gvs[q] : pvs[q];
-        unsigned int kk = 0xffffffffu;                             // sentinel: not part of the sample
-        if (ok && !isnan(v)) { kk = t3d_select::float_key(v); ++c; }
-        key[k] = kk;
+        for (int q = 0; q < kQ; ++q) {
+            const int k = (round * kQ + q) * THREADS + tid;
+            const int i0 = (n >= kSample) ? 4 * (int)(((long long)(k >> 2) * (n >> 2)) / (kSample >> 2)) + (k & 3) : k;
+            const bool ok = (i0 < n) && (m ? (mks[q] != 0) : (gvs[q] > 0.f && isfinite(gvs[q])));     // utils/metrics.py:27
+            const float v = (a == 0) ? gvs[q] : pvs[q];
+            unsigned int kk = 0xffffffffu;                             // sentinel: not part of the sample
+            if (ok && !isnan(v)) { kk = t3d_select::float_key(v); ++c; }
+            key[k] = kk;
+        }
     }
     c = __reduce_add_sync(0xffffffffu, c);
     if ((tid & 31) == 0) atomicAdd(&cnt, c);
@@ -145,29 +151,25 @@ __global__ void __launch_bounds__(1024, 1) metrics_sample_kernel(const PixelSrc 
         const int mid = mm / 2, rl = mid - d, rh = mid + d;
         const bool need_lo = rl > 0, need_hi = rh < mm - 1;
         lo = 0u; hi = 0xfffffffeu;
-        unsigned int kq[kQ];
-#pragma unroll
-        for (int q = 0; q < kQ; ++q) kq[q] = key[q * 1024 + tid];
-        for (int i = tid; i < t3d_select::kBins; i += 1024) { sm.hist[i] = 0u; sm2.hist[i] = 0u; }
+        for (int i = tid; i < t3d_select::kBins; i += THREADS) { sm.hist[i] = 0u; sm2.hist[i] = 0u; }
         __syncthreads();
-#pragma unroll
-        for (int q = 0; q < kQ; ++q) if (kq[q] != 0xffffffffu) atomicAdd(&sm.hist[kq[q] >> 21], 1u);
+        for (int i = tid; i < kSample; i += THREADS) { const unsigned int kq = key[i]; if (kq != 0xffffffffu) atomicAdd(&sm.hist[kq >> 21], 1u); }
         __syncthreads();
         unsigned int b_lo = 0u, r_lo = 0u, b_hi = 0u, r_hi = 0u;
-        if (need_lo) { t3d_select::pick_bin(sm, (unsigned)rl, 2048); b_lo = sm.sel_bin; r_lo = sm.sel_rank; __syncthreads(); }
-        if (need_hi) { t3d_select::pick_bin(sm, (unsigned)rh, 2048); b_hi = sm.sel_bin; r_hi = sm.sel_rank; __syncthreads(); }
-        for (int i = tid; i < t3d_select::kBins; i += 1024) sm.hist[i] = 0u;
+        if (need_lo) { t3d_select::pick_bin_t<THREADS>(sm, (unsigned)rl, 2048); b_lo = sm.sel_bin; r_lo = sm.sel_rank; __syncthreads(); }
+        if (need_hi) { t3d_select::pick_bin_t<THREADS>(sm, (unsigned)rh, 2048); b_hi = sm.sel_bin; r_hi = sm.sel_rank; __syncthreads(); }
+        for (int i = tid; i < t3d_select::kBins; i += THREADS) sm.hist[i] = 0u;
         __syncthreads();
-#pragma unroll
-        for (int q = 0; q < kQ; ++q) {
-            if (kq[q] == 0xffffffffu) continue;
-            const unsigned int top = kq[q] >> 21, nxt = (kq[q] >> 10) & 2047u;
+        for (int i = tid; i < kSample; i += THREADS) {
+            const unsigned int kq = key[i];
+            if (kq == 0xffffffffu) continue;
+            const unsigned int top = kq >> 21, nxt = (kq >> 10) & 2047u;
             if (need_lo && top == b_lo) atomicAdd(&sm.hist[nxt], 1u);
             if (need_hi && top == b_hi) atomicAdd(&sm2.hist[nxt], 1u);
         }
         __syncthreads();
-        if (need_lo) { t3d_select::pick_bin(sm, r_lo, 2048); lo = (b_lo << 21) | (sm.sel_bin << 10); __syncthreads(); }
-        if (need_hi) { t3d_select::pick_bin(sm2, r_hi, 2048); hi = (b_hi << 21) | (sm2.sel_bin << 10) | 0x3ffu; hi = min(hi, 0xfffffffeu); }
+        if (need_lo) { t3d_select::pick_bin_t<THREADS>(sm, r_lo, 2048); lo = (b_lo << 21) | (sm.sel_bin << 10); __syncthreads(); }
+        if (need_hi) { t3d_select::pick_bin_t<THREADS>(sm2, r_hi, 2048); hi = (b_hi << 21) | (sm2.sel_bin << 10) | 0x3ffu; hi = min(hi, 0xfffffffeu); }
     }
     if (tid == 0) { bracket[4 * b + 2 * a] = lo; bracket[4 * b + 2 * a + 1] = hi; }
 }
@@ -782,18 +784,38 @@ size_t t3d_depth_metrics_workspace_bytes(int B, int H, int W) {
     return metrics_ws(nullptr, B, H * W, chunks_for(H * W)).total;
 }
 
+size_t t3d_depth_metrics_state_bytes(int B) {
+    if (B < 1) return 0;
+    return (size_t)B * 12 * sizeof(int);          // [B][8] counters, [B][4] bracket keys
+}
+
 int t3d_depth_metrics(const float* pred, int pred_stride, int pred_offset,
                       const float* gt, int gt_h, int gt_w, const unsigned char* mask,
                       int B, int H, int W, int median_scaling,
                       float* out, double* out_f64, float* out_medians,
                       void* workspace, size_t workspace_bytes, void* stream) {
-    T3D_REQUIRE(pred && gt && out && workspace, "NULL pointer");
+    return t3d_depth_metrics_phase(pred, pred_stride, pred_offset, gt, gt_h, gt_w, mask, B, H, W, median_scaling,
+                                   out, out_f64, out_medians, workspace, workspace_bytes, nullptr, T3D_PHASE_ALL, stream);
+}
+
+int t3d_depth_metrics_phase(const float* pred, int pred_stride, int pred_offset,
+                            const float* gt, int gt_h, int gt_w, const unsigned char* mask,
+                            int B, int H, int W, int median_scaling,
+                            float* out, double* out_f64, float* out_medians,
+                            void* workspace, size_t workspace_bytes, void* state, int phase, void* stream) {
+    T3D_REQUIRE(phase == T3D_PHASE_ALL || phase == T3D_PHASE_SAMPLE || phase == T3D_PHASE_REST, "bad phase %d", phase);
+    T3D_REQUIRE(pred && gt && (out || phase == T3D_PHASE_SAMPLE) && workspace, "NULL pointer");
     T3D_REQUIRE(B >= 1 && H >= 1 && W >= 1 && gt_h >= 1 && gt_w >= 1, "bad dims");
     T3D_REQUIRE(pred_stride >= 1 && pred_offset >= 0 && pred_offset < pred_stride, "bad pred stride/offset");
     T3D_REQUIRE((double)H * W < 1.0e9, "image too large");
     const int n = H * W, chunks = chunks_for(n);
     MetricsWs w = metrics_ws(workspace, B, n, chunks);
     if (workspace_bytes < w.total) { t3d_set_error("workspace too small"); return T3D_ERR_WORKSPACE; }
+    if (state) {        // the sampling pass's outputs live in the caller's per-step state instead of the (shared) workspace
+        T3D_REQUIRE(t3d_aligned16(state), "state must be 16-byte aligned");
+        w.counters = reinterpret_cast<int*>(state);
+        w.bracket = reinterpret_cast<unsigned int*>(state) + (size_t)B * 8;
+    }
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     PixelSrc src;
     src.pred = pred; src.gt = gt; src.mask = mask; src.pred_stride = pred_stride;
@@ -807,11 +829,16 @@ int t3d_depth_metrics(const float* pred, int pred_stride, int pred_offset,
                                       kCandCap * (int)sizeof(unsigned int)));
         attr_set = true;
     }
-    if (median_scaling)
-        T3D_LAUNCH("metrics_sample_kernel", st, metrics_sample_kernel<<<dim3(2, B), 1024, 0, st>>>(src, pred_offset, w.bracket, w.counters));
-    else {
-        T3D_CUDA(cudaMemsetAsync(w.counters, 0, (size_t)B * 8 * sizeof(int), st));
-        T3D_CUDA(cudaMemsetAsync(w.bracket, 0xff, (size_t)B * 4 * sizeof(unsigned int), st));   // empty brackets
+    if (phase != T3D_PHASE_REST) {
+        if (median_scaling && phase == T3D_PHASE_SAMPLE)      // ahead of time, beside other kernels: the thin form
+            T3D_LAUNCH("metrics_sample_kernel", st, metrics_sample_kernel<256><<<dim3(2, B), 256, 0, st>>>(src, pred_offset, w.bracket, w.counters));
+        else if (median_scaling)
+            T3D_LAUNCH("metrics_sample_kernel", st, metrics_sample_kernel<1024><<<dim3(2, B), 1024, 0, st>>>(src, pred_offset, w.bracket, w.counters));
+        else {
+            T3D_CUDA(cudaMemsetAsync(w.counters, 0, (size_t)B * 8 * sizeof(int), st));
+            T3D_CUDA(cudaMemsetAsync(w.bracket, 0xff, (size_t)B * 4 * sizeof(unsigned int), st));   // empty brackets
+        }
+        if (phase == T3D_PHASE_SAMPLE) return T3D_OK;
     }
     const bool fast_x = !mask && (W % 4 == 0) && t3d_aligned16(pred) && t3d_aligned16(gt) &&
                         (!src.resample || H + W <= kResampleMaxDim) && (src.resample || (gt_h * gt_w) % 4 == 0) &&

@@ -887,6 +887,15 @@ size_t t3d_preprocess_workspace_bytes(int B, int dst_h, int dst_w) {
 int t3d_preprocess_train_u16(const uint16_t* raw, int B, int src_h, int src_w, int dst_h, int dst_w,
                              float* out, int out_channels, unsigned int* hist, double* percentiles,
                              float* grad_stats, void* workspace, size_t workspace_bytes, void* stream) {
+    return t3d_preprocess_train_u16_phase(raw, B, src_h, src_w, dst_h, dst_w, out, out_channels, hist, percentiles,
+                                          grad_stats, workspace, workspace_bytes, T3D_PHASE_ALL, stream);
+}
+
+int t3d_preprocess_train_u16_phase(const uint16_t* raw, int B, int src_h, int src_w, int dst_h, int dst_w,
+                                   float* out, int out_channels, unsigned int* hist, double* percentiles,
+                                   float* grad_stats, void* workspace, size_t workspace_bytes, int phase, void* stream) {
+    T3D_REQUIRE(phase == T3D_PHASE_ALL || phase == T3D_PHASE_SAMPLE || phase == T3D_PHASE_REST, "bad phase %d", phase);
+    T3D_REQUIRE(phase == T3D_PHASE_ALL || hist == nullptr, "phases are a feature of the sampled-window path (hist == NULL)");
     T3D_REQUIRE(raw && out && percentiles && workspace, "NULL pointer");
     T3D_REQUIRE(B >= 1 && src_h >= 1 && src_w >= 1 && dst_h >= 1 && dst_w >= 1, "bad dims");
     T3D_REQUIRE(out_channels == 1 || out_channels == 3, "out_channels must be 1 or 3");
@@ -906,7 +915,8 @@ int t3d_preprocess_train_u16(const uint16_t* raw, int B, int src_h, int src_w, i
     const int rep3 = (out_channels == 3);
     if (hist == nullptr) {
         // percentiles from sampled value windows: no per-pixel histogram atomic (t3d_preprocess_bracket.cu)
-        if (int rc = t3d_launch_bracket_percentiles(raw, B, src_h, src_w, dst_h, dst_w, same, w, rep3, percentiles, st)) return rc;
+        if (int rc = t3d_launch_bracket_percentiles(raw, B, src_h, src_w, dst_h, dst_w, same, w, rep3, percentiles, st, phase)) return rc;
+        if (phase == T3D_PHASE_SAMPLE) return T3D_OK;
     } else {
         // exact 65 536-bin histogram (an output) -> percentiles
         if (!same) {

@@ -134,7 +134,11 @@ __device__ __forceinline__ void select16_x4(Select16& sm, int n, const unsigned 
 // bracket[b] = {lo2, hi2, lo98, hi98}: window A = [lo2, hi2] around the p2 ranks, window B = [lo98, hi98] around
 // the p98 ranks.  When the two would touch or overlap (nearly constant frames) they are merged into A and B is
 // empty (lo98 = 65536), so a pixel is in at most one window.  CTA 0 also publishes the resize tap tables.
-__global__ void __launch_bounds__(1024, 1)
+// THREADS = 1024: one CTA fills an SM and is done after one exposed memory latency (the chain is waiting for it);
+// THREADS = 256: the thin form for sampling AHEAD of time (T3D_PHASE_SAMPLE): few enough registers to run beside any
+// other kernel, four latencies.  Same samples, same windows.
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS, THREADS == 1024 ? 1 : 4)
 bracket_sample_kernel(const uint16_t* __restrict__ src, int sh, int sw, int dh, int dw, int same,
                       unsigned int* __restrict__ bracket, uint2* __restrict__ gxt, uint4* __restrict__ gyt,
                       unsigned int* __restrict__ brhist, int B) {
@@ -144,59 +148,62 @@ bracket_sample_kernel(const uint16_t* __restrict__ src, int sh, int sw, int dh, 
     const int n = dh * dw, m = min(n, kSamp);
     const double scx = (double)sw / (double)dw, scy = (double)sh / (double)dh;
     if (!same && b == 0) {
-        for (int i = tid; i < max(dw, dh); i += 1024) {
+        for (int i = tid; i < max(dw, dh); i += THREADS) {
             if (i < dw) { const Tap t = linear_tap(i, sw, scx); gxt[i] = make_uint2((unsigned)t.s0 | ((unsigned)t.s1 << 16), __float_as_uint(t.c1)); }
             if (i < dh) { const Tap t = linear_tap(i, sh, scy); gyt[i] = make_uint4((unsigned)t.s0, (unsigned)t.s1, __float_as_uint(t.c0), __float_as_uint(t.c1)); }
         }
     }
     // zero this frame's windowed histograms (and, CTA 0, the fallback counter) for the classification pass
-    for (int i = tid; i < 2 * kBrStride; i += 1024) brhist[(size_t)b * 2 * kBrStride + i] = 0u;
+    for (int i = tid; i < 2 * kBrStride; i += THREADS) brhist[(size_t)b * 2 * kBrStride + i] = 0u;
     if (b == 0 && tid == 0) brhist[(size_t)B * 2 * kBrStride] = 0u;
     const uint16_t* s = src + (size_t)b * sh * sw;
     // 1024 jittered-stride locations x 4 consecutive pixels: the 4 pixels share their source cache lines
     // (a quarter of the scattered DRAM reads of 4096 single pixels); a plain stride would alias with
     // column-periodic images.  Neighbours are correlated, hence the wider (9 sigma) windows below.
-    // All taps of a thread's samples are loaded before the first one is used: ONE exposed DRAM latency.
-    constexpr int kQ = kSamp / 1024;
-    Tap ty[kQ], tx[kQ];
-    unsigned int raw[kQ][4];
+    // All taps of a round's samples are loaded before the first one is used: ONE exposed DRAM latency per round.
+    constexpr int kQ = 4, kRounds = kSamp / (kQ * THREADS);
+#pragma unroll 1
+    for (int round = 0; round < kRounds; ++round) {
+        Tap ty[kQ], tx[kQ];
+        unsigned int raw[kQ][4];
 #pragma unroll
-    for (int q = 0; q < kQ; ++q) {
-        const int k = min(q * 1024 + tid, m - 1);
-        int i = k;
-        if (n > kSamp) {
-            const int l = k >> 2, qstride = (n >> 2) / (kSamp >> 2);
-            i = 4 * (l * qstride + (int)((((unsigned)l * 2654435761u) >> 8) % (unsigned)qstride)) + (k & 3);
+        for (int q = 0; q < kQ; ++q) {
+            const int k = min((round * kQ + q) * THREADS + tid, m - 1);
+            int i = k;
+            if (n > kSamp) {
+                const int l = k >> 2, qstride = (n >> 2) / (kSamp >> 2);
+                i = 4 * (l * qstride + (int)((((unsigned)l * 2654435761u) >> 8) % (unsigned)qstride)) + (k & 3);
+            }
+            if (same) {
+                raw[q][0] = __ldg(s + i);
+            } else {
+                const int y = i / dw, x = i - y * dw;
+                ty[q] = linear_tap(y, sh, scy); tx[q] = linear_tap(x, sw, scx);
+                const uint16_t* r0 = s + (size_t)ty[q].s0 * sw;
+                const uint16_t* r1 = s + (size_t)ty[q].s1 * sw;
+                raw[q][0] = __ldg(r0 + tx[q].s0); raw[q][1] = __ldg(r0 + tx[q].s1);
+                raw[q][2] = __ldg(r1 + tx[q].s0); raw[q][3] = __ldg(r1 + tx[q].s1);
+            }
         }
-        if (same) {
-            raw[q][0] = __ldg(s + i);
-        } else {
-            const int y = i / dw, x = i - y * dw;
-            ty[q] = linear_tap(y, sh, scy); tx[q] = linear_tap(x, sw, scx);
-            const uint16_t* r0 = s + (size_t)ty[q].s0 * sw;
-            const uint16_t* r1 = s + (size_t)ty[q].s1 * sw;
-            raw[q][0] = __ldg(r0 + tx[q].s0); raw[q][1] = __ldg(r0 + tx[q].s1);
-            raw[q][2] = __ldg(r1 + tx[q].s0); raw[q][3] = __ldg(r1 + tx[q].s1);
-        }
-    }
-    if (!same) {
-        // make every use depend on every load, or ptxas schedules the first conversion (and its stall) between
-        // the loads of consecutive samples; raw values are u16, so the fold can never equal the constant
-        unsigned int fold = 0u;
+        if (!same) {
+            // make every use depend on every load, or ptxas schedules the first conversion (and its stall) between
+            // the loads of consecutive samples; raw values are u16, so the fold can never equal the constant
+            unsigned int fold = 0u;
 #pragma unroll
-        for (int q = 0; q < kQ; ++q) fold |= raw[q][0] | raw[q][1] | raw[q][2] | raw[q][3];
-        if (fold == 0xffffffffu) raw[0][0] = 0u;
-    }
-#pragma unroll
-    for (int q = 0; q < kQ; ++q) {
-        const int k = q * 1024 + tid;
-        unsigned int v = raw[q][0];
-        if (!same) {                                         // bilinear_u16 on the loaded taps
-            const float h0 = __fadd_rn(__fmul_rn((float)raw[q][0], tx[q].c0), __fmul_rn((float)raw[q][1], tx[q].c1));
-            const float h1 = __fadd_rn(__fmul_rn((float)raw[q][2], tx[q].c0), __fmul_rn((float)raw[q][3], tx[q].c1));
-            v = sat_u16(__fadd_rn(__fmul_rn(h0, ty[q].c0), __fmul_rn(h1, ty[q].c1)));
+            for (int q = 0; q < kQ; ++q) fold |= raw[q][0] | raw[q][1] | raw[q][2] | raw[q][3];
+            if (fold == 0xffffffffu) raw[0][0] = 0u;
         }
-        if (k < m) key[k] = (short)v;                        // bit pattern of the u16
+#pragma unroll
+        for (int q = 0; q < kQ; ++q) {
+            const int k = (round * kQ + q) * THREADS + tid;
+            unsigned int v = raw[q][0];
+            if (!same) {                                         // bilinear_u16 on the loaded taps
+                const float h0 = __fadd_rn(__fmul_rn((float)raw[q][0], tx[q].c0), __fmul_rn((float)raw[q][1], tx[q].c1));
+                const float h1 = __fadd_rn(__fmul_rn((float)raw[q][2], tx[q].c0), __fmul_rn((float)raw[q][3], tx[q].c1));
+                v = sat_u16(__fadd_rn(__fmul_rn(h0, ty[q].c0), __fmul_rn(h1, ty[q].c1)));
+            }
+            if (k < m) key[k] = (short)v;                        // bit pattern of the u16
+        }
     }
     __syncthreads();
     // sample ranks 9 sigma either side of each quantile's rank
@@ -528,10 +535,16 @@ percentile_from_brackets_kernel(const uint16_t* __restrict__ frames, int n, cons
 }  // namespace
 
 int t3d_launch_bracket_percentiles(const uint16_t* raw, int B, int sh, int sw, int dh, int dw, bool same,
-                                   const PreWs& w, int rep3, double* percentiles, cudaStream_t st) {
+                                   const PreWs& w, int rep3, double* percentiles, cudaStream_t st, int phase) {
     const int n = dh * dw;
-    T3D_LAUNCH("bracket_sample_kernel", st, bracket_sample_kernel<<<B, 1024, 0, st>>>(
-        raw, sh, sw, dh, dw, same ? 1 : 0, w.bracket, w.gxt, w.gyt, w.brhist, B));
+    if (phase == T3D_PHASE_SAMPLE) {            // ahead of time, beside other kernels: the thin form
+        T3D_LAUNCH("bracket_sample_kernel", st, bracket_sample_kernel<256><<<B, 256, 0, st>>>(
+            raw, sh, sw, dh, dw, same ? 1 : 0, w.bracket, w.gxt, w.gyt, w.brhist, B));
+        return T3D_OK;
+    }
+    if (phase != T3D_PHASE_REST)
+        T3D_LAUNCH("bracket_sample_kernel", st, bracket_sample_kernel<1024><<<B, 1024, 0, st>>>(
+            raw, sh, sw, dh, dw, same ? 1 : 0, w.bracket, w.gxt, w.gyt, w.brhist, B));
     const bool fast = !same && (dw % 8 == 0) && (sw % 8 == 0) && t3d_aligned16(raw);
     bool launched = false;
     if (fast) {

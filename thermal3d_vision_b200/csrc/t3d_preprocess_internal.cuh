@@ -112,4 +112,4 @@ static inline PreWs pre_ws_layout(void* base, int B, int dh, int dw) {
 // the few percent inside -> exact order statistics, np.percentile lerp, normalisation LUT.
 // `same` : source and destination sizes are equal (no resize; `resized` is not written, the raw frame is used).
 int t3d_launch_bracket_percentiles(const uint16_t* raw, int B, int sh, int sw, int dh, int dw, bool same,
-                                   const PreWs& w, int rep3, double* percentiles, cudaStream_t st);
+                                   const PreWs& w, int rep3, double* percentiles, cudaStream_t st, int phase = 0 /* T3D_PHASE_* */);

@@ -58,6 +58,41 @@ __device__ __forceinline__ void pick_bin(Smem& sm, unsigned int rank, int nb) {
     __syncthreads();
 }
 
+// pick_bin for a CTA of THREADS threads (a power of two, 64 .. 1024): every thread owns kBins / THREADS consecutive bins.
+template <int THREADS>
+__device__ __forceinline__ void pick_bin_t(Smem& sm, unsigned int rank, int nb) {
+    constexpr int PER = kBins / THREADS;
+    const int tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
+    unsigned int h[PER], v = 0u;
+#pragma unroll
+    for (int j = 0; j < PER; ++j) { h[j] = (PER * tid + j < nb) ? sm.hist[PER * tid + j] : 0u; v += h[j]; }
+    unsigned int incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    if (lane == 31) sm.warp_tot[wrp] = incl;
+    __syncthreads();
+    if (wrp == 0) {
+        unsigned int w = (lane < THREADS / 32) ? sm.warp_tot[lane] : 0u, wi = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned int t = __shfl_up_sync(0xffffffffu, wi, o);
+            if (lane >= o) wi += t;
+        }
+        if (lane < THREADS / 32) sm.warp_tot[lane] = wi - w;   // exclusive prefix of warp totals
+    }
+    __syncthreads();
+    unsigned int excl = sm.warp_tot[wrp] + incl - v;           // elements before this thread's first bin
+#pragma unroll
+    for (int j = 0; j < PER; ++j) {
+        if (rank >= excl && rank < excl + h[j]) { sm.sel_bin = PER * tid + j; sm.sel_rank = rank - excl; }
+        excl += h[j];
+    }
+    __syncthreads();
+}
+
 // Exact k-th smallest (0-based rank) among the valid elements produced by
 // `get(idx, &value) -> bool valid` for idx in [0, n).  NaNs must be excluded by
 // `get` (the caller decides what a NaN means).  Requires rank < #valid.

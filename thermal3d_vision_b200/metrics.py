@@ -32,9 +32,17 @@ def _as_cuda(x, dtype=None):
     return x.detach()
 
 
+PHASE_ALL, PHASE_SAMPLE, PHASE_REST = 0, 1, 2      # T3D_PHASE_* (include/t3d.h)
+
+
 @_lib.on_tensor_device
-def compute_depth_metrics_batch(pred, gt_depth, mask=None, median_scaling=True, out: Optional[dict] = None):
+def compute_depth_metrics_batch(pred, gt_depth, mask=None, median_scaling=True, out: Optional[dict] = None,
+                                phase: int = PHASE_ALL):
     """Batched metrics on the device, no host sync.
+
+    phase (pipeline.HotPathStep): PHASE_SAMPLE launches only the bracket-sampling kernel for these inputs (its outputs go
+    to out["state"], t3d_depth_metrics_state_bytes(B) bytes, or into the workspace) and returns None; PHASE_REST the
+    remaining passes of the same inputs on the same workspace / state.
 
     pred: depth maps [B,H,W] or AoS pointmaps [B,H,W,3] (the Z channel is read in place --
     depth is never materialised); gt_depth [B,gh,gw] (nearest-resampled when the size differs);
@@ -82,10 +90,13 @@ def compute_depth_metrics_batch(pred, gt_depth, mask=None, median_scaling=True, 
     med = out.get("medians")
     if med is None:
         med = torch.empty(B, 2, dtype=torch.float32, device=dev)
-    rc = lib.t3d_depth_metrics(_lib.ptr(pred), stride, offset, _lib.ptr(gt), gt.shape[1], gt.shape[2], _lib.ptr(m),
+    state = out.get("state")
+    rc = lib.t3d_depth_metrics_phase(_lib.ptr(pred), stride, offset, _lib.ptr(gt), gt.shape[1], gt.shape[2], _lib.ptr(m),
                                B, H, W, 1 if median_scaling else 0, _lib.ptr(res), _lib.ptr(res64), _lib.ptr(med),
-                               _lib.ptr(ws), ws.numel(), _lib.current_stream_ptr())
-    _lib.check(rc, "t3d_depth_metrics")
+                               _lib.ptr(ws), ws.numel(), _lib.ptr(state), int(phase), _lib.current_stream_ptr())
+    _lib.check(rc, "t3d_depth_metrics_phase")
+    if phase == PHASE_SAMPLE:
+        return None
     return {"metrics": res, "metrics_f64": res64, "medians": med}
 
 

@@ -9,6 +9,7 @@ only owns buffers, streams and the (optional) data-parallel all-reduce.
 """
 from __future__ import annotations
 
+import os
 from typing import Dict, Optional
 
 import torch
@@ -85,7 +86,17 @@ class HotPathStep:
         # on their own stream, only what the loss / the epilogue consume later exists twice.  (One metric workspace
         # also means ONE planar-Z scratch: the extraction pass parks it in the L2 for the sum pass, t3d_metrics.cu.)
         self.met_sets[1]["workspace"] = self.met_sets[0]["workspace"]
-        self.pre_sets[1]["workspace"] = self.pre_sets[0]["workspace"]
+        # Sampling ahead (pipelined steps): the two chains' sampling kernels -- one CTA per image, latency-bound, 30 us
+        # of nearly idle machine at the head of every step -- are launched for step i+1 as soon as its inputs are
+        # known, in their thin form, on streams of their own: they run beside step i's streaming kernels, and at the
+        # gate step i+1 starts with its heavy kernels.  What they write exists per set (the preprocessing workspace;
+        # for the metric chain a small state block -- its big scratch stays shared).
+        self.sample_ahead = self.pipelined and os.environ.get("T3D_SAMPLE_AHEAD", "1") != "0"
+        if self.sample_ahead:
+            for m in self.met_sets:
+                m["state"] = torch.empty(lib.t3d_depth_metrics_state_bytes(B), dtype=torch.uint8, device=dev)
+        else:
+            self.pre_sets[1]["workspace"] = self.pre_sets[0]["workspace"]
         self.loss_out, self.pre_both, self.met_out = self.loss_sets[0], self.pre_sets[0], self.met_sets[0]
         if self.sobel:
             # ThermalDUSt3R's Sobel enhancer in front of the model (thermal_dustr_model.py:110-142): its output is the
@@ -106,6 +117,10 @@ class HotPathStep:
         self.s_loss = torch.cuda.Stream(device=dev, priority=hi_pri)
         self.s_pre = torch.cuda.Stream(device=dev, priority=min(hi_pri + 1, lo_pri))
         self.s_met = torch.cuda.Stream(device=dev, priority=lo_pri)
+        self.s_samp_p = torch.cuda.Stream(device=dev, priority=lo_pri)
+        self.s_samp_m = torch.cuda.Stream(device=dev, priority=lo_pri)
+        self.ev_sp = [torch.cuda.Event() for _ in range(2)]
+        self.ev_sm = [torch.cuda.Event() for _ in range(2)]
         self.ev_ready = [torch.cuda.Event() for _ in range(2)]
         self.ev_pre = [torch.cuda.Event() for _ in range(2)]
         self.ev_met = [torch.cuda.Event() for _ in range(2)]
@@ -225,20 +240,41 @@ class HotPathStep:
         # earlier (their CTAs would take SMs away from that persistent kernel), not later (its second-stage
         # reduction and epilogue, and this step's one-CTA-per-image sampling kernels, then run beside each other)
         gate = self.ev_main[i ^ 1] if (self.pipelined and self._main_recorded[i ^ 1]) else None
+        raw_both = torch.as_strided(raw1, (2 * B,) + tuple(raw1.shape[1:]), raw1.stride(), raw1.storage_offset()) if stacked else None
+        ahead = self.sample_ahead and self.pipelined and stacked and not self.histogram
+        if ahead:
+            # ungated, on their own streams: ordered only after the inputs and after the last user of this set's
+            # sampling state (step - 2: its preprocessing / metric chain)
+            with torch.cuda.stream(self.s_samp_m):
+                self.s_samp_m.wait_event(ready)
+                self.s_samp_m.wait_event(self.ev_met[i])
+                _metrics.compute_depth_metrics_batch(pred1, gt_depth, out=met, phase=_metrics.PHASE_SAMPLE)
+                self.ev_sm[i].record(self.s_samp_m)
+            with torch.cuda.stream(self.s_samp_p):
+                self.s_samp_p.wait_event(ready)
+                self.s_samp_p.wait_event(self.ev_pre[i])
+                _pre.preprocess_thermal_batch(raw_both, size, path="train", out=pre, histogram=False,
+                                              half_res_stats=self.multi_scale, phase=_metrics.PHASE_SAMPLE)
+                self.ev_sp[i].record(self.s_samp_p)
+        phase = _metrics.PHASE_REST if ahead else _metrics.PHASE_ALL
         with torch.cuda.stream(self.s_met):                 # depth metrics (Z of pred1 read in place)
             self.s_met.wait_event(ready)
             if gate is not None:
                 self.s_met.wait_event(gate)
-            me = _metrics.compute_depth_metrics_batch(pred1, gt_depth, out=met)
+            if ahead:
+                self.s_met.wait_event(self.ev_sm[i])
+            me = _metrics.compute_depth_metrics_batch(pred1, gt_depth, out=met if ahead else {k: v for k, v in met.items() if k != "state"},
+                                                      phase=phase)
             self.ev_met[i].record(self.s_met)
         with torch.cuda.stream(self.s_pre):
             self.s_pre.wait_event(ready)
             if gate is not None:
                 self.s_pre.wait_event(gate)
+            if ahead:
+                self.s_pre.wait_event(self.ev_sp[i])
             if stacked:
-                raw_both = torch.as_strided(raw1, (2 * B,) + tuple(raw1.shape[1:]), raw1.stride(), raw1.storage_offset())
                 tb = _pre.preprocess_thermal_batch(raw_both, size, path="train", out=pre, histogram=self.histogram,
-                                                   half_res_stats=self.multi_scale)
+                                                   half_res_stats=self.multi_scale, phase=phase)
                 gs = tb.grad_stats
                 stats_scales = tb.stats_scales
                 (t1, t2), stats = (tb.thermal[:B], tb.thermal[B:]), ((None, None) if gs is None else (gs[:B], gs[B:]))
