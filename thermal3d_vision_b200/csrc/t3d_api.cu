@@ -44,6 +44,7 @@ struct Prof {
 
 // `pattern`: one substring, or several separated by '|'
 static bool prof_matches(const char* name, const char* pattern) {
+    if (pattern[0] == 0) return true;               // empty pattern: every kernel
     const char* p = pattern;
     for (;;) {
         const char* bar = strchr(p, '|');

@@ -60,7 +60,7 @@ MetricsWs metrics_ws(void* base, int B, int n, int chunks) {
 }
 
 int chunks_for(int n) {
-    static const int px = [] { const char* e = getenv("T3D_METRIC_CHUNK_PX"); const int v = e ? atoi(e) : 8192; return v < 1024 ? 1024 : v; }();
+    static const int px = [] { const char* e = getenv("T3D_METRIC_CHUNK_PX"); const int v = e ? atoi(e) : 12288; return v < 1024 ? 1024 : v; }();
     return max(1, min(96, (n + px - 1) / px));
 }
 
