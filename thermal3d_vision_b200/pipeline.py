@@ -85,7 +85,12 @@ class HotPathStep:
         # scratch that lives inside one chain is shared by the two sets: the chains of consecutive steps run in order
         # on their own stream, only what the loss / the epilogue consume later exists twice.  (One metric workspace
         # also means ONE planar-Z scratch: the extraction pass parks it in the L2 for the sum pass, t3d_metrics.cu.)
-        self.met_sets[1]["workspace"] = self.met_sets[0]["workspace"]
+        # Pipelined: the metric chains of consecutive steps alternate between two streams (and two workspaces), so that
+        # step i+1's extraction pass does not queue behind the tail of step i's sum pass, which the loss kernel held
+        # up (406.2 -> 403.4 us per step); T3D_MET_STREAMS=1 puts them back on one stream with one shared scratch.
+        self.met_two_streams = self.pipelined and os.environ.get("T3D_MET_STREAMS", "2") == "2"
+        if not self.met_two_streams:
+            self.met_sets[1]["workspace"] = self.met_sets[0]["workspace"]
         # Sampling ahead (pipelined steps): the two chains' sampling kernels -- one CTA per image, latency-bound, 30 us
         # of nearly idle machine at the head of every step -- are launched for step i+1 as soon as its inputs are
         # known, in their thin form, on streams of their own: they run beside step i's streaming kernels, and at the
@@ -117,6 +122,7 @@ class HotPathStep:
         self.s_loss = torch.cuda.Stream(device=dev, priority=hi_pri)
         self.s_pre = torch.cuda.Stream(device=dev, priority=min(hi_pri + 1, lo_pri))
         self.s_met = torch.cuda.Stream(device=dev, priority=lo_pri)
+        self.s_met_alt = torch.cuda.Stream(device=dev, priority=lo_pri) if self.met_two_streams else self.s_met
         self.s_samp_p = torch.cuda.Stream(device=dev, priority=lo_pri)
         self.s_samp_m = torch.cuda.Stream(device=dev, priority=lo_pri)
         self.ev_sp = [torch.cuda.Event() for _ in range(2)]
@@ -257,15 +263,16 @@ class HotPathStep:
                                               half_res_stats=self.multi_scale, phase=_metrics.PHASE_SAMPLE)
                 self.ev_sp[i].record(self.s_samp_p)
         phase = _metrics.PHASE_REST if ahead else _metrics.PHASE_ALL
-        with torch.cuda.stream(self.s_met):                 # depth metrics (Z of pred1 read in place)
-            self.s_met.wait_event(ready)
+        s_met = self.s_met_alt if (i & 1) else self.s_met
+        with torch.cuda.stream(s_met):                      # depth metrics (Z of pred1 read in place)
+            s_met.wait_event(ready)
             if gate is not None:
-                self.s_met.wait_event(gate)
+                s_met.wait_event(gate)
             if ahead:
-                self.s_met.wait_event(self.ev_sm[i])
+                s_met.wait_event(self.ev_sm[i])
             me = _metrics.compute_depth_metrics_batch(pred1, gt_depth, out=met if ahead else {k: v for k, v in met.items() if k != "state"},
                                                       phase=phase)
-            self.ev_met[i].record(self.s_met)
+            self.ev_met[i].record(s_met)
         with torch.cuda.stream(self.s_pre):
             self.s_pre.wait_event(ready)
             if gate is not None:
