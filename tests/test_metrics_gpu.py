@@ -237,6 +237,38 @@ def test_eval_step_config5_shape(cuda_device):
         assert got[k7] == pytest.approx(ref[k7], rel=1e-5), k7
 
 
+@pytest.mark.parametrize("what", ["both", "raw_only", "mismatch"])
+def test_eval_step_prefetch_gives_the_same_bits(cuda_device, what):
+    """EvalStep.prefetch (sampling kernels of batch k+1 launched while batch k is in flight) changes when the kernels
+    run, not what they compute: thermal batches and the accumulated metrics equal the plain loop's, also when only the
+    raw frames are sampled ahead and when a prefetch is followed by a different batch."""
+    from oracle import ref_preprocess
+    from thermal3d_vision_b200.pipeline import EvalStep
+    B, H, W, gh, gw, nb = 4, 96, 160, 128, 160, 4
+    rng = np.random.default_rng(9)
+    raws = [torch.from_numpy(ref_preprocess.make_raw_frames(B, seed=40 + k, hw=(120, 200))).to(cuda_device) for k in range(nb)]
+    gts = [torch.from_numpy((1.0 + 2 * np.abs(rng.standard_normal((B, gh, gw)))).astype(np.float32)).to(cuda_device) for _ in range(nb)]
+    pms = [torch.from_numpy((rng.standard_normal((B, H, W, 3)) + 3).astype(np.float32)).to(cuda_device) for _ in range(nb)]
+    plain = EvalStep(B, H, W, raw_hw=(120, 200), gt_hw=(gh, gw), device=cuda_device)
+    want_th = [plain.run_batch(raws[k], pms[k], gts[k]).clone() for k in range(nb)]
+    want = plain.finish()
+    step = EvalStep(B, H, W, raw_hw=(120, 200), gt_hw=(gh, gw), device=cuda_device)
+    order = list(range(nb))
+    def pf(k):
+        if what == "both": step.prefetch(raws[k], pms[k], gts[k])
+        elif what == "raw_only": step.prefetch(raws[k])
+        else: step.prefetch(raws[(k + 2) % nb], pms[(k + 2) % nb], gts[(k + 2) % nb])     # not the batch that follows
+    pf(0)
+    for k in order:
+        if k + 1 < nb:
+            pf(k + 1)
+        th = step.run_batch(raws[k], pms[k], gts[k])
+        assert torch.equal(th, want_th[k]), k
+    got = step.finish()
+    for k7 in K7:
+        assert got[k7] == want[k7] or (np.isnan(got[k7]) and np.isnan(want[k7])), k7
+
+
 @pytest.mark.parametrize("conv", ["tuple_dict_batched", "dict_pred1", "tuple_tensor"])
 def test_evaluate_thermal_depth_matches_reference_run(cuda_device, conv):
     """evaluate_thermal_depth(model, dataloader, device) (utils/metrics.py:72-138) with a fake model and loader

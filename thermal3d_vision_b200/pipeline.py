@@ -522,15 +522,29 @@ class EvalStep:
         self.device = torch.device(device if device is not None else "cuda")
         dev, lib = self.device, _lib.lib()
         f32 = dict(dtype=torch.float32, device=dev)
-        self.pre_out = {"thermal": torch.empty(B, 3, H, W, **f32),
-                        "percentiles": torch.empty(B, 2, dtype=torch.float64, device=dev),
-                        "workspace": torch.empty(lib.t3d_preprocess_workspace_bytes(B, H, W), dtype=torch.uint8, device=dev)}
-        self.met_out = {"workspace": torch.empty(lib.t3d_depth_metrics_workspace_bytes(B, H, W), dtype=torch.uint8, device=dev),
-                        "metrics": torch.empty(B, 8, **f32), "metrics_f64": torch.empty(B, 8, dtype=torch.float64, device=dev),
-                        "medians": torch.empty(B, 2, **f32)}
+        # every buffer twice: batches alternate, so that `prefetch` can sample batch k+1 while batch k is in flight and
+        # the thermal batch a call returns stays valid until the call after the next one
+        self.pre_sets = [{"thermal": torch.empty(B, 3, H, W, **f32),
+                          "percentiles": torch.empty(B, 2, dtype=torch.float64, device=dev),
+                          "workspace": torch.empty(lib.t3d_preprocess_workspace_bytes(B, H, W), dtype=torch.uint8, device=dev)}
+                         for _ in range(2)]
+        self.met_sets = [{"workspace": torch.empty(lib.t3d_depth_metrics_workspace_bytes(B, H, W), dtype=torch.uint8, device=dev),
+                          "state": torch.empty(lib.t3d_depth_metrics_state_bytes(B), dtype=torch.uint8, device=dev),
+                          "metrics": torch.empty(B, 8, **f32), "metrics_f64": torch.empty(B, 8, dtype=torch.float64, device=dev),
+                          "medians": torch.empty(B, 2, **f32)} for _ in range(2)]
+        self.pre_out, self.met_out = self.pre_sets[0], self.met_sets[0]
         self.acc = _metrics.MetricAccumulator(dev)
         self.side = torch.cuda.Stream(device=dev, priority=-1)
+        self.s_samp_p = torch.cuda.Stream(device=dev)
+        self.s_samp_m = torch.cuda.Stream(device=dev)
         self.fork, self.join = torch.cuda.Event(), torch.cuda.Event()
+        self.ev_ready = [torch.cuda.Event() for _ in range(2)]
+        self.ev_sp = [torch.cuda.Event() for _ in range(2)]
+        self.ev_sm = [torch.cuda.Event() for _ in range(2)]
+        self.ev_pre_done = [torch.cuda.Event() for _ in range(2)]
+        self.ev_met_done = [torch.cuda.Event() for _ in range(2)]
+        self._next = 0
+        self._prefetched = []          # [(raw ptr, pointmap ptr or None, set)], oldest first
         lib.t3d_preprocess_set_shared(1)            # the metric pipeline runs beside the preprocessing (run_batch)
 
     def algorithmic_bytes(self) -> int:
@@ -538,17 +552,66 @@ class EvalStep:
         n, raw, gt = self.H * self.W, self.raw_hw[0] * self.raw_hw[1], self.gt_hw[0] * self.gt_hw[1]
         return self.B * ((2 * raw + 12 * n) + (12 * n + 4 * min(gt, n) + 64))
 
+    def prefetch(self, raw, pointmap=None, gt_depth=None):
+        """Sample a FUTURE batch ahead of time (train path): launches only the sampling kernels of the two chains for
+        these tensors, in their thin form and on streams of their own, so that they run beside the streaming kernels
+        of the batch in flight; the `run_batch` call for the same tensors then starts with its heavy kernels.  Call it
+        BEFORE the `run_batch` of the batch in front (what is recorded now is that the inputs are ready now).  In a
+        real evaluation loop the raw frames of batch k+1 are known while the model still works on batch k -- the
+        pointmap is not: pass `pointmap=None` and only the preprocessing is sampled ahead."""
+        if self.path != "train":
+            return
+        with _lib.device_guard(self.device):
+            j = self._next
+            self._next ^= 1
+            main = torch.cuda.current_stream(self.device)
+            self.ev_ready[j].record(main)
+            with torch.cuda.stream(self.s_samp_p):
+                self.s_samp_p.wait_event(self.ev_ready[j])
+                self.s_samp_p.wait_event(self.ev_pre_done[j])          # the last batch on this set is done with it
+                _pre.preprocess_thermal_batch(raw, (self.W, self.H), path="train", out=self.pre_sets[j], histogram=False,
+                                              phase=_metrics.PHASE_SAMPLE)
+                self.ev_sp[j].record(self.s_samp_p)
+            if pointmap is not None:
+                with torch.cuda.stream(self.s_samp_m):
+                    self.s_samp_m.wait_event(self.ev_ready[j])
+                    self.s_samp_m.wait_event(self.ev_met_done[j])
+                    _metrics.compute_depth_metrics_batch(pointmap, gt_depth, out=self.met_sets[j], phase=_metrics.PHASE_SAMPLE)
+                    self.ev_sm[j].record(self.s_samp_m)
+            self._prefetched.append((raw.data_ptr(), pointmap.data_ptr() if pointmap is not None else None, j))
+
     def run_batch(self, raw, pointmap, gt_depth):
         """raw [B,Hs,Ws] uint16, pointmap [B,H,W,3] float32, gt_depth [B,gh,gw] float32, all on the device.
-        Returns the preprocessed thermal batch [B,3,H,W]; the metrics go into the accumulator.  No host sync."""
+        Returns the preprocessed thermal batch [B,3,H,W] (valid until the call after the next one); the metrics go
+        into the accumulator.  No host sync."""
         with _lib.device_guard(self.device):
             main = torch.cuda.current_stream(self.device)
+            pre_phase = met_phase = _metrics.PHASE_ALL
+            if self._prefetched and self._prefetched[0][0] == raw.data_ptr():
+                _, pm_ptr, j = self._prefetched.pop(0)
+                pre_phase = _metrics.PHASE_REST
+                if pm_ptr is not None and pm_ptr == pointmap.data_ptr():
+                    met_phase = _metrics.PHASE_REST
+            else:
+                self._prefetched.clear()                # not what was sampled ahead: start over
+                j = self._next
+                self._next ^= 1
+            pre, met = self.pre_sets[j], self.met_sets[j]
+            self.pre_out, self.met_out = pre, met
             self.fork.record(main)
             with torch.cuda.stream(self.side):
                 self.side.wait_event(self.fork)
-                me = _metrics.compute_depth_metrics_batch(pointmap, gt_depth, out=self.met_out)
+                if met_phase == _metrics.PHASE_REST:
+                    self.side.wait_event(self.ev_sm[j])
+                else:
+                    self.side.wait_event(self.ev_met_done[j])
+                me = _metrics.compute_depth_metrics_batch(pointmap, gt_depth, out=met, phase=met_phase)
                 self.join.record(self.side)
-            tb = _pre.preprocess_thermal_batch(raw, (self.W, self.H), path=self.path, out=self.pre_out, histogram=False)
+                self.ev_met_done[j].record(self.side)
+            if pre_phase == _metrics.PHASE_REST:
+                main.wait_event(self.ev_sp[j])
+            tb = _pre.preprocess_thermal_batch(raw, (self.W, self.H), path=self.path, out=pre, histogram=False, phase=pre_phase)
+            self.ev_pre_done[j].record(main)
             main.wait_event(self.join)
             self.acc.update(me["metrics_f64"])
             return tb.thermal

@@ -17,9 +17,16 @@ for k in range(2):
     pm = d["pred1"].clone()
     pm[..., 2] = torch.nn.functional.interpolate(gt[:, None], size=(H, W), mode="nearest")[:, 0] * 0.7
     pool.append((d["raw1"], pm, gt)); del d
-ms = bench.time_steps(lambda: [step.run_batch(*pool[0]), step.run_batch(*pool[1])], 10, 3) / 2
+ahead = os.environ.get("T3D_EVAL_PREFETCH", "1") != "0"
+def two():
+    if ahead:
+        step.prefetch(*pool[1]); step.run_batch(*pool[0]); step.prefetch(*pool[0]); step.run_batch(*pool[1])
+    else:
+        step.run_batch(*pool[0]); step.run_batch(*pool[1])
+if ahead: step.prefetch(*pool[0])
+ms = bench.time_steps(two, 10, 3) / 2
 print(f"# eval step, batch {B}: {ms * 1e3:.1f} us  ({B / ms / 1e3 * 1e3:.0f} frames/s)")
 _lib.profile_begin("", 256)
-step.run_batch(*pool[0]); torch.cuda.synchronize()
+two(); torch.cuda.synchronize()
 for nm, a, b in sorted(_lib.profile_timeline(), key=lambda r: r[1]): print(f"{a*1e3:9.1f} {b*1e3:9.1f} {(b-a)*1e3:7.1f}  {nm}")
 _lib.profile_end()
