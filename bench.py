@@ -614,7 +614,7 @@ def eval_shard(a, dev, rank, world, local):
     ahead = os.environ.get("T3D_EVAL_PREFETCH", "1") != "0"
 
     def run(k, last):
-        if ahead and not last:
+        if ahead:       # also for the last batch: the timed region then holds exactly `nb` samplings and `nb` batches
             step.prefetch(*pool[(k + 1) % npool])
         step.run_batch(*pool[k % npool])
 
