@@ -314,7 +314,10 @@ int t3d_depth_metrics(const float* pred, int pred_stride, int pred_offset,
  * running samples them ahead of time, off the step's critical path; results are identical to T3D_PHASE_ALL.
  * `state` (t3d_depth_metrics_state_bytes(B) bytes, 16-byte aligned, nullable): where the sampling pass leaves its
  * outputs (brackets, zeroed counters) -- per step, so that the big scratch in `workspace` can be shared by steps in
- * flight; NULL = inside `workspace`.  Both phases of a step take the same workspace / state. */
+ * flight; NULL = inside `workspace`.  Both phases of a step take the same workspace / state, and T3D_PHASE_REST
+ * REQUIRES that T3D_PHASE_SAMPLE ran on them since their last use (it also resets the counters / window histograms
+ * the streaming passes accumulate into).  The sampled windows are hints: if the data changed after it was sampled the
+ * results are still exact (a rank outside its window takes the exact-select fallback), only slower. */
 #define T3D_PHASE_ALL 0
 #define T3D_PHASE_SAMPLE 1
 #define T3D_PHASE_REST 2
