@@ -405,3 +405,36 @@ def test_chain_phases_equal_the_whole_call(cuda_device):
             assert torch.equal(ref.grad_stats, got.grad_stats), size
     with pytest.raises(_lib.T3DError, match="phases"):
         pp.preprocess_thermal_batch(raw, (224, 224), path="train", histogram=True, phase=1)
+
+
+def test_pipelined_soak_without_host_syncs(cuda_device):
+    """60 pipelined steps enqueued back to back (no host synchronisation: the host runs ahead, the sampling kernels of
+    step i+1 run during step i, output sets and metric streams alternate), two different input batches in an irregular
+    order: every step's packed result and a stride of its thermal planes / gradients equal the plain step's bits."""
+    import bench
+    from thermal3d_vision_b200.pipeline import HotPathStep
+    B, H, W = 4, 96, 256
+    sets = [bench.make_inputs_torch(B, H, W, seed, cuda_device, raw_hw=(120, 320)) for seed in (0, 7)]
+    args = [tuple(d[k] for k in bench.KEYS) for d in sets]
+    plain = HotPathStep(B, H, W, raw_hw=(120, 320), device=cuda_device, pipelined=False)
+    want = []
+    for a in args:
+        r = plain.run_device(*a).clone()
+        torch.cuda.synchronize()
+        want.append((r, plain.pre_both["thermal"].clone(), plain.loss_out["dpred2"].clone()))
+    step = HotPathStep(B, H, W, raw_hw=(120, 320), device=cuda_device, pipelined=True)
+    assert step.sample_ahead
+    snaps, prev = [], None
+    for k in range(60):
+        j = (k * 5 // 2) & 1 if k % 3 else k & 1
+        r = step.run_device(*args[j])
+        if prev is not None:            # this call's lazy join ordered the stream after the previous step
+            pj, pr, plo, ppre = prev
+            snaps.append((pj, pr.clone(), ppre["thermal"].clone(), plo["dpred2"].clone()))
+        prev = (j, r, step.loss_out, step.pre_both)
+    step.finish()
+    torch.cuda.synchronize()
+    for n, (jj, rr, th, d2) in enumerate(snaps):
+        assert torch.equal(rr.view(torch.int64), want[jj][0].view(torch.int64)), n
+        assert torch.equal(th, want[jj][1]), n
+        assert torch.equal(d2, want[jj][2]), n
