@@ -344,6 +344,7 @@ __device__ __forceinline__ void resize_march_rows(const uint16_t* __restrict__ s
     }
     const uint32_t lane_ld = ring + 20u * lane;                         // H54: this lane's 10 source pixels inside a slot
     const Windows w = load_windows(bracket, f);
+    const unsigned int mid0b = w.mid0 + 0x4B000000u;                    // is_mid on the magic-biased value
     unsigned int* hA = brhist + (size_t)f * 2 * kBrStride;
     const char* lane_src = reinterpret_cast<const char*>(src + (size_t)f * sh * sw + span0 + 8 * lane);
     const uint32_t lane_dst = ring + 16u * lane;
@@ -423,13 +424,19 @@ __device__ __forceinline__ void resize_march_rows(const uint16_t* __restrict__ s
             } else load_h(hB_);
             tagB = s1;
         }
-        unsigned int v[kRzU];
+        // round-half-even by the magic-number add: the float 2^23 + x has unit ulp, its low mantissa bits ARE the
+        // integer.  A convex combination of u16 values cannot exceed 65535.03 (weights sum to 1 within one ulp, two
+        // roundings of 2^-8 each), so cv2's saturation never binds and the low 16 bits of the float are the pixel:
+        // packed straight out of the bit patterns, classified on the biased value.
+        unsigned int vb[kRzU];
 #pragma unroll
-        for (int u = 0; u < kRzU; ++u) v[u] = round_u16(__fadd_rn(__fmul_rn(hA_[u], cy0), __fmul_rn(hB_[u], cy1)));
+        for (int u = 0; u < kRzU; ++u)
+            vb[u] = __float_as_uint(__fadd_rn(__fadd_rn(__fmul_rn(hA_[u], cy0), __fmul_rn(hB_[u], cy1)), 8388608.0f));
         if (active) {
-            *reinterpret_cast<uint4*>(out) = make_uint4(v[0] | (v[1] << 16), v[2] | (v[3] << 16), v[4] | (v[5] << 16), v[6] | (v[7] << 16));
+            *reinterpret_cast<uint4*>(out) = make_uint4(__byte_perm(vb[0], vb[1], 0x5410), __byte_perm(vb[2], vb[3], 0x5410),
+                                                        __byte_perm(vb[4], vb[5], 0x5410), __byte_perm(vb[6], vb[7], 0x5410));
 #pragma unroll
-            for (int u = 0; u < kRzU; ++u) if (!is_mid(v[u], w)) count_edge(v[u], w, hA);
+            for (int u = 0; u < kRzU; ++u) if ((vb[u] - mid0b) >= w.midw) count_edge(vb[u] - 0x4B000000u, w, hA);
         }
     }
     cp_async_wait<0>();
