@@ -97,6 +97,7 @@ class HotPathStep:
         # gate step i+1 starts with its heavy kernels.  What they write exists per set (the preprocessing workspace;
         # for the metric chain a small state block -- its big scratch stays shared).
         self.sample_ahead = self.pipelined and os.environ.get("T3D_SAMPLE_AHEAD", "1") != "0"
+        self._primed = False
         if self.sample_ahead:
             for m in self.met_sets:
                 m["state"] = torch.empty(lib.t3d_depth_metrics_state_bytes(B), dtype=torch.uint8, device=dev)
@@ -247,7 +248,10 @@ class HotPathStep:
         # reduction and epilogue, and this step's one-CTA-per-image sampling kernels, then run beside each other)
         gate = self.ev_main[i ^ 1] if (self.pipelined and self._main_recorded[i ^ 1]) else None
         raw_both = torch.as_strided(raw1, (2 * B,) + tuple(raw1.shape[1:]), raw1.stride(), raw1.storage_offset()) if stacked else None
-        ahead = self.sample_ahead and self.pipelined and stacked and not self.histogram
+        # (the first step after finish() has no step in flight to hide its sampling behind: it takes the one-call
+        # form with the 1 024-thread sampling kernels, which are faster when they have the machine to themselves)
+        ahead = self.sample_ahead and self.pipelined and stacked and not self.histogram and self._primed
+        self._primed = True
         if ahead:
             # ungated, on their own streams: ordered only after the inputs and after the last user of this set's
             # sampling state (step - 2: its preprocessing / metric chain)
@@ -450,6 +454,7 @@ class HotPathStep:
     def finish(self):
         """Order the current stream after every outstanding step / reduction (end of a run / of a timed region)."""
         self.wait_result()
+        self._primed = False        # nothing in flight any more: the next step samples inside its own chains
 
     # ------------------------------------------------------------------ host-buffer step (e2e)
     def run_host(self, host: Dict[str, torch.Tensor]):
