@@ -32,9 +32,13 @@ class HotPathStep:
     alternate, so consecutive steps may overlap: with ``pipelined=True`` the caller's stream is NOT ordered after the
     step by `run_device` itself but lazily (by the next call, after that call has forked its own work, or by
     `wait_result()` / `finish()`), which lets the preprocessing and metric kernels of step i + 1 fill the machine
-    while the tail of step i (the loss kernel's last work items, its second-stage reduction, the epilogue) drains,
-    and hides the one-CTA-per-image sampling kernels that would otherwise run alone at the head of every step.
-    Every step still does all of its work on its own inputs.  With ``pipelined=False`` (default) the caller's stream
+    while the tail of step i (the loss kernel's last work items, its second-stage reduction, the epilogue) drains.
+    Pipelined steps also SAMPLE AHEAD: the one-CTA-per-image sampling kernels at the head of both side chains (value
+    windows for the percentiles, brackets for the medians) are launched for step i + 1 -- from its `run_device` call,
+    on two more streams, in a thin 256-thread form -- while step i's streaming kernels run, so that step i + 1 starts
+    with its heavy kernels when step i's loss kernel ends; the metric chains of consecutive steps alternate between
+    two streams.  The first step after `finish()` has nothing in flight and samples inside its own chains.
+    Every step still does all of its work on its own inputs; results are bit-identical to the plain step's.  With ``pipelined=False`` (default) the caller's stream
     waits for the step before `run_device` returns: plain stream semantics.  `loss_out`, `pre_both`, `met_out` and
     `result` always name the set of the latest call.
     """
