@@ -74,9 +74,11 @@ __device__ __forceinline__ float rcp_fast(float x) { float y; asm("rcp.approx.ft
 __device__ __forceinline__ void metric_terms_nodiv(float g, float q, float accf[3], float& accl2, int cnt[3]) {
     const float a = fmaxf(g, q), b = fminf(g, q);
     const float c = 5.9604644775390625e-08f;                                 // 2^-24
-    cnt[0] += (fmaf(c, b, fmaf(-1.25f, b, a)) < 0.f) ? 1 : 0;                // :52
-    cnt[1] += (fmaf(c, b, fmaf(-1.5625f, b, a)) < 0.f) ? 1 : 0;              // :53
-    cnt[2] += (fmaf(c, b, fmaf(-1.953125f, b, a)) < 0.f) ? 1 : 0;            // :54
+    // a, b are positive normal numbers here, so the sum is finite and never -0: "< 0" is its sign bit (one shift-add
+    // instead of compare + select + add)
+    cnt[0] += (int)(__float_as_uint(fmaf(c, b, fmaf(-1.25f, b, a))) >> 31);        // :52
+    cnt[1] += (int)(__float_as_uint(fmaf(c, b, fmaf(-1.5625f, b, a))) >> 31);      // :53
+    cnt[2] += (int)(__float_as_uint(fmaf(c, b, fmaf(-1.953125f, b, a))) >> 31);    // :54
     const float rg = rcp_fast(g);
     float u = q * rg;
     u = fmaf(fmaf(-u, g, q), rg, u);                                         // Newton: u = q / g to ~1 ulp
