@@ -307,6 +307,7 @@ depth_extract_fast_kernel(const float* __restrict__ pred, const float* __restric
                           int H, int W, int gt_h, int gt_w) {
     __shared__ unsigned int scand[2][kCtaCand];
     __shared__ int scount[2], sbase[2], sred[5];
+    __shared__ unsigned int scount2;                              // slot counters of both streams: gt low half, pred high half
     __shared__ int stab[RESAMPLE ? kResampleMaxDim : 1];          // cv2 INTER_NEAREST source column (W) / row offset (H)
     const int b = blockIdx.y, tid = threadIdx.x, lane = tid & 31;
     if (RESAMPLE) {     // utils/evaluate_depth_metrics.py:321-323: sx = min(floor(x * gw / W), gw - 1), same for rows
@@ -325,11 +326,13 @@ depth_extract_fast_kernel(const float* __restrict__ pred, const float* __restric
     const unsigned int lo_g = br.x, w_g = br.y - br.x, lo_p = br.z, w_p = br.w - br.z;       // lo > hi (no bracket): w wraps,
     const bool has_g = br.y >= br.x, has_p = br.w >= br.z;                                    // masked by has_*
     if (tid < 2) scount[tid] = 0;
+    if (tid == 2) scount2 = 0u;
     if (tid < 5) sred[tid] = 0;
     __syncthreads();
     int nv = 0, pnan = 0, lt_g = 0, lt_p = 0;
     const int nq = n >> 2, per = (nq + gridDim.x - 1) / gridDim.x;
     const int q_begin = blockIdx.x * per, q_end = min(q_begin + per, nq);
+    const bool packed = per < 16384;                      // < 65 536 pixels per CTA: two 16-bit slot counters in one word
     for (int q = q_begin + tid; q < q_end; q += kChunkThreads) {
         float4 g;
         if (RESAMPLE) {                                   // W % 4 == 0: the quad lies in one row
@@ -365,21 +368,34 @@ depth_extract_fast_kernel(const float* __restrict__ pred, const float* __restric
             fp |= (unsigned)(okp && has_p && (kps[u] - lo_p) <= w_p) << u;
         }
         if (PSTRIDE == 3) stg_f4_l2hint(oz + 4 * (size_t)q, z, keep);      // planar: the caller's array IS the Z plane
-        if (fg) {                       // one shared-memory atomic per thread with candidates
-            int slot = atomicAdd(&scount[0], __popc(fg));
-            if (slot + 4 <= kCtaCand) {
+        if (fg | fp) {                  // ONE shared-memory atomic per thread with candidates: both streams' slot counters in
+            // one word (16 bits each when the CTA sees < 65 536 pixels, else two atomics) -- the compiler aggregates the
+            // atomic over the warp with a shuffle scan, which costs as much as the rest of the iteration when done twice
+            unsigned int old;
+            if (packed) old = atomicAdd(&scount2, (unsigned)__popc(fg) | ((unsigned)__popc(fp) << 16));
+            else {
+                const unsigned int og = fg ? (unsigned)atomicAdd(&scount[0], __popc(fg)) : 0u;
+                const unsigned int op = fp ? (unsigned)atomicAdd(&scount[1], __popc(fp)) : 0u;
+                old = min(og, 0xffffu) | (min(op, 0xffffu) << 16);        // >= kCtaCand either way: spills
+            }
+            if (fg) {
+                int slot = (int)(old & 0xffffu);
+                if (slot + 4 <= kCtaCand) {
 #pragma unroll
-                for (int u = 0; u < 4; ++u) if (fg & (1u << u)) scand[0][slot++] = kgs[u];
-            } else spill_candidates<4>(scand[0], slot, fg, kgs, &counters[8 * b + 6], &counters[8 * b + 3], cand + ((size_t)b * 2) * kCandCap);
-        }
-        if (fp) {
-            int slot = atomicAdd(&scount[1], __popc(fp));
-            if (slot + 4 <= kCtaCand) {
+                    for (int u = 0; u < 4; ++u) if (fg & (1u << u)) scand[0][slot++] = kgs[u];
+                } else spill_candidates<4>(scand[0], slot, fg, kgs, &counters[8 * b + 6], &counters[8 * b + 3], cand + ((size_t)b * 2) * kCandCap);
+            }
+            if (fp) {
+                int slot = (int)(old >> 16);
+                if (slot + 4 <= kCtaCand) {
 #pragma unroll
-                for (int u = 0; u < 4; ++u) if (fp & (1u << u)) scand[1][slot++] = kps[u];
-            } else spill_candidates<4>(scand[1], slot, fp, kps, &counters[8 * b + 7], &counters[8 * b + 3], cand + ((size_t)b * 2 + 1) * kCandCap);
+                    for (int u = 0; u < 4; ++u) if (fp & (1u << u)) scand[1][slot++] = kps[u];
+                } else spill_candidates<4>(scand[1], slot, fp, kps, &counters[8 * b + 7], &counters[8 * b + 3], cand + ((size_t)b * 2 + 1) * kCandCap);
+            }
         }
     }
+    __syncthreads();
+    if (packed && tid < 2) scount[tid] = (int)((scount2 >> (16 * tid)) & 0xffffu);
     nv = __reduce_add_sync(0xffffffffu, nv); pnan = __reduce_add_sync(0xffffffffu, pnan);
     lt_g = __reduce_add_sync(0xffffffffu, lt_g); lt_p = __reduce_add_sync(0xffffffffu, lt_p);
     int* c = counters + 8 * b;
