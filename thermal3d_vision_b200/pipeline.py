@@ -610,15 +610,12 @@ class EvalStep:
             self.fork.record(main)
             with torch.cuda.stream(self.side):
                 self.side.wait_event(self.fork)
-                if met_phase == _metrics.PHASE_REST:
-                    self.side.wait_event(self.ev_sm[j])
-                else:
-                    self.side.wait_event(self.ev_met_done[j])
+                self.side.wait_event(self.ev_sm[j])          # this batch's sampling -- or a stale one on this set: let it finish
+                self.side.wait_event(self.ev_met_done[j])
                 me = _metrics.compute_depth_metrics_batch(pointmap, gt_depth, out=met, phase=met_phase)
                 self.join.record(self.side)
                 self.ev_met_done[j].record(self.side)
-            if pre_phase == _metrics.PHASE_REST:
-                main.wait_event(self.ev_sp[j])
+            main.wait_event(self.ev_sp[j])                   # likewise for the preprocessing's sampling state
             tb = _pre.preprocess_thermal_batch(raw, (self.W, self.H), path=self.path, out=pre, histogram=False, phase=pre_phase)
             self.ev_pre_done[j].record(main)
             main.wait_event(self.join)
