@@ -795,7 +795,9 @@ int launch_w(const MarchArgs& a, cudaStream_t st) {
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set = true;
     }
-    const int grid = t3d_sm_count();
+    // T3D_MARCH_CTAS (tuning knob): fewer persistent CTAs than SMs leave whole SMs to other streams' kernels
+    static const int env_ctas = [] { const char* e = getenv("T3D_MARCH_CTAS"); return e ? atoi(e) : 0; }();
+    const int grid = (env_ctas > 0 && env_ctas < t3d_sm_count()) ? env_ctas : t3d_sm_count();
     T3D_LAUNCH("loss_march_kernel", st,
                loss_march_kernel<TCH, REP, BWD, S2, NS, WARPS><<<grid, WARPS * 32, smem, st>>>(a));
     return T3D_OK;
